@@ -1,0 +1,531 @@
+"""CPU oracle for the scoring-and-loss + full-catalog top-k hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is product code: only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may
+import it, and only as the checker / reported baseline.  The product path
+(``xfmr_rec_b200``) never imports this module and fails loudly without its CUDA
+library.
+
+This is a numpy restatement (float64 arithmetic unless stated) of the reference
+algorithm.  Every function cites the reference file:line it follows (paths are
+relative to the upstream repository root).
+
+Pinning status
+--------------
+* losses / logits statistics: PINNED — checked against the reference's own
+  ``xfmr_rec/losses.py`` executed in the build container; the vectors it
+  produced are committed under ``tests/golden/losses_*.npz`` together with the
+  generating script ``tests/golden/make_golden.py``.
+* candidate construction (``compute_embeds``): restated from
+  ``xfmr_rec/models.py:388-419`` (module not importable: sentence_transformers
+  absent); pinned only through torch's ``nn.Embedding`` semantics in the golden
+  script.
+* exact retrieval: the reference's search is an approximate ANN index in
+  un-vendored third-party code (lancedb 0.37.1 / faiss-cpu 1.15.0); the oracle
+  is the exact computation those indexes approximate — parity unpinned (and
+  unpinnable) against the reference's own results.
+* retrieval metrics: torchmetrics 1.9.0 is absent here; formulas restated from
+  its documented behaviour — parity unpinned.
+"""
+
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+LOSS_NAMES = [
+    "AlignmentLoss",
+    "AlignmentContrastiveLoss",
+    "ContrastiveLoss",
+    "InfoNCELoss",
+    "NCELoss",
+    "PairwiseHingeLoss",
+    "PairwiseLogisticLoss",
+]  # order = xfmr_rec/losses.py:546-554
+COSINE_LOSSES = {"AlignmentLoss", "AlignmentContrastiveLoss", "ContrastiveLoss"}
+
+
+class Config:
+    """Plain stand-in for ``LossConfig`` (xfmr_rec/losses.py:11-30)."""
+
+    def __init__(
+        self,
+        target_position="first",
+        mask_false_negatives=True,
+        num_hard_negatives=0,
+        scale=1.0,
+        margin=0.5,
+    ):
+        self.target_position = target_position
+        self.mask_false_negatives = mask_false_negatives
+        self.num_hard_negatives = num_hard_negatives
+        self.scale = scale
+        self.margin = margin
+
+
+# ---------------------------------------------------------------------------
+# bf16 helpers (round-to-nearest-even, as torch's .bfloat16())
+# ---------------------------------------------------------------------------
+def round_bf16(x: np.ndarray) -> np.ndarray:
+    """Round float32 values to the nearest bf16 (ties to even), return float32."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    u = x.view(np.uint32).astype(np.uint64)
+    nan = np.isnan(x)
+    rounded = ((u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000).astype(np.uint32)
+    out = rounded.view(np.float32).copy()
+    out[nan] = np.nan
+    return out.reshape(x.shape)
+
+
+# ---------------------------------------------------------------------------
+# candidate construction — xfmr_rec/models.py:388-419
+# ---------------------------------------------------------------------------
+def gather_rows(table: np.ndarray, idx: np.ndarray) -> np.ndarray:
+    """``nn.Embedding.forward`` (models.py:336-338, 400, 406): bit-exact row copy."""
+    return table[idx]
+
+
+def attention_mask_from_embeds(embeds: np.ndarray) -> np.ndarray:
+    """models.py:343 — ``(input_embeds != 0).any(-1)``."""
+    return (embeds != 0).any(-1)
+
+
+def compute_embeds(table, token_embeddings, history_idx, pos_idx, neg_idx, *, dense=True,
+                   is_normalized=False):
+    """Restatement of ``RecommenderModel.compute_embeds`` (models.py:388-419).
+
+    ``token_embeddings`` (B, L, D) stands in for the encoder output
+    (models.py:345).  With ``dense=False`` the O(M^2 D) candidate tensor of
+    models.py:408-416 is not materialised; the positives and the shared
+    negative pool that define it are returned instead.
+    """
+    input_embeds = gather_rows(table, history_idx)  # models.py:336-338
+    attention_mask = attention_mask_from_embeds(input_embeds)  # models.py:343, 390
+    query = token_embeddings[attention_mask]  # models.py:392
+    if is_normalized:  # models.py:394-395 (torch normalize, eps 1e-12)
+        nrm = np.maximum(np.linalg.norm(query, axis=-1, keepdims=True), 1e-12)
+        query = query / nrm
+    pos_sel = pos_idx[attention_mask]  # models.py:398
+    pos_embed = gather_rows(table, pos_sel)  # models.py:400
+    neg_sel = neg_idx[attention_mask]  # models.py:404
+    neg_embed = gather_rows(table, neg_sel)  # models.py:406
+    pos_mask = pos_sel != 0  # models.py:413
+    out = {
+        "query_embed": query[pos_mask],  # models.py:415
+        "attention_mask": attention_mask,
+        "positive_mask": pos_mask,
+        "pos_embed": pos_embed[pos_mask],
+        "neg_embed": neg_embed,
+    }
+    if dense:
+        m_a = pos_embed.shape[0]
+        cand = np.concatenate(
+            [pos_embed[:, None, :], np.broadcast_to(neg_embed[None], (m_a,) + neg_embed.shape)],
+            axis=1,
+        )  # models.py:408-410
+        out["candidate_embed"] = cand[pos_mask]  # models.py:416
+    return out
+
+
+# ---------------------------------------------------------------------------
+# logits — xfmr_rec/losses.py:179-209
+# ---------------------------------------------------------------------------
+def dot_logits(query, cand):
+    """losses.py:195 — l[i,j] = q_i . c_ij ; ``cand`` is (M,C,D)."""
+    return np.einsum("md,mcd->mc", np.asarray(query, np.float64), np.asarray(cand, np.float64))
+
+
+def cosine_logits(query, cand, eps=1e-8):
+    """losses.py:206-208 — torch cosine_similarity: each norm clamped to eps."""
+    q = np.asarray(query, np.float64)
+    c = np.asarray(cand, np.float64)
+    qn = q / np.maximum(np.linalg.norm(q, axis=-1, keepdims=True), eps)
+    cn = c / np.maximum(np.linalg.norm(c, axis=-1, keepdims=True), eps)
+    return np.einsum("md,mcd->mc", qn, cn)
+
+
+def lean_logits(query, pos, neg, *, cosine=False, eps=1e-8):
+    """[rowdot(q,pos) | Q.Neg^T] — equal to the dense logits of models.py:408-416 +
+    losses.py:195/206 for the shared-pool candidate tensor."""
+    q = np.asarray(query, np.float64)
+    p = np.asarray(pos, np.float64)
+    n = np.asarray(neg, np.float64)
+    if cosine:
+        q = q / np.maximum(np.linalg.norm(q, axis=-1, keepdims=True), eps)
+        p = p / np.maximum(np.linalg.norm(p, axis=-1, keepdims=True), eps)
+        n = n / np.maximum(np.linalg.norm(n, axis=-1, keepdims=True), eps)
+    return np.concatenate([(q * p).sum(-1, keepdims=True), q @ n.T], axis=1)
+
+
+# ---------------------------------------------------------------------------
+# EmbedLoss pipeline — xfmr_rec/losses.py:211-330
+# ---------------------------------------------------------------------------
+def check_target(n_rows, cfg, target=None):
+    """losses.py:233-261."""
+    assert target is not None or cfg.target_position is not None
+    assert target is None or cfg.target_position is None
+    if cfg.target_position is None:
+        pass
+    elif cfg.target_position == "first":
+        target = np.zeros(n_rows, dtype=np.int64)
+    elif cfg.target_position == "diagonal":
+        target = np.arange(n_rows, dtype=np.int64)
+    else:
+        raise ValueError(f"invalid {cfg.target_position = }")
+    target = np.asarray(target)
+    assert target.ndim == 1 and target.shape[0] == n_rows
+    return target.astype(np.int64)
+
+
+def mask_false_negatives(logits, target, cfg):
+    """losses.py:283-292 — strict ``<`` against the target logit."""
+    m, c = logits.shape
+    if not cfg.mask_false_negatives:
+        mask = np.ones((m, c), dtype=bool)
+        mask[np.arange(m), target] = False
+        return mask
+    t = logits[np.arange(m), target][:, None]
+    return logits < t
+
+
+def mine_hard_negatives(logits, mask, cfg):
+    """losses.py:311-330.  ``topk(sorted=False)`` leaves the choice among tied
+    logits implementation-defined; the oracle (and the CUDA path) prefer the
+    lower candidate index."""
+    k = cfg.num_hard_negatives
+    if k <= 0 or k >= logits.shape[1]:
+        return mask
+    masked = np.where(mask, logits, -np.inf)
+    order = np.argsort(-masked, axis=1, kind="stable")[:, :k]
+    sel = np.zeros_like(mask)
+    np.put_along_axis(sel, order, True, axis=1)
+    return mask & sel
+
+
+def _weighted_mean_rows(values, weights):
+    """losses.py:110-111 with dim=1."""
+    w = weights.astype(np.float64)
+    den = w.sum(axis=1, keepdims=True) + 1e-9
+    return (values * w / den).sum(axis=1)
+
+
+def _softplus(x):
+    return np.logaddexp(0.0, x)
+
+
+def _sigmoid(x):
+    return 0.5 * (1.0 + np.tanh(0.5 * x))
+
+
+def loss_from_logits(name, logits, target, mask, cfg, *, with_grad=False):
+    """The seven ``loss()`` bodies (losses.py:420-543) on given logits.
+
+    Returns the scalar loss (sum over rows) and, if asked, dL/dlogits.
+    """
+    l = np.asarray(logits, np.float64)
+    m, c = l.shape
+    rows = np.arange(m)
+    t = l[rows, target]
+    g = np.zeros_like(l)
+    w = mask.astype(np.float64)
+    cnt = w.sum(axis=1) + 1e-9
+    if name == "AlignmentLoss":  # losses.py:352-353
+        loss = (1.0 - t).sum()
+        g[rows, target] = -1.0
+    elif name in ("ContrastiveLoss", "AlignmentContrastiveLoss"):  # losses.py:370-372
+        x = l - 1.0 + cfg.margin
+        loss = _weighted_mean_rows(np.maximum(x, 0.0), mask).sum()
+        g = (x > 0) * w / cnt[:, None]
+        if name == "AlignmentContrastiveLoss":  # losses.py:445-447
+            loss = loss + (1.0 - t).sum()
+            g[rows, target] += -1.0
+    elif name == "InfoNCELoss":  # losses.py:483-488
+        keep = mask.copy()
+        keep[rows, target] = True
+        z = np.where(keep, l, -np.inf) * cfg.scale
+        # -inf * negative scale would flip sign in torch too; reference multiplies after where
+        zmax = z.max(axis=1, keepdims=True)
+        e = np.exp(z - zmax)
+        lse = np.log(e.sum(axis=1)) + zmax[:, 0]
+        loss = (lse - z[rows, target]).sum()
+        p = e / e.sum(axis=1, keepdims=True)
+        g = p.copy()
+        g[rows, target] -= 1.0
+        g = g * cfg.scale
+        g[~keep] = 0.0
+    elif name == "NCELoss":  # losses.py:501-511
+        sp_neg = _softplus(l)  # BCE-with-logits, label 0
+        pos_loss = _softplus(-t)  # label 1
+        loss = (pos_loss + _weighted_mean_rows(sp_neg, mask)).sum()
+        # the weighted mean uses nce_losses, whose target column carries the
+        # label-1 form; the target is never in the mask unless masking is off
+        # and then scatter(False) removed it, so label-0 form is all that counts.
+        g = _sigmoid(l) * w / cnt[:, None]
+        g[rows, target] += -_sigmoid(-t)
+    elif name in ("PairwiseHingeLoss", "PairwiseLogisticLoss"):  # losses.py:523-543
+        x = l - (t * (1.0 - cfg.margin))[:, None]
+        if name == "PairwiseHingeLoss":
+            v = np.maximum(x, 0.0)
+            dv = (x > 0).astype(np.float64)
+        else:
+            v = _softplus(x)
+            dv = _sigmoid(x)
+        loss = _weighted_mean_rows(v, mask).sum()
+        gx = dv * w / cnt[:, None]
+        g = gx.copy()
+        g[rows, target] += -(1.0 - cfg.margin) * gx.sum(axis=1)
+    else:
+        raise KeyError(name)
+    return (float(loss), g) if with_grad else float(loss)
+
+
+def logits_statistics(logits, target, mask, cfg):
+    """``LogitsStatistics.loss`` (losses.py:383-405); std is unbiased (torch default)."""
+    l = np.asarray(logits, np.float64)
+    m, c = l.shape
+    num_neg = c - 1
+    if cfg.num_hard_negatives > 0:
+        num_neg = min(num_neg, cfg.num_hard_negatives)
+    density = (mask.sum(axis=1) / (num_neg + 1e-9)).mean() if m > 0 else float("nan")
+    stats = {"logits/neg/density": float(density)}
+    groups = {"pos": l[np.arange(m), target], "neg": l[mask]}
+    for key, v in groups.items():
+        if v.size > 0:
+            stats[f"logits/{key}/mean"] = float(v.mean())
+            stats[f"logits/{key}/std"] = float(v.std(ddof=1)) if v.size > 1 else float("nan")
+            stats[f"logits/{key}/min"] = float(v.min())
+            stats[f"logits/{key}/max"] = float(v.max())
+    return stats
+
+
+def embed_loss(name, query, cand, cfg, target=None, *, with_grad=False, logits_dtype=None):
+    """``EmbedLoss.forward`` (losses.py:150-155) on a dense (M,C,D) candidate tensor.
+
+    ``logits_dtype='bf16'`` models Lightning's bf16-mixed autocast for the dot
+    losses: inputs rounded to bf16, logits rounded to bf16 before masking
+    (SURVEY §0.6); cosine logits stay fp32 there, as torch autocasts
+    cosine_similarity to fp32.
+
+    With ``with_grad`` returns (loss, dL/dquery) — the table is frozen in the
+    reference (models.py:251-253) so only dL/dquery is consumed.
+    """
+    q = np.asarray(query, np.float64)
+    c = np.asarray(cand, np.float64)
+    assert q.ndim == 2 and c.ndim == 3 and q.shape[0] == c.shape[0] and q.shape[1] == c.shape[2]
+    cosine = name in COSINE_LOSSES
+    if cosine:
+        logits = cosine_logits(q, c)
+    else:
+        if logits_dtype == "bf16":
+            q = round_bf16(q.astype(np.float32)).astype(np.float64)
+            c = round_bf16(c.astype(np.float32)).astype(np.float64)
+        logits = dot_logits(q, c)
+        if logits_dtype == "bf16":
+            logits = round_bf16(logits.astype(np.float32)).astype(np.float64)
+        elif logits_dtype == "fp32":
+            logits = logits.astype(np.float32).astype(np.float64)
+    tgt = check_target(logits.shape[0], cfg, target)
+    mask = mask_false_negatives(logits, tgt, cfg)
+    mask = mine_hard_negatives(logits, mask, cfg)
+    if not with_grad:
+        return loss_from_logits(name, logits, tgt, mask, cfg)
+    loss, g = loss_from_logits(name, logits, tgt, mask, cfg, with_grad=True)
+    dq = grad_query_from_dlogits(g, q, c, cosine=cosine)
+    return loss, dq
+
+
+def grad_query_from_dlogits(g, query, cand, *, cosine=False, eps=1e-8):
+    """Chain rule from dL/dlogits to dL/dquery for dense candidates."""
+    q = np.asarray(query, np.float64)
+    c = np.asarray(cand, np.float64)
+    if not cosine:
+        return np.einsum("mc,mcd->md", g, c)
+    qn_raw = np.linalg.norm(q, axis=-1, keepdims=True)
+    qn = np.maximum(qn_raw, eps)
+    cn = c / np.maximum(np.linalg.norm(c, axis=-1, keepdims=True), eps)
+    qhat = q / qn
+    ghat = np.einsum("mc,mcd->md", g, cn)  # dL/dqhat
+    # d(q/max(|q|,eps))/dq: projection when |q| > eps, plain 1/eps scaling otherwise
+    proj = ghat - (ghat * qhat).sum(-1, keepdims=True) * qhat
+    return np.where(qn_raw > eps, proj / qn, ghat / eps)
+
+
+def lean_loss(name, query, pos, neg, cfg, *, with_grad=False, logits_dtype=None, eps=1e-8):
+    """Same objective on the shared-pool form [rowdot | Q.Neg^T] (target first)."""
+    q = np.asarray(query, np.float64)
+    p = np.asarray(pos, np.float64)
+    n = np.asarray(neg, np.float64)
+    cosine = name in COSINE_LOSSES
+    if not cosine and logits_dtype == "bf16":
+        q = round_bf16(q.astype(np.float32)).astype(np.float64)
+        p = round_bf16(p.astype(np.float32)).astype(np.float64)
+        n = round_bf16(n.astype(np.float32)).astype(np.float64)
+    logits = lean_logits(q, p, n, cosine=cosine, eps=eps)
+    if not cosine and logits_dtype == "bf16":
+        logits = round_bf16(logits.astype(np.float32)).astype(np.float64)
+    tgt = np.zeros(q.shape[0], dtype=np.int64)
+    mask = mask_false_negatives(logits, tgt, cfg)
+    mask = mine_hard_negatives(logits, mask, cfg)
+    if not with_grad:
+        return loss_from_logits(name, logits, tgt, mask, cfg)
+    loss, g = loss_from_logits(name, logits, tgt, mask, cfg, with_grad=True)
+    if not cosine:
+        dq = g[:, :1] * p + g[:, 1:] @ n
+    else:
+        qn_raw = np.linalg.norm(q, axis=-1, keepdims=True)
+        qn = np.maximum(qn_raw, eps)
+        qhat = q / qn
+        phat = p / np.maximum(np.linalg.norm(p, axis=-1, keepdims=True), eps)
+        nhat = n / np.maximum(np.linalg.norm(n, axis=-1, keepdims=True), eps)
+        ghat = g[:, :1] * phat + g[:, 1:] @ nhat
+        proj = ghat - (ghat * qhat).sum(-1, keepdims=True) * qhat
+        dq = np.where(qn_raw > eps, proj / qn, ghat / eps)
+    return loss, dq, logits, mask
+
+
+# ---------------------------------------------------------------------------
+# exact retrieval — semantics of xfmr_rec/index.py:47, 239-254
+# ---------------------------------------------------------------------------
+def exact_search(queries, catalog, top_k, exclude=None, *, metric="cosine", eps=1e-12,
+                 chunk=262144, dtype=np.float32):
+    """Exact top-k the reference's ANN index approximates.
+
+    cosine metric (index.py:47), history ids filtered out before ranking
+    (prefilter, index.py:239-247), score = 1 - distance = cosine similarity
+    (index.py:252-254).  Ranking is a total order: score descending, ties by
+    lower catalog row (north_star tie rule; stable sort).
+    ``exclude`` is a list (one per query) of catalog row arrays.
+    """
+    q = np.asarray(queries, dtype)
+    if q.ndim == 1:
+        q = q[None]
+    cat = np.asarray(catalog, dtype)
+    if metric == "cosine":
+        q = q / np.maximum(np.linalg.norm(q, axis=-1, keepdims=True), eps)
+    u, n = q.shape[0], cat.shape[0]
+    best_s = np.full((u, 0), -np.inf, dtype)
+    best_i = np.zeros((u, 0), np.int64)
+    for lo in range(0, n, chunk):
+        blk = cat[lo:lo + chunk]
+        if metric == "cosine":
+            blk = blk / np.maximum(np.linalg.norm(blk, axis=-1, keepdims=True), eps)
+        s = q @ blk.T
+        ids = np.broadcast_to(np.arange(lo, lo + blk.shape[0])[None], s.shape)
+        if exclude is not None:
+            for r in range(u):
+                ex = np.asarray(exclude[r], np.int64)
+                ex = ex[(ex >= lo) & (ex < lo + blk.shape[0])] - lo
+                s[r, ex] = -np.inf
+        s = np.concatenate([best_s, s], axis=1)
+        ids = np.concatenate([best_i, ids], axis=1)
+        order = np.argsort(-s, axis=1, kind="stable")[:, :top_k]  # ids ascending within ties
+        best_s = np.take_along_axis(s, order, axis=1)
+        best_i = np.take_along_axis(ids, order, axis=1)
+    return best_s, best_i
+
+
+def topk_rows(scores, k):
+    """Stable top-k over a materialised (U,N) score matrix (score desc, index asc)."""
+    s = np.asarray(scores)
+    order = np.argsort(-s, axis=1, kind="stable")[:, :k]
+    return np.take_along_axis(s, order, axis=1), order.astype(np.int64)
+
+
+# ---------------------------------------------------------------------------
+# retrieval metrics — xfmr_rec/metrics.py:62-79 + torchmetrics 1.9.0 functional
+# ---------------------------------------------------------------------------
+METRIC_NAMES = [
+    "retrieval_normalized_dcg",
+    "retrieval_average_precision",
+    "retrieval_auroc",
+    "retrieval_precision",
+    "retrieval_recall",
+    "retrieval_hit_rate",
+    "retrieval_reciprocal_rank",
+]  # order = metrics.py:6-14
+
+
+def retrieval_metrics(rec_ids, target_ids, top_k):
+    """metrics.py:62-79.  Pure-Python restatement (small cases only).
+
+    ``preds = linspace(1, 0, len(all_items))`` is strictly decreasing, so the
+    ranking is the order of ``all_items`` and every metric reduces to a
+    function of the hit vector over the first ``top_k`` entries and the number
+    of targets.
+    """
+    if len(target_ids) == 0:  # metrics.py:62-63
+        return {}
+    recs = list(rec_ids)
+    if len(recs) < top_k:  # metrics.py:65-68
+        recs = recs + [""] * (top_k - len(recs))
+    tset = set(target_ids)
+    all_items = recs + list(tset - set(rec_ids))  # metrics.py:72
+    target = [item in tset for item in all_items]  # metrics.py:74
+    n_total = sum(target)
+    k = min(top_k, len(all_items))
+    hits = target[:k]
+    n_hit = sum(hits)
+    out = {}
+    # nDCG@k: gains are 0/1; ideal ranking puts all n_total targets first
+    dcg = sum(h / math.log2(r + 2) for r, h in enumerate(hits))
+    idcg = sum(1.0 / math.log2(r + 2) for r in range(min(n_total, k)))
+    out["retrieval_normalized_dcg"] = dcg / idcg if idcg > 0 else 0.0
+    # AP@k: mean over hits in the top-k of (hit ordinal / position)
+    if n_hit == 0:
+        ap = 0.0
+    else:
+        acc, seen = 0.0, 0
+        for r, h in enumerate(hits):
+            if h:
+                seen += 1
+                acc += seen / (r + 1)
+        ap = acc / n_hit
+    out["retrieval_average_precision"] = ap
+    # AUROC over the top-k: 0 when only one class is present
+    n_miss = k - n_hit
+    if n_hit == 0 or n_miss == 0:
+        auroc = 0.0
+    else:
+        pairs, misses_after = 0, 0
+        for h in reversed(hits):
+            if h:
+                pairs += misses_after
+            else:
+                misses_after += 1
+        auroc = pairs / (n_hit * n_miss)
+    out["retrieval_auroc"] = auroc
+    out["retrieval_precision"] = n_hit / top_k if n_total > 0 else 0.0
+    out["retrieval_recall"] = n_hit / n_total if n_total > 0 else 0.0
+    out["retrieval_hit_rate"] = 1.0 if n_hit > 0 else 0.0
+    rr = 0.0
+    for r, h in enumerate(hits):
+        if h:
+            rr = 1.0 / (r + 1)
+            break
+    out["retrieval_reciprocal_rank"] = rr
+    return out
+
+
+# ---------------------------------------------------------------------------
+# synthetic inputs — SURVEY §8(d); mimics data.py:669-805 (SeqBatch contract)
+# ---------------------------------------------------------------------------
+def synth_batch(n_items, batch, seq_len, dim=384, seed=0, pos_pad_frac=0.05, table=None):
+    rng = np.random.default_rng(seed)
+    if table is None:
+        table = (rng.standard_normal((n_items + 1, dim)) / math.sqrt(dim)).astype(np.float32)
+        table[0] = 0.0
+    lens = rng.integers(1, seq_len + 1, size=batch)
+    hist = np.zeros((batch, seq_len), np.int64)
+    pos = np.zeros((batch, seq_len), np.int64)
+    neg = np.zeros((batch, seq_len), np.int64)
+    for b in range(batch):  # right-padded with 0 like pad_sequence (data.py:801)
+        n = int(lens[b])
+        hist[b, :n] = rng.integers(1, n_items + 1, size=n)
+        pos[b, :n] = rng.integers(1, n_items + 1, size=n)
+        neg[b, :n] = rng.integers(1, n_items + 1, size=n)
+        drop = rng.random(n) < pos_pad_frac  # data.py:710-721: no future positive
+        pos[b, :n][drop] = 0
+    tokens = (rng.standard_normal((batch, seq_len, dim)) / math.sqrt(dim)).astype(np.float32)
+    return {"table": table, "history_item_idx": hist, "pos_item_idx": pos,
+            "neg_item_idx": neg, "token_embeddings": tokens}
