@@ -1,0 +1,234 @@
+/*
+ * xfmr_b200 — C ABI of the B200-native scoring-and-loss / full-catalog top-k path.
+ *
+ * The reference (yxtay/transformer-recommenders) is pure Python; it has no FFI layer.
+ * The drop-in boundary is therefore the Python call signature of its loss modules,
+ * `compute_embeds`, `compute_retrieval_metrics` and `LanceIndex.search`
+ * (SURVEY.md §8b).  Those signatures are mirrored by the `xfmr_rec_b200` package,
+ * which binds THIS header with ctypes and registers the entry points as
+ * `torch.library` custom ops.  Each entry point cites the reference lines whose
+ * arithmetic it replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *     the caller owns every buffer; the library allocates nothing persistent.
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no entry
+ *     point synchronises the device.
+ *   - return value: 0 = ok, <0 = error (XR_E_*); `xr_last_error()` gives the
+ *     message for the calling thread.
+ *   - dtype codes: XR_F32 = 0, XR_BF16 = 1.  Row-major, densely packed unless a
+ *     leading dimension is given.
+ */
+#ifndef XFMR_B200_H
+#define XFMR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XR_ABI_VERSION 1
+
+#define XR_F32 0
+#define XR_BF16 1
+
+#define XR_OK 0
+#define XR_E_INVALID (-1)     /* bad argument (shape, dtype, alignment, null pointer)      */
+#define XR_E_CUDA (-2)        /* a CUDA runtime / driver call failed                        */
+#define XR_E_UNSUPPORTED (-3) /* valid request this build cannot serve (e.g. not sm_100)    */
+
+/* loss kinds; order = LOSS_CLASSES, xfmr_rec/losses.py:546-554 */
+#define XR_LOSS_ALIGNMENT 0             /* losses.py:408-426 */
+#define XR_LOSS_ALIGNMENT_CONTRASTIVE 1 /* losses.py:429-447 (CCL)  */
+#define XR_LOSS_CONTRASTIVE 2           /* losses.py:450-469 */
+#define XR_LOSS_INFONCE 3               /* losses.py:472-488 (SSM)  */
+#define XR_LOSS_NCE 4                   /* losses.py:491-511 */
+#define XR_LOSS_PAIRWISE_HINGE 5        /* losses.py:514-527 */
+#define XR_LOSS_PAIRWISE_LOGISTIC 6     /* losses.py:530-543 (BPR at margin 0) */
+#define XR_NUM_LOSSES 7
+
+/* target_position, losses.py:26, 240-253 */
+#define XR_TARGET_FIRST 0
+#define XR_TARGET_DIAGONAL 1
+#define XR_TARGET_EXPLICIT 2
+#define XR_TARGET_LAST 3 /* internal layout of xr_logits_pool */
+
+/* LossConfig, xfmr_rec/losses.py:11-30 (target_position carried separately) */
+typedef struct xr_loss_config {
+  int32_t mask_false_negatives; /* losses.py:27, 283-292 */
+  int32_t num_hard_negatives;   /* losses.py:28, 311-330 */
+  float scale;                  /* losses.py:29, 486     */
+  float margin;                 /* losses.py:30, 370, 525, 541 */
+  int32_t logits_bf16;          /* 1: round dot logits to bf16 before masking, as Lightning's
+                                   bf16-mixed autocast does to losses.py:195 (trainer.py:450) */
+} xr_loss_config;
+
+/* number of float64 slots in the statistics block written by xr_rowloss / fused kernels */
+#define XR_STATS_SLOTS 16
+
+const char* xr_last_error(void);
+int xr_abi_version(void);
+/* sm count, compute capability and whether the tcgen05 kernels can run on the current device */
+int xr_device_info(int* sm_count, int* cc_major, int* cc_minor, int* has_tcgen05);
+
+/* ---- family 1: embedding row gathers ------------------------------------------------------
+ * nn.Embedding.forward — models.py:336-338 (history), :400 (positives), :406 (negatives).
+ * out[i,:] = table[ idx[ sel ? sel[i] : i ], : ].  Bit-exact copy when out_dtype ==
+ * table_dtype; XR_F32 -> XR_BF16 rounds to nearest even (torch's .bfloat16()).
+ * `sel` (nullable) is the second-level index produced by xr_compact_positions, which fuses
+ * the boolean-mask compaction of models.py:398/404 into the gather.
+ * `err_flag` (nullable, device int32): set to 1 if any index is outside [0, n_rows).          */
+int xr_gather_rows(const void* table, int64_t n_rows, int64_t dim, int table_dtype,
+                   const int64_t* idx, const int64_t* sel, int64_t n_out, void* out,
+                   int out_dtype, int32_t* err_flag, void* stream);
+
+/* dst[sel[i],:] = src[i,:] (dst pre-zeroed by the caller, sel unique) — the autograd transpose
+ * of the query compaction `token_embeddings[attention_mask][pos_mask]` (models.py:392, 415).  */
+int xr_scatter_rows(const float* src, int64_t n_src, int64_t dim, const int64_t* sel,
+                    float* dst, int64_t n_dst_rows, void* stream);
+
+/* rownz[r] = any(table[r,:] != 0) — lets the attention mask of models.py:343 be derived from
+ * the indices: mask = rownz[idx].                                                             */
+int xr_row_nonzero(const void* table, int64_t n_rows, int64_t dim, int dtype, uint8_t* rownz,
+                   void* stream);
+
+/* models.py:343, 390, 398, 404, 413-416 on the index tensors of one SeqBatch (flattened B*L):
+ *   attn[p]      = rownz[history_idx[p]]                      (attention_mask, :343/:390)
+ *   sel_attn[..] = positions p with attn[p], ascending        (neg / pos row order, :398/:404)
+ *   sel_pos[..]  = positions p with attn[p] && pos_idx[p]!=0  (query / candidate rows, :413-416)
+ *   pos_mask[a]  = pos_idx[sel_attn[a]] != 0                   (positive_mask, :413)
+ * counts[0] = M_a, counts[1] = M (device int64[2]).  rownz == NULL uses idx != 0 instead.
+ * workspace >= xr_compact_workspace_bytes(n_pos).                                             */
+size_t xr_compact_workspace_bytes(int64_t n_pos);
+int xr_compact_positions(const int64_t* history_idx, const int64_t* pos_idx,
+                         const uint8_t* rownz, int64_t n_table_rows, int64_t n_pos,
+                         uint8_t* attn, int64_t* sel_attn, int64_t* sel_pos, uint8_t* pos_mask,
+                         int64_t* counts, void* workspace, void* stream);
+
+/* y[r,:] = x[r,:] / max(||x[r,:]||, eps); inv_norm[r] = 1/max(||x[r,:]||, eps);
+ * the two normalisations inside torch's cosine_similarity, losses.py:206-208 (eps 1e-8) and
+ * the catalog/query normalisation of the cosine index metric, index.py:47.
+ * y may be null (norms only); y dtype may differ from x dtype.                               */
+int xr_normalize_rows(const void* x, int64_t n_rows, int64_t dim, int x_dtype, float eps,
+                      void* y, int y_dtype, float* inv_norm, void* stream);
+
+/* ---- family 2a: logits, materialised (fp32-exact path and API-compat paths) ---------------
+ * compute_logits / cosine_similarity_logits, losses.py:179-209.                               */
+
+/* shared-pool candidates (models.py:408-410 without the O(M^2 D) copy), fp32 accumulate:
+ *   logits[i,j] = q_i . neg_j  for j < Cn ;  logits[i,Cn] = q_i . pos_i
+ * The positive sits in the LAST column (XR_TARGET_LAST) so both GEMM operands stay 16-byte
+ * aligned; masking, mining and every loss are invariant to where the target column is.
+ * logits is (M, ld) fp32 with ld >= Cn+1 (ld % 4 == 0 keeps the vector path).                 */
+int xr_logits_pool(const void* q, const void* pos, const void* neg, int64_t m, int64_t cn,
+                   int64_t dim, int dtype, float* logits, int64_t ld, void* stream);
+
+/* genuine dense candidates (M,C,D) — the reference's bmm, losses.py:195 (batched GEMV).
+ * cosine (losses.py:206-208): pass q_inv_norm (from xr_normalize_rows) and a (M,C) fp32
+ * cand_inv_norm_out buffer, filled in the same pass over the candidates; both NULL for dot.  */
+int xr_logits_dense(const void* q, const void* cand, int64_t m, int64_t c, int64_t dim,
+                    int dtype, const float* q_inv_norm, float* cand_inv_norm_out, float eps,
+                    float* logits, int64_t ld, void* stream);
+
+/* per-row sampled negatives: candidates of row i are table[cand_idx[i,0..c)] (col 0 = positive)
+ * — BASELINE config 3; fused gather + dot, no (M,C,D) tensor.                                 */
+int xr_logits_sampled(const void* q, const void* table, int64_t n_rows, const int64_t* cand_idx,
+                      int64_t m, int64_t c, int64_t dim, int dtype, const float* table_inv_norm,
+                      const float* q_inv_norm, float* logits, int64_t ld, void* stream);
+
+/* ---- the EmbedLoss pipeline on logits: losses.py:211-330 + the seven loss() bodies ---------
+ * check_target (:233-261) -> mask_false_negatives (:283-292) -> mine_hard_negatives (:311-330)
+ * -> loss (:420-543) and LogitsStatistics (:383-405), one pass per row.
+ *   losses_out  : float64[XR_NUM_LOSSES] sums over rows for every loss whose bit is set in
+ *                 `loss_mask` (bit k = loss kind k); logits are used as given, so cosine and
+ *                 dot families are evaluated in separate calls.
+ *   stats_out   : float64[XR_STATS_SLOTS] (nullable): [0] sum_i n_valid_i/(num_neg+1e-9),
+ *                 [1] rows, pos {[2] sum,[3] sumsq,[4] min,[5] max}, neg {[6] count,[7] sum,
+ *                 [8] sumsq,[9] min,[10] max}, [11] num_neg used for the density.
+ *   dlogits     : (M, ld) fp32 (nullable): dL/dlogits of `grad_kind` (-1 = none), times
+ *                 grad_scale.
+ *   err_flag    : nullable device int32, set when an explicit target is out of range (the
+ *                 reference's gather would raise).
+ *   workspace   : >= xr_rowloss_workspace_bytes(m, c, cfg->num_hard_negatives) bytes.
+ * Hard-negative ties are resolved toward the lower candidate index (torch.topk(sorted=False)
+ * leaves it implementation-defined, losses.py:318-322).                                       */
+size_t xr_rowloss_workspace_bytes(int64_t m, int64_t c, int num_hard_negatives);
+int xr_rowloss(const float* logits, int64_t m, int64_t c, int64_t ld, int target_mode,
+               const int64_t* target, const xr_loss_config* cfg, uint32_t loss_mask,
+               int grad_kind, float grad_scale, float* dlogits, double* losses_out,
+               double* stats_out, int32_t* err_flag, void* workspace, void* stream);
+
+/* ---- family 2b: dL/dquery from dL/dlogits ---------------------------------------------------
+ * autograd of losses.py:195 / :206-208 w.r.t. query_embed (item table frozen, models.py:251).
+ * xr_dq_pool, cosine != 0: q/pos/neg are the NORMALISED rows plus q_inv_norm; it applies
+ * dq = inv_norm * (g - (g.qhat) qhat).  The dense / sampled variants take the RAW q plus the
+ * inverse norms and normalise on the fly.                                                     */
+int xr_dq_pool(const float* dlogits, int64_t ld, const void* q, const void* pos, const void* neg,
+               int64_t m, int64_t cn, int64_t dim, int dtype, int cosine,
+               const float* q_inv_norm, float* dq, void* stream);
+int xr_dq_dense(const float* dlogits, int64_t ld, const void* q, const void* cand, int64_t m,
+                int64_t c, int64_t dim, int dtype, int cosine, const float* q_inv_norm,
+                const float* cand_inv_norm, float* dq, void* stream);
+int xr_dq_sampled(const float* dlogits, int64_t ld, const void* q, const void* table,
+                  int64_t n_rows, const int64_t* cand_idx, int64_t m, int64_t c, int64_t dim,
+                  int dtype, const float* table_inv_norm, const float* q_inv_norm, float* dq,
+                  void* stream);
+
+/* ---- family 2c: fused contraction + loss + gradient (tcgen05/TMEM, bf16) -------------------
+ * One pass over the shared negative pool: S = Q.Neg^T on the 5th-gen tensor cores, the loss
+ * epilogue on the TMEM accumulator, dQ += W.Neg as a second UMMA — the M x C logits never
+ * reach HBM.  Replaces models.py:408-416 + losses.py:150-155 for InfoNCE (:479-488),
+ * PairwiseLogistic / PairwiseHinge (:520-543), NCE (:498-511) and, on pre-normalised inputs,
+ * Contrastive / AlignmentContrastive (:338-372, :436-447).  num_hard_negatives must be 0.
+ *   q, pos : (M, D) bf16;  neg : (Cn, D) bf16;  D = 384 in this build.
+ *   dq     : (M, D) fp32 (nullable => forward only), times grad_scale.
+ *   loss_out : float64[1] sum over rows;  row_loss (nullable): float32[M].
+ *   q_inv_norm (cosine kinds only): float32[M].
+ *   workspace: >= xr_fused_pool_workspace_bytes(m, cn, dim) bytes.                            */
+size_t xr_fused_pool_workspace_bytes(int64_t m, int64_t cn, int64_t dim);
+int xr_fused_pool_loss(const void* q, const void* pos, const void* neg, int64_t m, int64_t cn,
+                       int64_t dim, int loss_kind, const xr_loss_config* cfg,
+                       const float* q_inv_norm, float grad_scale, float* dq, double* loss_out,
+                       float* row_loss, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- family 3: top-k -------------------------------------------------------------------------
+ * Exact top-k of each row of a materialised (U,N) fp32 score matrix under the total order
+ * (score descending, column ascending) — the result the reference's ANN search
+ * (index.py:244-251, limit(top_k)) approximates; ties -> lower item id.
+ * col_offset is added to the reported indices (catalog shard base).  NaN ranks first
+ * (torch.sort convention).  out_scores (U,k) fp32, out_idx (U,k) int64; if N < k the tail is
+ * filled with -inf / -1.                                                                      */
+size_t xr_topk_workspace_bytes(int64_t u, int64_t n, int64_t k);
+int xr_topk(const float* scores, int64_t u, int64_t n, int64_t ld, int64_t k, int64_t col_offset,
+            float* out_scores, int64_t* out_idx, void* workspace, size_t workspace_bytes,
+            void* stream);
+/* merge G per-shard results laid out (U, G*k) (scores + global ids), same total order; the
+ * local step after the NCCL all-gather of SURVEY §8e.                                         */
+size_t xr_topk_merge_workspace_bytes(int64_t u, int64_t k);
+int xr_topk_merge(const float* scores, const int64_t* ids, int64_t u, int64_t gk, int64_t k,
+                  float* out_scores, int64_t* out_idx, void* workspace, void* stream);
+
+/* scores[u,n] = q_u . cat_n (* q_inv_norm[u] * cat_inv_norm[n] when given), fp32 accumulate;
+ * exclusion: for every (u, e) pair in the CSR lists excl_offsets/excl_ids (global ids), the
+ * score of column e - col_offset is set to -inf (the prefilter of index.py:239-247).          */
+int xr_scores(const void* q, int64_t u, const void* catalog, int64_t n, int64_t dim, int dtype,
+              const float* q_inv_norm, const float* cat_inv_norm, float* scores, int64_t ld,
+              void* stream);
+int xr_mask_excluded(float* scores, int64_t u, int64_t n, int64_t ld, int64_t col_offset,
+                     const int64_t* excl_offsets, const int64_t* excl_ids, void* stream);
+
+/* ---- retrieval metrics -------------------------------------------------------------------------
+ * compute_retrieval_metrics, metrics.py:62-79 (+ torchmetrics 1.9.0 functional definitions),
+ * batched: rec (U,k) int64 ranked ids (-1 = the "" padding of metrics.py:65-68), targets in CSR.
+ * out (U,7) fp32 in METRIC_FNS order (metrics.py:6-14); valid[u] = 0 where the user has no
+ * targets (the reference returns {} there, metrics.py:62-63).                                 */
+int xr_retrieval_metrics(const int64_t* rec, int64_t u, int64_t k, const int64_t* tgt_offsets,
+                         const int64_t* tgt_ids, int64_t top_k, float* out, uint8_t* valid,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XFMR_B200_H */

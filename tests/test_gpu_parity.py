@@ -1,0 +1,388 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden
+vectors produced by the reference's own losses.py.  Run on the B200 box: pytest -m gpu."""
+
+import json
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import xfmr_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+FP32_REL = 1e-5   # north_star: losses / gradients within 1e-5 relative in fp32
+BF16_REL = 2e-3   # ... and 2e-3 in bf16
+
+
+@pytest.fixture(scope="module")
+def xr():
+    import xfmr_rec_b200 as pkg
+
+    return pkg
+
+
+def dev(x, dtype=None):
+    t = torch.as_tensor(x).cuda()
+    return t.to(dtype) if dtype is not None else t
+
+
+def load(golden_dir, name):
+    z = np.load(golden_dir / f"losses_{name}.npz")
+    return z, json.loads(str(z["cfg"]))
+
+
+def assert_close_grad(got, want, rel):
+    scale = max(float(np.abs(want).max()), 1e-6)
+    err = float(np.abs(got - want).max())
+    assert err <= rel * scale * 4 + 1e-7, (err, scale)
+
+
+# ------------------------------------------------------------------------------------------
+# family 1: gathers / compaction
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim,dtype", [(384, torch.float32), (384, torch.bfloat16), (50, torch.float32),
+                                        (8, torch.bfloat16), (1024, torch.float32)])
+def test_gather_rows_bit_exact(xr, dim, dtype):
+    g = torch.Generator().manual_seed(0)
+    table = torch.randn(1000, dim, generator=g).to(dtype)
+    table[0] = 0
+    idx = torch.randint(0, 1000, (37, 11), generator=g)
+    out = xr.ops.gather_rows(table.cuda(), idx.cuda())
+    assert out.shape == (37, 11, dim)
+    assert torch.equal(out.cpu(), table[idx])           # bit-exact (nn.Embedding semantics)
+    # empty and single-row inputs
+    assert xr.ops.gather_rows(table.cuda(), idx[:0].cuda()).shape == (0, 11, dim)
+    sel = torch.tensor([5, 0, 5, 36 * 11], dtype=torch.int64)
+    out = xr.ops.gather_rows(table.cuda(), idx.cuda().view(-1), sel=sel.cuda())
+    assert torch.equal(out.cpu(), table[idx.view(-1)[sel]])
+
+
+def test_gather_rows_cast_and_bounds(xr):
+    g = torch.Generator().manual_seed(1)
+    table = torch.randn(300, 384, generator=g)
+    idx = torch.randint(0, 300, (1000,), generator=g)
+    out = xr.ops.gather_rows(table.cuda(), idx.cuda(), out_dtype=torch.bfloat16)
+    assert torch.equal(out.cpu(), table[idx].bfloat16())  # round-to-nearest-even like torch
+    bad = idx.clone()
+    bad[3] = 300
+    with pytest.raises(IndexError):
+        xr.ops.gather_rows(table.cuda(), bad.cuda(), check=True)
+
+
+def test_gather_large_matches_torch(xr):
+    g = torch.Generator().manual_seed(2)
+    table = torch.randn(27279, 384, generator=g).bfloat16().cuda()
+    idx = torch.randint(0, 27279, (25600,), generator=g).cuda()
+    assert torch.equal(xr.ops.gather_rows(table, idx), table[idx])
+
+
+@pytest.mark.parametrize("batch,seq", [(4, 9), (32, 50), (3, 4097)])
+def test_compute_embeds_matches_oracle(xr, batch, seq):
+    b = orc.synth_batch(200, batch, seq, dim=64, seed=batch)
+    b["table"][17] = 0.0    # a real item with an all-zero row: masked by (embeds != 0).any(-1)
+    want = orc.compute_embeds(b["table"], b["token_embeddings"], b["history_item_idx"],
+                              b["pos_item_idx"], b["neg_item_idx"], dense=False)
+    emb = xr.models.ItemEmbeddings(torch.from_numpy(b["table"]), add_padding_row=False).cuda()
+    tok = dev(b["token_embeddings"]).requires_grad_(True)
+    out = xr.models.compute_embeds(emb, tok, dev(b["history_item_idx"]), dev(b["pos_item_idx"]),
+                                   dev(b["neg_item_idx"]))
+    assert np.array_equal(out["attention_mask"].cpu().numpy(), want["attention_mask"])
+    assert np.array_equal(out["positive_mask"].cpu().numpy(), want["positive_mask"])
+    assert np.array_equal(out["query_embed"].detach().cpu().numpy(), want["query_embed"])
+    assert np.array_equal(out["candidate_embed"].pos.cpu().numpy(), want["pos_embed"])
+    assert np.array_equal(out["candidate_embed"].neg.cpu().numpy(), want["neg_embed"])
+    assert tuple(out["candidate_embed"].size()) == (want["query_embed"].shape[0],
+                                                    1 + want["neg_embed"].shape[0], 64)
+    # autograd reaches the encoder output through the compaction
+    out["query_embed"].sum().backward()
+    g = tok.grad.cpu().numpy().reshape(-1, 64)
+    am = want["attention_mask"].reshape(-1)
+    keep = np.zeros(am.shape, bool)
+    keep[np.flatnonzero(am)[want["positive_mask"]]] = True
+    assert np.array_equal(g, np.repeat(keep[:, None], 64, 1).astype(np.float32))
+
+
+def test_compute_embeds_dense_equals_reference_layout(xr):
+    b = orc.synth_batch(60, 3, 7, dim=32, seed=5)
+    want = orc.compute_embeds(b["table"], b["token_embeddings"], b["history_item_idx"],
+                              b["pos_item_idx"], b["neg_item_idx"], dense=True)
+    emb = xr.models.ItemEmbeddings(torch.from_numpy(b["table"]), add_padding_row=False).cuda()
+    out = xr.models.compute_embeds(emb, dev(b["token_embeddings"]), dev(b["history_item_idx"]),
+                                   dev(b["pos_item_idx"]), dev(b["neg_item_idx"]), dense=True)
+    assert np.array_equal(out["candidate_embed"].cpu().numpy(), want["candidate_embed"])
+
+
+# ------------------------------------------------------------------------------------------
+# family 2: losses vs the reference's own outputs (golden) — fp32
+# ------------------------------------------------------------------------------------------
+GOLDEN_FP32 = ["anchor_m64_d384", "pool_default", "pool_nomask", "pool_scale20_margin02",
+               "pool_margin0", "pool_hard5", "pool_hard5_nomask", "dense_first", "dense_diagonal",
+               "dense_explicit", "dense_c1"]
+
+
+@pytest.mark.parametrize("case", GOLDEN_FP32)
+@pytest.mark.parametrize("form", ["dense", "handle"])
+def test_losses_match_reference_fp32(xr, golden_dir, case, form):
+    z, cfg_kw = load(golden_dir, case)
+    if form == "handle" and "pos" not in z:
+        pytest.skip("dense-only case")
+    cfg = xr.LossConfig(**cfg_kw)
+    target = dev(z["target"]) if "target" in z else None
+    if form == "handle":
+        cand = xr.PoolCandidates(dev(z["pos"]), dev(z["neg"]))
+    elif "cand" in z:
+        cand = dev(z["cand"])
+    else:
+        cand = xr.PoolCandidates(dev(z["pos"]), dev(z["neg"])).dense()
+    for cls in xr.LOSS_CLASSES:
+        name = cls.__name__
+        q = dev(z["query"]).requires_grad_(True)
+        loss = cls(cfg)(query_embed=q, candidate_embed=cand, target=target)
+        assert loss.dim() == 0 and loss.dtype == torch.float32
+        want = float(z[f"loss/{name}"])
+        assert float(loss) == pytest.approx(want, rel=FP32_REL, abs=1e-5), (case, name)
+        loss.backward()
+        assert_close_grad(q.grad.cpu().numpy(), z[f"dq/{name}"], FP32_REL)
+
+
+@pytest.mark.parametrize("case", GOLDEN_FP32)
+def test_logits_statistics_match_reference(xr, golden_dir, case):
+    z, cfg_kw = load(golden_dir, case)
+    cfg = xr.LossConfig(**cfg_kw)
+    target = dev(z["target"]) if "target" in z else None
+    cand = dev(z["cand"]) if "cand" in z else xr.PoolCandidates(dev(z["pos"]), dev(z["neg"]))
+    got = xr.LogitsStatistics(cfg)(query_embed=dev(z["query"]), candidate_embed=cand, target=target)
+    want = json.loads(str(z["stats"]))
+    assert set(got) == set(want)
+    for k, v in want.items():
+        if math.isnan(v):
+            assert math.isnan(got[k]), k
+        else:
+            assert got[k] == pytest.approx(v, rel=2e-5, abs=2e-6), (case, k)
+
+
+def test_losses_under_bf16_autocast(xr, golden_dir):
+    """Lightning bf16-mixed (trainer.py:450): dot logits are bf16-rounded before masking."""
+    z, cfg_kw = load(golden_dir, "pool_autocast_bf16")
+    cfg = xr.LossConfig(**cfg_kw)
+    cand = xr.PoolCandidates(dev(z["pos"]), dev(z["neg"]))
+    for cls in xr.LOSS_CLASSES:
+        name = cls.__name__
+        q = dev(z["query"]).requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = cls(cfg)(query_embed=q, candidate_embed=cand)
+        want = float(z[f"loss/{name}"])
+        assert float(loss) == pytest.approx(want, rel=BF16_REL, abs=1e-4), name
+        loss.backward()
+        # gradients: compare with the oracle run on bf16-rounded logits (mask decided in bf16)
+        _, dq, _, _ = orc.lean_loss(name, z["query"], z["pos"], z["neg"], orc.Config(**cfg_kw),
+                                    with_grad=True, logits_dtype="bf16")
+        ref = z[f"dq/{name}"]
+        scale = max(float(np.abs(ref).max()), 1e-6)
+        g = q.grad.float().cpu().numpy()
+        # entries whose mask bit flipped under a 1-ulp bf16 difference are rare; judge in aggregate
+        assert np.abs(g - dq).max() <= 0.05 * scale + 1e-6, name
+        assert np.linalg.norm(g - dq) <= 1e-2 * np.linalg.norm(dq) + 1e-6, name
+
+
+@pytest.mark.parametrize("name", orc.LOSS_NAMES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_sampled_candidates_match_oracle(xr, name, dtype):
+    rng = np.random.default_rng(7)
+    n, m, c, d = 500, 33, 65, 384
+    table = (rng.standard_normal((n + 1, d)) / math.sqrt(d)).astype(np.float32)
+    table[0] = 0
+    if dtype == torch.bfloat16:
+        table = orc.round_bf16(table)
+    q = (rng.standard_normal((m, d)) / math.sqrt(d)).astype(np.float32)
+    if dtype == torch.bfloat16:
+        q = orc.round_bf16(q)
+    idx = rng.integers(1, n + 1, size=(m, c))
+    idx[3, 5] = idx[3, 0]      # duplicate of the positive among the negatives: tie -> masked
+    idx[4, 7] = 0              # padding row as a candidate
+    cfg_kw = {"margin": 0.3, "scale": 5.0}
+    cand_dense = table[idx]
+    logits_dtype = "bf16" if dtype == torch.bfloat16 else None
+    want, dq = orc.embed_loss(name, q, cand_dense, orc.Config(**cfg_kw), with_grad=True,
+                              logits_dtype=logits_dtype)
+    qt = dev(q, dtype).requires_grad_(True)
+    cand = xr.SampledCandidates(dev(table, dtype), dev(idx))
+    loss = getattr(xr, name)(xr.LossConfig(**cfg_kw))(qt, cand)
+    rel = FP32_REL if dtype == torch.float32 else BF16_REL
+    assert float(loss) == pytest.approx(want, rel=rel * 2, abs=1e-4)
+    loss.backward()
+    g = qt.grad.float().cpu().numpy()
+    tol = 4 * rel if dtype == torch.float32 else 2e-2
+    assert np.abs(g - dq).max() <= tol * max(np.abs(dq).max(), 1e-6) + 1e-6
+
+
+def test_pool_large_fp32_matches_oracle(xr):
+    """BASELINE config-1 shape class (fp32, shared pool), rows > one GEMM tile, ragged sizes."""
+    rng = np.random.default_rng(11)
+    m, cn, d = 301, 777, 384
+    q = (rng.standard_normal((m, d)) / math.sqrt(d)).astype(np.float32)
+    pos = (rng.standard_normal((m, d)) / math.sqrt(d)).astype(np.float32)
+    neg = (rng.standard_normal((cn, d)) / math.sqrt(d)).astype(np.float32)
+    for name in orc.LOSS_NAMES:
+        want, dq, _, _ = orc.lean_loss(name, q, pos, neg, orc.Config(), with_grad=True)
+        qt = dev(q).requires_grad_(True)
+        loss = getattr(xr, name)(xr.LossConfig())(qt, xr.PoolCandidates(dev(pos), dev(neg)))
+        assert float(loss) == pytest.approx(want, rel=FP32_REL, abs=1e-5), name
+        loss.backward()
+        assert_close_grad(qt.grad.cpu().numpy(), dq, FP32_REL)
+
+
+def test_loss_error_behaviour(xr):
+    q = torch.randn(4, 8).cuda()
+    cand = torch.randn(4, 5, 8).cuda()
+    with pytest.raises(AssertionError):
+        xr.InfoNCELoss(xr.LossConfig())(q[0], cand)                       # losses.py:166
+    with pytest.raises(AssertionError):
+        xr.InfoNCELoss(xr.LossConfig())(q, cand[:, 0])                    # losses.py:169
+    with pytest.raises(AssertionError):
+        xr.InfoNCELoss(xr.LossConfig())(q[:3], cand)                      # losses.py:172
+    with pytest.raises(AssertionError):
+        xr.InfoNCELoss(xr.LossConfig())(q, cand, target=torch.zeros(4).long().cuda())  # :236
+    with pytest.raises(AssertionError):
+        xr.InfoNCELoss(xr.LossConfig(target_position=None))(q, cand)      # losses.py:233
+    with pytest.raises(IndexError):
+        xr.InfoNCELoss(xr.LossConfig(target_position=None))(q, cand, target=torch.full((4,), 9).cuda())
+    cfg = xr.LossConfig()
+    object.__setattr__(cfg, "target_position", "bogus")
+    with pytest.raises(ValueError):
+        xr.InfoNCELoss(cfg)(q, cand)                                       # losses.py:251-253
+    assert len(list(xr.InfoNCELoss(xr.LossConfig()).parameters())) == 0
+    assert len(xr.InfoNCELoss(xr.LossConfig()).state_dict()) == 0          # checkpoint keys unchanged
+    with pytest.raises(xr._native.NativeError):
+        xr.InfoNCELoss(xr.LossConfig())(q.cpu(), cand.cpu())               # no CPU fallback
+
+
+# ------------------------------------------------------------------------------------------
+# family 3: top-k, exact search, metrics
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("u,n,k", [(1, 5, 2), (3, 1000, 100), (7, 70001, 100), (1, 300000, 100),
+                                   (130, 4099, 20), (2, 50, 100), (5, 2048, 1024)])
+def test_topk_bit_exact_vs_stable_sort(xr, u, n, k):
+    rng = np.random.default_rng(u * 1000 + k)
+    s = rng.standard_normal((u, n)).astype(np.float32)
+    s = np.round(s * 8) / 8            # heavy ties: the (score desc, index asc) rule decides
+    if n > 10:
+        s[0, 3] = np.inf
+        s[0, 7] = -np.inf
+        s[-1, 5] = -0.0
+        s[-1, 6] = 0.0
+    got_s, got_i = xr.ops.topk(dev(s), k)
+    want_s, want_i = orc.topk_rows(s, k)
+    kk = min(k, n)
+    assert np.array_equal(got_i.cpu().numpy()[:, :kk], want_i)
+    assert np.array_equal(got_s.cpu().numpy()[:, :kk], want_s)
+    if k > n:
+        assert (got_i.cpu().numpy()[:, n:] == -1).all()
+        assert np.isneginf(got_s.cpu().numpy()[:, n:]).all()
+
+
+def test_topk_sorted_and_adversarial_inputs(xr):
+    n, k = 100000, 100
+    asc = np.arange(n, dtype=np.float32)[None]          # every element beats the threshold
+    _, i = xr.ops.topk(dev(asc), k)
+    assert np.array_equal(i.cpu().numpy()[0], np.arange(n - 1, n - 1 - k, -1))
+    const = np.zeros((2, n), np.float32)                # all tied: lowest ids win
+    _, i = xr.ops.topk(dev(const), k)
+    assert np.array_equal(i.cpu().numpy(), np.tile(np.arange(k), (2, 1)))
+
+
+def test_topk_merge_equals_global_topk(xr):
+    rng = np.random.default_rng(3)
+    u, n, k, g = 9, 8000, 100, 4
+    s = np.round(rng.standard_normal((u, n)).astype(np.float32) * 4) / 4
+    per = n // g
+    ps, pi = [], []
+    for r in range(g):
+        a, b = xr.ops.topk(dev(s[:, r * per:(r + 1) * per].copy()), k, col_offset=r * per)
+        ps.append(a)
+        pi.append(b)
+    ms, mi = xr.ops.topk_merge(torch.cat(ps, 1), torch.cat(pi, 1), k)
+    want_s, want_i = orc.topk_rows(s, k)
+    assert np.array_equal(mi.cpu().numpy(), want_i)
+    assert np.array_equal(ms.cpu().numpy(), want_s)
+
+
+@pytest.mark.parametrize("metric", ["cosine", "dot"])
+def test_exact_index_matches_oracle(xr, metric):
+    """Small-integer embeddings make every dot product exact in bf16/fp32, so indices must be
+    IDENTICAL to the stable-sort oracle, ties included."""
+    rng = np.random.default_rng(5)
+    n, d, u, k = 5000, 384, 6, 100
+    cat = rng.integers(-2, 3, size=(n, d)).astype(np.float32)
+    qs = rng.integers(-2, 3, size=(u, d)).astype(np.float32)
+    excl = [list(rng.integers(0, n, size=rng.integers(20, 200))) for _ in range(u)]
+    idx = xr.index.ExactIndex(xr.index.ExactIndexConfig(index_metric=metric, dtype="fp32",
+                                                        max_score_bytes=u * 4 * 2048))
+    idx.set_catalog(torch.from_numpy(cat).cuda())
+    s, i = idx.search_batch(dev(qs), excl, k)
+    if metric == "dot":
+        want_s, want_i = orc.exact_search(qs, cat, k, excl, metric="dot")
+        assert np.array_equal(i.cpu().numpy(), want_i)
+        assert np.array_equal(s.cpu().numpy(), want_s)
+    else:
+        want_s, want_i = orc.exact_search(qs, cat, k, excl, metric="cosine", dtype=np.float64)
+        got_i, got_s = i.cpu().numpy(), s.cpu().numpy()
+        # normalisation is not exact arithmetic: require the same scores, and identical ids
+        # wherever the oracle's neighbouring scores are separated by more than fp32 noise
+        assert np.allclose(got_s, want_s, atol=2e-6)
+        gap = np.abs(np.diff(want_s, axis=1)).min(axis=1)
+        for r in range(u):
+            if gap[r] > 1e-5:
+                assert np.array_equal(got_i[r], want_i[r])
+            assert not set(got_i[r].tolist()) & set(int(x) for x in excl[r])
+
+
+def test_index_search_reference_surface(xr):
+    import datasets
+
+    rng = np.random.default_rng(9)
+    n, d = 300, 384
+    emb = rng.standard_normal((n, d)).astype(np.float32)
+    ds = datasets.Dataset.from_dict({"item_id": [f"i{j}" for j in range(n)],
+                                     "item_text": [f"text {j}" for j in range(n)],
+                                     "embedding": emb.tolist()})
+    idx = xr.index.ExactIndex(xr.index.ExactIndexConfig(dtype="fp32")).index_data(ds)
+    q = emb[17] + 0.01 * rng.standard_normal(d).astype(np.float32)
+    res = idx.search(q, exclude_item_ids=["i17", "i3", "nope"], top_k=20)
+    assert len(res) == 20 and {"item_id", "score", "item_text"} <= set(res.column_names)
+    assert "i17" not in res["item_id"] and "i3" not in res["item_id"]
+    want_s, want_i = orc.exact_search(q, emb, 20, [[17, 3]], dtype=np.float64)
+    assert res["item_id"] == [f"i{j}" for j in want_i[0]]
+    assert np.allclose(res["score"], want_s[0], atol=1e-5)
+    assert idx.get_id("i5")["item_text"] == "text 5" and idx.get_id(None) == {} and idx.get_id("zz") == {}
+    res = idx.search(q, None, top_k=400)          # more than the catalog holds
+    assert len(res) == n
+
+
+def test_retrieval_metrics_match_oracle(xr):
+    rng = np.random.default_rng(2)
+    for top_k in (1, 5, 20, 100):
+        recs, tgts = [], []
+        for _ in range(40):
+            k = int(rng.integers(0, top_k + 3))
+            rec = [int(x) for x in rng.choice(60, size=min(k, 60), replace=False)]
+            tgt = [int(x) for x in rng.choice(60, size=int(rng.integers(0, 11)), replace=False)]
+            recs.append(rec)
+            tgts.append(tgt)
+        width = max(top_k, max(len(r) for r in recs))
+        mat = torch.full((len(recs), width), -1, dtype=torch.int64)
+        for r, rec in enumerate(recs):
+            mat[r, :len(rec)] = torch.tensor(rec, dtype=torch.int64) if rec else mat[r, :0]
+        out, valid = xr.metrics.retrieval_metrics_batch(mat.cuda(), tgts, top_k)
+        out, valid = out.cpu().numpy(), valid.cpu().numpy()
+        for r, (rec, tgt) in enumerate(zip(recs, tgts)):
+            want = orc.retrieval_metrics([str(x) for x in rec], {str(x) for x in tgt}, top_k)
+            assert bool(valid[r]) == (len(want) > 0)
+            for c, name in enumerate(orc.METRIC_NAMES):
+                if want:
+                    assert out[r, c] == pytest.approx(want[name], rel=1e-6, abs=1e-7), (name, rec, tgt)
+    m = xr.metrics.compute_retrieval_metrics(["i10", "i3", "i7"], {"i3"}, top_k=3)
+    assert list(m) == orc.METRIC_NAMES and float(m["retrieval_auroc"]) == pytest.approx(0.5)
+    assert xr.metrics.compute_retrieval_metrics(["a"], set(), 3) == {}

@@ -1,0 +1,17 @@
+// Placeholder entry points used only until the tcgen05 translation units are compiled in.
+#include "common.cuh"
+extern "C" int xr_fused_available(void) { return 0; }
+extern "C" size_t xr_fused_pool_workspace_bytes(int64_t, int64_t, int64_t) { return 0; }
+extern "C" int xr_fused_pool_loss(const void*, const void*, const void*, int64_t, int64_t, int64_t,
+                                  int, const xr_loss_config*, const float*, float, float*, double*,
+                                  float*, void*, size_t, void*) {
+  xr::set_error("xr_fused_pool_loss: tcgen05 kernels not compiled into this build");
+  return XR_E_UNSUPPORTED;
+}
+extern "C" size_t xr_score_topk_workspace_bytes(int64_t, int64_t, int64_t) { return 0; }
+extern "C" int xr_score_topk(const void*, int64_t, const void*, int64_t, int64_t, const float*,
+                             const float*, int64_t, int64_t, const int64_t*, const int64_t*, float*,
+                             int64_t*, void*, size_t, void*) {
+  xr::set_error("xr_score_topk: tcgen05 kernels not compiled into this build");
+  return XR_E_UNSUPPORTED;
+}

@@ -1,0 +1,391 @@
+// The EmbedLoss pipeline on materialised logits, one thread block per row:
+//   check_target          xfmr_rec/losses.py:233-261
+//   mask_false_negatives  losses.py:283-292   (strict '<' against the target logit)
+//   mine_hard_negatives   losses.py:311-330   (exact radix select; ties -> lower index)
+//   loss() bodies         losses.py:352-372, 420-543 — all seven in one pass
+//   LogitsStatistics      losses.py:383-405   — one device block, one D2H copy instead of 9 syncs
+// plus dL/dlogits of one selected loss.  Rows stay L1/L2 resident across the passes.
+// Row sums are written to a workspace and folded by a single block in a fixed order, so the
+// results are run-to-run deterministic (no floating-point atomics).
+#include "common.cuh"
+
+namespace xr {
+
+constexpr int RL_THREADS = 256;
+constexpr int RL_WARPS = RL_THREADS / 32;
+constexpr int ROW_SLOTS = 20;  // doubles per row in the workspace
+
+enum RowSlot {
+  S_ALIGN = 0, S_CONTR, S_INFONCE, S_NCE, S_HINGE, S_LOGISTIC,  // per-row loss values
+  S_DENS, S_POS, S_NCOUNT, S_NSUM, S_NSQ, S_NMIN, S_NMAX, S_USED
+};
+
+__device__ __forceinline__ double block_sum(double v, double* s_buf) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_buf[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0.0;
+#pragma unroll
+  for (int w = 0; w < RL_WARPS; ++w) r += s_buf[w];
+  return r;
+}
+__device__ __forceinline__ float block_max(float v, float* s_buf) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_buf[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = s_buf[0];
+#pragma unroll
+  for (int w = 1; w < RL_WARPS; ++w) r = fmaxf(r, s_buf[w]);
+  return r;
+}
+__device__ __forceinline__ float block_min(float v, float* s_buf) {
+  v = warp_min(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_buf[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = s_buf[0];
+#pragma unroll
+  for (int w = 1; w < RL_WARPS; ++w) r = fminf(r, s_buf[w]);
+  return r;
+}
+
+__device__ __forceinline__ float softplusf(float x) {
+  return fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x)));
+}
+__device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+__global__ void __launch_bounds__(RL_THREADS)
+rowloss_kernel(const float* __restrict__ logits, int64_t m, int64_t c, int64_t ld, int target_mode,
+               const int64_t* __restrict__ target, xr_loss_config cfg, uint32_t loss_mask,
+               int grad_kind, float grad_scale, float* __restrict__ dlogits,
+               double* __restrict__ row_out /* [m][ROW_SLOTS] */,
+               uint8_t* __restrict__ maskbuf /* [gridDim.x][c] when hard mining */,
+               int32_t* __restrict__ err_flag) {
+  __shared__ double s_d[RL_WARPS];
+  __shared__ float s_f[RL_WARPS];
+  __shared__ unsigned s_hist[256];
+  __shared__ unsigned s_sel[4];  // prefix key, remaining quota, scratch
+  __shared__ int s_warp_cnt[RL_WARPS];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool round_bf16 = cfg.logits_bf16 != 0;
+  const float scale = cfg.scale, margin = cfg.margin;
+  const bool hard = cfg.num_hard_negatives > 0 && (int64_t)cfg.num_hard_negatives < c;
+  uint8_t* mrow = hard ? maskbuf + (int64_t)blockIdx.x * c : nullptr;
+
+  for (int64_t i = blockIdx.x; i < m; i += gridDim.x) {
+    const float* lrow = logits + i * ld;
+    int64_t ti = 0;
+    if (target_mode == XR_TARGET_DIAGONAL) ti = i;
+    else if (target_mode == XR_TARGET_EXPLICIT) ti = target[i];
+    else if (target_mode == 3 /* last */) ti = c - 1;
+    if (ti < 0 || ti >= c) {  // torch.gather would raise; flag it and keep memory safe
+      if (tid == 0 && err_flag) *err_flag = 1;
+      ti = 0;
+    }
+    auto val = [&](int64_t j) -> float {
+      const float v = lrow[j];
+      return round_bf16 ? bf16_round(v) : v;
+    };
+    const float t = val(ti);
+    auto valid0 = [&](int64_t j, float v) -> bool {
+      return cfg.mask_false_negatives ? (v < t) : (j != ti);
+    };
+
+    // ---- hard-negative mining: exact top-n_hard of the valid negatives ------------------------
+    if (hard) {
+      // count valid negatives first; if they fit, every valid negative survives (:326-328)
+      int cnt = 0;
+      for (int64_t j = tid; j < c; j += RL_THREADS) cnt += valid0(j, val(j));
+      const double nvalid = block_sum((double)cnt, s_d);
+      if (nvalid <= (double)cfg.num_hard_negatives) {
+        for (int64_t j = tid; j < c; j += RL_THREADS) mrow[j] = valid0(j, val(j));
+      } else {
+        // MSB-first radix select of the n_hard-th largest key among valid negatives
+        unsigned prefix = 0, prefix_mask = 0, want = (unsigned)cfg.num_hard_negatives;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+          for (int b = tid; b < 256; b += RL_THREADS) s_hist[b] = 0;
+          __syncthreads();
+          for (int64_t j = tid; j < c; j += RL_THREADS) {
+            const float v = val(j);
+            if (!valid0(j, v)) continue;
+            const unsigned k = float_key(v);
+            if ((k & prefix_mask) == prefix) atomicAdd(&s_hist[(k >> shift) & 255u], 1u);
+          }
+          __syncthreads();
+          if (tid == 0) {
+            unsigned acc = 0;
+            int b = 255;
+            for (; b > 0; --b) {
+              if (acc + s_hist[b] >= want) break;
+              acc += s_hist[b];
+            }
+            s_sel[0] = (unsigned)b;
+            s_sel[1] = want - acc;  // still to take inside bucket b
+          }
+          __syncthreads();
+          prefix |= s_sel[0] << shift;
+          prefix_mask |= 255u << shift;
+          want = s_sel[1];
+          __syncthreads();
+        }
+        // keys > prefix all survive; of the keys == prefix the first `want` by index survive
+        const unsigned tau = prefix;
+        int64_t taken = 0;  // equals taken so far (uniform across the block)
+        for (int64_t base = 0; base < c; base += RL_THREADS) {
+          const int64_t j = base + tid;
+          bool v0 = false, eq = false, gt = false;
+          if (j < c) {
+            const float v = val(j);
+            v0 = valid0(j, v);
+            const unsigned k = float_key(v);
+            eq = v0 && k == tau;
+            gt = v0 && k > tau;
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, eq);
+          if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+          __syncthreads();
+          int before = 0, total = 0;
+#pragma unroll
+          for (int w = 0; w < RL_WARPS; ++w) {
+            if (w < warp) before += s_warp_cnt[w];
+            total += s_warp_cnt[w];
+          }
+          const int64_t rank = taken + before + __popc(bal & ((1u << lane) - 1u));
+          if (j < c) mrow[j] = gt || (eq && rank < (int64_t)want);
+          taken += total;
+          __syncthreads();
+        }
+      }
+      __syncthreads();
+    }
+    auto is_valid = [&](int64_t j, float v) -> bool { return hard ? (mrow[j] != 0) : valid0(j, v); };
+
+    // ---- pass 1: count, extrema of the kept set ------------------------------------------------
+    int cnt = 0;
+    float vmax = -CUDART_INF_F, vmin = CUDART_INF_F;
+    for (int64_t j = tid; j < c; j += RL_THREADS) {
+      const float v = val(j);
+      if (is_valid(j, v)) {
+        ++cnt;
+        vmax = fmaxf(vmax, v);
+        vmin = fminf(vmin, v);
+      }
+    }
+    const double n_valid = block_sum((double)cnt, s_d);
+    const float neg_max = block_max(vmax, s_f);
+    const float neg_min = block_min(vmin, s_f);
+    auto scaled = [&](float v) -> float {
+      const float z = v * scale;
+      return round_bf16 ? bf16_round(z) : z;  // autocast: `logits * scale` is a bf16 op (:486)
+    };
+    // reference max of the softmax set {valid} U {target}
+    float zmax = scaled(t);
+    if (n_valid > 0) zmax = fmaxf(zmax, fmaxf(scaled(neg_max), scaled(neg_min)));
+    const float den = (float)n_valid + 1e-9f;
+    const float tm = t * (1.0f - margin);
+
+    // ---- pass 2: sums ----------------------------------------------------------------------------
+    double a_exp = 0, a_sp = 0, a_hinge = 0, a_logi = 0, a_dlogi = 0, a_dhinge = 0, a_contr = 0,
+           a_sum = 0, a_sq = 0;
+    for (int64_t j = tid; j < c; j += RL_THREADS) {
+      const float v = val(j);
+      if (!is_valid(j, v)) continue;
+      a_exp += (double)__expf(scaled(v) - zmax);
+      a_sp += (double)softplusf(v);
+      const float x = v - tm;
+      a_hinge += (double)fmaxf(x, 0.f);
+      a_dhinge += x > 0.f ? 1.0 : 0.0;
+      a_logi += (double)softplusf(x);
+      a_dlogi += (double)sigmoidf(x);
+      a_contr += (double)fmaxf(v - 1.0f + margin, 0.f);
+      a_sum += (double)v;
+      a_sq += (double)v * (double)v;
+    }
+    const double z_neg = block_sum(a_exp, s_d);
+    const double sum_sp = block_sum(a_sp, s_d);
+    const double sum_hinge = block_sum(a_hinge, s_d);
+    const double sum_dhinge = block_sum(a_dhinge, s_d);
+    const double sum_logi = block_sum(a_logi, s_d);
+    const double sum_dlogi = block_sum(a_dlogi, s_d);
+    const double sum_contr = block_sum(a_contr, s_d);
+    const double sum_v = block_sum(a_sum, s_d);
+    const double sum_sq = block_sum(a_sq, s_d);
+
+    const double z_all = z_neg + (double)__expf(scaled(t) - zmax);
+    const double lse = (double)zmax + log(z_all);
+    if (tid == 0) {
+      double* o = row_out + i * ROW_SLOTS;
+      o[S_ALIGN] = 1.0 - (double)t;
+      o[S_CONTR] = sum_contr / (double)den;
+      o[S_INFONCE] = lse - (double)scaled(t);
+      o[S_NCE] = (double)softplusf(-t) + sum_sp / (double)den;
+      o[S_HINGE] = sum_hinge / (double)den;
+      o[S_LOGISTIC] = sum_logi / (double)den;
+      o[S_DENS] = n_valid;
+      o[S_POS] = (double)t;
+      o[S_NCOUNT] = n_valid;
+      o[S_NSUM] = sum_v;
+      o[S_NSQ] = sum_sq;
+      o[S_NMIN] = (double)neg_min;
+      o[S_NMAX] = (double)neg_max;
+    }
+
+    // ---- pass 3: dL/dlogits of the selected loss ------------------------------------------------
+    if (dlogits && grad_kind >= 0) {
+      float* grow = dlogits + i * ld;
+      const float inv_den = 1.0f / den;
+      const float inv_z = (float)(1.0 / z_all);
+      for (int64_t j = tid; j < c; j += RL_THREADS) {
+        const float v = val(j);
+        const bool ok = is_valid(j, v);
+        float g = 0.f;
+        switch (grad_kind) {
+          case XR_LOSS_INFONCE:
+            if (ok || j == ti) g = scale * (__expf(scaled(v) - zmax) * inv_z - (j == ti ? 1.f : 0.f));
+            break;
+          case XR_LOSS_NCE:
+            if (ok) g = sigmoidf(v) * inv_den;
+            if (j == ti) g += -sigmoidf(-t);
+            break;
+          case XR_LOSS_PAIRWISE_HINGE:
+            if (ok) g = (v - tm > 0.f) ? inv_den : 0.f;
+            if (j == ti) g += -(1.0f - margin) * (float)sum_dhinge * inv_den;
+            break;
+          case XR_LOSS_PAIRWISE_LOGISTIC:
+            if (ok) g = sigmoidf(v - tm) * inv_den;
+            if (j == ti) g += -(1.0f - margin) * (float)sum_dlogi * inv_den;
+            break;
+          case XR_LOSS_ALIGNMENT:
+            if (j == ti) g = -1.f;
+            break;
+          case XR_LOSS_CONTRASTIVE:
+          case XR_LOSS_ALIGNMENT_CONTRASTIVE:
+            if (ok) g = (v - 1.0f + margin > 0.f) ? inv_den : 0.f;
+            if (grad_kind == XR_LOSS_ALIGNMENT_CONTRASTIVE && j == ti) g += -1.f;
+            break;
+          default:
+            break;
+        }
+        grow[j] = g * grad_scale;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// single block, fixed order: fold the per-row slots into the 7 loss sums and the stats block
+__global__ void __launch_bounds__(1024)
+rowloss_reduce_kernel(const double* __restrict__ row_out, int64_t m, int64_t c, int n_hard,
+                      double* __restrict__ losses_out, double* __restrict__ stats_out) {
+  constexpr int NS = 13;  // 6 losses + dens + pos sum + pos sq + ncount + nsum + nsq + (min/max apart)
+  __shared__ double s_sum[32][NS];
+  __shared__ double s_mm[32][4];
+  double acc[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) acc[k] = 0.0;
+  double pmin = CUDART_INF, pmax = -CUDART_INF, nmin = CUDART_INF, nmax = -CUDART_INF;
+  double num_neg = (double)(c - 1);
+  if (n_hard > 0 && (double)n_hard < num_neg) num_neg = (double)n_hard;  // losses.py:387-389
+  for (int64_t i = threadIdx.x; i < m; i += blockDim.x) {
+    const double* o = row_out + i * ROW_SLOTS;
+    acc[0] += o[S_ALIGN]; acc[1] += o[S_CONTR]; acc[2] += o[S_INFONCE]; acc[3] += o[S_NCE];
+    acc[4] += o[S_HINGE]; acc[5] += o[S_LOGISTIC];
+    acc[6] += o[S_DENS] / (num_neg + 1e-9);
+    acc[7] += o[S_POS]; acc[8] += o[S_POS] * o[S_POS];
+    acc[9] += o[S_NCOUNT]; acc[10] += o[S_NSUM]; acc[11] += o[S_NSQ];
+    pmin = fmin(pmin, o[S_POS]); pmax = fmax(pmax, o[S_POS]);
+    if (o[S_NCOUNT] > 0) { nmin = fmin(nmin, o[S_NMIN]); nmax = fmax(nmax, o[S_NMAX]); }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NS; ++k) acc[k] = warp_sum(acc[k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    pmin = fmin(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
+    pmax = fmax(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+    nmin = fmin(nmin, __shfl_xor_sync(0xffffffffu, nmin, o));
+    nmax = fmax(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) s_sum[warp][k] = acc[k];
+    s_mm[warp][0] = pmin; s_mm[warp][1] = pmax; s_mm[warp][2] = nmin; s_mm[warp][3] = nmax;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot[NS];
+    for (int k = 0; k < NS; ++k) tot[k] = 0.0;
+    const int nw = blockDim.x >> 5;
+    for (int w = 0; w < nw; ++w) {
+      for (int k = 0; k < NS; ++k) tot[k] += s_sum[w][k];
+      pmin = fmin(pmin, s_mm[w][0]); pmax = fmax(pmax, s_mm[w][1]);
+      nmin = fmin(nmin, s_mm[w][2]); nmax = fmax(nmax, s_mm[w][3]);
+    }
+    if (losses_out) {
+      losses_out[XR_LOSS_ALIGNMENT] = tot[0];
+      losses_out[XR_LOSS_CONTRASTIVE] = tot[1];
+      losses_out[XR_LOSS_ALIGNMENT_CONTRASTIVE] = tot[0] + tot[1];
+      losses_out[XR_LOSS_INFONCE] = tot[2];
+      losses_out[XR_LOSS_NCE] = tot[3];
+      losses_out[XR_LOSS_PAIRWISE_HINGE] = tot[4];
+      losses_out[XR_LOSS_PAIRWISE_LOGISTIC] = tot[5];
+    }
+    if (stats_out) {
+      stats_out[0] = tot[6];
+      stats_out[1] = (double)m;
+      stats_out[2] = tot[7]; stats_out[3] = tot[8]; stats_out[4] = pmin; stats_out[5] = pmax;
+      stats_out[6] = tot[9]; stats_out[7] = tot[10]; stats_out[8] = tot[11];
+      stats_out[9] = nmin; stats_out[10] = nmax; stats_out[11] = num_neg;
+      for (int k = 12; k < XR_STATS_SLOTS; ++k) stats_out[k] = 0.0;
+    }
+  }
+}
+
+static inline int rl_grid(int64_t m) {
+  const int64_t cap = (int64_t)sm_count() * 8;
+  return (int)(m < cap ? (m < 1 ? 1 : m) : cap);
+}
+
+}  // namespace xr
+
+using namespace xr;
+
+extern "C" size_t xr_rowloss_workspace_bytes(int64_t m, int64_t c, int num_hard_negatives) {
+  size_t b = (size_t)(m > 0 ? m : 1) * ROW_SLOTS * sizeof(double) + 256;
+  if (num_hard_negatives > 0 && num_hard_negatives < c)
+    b += (size_t)rl_grid(m) * (size_t)c + 256;
+  return b;
+}
+
+extern "C" int xr_rowloss(const float* logits, int64_t m, int64_t c, int64_t ld, int target_mode,
+                          const int64_t* target, const xr_loss_config* cfg, uint32_t loss_mask,
+                          int grad_kind, float grad_scale, float* dlogits, double* losses_out,
+                          double* stats_out, int32_t* err_flag, void* workspace, void* stream) {
+  XR_CHECK_ARG(logits && cfg && workspace, "xr_rowloss: null pointer");
+  XR_CHECK_ARG(m >= 0 && c >= 1 && ld >= c, "xr_rowloss: bad sizes (m=%lld c=%lld ld=%lld)",
+               (long long)m, (long long)c, (long long)ld);
+  XR_CHECK_ARG(target_mode >= 0 && target_mode <= 3, "xr_rowloss: bad target_mode");
+  XR_CHECK_ARG(target_mode != XR_TARGET_EXPLICIT || target, "xr_rowloss: explicit target is null");
+  XR_CHECK_ARG(target_mode != XR_TARGET_DIAGONAL || m <= c,
+               "xr_rowloss: diagonal targets need num_candidates >= batch");
+  XR_CHECK_ARG(grad_kind < XR_NUM_LOSSES, "xr_rowloss: bad grad_kind");
+  XR_CHECK_ARG(grad_kind < 0 || dlogits, "xr_rowloss: dlogits is null");
+  cudaStream_t s = as_stream(stream);
+  double* row_out = (double*)workspace;
+  uint8_t* maskbuf = (uint8_t*)workspace + (((size_t)(m > 0 ? m : 1) * ROW_SLOTS * sizeof(double) + 255) / 256) * 256;
+  if (m > 0) {
+    rowloss_kernel<<<rl_grid(m), RL_THREADS, 0, s>>>(logits, m, c, ld, target_mode, target, *cfg,
+                                                     loss_mask, grad_kind, grad_scale, dlogits,
+                                                     row_out, maskbuf, err_flag);
+    XR_LAUNCH_CHECK("rowloss");
+  }
+  if (losses_out || stats_out) {
+    rowloss_reduce_kernel<<<1, 1024, 0, s>>>(row_out, m, c, cfg->num_hard_negatives, losses_out,
+                                             stats_out);
+    XR_LAUNCH_CHECK("rowloss_reduce");
+  }
+  return XR_OK;
+}

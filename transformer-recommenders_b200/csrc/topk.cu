@@ -1,0 +1,380 @@
+// Family 3: exact top-k under the total order (score descending, column ascending).
+//
+// This is the exact computation that the reference's ANN search approximates
+// (xfmr_rec/index.py:244-251 `.limit(top_k)`, :465-467) with the north_star tie rule
+// "ties broken by lower item id" (oracle: stable descending sort).
+//
+// HBM-bound design: every score is read ONCE with 128-bit loads.  A block streams one chunk
+// of one row; a score is appended to a shared-memory candidate buffer only if its 64-bit key
+//     key = (order_preserving(score) << 32) | (0xFFFFFFFF - column)
+// beats the block's running k-th best key, so after a short warm-up almost no element leaves
+// the compare.  When the buffer fills, a bitonic sort keeps the best k and raises the
+// threshold.  Chunks of a row are merged by the same kernel running over the partial keys.
+// Selection on a strict total order makes single-GPU, chunked and sharded results identical.
+#include "common.cuh"
+
+namespace xr {
+
+constexpr int TK_THREADS = 256;
+constexpr int TK_CAP = 2048;        // candidate buffer (keys)
+constexpr int TK_PER_ITER = 1024;   // worst-case appends per iteration
+constexpr int TK_MAX_K = TK_CAP - TK_PER_ITER;
+
+__device__ __forceinline__ uint64_t make_key(float score, uint32_t col) {
+  return ((uint64_t)float_key(score) << 32) | (uint64_t)(0xFFFFFFFFu - col);
+}
+
+// descending bitonic sort of s_keys[0..n2) (n2 = power of two), all threads of the block
+__device__ __forceinline__ void bitonic_desc(uint64_t* s_keys, int n2) {
+  for (int k2 = 2; k2 <= n2; k2 <<= 1) {
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n2; i += TK_THREADS) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const uint64_t a = s_keys[i], b = s_keys[ixj];
+          const bool desc = (i & k2) == 0;
+          if (desc ? (a < b) : (a > b)) {
+            s_keys[i] = b;
+            s_keys[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+struct TopkState {
+  uint64_t* keys;   // [TK_CAP] shared
+  int* count;       // shared
+  uint64_t* tau;    // shared: current k-th best key (0 = accept everything)
+};
+
+// keep the best k of the buffered keys, update the threshold; block-uniform call
+__device__ __forceinline__ void compact(const TopkState& st, int k) {
+  __syncthreads();
+  const int n = *st.count;
+  int n2 = 2;
+  while (n2 < n) n2 <<= 1;
+  for (int i = n + threadIdx.x; i < n2; i += TK_THREADS) st.keys[i] = 0ull;
+  __syncthreads();
+  bitonic_desc(st.keys, n2);
+  if (threadIdx.x == 0) {
+    if (n >= k) {
+      *st.count = k;
+      *st.tau = st.keys[k - 1];
+    }
+  }
+  __syncthreads();
+}
+
+// warp-aggregated append of keys that beat the threshold
+__device__ __forceinline__ void offer(const TopkState& st, bool take, uint64_t key) {
+  const unsigned bal = __ballot_sync(0xffffffffu, take);
+  if (bal == 0) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(st.count, __popc(bal));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (take) st.keys[base + __popc(bal & ((1u << lane) - 1u))] = key;
+}
+
+// SRC 0: fp32 scores (vectorised when VEC), 1: uint64 keys, 2: fp32 scores + int64 ids
+template <int SRC, bool VEC>
+__global__ void __launch_bounds__(TK_THREADS)
+topk_stream_kernel(const float* __restrict__ scores, const int64_t* __restrict__ ids,
+                   const uint64_t* __restrict__ in_keys, int64_t n, int64_t ld, int64_t chunk_len,
+                   int k, uint64_t* __restrict__ out_keys /* [u][P][k] */) {
+  __shared__ uint64_t s_keys[TK_CAP];
+  __shared__ int s_count;
+  __shared__ uint64_t s_tau;
+  TopkState st{s_keys, &s_count, &s_tau};
+  const int64_t u = blockIdx.y, p = blockIdx.x, P = gridDim.x;
+  const int64_t lo = p * chunk_len;
+  const int64_t hi = lo + chunk_len < n ? lo + chunk_len : n;
+  if (threadIdx.x == 0) {
+    s_count = 0;
+    s_tau = 0ull;
+  }
+  __syncthreads();
+
+  const int64_t len = hi > lo ? hi - lo : 0;
+  const int64_t iters = (len + TK_PER_ITER - 1) / TK_PER_ITER;
+  const float* srow = SRC != 1 ? scores + u * ld : nullptr;
+  const int64_t* irow = SRC == 2 ? ids + u * ld : nullptr;
+  const uint64_t* krow = SRC == 1 ? in_keys + u * ld : nullptr;
+
+  float4 cur = make_float4(0, 0, 0, 0), nxt = cur;
+  auto load_vec = [&](int64_t it) -> float4 {
+    const int64_t e = lo + it * TK_PER_ITER + (int64_t)threadIdx.x * 4;
+    if (e + 3 < hi) {
+      const int4 r = ld_stream16(srow + e);
+      return make_float4(__int_as_float(r.x), __int_as_float(r.y), __int_as_float(r.z),
+                         __int_as_float(r.w));
+    }
+    float4 v;
+    v.x = e + 0 < hi ? srow[e + 0] : 0.f;
+    v.y = e + 1 < hi ? srow[e + 1] : 0.f;
+    v.z = e + 2 < hi ? srow[e + 2] : 0.f;
+    v.w = e + 3 < hi ? srow[e + 3] : 0.f;
+    return v;
+  };
+  if (SRC == 0 && VEC && iters > 0) cur = load_vec(0);
+
+  for (int64_t it = 0; it < iters; ++it) {
+    // make room: an iteration can append at most TK_PER_ITER keys (block-uniform branch)
+    if (s_count > TK_CAP - TK_PER_ITER) compact(st, k);
+    const uint64_t tau = s_tau;
+    const uint32_t tau_hi = (uint32_t)(tau >> 32);
+    if (SRC == 0 && VEC) {
+      if (it + 1 < iters) nxt = load_vec(it + 1);  // keep the next 16 B in flight
+      const int64_t e = lo + it * TK_PER_ITER + (int64_t)threadIdx.x * 4;
+      const float v[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const bool in = e + r < hi;
+        const uint32_t fk = float_key(v[r]);
+        uint64_t key = 0;
+        bool take = in && fk >= tau_hi;
+        if (take) {
+          key = ((uint64_t)fk << 32) | (uint64_t)(0xFFFFFFFFu - (uint32_t)(e + r));
+          take = key > tau;
+        }
+        offer(st, take, key);
+      }
+      cur = nxt;
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int64_t e = lo + it * TK_PER_ITER + r * TK_THREADS + threadIdx.x;
+        const bool in = e < hi;
+        uint64_t key = 0;
+        if (in) {
+          if (SRC == 0) key = make_key(srow[e], (uint32_t)e);
+          else if (SRC == 1) key = krow[e];
+          else {
+            const int64_t id = irow[e];
+            key = id < 0 ? 0ull : make_key(srow[e], (uint32_t)id);
+          }
+        }
+        offer(st, in && key > tau, key);
+      }
+    }
+    __syncthreads();
+  }
+  compact(st, k);
+  // after compact(): keys sorted descending, zero padded up to a power of two >= count
+  const int cnt = s_count < k ? s_count : k;
+  uint64_t* o = out_keys + (u * P + p) * (int64_t)k;
+  for (int i = threadIdx.x; i < k; i += TK_THREADS) o[i] = i < cnt ? s_keys[i] : 0ull;
+}
+
+__global__ void topk_emit_kernel(const uint64_t* __restrict__ keys, int64_t total,
+                                 int64_t col_offset, float* __restrict__ out_scores,
+                                 int64_t* __restrict__ out_idx) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t key = keys[i];
+    if (key == 0ull) {
+      out_scores[i] = -CUDART_INF_F;
+      out_idx[i] = -1;
+    } else {
+      out_scores[i] = key_float((uint32_t)(key >> 32));
+      out_idx[i] = (int64_t)(0xFFFFFFFFu - (uint32_t)key) + col_offset;
+    }
+  }
+}
+
+// one warp per query row: scores[u, id - col_offset] = -inf for the row's exclusion list
+__global__ void mask_excluded_kernel(float* __restrict__ scores, int64_t u, int64_t n, int64_t ld,
+                                     int64_t col_offset, const int64_t* __restrict__ offs,
+                                     const int64_t* __restrict__ ids) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < u; r += nwarps) {
+    for (int64_t e = offs[r] + lane; e < offs[r + 1]; e += 32) {
+      const int64_t col = ids[e] - col_offset;
+      if (col >= 0 && col < n) scores[r * ld + col] = -CUDART_INF_F;
+    }
+  }
+}
+
+// ---- retrieval metrics: metrics.py:62-79, one thread per user ---------------------------------
+__global__ void retrieval_metrics_kernel(const int64_t* __restrict__ rec, int64_t u, int64_t k,
+                                         const int64_t* __restrict__ toffs,
+                                         const int64_t* __restrict__ tids, int64_t top_k,
+                                         float* __restrict__ out, uint8_t* __restrict__ valid) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= u) return;
+  const int64_t t0 = toffs[r], t1 = toffs[r + 1];
+  // number of DISTINCT targets (metrics.py:70 builds a set)
+  int n_total = 0;
+  for (int64_t a = t0; a < t1; ++a) {
+    bool dup = false;
+    for (int64_t b = t0; b < a; ++b) dup |= (tids[b] == tids[a]);
+    n_total += !dup;
+  }
+  float* o = out + r * 7;
+  if (n_total == 0) {  // metrics.py:62-63 returns {}
+    valid[r] = 0;
+    for (int j = 0; j < 7; ++j) o[j] = 0.f;
+    return;
+  }
+  valid[r] = 1;
+  // ranked list = rec padded to top_k (:65-68) followed by the targets it missed (:72); only the
+  // first top_k positions matter, and a missed target can enter them only when k < top_k is
+  // padded — padding ("" items) never hits, so hits come from rec[0..min(k,top_k)) alone.
+  const int64_t kk = k < top_k ? k : top_k;
+  double dcg = 0.0, ap_acc = 0.0, rr = 0.0;
+  int n_hit = 0;
+  long long pairs = 0;  // (hit before miss) pairs for the AUROC
+  int misses_seen = 0;
+  for (int64_t p = 0; p < kk; ++p) {
+    const int64_t id = rec[r * k + p];
+    bool hit = false;
+    if (id >= 0)
+      for (int64_t a = t0; a < t1; ++a) hit |= (tids[a] == id);
+    if (hit) {
+      ++n_hit;
+      dcg += 1.0 / log2((double)p + 2.0);
+      ap_acc += (double)n_hit / (double)(p + 1);
+      if (rr == 0.0) rr = 1.0 / (double)(p + 1);
+    } else {
+      ++misses_seen;
+    }
+  }
+  // AUROC over the top_k positions: fraction of (hit, miss) pairs ranked hit-first
+  const int n_miss = (int)top_k - n_hit;  // padded tail positions are misses
+  {
+    int misses_before = 0;
+    long long hits_after_miss = 0;
+    for (int64_t p = 0; p < kk; ++p) {
+      const int64_t id = rec[r * k + p];
+      bool hit = false;
+      if (id >= 0)
+        for (int64_t a = t0; a < t1; ++a) hit |= (tids[a] == id);
+      if (hit) hits_after_miss += misses_before;
+      else ++misses_before;
+    }
+    pairs = (long long)n_hit * (long long)n_miss - hits_after_miss;
+  }
+  double idcg = 0.0;
+  const int ideal = n_total < (int)top_k ? n_total : (int)top_k;
+  for (int p = 0; p < ideal; ++p) idcg += 1.0 / log2((double)p + 2.0);
+  o[0] = (float)(idcg > 0 ? dcg / idcg : 0.0);
+  o[1] = (float)(n_hit > 0 ? ap_acc / n_hit : 0.0);
+  o[2] = (float)((n_hit == 0 || n_miss == 0) ? 0.0 : (double)pairs / ((double)n_hit * n_miss));
+  o[3] = (float)((double)n_hit / (double)top_k);
+  o[4] = (float)((double)n_hit / (double)n_total);
+  o[5] = n_hit > 0 ? 1.f : 0.f;
+  o[6] = (float)rr;
+  (void)misses_seen;
+}
+
+static int pick_chunks(int64_t u, int64_t n) {
+  // enough blocks for ~4 per SM, but chunks no shorter than 16k scores
+  int64_t want = ((int64_t)sm_count() * 4 + u - 1) / (u > 0 ? u : 1);
+  int64_t maxp = (n + 16383) / 16384;
+  if (want > maxp) want = maxp;
+  if (want < 1) want = 1;
+  if (want > 4096) want = 4096;
+  return (int)want;
+}
+
+}  // namespace xr
+
+using namespace xr;
+
+extern "C" size_t xr_topk_workspace_bytes(int64_t u, int64_t n, int64_t k) {
+  const int P = pick_chunks(u, n);
+  // stage-1 partial keys + final keys
+  return (size_t)(u > 0 ? u : 1) * (size_t)(P + 1) * (size_t)k * sizeof(uint64_t) + 256;
+}
+
+extern "C" int xr_topk(const float* scores, int64_t u, int64_t n, int64_t ld, int64_t k,
+                       int64_t col_offset, float* out_scores, int64_t* out_idx, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  XR_CHECK_ARG(scores && out_scores && out_idx && workspace, "xr_topk: null pointer");
+  XR_CHECK_ARG(u >= 0 && n >= 0 && ld >= n, "xr_topk: bad sizes");
+  XR_CHECK_ARG(k >= 1 && k <= TK_MAX_K, "xr_topk: k must be in [1, %d]", TK_MAX_K);
+  XR_CHECK_ARG(n < (1ll << 32) && u <= 65535, "xr_topk: n must be < 2^32 and u <= 65535 per call");
+  XR_CHECK_ARG(workspace_bytes >= xr_topk_workspace_bytes(u, n, k), "xr_topk: workspace too small");
+  if (u == 0) return XR_OK;
+  cudaStream_t s = as_stream(stream);
+  const int P = pick_chunks(u, n);
+  int64_t chunk = (n + P - 1) / P;
+  chunk = (chunk + 3) / 4 * 4;  // chunk starts stay 16-byte aligned
+  if (chunk < 4) chunk = 4;
+  uint64_t* partial = (uint64_t*)workspace;
+  uint64_t* final_keys = partial + (size_t)u * P * k;
+  const bool vec = ((uintptr_t)scores % 16 == 0) && (ld % 4 == 0);
+  dim3 grid((unsigned)P, (unsigned)u);
+  uint64_t* stage1_out = P == 1 ? final_keys : partial;
+  if (vec)
+    topk_stream_kernel<0, true><<<grid, TK_THREADS, 0, s>>>(scores, nullptr, nullptr, n, ld, chunk,
+                                                            (int)k, stage1_out);
+  else
+    topk_stream_kernel<0, false><<<grid, TK_THREADS, 0, s>>>(scores, nullptr, nullptr, n, ld,
+                                                             chunk, (int)k, stage1_out);
+  XR_LAUNCH_CHECK("topk_stream");
+  if (P > 1) {
+    const int64_t pk = (int64_t)P * k;
+    topk_stream_kernel<1, false><<<dim3(1, (unsigned)u), TK_THREADS, 0, s>>>(
+        nullptr, nullptr, partial, pk, pk, pk, (int)k, final_keys);
+    XR_LAUNCH_CHECK("topk_merge_chunks");
+  }
+  const int64_t total = u * k;
+  topk_emit_kernel<<<(unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0,
+                     s>>>(final_keys, total, col_offset, out_scores, out_idx);
+  XR_LAUNCH_CHECK("topk_emit");
+  return XR_OK;
+}
+
+extern "C" size_t xr_topk_merge_workspace_bytes(int64_t u, int64_t k) {
+  return (size_t)(u > 0 ? u : 1) * (size_t)k * sizeof(uint64_t) + 256;
+}
+
+extern "C" int xr_topk_merge(const float* scores, const int64_t* ids, int64_t u, int64_t gk,
+                             int64_t k, float* out_scores, int64_t* out_idx, void* workspace,
+                             void* stream) {
+  XR_CHECK_ARG(scores && ids && out_scores && out_idx && workspace, "xr_topk_merge: null pointer");
+  XR_CHECK_ARG(u >= 0 && gk >= 0 && k >= 1 && k <= TK_MAX_K && u <= 65535,
+               "xr_topk_merge: bad sizes");
+  if (u == 0) return XR_OK;
+  cudaStream_t s = as_stream(stream);
+  uint64_t* final_keys = (uint64_t*)workspace;
+  topk_stream_kernel<2, false><<<dim3(1, (unsigned)u), TK_THREADS, 0, s>>>(
+      scores, ids, nullptr, gk, gk, gk > 0 ? gk : 1, (int)k, final_keys);
+  XR_LAUNCH_CHECK("topk_merge");
+  const int64_t total = u * k;
+  topk_emit_kernel<<<(unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0,
+                     s>>>(final_keys, total, 0, out_scores, out_idx);
+  XR_LAUNCH_CHECK("topk_emit");
+  return XR_OK;
+}
+
+extern "C" int xr_mask_excluded(float* scores, int64_t u, int64_t n, int64_t ld,
+                                int64_t col_offset, const int64_t* excl_offsets,
+                                const int64_t* excl_ids, void* stream) {
+  XR_CHECK_ARG(scores && excl_offsets && (excl_ids || u == 0), "xr_mask_excluded: null pointer");
+  if (u == 0) return XR_OK;
+  int64_t blocks = (u * 32 + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+  mask_excluded_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+      scores, u, n, ld, col_offset, excl_offsets, excl_ids);
+  XR_LAUNCH_CHECK("mask_excluded");
+  return XR_OK;
+}
+
+extern "C" int xr_retrieval_metrics(const int64_t* rec, int64_t u, int64_t k,
+                                    const int64_t* tgt_offsets, const int64_t* tgt_ids,
+                                    int64_t top_k, float* out, uint8_t* valid, void* stream) {
+  XR_CHECK_ARG(rec && tgt_offsets && out && valid, "xr_retrieval_metrics: null pointer");
+  XR_CHECK_ARG(u >= 0 && k >= 0 && top_k >= 1, "xr_retrieval_metrics: bad sizes");
+  if (u == 0) return XR_OK;
+  retrieval_metrics_kernel<<<(unsigned)((u + 127) / 128), 128, 0, as_stream(stream)>>>(
+      rec, u, k, tgt_offsets, tgt_ids, top_k, out, valid);
+  XR_LAUNCH_CHECK("retrieval_metrics");
+  return XR_OK;
+}

@@ -1,0 +1,30 @@
+"""xfmr_rec_b200 — B200-native scoring-and-loss / full-catalog top-k path of
+yxtay/transformer-recommenders behind the reference's own Python interfaces.
+
+    losses   mirror of xfmr_rec/losses.py      (LossConfig, 7 losses, LogitsStatistics, registry)
+    models   compute_embeds of xfmr_rec/models.py:366-419 without the O(M^2 D) candidate copy
+    index    exact full-catalog search with the LanceIndex.search surface (index.py:214-255)
+    metrics  compute_retrieval_metrics of xfmr_rec/metrics.py:17-79 (+ batched device version)
+    dist     catalog sharding + NCCL all-gather merge, data-parallel loss reduction
+    ops      tensor-level wrappers over the C ABI (include/xfmr_b200.h)
+"""
+
+from . import _native, ops  # noqa: F401
+from .losses import (  # noqa: F401
+    LOSS_CLASSES,
+    AlignmentContrastiveLoss,
+    AlignmentLoss,
+    ContrastiveLoss,
+    EmbedLoss,
+    InfoNCELoss,
+    LogitsStatistics,
+    LossConfig,
+    LossType,
+    NCELoss,
+    PairwiseHingeLoss,
+    PairwiseLogisticLoss,
+    PoolCandidates,
+    SampledCandidates,
+)
+
+__version__ = "0.1.0"

@@ -1,0 +1,188 @@
+"""Exact full-catalog retrieval behind the ``LanceIndex`` surface of ``xfmr_rec/index.py``.
+
+The reference's ``search`` is an approximate IVF_HNSW_PQ query in LanceDB (index.py:194-200,
+244-251) or Faiss (index.py:422, 465-467).  This index computes the exact result those
+structures approximate: cosine (default, index.py:47) or inner-product scores of the query
+against EVERY catalog row, history ids filtered out before ranking (index.py:239-247),
+top-k by (score descending, catalog row ascending), ``score = 1 - distance`` = the cosine
+itself (index.py:252-254).  Index construction, FTS / scalar indexes and the Lance storage
+format are out of scope.
+"""
+
+from __future__ import annotations
+
+import json
+import pathlib
+from typing import Any, Literal
+
+import numpy as np
+import pydantic
+import torch
+
+from . import ops
+from .params import TOP_K
+
+
+class ExactIndexConfig(pydantic.BaseModel):
+    """Column names follow ``LanceIndexConfig`` (index.py:23-47)."""
+
+    id_col: str = "item_id"
+    embedding_col: str | None = "embedding"
+    text_col: str = "item_text"
+    index_metric: Literal["dot", "cosine"] = "cosine"
+    dtype: Literal["bf16", "fp32"] = "bf16"
+    max_score_bytes: int = 1 << 30  # materialised-score budget of the unfused path
+
+
+class ExactIndex:
+    def __init__(self, config: ExactIndexConfig | None = None, device=None, *, row_offset: int = 0):
+        self.config = config or ExactIndexConfig()
+        self.device = torch.device(device) if device is not None else None
+        self.ids: list[str] | None = None
+        self.id2row: dict[str, int] | None = None
+        self.catalog: torch.Tensor | None = None  # (N, D), rows normalised for the cosine metric
+        self.columns: dict[str, list] = {}
+        self.row_offset = row_offset  # global row of local row 0 (catalog shards)
+
+    # -- construction -------------------------------------------------------------------------
+    def index_data(self, dataset, *, overwrite: bool = False) -> "ExactIndex":
+        """Accepts a HuggingFace ``datasets.Dataset`` (as index.py:135-137) or any mapping of
+        column name -> sequence."""
+        if self.catalog is not None and not overwrite:
+            return self
+        cfg = self.config
+        get = (lambda c: dataset[c][:]) if hasattr(dataset, "column_names") else (lambda c: dataset[c])
+        names = list(dataset.column_names) if hasattr(dataset, "column_names") else list(dataset.keys())
+        self.ids = [str(x) for x in get(cfg.id_col)]
+        self.id2row = {k: i for i, k in enumerate(self.ids)}
+        self.columns = {c: list(get(c)) for c in names if c not in (cfg.id_col, cfg.embedding_col)}
+        emb = get(cfg.embedding_col)
+        emb = emb if isinstance(emb, torch.Tensor) else torch.as_tensor(np.asarray(emb, dtype=np.float32))
+        return self.set_catalog(emb)
+
+    def set_catalog(self, embeddings: torch.Tensor) -> "ExactIndex":
+        """Install a (N, D) embedding matrix directly (synthetic catalogs, shards)."""
+        if self.device is None:
+            self.device = embeddings.device if embeddings.is_cuda else torch.device(
+                "cuda", torch.cuda.current_device())
+        emb = embeddings.to(self.device)
+        dt = torch.bfloat16 if self.config.dtype == "bf16" else torch.float32
+        if self.config.index_metric == "cosine":
+            self.catalog, _ = ops.normalize_rows(emb, 1e-12, dt)
+        else:
+            self.catalog = emb.to(dt).contiguous()
+        if self.ids is None:
+            n = emb.size(0)
+            self.ids = None  # ids are the global row numbers; materialised lazily
+            self.id2row = None
+        return self
+
+    def __len__(self) -> int:
+        return 0 if self.catalog is None else self.catalog.size(0)
+
+    def _row_of(self, item_id) -> int | None:
+        if self.id2row is not None:
+            return self.id2row.get(str(item_id))
+        try:
+            r = int(item_id) - self.row_offset
+        except (TypeError, ValueError):
+            return None
+        return r if 0 <= r < len(self) else None
+
+    def _id_of(self, row: int) -> str:
+        return self.ids[row] if self.ids is not None else str(row + self.row_offset)
+
+    # -- search -------------------------------------------------------------------------------
+    def search_batch(self, queries: torch.Tensor, exclude_rows=None, top_k: int = TOP_K):
+        """queries (U, D) on the device; exclude_rows: per-query lists of GLOBAL catalog rows
+        (or a CSR tensor pair).  Returns (scores (U,k) fp32, rows (U,k) int64 global; -1/-inf
+        where fewer than k rows remain)."""
+        assert self.catalog is not None, "index_data / set_catalog first"
+        cat = self.catalog
+        q = queries.to(self.device)
+        if q.dim() == 1:
+            q = q[None]
+        if self.config.index_metric == "cosine":
+            q, _ = ops.normalize_rows(q.float(), 1e-12, cat.dtype)
+        else:
+            q = q.to(cat.dtype).contiguous()
+        u, n = q.size(0), cat.size(0)
+        csr = None
+        if exclude_rows is not None:
+            csr = exclude_rows if isinstance(exclude_rows, tuple) else ops._csr(exclude_rows, self.device)
+        if ops.score_topk_supported(q, cat) and top_k <= 128:
+            s, i = ops.score_topk(q, cat, top_k, exclude=csr, col_offset=self.row_offset)
+        else:
+            chunk = max(4096, min(n, self.config.max_score_bytes // (4 * max(u, 1)) // 4 * 4))
+            parts_s, parts_i = [], []
+            for lo in range(0, n, chunk):
+                blk = cat[lo:lo + chunk]
+                sc = ops.scores(q, blk)
+                if csr is not None:
+                    ops.mask_excluded(sc, blk.size(0), csr, col_offset=self.row_offset + lo)
+                ps, pi = ops.topk(sc, top_k, n=blk.size(0), col_offset=self.row_offset + lo)
+                parts_s.append(ps)
+                parts_i.append(pi)
+            if len(parts_s) == 1:
+                s, i = parts_s[0], parts_i[0]
+            else:
+                s, i = ops.topk_merge(torch.cat(parts_s, 1), torch.cat(parts_i, 1), top_k)
+        # excluded rows carry -inf: they are filtered out, never returned (index.py:246)
+        dead = s == float("-inf")
+        i = torch.where(dead, torch.full_like(i, -1), i)
+        return s, i
+
+    def search(self, embedding, exclude_item_ids: list[str] | None = None, top_k: int = TOP_K):
+        """``LanceIndex.search`` (index.py:214-255): one query vector in, a
+        ``datasets.Dataset`` with ``item_id`` / ``score`` (+ stored columns) out, rank order."""
+        import datasets
+
+        q = torch.as_tensor(np.asarray(embedding, dtype=np.float32))
+        excl = [r for r in (self._row_of(x) for x in (exclude_item_ids or [])) if r is not None]
+        excl = [r + self.row_offset for r in excl]
+        s, i = self.search_batch(q[None].to(self.device), [excl], top_k)
+        rows = [r - self.row_offset for r in i[0].tolist() if r >= 0]
+        sc = s[0].tolist()[: len(rows)]
+        out: dict[str, list] = {self.config.id_col: [self._id_of(r) for r in rows]}
+        for c, vals in self.columns.items():
+            out[c] = [vals[r] for r in rows]
+        out["_distance"] = [1.0 - x for x in sc]
+        out["score"] = sc
+        return datasets.Dataset.from_dict(out)
+
+    # -- lookups (index.py:257-292) --------------------------------------------------------------
+    def get_ids(self, ids: list[str]):
+        import datasets
+
+        rows = [r for r in (self._row_of(x) for x in ids) if r is not None]
+        out: dict[str, list] = {self.config.id_col: [self._id_of(r) for r in rows]}
+        for c, vals in self.columns.items():
+            out[c] = [vals[r] for r in rows]
+        return datasets.Dataset.from_dict(out)
+
+    def get_id(self, id_val: str | None) -> dict[str, Any]:
+        if id_val is None:
+            return {}
+        result = self.get_ids([id_val])
+        return {} if len(result) == 0 else result[0]
+
+    # -- persistence ----------------------------------------------------------------------------
+    def save(self, path: str) -> None:
+        p = pathlib.Path(path)
+        p.mkdir(parents=True, exist_ok=True)
+        torch.save({"catalog": self.catalog.cpu(), "ids": self.ids, "columns": self.columns,
+                    "row_offset": self.row_offset}, p / "exact_index.pt")
+        (p / "config.json").write_text(json.dumps(self.config.model_dump()))
+
+    @classmethod
+    def load(cls, path: str, device=None) -> "ExactIndex":
+        p = pathlib.Path(path)
+        cfg = ExactIndexConfig(**json.loads((p / "config.json").read_text()))
+        blob = torch.load(p / "exact_index.pt", weights_only=False)
+        self = cls(cfg, device, row_offset=blob["row_offset"])
+        self.device = self.device or torch.device("cuda", torch.cuda.current_device())
+        self.catalog = blob["catalog"].to(self.device)
+        self.ids = blob["ids"]
+        self.id2row = None if self.ids is None else {k: i for i, k in enumerate(self.ids)}
+        self.columns = blob["columns"]
+        return self

@@ -1,0 +1,399 @@
+"""Tensor-level wrappers over the C ABI (``include/xfmr_b200.h``).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every function
+hands raw device pointers to libxfmr_b200.so.  Inputs must live on a CUDA device — there is
+no CPU path.  The main entry points are also registered as ``torch.library`` custom ops
+(``xfmr_b200::gather_rows``, ``::pool_loss_fwd_bwd``, ``::topk``, ``::score_topk``,
+``::retrieval_metrics``) so they compose with the dispatcher / autograd machinery.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _native as N
+
+_DT = {torch.float32: N.XR_F32, torch.bfloat16: N.XR_BF16}
+
+
+def _require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise N.NativeError(
+                "xfmr_b200 kernels need CUDA tensors (got a tensor on "
+                f"{t.device}); there is no CPU fallback"
+            )
+        dev = dev or t.device
+        if t.device != dev:
+            raise N.NativeError(f"tensors on different devices: {t.device} vs {dev}")
+    return dev
+
+
+def _p(t: torch.Tensor | None):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise N.NativeError(f"unsupported dtype {t.dtype} (float32 / bfloat16 only)") from None
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def make_cfg(config, *, logits_bf16: bool = False) -> N.XrLossConfig:
+    return N.XrLossConfig(
+        int(bool(config.mask_false_negatives)),
+        int(config.num_hard_negatives),
+        float(config.scale),
+        float(config.margin),
+        int(logits_bf16),
+    )
+
+
+# ---------------------------------------------------------------------------------------------
+# family 1: gathers / compaction / normalisation
+# ---------------------------------------------------------------------------------------------
+def gather_rows(table, idx, sel=None, out_dtype=None, n_out=None, check=False):
+    """``table[idx[sel]]`` — nn.Embedding.forward of models.py:336-338/400/406 (bit-exact)."""
+    dev = _require_cuda(table, idx, sel)
+    table = table.contiguous()
+    idx = idx.contiguous()
+    assert table.dim() == 2 and idx.dtype == torch.int64
+    out_dtype = out_dtype or table.dtype
+    lead = idx.shape if sel is None else (sel.numel() if n_out is None else n_out,)
+    n = 1
+    for s in lead:
+        n *= int(s)
+    out = torch.empty((n, table.size(1)), dtype=out_dtype, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev) if check else None
+    with torch.cuda.device(dev):
+        N.call("xr_gather_rows", _p(table), table.size(0), table.size(1), _dt(table), _p(idx),
+               _p(sel), n, _p(out), _DT[out_dtype], _p(err), _stream())
+    if check and int(err.item()):
+        raise IndexError("index out of range in gather_rows")
+    return out.view(*lead, table.size(1))
+
+
+def scatter_rows(src, sel, n_dst_rows):
+    dev = _require_cuda(src, sel)
+    src = src.contiguous().float()
+    dst = torch.zeros((n_dst_rows, src.size(1)), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        N.call("xr_scatter_rows", _p(src), src.size(0), src.size(1), _p(sel), _p(dst), n_dst_rows,
+               _stream())
+    return dst
+
+
+def row_nonzero(table):
+    dev = _require_cuda(table)
+    table = table.contiguous()
+    out = torch.empty(table.size(0), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        N.call("xr_row_nonzero", _p(table), table.size(0), table.size(1), _dt(table), _p(out),
+               _stream())
+    return out
+
+
+def compact_positions(history_idx, pos_idx, rownz=None, n_table_rows=0):
+    """models.py:343/390/398/404/413-416 on the index tensors; one host sync for the counts
+    (the reference syncs twice for the same numbers, trainer.py:239-240)."""
+    dev = _require_cuda(history_idx, pos_idx, rownz)
+    h = history_idx.contiguous().view(-1)
+    p = pos_idx.contiguous().view(-1)
+    n = h.numel()
+    attn = torch.empty(n, dtype=torch.uint8, device=dev)
+    sel_attn = torch.empty(n, dtype=torch.int64, device=dev)
+    sel_pos = torch.empty(n, dtype=torch.int64, device=dev)
+    pos_mask = torch.empty(n, dtype=torch.uint8, device=dev)
+    counts = torch.zeros(2, dtype=torch.int64, device=dev)
+    ws = _ws(N.lib().xr_compact_workspace_bytes(n), dev)
+    with torch.cuda.device(dev):
+        N.call("xr_compact_positions", _p(h), _p(p), _p(rownz), n_table_rows, n, _p(attn),
+               _p(sel_attn), _p(sel_pos), _p(pos_mask), _p(counts), _p(ws), _stream())
+    m_a, m = (int(v) for v in counts.tolist())
+    return attn.view(history_idx.shape).bool(), sel_attn[:m_a], sel_pos[:m], pos_mask[:m_a].bool()
+
+
+def normalize_rows(x, eps=1e-8, out_dtype=None, want_y=True):
+    dev = _require_cuda(x)
+    x2 = x.contiguous().view(-1, x.size(-1))
+    out_dtype = out_dtype or x.dtype
+    y = torch.empty(x2.shape, dtype=out_dtype, device=dev) if want_y else None
+    inv = torch.empty(x2.size(0), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        N.call("xr_normalize_rows", _p(x2), x2.size(0), x2.size(1), _dt(x2), float(eps), _p(y),
+               _DT[out_dtype], _p(inv), _stream())
+    return (y.view(x.shape) if want_y else None), inv.view(x.shape[:-1])
+
+
+# ---------------------------------------------------------------------------------------------
+# family 2: logits / rowloss / dq (materialised paths)
+# ---------------------------------------------------------------------------------------------
+def _ld4(c):
+    return (c + 3) // 4 * 4
+
+
+def logits_pool(q, pos, neg):
+    dev = _require_cuda(q, pos, neg)
+    m, d = q.shape
+    cn = neg.size(0)
+    ld = _ld4(cn + 1)
+    logits = torch.empty((m, ld), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        N.call("xr_logits_pool", _p(q), _p(pos), _p(neg), m, cn, d, _dt(q), _p(logits), ld,
+               _stream())
+    return logits  # columns [0,cn) negatives, column cn the positive
+
+
+def logits_dense(q, cand, q_inv=None, cosine=False, eps=1e-8):
+    dev = _require_cuda(q, cand)
+    m, c, d = cand.shape
+    ld = _ld4(c)
+    logits = torch.empty((m, ld), dtype=torch.float32, device=dev)
+    cand_inv = torch.empty((m, c), dtype=torch.float32, device=dev) if cosine else None
+    with torch.cuda.device(dev):
+        N.call("xr_logits_dense", _p(q), _p(cand), m, c, d, _dt(q), _p(q_inv), _p(cand_inv),
+               float(eps), _p(logits), ld, _stream())
+    return logits, cand_inv
+
+
+def logits_sampled(q, table, cand_idx, table_inv=None, q_inv=None):
+    dev = _require_cuda(q, table, cand_idx)
+    m, c = cand_idx.shape
+    ld = _ld4(c)
+    logits = torch.empty((m, ld), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        N.call("xr_logits_sampled", _p(q), _p(table), table.size(0), _p(cand_idx), m, c, q.size(1),
+               _dt(q), _p(table_inv), _p(q_inv), _p(logits), ld, _stream())
+    return logits
+
+
+def rowloss(logits, c, cfg, target_mode, target=None, grad_kind=-1, grad_scale=1.0,
+            want_stats=False, check=True):
+    """EmbedLoss pipeline on logits (losses.py:211-330 + loss bodies).  Returns
+    (losses float64[7] device tensor, stats float64[16] | None, dlogits | None)."""
+    dev = _require_cuda(logits, target)
+    m, ld = logits.shape
+    losses = torch.empty(N.XR_NUM_LOSSES, dtype=torch.float64, device=dev)
+    stats = torch.empty(N.XR_STATS_SLOTS, dtype=torch.float64, device=dev) if want_stats else None
+    dlogits = torch.empty_like(logits) if grad_kind >= 0 else None
+    err = torch.zeros(1, dtype=torch.int32, device=dev) if (check and target is not None) else None
+    ws = _ws(N.lib().xr_rowloss_workspace_bytes(m, c, cfg.num_hard_negatives), dev)
+    with torch.cuda.device(dev):
+        N.call("xr_rowloss", _p(logits), m, c, ld, target_mode, _p(target), C.byref(cfg), 0x7F,
+               grad_kind, float(grad_scale), _p(dlogits), _p(losses), _p(stats), _p(err), _p(ws),
+               _stream())
+    if err is not None and int(err.item()):
+        raise IndexError("target index out of range")
+    return losses, stats, dlogits
+
+
+def dq_pool(dlogits, q, pos, neg, cosine=False, q_inv=None):
+    dev = _require_cuda(dlogits, q, pos, neg)
+    m, d = q.shape
+    dq = torch.empty((m, d), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        N.call("xr_dq_pool", _p(dlogits), dlogits.size(1), _p(q), _p(pos), _p(neg), m, neg.size(0),
+               d, _dt(q), int(cosine), _p(q_inv), _p(dq), _stream())
+    return dq
+
+
+def dq_dense(dlogits, q, cand, cosine=False, q_inv=None, cand_inv=None):
+    dev = _require_cuda(dlogits, q, cand)
+    m, c, d = cand.shape
+    dq = torch.empty((m, d), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        N.call("xr_dq_dense", _p(dlogits), dlogits.size(1), _p(q), _p(cand), m, c, d, _dt(q),
+               int(cosine), _p(q_inv), _p(cand_inv), _p(dq), _stream())
+    return dq
+
+
+def dq_sampled(dlogits, q, table, cand_idx, table_inv=None, q_inv=None):
+    dev = _require_cuda(dlogits, q, table, cand_idx)
+    m, c = cand_idx.shape
+    dq = torch.empty((m, q.size(1)), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        N.call("xr_dq_sampled", _p(dlogits), dlogits.size(1), _p(q), _p(table), table.size(0),
+               _p(cand_idx), m, c, q.size(1), _dt(q), _p(table_inv), _p(q_inv), _p(dq), _stream())
+    return dq
+
+
+def fused_pool_supported(q, neg) -> bool:
+    if not (q.is_cuda and q.dtype == torch.bfloat16 and q.size(1) == 384):
+        return False
+    major, _ = torch.cuda.get_device_capability(q.device)
+    return major == 10 and bool(N.lib().xr_fused_available())
+
+
+def fused_pool_loss(q, pos, neg, loss_kind, cfg, q_inv=None, grad_scale=1.0, want_grad=True,
+                    want_row_loss=False):
+    """tcgen05/TMEM fused contraction + loss + dQ (xr_fused_pool_loss).  bf16 inputs."""
+    dev = _require_cuda(q, pos, neg, q_inv)
+    assert q.dtype == pos.dtype == neg.dtype == torch.bfloat16
+    q, pos, neg = q.contiguous(), pos.contiguous(), neg.contiguous()
+    m, d = q.shape
+    cn = neg.size(0)
+    dq = torch.empty((m, d), dtype=torch.float32, device=dev) if want_grad else None
+    loss = torch.empty(1, dtype=torch.float64, device=dev)
+    row_loss = torch.empty(m, dtype=torch.float32, device=dev) if want_row_loss else None
+    nbytes = N.lib().xr_fused_pool_workspace_bytes(m, cn, d)
+    ws = _ws(nbytes, dev)
+    with torch.cuda.device(dev):
+        N.call("xr_fused_pool_loss", _p(q), _p(pos), _p(neg), m, cn, d, loss_kind, C.byref(cfg),
+               _p(q_inv), float(grad_scale), _p(dq), _p(loss), _p(row_loss), _p(ws), ws.numel(),
+               _stream())
+    return loss, dq, row_loss
+
+
+# ---------------------------------------------------------------------------------------------
+# family 3: scores / top-k / metrics
+# ---------------------------------------------------------------------------------------------
+def scores(q, catalog, q_inv=None, cat_inv=None, out=None):
+    dev = _require_cuda(q, catalog)
+    u, d = q.shape
+    n = catalog.size(0)
+    ld = _ld4(n)
+    if out is None:
+        out = torch.empty((u, ld), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        N.call("xr_scores", _p(q), u, _p(catalog), n, d, _dt(q), _p(q_inv), _p(cat_inv), _p(out),
+               out.size(1), _stream())
+    return out
+
+
+def _csr(lists, device):
+    offs = [0]
+    flat: list[int] = []
+    for l in lists:
+        flat.extend(int(x) for x in l)
+        offs.append(len(flat))
+    return (torch.tensor(offs, dtype=torch.int64, device=device),
+            torch.tensor(flat if flat else [0], dtype=torch.int64, device=device))
+
+
+def mask_excluded(score_mat, n, exclude_lists, col_offset=0):
+    dev = _require_cuda(score_mat)
+    offs, ids = exclude_lists if isinstance(exclude_lists, tuple) else _csr(exclude_lists, dev)
+    with torch.cuda.device(dev):
+        N.call("xr_mask_excluded", _p(score_mat), score_mat.size(0), n, score_mat.size(1),
+               col_offset, _p(offs), _p(ids), _stream())
+    return score_mat
+
+
+def topk(score_mat, k, n=None, col_offset=0):
+    """Exact (score desc, column asc) top-k of each row — stable-sort oracle semantics."""
+    dev = _require_cuda(score_mat)
+    assert score_mat.dtype == torch.float32 and score_mat.dim() == 2
+    score_mat = score_mat if score_mat.stride(1) == 1 else score_mat.contiguous()
+    u, ld = score_mat.size(0), score_mat.stride(0)
+    n = score_mat.size(1) if n is None else n
+    out_s = torch.empty((u, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((u, k), dtype=torch.int64, device=dev)
+    step = 65535
+    for lo in range(0, max(u, 1), step):
+        uu = min(step, u - lo)
+        if uu <= 0:
+            break
+        nbytes = N.lib().xr_topk_workspace_bytes(uu, n, k)
+        ws = _ws(nbytes, dev)
+        with torch.cuda.device(dev):
+            N.call("xr_topk", _p(score_mat[lo:]), uu, n, ld, k, col_offset, _p(out_s[lo:]),
+                   _p(out_i[lo:]), _p(ws), ws.numel(), _stream())
+    return out_s, out_i
+
+
+def topk_merge(cand_scores, cand_ids, k):
+    """Merge (U, G*k) per-shard candidates (global ids) under the same total order."""
+    dev = _require_cuda(cand_scores, cand_ids)
+    cand_scores, cand_ids = cand_scores.contiguous(), cand_ids.contiguous()
+    u, gk = cand_scores.shape
+    out_s = torch.empty((u, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((u, k), dtype=torch.int64, device=dev)
+    ws = _ws(N.lib().xr_topk_merge_workspace_bytes(u, k), dev)
+    with torch.cuda.device(dev):
+        N.call("xr_topk_merge", _p(cand_scores), _p(cand_ids), u, gk, k, _p(out_s), _p(out_i),
+               _p(ws), _stream())
+    return out_s, out_i
+
+
+def score_topk_supported(q, catalog) -> bool:
+    if not (q.is_cuda and q.dtype == torch.bfloat16 and catalog.dtype == torch.bfloat16
+            and q.size(1) == 384):
+        return False
+    major, _ = torch.cuda.get_device_capability(q.device)
+    return major == 10 and bool(N.lib().xr_fused_available() & 2)
+
+
+def score_topk(q, catalog, k, q_inv=None, cat_inv=None, exclude=None, col_offset=0):
+    """Fused tcgen05 scoring + top-k over one catalog shard (xr_score_topk)."""
+    dev = _require_cuda(q, catalog)
+    q, catalog = q.contiguous(), catalog.contiguous()
+    u, d = q.shape
+    n = catalog.size(0)
+    offs, ids = (None, None)
+    if exclude is not None:
+        offs, ids = exclude if isinstance(exclude, tuple) else _csr(exclude, dev)
+    out_s = torch.empty((u, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((u, k), dtype=torch.int64, device=dev)
+    ws = _ws(N.lib().xr_score_topk_workspace_bytes(u, n, k), dev)
+    with torch.cuda.device(dev):
+        N.call("xr_score_topk", _p(q), u, _p(catalog), n, d, _p(q_inv), _p(cat_inv), k, col_offset,
+               _p(offs), _p(ids), _p(out_s), _p(out_i), _p(ws), ws.numel(), _stream())
+    return out_s, out_i
+
+
+def retrieval_metrics(rec_idx, target_lists, top_k):
+    """metrics.py:62-79 batched.  rec_idx (U,k) int64 (-1 = padding); returns ((U,7) fp32, valid)."""
+    dev = _require_cuda(rec_idx)
+    rec_idx = rec_idx.contiguous()
+    u, k = rec_idx.shape
+    offs, ids = target_lists if isinstance(target_lists, tuple) else _csr(target_lists, dev)
+    out = torch.empty((u, 7), dtype=torch.float32, device=dev)
+    valid = torch.empty(u, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        N.call("xr_retrieval_metrics", _p(rec_idx), u, k, _p(offs), _p(ids), top_k, _p(out),
+               _p(valid), _stream())
+    return out, valid.bool()
+
+
+# ---------------------------------------------------------------------------------------------
+# torch.library registration (dispatcher-visible names of SURVEY §8b)
+# ---------------------------------------------------------------------------------------------
+_registered = False
+
+
+def register_custom_ops() -> None:
+    global _registered
+    if _registered:
+        return
+    _registered = True
+    lib = torch.library.Library("xfmr_b200", "DEF")
+    lib.define("gather_rows(Tensor table, Tensor idx) -> Tensor")
+    lib.define("topk(Tensor scores, int k) -> (Tensor, Tensor)")
+    lib.define("score_topk(Tensor q, Tensor catalog, int k) -> (Tensor, Tensor)")
+    lib.define("pool_loss_fwd_bwd(Tensor q, Tensor pos, Tensor neg, int loss_kind, bool mask_fn, "
+               "float scale, float margin, bool logits_bf16) -> (Tensor, Tensor)")
+    lib.impl("gather_rows", lambda table, idx: gather_rows(table, idx), "CUDA")
+    lib.impl("topk", lambda s, k: topk(s, k), "CUDA")
+    lib.impl("score_topk", lambda q, c, k: score_topk(q, c, k), "CUDA")
+
+    def _pool(q, pos, neg, loss_kind, mask_fn, scale, margin, logits_bf16):
+        cfg = N.XrLossConfig(int(mask_fn), 0, scale, margin, int(logits_bf16))
+        loss, dq, _ = fused_pool_loss(q, pos, neg, loss_kind, cfg)
+        return loss, dq
+
+    lib.impl("pool_loss_fwd_bwd", _pool, "CUDA")
+    globals()["_torch_lib"] = lib  # keep alive
