@@ -145,9 +145,15 @@ def cosine_logits(query, cand, eps=1e-8):
     return np.einsum("md,mcd->mc", qn, cn)
 
 
-def lean_logits(query, pos, neg, *, cosine=False, eps=1e-8):
+def lean_logits(query, pos, neg, *, cosine=False, eps=1e-8, exact_ties=True):
     """[rowdot(q,pos) | Q.Neg^T] — equal to the dense logits of models.py:408-416 +
-    losses.py:195/206 for the shared-pool candidate tensor."""
+    losses.py:195/206 for the shared-pool candidate tensor.
+
+    In the reference the positive and every negative of a row go through ONE bmm, so a pool
+    entry that is the same item as the row's positive gets a bit-identical logit and the
+    strict `<` of losses.py:292 masks it.  ``exact_ties`` keeps that property here by
+    reducing every (row, candidate) pair with the same elementwise-product-then-sum routine;
+    ``exact_ties=False`` uses a BLAS matmul (timing baselines at large sizes only)."""
     q = np.asarray(query, np.float64)
     p = np.asarray(pos, np.float64)
     n = np.asarray(neg, np.float64)
@@ -155,7 +161,15 @@ def lean_logits(query, pos, neg, *, cosine=False, eps=1e-8):
         q = q / np.maximum(np.linalg.norm(q, axis=-1, keepdims=True), eps)
         p = p / np.maximum(np.linalg.norm(p, axis=-1, keepdims=True), eps)
         n = n / np.maximum(np.linalg.norm(n, axis=-1, keepdims=True), eps)
-    return np.concatenate([(q * p).sum(-1, keepdims=True), q @ n.T], axis=1)
+    if not exact_ties:
+        return np.concatenate([(q * p).sum(-1, keepdims=True), q @ n.T], axis=1)
+    out = np.empty((q.shape[0], 1 + n.shape[0]), np.float64)
+    step = max(1, (64 << 20) // max(1, 8 * max(n.shape[0], 1) * q.shape[1]))
+    for lo in range(0, q.shape[0], step):
+        qs = np.ascontiguousarray(q[lo:lo + step])
+        out[lo:lo + step, 0] = (qs * np.ascontiguousarray(p[lo:lo + step])).sum(-1)
+        out[lo:lo + step, 1:] = (qs[:, None, :] * n[None, :, :]).sum(-1)
+    return out
 
 
 # ---------------------------------------------------------------------------

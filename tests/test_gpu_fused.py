@@ -1,0 +1,155 @@
+"""GPU parity tests for the tcgen05/TMEM fused contraction+loss kernel (xr_fused_pool_loss)
+against the oracle on bf16-rounded inputs and against the library's own fp32-accumulate
+materialised path."""
+
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import xfmr_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+FUSED = ["InfoNCELoss", "NCELoss", "PairwiseHingeLoss", "PairwiseLogisticLoss", "ContrastiveLoss",
+         "AlignmentContrastiveLoss"]
+
+
+@pytest.fixture(scope="module")
+def xr():
+    import xfmr_rec_b200 as pkg
+
+    if not torch.cuda.is_available() or torch.cuda.get_device_capability()[0] != 10:
+        pytest.skip("needs an sm_100 device")
+    assert pkg._native.lib().xr_fused_available() & 1, "tcgen05 kernels missing from the build"
+    return pkg
+
+
+def make_inputs(m, cn, d=384, seed=0, dup=True, scale_q=1.0):
+    rng = np.random.default_rng(seed)
+    s = 1.0 / math.sqrt(d)
+    q = orc.round_bf16((rng.standard_normal((m, d)) * s * scale_q).astype(np.float32))
+    pos = orc.round_bf16((rng.standard_normal((m, d)) * s).astype(np.float32))
+    neg = orc.round_bf16((rng.standard_normal((cn, d)) * s).astype(np.float32))
+    if dup and cn > 3 and m > 2:
+        neg[1] = pos[0]          # the row's own positive inside the pool: exact tie -> masked
+        neg[cn - 1] = pos[m - 1]
+        neg[2] = 0.0             # a padding row in the pool
+    return q, pos, neg
+
+
+def bf(x):
+    return torch.from_numpy(x).cuda().bfloat16()
+
+
+def run_fused(xr, name, q, pos, neg, cfg_kw, logits_bf16, want_grad=True):
+    from xfmr_rec_b200 import _native as N, ops
+
+    class C:
+        pass
+
+    c = C()
+    for k, v in {**dict(mask_false_negatives=True, num_hard_negatives=0, scale=1.0, margin=0.5), **cfg_kw}.items():
+        setattr(c, k, v)
+    cosine = name in orc.COSINE_LOSSES
+    cfg = ops.make_cfg(c, logits_bf16=logits_bf16 and not cosine)
+    qt, pt, nt = bf(q), bf(pos), bf(neg)
+    q_inv = None
+    if cosine:
+        qt, q_inv = ops.normalize_rows(torch.from_numpy(q).cuda(), 1e-8, torch.bfloat16)
+        pt, _ = ops.normalize_rows(torch.from_numpy(pos).cuda(), 1e-8, torch.bfloat16)
+        nt, _ = ops.normalize_rows(torch.from_numpy(neg).cuda(), 1e-8, torch.bfloat16)
+    loss, dq, _ = ops.fused_pool_loss(qt, pt, nt, N.LOSS_KIND[name], cfg, q_inv=q_inv,
+                                      want_grad=want_grad)
+    torch.cuda.synchronize()
+    extras = (qt.float().cpu().numpy(), pt.float().cpu().numpy(), nt.float().cpu().numpy(),
+              None if q_inv is None else q_inv.cpu().numpy())
+    return float(loss[0]), (None if dq is None else dq.cpu().numpy()), extras
+
+
+def oracle_on_bf16(name, qh, ph, nh, q_inv, cfg_kw, logits_bf16):
+    """Oracle on exactly the bf16 operands the kernel saw.  For the cosine kinds those are the
+    already-normalised rows: logits are plain dots of them, and d/dq chains through q_inv."""
+    cfg = orc.Config(**cfg_kw)
+    cosine = name in orc.COSINE_LOSSES
+    logits = orc.lean_logits(qh, ph, nh)
+    if logits_bf16 and not cosine:
+        logits = orc.round_bf16(logits.astype(np.float32)).astype(np.float64)
+    else:
+        logits = logits.astype(np.float32).astype(np.float64)
+    tgt = np.zeros(qh.shape[0], np.int64)
+    mask = orc.mask_false_negatives(logits, tgt, cfg)
+    loss, g = orc.loss_from_logits(name, logits, tgt, mask, cfg, with_grad=True)
+    ghat = g[:, :1] * ph + g[:, 1:] @ nh
+    if cosine:
+        ghat = q_inv[:, None] * (ghat - (ghat * qh).sum(-1, keepdims=True) * qh)
+    return loss, ghat
+
+
+@pytest.mark.parametrize("name", FUSED)
+@pytest.mark.parametrize("m,cn", [(128, 64), (1, 1), (130, 65), (301, 777), (700, 3000)])
+def test_fused_matches_oracle(xr, name, m, cn):
+    q, pos, neg = make_inputs(m, cn, seed=m + cn)
+    for cfg_kw, lbf in [({}, True), ({"scale": 8.0, "margin": 0.2}, True), ({"mask_false_negatives": False}, False)]:
+        loss, dq, (qh, ph, nh, q_inv) = run_fused(xr, name, q, pos, neg, cfg_kw, lbf)
+        want, want_dq = oracle_on_bf16(name, qh, ph, nh, q_inv, cfg_kw, lbf)
+        assert loss == pytest.approx(want, rel=2e-3, abs=2e-3), (name, cfg_kw, loss, want)
+        scale = max(np.abs(want_dq).max(), 1e-6)
+        assert np.abs(dq - want_dq).max() <= 2e-2 * scale + 1e-6, (name, cfg_kw)
+        assert np.linalg.norm(dq - want_dq) <= 5e-3 * np.linalg.norm(want_dq) + 1e-6, (name, cfg_kw)
+
+
+def test_fused_forward_only_equals_forward_backward(xr):
+    q, pos, neg = make_inputs(260, 900, seed=3)
+    for name in FUSED:
+        a, _, _ = run_fused(xr, name, q, pos, neg, {}, True, want_grad=True)
+        b, dq, _ = run_fused(xr, name, q, pos, neg, {}, True, want_grad=False)
+        assert dq is None and a == b, name
+
+
+def test_fused_is_deterministic(xr):
+    q, pos, neg = make_inputs(513, 2100, seed=4)
+    a, da, _ = run_fused(xr, "InfoNCELoss", q, pos, neg, {}, True)
+    b, db, _ = run_fused(xr, "InfoNCELoss", q, pos, neg, {}, True)
+    assert a == b and np.array_equal(da, db)
+
+
+def test_fused_duplicate_positive_is_masked(xr):
+    """In-batch negatives routinely contain the row's own positive item; the reference masks it
+    because one bmm gives both logits identical bits (losses.py:289-292)."""
+    m, cn = 256, 256
+    q, pos, neg = make_inputs(m, cn, seed=9, dup=False)
+    neg[:] = pos            # every row's positive sits in the pool (the in-batch setting)
+    loss, dq, (qh, ph, nh, _) = run_fused(xr, "InfoNCELoss", q, pos, neg, {}, False)
+    want, _ = oracle_on_bf16("InfoNCELoss", qh, ph, nh, None, {}, False)
+    assert loss == pytest.approx(want, rel=1e-4)
+
+
+def test_loss_modules_take_the_fused_path(xr):
+    """Through the public loss modules: bf16 inputs + PoolCandidates -> tcgen05 kernel."""
+    q, pos, neg = make_inputs(300, 1000, seed=5)
+    for name in orc.LOSS_NAMES:
+        qt = bf(q).requires_grad_(True)
+        cand = xr.PoolCandidates(bf(pos), bf(neg))
+        loss = getattr(xr, name)(xr.LossConfig())(qt, cand)
+        loss.backward()
+        lb = None if name in orc.COSINE_LOSSES else "bf16"
+        want, want_dq, _, _ = orc.lean_loss(name, q, pos, neg, orc.Config(), with_grad=True, logits_dtype=lb)
+        assert float(loss) == pytest.approx(want, rel=4e-3, abs=4e-3), name
+        g = qt.grad.float().cpu().numpy()
+        assert np.linalg.norm(g - want_dq) <= 2e-2 * np.linalg.norm(want_dq) + 1e-6, name
+
+
+def test_fused_under_autocast_matches_golden(xr, golden_dir):
+    """fp32 inputs under bf16-mixed autocast (trainer.py:450) with D=384 take the fused path."""
+    import json
+
+    z = np.load(golden_dir / "losses_anchor_m64_d384.npz")
+    cand = xr.PoolCandidates(torch.from_numpy(z["pos"]).cuda(), torch.from_numpy(z["neg"]).cuda())
+    q = torch.from_numpy(z["query"]).cuda().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = xr.InfoNCELoss(xr.LossConfig())(q, cand)
+    want, _, _, _ = orc.lean_loss("InfoNCELoss", z["query"], z["pos"], z["neg"], orc.Config(),
+                                  with_grad=True, logits_dtype="bf16")
+    assert float(loss) == pytest.approx(want, rel=2e-3)

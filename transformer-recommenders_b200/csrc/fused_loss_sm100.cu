@@ -1,0 +1,736 @@
+// Family 2: fused query x candidate contraction + loss + gradient on the 5th-gen tensor cores.
+//
+// Replaces, for the shared-negative-pool candidate set the trainer builds
+// (xfmr_rec/models.py:398-416), the whole of EmbedLoss.forward (xfmr_rec/losses.py:150-155):
+// compute_logits (:195) -> mask_false_negatives (:283-292) -> loss (:479-488 InfoNCE,
+// :498-511 NCE, :520-543 pairwise hinge / logistic, :338-372 + :436-469 contrastive on
+// pre-normalised rows) AND its backward w.r.t. the query, in one pass over the pool:
+//
+//     S  = Q_blk . Neg_tile^T          tcgen05.mma  (A, B from shared memory, D in TMEM)
+//     W  = f(S, t_row)                 epilogue warps: tcgen05.ld -> mask / exp / sigmoid ->
+//                                      bf16 -> tcgen05.st back into TMEM (aliasing S)
+//     dQ += W . Neg_tile               tcgen05.mma  (A = W from TMEM, B = the SAME smem tile,
+//                                      now addressed MN-major)
+//
+// The M x C logits never leave the SM.  Because every per-row normaliser factors out of the
+// sum over candidates (softmax with a known reference maximum, weighted means), no online
+// rescaling of the accumulator is needed: partial dQ and three scalars per row are written once
+// per work item and folded by a small finalize kernel in a fixed order (deterministic, no
+// floating-point atomics).
+//
+// One CTA per SM (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2-5 = epilogue (one TMEM lane quadrant each).  TMEM: 384 columns dQ accumulator +
+// 2 x 64 columns S/W double buffer = 512.  Shared memory: Q tile 96 KB + a 16-slot ring of
+// 64x64 bf16 sub-tiles (128 KB) fed by TMA with 128-byte swizzle.
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace xr {
+
+using namespace sm100;
+
+namespace fk {
+constexpr int BM = 128;             // query rows per CTA tile (UMMA M)
+constexpr int BN = 64;              // candidates per tile (UMMA N of the score MMA)
+constexpr int D = 384;              // embedding dim (all-MiniLM-L6-v2, params.py:11)
+constexpr int KB = D / 64;          // 64-column (128-byte) k-blocks per row
+constexpr int SLOTS = 16;           // ring of [64 cand x 64 col] sub-tiles
+constexpr int SUB_BYTES = BN * 64 * 2;
+constexpr int QSUB_BYTES = BM * 64 * 2;
+constexpr int Q_BYTES = KB * QSUB_BYTES;
+constexpr int RING_BYTES = SLOTS * SUB_BYTES;
+constexpr int BAR_OFF = Q_BYTES + RING_BYTES;
+constexpr int NBARS = 2 * SLOTS + 8;
+constexpr int SMEM_BYTES = BAR_OFF + NBARS * 8 + 16 + 1024;  // + manual 1024 B alignment slack
+constexpr int THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int COL_O = 0, COL_S = 384;
+constexpr int KIND_DIAG = 100;      // extract q_i . pos_i from the diagonal of Q_blk . Pos_blk^T
+constexpr int NSCAL = 4;
+}  // namespace fk
+
+struct FusedParams {
+  int m, cn, nt_count, spl, tiles_per_split, n_items;
+  int mask_fn, logits_bf16, with_grad;
+  float scale, margin;
+  const float* t;      // [m] target logits (raw fp32)           (loss modes)
+  const float* zref;   // [m] softmax reference maximum, nullable (defaults to scaled t)
+  float* t_out;        // [m]                                      (KIND_DIAG)
+  float* part_o;       // [n_items][128][384]
+  float* part_s;       // [n_items][128][NSCAL]
+  int* hang_flag;
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2f(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcpf(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// per-element weight / loss term; returns w (goes to the dQ MMA), adds to the row scalars
+template <int KIND>
+__device__ __forceinline__ float elem(float l, bool valid, float t, float tm, float zref2,
+                                      float scale2, float scale, float margin, bool round_scaled,
+                                      float& sum_a, float& sum_w) {
+  float w = 0.f;
+  if (KIND == XR_LOSS_INFONCE) {
+    float z2;
+    if (round_scaled) z2 = bf16_round(l * scale) * kLog2e;
+    else z2 = l * scale2;
+    w = valid ? ex2f(z2 - zref2) : 0.f;
+    sum_w += w;
+  } else if (KIND == XR_LOSS_NCE || KIND == XR_LOSS_PAIRWISE_LOGISTIC) {
+    const float x = (KIND == XR_LOSS_NCE) ? l : l - tm;
+    const float u = ex2f(-fabsf(x) * kLog2e);          // exp(-|x|) in (0,1]
+    const float r = rcpf(1.0f + u);
+    const float sp = fmaxf(x, 0.f) + lg2f(1.0f + u) * kLn2;
+    const float sg = x >= 0.f ? r : u * r;
+    w = valid ? sg : 0.f;
+    sum_a += valid ? sp : 0.f;
+    sum_w += w;
+  } else if (KIND == XR_LOSS_PAIRWISE_HINGE) {
+    const float x = l - tm;
+    const bool on = valid && x > 0.f;
+    w = on ? 1.f : 0.f;
+    sum_a += on ? x : 0.f;
+    sum_w += w;
+  } else if (KIND == XR_LOSS_CONTRASTIVE || KIND == XR_LOSS_ALIGNMENT_CONTRASTIVE) {
+    const float x = l - 1.0f + margin;
+    const bool on = valid && x > 0.f;
+    w = on ? 1.f : 0.f;
+    sum_a += on ? x : 0.f;
+  }
+  return w;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(fk::THREADS, 1)
+fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                  const __grid_constant__ CUtensorMap tmap_b, const FusedParams p) {
+  using namespace fk;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;   // SWIZZLE_128B operands need 1024 B alignment
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t q_smem = base;
+  const uint32_t ring = base + Q_BYTES;
+  const uint32_t bars = base + BAR_OFF;
+  auto bar_full = [&](int s) { return bars + 8u * s; };
+  auto bar_empty = [&](int s) { return bars + 8u * (SLOTS + s); };
+  const uint32_t bar_q_full = bars + 8u * (2 * SLOTS + 0);
+  const uint32_t bar_q_empty = bars + 8u * (2 * SLOTS + 1);
+  auto bar_s_full = [&](int b) { return bars + 8u * (2 * SLOTS + 2 + b); };
+  auto bar_p_full = [&](int b) { return bars + 8u * (2 * SLOTS + 4 + b); };
+  const uint32_t bar_o_full = bars + 8u * (2 * SLOTS + 6);
+  const uint32_t bar_o_empty = bars + 8u * (2 * SLOTS + 7);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + BAR_OFF + NBARS * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool diag = (KIND == KIND_DIAG);
+  const bool grad = !diag && p.with_grad;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SLOTS; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    mbar_init(bar_q_full, 1);
+    mbar_init(bar_q_empty, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_s_full(b), 1);
+      mbar_init(bar_p_full(b), 128);
+    }
+    mbar_init(bar_o_full, 1);
+    mbar_init(bar_o_empty, 128);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmap_q);
+    prefetch_tensormap(&tmap_b);
+  }
+  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_ptr_smem), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_smem;
+
+  // work items: (row block, split of the candidate tiles); identical iteration in every role
+  auto item_tiles = [&](int item, int& rb, int& t0, int& t1) {
+    if (diag) {
+      rb = item;
+      t0 = 2 * rb;
+      t1 = t0 + 2;
+    } else {
+      rb = item / p.spl;
+      const int sp = item - rb * p.spl;
+      t0 = sp * p.tiles_per_split;
+      t1 = min(p.nt_count, t0 + p.tiles_per_split);
+    }
+  };
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      uint32_t g = 0, it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        int rb, t0, t1;
+        item_tiles(item, rb, t0, t1);
+        mbar_wait(bar_q_empty, (it & 1) ^ 1, p.hang_flag, 1);
+        mbar_expect_tx(bar_q_full, Q_BYTES);
+        for (int kb = 0; kb < KB; ++kb)
+          tma_load_2d(q_smem + kb * QSUB_BYTES, &tmap_q, bar_q_full, kb * 64, rb * BM);
+        for (int t = t0; t < t1; ++t) {
+          for (int kb = 0; kb < KB; ++kb, ++g) {
+            const int s = g % SLOTS;
+            mbar_wait(bar_empty(s), ((g / SLOTS) & 1) ^ 1, p.hang_flag, 2);
+            mbar_expect_tx(bar_full(s), SUB_BYTES);
+            tma_load_2d(ring + s * SUB_BYTES, &tmap_b, bar_full(s), kb * 64, t * BN);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(BM, BN, 0, 0);   // S  = Q . Neg^T (both K-major)
+      constexpr uint32_t idesc_o = umma_idesc_bf16(BM, 64, 0, 1);   // dQ += W . Neg (B MN-major)
+      uint32_t g1 = 0, g2 = 0, tt = 0, it = 0;
+      // dQ += W(tile) . Neg(tile): A = W from TMEM, B = the tile's six sub-tiles, MN-major
+      auto issue_o = [&](uint32_t tile, bool first) {
+        const int b = tile & 1;
+        mbar_wait(bar_p_full(b), (tile >> 1) & 1, p.hang_flag, 3);
+        tc_fence_after();
+        const uint32_t a_tmem = tmem + COL_S + b * BN;   // packed bf16 pairs: 8 columns per K=16
+#pragma unroll
+        for (int ks = 0; ks < BN / 16; ++ks) {
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) {
+            const int s = (g2 + kb) % SLOTS;
+            const uint64_t bdesc = umma_desc_sw128(ring + s * SUB_BYTES + ks * 2048, 1024, 1024);
+            umma_ts(tmem + COL_O + kb * 64, a_tmem + ks * 8, bdesc, idesc_o,
+                    (first && ks == 0) ? 0u : 1u);
+          }
+        }
+        for (int kb = 0; kb < KB; ++kb) umma_commit(bar_empty((g2 + kb) % SLOTS));
+        g2 += KB;
+      };
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        int rb, t0, t1;
+        item_tiles(item, rb, t0, t1);
+        const int T = t1 - t0;
+        mbar_wait(bar_q_full, it & 1, p.hang_flag, 4);
+        if (grad) mbar_wait(bar_o_empty, (it & 1) ^ 1, p.hang_flag, 5);
+        tc_fence_after();
+        for (int tl = 0; tl < T; ++tl) {
+          const uint32_t tile = tt + tl;
+          const int b = tile & 1;
+          if (!grad && tile >= 2) {   // S buffer reuse: the epilogue must have drained tile-2
+            mbar_wait(bar_p_full(b), ((tile - 2) >> 1) & 1, p.hang_flag, 6);
+            tc_fence_after();
+          }
+          for (int kb = 0; kb < KB; ++kb, ++g1) {
+            const int s = g1 % SLOTS;
+            mbar_wait(bar_full(s), (g1 / SLOTS) & 1, p.hang_flag, 7);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t adesc = umma_desc_sw128(q_smem + kb * QSUB_BYTES + k * 32, 16, 1024);
+              const uint64_t bdesc = umma_desc_sw128(ring + s * SUB_BYTES + k * 32, 16, 1024);
+              umma_ss(tmem + COL_S + b * BN, adesc, bdesc, idesc_s, (kb | k) ? 1u : 0u);
+            }
+            if (!grad) umma_commit(bar_empty(s));   // forward only: the slot is free after S
+          }
+          umma_commit(bar_s_full(b));
+          if (tl == T - 1) umma_commit(bar_q_empty);   // Q is only read by the score MMAs
+          if (grad && tl >= 1) issue_o(tile - 1, tl - 1 == 0);
+        }
+        if (grad) {
+          issue_o(tt + T - 1, T == 1);
+          umma_commit(bar_o_full);
+        }
+        tt += T;
+      }
+    }
+  } else {
+    // ================================ epilogue warps ==============================
+    const int quad = warp & 3;                       // TMEM lane quadrant of this warp
+    const int r_local = quad * 32 + lane;
+    const uint32_t tmem_lane = tmem + ((uint32_t)(quad * 32) << 16);
+    const bool mask_fn = p.mask_fn != 0, rbf = p.logits_bf16 != 0;
+    const bool round_scaled = rbf && p.scale != 1.0f;
+    const float scale2 = p.scale * kLog2e;
+    uint32_t tt = 0, it = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      int rb, t0, t1;
+      item_tiles(item, rb, t0, t1);
+      const int T = t1 - t0;
+      const int row = rb * BM + r_local;
+      const bool row_ok = row < p.m;
+      float t = 0.f, tm = 0.f, zref2 = 0.f;
+      if (!diag && row_ok) {
+        t = p.t[row];
+        if (rbf) t = bf16_round(t);
+        tm = t * (1.0f - p.margin);
+        float zr;
+        if (p.zref) zr = p.zref[row];
+        else zr = round_scaled ? bf16_round(t * p.scale) : t * p.scale;
+        zref2 = zr * kLog2e;
+      }
+      float cnt = 0.f, sum_a = 0.f, sum_w = 0.f, diag_val = 0.f;
+      for (int tl = 0; tl < T; ++tl) {
+        const uint32_t tile = tt + tl;
+        const int b = tile & 1;
+        mbar_wait(bar_s_full(b), (tile >> 1) & 1, p.hang_flag, 8);
+        tc_fence_after();
+        uint32_t v0[32], v1[32];
+        tmem_ld32(tmem_lane + COL_S + b * BN, v0);
+        tmem_ld32(tmem_lane + COL_S + b * BN + 32, v1);
+        tmem_wait_ld();
+        if (diag) {
+          // tile tl holds pos rows [rb*128 + tl*64, +64): the diagonal entry of local row r is
+          // column r - tl*64 of tile tl = r/64
+          if ((r_local >> 6) == tl) {
+            const int c = r_local & 63;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (c == j) diag_val = __uint_as_float(v0[j]);
+              if (c == 32 + j) diag_val = __uint_as_float(v1[j]);
+            }
+          }
+        } else {
+          const int ncols = p.cn - (t0 + tl) * BN;   // valid candidates in this tile (>= 1)
+          uint32_t pk[32];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float w2[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int c = h * 32 + j + e;
+                float l = __uint_as_float(h == 0 ? v0[j + e] : v1[j + e]);
+                if (rbf) l = bf16_round(l);
+                bool valid = c < ncols;
+                if (mask_fn) valid = valid && (l < t);
+                cnt += valid ? 1.f : 0.f;
+                w2[e] = elem<KIND>(l, valid, t, tm, zref2, scale2, p.scale, p.margin, round_scaled,
+                                   sum_a, sum_w);
+              }
+              const __nv_bfloat162 pr = __floats2bfloat162_rn(w2[0], w2[1]);
+              pk[(h * 32 + j) >> 1] = *reinterpret_cast<const uint32_t*>(&pr);
+            }
+          }
+          if (grad) {
+            tmem_st32(tmem_lane + COL_S + b * BN, pk);   // W overwrites the S columns it came from
+            tmem_wait_st();
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bar_p_full(b));
+      }
+      if (diag) {
+        if (row_ok) p.t_out[row] = diag_val;
+      } else {
+        if (grad) {
+          mbar_wait(bar_o_full, it & 1, p.hang_flag, 9);
+          tc_fence_after();
+          float* dst = p.part_o + ((size_t)item * BM + r_local) * D;
+#pragma unroll 1
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tmem_lane + COL_O + c * 32, o);
+            tmem_wait_ld();
+            if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<uint4*>(dst + c * 32 + j) = make_uint4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(bar_o_empty);
+        }
+        if (row_ok) {
+          float* ds = p.part_s + ((size_t)item * BM + r_local) * NSCAL;
+          *reinterpret_cast<float4*>(ds) = make_float4(cnt, sum_a, sum_w, 0.f);
+        }
+      }
+      tt += T;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
+// ---- finalize: fold the per-item partials, apply the per-row normalisers and the positive's
+//      term, chain through the query normalisation for the cosine kinds (one warp per row) ------
+__global__ void __launch_bounds__(256)
+fused_finalize_kernel(const float* __restrict__ part_o, const float* __restrict__ part_s,
+                      const float* __restrict__ t_raw, const float* __restrict__ zref,
+                      const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ pos,
+                      const float* __restrict__ q_inv, int m, int spl, int kind, int logits_bf16,
+                      float scale, float margin, float grad_scale, float* __restrict__ dq,
+                      float* __restrict__ row_loss) {
+  using namespace fk;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool cosine = kind == XR_LOSS_CONTRASTIVE || kind == XR_LOSS_ALIGNMENT_CONTRASTIVE;
+  for (int64_t i = warp; i < m; i += nwarps) {
+    const int rb = (int)(i / BM), rl = (int)(i % BM);
+    float cnt = 0.f, sum_a = 0.f, sum_w = 0.f;
+    float o[D / 32];
+#pragma unroll
+    for (int c = 0; c < D / 32; ++c) o[c] = 0.f;
+    for (int sp = 0; sp < spl; ++sp) {   // fixed order: deterministic
+      const size_t item = (size_t)rb * spl + sp;
+      const float4 s = *reinterpret_cast<const float4*>(part_s + (item * BM + rl) * NSCAL);
+      cnt += s.x; sum_a += s.y; sum_w += s.z;
+      if (dq) {
+        const float* src = part_o + (item * BM + rl) * D;
+#pragma unroll
+        for (int c = 0; c < D / 32; ++c) o[c] += src[c * 32 + lane];
+      }
+    }
+    float t = t_raw[i];
+    if (logits_bf16) t = bf16_round(t);
+    const float den = cnt + 1e-9f;
+    float loss = 0.f, co = 0.f, cp = 0.f;   // dq = co * O + cp * pos
+    switch (kind) {
+      case XR_LOSS_INFONCE: {
+        const float st = (logits_bf16 && scale != 1.0f) ? bf16_round(t * scale) : t * scale;
+        const float zr = zref ? zref[i] : st;
+        const float et = __expf(st - zr);
+        const float zall = sum_w + et;
+        loss = zr + __logf(zall) - st;
+        co = scale / zall;
+        cp = scale * (et / zall - 1.0f);
+        break;
+      }
+      case XR_LOSS_NCE: {
+        const float at = fabsf(t);
+        loss = fmaxf(-t, 0.f) + log1pf(__expf(-at)) + sum_a / den;
+        co = 1.0f / den;
+        cp = -1.0f / (1.0f + __expf(t));
+        break;
+      }
+      case XR_LOSS_PAIRWISE_HINGE:
+      case XR_LOSS_PAIRWISE_LOGISTIC:
+        loss = sum_a / den;
+        co = 1.0f / den;
+        cp = -(1.0f - margin) * sum_w / den;
+        break;
+      case XR_LOSS_CONTRASTIVE:
+        loss = sum_a / den;
+        co = 1.0f / den;
+        break;
+      case XR_LOSS_ALIGNMENT_CONTRASTIVE:
+        loss = sum_a / den + (1.0f - t);
+        co = 1.0f / den;
+        cp = -1.0f;
+        break;
+      default:
+        break;
+    }
+    if (lane == 0 && row_loss) row_loss[i] = loss;
+    if (dq) {
+      float g[D / 32], dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        const int d = c * 32 + lane;
+        g[c] = co * o[c] + cp * __bfloat162float(pos[i * D + d]);
+        if (cosine) dot = fmaf(g[c], __bfloat162float(q[i * D + d]), dot);
+      }
+      if (cosine) {
+        dot = warp_sum(dot);
+        const float inv = q_inv[i];
+#pragma unroll
+        for (int c = 0; c < D / 32; ++c) {
+          const int d = c * 32 + lane;
+          g[c] = inv * (g[c] - dot * __bfloat162float(q[i * D + d]));
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) dq[i * D + c * 32 + lane] = g[c] * grad_scale;
+    }
+  }
+}
+
+// single block, fixed order: loss = sum_i row_loss[i]   (double accumulation)
+__global__ void __launch_bounds__(1024)
+sum_rows_kernel(const float* __restrict__ row_loss, int64_t m, double* __restrict__ out) {
+  __shared__ double s[32];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < m; i += blockDim.x) acc += (double)row_loss[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s[w];
+    out[0] = tot;
+  }
+}
+
+// reference maximum when the false-negative mask is off (losses.py:283-287): by Cauchy-Schwarz
+// |s * q.n| <= |s| * ||q|| * max_j ||n_j||, and the target itself is in the set.
+__global__ void negnorm_max_kernel(const __nv_bfloat16* __restrict__ neg, int64_t cn,
+                                   unsigned* __restrict__ out_bits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float best = 0.f;
+  for (int64_t r = warp; r < cn; r += nwarps) {
+    float ss = 0.f;
+    for (int c = lane; c < fk::D; c += 32) {
+      const float v = __bfloat162float(neg[r * fk::D + c]);
+      ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    best = fmaxf(best, sqrtf(ss));
+  }
+  if (lane == 0) atomicMax(out_bits, __float_as_uint(best));   // non-negative floats order as uints
+}
+__global__ void zref_bound_kernel(const __nv_bfloat16* __restrict__ q, const float* __restrict__ t,
+                                  const unsigned* __restrict__ maxnorm_bits, int64_t m, float scale,
+                                  int logits_bf16, float* __restrict__ zref) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float nmax = __uint_as_float(*maxnorm_bits);
+  for (int64_t r = warp; r < m; r += nwarps) {
+    float ss = 0.f;
+    for (int c = lane; c < fk::D; c += 32) {
+      const float v = __bfloat162float(q[r * fk::D + c]);
+      ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    float tr = t[r];
+    if (logits_bf16) tr = bf16_round(tr);
+    float st = tr * scale;
+    if (logits_bf16 && scale != 1.0f) st = bf16_round(st);
+    if (lane == 0) zref[r] = fmaxf(st, fabsf(scale) * sqrtf(ss) * nmax * 1.01f);
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+int make_tmap_bf16_rows(CUtensorMap* out, const void* base, int64_t rows, int64_t cols,
+                        int64_t ld_elems, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return XR_E_CUDA;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld_elems * 2};
+  const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+                         gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) rows=%lld cols=%lld", (int)r,
+              (long long)rows, (long long)cols);
+    return XR_E_CUDA;
+  }
+  return XR_OK;
+}
+
+struct FusedPlan {
+  int rb, nt, spl, tps, n_items;
+};
+static FusedPlan make_plan(int64_t m, int64_t cn, int n_sm) {
+  FusedPlan pl;
+  pl.rb = (int)((m + fk::BM - 1) / fk::BM);
+  pl.nt = (int)((cn + fk::BN - 1) / fk::BN);
+  // choose the split of the candidate tiles that minimises (waves x tiles per item + per-item
+  // overhead), so the persistent grid of n_sm CTAs stays balanced for any M
+  double best = 1e30;
+  int best_spl = 1;
+  const int max_spl = pl.nt < 64 ? pl.nt : 64;
+  for (int s = 1; s <= max_spl; ++s) {
+    const int tps = (pl.nt + s - 1) / s;
+    const int s_eff = (pl.nt + tps - 1) / tps;
+    const int64_t items = (int64_t)pl.rb * s_eff;
+    const int64_t waves = (items + n_sm - 1) / n_sm;
+    const double cost = (double)waves * (tps + 3.0);
+    if (cost < best - 1e-9) {
+      best = cost;
+      best_spl = s_eff;
+    }
+  }
+  pl.spl = best_spl;
+  pl.tps = (pl.nt + pl.spl - 1) / pl.spl;
+  pl.spl = (pl.nt + pl.tps - 1) / pl.tps;
+  pl.n_items = pl.rb * pl.spl;
+  return pl;
+}
+
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+template <int KIND>
+static int launch_fused(const CUtensorMap& tq, const CUtensorMap& tb, const FusedParams& p,
+                        int grid, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    XR_CUDA(cudaFuncSetAttribute(fused_pool_kernel<KIND>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, fk::SMEM_BYTES));
+    configured = true;
+  }
+  fused_pool_kernel<KIND><<<grid, fk::THREADS, fk::SMEM_BYTES, s>>>(tq, tb, p);
+  XR_LAUNCH_CHECK("fused_pool_kernel");
+  return XR_OK;
+}
+
+}  // namespace xr
+
+using namespace xr;
+
+extern "C" int xr_fused_available(void) { return 1; }
+
+extern "C" size_t xr_fused_pool_workspace_bytes(int64_t m, int64_t cn, int64_t dim) {
+  if (dim != fk::D || m <= 0 || cn <= 0) return 256;
+  const FusedPlan pl = make_plan(m, cn, sm_count());
+  size_t b = 0;
+  b += align256((size_t)m * 4);                                   // t
+  b += align256((size_t)m * 4);                                   // zref
+  b += align256((size_t)m * 4);                                   // row_loss
+  b += align256((size_t)pl.n_items * fk::BM * fk::NSCAL * 4);     // partial scalars
+  b += align256((size_t)pl.n_items * fk::BM * fk::D * 4);         // partial dQ
+  b += 256;                                                       // flags
+  return b;
+}
+
+extern "C" int xr_fused_pool_loss(const void* q, const void* pos, const void* neg, int64_t m,
+                                  int64_t cn, int64_t dim, int loss_kind,
+                                  const xr_loss_config* cfg, const float* q_inv_norm,
+                                  float grad_scale, float* dq, double* loss_out, float* row_loss,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  XR_CHECK_ARG(q && pos && neg && cfg && loss_out && workspace, "xr_fused_pool_loss: null pointer");
+  XR_CHECK_ARG(dim == fk::D, "xr_fused_pool_loss: this build is specialised for dim = %d", fk::D);
+  XR_CHECK_ARG(m > 0 && cn > 0 && m < (1ll << 30) && cn < (1ll << 30),
+               "xr_fused_pool_loss: bad sizes");
+  XR_CHECK_ARG(cfg->num_hard_negatives == 0,
+               "xr_fused_pool_loss: hard-negative mining needs the materialised path");
+  XR_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)pos % 16 == 0) && ((uintptr_t)neg % 16 == 0),
+               "xr_fused_pool_loss: operands must be 16-byte aligned");
+  const bool cosine = loss_kind == XR_LOSS_CONTRASTIVE || loss_kind == XR_LOSS_ALIGNMENT_CONTRASTIVE;
+  XR_CHECK_ARG(loss_kind == XR_LOSS_INFONCE || loss_kind == XR_LOSS_NCE ||
+                   loss_kind == XR_LOSS_PAIRWISE_HINGE || loss_kind == XR_LOSS_PAIRWISE_LOGISTIC ||
+                   cosine,
+               "xr_fused_pool_loss: unsupported loss kind %d", loss_kind);
+  XR_CHECK_ARG(!cosine || !dq || q_inv_norm, "xr_fused_pool_loss: cosine kinds need q_inv_norm");
+  XR_CHECK_ARG(loss_kind != XR_LOSS_INFONCE || cfg->scale > 0.f,
+               "xr_fused_pool_loss: InfoNCE needs scale > 0");
+  XR_CHECK_ARG(workspace_bytes >= xr_fused_pool_workspace_bytes(m, cn, dim),
+               "xr_fused_pool_loss: workspace too small");
+  int dev = 0, major = 0;
+  XR_CUDA(cudaGetDevice(&dev));
+  XR_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    set_error("xr_fused_pool_loss: needs an sm_100 device (tcgen05/TMEM), found sm_%d", major * 10);
+    return XR_E_UNSUPPORTED;
+  }
+  cudaStream_t s = as_stream(stream);
+  const int n_sm = sm_count();
+  const FusedPlan pl = make_plan(m, cn, n_sm);
+
+  uint8_t* w = (uint8_t*)workspace;
+  float* t_buf = (float*)w;            w += align256((size_t)m * 4);
+  float* zref_buf = (float*)w;         w += align256((size_t)m * 4);
+  float* rl_buf = (float*)w;           w += align256((size_t)m * 4);
+  float* part_s = (float*)w;           w += align256((size_t)pl.n_items * fk::BM * fk::NSCAL * 4);
+  float* part_o = (float*)w;           w += align256((size_t)pl.n_items * fk::BM * fk::D * 4);
+  int* flags = (int*)w;
+  XR_CUDA(cudaMemsetAsync(flags, 0, 256, s));
+
+  CUtensorMap tq, tp, tn;
+  int rc;
+  if ((rc = make_tmap_bf16_rows(&tq, q, m, dim, dim, fk::BM))) return rc;
+  if ((rc = make_tmap_bf16_rows(&tp, pos, m, dim, dim, fk::BN))) return rc;
+  if ((rc = make_tmap_bf16_rows(&tn, neg, cn, dim, dim, fk::BN))) return rc;
+
+  // pass 1: target logits q_i . pos_i from the diagonal of Q_blk . Pos_blk^T, through the SAME
+  // MMA instruction sequence as every pool logit, so a pool entry equal to the row's positive
+  // ties exactly and the strict '<' of losses.py:292 masks it (as one bmm does in the reference)
+  FusedParams pd{};
+  pd.m = (int)m; pd.cn = (int)m; pd.nt_count = 0; pd.spl = 1; pd.tiles_per_split = 2;
+  pd.n_items = pl.rb; pd.t_out = t_buf; pd.hang_flag = flags;
+  if ((rc = launch_fused<fk::KIND_DIAG>(tq, tp, pd, pl.rb < n_sm ? pl.rb : n_sm, s))) return rc;
+
+  const float* zref = nullptr;
+  if (loss_kind == XR_LOSS_INFONCE && !cfg->mask_false_negatives) {
+    unsigned* nmax = (unsigned*)(flags + 8);
+    negnorm_max_kernel<<<n_sm * 4, 256, 0, s>>>((const __nv_bfloat16*)neg, cn, nmax);
+    XR_LAUNCH_CHECK("negnorm_max");
+    zref_bound_kernel<<<n_sm * 4, 256, 0, s>>>((const __nv_bfloat16*)q, t_buf, nmax, m, cfg->scale,
+                                               cfg->logits_bf16, zref_buf);
+    XR_LAUNCH_CHECK("zref_bound");
+    zref = zref_buf;
+  }
+
+  FusedParams p{};
+  p.m = (int)m; p.cn = (int)cn; p.nt_count = pl.nt; p.spl = pl.spl; p.tiles_per_split = pl.tps;
+  p.n_items = pl.n_items; p.mask_fn = cfg->mask_false_negatives; p.logits_bf16 = cfg->logits_bf16;
+  p.with_grad = dq != nullptr; p.scale = cfg->scale; p.margin = cfg->margin;
+  p.t = t_buf; p.zref = zref; p.part_o = part_o; p.part_s = part_s; p.hang_flag = flags;
+  const int grid = pl.n_items < n_sm ? pl.n_items : n_sm;
+  switch (loss_kind) {
+    case XR_LOSS_INFONCE: rc = launch_fused<XR_LOSS_INFONCE>(tq, tn, p, grid, s); break;
+    case XR_LOSS_NCE: rc = launch_fused<XR_LOSS_NCE>(tq, tn, p, grid, s); break;
+    case XR_LOSS_PAIRWISE_HINGE: rc = launch_fused<XR_LOSS_PAIRWISE_HINGE>(tq, tn, p, grid, s); break;
+    case XR_LOSS_PAIRWISE_LOGISTIC: rc = launch_fused<XR_LOSS_PAIRWISE_LOGISTIC>(tq, tn, p, grid, s); break;
+    case XR_LOSS_CONTRASTIVE: rc = launch_fused<XR_LOSS_CONTRASTIVE>(tq, tn, p, grid, s); break;
+    default: rc = launch_fused<XR_LOSS_ALIGNMENT_CONTRASTIVE>(tq, tn, p, grid, s); break;
+  }
+  if (rc) return rc;
+
+  float* rl = row_loss ? row_loss : rl_buf;
+  fused_finalize_kernel<<<n_sm * 4, 256, 0, s>>>(
+      part_o, part_s, t_buf, zref, (const __nv_bfloat16*)q, (const __nv_bfloat16*)pos, q_inv_norm,
+      (int)m, pl.spl, loss_kind, cfg->logits_bf16, cfg->scale, cfg->margin, grad_scale, dq, rl);
+  XR_LAUNCH_CHECK("fused_finalize");
+  sum_rows_kernel<<<1, 1024, 0, s>>>(rl, m, loss_out);
+  XR_LAUNCH_CHECK("sum_rows");
+  return XR_OK;
+}
+
+// score + top-k fusion is provided by score_topk_sm100.cu when present
+#ifndef XR_HAVE_SCORE_TOPK
+extern "C" size_t xr_score_topk_workspace_bytes(int64_t, int64_t, int64_t) { return 0; }
+extern "C" int xr_score_topk(const void*, int64_t, const void*, int64_t, int64_t, const float*,
+                             const float*, int64_t, int64_t, const int64_t*, const int64_t*, float*,
+                             int64_t*, void*, size_t, void*) {
+  xr::set_error("xr_score_topk: not compiled into this build");
+  return XR_E_UNSUPPORTED;
+}
+#endif

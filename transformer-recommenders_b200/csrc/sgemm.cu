@@ -186,19 +186,21 @@ static int launch_sgemm(const TA* A, int64_t lda, const TB* B, int64_t ldb, floa
   return XR_OK;
 }
 
-// out[i*ld_out] = a_i . b_i   (one warp per row)
+// out[i*ld_out] = a_i . b_i, accumulated in EXACTLY the order sgemm_kernel uses for one output
+// element (a single fmaf chain over k = 0..dim-1).  In the reference the positive and the
+// negatives of a row come out of one bmm, so a pool entry that is the row's own positive item
+// has a bit-identical logit and the strict '<' of losses.py:292 masks it; keeping the two
+// reduction orders identical preserves that tie.  One thread per row (M x dim FMAs: negligible).
 template <typename T>
 __global__ void rowdot_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t m,
                               int64_t dim, float* __restrict__ out, int64_t ld_out) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t r = warp; r < m; r += nwarps) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < m;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    const T* pa = a + r * dim;
+    const T* pb = b + r * dim;
     float s = 0.f;
-    for (int64_t c = lane; c < dim; c += 32)
-      s = fmaf(to_f32(a[r * dim + c]), to_f32(b[r * dim + c]), s);
-    s = warp_sum(s);
-    if (lane == 0) out[r * ld_out] = s;
+    for (int64_t c = 0; c < dim; ++c) s = fmaf(to_f32(pa[c]), to_f32(pb[c]), s);
+    out[r * ld_out] = s;
   }
 }
 
@@ -252,13 +254,13 @@ extern "C" int xr_logits_pool(const void* q, const void* pos, const void* neg, i
   // layout: columns [0,cn) negatives, column cn the positive (keeps the GEMM operands aligned;
   // callers pass target_mode = explicit "last" to xr_rowloss)
   if (dtype == XR_F32) {
-    rowdot_kernel<float><<<warp_grid(m), 256, 0, s>>>((const float*)q, (const float*)pos, m, dim,
+    rowdot_kernel<float><<<(unsigned)((m + 127) / 128), 128, 0, s>>>((const float*)q, (const float*)pos, m, dim,
                                                       logits + cn, ld);
     XR_LAUNCH_CHECK("rowdot");
     return launch_sgemm<float, float, false>((const float*)q, dim, (const float*)neg, dim, logits,
                                              ld, m, cn, dim, nullptr, nullptr, s);
   } else if (dtype == XR_BF16) {
-    rowdot_kernel<__nv_bfloat16><<<warp_grid(m), 256, 0, s>>>(
+    rowdot_kernel<__nv_bfloat16><<<(unsigned)((m + 127) / 128), 128, 0, s>>>(
         (const __nv_bfloat16*)q, (const __nv_bfloat16*)pos, m, dim, logits + cn, ld);
     XR_LAUNCH_CHECK("rowdot");
     return launch_sgemm<__nv_bfloat16, __nv_bfloat16, false>(

@@ -10,6 +10,7 @@ yxtay/transformer-recommenders behind the reference's own Python interfaces.
 """
 
 from . import _native, ops  # noqa: F401
+from . import dist, index, losses, metrics, models, params  # noqa: F401
 from .losses import (  # noqa: F401
     LOSS_CLASSES,
     AlignmentContrastiveLoss,

@@ -227,6 +227,11 @@ class EmbedLoss(torch.nn.Module, abc.ABC):
                 "gradients w.r.t. candidate_embed are not produced: the item table is frozen in the "
                 "reference (models.py:251-253); detach the candidates"
             )
+        if m == 0:  # empty batch: every sum is 0 (and the stats block reports zero rows)
+            z = torch.zeros(N.XR_NUM_LOSSES, dtype=torch.float64, device=query_embed.device)
+            st = torch.zeros(N.XR_STATS_SLOTS, dtype=torch.float64, device=query_embed.device)
+            dq0 = torch.zeros_like(query_embed, dtype=torch.float32) if need_grad else None
+            return z, (st if want_stats else None), dq0
         cdt, logits_bf16 = self._compute_dtype(query_embed)
         cfg = ops.make_cfg(self.config, logits_bf16=logits_bf16)
         kind = N.LOSS_KIND.get(type(self).__name__, -1)

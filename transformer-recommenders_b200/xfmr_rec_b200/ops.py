@@ -79,6 +79,8 @@ def gather_rows(table, idx, sel=None, out_dtype=None, n_out=None, check=False):
         n *= int(s)
     out = torch.empty((n, table.size(1)), dtype=out_dtype, device=dev)
     err = torch.zeros(1, dtype=torch.int32, device=dev) if check else None
+    if n == 0:
+        return out.view(*lead, table.size(1))
     with torch.cuda.device(dev):
         N.call("xr_gather_rows", _p(table), table.size(0), table.size(1), _dt(table), _p(idx),
                _p(sel), n, _p(out), _DT[out_dtype], _p(err), _stream())
@@ -91,6 +93,8 @@ def scatter_rows(src, sel, n_dst_rows):
     dev = _require_cuda(src, sel)
     src = src.contiguous().float()
     dst = torch.zeros((n_dst_rows, src.size(1)), dtype=torch.float32, device=dev)
+    if src.size(0) == 0:
+        return dst
     with torch.cuda.device(dev):
         N.call("xr_scatter_rows", _p(src), src.size(0), src.size(1), _p(sel), _p(dst), n_dst_rows,
                _stream())
@@ -120,6 +124,8 @@ def compact_positions(history_idx, pos_idx, rownz=None, n_table_rows=0):
     pos_mask = torch.empty(n, dtype=torch.uint8, device=dev)
     counts = torch.zeros(2, dtype=torch.int64, device=dev)
     ws = _ws(N.lib().xr_compact_workspace_bytes(n), dev)
+    if n == 0:
+        return attn.view(history_idx.shape).bool(), sel_attn, sel_pos, pos_mask.bool()
     with torch.cuda.device(dev):
         N.call("xr_compact_positions", _p(h), _p(p), _p(rownz), n_table_rows, n, _p(attn),
                _p(sel_attn), _p(sel_pos), _p(pos_mask), _p(counts), _p(ws), _stream())
@@ -133,6 +139,8 @@ def normalize_rows(x, eps=1e-8, out_dtype=None, want_y=True):
     out_dtype = out_dtype or x.dtype
     y = torch.empty(x2.shape, dtype=out_dtype, device=dev) if want_y else None
     inv = torch.empty(x2.size(0), dtype=torch.float32, device=dev)
+    if x2.size(0) == 0:
+        return (y.view(x.shape) if want_y else None), inv.view(x.shape[:-1])
     with torch.cuda.device(dev):
         N.call("xr_normalize_rows", _p(x2), x2.size(0), x2.size(1), _dt(x2), float(eps), _p(y),
                _DT[out_dtype], _p(inv), _stream())
@@ -300,6 +308,9 @@ def topk(score_mat, k, n=None, col_offset=0):
     score_mat = score_mat if score_mat.stride(1) == 1 else score_mat.contiguous()
     u, ld = score_mat.size(0), score_mat.stride(0)
     n = score_mat.size(1) if n is None else n
+    if u <= 1 or ld < n:  # a single row's stride is arbitrary
+        score_mat = score_mat.contiguous()
+        ld = max(score_mat.size(1), 1)
     out_s = torch.empty((u, k), dtype=torch.float32, device=dev)
     out_i = torch.empty((u, k), dtype=torch.int64, device=dev)
     step = 65535
