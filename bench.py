@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py — scoring-and-loss train step (BASELINE config 2) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (`config.workload`): MovieLens-20M-shaped synthetic batch — 27,278 items, 384-d frozen
+item table, B=128 sequences of up to L=200 positions, InfoNCE (sampled softmax) with the
+in-batch shared negative pool, bf16 tensor-core arithmetic.  One step = one pass of the hot path
+over one batch: index compaction + the three embedding gathers (compute_embeds,
+models.py:366-419) + fused contraction / loss / gradient (losses.py:150-155, 479-488) +
+the scatter of dL/dquery back to the encoder-output layout.  The sequence encoder is outside the
+path (north_star); a random (B, L, 384) tensor stands in for its output.
+
+`value`  : sequences/s with every input already resident in HBM.
+`e2e`    : the same step through the public API with HOST (pinned) inputs: per step the index
+           tensors and the encoder-output stand-in are copied host->device and the loss scalar is
+           read back.
+`roofline`: the fused tcgen05 kernel alone, timed per launch with CUDA events on its stream,
+           4*M*C*D algorithmic FLOPs (scores + dQ) against the measured sustained bf16 peak.
+`cpu_baseline` / `--impl reference`: the reference's arithmetic in torch CPU ops on all host
+           threads (oracle/cpu_baseline.py; the reference is Python and cannot travel).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+for _p in (ROOT, ROOT / "transformer-recommenders_b200"):
+    if str(_p) not in sys.path:
+        sys.path.insert(0, str(_p))
+
+N_ITEMS, BATCH, SEQ_LEN, DIM = 27278, 128, 200, 384
+WORKLOAD = ("ML-20M-shaped synthetic (27,278 items, 384-d), B=128 x L=200, InfoNCE in-batch "
+            "shared-pool negatives, bf16 (BASELINE configs[1])")
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def reference_arm(args, rank, world):
+    """The reference's CPU path for the same workload, all host threads (rank 0 only)."""
+    if rank != 0:
+        return
+    import torch
+
+    from oracle import cpu_baseline, xfmr_oracle as orc
+
+    batch = orc.synth_batch(N_ITEMS, BATCH, SEQ_LEN, dim=DIM, seed=0)
+    cores = os.cpu_count() or 1
+    times = cpu_baseline.time_train_steps(batch, args.steps, warmup=max(1, min(args.warmup, 2)))
+    ms = 1e3 * sum(times) / len(times)
+    value = BATCH / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "train seq/sec (scoring-and-loss step)", "value": value,
+        "unit": "seq/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": BATCH, "seq_len": SEQ_LEN},
+        "cpu_baseline": {"value": value, "unit": "seq/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full steps (B={BATCH}) of the same workload, "
+                                   "reference-lean form, torch CPU ops, fp32"},
+        "e2e": {"value": value, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "torch_threads": torch.get_num_threads(),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-retrieval", action="store_true")
+    ap.add_argument("--catalog", type=int, default=10_000_000)
+    ap.add_argument("--queries", type=int, default=256)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import xfmr_rec_b200 as xr
+    from oracle import xfmr_oracle as orc  # synthetic inputs + cpu_baseline leg only
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    peak_tf, peak_hbm, peak_src = load_peaks()
+
+    # ---- synthetic inputs, per-rank seed = rank: weak scaling ----------------------
+    batch = orc.synth_batch(N_ITEMS, BATCH, SEQ_LEN, dim=DIM, seed=rank)
+    emb = xr.models.ItemEmbeddings(torch.from_numpy(batch["table"]), add_padding_row=False).to(dev)
+    emb.weight_bf16(), emb.rownz()
+    host = {k: torch.from_numpy(batch[k]).pin_memory() for k in
+            ("history_item_idx", "pos_item_idx", "neg_item_idx")}
+    host_tok = torch.from_numpy(batch["token_embeddings"]).bfloat16().pin_memory()
+    d_idx = {k: v.to(dev) for k, v in host.items()}
+    d_tok = host_tok.to(dev)
+    loss_fn = xr.InfoNCELoss(xr.LossConfig())
+    # the second operand set exists so consecutive timed steps never touch the same HBM lines:
+    # per-step traffic (~70 MB incl. partials) is below the 126 MB L2, so L2 is flushed between
+    # timed iterations by writing a 256 MB buffer
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_device():
+        tok = d_tok.detach().requires_grad_(True)
+        out = xr.models.compute_embeds(emb, tok, d_idx["history_item_idx"], d_idx["pos_item_idx"],
+                                       d_idx["neg_item_idx"], candidate_dtype=torch.bfloat16)
+        loss = loss_fn(out["query_embed"], out["candidate_embed"])
+        loss.backward()
+        return loss, tok.grad, out
+
+    def step_e2e():
+        idx = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        tok = host_tok.to(dev, non_blocking=True).requires_grad_(True)
+        out = xr.models.compute_embeds(emb, tok, idx["history_item_idx"], idx["pos_item_idx"],
+                                       idx["neg_item_idx"], candidate_dtype=torch.bfloat16)
+        loss = loss_fn(out["query_embed"], out["candidate_embed"])
+        loss.backward()
+        return float(loss)  # device -> host read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        if profile:
+            xr._native.lib().xr_fused_profile(1)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+               for _ in range(steps)]
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        last = None
+        for a, b in evs:
+            flush.fill_(1)      # L2 flush between timed iterations (not timed)
+            a.record()
+            last = fn()
+            b.record()
+        barrier()
+        clocks = sampler.stop()
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        if world > 1:
+            t = torch.tensor([total_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t)
+        return total_ms, clocks, last
+
+    # ---- device-resident throughput ---------------------------------------------------------------
+    total_ms, clocks, last = timed(step_device, args.steps, args.warmup, profile=True)
+    loss_val, _, out = last
+    m_rows = out["query_embed"].size(0)
+    c_cols = out["candidate_embed"].size(1)
+    import ctypes
+
+    buf = (ctypes.c_float * 512)()
+    n_prof = xr._native.lib().xr_fused_profile_read(buf, 512)
+    xr._native.lib().xr_fused_profile(0)
+    kern_ms = [buf[i] for i in range(max(n_prof, 0))]
+    ms_per_step = total_ms / args.steps
+    value = world * BATCH / (ms_per_step / 1e3)
+
+    # ---- end to end: host buffers in, loss scalar out --------------------------------------------
+    e2e_ms, _, _ = timed(step_e2e, args.steps, args.warmup)
+    e2e_value = world * BATCH / (e2e_ms / args.steps / 1e3)
+    h2d = sum(v.numel() * v.element_size() for v in host.values()) + host_tok.numel() * 2
+    d2h = 4
+
+    flops = 4.0 * m_rows * c_cols * DIM          # scores + dQ, table frozen
+    k_ms = statistics.mean(kern_ms) if kern_ms else float("nan")
+    achieved = flops / (k_ms * 1e-3) / 1e12 if kern_ms else float("nan")
+    line = {
+        "metric": "train seq/sec (scoring-and-loss step)", "value": value, "unit": "seq/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "seq_len": SEQ_LEN,
+                   "rows_M": m_rows, "candidates_C": c_cols, "l2": "flushed between timed steps "
+                   "(256 MB write)", "parallelism": f"dp{world} (independent batches, table replicated)"},
+        "e2e": {"value": e2e_value, "unit": "seq/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": 11 * args.steps,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "fused_pool_kernel<InfoNCE> (tcgen05)",
+                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": achieved / peak_tf if kern_ms else None, "traffic": None,
+                     "peak_source": f"{peak_src} sustained bf16 (MEASURED_PEAKS.json)",
+                     "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step if kern_ms else None,
+                     "algorithmic_flops_per_launch": flops},
+        "loss": float(loss_val),
+    }
+
+    if rank == 0:
+        # ---- CPU baseline: same workload, reference arithmetic on the host cores ------------------
+        from oracle import cpu_baseline
+
+        b0 = orc.synth_batch(N_ITEMS, BATCH, SEQ_LEN, dim=DIM, seed=0)
+        times = cpu_baseline.time_train_steps(b0, args.cpu_steps, warmup=1)
+        cpu_ms = 1e3 * sum(times) / len(times)
+        line["cpu_baseline"] = {"value": BATCH / (cpu_ms / 1e3), "unit": "seq/s",
+                                "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"{args.cpu_steps} full steps (B={BATCH}) of the same "
+                                          "workload, reference-lean torch CPU ops, fp32",
+                                "ms_per_step": cpu_ms}
+
+    if not args.no_retrieval:
+        line["retrieval"] = bench_retrieval(args, xr, dev, rank, world, peak_hbm)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_retrieval(args, xr, dev, rank, world, peak_hbm):
+    """Secondary metric of BASELINE.json: full-catalog top-100 queries/s, catalog sharded by rows
+    across ranks, per-shard top-k merged after one NCCL all-gather (BASELINE configs[3])."""
+    import torch
+
+    from xfmr_rec_b200.dist import ShardedIndex, shard_range
+
+    n, u, k = args.catalog, args.queries, 100
+    lo, hi = shard_range(n, rank, world)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    shard = torch.randn((hi - lo, DIM), generator=g, device=dev, dtype=torch.float32).bfloat16()
+    idx = xr.index.ExactIndex(xr.index.ExactIndexConfig(index_metric="cosine", dtype="bf16"), dev,
+                              row_offset=lo)
+    idx.catalog = shard  # rows are i.i.d. normal: norms ~ sqrt(384); normalise in place
+    idx.catalog, _ = xr.ops.normalize_rows(shard, 1e-12, torch.bfloat16)
+    del shard
+    sharded = ShardedIndex(idx)
+    gq = torch.Generator(device=dev).manual_seed(99)
+    q = torch.randn((u, DIM), generator=gq, device=dev)
+    excl = None
+    for _ in range(2):
+        sharded.search_batch(q, excl, k)
+    torch.cuda.synchronize()
+    reps = 5
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        s, i = sharded.search_batch(q, excl, k)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    return {"metric": "full-catalog top-100 queries/sec", "value": u / (ms / 1e3), "unit": "queries/s",
+            "catalog_rows": n, "queries": u, "k": k, "ms_per_batch": ms, "dtype": "bf16",
+            "path": "fused tcgen05 score+topk" if xr.ops.score_topk_supported(q.bfloat16(), idx.catalog)
+            else "scores (fp32-accumulate GEMM) + streaming top-k + merge",
+            "catalog_bytes_per_rank": (hi - lo) * DIM * 2}
+
+
+if __name__ == "__main__":
+    main()

@@ -187,6 +187,11 @@ int xr_dq_sampled(const float* dlogits, int64_t ld, const void* q, const void* t
  *   loss_out : float64[1] sum over rows;  row_loss (nullable): float32[M].
  *   q_inv_norm (cosine kinds only): float32[M].
  *   workspace: >= xr_fused_pool_workspace_bytes(m, cn, dim) bytes.                            */
+int xr_fused_available(void); /* bit 0: fused loss kernel, bit 1: fused score+top-k kernel */
+/* measurement hook: record a CUDA event pair around every main fused-kernel launch (ring of
+ * 512); xr_fused_profile_read copies the durations in ms to HOST memory and resets the ring. */
+int xr_fused_profile(int enable);
+int xr_fused_profile_read(float* ms_out_host, int max_n);
 size_t xr_fused_pool_workspace_bytes(int64_t m, int64_t cn, int64_t dim);
 int xr_fused_pool_loss(const void* q, const void* pos, const void* neg, int64_t m, int64_t cn,
                        int64_t dim, int loss_kind, const xr_loss_config* cfg,
@@ -218,6 +223,17 @@ int xr_scores(const void* q, int64_t u, const void* catalog, int64_t n, int64_t 
               void* stream);
 int xr_mask_excluded(float* scores, int64_t u, int64_t n, int64_t ld, int64_t col_offset,
                      const int64_t* excl_offsets, const int64_t* excl_ids, void* stream);
+
+/* fused tcgen05 scoring + top-k over one catalog shard (bf16, dim 384): scores = Q . Cat^T on the
+ * tensor cores, threshold-filtered selection in the epilogue, no (U,N) score matrix in HBM.
+ * Same result as xr_scores + xr_mask_excluded + xr_topk.  Returns XR_E_UNSUPPORTED when the
+ * kernel is not part of the build (xr_fused_available() bit 1).                                */
+size_t xr_score_topk_workspace_bytes(int64_t u, int64_t n, int64_t k);
+int xr_score_topk(const void* q, int64_t u, const void* catalog, int64_t n, int64_t dim,
+                  const float* q_inv_norm, const float* cat_inv_norm, int64_t k,
+                  int64_t col_offset, const int64_t* excl_offsets, const int64_t* excl_ids,
+                  float* out_scores, int64_t* out_idx, void* workspace, size_t workspace_bytes,
+                  void* stream);
 
 /* ---- retrieval metrics -------------------------------------------------------------------------
  * compute_retrieval_metrics, metrics.py:62-79 (+ torchmetrics 1.9.0 functional definitions),

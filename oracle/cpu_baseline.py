@@ -1,0 +1,82 @@
+"""CPU timing baseline ("port"): the reference's arithmetic for the bench workload, written
+with the same torch CPU ops the reference dispatches to, on all host threads.
+
+TEST / MEASUREMENT INFRASTRUCTURE ONLY (see oracle/xfmr_oracle.py header).  Used by
+``bench.py``'s ``cpu_baseline`` leg and by ``bench.py --impl reference`` — the reference
+itself is Python that cannot travel to the GPU box, and its verbatim (M, 1+M, D) candidate
+tensor does not fit host RAM at the benchmark shape (62.9 GB per copy at M=6400),
+so this is the "reference-lean" form of BASELINE.md §4: the reference's own
+check_target / mask_false_negatives / loss bodies (losses.py:289-292, 483-488) applied to
+``[rowdot(q,pos) | Q.Neg^T]`` logits, forward + backward to dL/dquery, fp32.
+"""
+
+from __future__ import annotations
+
+import time
+
+import torch
+import torch.nn.functional as F
+
+
+def compute_embeds_lean(table, tokens, hist, pos, neg):
+    """models.py:388-416 without the expand+cat (pos rows, shared negative pool)."""
+    input_embeds = table[hist]                       # models.py:336-338
+    attention_mask = (input_embeds != 0).any(-1)     # models.py:343
+    query = tokens[attention_mask]                   # models.py:392
+    pos_sel = pos[attention_mask]
+    pos_embed = table[pos_sel]                       # models.py:400
+    neg_embed = table[neg[attention_mask]]           # models.py:406
+    pos_mask = pos_sel != 0                          # models.py:413
+    return query[pos_mask], pos_embed[pos_mask], neg_embed
+
+
+def infonce_lean(query, pos_embed, neg_embed, scale=1.0, mask_false_negatives=True):
+    """losses.py:195 (as one GEMM) + :289-292 + :483-488."""
+    logits = torch.cat([(query * pos_embed).sum(-1, keepdim=True), query @ neg_embed.T], dim=1)
+    target = torch.zeros(logits.size(0), dtype=torch.long)
+    if mask_false_negatives:
+        neg_mask = logits < logits.gather(1, target[:, None])
+    else:
+        neg_mask = torch.ones_like(logits, dtype=torch.bool).scatter(1, target[:, None], False)
+    keep = neg_mask.scatter(1, target[:, None], True)
+    z = logits.where(keep, -torch.inf) * scale
+    return F.cross_entropy(z, target, reduction="sum")
+
+
+def train_step(table, tokens, hist, pos, neg):
+    """One scoring-and-loss step: gathers + logits + InfoNCE forward + backward to dL/dtokens."""
+    tokens = tokens.detach().requires_grad_(True)
+    q, p, n = compute_embeds_lean(table, tokens, hist, pos, neg)
+    loss = infonce_lean(q, p, n)
+    loss.backward()
+    return float(loss.detach()), tokens.grad
+
+
+def exact_search(queries, catalog_normed, k, chunk=262144):
+    """Exact cosine top-k (stable sort), the computation index.py:244-254 approximates."""
+    q = F.normalize(queries, dim=-1)
+    best_s = torch.full((q.size(0), 0), -torch.inf)
+    best_i = torch.zeros((q.size(0), 0), dtype=torch.long)
+    for lo in range(0, catalog_normed.size(0), chunk):
+        s = q @ catalog_normed[lo:lo + chunk].T
+        ids = torch.arange(lo, lo + s.size(1)).expand_as(s)
+        s, ids = torch.cat([best_s, s], 1), torch.cat([best_i, ids], 1)
+        order = torch.sort(s, dim=1, descending=True, stable=True).indices[:, :k]
+        best_s, best_i = s.gather(1, order), ids.gather(1, order)
+    return best_s, best_i
+
+
+def time_train_steps(batch, steps, warmup=1):
+    import os
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    args = [torch.from_numpy(batch[k]) for k in
+            ("table", "token_embeddings", "history_item_idx", "pos_item_idx", "neg_item_idx")]
+    for _ in range(warmup):
+        train_step(*args)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        train_step(*args)
+        times.append(time.perf_counter() - t0)
+    return times

@@ -42,7 +42,9 @@ constexpr int RING_BYTES = SLOTS * SUB_BYTES;
 constexpr int BAR_OFF = Q_BYTES + RING_BYTES;
 constexpr int NBARS = 2 * SLOTS + 8;
 constexpr int SMEM_BYTES = BAR_OFF + NBARS * 8 + 16 + 1024;  // + manual 1024 B alignment slack
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 16;           // 4 TMEM lane quadrants x 4 column groups
+constexpr int CG = 4;
+constexpr int THREADS = 64 + EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int COL_O = 0, COL_S = 384;
 constexpr int KIND_DIAG = 100;      // extract q_i . pos_i from the diagonal of Q_blk . Pos_blk^T
@@ -81,8 +83,8 @@ constexpr float kLn2 = 0.6931471805599453f;
 
 // per-element weight / loss term; returns w (goes to the dQ MMA), adds to the row scalars
 template <int KIND>
-__device__ __forceinline__ float elem(float l, bool valid, float t, float tm, float zref2,
-                                      float scale2, float scale, float margin, bool round_scaled,
+__device__ __forceinline__ float elem(float l, bool valid, float tm, float zref2, float scale2,
+                                      float scale, float margin, bool round_scaled, float& cnt,
                                       float& sum_a, float& sum_w) {
   float w = 0.f;
   if (KIND == XR_LOSS_INFONCE) {
@@ -100,22 +102,52 @@ __device__ __forceinline__ float elem(float l, bool valid, float t, float tm, fl
     w = valid ? sg : 0.f;
     sum_a += valid ? sp : 0.f;
     sum_w += w;
+    cnt += valid ? 1.f : 0.f;
   } else if (KIND == XR_LOSS_PAIRWISE_HINGE) {
     const float x = l - tm;
     const bool on = valid && x > 0.f;
     w = on ? 1.f : 0.f;
     sum_a += on ? x : 0.f;
     sum_w += w;
+    cnt += valid ? 1.f : 0.f;
   } else if (KIND == XR_LOSS_CONTRASTIVE || KIND == XR_LOSS_ALIGNMENT_CONTRASTIVE) {
     const float x = l - 1.0f + margin;
     const bool on = valid && x > 0.f;
     w = on ? 1.f : 0.f;
     sum_a += on ? x : 0.f;
+    cnt += valid ? 1.f : 0.f;
   }
   return w;
 }
 
-template <int KIND>
+// one column group (16 logits of one row) of one tile: logits -> packed bf16 weights + scalars
+template <int KIND, bool RBF, bool FULL>
+__device__ __forceinline__ void group_math(const uint32_t (&v)[16], uint32_t (&pk)[8], int ncols,
+                                           float t_eff, float tm, float zref2, float scale2,
+                                           float scale, float margin, bool round_scaled, float& cnt,
+                                           float& sum_a, float& sum_w) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) {
+    float l0 = __uint_as_float(v[j]), l1 = __uint_as_float(v[j + 1]);
+    if (RBF) {   // autocast: the bmm output is bf16 (losses.py:195 under trainer.py:450)
+      const __nv_bfloat162 h = __floats2bfloat162_rn(l0, l1);
+      const uint32_t u = *reinterpret_cast<const uint32_t*>(&h);
+      l0 = __uint_as_float(u << 16);
+      l1 = __uint_as_float(u & 0xFFFF0000u);
+    }
+    bool v0 = l0 < t_eff, v1 = l1 < t_eff;   // strict '<' (losses.py:292); t_eff = +inf if unmasked
+    if (!FULL) {
+      v0 = v0 && (j < ncols);
+      v1 = v1 && (j + 1 < ncols);
+    }
+    const float w0 = elem<KIND>(l0, v0, tm, zref2, scale2, scale, margin, round_scaled, cnt, sum_a, sum_w);
+    const float w1 = elem<KIND>(l1, v1, tm, zref2, scale2, scale, margin, round_scaled, cnt, sum_a, sum_w);
+    const __nv_bfloat162 pr = __floats2bfloat162_rn(w0, w1);
+    pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&pr);
+  }
+}
+
+template <int KIND, bool RBF>
 __global__ void __launch_bounds__(fk::THREADS, 1)
 fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
                   const __grid_constant__ CUtensorMap tmap_b, const FusedParams p) {
@@ -138,7 +170,7 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + BAR_OFF + NBARS * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool diag = (KIND == KIND_DIAG);
+  constexpr bool diag = (KIND == KIND_DIAG);
   const bool grad = !diag && p.with_grad;
 
   if (threadIdx.x == 0) {
@@ -150,10 +182,10 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
     mbar_init(bar_q_empty, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_s_full(b), 1);
-      mbar_init(bar_p_full(b), 128);
+      mbar_init(bar_p_full(b), EPI_WARPS * 32);
     }
     mbar_init(bar_o_full, 1);
-    mbar_init(bar_o_empty, 128);
+    mbar_init(bar_o_empty, EPI_WARPS * 32);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -182,94 +214,115 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      uint32_t g = 0, it = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-        int rb, t0, t1;
-        item_tiles(item, rb, t0, t1);
-        mbar_wait(bar_q_empty, (it & 1) ^ 1, p.hang_flag, 1);
+    // the whole warp walks the loop (warp-uniform control flow); one elected lane issues
+    uint32_t g = 0, it = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      int rb, t0, t1;
+      item_tiles(item, rb, t0, t1);
+      mbar_wait(bar_q_empty, (it & 1) ^ 1, p.hang_flag, 1);
+      if (elect_one()) {
         mbar_expect_tx(bar_q_full, Q_BYTES);
         for (int kb = 0; kb < KB; ++kb)
           tma_load_2d(q_smem + kb * QSUB_BYTES, &tmap_q, bar_q_full, kb * 64, rb * BM);
-        for (int t = t0; t < t1; ++t) {
-          for (int kb = 0; kb < KB; ++kb, ++g) {
-            const int s = g % SLOTS;
-            mbar_wait(bar_empty(s), ((g / SLOTS) & 1) ^ 1, p.hang_flag, 2);
+      }
+      __syncwarp();
+      for (int t = t0; t < t1; ++t) {
+        for (int kb = 0; kb < KB; ++kb, ++g) {
+          const int s = g % SLOTS;
+          mbar_wait(bar_empty(s), ((g / SLOTS) & 1) ^ 1, p.hang_flag, 2);
+          if (elect_one()) {
             mbar_expect_tx(bar_full(s), SUB_BYTES);
             tma_load_2d(ring + s * SUB_BYTES, &tmap_b, bar_full(s), kb * 64, t * BN);
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(BM, BN, 0, 0);   // S  = Q . Neg^T (both K-major)
-      constexpr uint32_t idesc_o = umma_idesc_bf16(BM, 64, 0, 1);   // dQ += W . Neg (B MN-major)
-      uint32_t g1 = 0, g2 = 0, tt = 0, it = 0;
-      // dQ += W(tile) . Neg(tile): A = W from TMEM, B = the tile's six sub-tiles, MN-major
-      auto issue_o = [&](uint32_t tile, bool first) {
-        const int b = tile & 1;
-        mbar_wait(bar_p_full(b), (tile >> 1) & 1, p.hang_flag, 3);
-        tc_fence_after();
-        const uint32_t a_tmem = tmem + COL_S + b * BN;   // packed bf16 pairs: 8 columns per K=16
+    // warp-uniform control flow; descriptors live in uniform registers, one elected lane issues
+    constexpr uint32_t idesc_s = umma_idesc_bf16(BM, BN, 0, 0);    // S  = Q . Neg^T (both K-major)
+    constexpr uint32_t idesc_o = umma_idesc_bf16(BM, 128, 0, 1);   // dQ += W . Neg  (B MN-major)
+    const uint64_t q_desc0 = umma_desc_sw128(q_smem, 16, 1024);
+    const uint64_t ring_k_desc0 = umma_desc_sw128(ring, 16, 1024);
+    // MN-major view of two adjacent sub-tiles: 64-column atoms SUB_BYTES apart, 8-row groups 1 KB
+    const uint64_t ring_mn_desc0 = umma_desc_sw128(ring, SUB_BYTES, 1024);
+    uint32_t g1 = 0, g2 = 0, tt = 0, it = 0;
+    // dQ += W(tile) . Neg(tile): A = W from TMEM (8 columns per K=16), B = the tile's sub-tiles
+    auto issue_o = [&](uint32_t tile, bool first) {
+      const int b = tile & 1;
+      if (first) mbar_wait(bar_o_empty, (it & 1) ^ 1, p.hang_flag, 5);   // epilogue drained dQ
+      mbar_wait(bar_p_full(b), (tile >> 1) & 1, p.hang_flag, 3);
+      tc_fence_after();
+      const uint32_t a_tmem = tmem + COL_S + b * BN;
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < BN / 16; ++ks) {
 #pragma unroll
-          for (int kb = 0; kb < KB; ++kb) {
-            const int s = (g2 + kb) % SLOTS;
-            const uint64_t bdesc = umma_desc_sw128(ring + s * SUB_BYTES + ks * 2048, 1024, 1024);
-            umma_ts(tmem + COL_O + kb * 64, a_tmem + ks * 8, bdesc, idesc_o,
+          for (int pr = 0; pr < KB / 2; ++pr) {
+            const uint32_t s = (g2 + 2 * pr) % SLOTS;   // even: (s, s+1) never wraps the ring
+            const uint64_t bdesc = ring_mn_desc0 + (uint64_t)((s * SUB_BYTES + ks * 2048) >> 4);
+            umma_ts(tmem + COL_O + pr * 128, a_tmem + ks * 16, bdesc, idesc_o,
                     (first && ks == 0) ? 0u : 1u);
           }
         }
-        for (int kb = 0; kb < KB; ++kb) umma_commit(bar_empty((g2 + kb) % SLOTS));
-        g2 += KB;
-      };
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-        int rb, t0, t1;
-        item_tiles(item, rb, t0, t1);
-        const int T = t1 - t0;
-        mbar_wait(bar_q_full, it & 1, p.hang_flag, 4);
-        if (grad) mbar_wait(bar_o_empty, (it & 1) ^ 1, p.hang_flag, 5);
-        tc_fence_after();
-        for (int tl = 0; tl < T; ++tl) {
-          const uint32_t tile = tt + tl;
-          const int b = tile & 1;
-          if (!grad && tile >= 2) {   // S buffer reuse: the epilogue must have drained tile-2
-            mbar_wait(bar_p_full(b), ((tile - 2) >> 1) & 1, p.hang_flag, 6);
-            tc_fence_after();
-          }
-          for (int kb = 0; kb < KB; ++kb, ++g1) {
-            const int s = g1 % SLOTS;
-            mbar_wait(bar_full(s), (g1 / SLOTS) & 1, p.hang_flag, 7);
-            tc_fence_after();
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t adesc = umma_desc_sw128(q_smem + kb * QSUB_BYTES + k * 32, 16, 1024);
-              const uint64_t bdesc = umma_desc_sw128(ring + s * SUB_BYTES + k * 32, 16, 1024);
-              umma_ss(tmem + COL_S + b * BN, adesc, bdesc, idesc_s, (kb | k) ? 1u : 0u);
-            }
+        for (int kb = 0; kb < KB; ++kb) umma_commit(bar_empty((g2 + kb) % SLOTS));
+      }
+      __syncwarp();
+      g2 += KB;
+    };
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      int rb, t0, t1;
+      item_tiles(item, rb, t0, t1);
+      const int T = t1 - t0;
+      mbar_wait(bar_q_full, it & 1, p.hang_flag, 4);
+      tc_fence_after();
+      for (int tl = 0; tl < T; ++tl) {
+        const uint32_t tile = tt + tl;
+        const int b = tile & 1;
+        if (!grad && tile >= 2) {   // S buffer reuse: the epilogue must have drained tile-2
+          mbar_wait(bar_p_full(b), ((tile - 2) >> 1) & 1, p.hang_flag, 6);
+          tc_fence_after();
+        }
+#pragma unroll 1
+        for (int kb = 0; kb < KB; ++kb, ++g1) {
+          const uint32_t s = g1 % SLOTS;
+          mbar_wait(bar_full(s), (g1 / SLOTS) & 1, p.hang_flag, 7);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t a0 = q_desc0 + (uint64_t)((kb * QSUB_BYTES) >> 4);
+            const uint64_t b0 = ring_k_desc0 + (uint64_t)((s * SUB_BYTES) >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_ss(tmem + COL_S + b * BN, a0 + 2 * k, b0 + 2 * k, idesc_s, (kb | k) ? 1u : 0u);
             if (!grad) umma_commit(bar_empty(s));   // forward only: the slot is free after S
           }
+          __syncwarp();
+        }
+        if (elect_one()) {
           umma_commit(bar_s_full(b));
           if (tl == T - 1) umma_commit(bar_q_empty);   // Q is only read by the score MMAs
-          if (grad && tl >= 1) issue_o(tile - 1, tl - 1 == 0);
         }
-        if (grad) {
-          issue_o(tt + T - 1, T == 1);
-          umma_commit(bar_o_full);
-        }
-        tt += T;
+        __syncwarp();
+        if (grad && tl >= 1) issue_o(tile - 1, tl - 1 == 0);
       }
+      if (grad) {
+        issue_o(tt + T - 1, T == 1);
+        if (elect_one()) umma_commit(bar_o_full);
+        __syncwarp();
+      }
+      tt += T;
     }
   } else {
     // ================================ epilogue warps ==============================
-    const int quad = warp & 3;                       // TMEM lane quadrant of this warp
+    // 16 warps = 4 TMEM lane quadrants x 4 column groups of 16 logits: enough warps per scheduler
+    // to hide the MUFU / conversion latencies behind each other
+    const int quad = warp & 3;                       // TMEM lane quadrant this warp may touch
+    const int cg = (warp - 2) >> 2;                  // column group
     const int r_local = quad * 32 + lane;
     const uint32_t tmem_lane = tmem + ((uint32_t)(quad * 32) << 16);
-    const bool mask_fn = p.mask_fn != 0, rbf = p.logits_bf16 != 0;
-    const bool round_scaled = rbf && p.scale != 1.0f;
+    const bool round_scaled = RBF && p.scale != 1.0f;
     const float scale2 = p.scale * kLog2e;
     uint32_t tt = 0, it = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
@@ -278,62 +331,49 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int T = t1 - t0;
       const int row = rb * BM + r_local;
       const bool row_ok = row < p.m;
-      float t = 0.f, tm = 0.f, zref2 = 0.f;
+      float t = 0.f, tm = 0.f, zref2 = 0.f, t_eff = 0.f;
       if (!diag && row_ok) {
         t = p.t[row];
-        if (rbf) t = bf16_round(t);
+        if (RBF) t = bf16_round(t);
         tm = t * (1.0f - p.margin);
         float zr;
         if (p.zref) zr = p.zref[row];
         else zr = round_scaled ? bf16_round(t * p.scale) : t * p.scale;
         zref2 = zr * kLog2e;
       }
+      t_eff = p.mask_fn ? t : CUDART_INF_F;
       float cnt = 0.f, sum_a = 0.f, sum_w = 0.f, diag_val = 0.f;
       for (int tl = 0; tl < T; ++tl) {
         const uint32_t tile = tt + tl;
         const int b = tile & 1;
         mbar_wait(bar_s_full(b), (tile >> 1) & 1, p.hang_flag, 8);
         tc_fence_after();
-        uint32_t v0[32], v1[32];
-        tmem_ld32(tmem_lane + COL_S + b * BN, v0);
-        tmem_ld32(tmem_lane + COL_S + b * BN + 32, v1);
+        uint32_t v[16];
+        tmem_ld16(tmem_lane + COL_S + b * BN + cg * 16, v);
         tmem_wait_ld();
         if (diag) {
           // tile tl holds pos rows [rb*128 + tl*64, +64): the diagonal entry of local row r is
-          // column r - tl*64 of tile tl = r/64
-          if ((r_local >> 6) == tl) {
-            const int c = r_local & 63;
+          // column r - tl*64 of tile tl = r/64, owned by column group (r%64)/16
+          if ((r_local >> 6) == tl && ((r_local & 63) >> 4) == cg) {
+            const int c = r_local & 15;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (c == j) diag_val = __uint_as_float(v0[j]);
-              if (c == 32 + j) diag_val = __uint_as_float(v1[j]);
-            }
+            for (int j = 0; j < 16; ++j)
+              if (c == j) diag_val = __uint_as_float(v[j]);
           }
         } else {
-          const int ncols = p.cn - (t0 + tl) * BN;   // valid candidates in this tile (>= 1)
-          uint32_t pk[32];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              float w2[2];
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int c = h * 32 + j + e;
-                float l = __uint_as_float(h == 0 ? v0[j + e] : v1[j + e]);
-                if (rbf) l = bf16_round(l);
-                bool valid = c < ncols;
-                if (mask_fn) valid = valid && (l < t);
-                cnt += valid ? 1.f : 0.f;
-                w2[e] = elem<KIND>(l, valid, t, tm, zref2, scale2, p.scale, p.margin, round_scaled,
-                                   sum_a, sum_w);
-              }
-              const __nv_bfloat162 pr = __floats2bfloat162_rn(w2[0], w2[1]);
-              pk[(h * 32 + j) >> 1] = *reinterpret_cast<const uint32_t*>(&pr);
-            }
-          }
+          const int ncols = p.cn - (t0 + tl) * BN - cg * 16;   // valid candidates in this group
+          uint32_t pk[8];
+          if (ncols >= 16)
+            group_math<KIND, RBF, true>(v, pk, ncols, t_eff, tm, zref2, scale2, p.scale, p.margin,
+                                        round_scaled, cnt, sum_a, sum_w);
+          else
+            group_math<KIND, RBF, false>(v, pk, ncols, t_eff, tm, zref2, scale2, p.scale, p.margin,
+                                         round_scaled, cnt, sum_a, sum_w);
           if (grad) {
-            tmem_st32(tmem_lane + COL_S + b * BN, pk);   // W overwrites the S columns it came from
+            // W goes back into the first 8 of this group's OWN 16 columns (already in registers),
+            // so no other warp's unread logits are overwritten; K-step ks of the dQ MMA reads
+            // columns [16 ks, 16 ks + 8)
+            tmem_st8(tmem_lane + COL_S + b * BN + cg * 16, pk);
             tmem_wait_st();
           }
         }
@@ -341,16 +381,16 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
         mbar_arrive(bar_p_full(b));
       }
       if (diag) {
-        if (row_ok) p.t_out[row] = diag_val;
+        if (row_ok && (r_local & 63) >> 4 == cg) p.t_out[row] = diag_val;
       } else {
         if (grad) {
           mbar_wait(bar_o_full, it & 1, p.hang_flag, 9);
           tc_fence_after();
-          float* dst = p.part_o + ((size_t)item * BM + r_local) * D;
+          float* dst = p.part_o + ((size_t)item * BM + r_local) * D + cg * (D / CG);
 #pragma unroll 1
-          for (int c = 0; c < D / 32; ++c) {
+          for (int c = 0; c < D / CG / 32; ++c) {
             uint32_t o[32];
-            tmem_ld32(tmem_lane + COL_O + c * 32, o);
+            tmem_ld32(tmem_lane + COL_O + cg * (D / CG) + c * 32, o);
             tmem_wait_ld();
             if (row_ok) {
 #pragma unroll
@@ -362,7 +402,7 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
           mbar_arrive(bar_o_empty);
         }
         if (row_ok) {
-          float* ds = p.part_s + ((size_t)item * BM + r_local) * NSCAL;
+          float* ds = p.part_s + (((size_t)item * CG + cg) * BM + r_local) * NSCAL;
           *reinterpret_cast<float4*>(ds) = make_float4(cnt, sum_a, sum_w, 0.f);
         }
       }
@@ -399,8 +439,11 @@ fused_finalize_kernel(const float* __restrict__ part_o, const float* __restrict_
     for (int c = 0; c < D / 32; ++c) o[c] = 0.f;
     for (int sp = 0; sp < spl; ++sp) {   // fixed order: deterministic
       const size_t item = (size_t)rb * spl + sp;
-      const float4 s = *reinterpret_cast<const float4*>(part_s + (item * BM + rl) * NSCAL);
-      cnt += s.x; sum_a += s.y; sum_w += s.z;
+#pragma unroll
+      for (int cg = 0; cg < CG; ++cg) {
+        const float4 s = *reinterpret_cast<const float4*>(part_s + ((item * CG + cg) * BM + rl) * NSCAL);
+        cnt += s.x; sum_a += s.y; sum_w += s.z;
+      }
       if (dq) {
         const float* src = part_o + (item * BM + rl) * D;
 #pragma unroll
@@ -597,18 +640,32 @@ static FusedPlan make_plan(int64_t m, int64_t cn, int n_sm) {
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
-template <int KIND>
-static int launch_fused(const CUtensorMap& tq, const CUtensorMap& tb, const FusedParams& p,
-                        int grid, cudaStream_t s) {
+// optional per-launch timing of the main fused kernel (bench.py's roofline leg): a ring of
+// CUDA event pairs recorded on the launching stream; nothing is synchronised until it is read.
+constexpr int kProfRing = 512;
+static bool g_prof_on = false;
+static cudaEvent_t g_prof_ev[kProfRing][2];
+static bool g_prof_made = false;
+static int g_prof_n = 0;
+
+template <int KIND, bool RBF>
+static int launch_fused1(const CUtensorMap& tq, const CUtensorMap& tb, const FusedParams& p,
+                         int grid, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    XR_CUDA(cudaFuncSetAttribute(fused_pool_kernel<KIND>,
+    XR_CUDA(cudaFuncSetAttribute(fused_pool_kernel<KIND, RBF>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, fk::SMEM_BYTES));
     configured = true;
   }
-  fused_pool_kernel<KIND><<<grid, fk::THREADS, fk::SMEM_BYTES, s>>>(tq, tb, p);
+  fused_pool_kernel<KIND, RBF><<<grid, fk::THREADS, fk::SMEM_BYTES, s>>>(tq, tb, p);
   XR_LAUNCH_CHECK("fused_pool_kernel");
   return XR_OK;
+}
+template <int KIND>
+static int launch_fused(const CUtensorMap& tq, const CUtensorMap& tb, const FusedParams& p,
+                        int grid, cudaStream_t s) {
+  return p.logits_bf16 ? launch_fused1<KIND, true>(tq, tb, p, grid, s)
+                       : launch_fused1<KIND, false>(tq, tb, p, grid, s);
 }
 
 }  // namespace xr
@@ -624,7 +681,7 @@ extern "C" size_t xr_fused_pool_workspace_bytes(int64_t m, int64_t cn, int64_t d
   b += align256((size_t)m * 4);                                   // t
   b += align256((size_t)m * 4);                                   // zref
   b += align256((size_t)m * 4);                                   // row_loss
-  b += align256((size_t)pl.n_items * fk::BM * fk::NSCAL * 4);     // partial scalars
+  b += align256((size_t)pl.n_items * fk::CG * fk::BM * fk::NSCAL * 4);   // partial scalars
   b += align256((size_t)pl.n_items * fk::BM * fk::D * 4);         // partial dQ
   b += 256;                                                       // flags
   return b;
@@ -668,7 +725,7 @@ extern "C" int xr_fused_pool_loss(const void* q, const void* pos, const void* ne
   float* t_buf = (float*)w;            w += align256((size_t)m * 4);
   float* zref_buf = (float*)w;         w += align256((size_t)m * 4);
   float* rl_buf = (float*)w;           w += align256((size_t)m * 4);
-  float* part_s = (float*)w;           w += align256((size_t)pl.n_items * fk::BM * fk::NSCAL * 4);
+  float* part_s = (float*)w;           w += align256((size_t)pl.n_items * fk::CG * fk::BM * fk::NSCAL * 4);
   float* part_o = (float*)w;           w += align256((size_t)pl.n_items * fk::BM * fk::D * 4);
   int* flags = (int*)w;
   XR_CUDA(cudaMemsetAsync(flags, 0, 256, s));
@@ -704,6 +761,8 @@ extern "C" int xr_fused_pool_loss(const void* q, const void* pos, const void* ne
   p.with_grad = dq != nullptr; p.scale = cfg->scale; p.margin = cfg->margin;
   p.t = t_buf; p.zref = zref; p.part_o = part_o; p.part_s = part_s; p.hang_flag = flags;
   const int grid = pl.n_items < n_sm ? pl.n_items : n_sm;
+  const bool prof = g_prof_on && g_prof_n < kProfRing;
+  if (prof) cudaEventRecord(g_prof_ev[g_prof_n][0], s);
   switch (loss_kind) {
     case XR_LOSS_INFONCE: rc = launch_fused<XR_LOSS_INFONCE>(tq, tn, p, grid, s); break;
     case XR_LOSS_NCE: rc = launch_fused<XR_LOSS_NCE>(tq, tn, p, grid, s); break;
@@ -712,6 +771,7 @@ extern "C" int xr_fused_pool_loss(const void* q, const void* pos, const void* ne
     case XR_LOSS_CONTRASTIVE: rc = launch_fused<XR_LOSS_CONTRASTIVE>(tq, tn, p, grid, s); break;
     default: rc = launch_fused<XR_LOSS_ALIGNMENT_CONTRASTIVE>(tq, tn, p, grid, s); break;
   }
+  if (prof) cudaEventRecord(g_prof_ev[g_prof_n++][1], s);
   if (rc) return rc;
 
   float* rl = row_loss ? row_loss : rl_buf;
@@ -722,6 +782,29 @@ extern "C" int xr_fused_pool_loss(const void* q, const void* pos, const void* ne
   sum_rows_kernel<<<1, 1024, 0, s>>>(rl, m, loss_out);
   XR_LAUNCH_CHECK("sum_rows");
   return XR_OK;
+}
+
+extern "C" int xr_fused_profile(int enable) {
+  if (enable && !g_prof_made) {
+    for (int i = 0; i < kProfRing; ++i)
+      for (int j = 0; j < 2; ++j) XR_CUDA(cudaEventCreate(&g_prof_ev[i][j]));
+    g_prof_made = true;
+  }
+  g_prof_on = enable != 0;
+  g_prof_n = 0;
+  return XR_OK;
+}
+
+// durations (ms) of the main fused kernel launches recorded since xr_fused_profile(1);
+// synchronises on the recorded events.  Returns the number written (<= max_n) or <0.
+extern "C" int xr_fused_profile_read(float* ms_out_host, int max_n) {
+  int n = g_prof_n < max_n ? g_prof_n : max_n;
+  for (int i = 0; i < n; ++i) {
+    XR_CUDA(cudaEventSynchronize(g_prof_ev[i][1]));
+    XR_CUDA(cudaEventElapsedTime(&ms_out_host[i], g_prof_ev[i][0], g_prof_ev[i][1]));
+  }
+  g_prof_n = 0;
+  return n;
 }
 
 // score + top-k fusion is provided by score_topk_sm100.cu when present

@@ -15,3 +15,5 @@ extern "C" int xr_score_topk(const void*, int64_t, const void*, int64_t, int64_t
   xr::set_error("xr_score_topk: tcgen05 kernels not compiled into this build");
   return XR_E_UNSUPPORTED;
 }
+extern "C" int xr_fused_profile(int) { return XR_E_UNSUPPORTED; }
+extern "C" int xr_fused_profile_read(float*, int) { return XR_E_UNSUPPORTED; }
