@@ -53,20 +53,26 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe): an
+    `nvidia-smi -lms` child process (no GIL contention with the launch thread) started before the
+    warm-up; samples are attributed to the timed window by their wall-clock arrival time."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [x.strip() for x in vis.split(",")] if vis else []
+        phys = ids[self.gpu] if self.gpu < len(ids) and ids[self.gpu].isdigit() else str(self.gpu)
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={phys}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -74,26 +80,37 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
+        inside = [r for ts, r in self.rows if self.t0 - 0.03 <= ts <= self.t1 + 0.03]
+        window = "timed region"
+        if not inside:  # region shorter than the sampling period: use the whole loaded run
+            inside, window = [r for _, r in self.rows], "warm-up + timed region"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in inside:
             try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
             except (ValueError, IndexError):
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                                "sw_power_cap"), r[3:7]):
+                                "sw_power_cap"), r[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def reference_arm(args, rank, world):
@@ -196,6 +213,8 @@ def main():
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup, profile=False):
+        sampler = ClockSampler(local_rank)
+        sampler.start()
         for _ in range(warmup):
             fn()
         barrier()
@@ -203,15 +222,15 @@ def main():
             xr._native.lib().xr_fused_profile(1)
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                for _ in range(steps)]
-        sampler = ClockSampler(local_rank)
-        sampler.start()
         last = None
+        sampler.mark_begin()
         for a, b in evs:
             flush.fill_(1)      # L2 flush between timed iterations (not timed)
             a.record()
             last = fn()
             b.record()
         barrier()
+        sampler.mark_end()
         clocks = sampler.stop()
         total_ms = sum(a.elapsed_time(b) for a, b in evs)
         if world > 1:

@@ -34,17 +34,18 @@ constexpr int BM = 128;             // query rows per CTA tile (UMMA M)
 constexpr int BN = 64;              // candidates per tile (UMMA N of the score MMA)
 constexpr int D = 384;              // embedding dim (all-MiniLM-L6-v2, params.py:11)
 constexpr int KB = D / 64;          // 64-column (128-byte) k-blocks per row
-constexpr int SLOTS = 16;           // ring of [64 cand x 64 col] sub-tiles
+constexpr int SLOTS = 16;           // ring of [64 cand x 64 col] sub-tiles ...
+constexpr int PAIRS = SLOTS / 2;    // ... managed as 8 pairs (two adjacent k-blocks, 16 KB)
 constexpr int SUB_BYTES = BN * 64 * 2;
 constexpr int QSUB_BYTES = BM * 64 * 2;
 constexpr int Q_BYTES = KB * QSUB_BYTES;
 constexpr int RING_BYTES = SLOTS * SUB_BYTES;
 constexpr int BAR_OFF = Q_BYTES + RING_BYTES;
-constexpr int NBARS = 2 * SLOTS + 8;
+constexpr int NBARS = 2 * PAIRS + 10;
 constexpr int SMEM_BYTES = BAR_OFF + NBARS * 8 + 16 + 1024;  // + manual 1024 B alignment slack
 constexpr int EPI_WARPS = 16;           // 4 TMEM lane quadrants x 4 column groups
 constexpr int CG = 4;
-constexpr int THREADS = 64 + EPI_WARPS * 32;
+constexpr int THREADS = 128 + EPI_WARPS * 32;   // producer, 2 MMA issuers, 1 spare, 16 epilogue
 constexpr int TMEM_COLS = 512;
 constexpr int COL_O = 0, COL_S = 384;
 constexpr int KIND_DIAG = 100;      // extract q_i . pos_i from the diagonal of Q_blk . Pos_blk^T
@@ -159,14 +160,16 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const uint32_t q_smem = base;
   const uint32_t ring = base + Q_BYTES;
   const uint32_t bars = base + BAR_OFF;
-  auto bar_full = [&](int s) { return bars + 8u * s; };
-  auto bar_empty = [&](int s) { return bars + 8u * (SLOTS + s); };
-  const uint32_t bar_q_full = bars + 8u * (2 * SLOTS + 0);
-  const uint32_t bar_q_empty = bars + 8u * (2 * SLOTS + 1);
-  auto bar_s_full = [&](int b) { return bars + 8u * (2 * SLOTS + 2 + b); };
-  auto bar_p_full = [&](int b) { return bars + 8u * (2 * SLOTS + 4 + b); };
-  const uint32_t bar_o_full = bars + 8u * (2 * SLOTS + 6);
-  const uint32_t bar_o_empty = bars + 8u * (2 * SLOTS + 7);
+  // ring of PAIRS: two adjacent 64x64 sub-tiles (k-blocks 2j, 2j+1 of one candidate tile)
+  auto bar_full = [&](uint32_t s) { return bars + 8u * s; };
+  auto bar_empty = [&](uint32_t s) { return bars + 8u * (PAIRS + s); };
+  const uint32_t bar_q_full = bars + 8u * (2 * PAIRS + 0);
+  const uint32_t bar_q_empty = bars + 8u * (2 * PAIRS + 1);
+  auto bar_s_full = [&](int b) { return bars + 8u * (2 * PAIRS + 2 + b); };
+  auto bar_p_full = [&](int b) { return bars + 8u * (2 * PAIRS + 4 + b); };
+  auto bar_s_free = [&](int b) { return bars + 8u * (2 * PAIRS + 6 + b); };
+  const uint32_t bar_o_full = bars + 8u * (2 * PAIRS + 8);
+  const uint32_t bar_o_empty = bars + 8u * (2 * PAIRS + 9);
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + BAR_OFF + NBARS * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -174,7 +177,7 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const bool grad = !diag && p.with_grad;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < SLOTS; ++s) {
+    for (int s = 0; s < PAIRS; ++s) {
       mbar_init(bar_full(s), 1);
       mbar_init(bar_empty(s), 1);
     }
@@ -183,6 +186,7 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_s_full(b), 1);
       mbar_init(bar_p_full(b), EPI_WARPS * 32);
+      mbar_init(bar_s_free(b), 1);
     }
     mbar_init(bar_o_full, 1);
     mbar_init(bar_o_empty, EPI_WARPS * 32);
@@ -227,76 +231,54 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
       __syncwarp();
       for (int t = t0; t < t1; ++t) {
-        for (int kb = 0; kb < KB; ++kb, ++g) {
-          const int s = g % SLOTS;
-          mbar_wait(bar_empty(s), ((g / SLOTS) & 1) ^ 1, p.hang_flag, 2);
+#pragma unroll 1
+        for (int pr = 0; pr < KB / 2; ++pr, ++g) {
+          const uint32_t s = g & (PAIRS - 1);
+          mbar_wait(bar_empty(s), ((g / PAIRS) & 1) ^ 1, p.hang_flag, 2);
           if (elect_one()) {
-            mbar_expect_tx(bar_full(s), SUB_BYTES);
-            tma_load_2d(ring + s * SUB_BYTES, &tmap_b, bar_full(s), kb * 64, t * BN);
+            mbar_expect_tx(bar_full(s), 2 * SUB_BYTES);
+            tma_load_2d(ring + s * 2 * SUB_BYTES, &tmap_b, bar_full(s), pr * 128, t * BN);
+            tma_load_2d(ring + s * 2 * SUB_BYTES + SUB_BYTES, &tmap_b, bar_full(s), pr * 128 + 64, t * BN);
           }
           __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ==================================
+    // ========================= score MMA issuer: S = Q . Neg^T =========================
     // warp-uniform control flow; descriptors live in uniform registers, one elected lane issues
-    constexpr uint32_t idesc_s = umma_idesc_bf16(BM, BN, 0, 0);    // S  = Q . Neg^T (both K-major)
-    constexpr uint32_t idesc_o = umma_idesc_bf16(BM, 128, 0, 1);   // dQ += W . Neg  (B MN-major)
+    constexpr uint32_t idesc_s = umma_idesc_bf16(BM, BN, 0, 0);    // both operands K-major
     const uint64_t q_desc0 = umma_desc_sw128(q_smem, 16, 1024);
     const uint64_t ring_k_desc0 = umma_desc_sw128(ring, 16, 1024);
-    // MN-major view of two adjacent sub-tiles: 64-column atoms SUB_BYTES apart, 8-row groups 1 KB
-    const uint64_t ring_mn_desc0 = umma_desc_sw128(ring, SUB_BYTES, 1024);
-    uint32_t g1 = 0, g2 = 0, tt = 0, it = 0;
-    // dQ += W(tile) . Neg(tile): A = W from TMEM (8 columns per K=16), B = the tile's sub-tiles
-    auto issue_o = [&](uint32_t tile, bool first) {
-      const int b = tile & 1;
-      if (first) mbar_wait(bar_o_empty, (it & 1) ^ 1, p.hang_flag, 5);   // epilogue drained dQ
-      mbar_wait(bar_p_full(b), (tile >> 1) & 1, p.hang_flag, 3);
-      tc_fence_after();
-      const uint32_t a_tmem = tmem + COL_S + b * BN;
-      if (elect_one()) {
-#pragma unroll
-        for (int ks = 0; ks < BN / 16; ++ks) {
-#pragma unroll
-          for (int pr = 0; pr < KB / 2; ++pr) {
-            const uint32_t s = (g2 + 2 * pr) % SLOTS;   // even: (s, s+1) never wraps the ring
-            const uint64_t bdesc = ring_mn_desc0 + (uint64_t)((s * SUB_BYTES + ks * 2048) >> 4);
-            umma_ts(tmem + COL_O + pr * 128, a_tmem + ks * 16, bdesc, idesc_o,
-                    (first && ks == 0) ? 0u : 1u);
-          }
-        }
-#pragma unroll
-        for (int kb = 0; kb < KB; ++kb) umma_commit(bar_empty((g2 + kb) % SLOTS));
-      }
-      __syncwarp();
-      g2 += KB;
-    };
+    uint32_t g = 0, tt = 0, it = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
       int rb, t0, t1;
       item_tiles(item, rb, t0, t1);
       const int T = t1 - t0;
       mbar_wait(bar_q_full, it & 1, p.hang_flag, 4);
-      tc_fence_after();
       for (int tl = 0; tl < T; ++tl) {
         const uint32_t tile = tt + tl;
         const int b = tile & 1;
-        if (!grad && tile >= 2) {   // S buffer reuse: the epilogue must have drained tile-2
-          mbar_wait(bar_p_full(b), ((tile - 2) >> 1) & 1, p.hang_flag, 6);
-          tc_fence_after();
+        if (tile >= 2) {   // S/W buffer b is free once tile-2's weights were consumed
+          if (grad) mbar_wait(bar_s_free(b), ((tile - 2) >> 1) & 1, p.hang_flag, 6);
+          else mbar_wait(bar_p_full(b), ((tile - 2) >> 1) & 1, p.hang_flag, 6);
         }
+        tc_fence_after();
 #pragma unroll 1
-        for (int kb = 0; kb < KB; ++kb, ++g1) {
-          const uint32_t s = g1 % SLOTS;
-          mbar_wait(bar_full(s), (g1 / SLOTS) & 1, p.hang_flag, 7);
+        for (int pr = 0; pr < KB / 2; ++pr, ++g) {
+          const uint32_t s = g & (PAIRS - 1);
+          mbar_wait(bar_full(s), (g / PAIRS) & 1, p.hang_flag, 7);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t a0 = q_desc0 + (uint64_t)((kb * QSUB_BYTES) >> 4);
-            const uint64_t b0 = ring_k_desc0 + (uint64_t)((s * SUB_BYTES) >> 4);
+            const uint64_t a0 = q_desc0 + (uint64_t)(pr * ((2 * QSUB_BYTES) >> 4));
+            const uint64_t b0 = ring_k_desc0 + (uint64_t)(s * ((2 * SUB_BYTES) >> 4));
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_ss(tmem + COL_S + b * BN, a0 + 2 * k, b0 + 2 * k, idesc_s, (kb | k) ? 1u : 0u);
-            if (!grad) umma_commit(bar_empty(s));   // forward only: the slot is free after S
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_ss(tmem + COL_S + b * BN, a0 + h * (QSUB_BYTES >> 4) + 2 * k,
+                        b0 + h * (SUB_BYTES >> 4) + 2 * k, idesc_s, (pr | h | k) ? 1u : 0u);
+            if (!grad) umma_commit(bar_empty(s));   // forward only: the pair is free after S
           }
           __syncwarp();
         }
@@ -305,21 +287,55 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
           if (tl == T - 1) umma_commit(bar_q_empty);   // Q is only read by the score MMAs
         }
         __syncwarp();
-        if (grad && tl >= 1) issue_o(tile - 1, tl - 1 == 0);
-      }
-      if (grad) {
-        issue_o(tt + T - 1, T == 1);
-        if (elect_one()) umma_commit(bar_o_full);
-        __syncwarp();
       }
       tt += T;
     }
-  } else {
+  } else if (warp == 2) {
+    // ========================= gradient MMA issuer: dQ += W . Neg =========================
+    // A = W from TMEM (8 columns per K=16 step), B = the tile's pairs addressed MN-major
+    if (grad) {
+      constexpr uint32_t idesc_o = umma_idesc_bf16(BM, 128, 0, 1);
+      // MN-major view of a pair: two 64-column atoms SUB_BYTES apart, 8-row groups of 1 KB
+      const uint64_t ring_mn_desc0 = umma_desc_sw128(ring, SUB_BYTES, 1024);
+      uint32_t g = 0, tt = 0, it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        int rb, t0, t1;
+        item_tiles(item, rb, t0, t1);
+        const int T = t1 - t0;
+        mbar_wait(bar_o_empty, (it & 1) ^ 1, p.hang_flag, 5);   // epilogue drained the last dQ
+        for (int tl = 0; tl < T; ++tl, g += KB / 2) {
+          const uint32_t tile = tt + tl;
+          const int b = tile & 1;
+          mbar_wait(bar_p_full(b), (tile >> 1) & 1, p.hang_flag, 3);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_tmem = tmem + COL_S + b * BN;
+#pragma unroll
+            for (int ks = 0; ks < BN / 16; ++ks) {
+#pragma unroll
+              for (int pr = 0; pr < KB / 2; ++pr) {
+                const uint32_t s = (g + pr) & (PAIRS - 1);
+                const uint64_t bdesc = ring_mn_desc0 + (uint64_t)(s * ((2 * SUB_BYTES) >> 4) + ks * (2048 >> 4));
+                umma_ts(tmem + COL_O + pr * 128, a_tmem + ks * 16, bdesc, idesc_o,
+                        (tl == 0 && ks == 0) ? 0u : 1u);
+              }
+            }
+#pragma unroll
+            for (int pr = 0; pr < KB / 2; ++pr) umma_commit(bar_empty((g + pr) & (PAIRS - 1)));
+            umma_commit(bar_s_free(b));
+            if (tl == T - 1) umma_commit(bar_o_full);
+          }
+          __syncwarp();
+        }
+        tt += T;
+      }
+    }
+  } else if (warp >= 4) {
     // ================================ epilogue warps ==============================
     // 16 warps = 4 TMEM lane quadrants x 4 column groups of 16 logits: enough warps per scheduler
     // to hide the MUFU / conversion latencies behind each other
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may touch
-    const int cg = (warp - 2) >> 2;                  // column group
+    const int cg = (warp - 4) >> 2;                  // column group
     const int r_local = quad * 32 + lane;
     const uint32_t tmem_lane = tmem + ((uint32_t)(quad * 32) << 16);
     const bool round_scaled = RBF && p.scale != 1.0f;
