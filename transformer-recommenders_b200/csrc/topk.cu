@@ -68,6 +68,80 @@ __device__ __forceinline__ void compact(const TopkState& st, int k) {
   __syncthreads();
 }
 
+// Threshold refresh WITHOUT a sort: MSB-first radix select (8-bit digits) of the k-th largest
+// buffered key, then an unordered filter of the survivors.  ~8x cheaper than the bitonic sort;
+// the single ordered sort happens once, on k keys, when the block emits its result.
+// Keys are unique (the low word is the column), so exactly k keys survive.  Block-uniform call.
+__device__ __forceinline__ void compact_select(const TopkState& st, int k) {
+  __shared__ unsigned s_hist[256];
+  __shared__ unsigned s_pick[2];
+  __syncthreads();
+  const int n = *st.count;
+  if (n <= k) return;
+  constexpr int PER = TK_CAP / TK_THREADS;
+  uint64_t my[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = threadIdx.x + j * TK_THREADS;
+    my[j] = i < n ? st.keys[i] : 0ull;   // 0 never matches a live prefix bucket that is selected
+  }
+  uint64_t prefix = 0ull, mask = 0ull;
+  unsigned want = (unsigned)k;
+  const int lane = threadIdx.x & 31;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    s_hist[threadIdx.x] = 0u;   // TK_THREADS == 256 bins
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int i = threadIdx.x + j * TK_THREADS;
+      if (i < n && (my[j] & mask) == prefix) atomicAdd(&s_hist[(unsigned)(my[j] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {   // warp 0 walks the 256 bins from the top
+      unsigned c[8], tot = 0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        c[b] = s_hist[255 - (lane * 8 + b)];
+        tot += c[b];
+      }
+      unsigned incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      unsigned acc = incl - tot;
+      if (acc < want && want <= incl) {
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          if (acc < want && want <= acc + c[b]) {
+            s_pick[0] = 255u - (unsigned)(lane * 8 + b);
+            s_pick[1] = want - acc;
+          }
+          acc += c[b];
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= (uint64_t)s_pick[0] << shift;
+    mask |= 0xFFull << shift;
+    want = s_pick[1];
+  }
+  const uint64_t kth = prefix;   // all 64 bits resolved: the k-th largest key itself
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *st.count = 0;
+    *st.tau = kth;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = threadIdx.x + j * TK_THREADS;
+    if (i < n && my[j] >= kth) st.keys[atomicAdd(st.count, 1)] = my[j];
+  }
+  __syncthreads();
+}
+
 // warp-aggregated append of keys that beat the threshold
 __device__ __forceinline__ void offer(const TopkState& st, bool take, uint64_t key) {
   const unsigned bal = __ballot_sync(0xffffffffu, take);
@@ -79,12 +153,43 @@ __device__ __forceinline__ void offer(const TopkState& st, bool take, uint64_t k
   if (take) st.keys[base + __popc(bal & ((1u << lane) - 1u))] = key;
 }
 
-// SRC 0: fp32 scores (vectorised when VEC), 1: uint64 keys, 2: fp32 scores + int64 ids
-template <int SRC, bool VEC>
+// ---- generic (slow) path: SRC 0 fp32 scores, 1 uint64 keys, 2 fp32 scores + int64 ids ----------
+// one block-wide barrier per 1024 elements; used for merges, unaligned rows and as the overflow
+// fallback of the streaming fast path below.
+template <int SRC>
+__device__ __forceinline__ void slow_range(const TopkState& st, const float* srow,
+                                           const int64_t* irow, const uint64_t* krow, int64_t lo,
+                                           int64_t hi, int k) {
+  const int64_t len = hi > lo ? hi - lo : 0;
+  const int64_t iters = (len + TK_PER_ITER - 1) / TK_PER_ITER;
+  for (int64_t it = 0; it < iters; ++it) {
+    // make room: an iteration can append at most TK_PER_ITER keys (block-uniform branch)
+    if (*st.count > TK_CAP - TK_PER_ITER) compact_select(st, k);
+    const uint64_t tau = *st.tau;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int64_t e = lo + it * TK_PER_ITER + r * TK_THREADS + threadIdx.x;
+      const bool in = e < hi;
+      uint64_t key = 0;
+      if (in) {
+        if (SRC == 0) key = make_key(srow[e], (uint32_t)e);
+        else if (SRC == 1) key = krow[e];
+        else {
+          const int64_t id = irow[e];
+          key = id < 0 ? 0ull : make_key(srow[e], (uint32_t)id);
+        }
+      }
+      offer(st, in && key > tau, key);
+    }
+    __syncthreads();
+  }
+}
+
+template <int SRC>
 __global__ void __launch_bounds__(TK_THREADS)
-topk_stream_kernel(const float* __restrict__ scores, const int64_t* __restrict__ ids,
-                   const uint64_t* __restrict__ in_keys, int64_t n, int64_t ld, int64_t chunk_len,
-                   int k, uint64_t* __restrict__ out_keys /* [u][P][k] */) {
+topk_generic_kernel(const float* __restrict__ scores, const int64_t* __restrict__ ids,
+                    const uint64_t* __restrict__ in_keys, int64_t n, int64_t ld, int64_t chunk_len,
+                    int k, uint64_t* __restrict__ out_keys /* [u][P][k] */) {
   __shared__ uint64_t s_keys[TK_CAP];
   __shared__ int s_count;
   __shared__ uint64_t s_tau;
@@ -97,73 +202,113 @@ topk_stream_kernel(const float* __restrict__ scores, const int64_t* __restrict__
     s_tau = 0ull;
   }
   __syncthreads();
+  slow_range<SRC>(st, SRC != 1 ? scores + u * ld : nullptr, SRC == 2 ? ids + u * ld : nullptr,
+                  SRC == 1 ? in_keys + u * ld : nullptr, lo, hi, k);
+  compact_select(st, k);
+  compact(st, k);   // ordered emit: a sort of <= k keys
+  const int cnt = s_count < k ? s_count : k;
+  uint64_t* o = out_keys + (u * P + p) * (int64_t)k;
+  for (int i = threadIdx.x; i < k; i += TK_THREADS) o[i] = i < cnt ? s_keys[i] : 0ull;
+}
 
-  const int64_t len = hi > lo ? hi - lo : 0;
-  const int64_t iters = (len + TK_PER_ITER - 1) / TK_PER_ITER;
-  const float* srow = SRC != 1 ? scores + u * ld : nullptr;
-  const int64_t* irow = SRC == 2 ? ids + u * ld : nullptr;
-  const uint64_t* krow = SRC == 1 ? in_keys + u * ld : nullptr;
+// ---- streaming fast path over fp32 scores (16-byte aligned rows) --------------------------------
+// Super-blocks of 8 x 2048 scores with NO barrier inside: a score is compared against the float
+// threshold (one FSETP); the rare survivors build their 64-bit key, re-check it exactly and claim
+// a buffer slot with a shared-memory atomic.  If a super-block overflows the buffer (cold start,
+// adversarial input) its appends are discarded and it is replayed through the barrier-per-
+// iteration path, so the result is exact for every input.
+constexpr int TK_VEC_PER_THREAD = 2;                                  // float4 loads in flight
+constexpr int TK_FAST_ITER = TK_THREADS * 4 * TK_VEC_PER_THREAD;      // 2048 scores
+constexpr int TK_SUPER = 8 * TK_FAST_ITER;                            // 16384 scores
+constexpr int TK_BOOT = 1024;                                         // bootstrap sample
+constexpr int TK_COMPACT_AT = 640;                                    // compact early: sorts stay <= 1024 wide
 
-  float4 cur = make_float4(0, 0, 0, 0), nxt = cur;
-  auto load_vec = [&](int64_t it) -> float4 {
-    const int64_t e = lo + it * TK_PER_ITER + (int64_t)threadIdx.x * 4;
-    if (e + 3 < hi) {
-      const int4 r = ld_stream16(srow + e);
-      return make_float4(__int_as_float(r.x), __int_as_float(r.y), __int_as_float(r.z),
-                         __int_as_float(r.w));
-    }
-    float4 v;
-    v.x = e + 0 < hi ? srow[e + 0] : 0.f;
-    v.y = e + 1 < hi ? srow[e + 1] : 0.f;
-    v.z = e + 2 < hi ? srow[e + 2] : 0.f;
-    v.w = e + 3 < hi ? srow[e + 3] : 0.f;
-    return v;
-  };
-  if (SRC == 0 && VEC && iters > 0) cur = load_vec(0);
+__global__ void __launch_bounds__(TK_THREADS)
+topk_stream_kernel(const float* __restrict__ scores, int64_t n, int64_t ld, int64_t chunk_len,
+                   int k, uint64_t* __restrict__ out_keys /* [u][P][k] */) {
+  __shared__ uint64_t s_keys[TK_CAP];
+  __shared__ int s_count;
+  __shared__ int s_ovf;
+  __shared__ uint64_t s_tau;
+  TopkState st{s_keys, &s_count, &s_tau};
+  const int64_t u = blockIdx.y, p = blockIdx.x, P = gridDim.x;
+  const int64_t lo = p * chunk_len;
+  const int64_t hi = lo + chunk_len < n ? lo + chunk_len : n;
+  const float* srow = scores + u * ld;
+  if (threadIdx.x == 0) {
+    s_count = 0;
+    s_ovf = 0;
+    s_tau = 0ull;
+  }
+  __syncthreads();
 
-  for (int64_t it = 0; it < iters; ++it) {
-    // make room: an iteration can append at most TK_PER_ITER keys (block-uniform branch)
-    if (s_count > TK_CAP - TK_PER_ITER) compact(st, k);
+  // bootstrap: the first TK_CAP scores go straight into the buffer; one sort gives a threshold
+  // good enough (k-th of 2048) for the streaming loop, instead of a cold start with tau = 0
+  int64_t pos0 = lo;
+  {
+    const int64_t b_hi = lo + TK_BOOT < hi ? lo + TK_BOOT : hi;
+    for (int64_t e = lo + threadIdx.x; e < b_hi; e += TK_THREADS)
+      s_keys[e - lo] = make_key(srow[e], (uint32_t)e);
+    if (threadIdx.x == 0) s_count = (int)(b_hi - lo);
+    compact_select(st, k);
+    pos0 = b_hi;
+  }
+  // super-blocks grow geometrically (2K, 4K, 8K, 16K scores) while the threshold tightens
+  int64_t sb_len = TK_FAST_ITER;
+  for (int64_t sb = pos0; sb < hi; sb += sb_len, sb_len = sb_len < TK_SUPER ? sb_len * 2 : TK_SUPER) {
+    const int64_t sb_hi = sb + sb_len < hi ? sb + sb_len : hi;
+    const int64_t full_hi = sb + (sb_hi - sb) / TK_FAST_ITER * TK_FAST_ITER;   // whole iterations
     const uint64_t tau = s_tau;
-    const uint32_t tau_hi = (uint32_t)(tau >> 32);
-    if (SRC == 0 && VEC) {
-      if (it + 1 < iters) nxt = load_vec(it + 1);  // keep the next 16 B in flight
-      const int64_t e = lo + it * TK_PER_ITER + (int64_t)threadIdx.x * 4;
-      const float v[4] = {cur.x, cur.y, cur.z, cur.w};
+    const int count0 = s_count;
+    // float form of the threshold: a score strictly below it can never enter the top-k
+    const float tau_f = tau == 0ull ? -CUDART_INF_F : key_float((uint32_t)(tau >> 32));
+    __syncthreads();   // everyone has the snapshot before anyone appends
+#pragma unroll 2
+    for (int64_t base = sb; base < full_hi; base += TK_FAST_ITER) {
+      int4 r[TK_VEC_PER_THREAD];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const bool in = e + r < hi;
-        const uint32_t fk = float_key(v[r]);
-        uint64_t key = 0;
-        bool take = in && fk >= tau_hi;
-        if (take) {
-          key = ((uint64_t)fk << 32) | (uint64_t)(0xFFFFFFFFu - (uint32_t)(e + r));
-          take = key > tau;
-        }
-        offer(st, take, key);
-      }
-      cur = nxt;
-    } else {
+      for (int q = 0; q < TK_VEC_PER_THREAD; ++q)
+        r[q] = ld_stream16(srow + base + (q * TK_THREADS + threadIdx.x) * 4);
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int64_t e = lo + it * TK_PER_ITER + r * TK_THREADS + threadIdx.x;
-        const bool in = e < hi;
-        uint64_t key = 0;
-        if (in) {
-          if (SRC == 0) key = make_key(srow[e], (uint32_t)e);
-          else if (SRC == 1) key = krow[e];
-          else {
-            const int64_t id = irow[e];
-            key = id < 0 ? 0ull : make_key(srow[e], (uint32_t)id);
+      for (int q = 0; q < TK_VEC_PER_THREAD; ++q) {
+        const float v[4] = {__int_as_float(r[q].x), __int_as_float(r[q].y), __int_as_float(r[q].z),
+                            __int_as_float(r[q].w)};
+        // one test for the whole vector keeps the common case at ~1 instruction per score
+        const bool any = !(v[0] < tau_f) | !(v[1] < tau_f) | !(v[2] < tau_f) | !(v[3] < tau_f);
+        if (any) {                                      // rare after warm-up (NaN passes: ranks first)
+          const int64_t e = base + (q * TK_THREADS + threadIdx.x) * 4;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (!(v[j] < tau_f)) {
+              const uint64_t key = make_key(v[j], (uint32_t)(e + j));
+              if (key > tau) {
+                const int pos = atomicAdd(&s_count, 1);
+                if (pos < TK_CAP) s_keys[pos] = key;
+                else s_ovf = 1;
+              }
+            }
           }
         }
-        offer(st, in && key > tau, key);
       }
     }
     __syncthreads();
+    const int ovf = s_ovf;
+    const int cnt = s_count;
+    __syncthreads();
+    if (ovf) {                                           // block-uniform
+      if (threadIdx.x == 0) {
+        s_count = count0;                                // drop this super-block's appends
+        s_ovf = 0;
+      }
+      __syncthreads();
+      slow_range<0>(st, srow, nullptr, nullptr, sb, full_hi, k);
+    } else if (cnt > (k <= 320 ? TK_COMPACT_AT : TK_CAP / 2 + k / 2)) {
+      compact_select(st, k);
+    }
+    if (full_hi < sb_hi) slow_range<0>(st, srow, nullptr, nullptr, full_hi, sb_hi, k);   // ragged tail
   }
-  compact(st, k);
-  // after compact(): keys sorted descending, zero padded up to a power of two >= count
+  compact_select(st, k);
+  compact(st, k);   // ordered emit: a sort of <= k keys
   const int cnt = s_count < k ? s_count : k;
   uint64_t* o = out_keys + (u * P + p) * (int64_t)k;
   for (int i = threadIdx.x; i < k; i += TK_THREADS) o[i] = i < cnt ? s_keys[i] : 0ull;
@@ -273,12 +418,13 @@ __global__ void retrieval_metrics_kernel(const int64_t* __restrict__ rec, int64_
 }
 
 static int pick_chunks(int64_t u, int64_t n) {
-  // enough blocks for ~4 per SM, but chunks no shorter than 16k scores
-  int64_t want = ((int64_t)sm_count() * 4 + u - 1) / (u > 0 ? u : 1);
-  int64_t maxp = (n + 16383) / 16384;
+  // one full wave of resident blocks (8 per SM) and never a ragged second wave; chunks no
+  // shorter than 64k scores (and few enough partial lists that the merge stage stays short)
+  int64_t want = ((int64_t)sm_count() * 8) / (u > 0 ? u : 1);
+  int64_t maxp = (n + 65535) / 65536;
   if (want > maxp) want = maxp;
   if (want < 1) want = 1;
-  if (want > 4096) want = 4096;
+  if (want > 296) want = 296;
   return (int)want;
 }
 
@@ -312,15 +458,14 @@ extern "C" int xr_topk(const float* scores, int64_t u, int64_t n, int64_t ld, in
   dim3 grid((unsigned)P, (unsigned)u);
   uint64_t* stage1_out = P == 1 ? final_keys : partial;
   if (vec)
-    topk_stream_kernel<0, true><<<grid, TK_THREADS, 0, s>>>(scores, nullptr, nullptr, n, ld, chunk,
-                                                            (int)k, stage1_out);
+    topk_stream_kernel<<<grid, TK_THREADS, 0, s>>>(scores, n, ld, chunk, (int)k, stage1_out);
   else
-    topk_stream_kernel<0, false><<<grid, TK_THREADS, 0, s>>>(scores, nullptr, nullptr, n, ld,
-                                                             chunk, (int)k, stage1_out);
+    topk_generic_kernel<0><<<grid, TK_THREADS, 0, s>>>(scores, nullptr, nullptr, n, ld, chunk,
+                                                       (int)k, stage1_out);
   XR_LAUNCH_CHECK("topk_stream");
   if (P > 1) {
     const int64_t pk = (int64_t)P * k;
-    topk_stream_kernel<1, false><<<dim3(1, (unsigned)u), TK_THREADS, 0, s>>>(
+    topk_generic_kernel<1><<<dim3(1, (unsigned)u), TK_THREADS, 0, s>>>(
         nullptr, nullptr, partial, pk, pk, pk, (int)k, final_keys);
     XR_LAUNCH_CHECK("topk_merge_chunks");
   }
@@ -344,7 +489,7 @@ extern "C" int xr_topk_merge(const float* scores, const int64_t* ids, int64_t u,
   if (u == 0) return XR_OK;
   cudaStream_t s = as_stream(stream);
   uint64_t* final_keys = (uint64_t*)workspace;
-  topk_stream_kernel<2, false><<<dim3(1, (unsigned)u), TK_THREADS, 0, s>>>(
+  topk_generic_kernel<2><<<dim3(1, (unsigned)u), TK_THREADS, 0, s>>>(
       scores, ids, nullptr, gk, gk, gk > 0 ? gk : 1, (int)k, final_keys);
   XR_LAUNCH_CHECK("topk_merge");
   const int64_t total = u * k;
