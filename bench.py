@@ -330,6 +330,9 @@ def bench_retrieval(args, xr, dev, rank, world, peak_hbm):
     for _ in range(2):
         sharded.search_batch(q, excl, k)
     torch.cuda.synchronize()
+    fused = xr.ops.score_groupmax_supported(q.bfloat16(), idx.catalog)
+    if fused:
+        xr._native.lib().xr_fused_profile(1)
     reps = 5
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
@@ -344,11 +347,28 @@ def bench_retrieval(args, xr, dev, rank, world, peak_hbm):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
-    return {"metric": "full-catalog top-100 queries/sec", "value": u / (ms / 1e3), "unit": "queries/s",
-            "catalog_rows": n, "queries": u, "k": k, "ms_per_batch": ms, "dtype": "bf16",
-            "path": "fused tcgen05 score+topk" if xr.ops.score_topk_supported(q.bfloat16(), idx.catalog)
-            else "scores (fp32-accumulate GEMM) + streaming top-k + merge",
-            "catalog_bytes_per_rank": (hi - lo) * DIM * 2}
+    out = {"metric": "full-catalog top-100 queries/sec", "value": u / (ms / 1e3), "unit": "queries/s",
+           "catalog_rows": n, "queries": u, "k": k, "ms_per_batch": ms, "dtype": "bf16",
+           "path": "tcgen05 group-max scoring + top groups re-scored + merge (+ NCCL all-gather of (U,k) when sharded)"
+           if fused else "scores (fp32-accumulate GEMM) + streaming top-k + merge",
+           "catalog_bytes_per_rank": (hi - lo) * DIM * 2}
+    if fused:
+        import ctypes
+
+        buf = (ctypes.c_float * 512)()
+        cnt = xr._native.lib().xr_fused_profile_read(buf, 512)
+        xr._native.lib().xr_fused_profile(0)
+        if cnt > 0:
+            k_ms = sum(buf[i] for i in range(cnt)) / cnt
+            flops = 2.0 * u * (hi - lo) * DIM
+            byts = (hi - lo) * DIM * 2
+            out["scoring_kernel"] = {
+                "kernel": "fused_pool_kernel<GMAX> (tcgen05)", "kernel_ms": k_ms,
+                "TFLOP/s": flops / (k_ms * 1e-3) / 1e12,
+                "catalog_GB/s": byts / (k_ms * 1e-3) / 1e9,
+                "frac_of_measured_hbm": byts / (k_ms * 1e-3) / 1e9 / peak_hbm,
+                "note": "U=256: 2*U*N*D FLOP vs N*D*2 catalog bytes read once; bound = max(tensor, HBM)"}
+    return out
 
 
 if __name__ == "__main__":

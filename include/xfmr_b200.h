@@ -224,6 +224,20 @@ int xr_scores(const void* q, int64_t u, const void* catalog, int64_t n, int64_t 
 int xr_mask_excluded(float* scores, int64_t u, int64_t n, int64_t ld, int64_t col_offset,
                      const int64_t* excl_offsets, const int64_t* excl_ids, void* stream);
 
+/* Retrieval scoring on the tensor cores without materialising the (U, N) score matrix:
+ *   gmax[u, g] = max over catalog rows c in [16g, 16g+16) of q_u . cat_c   (fp32; -inf past n)
+ * q (U, 384) and catalog (N, 384) bf16 (pre-normalised rows for the cosine metric, index.py:47);
+ * gmax is (U, ld) fp32 with ld >= 4 * ceil(N / 64).  The k-th largest group maximum of a row
+ * lower-bounds its k-th largest score, so the exact top-k (index.py:244-254, `.limit(top_k)`)
+ * only needs the top groups re-scored (xr_logits_sampled) and merged (xr_topk_merge).          */
+int xr_score_groupmax(const void* q, int64_t u, const void* catalog, int64_t n, int64_t dim,
+                      float* gmax, int64_t ld, void* stream);
+/* scores[u, j] = -inf where ids[u, j] lies outside [id_lo, id_hi) or in row u's CSR exclusion
+ * list (nullable) — the prefilter of index.py:239-247 applied to re-scored candidate lists.     */
+int xr_mask_excluded_ids(float* scores, const int64_t* ids, int64_t u, int64_t c, int64_t ld,
+                         int64_t id_lo, int64_t id_hi, const int64_t* excl_offsets,
+                         const int64_t* excl_ids, void* stream);
+
 /* fused tcgen05 scoring + top-k over one catalog shard (bf16, dim 384): scores = Q . Cat^T on the
  * tensor cores, threshold-filtered selection in the epilogue, no (U,N) score matrix in HBM.
  * Same result as xr_scores + xr_mask_excluded + xr_topk.  Returns XR_E_UNSUPPORTED when the

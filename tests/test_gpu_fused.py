@@ -153,3 +153,48 @@ def test_fused_under_autocast_matches_golden(xr, golden_dir):
     want, _, _, _ = orc.lean_loss("InfoNCELoss", z["query"], z["pos"], z["neg"], orc.Config(),
                                   with_grad=True, logits_dtype="bf16")
     assert float(loss) == pytest.approx(want, rel=2e-3)
+
+
+@pytest.mark.parametrize("u,n,k", [(1, 5000, 20), (6, 70001, 100), (130, 20000, 100), (257, 3001, 50)])
+def test_groupmax_retrieval_equals_full_scan(xr, u, n, k):
+    """tcgen05 group-max path vs the stable-sort oracle on exact-arithmetic inputs (small integers:
+    every bf16 product / fp32 sum is exact, so indices must be IDENTICAL, ties included) and vs the
+    library's own unfused path."""
+    rng = np.random.default_rng(n)
+    cat = rng.integers(-2, 3, size=(n, 384)).astype(np.float32)
+    cat[5] = cat[3]                      # duplicate rows: ties -> lower id first
+    qs = rng.integers(-2, 3, size=(u, 384)).astype(np.float32)
+    excl = [list(rng.integers(0, n, size=int(rng.integers(0, 60)))) for _ in range(u)]
+    cfg = dict(index_metric="dot", dtype="bf16")
+    fused = xr.index.ExactIndex(xr.index.ExactIndexConfig(**cfg)).set_catalog(torch.from_numpy(cat).cuda())
+    plain = xr.index.ExactIndex(xr.index.ExactIndexConfig(fused=False, **cfg)).set_catalog(torch.from_numpy(cat).cuda())
+    q = torch.from_numpy(qs).cuda()
+    s1, i1 = fused.search_batch(q, excl, k)
+    s2, i2 = plain.search_batch(q, excl, k)
+    want_s, want_i = orc.exact_search(qs, cat, k, excl, metric="dot")
+    assert np.array_equal(i1.cpu().numpy(), want_i)
+    assert np.array_equal(s1.cpu().numpy(), want_s)
+    assert torch.equal(i1, i2) and torch.equal(s1, s2)
+
+
+def test_groupmax_retrieval_random_cosine(xr):
+    """Random bf16 catalog, cosine metric: same ids as the unfused path wherever neighbouring
+    scores are separated by more than fp32 accumulation-order noise; recall@100 = 1 vs fp64."""
+    rng = np.random.default_rng(1)
+    n, u, k = 200_000, 64, 100
+    cat = rng.standard_normal((n, 384)).astype(np.float32)
+    qs = rng.standard_normal((u, 384)).astype(np.float32)
+    fused = xr.index.ExactIndex().set_catalog(torch.from_numpy(cat).cuda())
+    plain = xr.index.ExactIndex(xr.index.ExactIndexConfig(fused=False)).set_catalog(torch.from_numpy(cat).cuda())
+    q = torch.from_numpy(qs).cuda()
+    s1, i1 = fused.search_batch(q, None, k)
+    s2, i2 = plain.search_batch(q, None, k)
+    assert torch.allclose(s1, s2, atol=2e-6)
+    same = (i1 == i2).float().mean().item()
+    assert same > 0.995, same
+    # the arithmetic the index defines: dot products of the normalised-then-bf16-rounded rows
+    catn = fused.catalog.float().cpu().numpy()
+    qn, _ = xr.ops.normalize_rows(q, 1e-12, torch.bfloat16)
+    want_s, want_i = orc.exact_search(qn.float().cpu().numpy(), catn, k, None, metric="dot", dtype=np.float64)
+    recall = np.mean([len(set(i1[r].tolist()) & set(want_i[r].tolist())) / k for r in range(u)])
+    assert recall >= 0.999, recall

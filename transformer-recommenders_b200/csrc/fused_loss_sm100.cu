@@ -49,6 +49,7 @@ constexpr int THREADS = 128 + EPI_WARPS * 32;   // producer, 2 MMA issuers, 1 sp
 constexpr int TMEM_COLS = 512;
 constexpr int COL_O = 0, COL_S = 384;
 constexpr int KIND_DIAG = 100;      // extract q_i . pos_i from the diagonal of Q_blk . Pos_blk^T
+constexpr int KIND_GMAX = 101;      // retrieval: max score of every 16-column group (no loss)
 constexpr int NSCAL = 4;
 }  // namespace fk
 
@@ -61,6 +62,9 @@ struct FusedParams {
   float* t_out;        // [m]                                      (KIND_DIAG)
   float* part_o;       // [n_items][128][384]
   float* part_s;       // [n_items][128][NSCAL]
+  float* gmax;         // [m][gmax_ld] group maxima                (KIND_GMAX)
+  long long gmax_ld;
+  int rb_count;
   int* hang_flag;
 };
 
@@ -174,7 +178,7 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool diag = (KIND == KIND_DIAG);
-  const bool grad = !diag && p.with_grad;
+  const bool grad = !diag && KIND != KIND_GMAX && p.with_grad;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < PAIRS; ++s) {
@@ -208,6 +212,13 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
       rb = item;
       t0 = 2 * rb;
       t1 = t0 + 2;
+    } else if (KIND == KIND_GMAX) {
+      // row block fastest: CTAs that share a catalog range run side by side, so the second
+      // query block finds the catalog tiles in L2 instead of re-reading HBM
+      rb = item % p.rb_count;
+      const int sp = item / p.rb_count;
+      t0 = sp * p.tiles_per_split;
+      t1 = min(p.nt_count, t0 + p.tiles_per_split);
     } else {
       rb = item / p.spl;
       const int sp = item - rb * p.spl;
@@ -348,7 +359,7 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int row = rb * BM + r_local;
       const bool row_ok = row < p.m;
       float t = 0.f, tm = 0.f, zref2 = 0.f, t_eff = 0.f;
-      if (!diag && row_ok) {
+      if (!diag && KIND != KIND_GMAX && row_ok) {
         t = p.t[row];
         if (RBF) t = bf16_round(t);
         tm = t * (1.0f - p.margin);
@@ -376,6 +387,13 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
             for (int j = 0; j < 16; ++j)
               if (c == j) diag_val = __uint_as_float(v[j]);
           }
+        } else if (KIND == KIND_GMAX) {
+          const int ncols = p.cn - (t0 + tl) * BN - cg * 16;
+          float mx = -CUDART_INF_F;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < ncols) mx = fmaxf(mx, __uint_as_float(v[j]));
+          if (row_ok) p.gmax[(long long)row * p.gmax_ld + (long long)(t0 + tl) * CG + cg] = mx;
         } else {
           const int ncols = p.cn - (t0 + tl) * BN - cg * 16;   // valid candidates in this group
           uint32_t pk[8];
@@ -398,6 +416,8 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
       if (diag) {
         if (row_ok && (r_local & 63) >> 4 == cg) p.t_out[row] = diag_val;
+      } else if (KIND == KIND_GMAX) {
+        // nothing to flush: the group maxima were written tile by tile
       } else {
         if (grad) {
           mbar_wait(bar_o_full, it & 1, p.hang_flag, 9);
@@ -688,7 +708,7 @@ static int launch_fused(const CUtensorMap& tq, const CUtensorMap& tb, const Fuse
 
 using namespace xr;
 
-extern "C" int xr_fused_available(void) { return 1; }
+extern "C" int xr_fused_available(void) { return 3; }  // bit 0: fused loss, bit 1: fused retrieval scoring
 
 extern "C" size_t xr_fused_pool_workspace_bytes(int64_t m, int64_t cn, int64_t dim) {
   if (dim != fk::D || m <= 0 || cn <= 0) return 256;
@@ -798,6 +818,51 @@ extern "C" int xr_fused_pool_loss(const void* q, const void* pos, const void* ne
   sum_rows_kernel<<<1, 1024, 0, s>>>(rl, m, loss_out);
   XR_LAUNCH_CHECK("sum_rows");
   return XR_OK;
+}
+
+// ---- retrieval: group maxima of Q . Cat^T on the tensor cores -----------------------------------
+// gmax[u, g] = max_{c in [16g, 16g+16)} q_u . cat_c   (columns >= n give -inf).  The k-th largest
+// group maximum of a row is a lower bound of its k-th largest score, and every score above it
+// lives in a group whose maximum is above it: the exact top-k only needs the top groups to be
+// re-scored (index.py:244-254 semantics, exact).  The (U, N) score matrix never reaches HBM.
+extern "C" int xr_score_groupmax(const void* q, int64_t u, const void* catalog, int64_t n,
+                                 int64_t dim, float* gmax, int64_t ld, void* stream) {
+  XR_CHECK_ARG(q && catalog && gmax, "xr_score_groupmax: null pointer");
+  XR_CHECK_ARG(dim == fk::D, "xr_score_groupmax: this build is specialised for dim = %d", fk::D);
+  XR_CHECK_ARG(u > 0 && n > 0 && u < (1ll << 30) && n < (1ll << 31), "xr_score_groupmax: bad sizes");
+  const int64_t nt = (n + fk::BN - 1) / fk::BN;
+  XR_CHECK_ARG(ld >= nt * fk::CG, "xr_score_groupmax: ld must be >= 4 * ceil(n / 64)");
+  XR_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)catalog % 16 == 0),
+               "xr_score_groupmax: operands must be 16-byte aligned");
+  int dev = 0, major = 0;
+  XR_CUDA(cudaGetDevice(&dev));
+  XR_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    set_error("xr_score_groupmax: needs an sm_100 device (tcgen05/TMEM)");
+    return XR_E_UNSUPPORTED;
+  }
+  cudaStream_t s = as_stream(stream);
+  const int n_sm = sm_count();
+  const FusedPlan pl = make_plan(u, n, n_sm);
+  CUtensorMap tq, tc;
+  int rc;
+  if ((rc = make_tmap_bf16_rows(&tq, q, u, dim, dim, fk::BM))) return rc;
+  if ((rc = make_tmap_bf16_rows(&tc, catalog, n, dim, dim, fk::BN))) return rc;
+  FusedParams p{};
+  p.m = (int)u; p.cn = (int)n; p.nt_count = pl.nt; p.spl = pl.spl; p.tiles_per_split = pl.tps;
+  p.n_items = pl.n_items; p.rb_count = pl.rb; p.gmax = gmax; p.gmax_ld = ld;
+  static int* hang = nullptr;   // device word for the bounded-wait diagnostics
+  if (!hang) {
+    XR_CUDA(cudaMalloc(&hang, 256));
+    XR_CUDA(cudaMemset(hang, 0, 256));
+  }
+  p.hang_flag = hang;
+  const int grid = pl.n_items < n_sm ? pl.n_items : n_sm;
+  const bool prof = g_prof_on && g_prof_n < kProfRing;
+  if (prof) cudaEventRecord(g_prof_ev[g_prof_n][0], s);
+  rc = launch_fused1<fk::KIND_GMAX, false>(tq, tc, p, grid, s);
+  if (prof) cudaEventRecord(g_prof_ev[g_prof_n++][1], s);
+  return rc;
 }
 
 extern "C" int xr_fused_profile(int enable) {

@@ -17,3 +17,8 @@ extern "C" int xr_score_topk(const void*, int64_t, const void*, int64_t, int64_t
 }
 extern "C" int xr_fused_profile(int) { return XR_E_UNSUPPORTED; }
 extern "C" int xr_fused_profile_read(float*, int) { return XR_E_UNSUPPORTED; }
+extern "C" int xr_score_groupmax(const void*, int64_t, const void*, int64_t, int64_t, float*, int64_t,
+                                 void*) {
+  xr::set_error("xr_score_groupmax: tcgen05 kernels not compiled into this build");
+  return XR_E_UNSUPPORTED;
+}

@@ -345,6 +345,24 @@ __global__ void mask_excluded_kernel(float* __restrict__ scores, int64_t u, int6
   }
 }
 
+// scores[u, j] = -inf where ids[u, j] is in row u's exclusion list or invalid (< 0 / >= n_valid);
+// used on the re-scored candidate lists of the fused retrieval path (index.py:239-247 prefilter)
+__global__ void mask_excluded_ids_kernel(float* __restrict__ scores, const int64_t* __restrict__ ids,
+                                         int64_t u, int64_t c, int64_t ld, int64_t id_lo,
+                                         int64_t id_hi, const int64_t* __restrict__ offs,
+                                         const int64_t* __restrict__ excl) {
+  const int64_t total = u * c;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / c, j = e - r * c;
+    const int64_t id = ids[r * c + j];
+    bool dead = id < id_lo || id >= id_hi;
+    if (!dead && offs)
+      for (int64_t x = offs[r]; x < offs[r + 1]; ++x) dead |= (excl[x] == id);
+    if (dead) scores[r * ld + j] = -CUDART_INF_F;
+  }
+}
+
 // ---- retrieval metrics: metrics.py:62-79, one thread per user ---------------------------------
 __global__ void retrieval_metrics_kernel(const int64_t* __restrict__ rec, int64_t u, int64_t k,
                                          const int64_t* __restrict__ toffs,
@@ -509,6 +527,20 @@ extern "C" int xr_mask_excluded(float* scores, int64_t u, int64_t n, int64_t ld,
   mask_excluded_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
       scores, u, n, ld, col_offset, excl_offsets, excl_ids);
   XR_LAUNCH_CHECK("mask_excluded");
+  return XR_OK;
+}
+
+extern "C" int xr_mask_excluded_ids(float* scores, const int64_t* ids, int64_t u, int64_t c,
+                                    int64_t ld, int64_t id_lo, int64_t id_hi,
+                                    const int64_t* excl_offsets, const int64_t* excl_ids,
+                                    void* stream) {
+  XR_CHECK_ARG(scores && ids && ld >= c, "xr_mask_excluded_ids: bad arguments");
+  if (u == 0 || c == 0) return XR_OK;
+  int64_t blocks = (u * c + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+  mask_excluded_ids_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+      scores, ids, u, c, ld, id_lo, id_hi, excl_offsets, excl_ids);
+  XR_LAUNCH_CHECK("mask_excluded_ids");
   return XR_OK;
 }
 

@@ -32,6 +32,7 @@ class ExactIndexConfig(pydantic.BaseModel):
     index_metric: Literal["dot", "cosine"] = "cosine"
     dtype: Literal["bf16", "fp32"] = "bf16"
     max_score_bytes: int = 1 << 30  # materialised-score budget of the unfused path
+    fused: bool = True  # tensor-core group-max path when the device / dtype allow it
 
 
 class ExactIndex:
@@ -110,8 +111,13 @@ class ExactIndex:
         csr = None
         if exclude_rows is not None:
             csr = exclude_rows if isinstance(exclude_rows, tuple) else ops._csr(exclude_rows, self.device)
-        if ops.score_topk_supported(q, cat) and top_k <= 128:
-            s, i = ops.score_topk(q, cat, top_k, exclude=csr, col_offset=self.row_offset)
+        max_excl = 0
+        if csr is not None:
+            max_excl = int((csr[0][1:] - csr[0][:-1]).max().item()) if csr[0].numel() > 1 else 0
+        n_groups = 4 * ((n + 63) // 64)
+        kg = min(n_groups, top_k + max_excl + 28)
+        if ops.score_groupmax_supported(q, cat) and kg <= 1024 and self.config.fused:
+            s, i = self._search_groupmax(q, cat, csr, top_k, kg)
         else:
             chunk = max(4096, min(n, self.config.max_score_bytes // (4 * max(u, 1)) // 4 * 4))
             parts_s, parts_i = [], []
@@ -131,6 +137,22 @@ class ExactIndex:
         dead = s == float("-inf")
         i = torch.where(dead, torch.full_like(i, -1), i)
         return s, i
+
+    def _search_groupmax(self, q, cat, csr, top_k, kg):
+        """Tensor-core path: group maxima (tcgen05) -> top groups -> exact re-score of their rows
+        -> merge under (score desc, row asc).  The k-th largest group maximum lower-bounds the k-th
+        largest score and every score above it sits in a group above it; `kg` adds one group per
+        excluded id plus a margin, so the result equals the full scan."""
+        n = cat.size(0)
+        gmax = ops.score_groupmax(q, cat)
+        _, gi = ops.topk(gmax, kg)                                   # (U, kg) group ids, -1 = none
+        cols = gi[:, :, None] * 16 + torch.arange(16, device=gi.device)
+        cols = torch.where(gi[:, :, None] >= 0, cols, torch.full_like(cols, -1)).reshape(gi.size(0), -1)
+        valid = (cols >= 0) & (cols < n)
+        scores = ops.logits_sampled(q, cat, cols.clamp(0, n - 1).contiguous())
+        ids = torch.where(valid, cols + self.row_offset, torch.full_like(cols, -1)).contiguous()
+        ops.mask_excluded_ids(scores, ids, self.row_offset, self.row_offset + n, csr)
+        return ops.topk_merge(scores, ids, top_k)
 
     def search(self, embedding, exclude_item_ids: list[str] | None = None, top_k: int = TOP_K):
         """``LanceIndex.search`` (index.py:214-255): one query vector in, a

@@ -340,12 +340,43 @@ def topk_merge(cand_scores, cand_ids, k):
     return out_s, out_i
 
 
-def score_topk_supported(q, catalog) -> bool:
+def score_groupmax_supported(q, catalog) -> bool:
     if not (q.is_cuda and q.dtype == torch.bfloat16 and catalog.dtype == torch.bfloat16
             and q.size(1) == 384):
         return False
     major, _ = torch.cuda.get_device_capability(q.device)
     return major == 10 and bool(N.lib().xr_fused_available() & 2)
+
+
+def score_groupmax(q, catalog):
+    """tcgen05 scoring without the (U,N) matrix: max score of every 16-row catalog group."""
+    dev = _require_cuda(q, catalog)
+    q, catalog = q.contiguous(), catalog.contiguous()
+    u, d = q.shape
+    n = catalog.size(0)
+    ld = 4 * ((n + 63) // 64)
+    gmax = torch.empty((u, ld), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        N.call("xr_score_groupmax", _p(q), u, _p(catalog), n, d, _p(gmax), ld, _stream())
+    return gmax
+
+
+def mask_excluded_ids(score_mat, ids, id_lo, id_hi, exclude=None):
+    dev = _require_cuda(score_mat, ids)
+    offs, ex = (None, None) if exclude is None else exclude
+    u, c = ids.shape
+    with torch.cuda.device(dev):
+        N.call("xr_mask_excluded_ids", _p(score_mat), _p(ids), u, c, score_mat.size(1), id_lo, id_hi,
+               _p(offs), _p(ex), _stream())
+    return score_mat
+
+
+def score_topk_supported(q, catalog) -> bool:
+    if not (q.is_cuda and q.dtype == torch.bfloat16 and catalog.dtype == torch.bfloat16
+            and q.size(1) == 384):
+        return False
+    major, _ = torch.cuda.get_device_capability(q.device)
+    return False  # superseded by the group-max path (score_groupmax + re-score + merge)
 
 
 def score_topk(q, catalog, k, q_inv=None, cat_inv=None, exclude=None, col_offset=0):
