@@ -89,6 +89,11 @@ int xr_gather_rows(const void* table, int64_t n_rows, int64_t dim, int table_dty
 int xr_scatter_rows(const float* src, int64_t n_src, int64_t dim, const int64_t* sel,
                     float* dst, int64_t n_dst_rows, void* stream);
 
+/* dst[p,:] = inv_pos[p] >= 0 ? cast(src[inv_pos[p],:] * *scale) : 0 — zero fill + scatter + the
+ * grad_output scale (device scalar, nullable = 1) + cast in one pass; dst is (n_dst_rows, dim).  */
+int xr_scatter_scaled(const float* src, const int64_t* inv_pos, const float* scale,
+                      int64_t n_dst_rows, int64_t dim, void* dst, int dst_dtype, void* stream);
+
 /* rownz[r] = any(table[r,:] != 0) — lets the attention mask of models.py:343 be derived from
  * the indices: mask = rownz[idx].                                                             */
 int xr_row_nonzero(const void* table, int64_t n_rows, int64_t dim, int dtype, uint8_t* rownz,
@@ -99,13 +104,14 @@ int xr_row_nonzero(const void* table, int64_t n_rows, int64_t dim, int dtype, ui
  *   sel_attn[..] = positions p with attn[p], ascending        (neg / pos row order, :398/:404)
  *   sel_pos[..]  = positions p with attn[p] && pos_idx[p]!=0  (query / candidate rows, :413-416)
  *   pos_mask[a]  = pos_idx[sel_attn[a]] != 0                   (positive_mask, :413)
+ *   inv_pos[p]   = row of position p in sel_pos, or -1      (nullable; inverse map for the backward)
  * counts[0] = M_a, counts[1] = M (device int64[2]).  rownz == NULL uses idx != 0 instead.
  * workspace >= xr_compact_workspace_bytes(n_pos).                                             */
 size_t xr_compact_workspace_bytes(int64_t n_pos);
 int xr_compact_positions(const int64_t* history_idx, const int64_t* pos_idx,
                          const uint8_t* rownz, int64_t n_table_rows, int64_t n_pos,
                          uint8_t* attn, int64_t* sel_attn, int64_t* sel_pos, uint8_t* pos_mask,
-                         int64_t* counts, void* workspace, void* stream);
+                         int64_t* inv_pos, int64_t* counts, void* workspace, void* stream);
 
 /* y[r,:] = x[r,:] / max(||x[r,:]||, eps); inv_norm[r] = 1/max(||x[r,:]||, eps);
  * the two normalisations inside torch's cosine_similarity, losses.py:206-208 (eps 1e-8) and
@@ -184,7 +190,8 @@ int xr_dq_sampled(const float* dlogits, int64_t ld, const void* q, const void* t
  * Contrastive / AlignmentContrastive (:338-372, :436-447).  num_hard_negatives must be 0.
  *   q, pos : (M, D) bf16;  neg : (Cn, D) bf16;  D = 384 in this build.
  *   dq     : (M, D) fp32 (nullable => forward only), times grad_scale.
- *   loss_out : float64[1] sum over rows;  row_loss (nullable): float32[M].
+ *   loss_out : float64[2]: [0] sum over rows; the first 4 bytes of [1] receive its fp32 copy.
+ *   row_loss (nullable): float32[M].
  *   q_inv_norm (cosine kinds only): float32[M].
  *   workspace: >= xr_fused_pool_workspace_bytes(m, cn, dim) bytes.                            */
 int xr_fused_available(void); /* bit 0: fused loss kernel, bit 1: fused score+top-k kernel */

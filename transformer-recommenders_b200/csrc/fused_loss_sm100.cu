@@ -552,7 +552,8 @@ fused_finalize_kernel(const float* __restrict__ part_o, const float* __restrict_
 
 // single block, fixed order: loss = sum_i row_loss[i]   (double accumulation)
 __global__ void __launch_bounds__(1024)
-sum_rows_kernel(const float* __restrict__ row_loss, int64_t m, double* __restrict__ out) {
+sum_rows_kernel(const float* __restrict__ row_loss, int64_t m, double* __restrict__ out,
+                float* __restrict__ out_f32) {
   __shared__ double s[32];
   double acc = 0.0;
   for (int64_t i = threadIdx.x; i < m; i += blockDim.x) acc += (double)row_loss[i];
@@ -563,6 +564,7 @@ sum_rows_kernel(const float* __restrict__ row_loss, int64_t m, double* __restric
     double tot = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s[w];
     out[0] = tot;
+    if (out_f32) out_f32[0] = (float)tot;
   }
 }
 
@@ -815,7 +817,8 @@ extern "C" int xr_fused_pool_loss(const void* q, const void* pos, const void* ne
       part_o, part_s, t_buf, zref, (const __nv_bfloat16*)q, (const __nv_bfloat16*)pos, q_inv_norm,
       (int)m, pl.spl, loss_kind, cfg->logits_bf16, cfg->scale, cfg->margin, grad_scale, dq, rl);
   XR_LAUNCH_CHECK("fused_finalize");
-  sum_rows_kernel<<<1, 1024, 0, s>>>(rl, m, loss_out);
+  // loss_out[1] (if the caller left room) receives the fp32 copy the loss module returns
+  sum_rows_kernel<<<1, 1024, 0, s>>>(rl, m, loss_out, reinterpret_cast<float*>(loss_out + 1));
   XR_LAUNCH_CHECK("sum_rows");
   return XR_OK;
 }

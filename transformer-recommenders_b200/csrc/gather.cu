@@ -189,7 +189,8 @@ compact_write_kernel(const int64_t* __restrict__ history_idx, const int64_t* __r
                      const uint8_t* __restrict__ rownz, int64_t n_table_rows, int64_t n_pos,
                      const int64_t* __restrict__ chunk_offsets, int64_t nchunks,
                      uint8_t* __restrict__ attn, int64_t* __restrict__ sel_attn,
-                     int64_t* __restrict__ sel_pos, uint8_t* __restrict__ pos_mask) {
+                     int64_t* __restrict__ sel_pos, uint8_t* __restrict__ pos_mask,
+                     int64_t* __restrict__ inv_pos) {
   // each thread owns 8 CONSECUTIVE positions so that a block-level scan of per-thread counts
   // yields a stable (ascending-position) compaction
   constexpr int PER = kChunk / kCompactThreads;
@@ -233,7 +234,51 @@ compact_write_kernel(const int64_t* __restrict__ history_idx, const int64_t* __r
       pos_mask[oa] = fq[i];
       ++oa;
     }
-    if (fq[i]) sel_pos[oq++] = p;
+    if (fq[i]) {
+      if (inv_pos) inv_pos[p] = oq;
+      sel_pos[oq++] = p;
+    } else if (inv_pos && p < n_pos) {
+      inv_pos[p] = -1;
+    }
+  }
+}
+
+// dst[p,:] = inv[p] >= 0 ? cast(src[inv[p],:] * *scale) : 0  — the whole backward of the query
+// compaction (models.py:392, 415) in one pass: zero fill + scatter + grad_output scale + cast.
+template <typename TO>
+__global__ void __launch_bounds__(256)
+scatter_scaled_kernel(const float* __restrict__ src, const int64_t* __restrict__ inv,
+                      const float* __restrict__ scale, int64_t n_dst_rows, int vec_per_row,
+                      TO* __restrict__ dst) {
+  const float sc = scale ? *scale : 1.0f;
+  const int64_t total = n_dst_rows * vec_per_row;   // vec = 8 output elements
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total;
+       v += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = v / vec_per_row;
+    const int c = (int)(v - r * vec_per_row);
+    const int64_t s = inv[r];
+    float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (s >= 0) {
+      const int4 a = ld_stream16(reinterpret_cast<const int4*>(src + (s * vec_per_row + c) * 8));
+      const int4 b = ld_stream16(reinterpret_cast<const int4*>(src + (s * vec_per_row + c) * 8 + 4));
+      x[0] = __int_as_float(a.x) * sc; x[1] = __int_as_float(a.y) * sc;
+      x[2] = __int_as_float(a.z) * sc; x[3] = __int_as_float(a.w) * sc;
+      x[4] = __int_as_float(b.x) * sc; x[5] = __int_as_float(b.y) * sc;
+      x[6] = __int_as_float(b.z) * sc; x[7] = __int_as_float(b.w) * sc;
+    }
+    if (sizeof(TO) == 2) {
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(x[0], x[1]), h1 = __floats2bfloat162_rn(x[2], x[3]);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(x[4], x[5]), h3 = __floats2bfloat162_rn(x[6], x[7]);
+      int4 o;
+      o.x = *reinterpret_cast<int*>(&h0); o.y = *reinterpret_cast<int*>(&h1);
+      o.z = *reinterpret_cast<int*>(&h2); o.w = *reinterpret_cast<int*>(&h3);
+      st_stream16(reinterpret_cast<int4*>(dst) + v, o);
+    } else {
+      int4 o0 = make_int4(__float_as_int(x[0]), __float_as_int(x[1]), __float_as_int(x[2]), __float_as_int(x[3]));
+      int4 o1 = make_int4(__float_as_int(x[4]), __float_as_int(x[5]), __float_as_int(x[6]), __float_as_int(x[7]));
+      st_stream16(reinterpret_cast<int4*>(dst) + 2 * v, o0);
+      st_stream16(reinterpret_cast<int4*>(dst) + 2 * v + 1, o1);
+    }
   }
 }
 
@@ -328,6 +373,27 @@ extern "C" int xr_scatter_rows(const float* src, int64_t n_src, int64_t dim, con
   return XR_OK;
 }
 
+extern "C" int xr_scatter_scaled(const float* src, const int64_t* inv_pos, const float* scale,
+                                 int64_t n_dst_rows, int64_t dim, void* dst, int dst_dtype,
+                                 void* stream) {
+  XR_CHECK_ARG(src && inv_pos && dst, "xr_scatter_scaled: null pointer");
+  XR_CHECK_ARG(dim > 0 && dim % 8 == 0 && (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0,
+               "xr_scatter_scaled: dim must be a multiple of 8 and buffers 16B aligned");
+  if (n_dst_rows == 0) return XR_OK;
+  const int vpr = (int)(dim / 8);
+  const int grid = grid_for(n_dst_rows * vpr, 256);
+  if (dst_dtype == XR_BF16)
+    scatter_scaled_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(
+        src, inv_pos, scale, n_dst_rows, vpr, (__nv_bfloat16*)dst);
+  else if (dst_dtype == XR_F32)
+    scatter_scaled_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(src, inv_pos, scale,
+                                                                      n_dst_rows, vpr, (float*)dst);
+  else
+    XR_CHECK_ARG(false, "xr_scatter_scaled: bad dtype");
+  XR_LAUNCH_CHECK("scatter_scaled");
+  return XR_OK;
+}
+
 extern "C" int xr_row_nonzero(const void* table, int64_t n_rows, int64_t dim, int dtype,
                               uint8_t* rownz, void* stream) {
   XR_CHECK_ARG(table && rownz && n_rows > 0 && dim > 0, "xr_row_nonzero: bad arguments");
@@ -352,8 +418,8 @@ extern "C" size_t xr_compact_workspace_bytes(int64_t n_pos) {
 extern "C" int xr_compact_positions(const int64_t* history_idx, const int64_t* pos_idx,
                                     const uint8_t* rownz, int64_t n_table_rows, int64_t n_pos,
                                     uint8_t* attn, int64_t* sel_attn, int64_t* sel_pos,
-                                    uint8_t* pos_mask, int64_t* counts, void* workspace,
-                                    void* stream) {
+                                    uint8_t* pos_mask, int64_t* inv_pos, int64_t* counts,
+                                    void* workspace, void* stream) {
   XR_CHECK_ARG(history_idx && pos_idx && attn && sel_attn && sel_pos && pos_mask && counts &&
                    workspace,
                "xr_compact_positions: null pointer");
@@ -372,7 +438,7 @@ extern "C" int xr_compact_positions(const int64_t* history_idx, const int64_t* p
   XR_LAUNCH_CHECK("compact_scan");
   compact_write_kernel<<<(unsigned)nchunks, kCompactThreads, 0, s>>>(
       history_idx, pos_idx, rownz, n_table_rows, n_pos, cc, nchunks, attn, sel_attn, sel_pos,
-      pos_mask);
+      pos_mask, inv_pos);
   XR_LAUNCH_CHECK("compact_write");
   return XR_OK;
 }

@@ -52,7 +52,8 @@ PROTOTYPES = {
     "xr_scatter_rows": (_int, [_p, _i64, _i64, _p, _p, _i64, _p]),
     "xr_row_nonzero": (_int, [_p, _i64, _i64, _int, _p, _p]),
     "xr_compact_workspace_bytes": (_sz, [_i64]),
-    "xr_compact_positions": (_int, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p]),
+    "xr_compact_positions": (_int, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "xr_scatter_scaled": (_int, [_p, _p, _p, _i64, _i64, _p, _int, _p]),
     "xr_normalize_rows": (_int, [_p, _i64, _i64, _int, _f, _p, _int, _p, _p]),
     "xr_logits_pool": (_int, [_p, _p, _p, _i64, _i64, _i64, _int, _p, _i64, _p]),
     "xr_logits_dense": (_int, [_p, _p, _i64, _i64, _i64, _int, _p, _p, _f, _p, _i64, _p]),

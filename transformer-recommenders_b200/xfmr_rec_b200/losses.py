@@ -126,12 +126,39 @@ class _AttachGrad(torch.autograd.Function):
     def forward(ctx, query, loss, dq):
         ctx.save_for_backward(dq)
         ctx.q_dtype = query.dtype
-        return loss.clone()
+        return loss.view(())
 
     @staticmethod
     def backward(ctx, grad_out):
         (dq,) = ctx.saved_tensors
         return (dq * grad_out).to(ctx.q_dtype), None, None
+
+
+class _AttachGradScatter(torch.autograd.Function):
+    """Same, but connected to the encoder output the query rows were compacted from
+    (models.compute_embeds): backward is ONE kernel — grad_output scale, cast and scatter into the
+    (B*L, D) layout with zeros for unselected positions (autograd of models.py:392, 415)."""
+
+    @staticmethod
+    def forward(ctx, tok2d, loss, dq, inv_pos):
+        ctx.save_for_backward(dq, inv_pos)
+        ctx.n_rows, ctx.tok_dtype = tok2d.size(0), tok2d.dtype
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        dq, inv_pos = ctx.saved_tensors
+        return ops.scatter_scaled(dq, inv_pos, grad_out, ctx.n_rows, ctx.tok_dtype), None, None, None
+
+
+class _OneLoss:
+    """losses[kind] container of the fused path (only the requested kind was evaluated)."""
+
+    def __init__(self, kind, value):
+        self.kind, self.value = kind, value
+
+    def __getitem__(self, k):
+        return self.value if k == self.kind else torch.zeros((), device=self.value.device)
 
 
 def weighted_mean(values, sample_weights, *, dim=None, keepdim=False):
@@ -263,9 +290,7 @@ class EmbedLoss(torch.nn.Module, abc.ABC):
         if fused_ok:
             loss, dq, _ = ops.fused_pool_loss(q, pos, neg, kind, cfg, q_inv=q_inv,
                                               want_grad=grad_kind >= 0)
-            losses = torch.zeros(N.XR_NUM_LOSSES, dtype=torch.float64, device=q.device)
-            losses[kind] = loss[0]
-            return losses, None, dq
+            return _OneLoss(kind, loss.view(torch.float32)[2]), None, dq
         # materialised path, row-chunked so the logits stay bounded
         m, cn = q.size(0), neg.size(0)
         rows = max(1, min(m, _MAX_LOGIT_BYTES // (4 * (cn + 4)))) if m else 1
@@ -315,8 +340,13 @@ class EmbedLoss(torch.nn.Module, abc.ABC):
     def forward(self, query_embed, candidate_embed, target=None):
         """Summed loss over the batch (xfmr_rec/losses.py:128-155)."""
         losses, _, dq = self._evaluate(query_embed, candidate_embed, target)
-        loss = losses[N.LOSS_KIND[type(self).__name__]].to(torch.float32)
+        loss = losses[N.LOSS_KIND[type(self).__name__]]
+        if loss.dtype != torch.float32:
+            loss = loss.to(torch.float32)
         if dq is not None:
+            src = getattr(query_embed, "_xr_src", None)
+            if src is not None and src[0].requires_grad and dq.size(1) % 8 == 0:
+                return _AttachGradScatter.apply(src[0], loss, dq, src[1])
             return _AttachGrad.apply(query_embed, loss, dq)
         return loss
 

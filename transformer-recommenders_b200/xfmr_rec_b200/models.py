@@ -95,13 +95,17 @@ def compute_embeds(
     pos = pos_item_idx.to(dev).contiguous().view(-1)
     neg = neg_item_idx.to(dev).contiguous().view(-1)
     b, l = hist.shape
-    attention_mask, sel_attn, sel_pos, positive_mask = ops.compact_positions(
+    attention_mask, sel_attn, sel_pos, positive_mask, inv_pos = ops.compact_positions(
         hist, pos, embeddings.rownz(), embeddings.num_embeddings
     )  # models.py:343, 390, 398, 404, 413
     tok2d = token_embeddings.reshape(b * l, token_embeddings.size(-1))
     if tok2d.dtype not in (torch.float32, torch.bfloat16):
         tok2d = tok2d.float()
-    query_embed = _RowGather.apply(tok2d.contiguous(), sel_pos)  # models.py:392 + :415
+    tok2d = tok2d.contiguous()
+    query_embed = _RowGather.apply(tok2d, sel_pos)  # models.py:392 + :415
+    # lets the loss attach its fused backward (scale + cast + scatter in one kernel) straight to
+    # the encoder output; lost (on purpose) as soon as the tensor is transformed
+    query_embed._xr_src = (tok2d, inv_pos)
     if is_normalized:  # models.py:394-395
         query_embed = torch.nn.functional.normalize(query_embed, dim=-1)
     pos_embed = embeddings(pos, sel=sel_pos, dtype=candidate_dtype)  # models.py:400 + :416

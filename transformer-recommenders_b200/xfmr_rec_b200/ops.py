@@ -113,24 +113,40 @@ def row_nonzero(table):
 
 def compact_positions(history_idx, pos_idx, rownz=None, n_table_rows=0):
     """models.py:343/390/398/404/413-416 on the index tensors; one host sync for the counts
-    (the reference syncs twice for the same numbers, trainer.py:239-240)."""
+    (the reference syncs twice for the same numbers, trainer.py:239-240).
+    Returns (attention_mask (B,L) bool, sel_attn (M_a,), sel_pos (M,), positive_mask (M_a,) bool,
+    inv_pos (B*L,) int64: row of each position in sel_pos or -1)."""
     dev = _require_cuda(history_idx, pos_idx, rownz)
     h = history_idx.contiguous().view(-1)
     p = pos_idx.contiguous().view(-1)
     n = h.numel()
-    attn = torch.empty(n, dtype=torch.uint8, device=dev)
-    sel_attn = torch.empty(n, dtype=torch.int64, device=dev)
-    sel_pos = torch.empty(n, dtype=torch.int64, device=dev)
-    pos_mask = torch.empty(n, dtype=torch.uint8, device=dev)
-    counts = torch.zeros(2, dtype=torch.int64, device=dev)
-    ws = _ws(N.lib().xr_compact_workspace_bytes(n), dev)
+    ibuf = torch.empty(3 * n + 2, dtype=torch.int64, device=dev)   # sel_attn | sel_pos | inv | counts
+    bbuf = torch.empty(2 * n, dtype=torch.uint8, device=dev)       # attn | pos_mask
+    sel_attn, sel_pos, inv_pos, counts = ibuf[:n], ibuf[n:2 * n], ibuf[2 * n:3 * n], ibuf[3 * n:]
+    attn, pos_mask = bbuf[:n], bbuf[n:]
     if n == 0:
-        return attn.view(history_idx.shape).bool(), sel_attn, sel_pos, pos_mask.bool()
+        return attn.view(history_idx.shape).view(torch.bool), sel_attn, sel_pos, pos_mask.view(torch.bool), inv_pos
+    ws = _ws(N.lib().xr_compact_workspace_bytes(n), dev)
     with torch.cuda.device(dev):
         N.call("xr_compact_positions", _p(h), _p(p), _p(rownz), n_table_rows, n, _p(attn),
-               _p(sel_attn), _p(sel_pos), _p(pos_mask), _p(counts), _p(ws), _stream())
+               _p(sel_attn), _p(sel_pos), _p(pos_mask), _p(inv_pos), _p(counts), _p(ws), _stream())
     m_a, m = (int(v) for v in counts.tolist())
-    return attn.view(history_idx.shape).bool(), sel_attn[:m_a], sel_pos[:m], pos_mask[:m_a].bool()
+    return (attn.view(history_idx.shape).view(torch.bool), sel_attn[:m_a], sel_pos[:m],
+            pos_mask[:m_a].view(torch.bool), inv_pos)
+
+
+def scatter_scaled(src, inv_pos, scale, n_dst_rows, out_dtype):
+    """dst[p] = inv_pos[p] >= 0 ? cast(src[inv_pos[p]] * scale) : 0 (scale: 0-dim fp32 device tensor
+    or None) — the whole backward of the query compaction in one kernel."""
+    dev = _require_cuda(src, inv_pos, scale)
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    dst = torch.empty((n_dst_rows, src.size(1)), dtype=out_dtype, device=dev)
+    if scale is not None and scale.dtype != torch.float32:
+        scale = scale.float()
+    with torch.cuda.device(dev):
+        N.call("xr_scatter_scaled", _p(src), _p(inv_pos), _p(scale), n_dst_rows, src.size(1),
+               _p(dst), _DT[out_dtype], _stream())
+    return dst
 
 
 def normalize_rows(x, eps=1e-8, out_dtype=None, want_y=True):
@@ -255,7 +271,7 @@ def fused_pool_loss(q, pos, neg, loss_kind, cfg, q_inv=None, grad_scale=1.0, wan
     m, d = q.shape
     cn = neg.size(0)
     dq = torch.empty((m, d), dtype=torch.float32, device=dev) if want_grad else None
-    loss = torch.empty(1, dtype=torch.float64, device=dev)
+    loss = torch.empty(2, dtype=torch.float64, device=dev)   # [0] f64 sum, [1] carries the f32 copy
     row_loss = torch.empty(m, dtype=torch.float32, device=dev) if want_row_loss else None
     nbytes = N.lib().xr_fused_pool_workspace_bytes(m, cn, d)
     ws = _ws(nbytes, dev)
