@@ -9,6 +9,7 @@ no CPU path.  The main entry points are also registered as ``torch.library`` cus
 
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 
 import torch
@@ -39,7 +40,19 @@ def _p(t: torch.Tensor | None):
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # raw handle of torch's CURRENT stream on the current device (cheap C call; honours
+    # torch.cuda.stream(...) contexts)
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
+
+
+_NULL_CTX = contextlib.nullcontext()
+
+
+def _on(dev):
+    """Device guard that costs nothing when `dev` is already current (the common case)."""
+    if dev.index is None or dev.index == torch.cuda.current_device():
+        return _NULL_CTX
+    return torch.cuda.device(dev)
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -81,7 +94,7 @@ def gather_rows(table, idx, sel=None, out_dtype=None, n_out=None, check=False):
     err = torch.zeros(1, dtype=torch.int32, device=dev) if check else None
     if n == 0:
         return out.view(*lead, table.size(1))
-    with torch.cuda.device(dev):
+    with _on(dev):
         N.call("xr_gather_rows", _p(table), table.size(0), table.size(1), _dt(table), _p(idx),
                _p(sel), n, _p(out), _DT[out_dtype], _p(err), _stream())
     if check and int(err.item()):
@@ -95,7 +108,7 @@ def scatter_rows(src, sel, n_dst_rows):
     dst = torch.zeros((n_dst_rows, src.size(1)), dtype=torch.float32, device=dev)
     if src.size(0) == 0:
         return dst
-    with torch.cuda.device(dev):
+    with _on(dev):
         N.call("xr_scatter_rows", _p(src), src.size(0), src.size(1), _p(sel), _p(dst), n_dst_rows,
                _stream())
     return dst
@@ -105,7 +118,7 @@ def row_nonzero(table):
     dev = _require_cuda(table)
     table = table.contiguous()
     out = torch.empty(table.size(0), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         N.call("xr_row_nonzero", _p(table), table.size(0), table.size(1), _dt(table), _p(out),
                _stream())
     return out
@@ -127,7 +140,7 @@ def compact_positions(history_idx, pos_idx, rownz=None, n_table_rows=0):
     if n == 0:
         return attn.view(history_idx.shape).view(torch.bool), sel_attn, sel_pos, pos_mask.view(torch.bool), inv_pos
     ws = _ws(N.lib().xr_compact_workspace_bytes(n), dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         N.call("xr_compact_positions", _p(h), _p(p), _p(rownz), n_table_rows, n, _p(attn),
                _p(sel_attn), _p(sel_pos), _p(pos_mask), _p(inv_pos), _p(counts), _p(ws), _stream())
     m_a, m = (int(v) for v in counts.tolist())
@@ -143,7 +156,7 @@ def scatter_scaled(src, inv_pos, scale, n_dst_rows, out_dtype):
     dst = torch.empty((n_dst_rows, src.size(1)), dtype=out_dtype, device=dev)
     if scale is not None and scale.dtype != torch.float32:
         scale = scale.float()
-    with torch.cuda.device(dev):
+    with _on(dev):
         N.call("xr_scatter_scaled", _p(src), _p(inv_pos), _p(scale), n_dst_rows, src.size(1),
                _p(dst), _DT[out_dtype], _stream())
     return dst
@@ -157,7 +170,7 @@ def normalize_rows(x, eps=1e-8, out_dtype=None, want_y=True):
     inv = torch.empty(x2.size(0), dtype=torch.float32, device=dev)
     if x2.size(0) == 0:
         return (y.view(x.shape) if want_y else None), inv.view(x.shape[:-1])
-    with torch.cuda.device(dev):
+    with _on(dev):
         N.call("xr_normalize_rows", _p(x2), x2.size(0), x2.size(1), _dt(x2), float(eps), _p(y),
                _DT[out_dtype], _p(inv), _stream())
     return (y.view(x.shape) if want_y else None), inv.view(x.shape[:-1])
@@ -176,7 +189,7 @@ def logits_pool(q, pos, neg):
     cn = neg.size(0)
     ld = _ld4(cn + 1)
     logits = torch.empty((m, ld), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         N.call("xr_logits_pool", _p(q), _p(pos), _p(neg), m, cn, d, _dt(q), _p(logits), ld,
                _stream())
     return logits  # columns [0,cn) negatives, column cn the positive
@@ -188,7 +201,7 @@ def logits_dense(q, cand, q_inv=None, cosine=False, eps=1e-8):
     ld = _ld4(c)
     logits = torch.empty((m, ld), dtype=torch.float32, device=dev)
     cand_inv = torch.empty((m, c), dtype=torch.float32, device=dev) if cosine else None
-    with torch.cuda.device(dev):
+    with _on(dev):
         N.call("xr_logits_dense", _p(q), _p(cand), m, c, d, _dt(q), _p(q_inv), _p(cand_inv),
                float(eps), _p(logits), ld, _stream())
     return logits, cand_inv
@@ -199,7 +212,7 @@ def logits_sampled(q, table, cand_idx, table_inv=None, q_inv=None):
     m, c = cand_idx.shape
     ld = _ld4(c)
     logits = torch.empty((m, ld), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         N.call("xr_logits_sampled", _p(q), _p(table), table.size(0), _p(cand_idx), m, c, q.size(1),
                _dt(q), _p(table_inv), _p(q_inv), _p(logits), ld, _stream())
     return logits
@@ -216,7 +229,7 @@ def rowloss(logits, c, cfg, target_mode, target=None, grad_kind=-1, grad_scale=1
     dlogits = torch.empty_like(logits) if grad_kind >= 0 else None
     err = torch.zeros(1, dtype=torch.int32, device=dev) if (check and target is not None) else None
     ws = _ws(N.lib().xr_rowloss_workspace_bytes(m, c, cfg.num_hard_negatives), dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         N.call("xr_rowloss", _p(logits), m, c, ld, target_mode, _p(target), C.byref(cfg), 0x7F,
                grad_kind, float(grad_scale), _p(dlogits), _p(losses), _p(stats), _p(err), _p(ws),
                _stream())
@@ -229,7 +242,7 @@ def dq_pool(dlogits, q, pos, neg, cosine=False, q_inv=None):
     dev = _require_cuda(dlogits, q, pos, neg)
     m, d = q.shape
     dq = torch.empty((m, d), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         N.call("xr_dq_pool", _p(dlogits), dlogits.size(1), _p(q), _p(pos), _p(neg), m, neg.size(0),
                d, _dt(q), int(cosine), _p(q_inv), _p(dq), _stream())
     return dq
@@ -239,7 +252,7 @@ def dq_dense(dlogits, q, cand, cosine=False, q_inv=None, cand_inv=None):
     dev = _require_cuda(dlogits, q, cand)
     m, c, d = cand.shape
     dq = torch.empty((m, d), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         N.call("xr_dq_dense", _p(dlogits), dlogits.size(1), _p(q), _p(cand), m, c, d, _dt(q),
                int(cosine), _p(q_inv), _p(cand_inv), _p(dq), _stream())
     return dq
@@ -249,7 +262,7 @@ def dq_sampled(dlogits, q, table, cand_idx, table_inv=None, q_inv=None):
     dev = _require_cuda(dlogits, q, table, cand_idx)
     m, c = cand_idx.shape
     dq = torch.empty((m, q.size(1)), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         N.call("xr_dq_sampled", _p(dlogits), dlogits.size(1), _p(q), _p(table), table.size(0),
                _p(cand_idx), m, c, q.size(1), _dt(q), _p(table_inv), _p(q_inv), _p(dq), _stream())
     return dq
@@ -275,7 +288,7 @@ def fused_pool_loss(q, pos, neg, loss_kind, cfg, q_inv=None, grad_scale=1.0, wan
     row_loss = torch.empty(m, dtype=torch.float32, device=dev) if want_row_loss else None
     nbytes = N.lib().xr_fused_pool_workspace_bytes(m, cn, d)
     ws = _ws(nbytes, dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         N.call("xr_fused_pool_loss", _p(q), _p(pos), _p(neg), m, cn, d, loss_kind, C.byref(cfg),
                _p(q_inv), float(grad_scale), _p(dq), _p(loss), _p(row_loss), _p(ws), ws.numel(),
                _stream())
@@ -292,7 +305,7 @@ def scores(q, catalog, q_inv=None, cat_inv=None, out=None):
     ld = _ld4(n)
     if out is None:
         out = torch.empty((u, ld), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         N.call("xr_scores", _p(q), u, _p(catalog), n, d, _dt(q), _p(q_inv), _p(cat_inv), _p(out),
                out.size(1), _stream())
     return out
@@ -311,7 +324,7 @@ def _csr(lists, device):
 def mask_excluded(score_mat, n, exclude_lists, col_offset=0):
     dev = _require_cuda(score_mat)
     offs, ids = exclude_lists if isinstance(exclude_lists, tuple) else _csr(exclude_lists, dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         N.call("xr_mask_excluded", _p(score_mat), score_mat.size(0), n, score_mat.size(1),
                col_offset, _p(offs), _p(ids), _stream())
     return score_mat
@@ -336,7 +349,7 @@ def topk(score_mat, k, n=None, col_offset=0):
             break
         nbytes = N.lib().xr_topk_workspace_bytes(uu, n, k)
         ws = _ws(nbytes, dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             N.call("xr_topk", _p(score_mat[lo:]), uu, n, ld, k, col_offset, _p(out_s[lo:]),
                    _p(out_i[lo:]), _p(ws), ws.numel(), _stream())
     return out_s, out_i
@@ -350,7 +363,7 @@ def topk_merge(cand_scores, cand_ids, k):
     out_s = torch.empty((u, k), dtype=torch.float32, device=dev)
     out_i = torch.empty((u, k), dtype=torch.int64, device=dev)
     ws = _ws(N.lib().xr_topk_merge_workspace_bytes(u, k), dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         N.call("xr_topk_merge", _p(cand_scores), _p(cand_ids), u, gk, k, _p(out_s), _p(out_i),
                _p(ws), _stream())
     return out_s, out_i
@@ -372,7 +385,7 @@ def score_groupmax(q, catalog):
     n = catalog.size(0)
     ld = 4 * ((n + 63) // 64)
     gmax = torch.empty((u, ld), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         N.call("xr_score_groupmax", _p(q), u, _p(catalog), n, d, _p(gmax), ld, _stream())
     return gmax
 
@@ -381,7 +394,7 @@ def mask_excluded_ids(score_mat, ids, id_lo, id_hi, exclude=None):
     dev = _require_cuda(score_mat, ids)
     offs, ex = (None, None) if exclude is None else exclude
     u, c = ids.shape
-    with torch.cuda.device(dev):
+    with _on(dev):
         N.call("xr_mask_excluded_ids", _p(score_mat), _p(ids), u, c, score_mat.size(1), id_lo, id_hi,
                _p(offs), _p(ex), _stream())
     return score_mat
@@ -407,7 +420,7 @@ def score_topk(q, catalog, k, q_inv=None, cat_inv=None, exclude=None, col_offset
     out_s = torch.empty((u, k), dtype=torch.float32, device=dev)
     out_i = torch.empty((u, k), dtype=torch.int64, device=dev)
     ws = _ws(N.lib().xr_score_topk_workspace_bytes(u, n, k), dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         N.call("xr_score_topk", _p(q), u, _p(catalog), n, d, _p(q_inv), _p(cat_inv), k, col_offset,
                _p(offs), _p(ids), _p(out_s), _p(out_i), _p(ws), ws.numel(), _stream())
     return out_s, out_i
@@ -421,7 +434,7 @@ def retrieval_metrics(rec_idx, target_lists, top_k):
     offs, ids = target_lists if isinstance(target_lists, tuple) else _csr(target_lists, dev)
     out = torch.empty((u, 7), dtype=torch.float32, device=dev)
     valid = torch.empty(u, dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         N.call("xr_retrieval_metrics", _p(rec_idx), u, k, _p(offs), _p(ids), top_k, _p(out),
                _p(valid), _stream())
     return out, valid.bool()
