@@ -199,6 +199,9 @@ int xr_fused_available(void); /* bit 0: fused loss kernel, bit 1: fused score+to
  * 512); xr_fused_profile_read copies the durations in ms to HOST memory and resets the ring. */
 int xr_fused_profile(int enable);
 int xr_fused_profile_read(float* ms_out_host, int max_n);
+/* profiling aid: per-barrier wait cycles of the last fused call (16 host counters, see the .cu) */
+int xr_fused_wait_stats(int enable, unsigned long long* out16_host);
+int xr_fused_timeline(long long* out512_host); /* profiling aid: per-tile timestamps of CTA 0 */
 size_t xr_fused_pool_workspace_bytes(int64_t m, int64_t cn, int64_t dim);
 int xr_fused_pool_loss(const void* q, const void* pos, const void* neg, int64_t m, int64_t cn,
                        int64_t dim, int loss_kind, const xr_loss_config* cfg,

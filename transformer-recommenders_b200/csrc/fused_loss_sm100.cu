@@ -25,6 +25,8 @@
 #include "common.cuh"
 #include "sm100.cuh"
 
+#include <cstring>
+
 namespace xr {
 
 using namespace sm100;
@@ -66,6 +68,7 @@ struct FusedParams {
   long long gmax_ld;
   int rb_count;
   int* hang_flag;
+  long long* dbg;      // STATS builds: per-tile timestamps of CTA 0 (profiling aid)
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -152,7 +155,7 @@ __device__ __forceinline__ void group_math(const uint32_t (&v)[16], uint32_t (&p
   }
 }
 
-template <int KIND, bool RBF>
+template <int KIND, bool RBF, bool STATS>
 __global__ void __launch_bounds__(fk::THREADS, 1)
 fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
                   const __grid_constant__ CUtensorMap tmap_b, const FusedParams p) {
@@ -207,6 +210,15 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const uint32_t tmem = *tmem_ptr_smem;
 
   // work items: (row block, split of the candidate tiles); identical iteration in every role
+  // the tiles of an item are visited in a rotated order that depends on the row block, so the
+  // CTAs sweeping the same candidate range do not hammer the same L2 lines in lockstep
+  auto rot_tile = [&](int t0, int T, int rb, int tl) {
+    if (diag || KIND == KIND_GMAX) return t0 + tl;   // GMAX: row blocks share catalog tiles via L2
+    const int r = (int)(((unsigned)rb * 29u) % (unsigned)T);
+    int x = tl + r;
+    if (x >= T) x -= T;
+    return t0 + x;
+  };
   auto item_tiles = [&](int item, int& rb, int& t0, int& t1) {
     if (diag) {
       rb = item;
@@ -234,18 +246,19 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
       int rb, t0, t1;
       item_tiles(item, rb, t0, t1);
-      mbar_wait(bar_q_empty, (it & 1) ^ 1, p.hang_flag, 1);
+      mbar_wait<STATS>(bar_q_empty, (it & 1) ^ 1, p.hang_flag, 1);
       if (elect_one()) {
         mbar_expect_tx(bar_q_full, Q_BYTES);
         for (int kb = 0; kb < KB; ++kb)
           tma_load_2d(q_smem + kb * QSUB_BYTES, &tmap_q, bar_q_full, kb * 64, rb * BM);
       }
       __syncwarp();
-      for (int t = t0; t < t1; ++t) {
+      for (int tl = 0; tl < t1 - t0; ++tl) {
+        const int t = rot_tile(t0, t1 - t0, rb, tl);
 #pragma unroll 1
         for (int pr = 0; pr < KB / 2; ++pr, ++g) {
           const uint32_t s = g & (PAIRS - 1);
-          mbar_wait(bar_empty(s), ((g / PAIRS) & 1) ^ 1, p.hang_flag, 2);
+          mbar_wait<STATS>(bar_empty(s), ((g / PAIRS) & 1) ^ 1, p.hang_flag, 2);
           if (elect_one()) {
             mbar_expect_tx(bar_full(s), 2 * SUB_BYTES);
             tma_load_2d(ring + s * 2 * SUB_BYTES, &tmap_b, bar_full(s), pr * 128, t * BN);
@@ -266,19 +279,20 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
       int rb, t0, t1;
       item_tiles(item, rb, t0, t1);
       const int T = t1 - t0;
-      mbar_wait(bar_q_full, it & 1, p.hang_flag, 4);
+      mbar_wait<STATS>(bar_q_full, it & 1, p.hang_flag, 4);
       for (int tl = 0; tl < T; ++tl) {
         const uint32_t tile = tt + tl;
         const int b = tile & 1;
         if (tile >= 2) {   // S/W buffer b is free once tile-2's weights were consumed
-          if (grad) mbar_wait(bar_s_free(b), ((tile - 2) >> 1) & 1, p.hang_flag, 6);
-          else mbar_wait(bar_p_full(b), ((tile - 2) >> 1) & 1, p.hang_flag, 6);
+          if (grad) mbar_wait<STATS>(bar_s_free(b), ((tile - 2) >> 1) & 1, p.hang_flag, 6);
+          else mbar_wait<STATS>(bar_p_full(b), ((tile - 2) >> 1) & 1, p.hang_flag, 6);
         }
         tc_fence_after();
+        if (STATS && p.dbg && blockIdx.x == 0 && lane == 0 && tile < 64) p.dbg[tile * 8 + 0] = clock64();
 #pragma unroll 1
         for (int pr = 0; pr < KB / 2; ++pr, ++g) {
           const uint32_t s = g & (PAIRS - 1);
-          mbar_wait(bar_full(s), (g / PAIRS) & 1, p.hang_flag, 7);
+          mbar_wait<STATS>(bar_full(s), (g / PAIRS) & 1, p.hang_flag, 7);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t a0 = q_desc0 + (uint64_t)(pr * ((2 * QSUB_BYTES) >> 4));
@@ -298,6 +312,7 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
           if (tl == T - 1) umma_commit(bar_q_empty);   // Q is only read by the score MMAs
         }
         __syncwarp();
+        if (STATS && p.dbg && blockIdx.x == 0 && lane == 0 && tile < 64) p.dbg[tile * 8 + 1] = clock64();
       }
       tt += T;
     }
@@ -313,12 +328,13 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
         int rb, t0, t1;
         item_tiles(item, rb, t0, t1);
         const int T = t1 - t0;
-        mbar_wait(bar_o_empty, (it & 1) ^ 1, p.hang_flag, 5);   // epilogue drained the last dQ
+        mbar_wait<STATS>(bar_o_empty, (it & 1) ^ 1, p.hang_flag, 5);   // epilogue drained the last dQ
         for (int tl = 0; tl < T; ++tl, g += KB / 2) {
           const uint32_t tile = tt + tl;
           const int b = tile & 1;
-          mbar_wait(bar_p_full(b), (tile >> 1) & 1, p.hang_flag, 3);
+          mbar_wait<STATS>(bar_p_full(b), (tile >> 1) & 1, p.hang_flag, 3);
           tc_fence_after();
+          if (STATS && p.dbg && blockIdx.x == 0 && lane == 0 && tile < 64) p.dbg[tile * 8 + 5] = clock64();
           if (elect_one()) {
             const uint32_t a_tmem = tmem + COL_S + b * BN;
 #pragma unroll
@@ -373,11 +389,14 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
       for (int tl = 0; tl < T; ++tl) {
         const uint32_t tile = tt + tl;
         const int b = tile & 1;
-        mbar_wait(bar_s_full(b), (tile >> 1) & 1, p.hang_flag, 8);
+        mbar_wait<STATS>(bar_s_full(b), (tile >> 1) & 1, p.hang_flag, 8);
         tc_fence_after();
+        const bool dbg_on = STATS && p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0 && tile < 64;
+        if (dbg_on) p.dbg[tile * 8 + 2] = clock64();
         uint32_t v[16];
         tmem_ld16(tmem_lane + COL_S + b * BN + cg * 16, v);
         tmem_wait_ld();
+        if (dbg_on) p.dbg[tile * 8 + 3] = clock64();
         if (diag) {
           // tile tl holds pos rows [rb*128 + tl*64, +64): the diagonal entry of local row r is
           // column r - tl*64 of tile tl = r/64, owned by column group (r%64)/16
@@ -388,14 +407,14 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
               if (c == j) diag_val = __uint_as_float(v[j]);
           }
         } else if (KIND == KIND_GMAX) {
-          const int ncols = p.cn - (t0 + tl) * BN - cg * 16;
+          const int ncols = p.cn - rot_tile(t0, T, rb, tl) * BN - cg * 16;
           float mx = -CUDART_INF_F;
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             if (j < ncols) mx = fmaxf(mx, __uint_as_float(v[j]));
-          if (row_ok) p.gmax[(long long)row * p.gmax_ld + (long long)(t0 + tl) * CG + cg] = mx;
+          if (row_ok) p.gmax[(long long)row * p.gmax_ld + (long long)rot_tile(t0, T, rb, tl) * CG + cg] = mx;
         } else {
-          const int ncols = p.cn - (t0 + tl) * BN - cg * 16;   // valid candidates in this group
+          const int ncols = p.cn - rot_tile(t0, T, rb, tl) * BN - cg * 16;   // valid candidates in this group
           uint32_t pk[8];
           if (ncols >= 16)
             group_math<KIND, RBF, true>(v, pk, ncols, t_eff, tm, zref2, scale2, p.scale, p.margin,
@@ -413,6 +432,7 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
         tc_fence_before();
         mbar_arrive(bar_p_full(b));
+        if (dbg_on) p.dbg[tile * 8 + 4] = clock64();
       }
       if (diag) {
         if (row_ok && (r_local & 63) >> 4 == cg) p.t_out[row] = diag_val;
@@ -420,7 +440,7 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
         // nothing to flush: the group maxima were written tile by tile
       } else {
         if (grad) {
-          mbar_wait(bar_o_full, it & 1, p.hang_flag, 9);
+          mbar_wait<STATS>(bar_o_full, it & 1, p.hang_flag, 9);
           tc_fence_after();
           float* dst = p.part_o + ((size_t)item * BM + r_local) * D + cg * (D / CG);
 #pragma unroll 1
@@ -680,22 +700,26 @@ static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 // optional per-launch timing of the main fused kernel (bench.py's roofline leg): a ring of
 // CUDA event pairs recorded on the launching stream; nothing is synchronised until it is read.
+static bool g_wait_stats = false;
+static long long* g_dbg_dev = nullptr;
+static long long g_dbg_host[64 * 8];
+static unsigned long long g_wait_host[16];
 constexpr int kProfRing = 512;
 static bool g_prof_on = false;
 static cudaEvent_t g_prof_ev[kProfRing][2];
 static bool g_prof_made = false;
 static int g_prof_n = 0;
 
-template <int KIND, bool RBF>
+template <int KIND, bool RBF, bool STATS = false>
 static int launch_fused1(const CUtensorMap& tq, const CUtensorMap& tb, const FusedParams& p,
                          int grid, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    XR_CUDA(cudaFuncSetAttribute(fused_pool_kernel<KIND, RBF>,
+    XR_CUDA(cudaFuncSetAttribute(fused_pool_kernel<KIND, RBF, STATS>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, fk::SMEM_BYTES));
     configured = true;
   }
-  fused_pool_kernel<KIND, RBF><<<grid, fk::THREADS, fk::SMEM_BYTES, s>>>(tq, tb, p);
+  fused_pool_kernel<KIND, RBF, STATS><<<grid, fk::THREADS, fk::SMEM_BYTES, s>>>(tq, tb, p);
   XR_LAUNCH_CHECK("fused_pool_kernel");
   return XR_OK;
 }
@@ -768,6 +792,7 @@ extern "C" int xr_fused_pool_loss(const void* q, const void* pos, const void* ne
   int* flags = (int*)w;
   XR_CUDA(cudaMemsetAsync(flags, 0, 256, s));
 
+
   CUtensorMap tq, tp, tn;
   int rc;
   if ((rc = make_tmap_bf16_rows(&tq, q, m, dim, dim, fk::BM))) return rc;
@@ -802,7 +827,15 @@ extern "C" int xr_fused_pool_loss(const void* q, const void* pos, const void* ne
   const bool prof = g_prof_on && g_prof_n < kProfRing;
   if (prof) cudaEventRecord(g_prof_ev[g_prof_n][0], s);
   switch (loss_kind) {
-    case XR_LOSS_INFONCE: rc = launch_fused<XR_LOSS_INFONCE>(tq, tn, p, grid, s); break;
+    case XR_LOSS_INFONCE:
+      if (g_wait_stats) {   // profiling aid
+        if (!g_dbg_dev) XR_CUDA(cudaMalloc(&g_dbg_dev, sizeof(g_dbg_host)));
+        XR_CUDA(cudaMemsetAsync(g_dbg_dev, 0, sizeof(g_dbg_host), s));
+        p.dbg = g_dbg_dev;
+        rc = launch_fused1<XR_LOSS_INFONCE, true, true>(tq, tn, p, grid, s);
+      }
+      else rc = launch_fused<XR_LOSS_INFONCE>(tq, tn, p, grid, s);
+      break;
     case XR_LOSS_NCE: rc = launch_fused<XR_LOSS_NCE>(tq, tn, p, grid, s); break;
     case XR_LOSS_PAIRWISE_HINGE: rc = launch_fused<XR_LOSS_PAIRWISE_HINGE>(tq, tn, p, grid, s); break;
     case XR_LOSS_PAIRWISE_LOGISTIC: rc = launch_fused<XR_LOSS_PAIRWISE_LOGISTIC>(tq, tn, p, grid, s); break;
@@ -820,6 +853,11 @@ extern "C" int xr_fused_pool_loss(const void* q, const void* pos, const void* ne
   // loss_out[1] (if the caller left room) receives the fp32 copy the loss module returns
   sum_rows_kernel<<<1, 1024, 0, s>>>(rl, m, loss_out, reinterpret_cast<float*>(loss_out + 1));
   XR_LAUNCH_CHECK("sum_rows");
+  if (g_wait_stats) {
+    XR_CUDA(cudaMemcpyAsync(g_wait_host, flags + 16, sizeof(g_wait_host), cudaMemcpyDeviceToHost, s));
+    if (g_dbg_dev) XR_CUDA(cudaMemcpyAsync(g_dbg_host, g_dbg_dev, sizeof(g_dbg_host), cudaMemcpyDeviceToHost, s));
+    XR_CUDA(cudaStreamSynchronize(s));
+  }
   return XR_OK;
 }
 
@@ -866,6 +904,24 @@ extern "C" int xr_score_groupmax(const void* q, int64_t u, const void* catalog, 
   rc = launch_fused1<fk::KIND_GMAX, false>(tq, tc, p, grid, s);
   if (prof) cudaEventRecord(g_prof_ev[g_prof_n++][1], s);
   return rc;
+}
+
+// profiling aid (not part of the product path): summed wait cycles per barrier tag of the LAST
+// xr_fused_pool_loss call while enabled.  tags: 1 q_empty(producer) 2 ring-empty(producer)
+// 3 p_full(gradient issuer) 4 q_full 5 o_empty 6 s_free(score issuer) 7 ring-full(score issuer)
+// 8 s_full(epilogue warps) 9 o_full(epilogue warps)
+// per-tile timestamps of CTA 0 from the last stats-enabled call: 64 tiles x 8 slots
+// [0] score issue start [1] score issued+committed [2] epilogue woke on s_full [3] tcgen05.ld done
+// [4] weights stored + p_full arrive [5] gradient issuer woke on p_full
+extern "C" int xr_fused_timeline(long long* out512_host) {
+  memcpy(out512_host, g_dbg_host, sizeof(g_dbg_host));
+  return XR_OK;
+}
+
+extern "C" int xr_fused_wait_stats(int enable, unsigned long long* out16_host) {
+  g_wait_stats = enable != 0;
+  if (out16_host) memcpy(out16_host, g_wait_host, sizeof(g_wait_host));
+  return XR_OK;
 }
 
 extern "C" int xr_fused_profile(int enable) {

@@ -22,3 +22,5 @@ extern "C" int xr_score_groupmax(const void*, int64_t, const void*, int64_t, int
   xr::set_error("xr_score_groupmax: tcgen05 kernels not compiled into this build");
   return XR_E_UNSUPPORTED;
 }
+extern "C" int xr_fused_wait_stats(int, unsigned long long*) { return XR_E_UNSUPPORTED; }
+extern "C" int xr_fused_timeline(long long*) { return XR_E_UNSUPPORTED; }

@@ -41,10 +41,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must not hang the GPU.  After ~2 s of spinning the kernel
-// records the barrier id and traps (the launch fails with an error instead of wedging the SM).
+// records the barrier id in hang_flag[0] and traps (the launch fails with an error instead of
+// wedging the SM).  With STATS (profiling aid) lane 0 of every waiting warp adds its wait cycles
+// to the per-tag counters at hang_flag + 16.
+template <bool STATS = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* hang_flag, int tag) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  if (!STATS) {
+    if (mbar_try_wait(bar, parity)) return;
+  }
+  const long long t0 = clock64();   // try_wait itself blocks for a HW-bounded time
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000ll) {
       if (hang_flag) atomicExch(hang_flag, tag);
@@ -52,6 +57,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* ha
       asm volatile("trap;");
     }
   }
+  if (STATS && (threadIdx.x & 31) == 0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(hang_flag + 16) + tag,
+              (unsigned long long)(clock64() - t0));
 }
 
 // ---- TMA ----------------------------------------------------------------------------------------
