@@ -22,7 +22,9 @@ lib = xr._native.lib()
 for _ in range(3):
     fn(out["query_embed"], out["candidate_embed"])
 torch.cuda.synchronize()
-lib.xr_fused_wait_stats(1, None)
+mask = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+mode = int(sys.argv[2]) if len(sys.argv) > 2 else 1   # 1 wait counters + timeline, 2 timeline only
+lib.xr_fused_wait_stats(mode | (mask << 8), None)
 fn(out["query_embed"], out["candidate_embed"])
 torch.cuda.synchronize()
 buf = (ctypes.c_uint64 * 16)()
@@ -40,7 +42,8 @@ for t, n in names.items():
 tl = (ctypes.c_int64 * 512)()
 lib.xr_fused_timeline(tl)
 base = tl[0]
-print("tile: score_issue_start  issued  | epi_wake  ld_done  p_arrive | grad_wake   (cycles rel. to tile 0 start)")
-for t in range(24):
-    r = [tl[t * 8 + k] - base if tl[t * 8 + k] else -1 for k in range(6)]
-    print(f"{t:3d}: {r[0]:8d} {r[1]:8d} | {r[2]:8d} {r[3]:8d} {r[4]:8d} | {r[5]:8d}")
+print(f"ablate mask {mask}")
+print("tile: score_issue_start  issued  | epi_wake  ld_done  math_done st_done p_arrive | grad_wake   (cycles rel. to tile 0 start)")
+for t in range(16):
+    r = [tl[t * 8 + k] - base if tl[t * 8 + k] else -1 for k in range(8)]
+    print(f"{t:3d}: {r[0]:8d} {r[1]:8d} | {r[2]:8d} {r[3]:8d} {r[6]:8d} {r[7]:8d} {r[4]:8d} | {r[5]:8d}")

@@ -18,10 +18,16 @@
 // per work item and folded by a small finalize kernel in a fixed order (deterministic, no
 // floating-point atomics).
 //
-// One CTA per SM (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2-5 = epilogue (one TMEM lane quadrant each).  TMEM: 384 columns dQ accumulator +
-// 2 x 64 columns S/W double buffer = 512.  Shared memory: Q tile 96 KB + a 16-slot ring of
-// 64x64 bf16 sub-tiles (128 KB) fed by TMA with 128-byte swizzle.
+// One CTA per SM (640 threads): warp 0 = TMA producer, warp 1 = score-MMA issuer (+ TMEM owner),
+// warp 2 = gradient-MMA issuer, warps 4-19 = epilogue (4 TMEM lane quadrants x 4 column groups).
+// TMEM (512 columns): dQ accumulator 384 | S 64 | W double buffer 2 x 32 (packed bf16).  Without the
+// gradient pass the last 128 columns are an S double buffer.  Shared memory: Q tile 96 KB + a ring
+// of 8 pairs of 64x64 bf16 sub-tiles (128 KB) fed by TMA with 128-byte swizzle.
+//
+// Measured facts the structure follows (profiles/microbench/): the tcgen05.mma queue is ~4 deep,
+// so an issuer must never wait for an MMA it has just issued; shared-memory ingest by TMA is
+// ~35 B/cycle/SM whatever the ring depth or multicast; a commit -> waiter hand-off costs ~260
+// cycles, an mbarrier arrive -> waiter hand-off ~130.
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -43,13 +49,14 @@ constexpr int QSUB_BYTES = BM * 64 * 2;
 constexpr int Q_BYTES = KB * QSUB_BYTES;
 constexpr int RING_BYTES = SLOTS * SUB_BYTES;
 constexpr int BAR_OFF = Q_BYTES + RING_BYTES;
-constexpr int NBARS = 2 * PAIRS + 10;
+constexpr int NBARS = 2 * PAIRS + 12;
 constexpr int SMEM_BYTES = BAR_OFF + NBARS * 8 + 16 + 1024;  // + manual 1024 B alignment slack
 constexpr int EPI_WARPS = 16;           // 4 TMEM lane quadrants x 4 column groups
 constexpr int CG = 4;
 constexpr int THREADS = 128 + EPI_WARPS * 32;   // producer, 2 MMA issuers, 1 spare, 16 epilogue
 constexpr int TMEM_COLS = 512;
-constexpr int COL_O = 0, COL_S = 384;
+constexpr int COL_O = 0, COL_S = 384;   // S: one 64-column buffer with the gradient pass, two without
+constexpr int COL_W = 448;              // W: two 32-column buffers of packed bf16 weights (gradient pass)
 constexpr int KIND_DIAG = 100;      // extract q_i . pos_i from the diagonal of Q_blk . Pos_blk^T
 constexpr int KIND_GMAX = 101;      // retrieval: max score of every 16-column group (no loss)
 constexpr int NSCAL = 4;
@@ -69,6 +76,7 @@ struct FusedParams {
   int rb_count;
   int* hang_flag;
   long long* dbg;      // STATS builds: per-tile timestamps of CTA 0 (profiling aid)
+  int ablate;          // STATS builds: 1 skip TMA loads, 2 skip epilogue math, 4 skip score MMAs, 8 skip dQ MMAs, 16 skip epilogue TMEM ld/st
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -155,11 +163,13 @@ __device__ __forceinline__ void group_math(const uint32_t (&v)[16], uint32_t (&p
   }
 }
 
-template <int KIND, bool RBF, bool STATS>
+template <int KIND, bool RBF, int DBG>
 __global__ void __launch_bounds__(fk::THREADS, 1)
 fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
                   const __grid_constant__ CUtensorMap tmap_b, const FusedParams p) {
   using namespace fk;
+  constexpr bool STATS = DBG == 2;     // wait counters + timeline (profiling aid)
+  constexpr bool ABL = DBG != 0;       // ablation switches (timing experiments)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;   // SWIZZLE_128B operands need 1024 B alignment
@@ -172,16 +182,19 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
   auto bar_empty = [&](uint32_t s) { return bars + 8u * (PAIRS + s); };
   const uint32_t bar_q_full = bars + 8u * (2 * PAIRS + 0);
   const uint32_t bar_q_empty = bars + 8u * (2 * PAIRS + 1);
-  auto bar_s_full = [&](int b) { return bars + 8u * (2 * PAIRS + 2 + b); };
-  auto bar_p_full = [&](int b) { return bars + 8u * (2 * PAIRS + 4 + b); };
-  auto bar_s_free = [&](int b) { return bars + 8u * (2 * PAIRS + 6 + b); };
+  auto bar_s_full = [&](int b) { return bars + 8u * (2 * PAIRS + 2 + b); };   // S(tile) complete
+  auto bar_p_full = [&](int b) { return bars + 8u * (2 * PAIRS + 4 + b); };   // W(tile) stored
+  auto bar_s_read = [&](int b) { return bars + 8u * (2 * PAIRS + 6 + b); };   // S(tile) is in registers
   const uint32_t bar_o_full = bars + 8u * (2 * PAIRS + 8);
   const uint32_t bar_o_empty = bars + 8u * (2 * PAIRS + 9);
+  auto bar_w_free = [&](int b) { return bars + 8u * (2 * PAIRS + 10 + b); };  // dQ(tile) consumed W
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + BAR_OFF + NBARS * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool diag = (KIND == KIND_DIAG);
   const bool grad = !diag && KIND != KIND_GMAX && p.with_grad;
+  // S buffers: ONE with the gradient pass (the other 64 columns hold the W double buffer), two without
+  const int nsb_shift = grad ? 0 : 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < PAIRS; ++s) {
@@ -192,11 +205,14 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
     mbar_init(bar_q_empty, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_s_full(b), 1);
+      // every epilogue thread waits and arrives for itself: measured faster than one polling /
+      // arriving lane per warp plus __syncwarp (reconvergence sits on the critical path)
       mbar_init(bar_p_full(b), EPI_WARPS * 32);
-      mbar_init(bar_s_free(b), 1);
+      mbar_init(bar_s_read(b), EPI_WARPS * 32);
+      mbar_init(bar_w_free(b), 1);
     }
     mbar_init(bar_o_full, 1);
-    mbar_init(bar_o_empty, EPI_WARPS * 32);
+    mbar_init(bar_o_empty, EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -260,9 +276,13 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
           const uint32_t s = g & (PAIRS - 1);
           mbar_wait<STATS>(bar_empty(s), ((g / PAIRS) & 1) ^ 1, p.hang_flag, 2);
           if (elect_one()) {
-            mbar_expect_tx(bar_full(s), 2 * SUB_BYTES);
-            tma_load_2d(ring + s * 2 * SUB_BYTES, &tmap_b, bar_full(s), pr * 128, t * BN);
-            tma_load_2d(ring + s * 2 * SUB_BYTES + SUB_BYTES, &tmap_b, bar_full(s), pr * 128 + 64, t * BN);
+            if (ABL && (p.ablate & 1)) {
+              mbar_arrive(bar_full(s));
+            } else {
+              mbar_expect_tx(bar_full(s), 2 * SUB_BYTES);
+              tma_load_2d(ring + s * 2 * SUB_BYTES, &tmap_b, bar_full(s), pr * 128, t * BN);
+              tma_load_2d(ring + s * 2 * SUB_BYTES + SUB_BYTES, &tmap_b, bar_full(s), pr * 128 + 64, t * BN);
+            }
           }
           __syncwarp();
         }
@@ -270,6 +290,12 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
   } else if (warp == 1) {
     // ========================= score MMA issuer: S = Q . Neg^T =========================
+    // The tcgen05.mma queue is only ~4 instructions deep (profiles/microbench/umma_mix.cu), so an
+    // issuer that waits for the completion of an MMA it has just issued drains the tensor pipe.
+    // Neither issuer does: S(t+1) needs the epilogue to have LOADED S(t) into registers
+    // (bar_s_read, ~100 cycles after S(t) completes, hidden behind dQ(t-1)), dQ(t) needs W(t),
+    // which the epilogue finished a whole S pass earlier.  Steady-state pipe order:
+    //     S(t) dQ(t-1) S(t+1) dQ(t) ...
     // warp-uniform control flow; descriptors live in uniform registers, one elected lane issues
     constexpr uint32_t idesc_s = umma_idesc_bf16(BM, BN, 0, 0);    // both operands K-major
     const uint64_t q_desc0 = umma_desc_sw128(q_smem, 16, 1024);
@@ -282,13 +308,11 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
       mbar_wait<STATS>(bar_q_full, it & 1, p.hang_flag, 4);
       for (int tl = 0; tl < T; ++tl) {
         const uint32_t tile = tt + tl;
-        const int b = tile & 1;
-        if (tile >= 2) {   // S/W buffer b is free once tile-2's weights were consumed
-          if (grad) mbar_wait<STATS>(bar_s_free(b), ((tile - 2) >> 1) & 1, p.hang_flag, 6);
-          else mbar_wait<STATS>(bar_p_full(b), ((tile - 2) >> 1) & 1, p.hang_flag, 6);
-        }
+        const uint32_t use = tile >> nsb_shift;            // how often this S buffer was used before
+        const int sb = tile & ((1 << nsb_shift) - 1);
+        if (use >= 1) mbar_wait<STATS>(bar_s_read(sb), (use - 1) & 1, p.hang_flag, 6);
         tc_fence_after();
-        if (STATS && p.dbg && blockIdx.x == 0 && lane == 0 && tile < 64) p.dbg[tile * 8 + 0] = clock64();
+        if (ABL && p.dbg && blockIdx.x == 0 && lane == 0 && tile < 64) p.dbg[tile * 8 + 0] = clock64();
 #pragma unroll 1
         for (int pr = 0; pr < KB / 2; ++pr, ++g) {
           const uint32_t s = g & (PAIRS - 1);
@@ -297,28 +321,32 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
           if (elect_one()) {
             const uint64_t a0 = q_desc0 + (uint64_t)(pr * ((2 * QSUB_BYTES) >> 4));
             const uint64_t b0 = ring_k_desc0 + (uint64_t)(s * ((2 * SUB_BYTES) >> 4));
+            if (!(ABL && (p.ablate & 4)))
 #pragma unroll
             for (int h = 0; h < 2; ++h)
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_ss(tmem + COL_S + b * BN, a0 + h * (QSUB_BYTES >> 4) + 2 * k,
+                umma_ss(tmem + COL_S + sb * BN, a0 + h * (QSUB_BYTES >> 4) + 2 * k,
                         b0 + h * (SUB_BYTES >> 4) + 2 * k, idesc_s, (pr | h | k) ? 1u : 0u);
             if (!grad) umma_commit(bar_empty(s));   // forward only: the pair is free after S
           }
           __syncwarp();
         }
         if (elect_one()) {
-          umma_commit(bar_s_full(b));
+          umma_commit(bar_s_full(sb));
           if (tl == T - 1) umma_commit(bar_q_empty);   // Q is only read by the score MMAs
         }
         __syncwarp();
-        if (STATS && p.dbg && blockIdx.x == 0 && lane == 0 && tile < 64) p.dbg[tile * 8 + 1] = clock64();
+        if (ABL && p.dbg && blockIdx.x == 0 && lane == 0 && tile < 64) p.dbg[tile * 8 + 1] = clock64();
       }
       tt += T;
     }
   } else if (warp == 2) {
     // ========================= gradient MMA issuer: dQ += W . Neg =========================
-    // A = W from TMEM (8 columns per K=16 step), B = the tile's pairs addressed MN-major
+    // A = W from TMEM (8 columns per K=16 step), B = the tile's pairs addressed MN-major.
+    // pair-outer order: a pair goes back to the producer as soon as ITS four K-steps are done, so
+    // the reload of the tile's 48 KB (shared-memory ingest is ~35 B/cycle/SM,
+    // profiles/microbench/tma_stream.cu) starts two thirds of a dQ pass earlier
     if (grad) {
       constexpr uint32_t idesc_o = umma_idesc_bf16(BM, 128, 0, 1);
       // MN-major view of a pair: two 64-column atoms SUB_BYTES apart, 8-row groups of 1 KB
@@ -331,25 +359,25 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
         mbar_wait<STATS>(bar_o_empty, (it & 1) ^ 1, p.hang_flag, 5);   // epilogue drained the last dQ
         for (int tl = 0; tl < T; ++tl, g += KB / 2) {
           const uint32_t tile = tt + tl;
-          const int b = tile & 1;
-          mbar_wait<STATS>(bar_p_full(b), (tile >> 1) & 1, p.hang_flag, 3);
+          const int wb = tile & 1;
+          mbar_wait<STATS>(bar_p_full(wb), (tile >> 1) & 1, p.hang_flag, 3);
           tc_fence_after();
-          if (STATS && p.dbg && blockIdx.x == 0 && lane == 0 && tile < 64) p.dbg[tile * 8 + 5] = clock64();
+          if (ABL && p.dbg && blockIdx.x == 0 && lane == 0 && tile < 64) p.dbg[tile * 8 + 5] = clock64();
           if (elect_one()) {
-            const uint32_t a_tmem = tmem + COL_S + b * BN;
+            const uint32_t a_tmem = tmem + COL_W + wb * (BN / 2);
 #pragma unroll
-            for (int ks = 0; ks < BN / 16; ++ks) {
+            for (int pr = 0; pr < KB / 2; ++pr) {
+              const uint32_t s = (g + pr) & (PAIRS - 1);
+              if (!(ABL && (p.ablate & 8)))
 #pragma unroll
-              for (int pr = 0; pr < KB / 2; ++pr) {
-                const uint32_t s = (g + pr) & (PAIRS - 1);
+              for (int ks = 0; ks < BN / 16; ++ks) {
                 const uint64_t bdesc = ring_mn_desc0 + (uint64_t)(s * ((2 * SUB_BYTES) >> 4) + ks * (2048 >> 4));
-                umma_ts(tmem + COL_O + pr * 128, a_tmem + ks * 16, bdesc, idesc_o,
+                umma_ts(tmem + COL_O + pr * 128, a_tmem + ks * 8, bdesc, idesc_o,
                         (tl == 0 && ks == 0) ? 0u : 1u);
               }
+              umma_commit(bar_empty(s));
             }
-#pragma unroll
-            for (int pr = 0; pr < KB / 2; ++pr) umma_commit(bar_empty((g + pr) & (PAIRS - 1)));
-            umma_commit(bar_s_free(b));
+            umma_commit(bar_w_free(wb));
             if (tl == T - 1) umma_commit(bar_o_full);
           }
           __syncwarp();
@@ -388,14 +416,27 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
       float cnt = 0.f, sum_a = 0.f, sum_w = 0.f, diag_val = 0.f;
       for (int tl = 0; tl < T; ++tl) {
         const uint32_t tile = tt + tl;
-        const int b = tile & 1;
-        mbar_wait<STATS>(bar_s_full(b), (tile >> 1) & 1, p.hang_flag, 8);
+        const uint32_t use = tile >> nsb_shift;
+        const int sb = tile & ((1 << nsb_shift) - 1);
+        const int wb = tile & 1;
+        mbar_wait<STATS>(bar_s_full(sb), use & 1, p.hang_flag, 8);
         tc_fence_after();
-        const bool dbg_on = STATS && p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0 && tile < 64;
+        const bool dbg_on = ABL && p.dbg && blockIdx.x == 0 && warp == 4 && lane == 0 && tile < 64;
         if (dbg_on) p.dbg[tile * 8 + 2] = clock64();
         uint32_t v[16];
-        tmem_ld16(tmem_lane + COL_S + b * BN + cg * 16, v);
-        tmem_wait_ld();
+        if (ABL && (p.ablate & 16)) {   // no TMEM traffic from the epilogue at all
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0x3c003c00u + tile;
+        } else {
+          tmem_ld16(tmem_lane + COL_S + sb * BN + cg * 16, v);
+          tmem_wait_ld();
+        }
+        // the logits are in registers: hand the S buffer back to the score issuer right away
+        const bool late_read = ABL && (p.ablate & 64);
+        if (!late_read) {
+          tc_fence_before();
+          mbar_arrive(bar_s_read(sb));
+        }
         if (dbg_on) p.dbg[tile * 8 + 3] = clock64();
         if (diag) {
           // tile tl holds pos rows [rb*128 + tl*64, +64): the diagonal entry of local row r is
@@ -416,22 +457,36 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
         } else {
           const int ncols = p.cn - rot_tile(t0, T, rb, tl) * BN - cg * 16;   // valid candidates in this group
           uint32_t pk[8];
-          if (ncols >= 16)
+          if (ABL && (p.ablate & 2)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pk[j] = v[j];
+          } else if (ncols >= 16)
             group_math<KIND, RBF, true>(v, pk, ncols, t_eff, tm, zref2, scale2, p.scale, p.margin,
                                         round_scaled, cnt, sum_a, sum_w);
           else
             group_math<KIND, RBF, false>(v, pk, ncols, t_eff, tm, zref2, scale2, p.scale, p.margin,
                                          round_scaled, cnt, sum_a, sum_w);
           if (grad) {
-            // W goes back into the first 8 of this group's OWN 16 columns (already in registers),
-            // so no other warp's unread logits are overwritten; K-step ks of the dQ MMA reads
-            // columns [16 ks, 16 ks + 8)
-            tmem_st8(tmem_lane + COL_S + b * BN + cg * 16, pk);
-            tmem_wait_st();
+            // W (16 bf16 = 8 packed columns per group) goes to its own double buffer, so the S
+            // buffer never waits for a gradient MMA; buffer wb was last read by dQ(tile - 2)
+            if (dbg_on) p.dbg[tile * 8 + 6] = clock64();
+            if (tile >= 2 && !(ABL && (p.ablate & 32))) {
+              mbar_wait<STATS>(bar_w_free(wb), ((tile - 2) >> 1) & 1, p.hang_flag, 10);
+              tc_fence_after();
+            }
+            if (!(ABL && (p.ablate & 16))) {
+              tmem_st8(tmem_lane + COL_W + wb * (BN / 2) + cg * 8, pk);
+              tmem_wait_st();
+            }
+            if (dbg_on) p.dbg[tile * 8 + 7] = clock64();
+            tc_fence_before();
+            mbar_arrive(bar_p_full(wb));
           }
         }
-        tc_fence_before();
-        mbar_arrive(bar_p_full(b));
+        if (late_read) {
+          tc_fence_before();
+          mbar_arrive(bar_s_read(sb));
+        }
         if (dbg_on) p.dbg[tile * 8 + 4] = clock64();
       }
       if (diag) {
@@ -455,7 +510,8 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
             }
           }
           tc_fence_before();
-          mbar_arrive(bar_o_empty);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_o_empty);
         }
         if (row_ok) {
           float* ds = p.part_s + (((size_t)item * CG + cg) * BM + r_local) * NSCAL;
@@ -701,6 +757,8 @@ static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 // optional per-launch timing of the main fused kernel (bench.py's roofline leg): a ring of
 // CUDA event pairs recorded on the launching stream; nothing is synchronised until it is read.
 static bool g_wait_stats = false;
+static int g_ablate = 0;
+static bool g_timeline = false;
 static long long* g_dbg_dev = nullptr;
 static long long g_dbg_host[64 * 8];
 static unsigned long long g_wait_host[16];
@@ -710,16 +768,16 @@ static cudaEvent_t g_prof_ev[kProfRing][2];
 static bool g_prof_made = false;
 static int g_prof_n = 0;
 
-template <int KIND, bool RBF, bool STATS = false>
+template <int KIND, bool RBF, int DBG = 0>
 static int launch_fused1(const CUtensorMap& tq, const CUtensorMap& tb, const FusedParams& p,
                          int grid, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    XR_CUDA(cudaFuncSetAttribute(fused_pool_kernel<KIND, RBF, STATS>,
+    XR_CUDA(cudaFuncSetAttribute(fused_pool_kernel<KIND, RBF, DBG>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, fk::SMEM_BYTES));
     configured = true;
   }
-  fused_pool_kernel<KIND, RBF, STATS><<<grid, fk::THREADS, fk::SMEM_BYTES, s>>>(tq, tb, p);
+  fused_pool_kernel<KIND, RBF, DBG><<<grid, fk::THREADS, fk::SMEM_BYTES, s>>>(tq, tb, p);
   XR_LAUNCH_CHECK("fused_pool_kernel");
   return XR_OK;
 }
@@ -828,11 +886,13 @@ extern "C" int xr_fused_pool_loss(const void* q, const void* pos, const void* ne
   if (prof) cudaEventRecord(g_prof_ev[g_prof_n][0], s);
   switch (loss_kind) {
     case XR_LOSS_INFONCE:
-      if (g_wait_stats) {   // profiling aid
+      if (g_wait_stats || g_ablate || g_timeline) {   // profiling aid
         if (!g_dbg_dev) XR_CUDA(cudaMalloc(&g_dbg_dev, sizeof(g_dbg_host)));
-        XR_CUDA(cudaMemsetAsync(g_dbg_dev, 0, sizeof(g_dbg_host), s));
         p.dbg = g_dbg_dev;
-        rc = launch_fused1<XR_LOSS_INFONCE, true, true>(tq, tn, p, grid, s);
+        p.ablate = g_ablate;
+        XR_CUDA(cudaMemsetAsync(g_dbg_dev, 0, sizeof(g_dbg_host), s));
+        if (g_wait_stats) rc = launch_fused1<XR_LOSS_INFONCE, true, 2>(tq, tn, p, grid, s);
+        else rc = launch_fused1<XR_LOSS_INFONCE, true, 1>(tq, tn, p, grid, s);
       }
       else rc = launch_fused<XR_LOSS_INFONCE>(tq, tn, p, grid, s);
       break;
@@ -853,7 +913,7 @@ extern "C" int xr_fused_pool_loss(const void* q, const void* pos, const void* ne
   // loss_out[1] (if the caller left room) receives the fp32 copy the loss module returns
   sum_rows_kernel<<<1, 1024, 0, s>>>(rl, m, loss_out, reinterpret_cast<float*>(loss_out + 1));
   XR_LAUNCH_CHECK("sum_rows");
-  if (g_wait_stats) {
+  if (g_wait_stats || g_timeline) {
     XR_CUDA(cudaMemcpyAsync(g_wait_host, flags + 16, sizeof(g_wait_host), cudaMemcpyDeviceToHost, s));
     if (g_dbg_dev) XR_CUDA(cudaMemcpyAsync(g_dbg_host, g_dbg_dev, sizeof(g_dbg_host), cudaMemcpyDeviceToHost, s));
     XR_CUDA(cudaStreamSynchronize(s));
@@ -919,7 +979,9 @@ extern "C" int xr_fused_timeline(long long* out512_host) {
 }
 
 extern "C" int xr_fused_wait_stats(int enable, unsigned long long* out16_host) {
-  g_wait_stats = enable != 0;
+  g_wait_stats = (enable & 1) != 0;
+  g_timeline = (enable & 2) != 0;   // per-tile timestamps without the wait counters
+  g_ablate = enable >> 8;   // ablation mask for timing experiments (results are garbage)
   if (out16_host) memcpy(out16_host, g_wait_host, sizeof(g_wait_host));
   return XR_OK;
 }
