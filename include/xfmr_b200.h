@@ -208,6 +208,32 @@ int xr_fused_pool_loss(const void* q, const void* pos, const void* neg, int64_t 
                        const float* q_inv_norm, float grad_scale, float* dq, double* loss_out,
                        float* row_loss, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- the whole scoring-and-loss step, sync-free ----------------------------------------------
+ * RecommenderModel.compute_embeds (models.py:388-416) + EmbedLoss.forward (losses.py:128-155)
+ * + the backward to the encoder output (autograd of models.py:392, 415), for ONE SeqBatch of
+ * n_pos = B*L positions, in one stream-ordered call with no device->host copy: the row counts
+ * M_a / M stay on the device (`counts`, int64[2], also an output), the tensor-core kernel is
+ * planned there, and every buffer is sized by n_pos — so the launch sequence is static and the
+ * call can be captured into a CUDA graph.  The same kernels, in the same order, as
+ * xr_compact_positions + xr_gather_rows x3 + xr_fused_pool_loss + xr_scatter_scaled: results
+ * are bit-identical to that sequence (tests/test_gpu_step.py).
+ *   history_idx / pos_idx / neg_idx: int64[n_pos] (SeqBatch index tensors, flattened B*L)
+ *   tok:       (n_pos, dim) encoder output, XR_F32 or XR_BF16 (rounded to bf16 operands)
+ *   table_bf16:(n_table_rows, dim) bf16 item table, row 0 = padding;  rownz: xr_row_nonzero of
+ *              the fp32 master table (nullable: idx != 0)
+ *   loss_kind: InfoNCE / NCE / PairwiseHinge / PairwiseLogistic (dot-product kinds)
+ *   dtok:      (n_pos, dim) dL/d tok scaled by grad_scale, zero rows for unselected positions;
+ *              nullable = forward only.  loss_out: double[2] ([0] f64 sum, [1] low word = f32).
+ *   err_flag:  nullable device int32, set to 1 on an out-of-range item index.
+ *   workspace: >= xr_pool_step_workspace_bytes(n_pos, dim) bytes, 256-byte aligned.             */
+size_t xr_pool_step_workspace_bytes(int64_t n_pos, int64_t dim);
+int xr_pool_step(const int64_t* history_idx, const int64_t* pos_idx, const int64_t* neg_idx,
+                 int64_t n_pos, const void* tok, int tok_dtype, const void* table_bf16,
+                 const uint8_t* rownz, int64_t n_table_rows, int64_t dim, int loss_kind,
+                 const xr_loss_config* cfg, float grad_scale, void* dtok, int dtok_dtype,
+                 double* loss_out, int64_t* counts, int32_t* err_flag, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
 /* ---- family 3: top-k -------------------------------------------------------------------------
  * Exact top-k of each row of a materialised (U,N) fp32 score matrix under the total order
  * (score descending, column ascending) — the result the reference's ANN search

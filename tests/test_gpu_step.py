@@ -1,0 +1,136 @@
+"""GPU parity tests for the sync-free scoring-and-loss step (xr_pool_step / PoolLossStep):
+bit-identical to compute_embeds + loss module + backward (the same kernels, planned on the device
+instead of the host), and within tolerance of the oracle."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import xfmr_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+KINDS = ["InfoNCELoss", "NCELoss", "PairwiseHingeLoss", "PairwiseLogisticLoss"]
+
+
+@pytest.fixture(scope="module")
+def xr():
+    import xfmr_rec_b200 as pkg
+
+    if not torch.cuda.is_available() or torch.cuda.get_device_capability()[0] != 10:
+        pytest.skip("needs an sm_100 device")
+    assert pkg._native.lib().xr_fused_available() & 1, "tcgen05 kernels missing from the build"
+    return pkg
+
+
+def modular(xr, emb, loss_fn, b, tok_dtype):
+    """The drop-in path: compute_embeds -> loss -> backward (one host sync for the counts)."""
+    tok = torch.from_numpy(b["token_embeddings"]).cuda().to(tok_dtype).requires_grad_(True)
+    hist, pos, neg = (torch.from_numpy(b[k]).cuda() for k in
+                      ("history_item_idx", "pos_item_idx", "neg_item_idx"))
+    out = xr.models.compute_embeds(emb, tok, hist, pos, neg, candidate_dtype=torch.bfloat16)
+    q = out["query_embed"]
+    if q.dtype != torch.bfloat16:   # the step rounds fp32 encoder output to bf16 operands
+        q = q.bfloat16()
+    loss = loss_fn(q, out["candidate_embed"])
+    loss.backward()
+    return loss.detach(), tok.grad, int(out["attention_mask"].sum()), q.size(0)
+
+
+def run_step(step, b, dtype):
+    tok = torch.from_numpy(b["token_embeddings"]).to(dtype)
+    return step(tok.pin_memory(), torch.from_numpy(b["history_item_idx"]).pin_memory(),
+                torch.from_numpy(b["pos_item_idx"]).pin_memory(),
+                torch.from_numpy(b["neg_item_idx"]).pin_memory())
+
+
+@pytest.mark.parametrize("name", KINDS)
+@pytest.mark.parametrize("graph", [True, False])
+def test_step_matches_modular_path_bitwise(xr, name, graph):
+    b = orc.synth_batch(3000, 16, 60, dim=384, seed=3)
+    emb = xr.models.ItemEmbeddings(torch.from_numpy(b["table"]), add_padding_row=False).cuda()
+    loss_fn = getattr(xr, name)(xr.LossConfig())
+    want_loss, want_grad, m_a, m = modular(xr, emb, loss_fn, b, torch.bfloat16)
+    step = xr.PoolLossStep(emb, loss_fn, 16, 60, use_graph=graph)
+    loss, dtok = run_step(step, b, torch.bfloat16)
+    torch.cuda.synchronize()
+    assert step.row_counts() == (m_a, m)
+    assert torch.equal(loss, want_loss), (float(loss), float(want_loss))
+    assert torch.equal(dtok.reshape(want_grad.shape), want_grad)
+
+
+@pytest.mark.parametrize("cfg_kw", [dict(mask_false_negatives=False), dict(scale=20.0, margin=0.2),
+                                    dict(mask_false_negatives=False, scale=5.0)])
+def test_step_config_variants(xr, cfg_kw):
+    b = orc.synth_batch(2000, 8, 100, dim=384, seed=5)
+    emb = xr.models.ItemEmbeddings(torch.from_numpy(b["table"]), add_padding_row=False).cuda()
+    for name in ("InfoNCELoss", "PairwiseLogisticLoss"):
+        loss_fn = getattr(xr, name)(xr.LossConfig(**cfg_kw))
+        want_loss, want_grad, _, _ = modular(xr, emb, loss_fn, b, torch.bfloat16)
+        loss, dtok = run_step(xr.PoolLossStep(emb, loss_fn, 8, 100), b, torch.bfloat16)
+        assert torch.equal(loss, want_loss)
+        assert torch.equal(dtok.reshape(want_grad.shape), want_grad)
+
+
+def test_step_reuse_with_shrinking_batches(xr):
+    """One step object, consecutive batches with fewer and fewer valid rows: rows left over from
+    an earlier, larger batch must never leak into a later result (zero fill of the last tile)."""
+    table = orc.synth_batch(1500, 1, 1, seed=0)["table"]
+    emb = xr.models.ItemEmbeddings(torch.from_numpy(table), add_padding_row=False).cuda()
+    loss_fn = xr.InfoNCELoss(xr.LossConfig())
+    step = xr.PoolLossStep(emb, loss_fn, 12, 70)
+    for seed, frac in ((1, 0.0), (2, 0.5), (3, 0.9), (4, 0.2)):
+        b = orc.synth_batch(1500, 12, 70, dim=384, seed=seed, pos_pad_frac=frac, table=table)
+        if seed == 3:   # also shorten the histories a lot
+            b["history_item_idx"][:, 9:] = 0
+        want_loss, want_grad, m_a, m = modular(xr, emb, loss_fn, b, torch.bfloat16)
+        loss, dtok = run_step(step, b, torch.bfloat16)
+        torch.cuda.synchronize()
+        assert step.row_counts() == (m_a, m)
+        assert torch.equal(loss, want_loss)
+        assert torch.equal(dtok.reshape(want_grad.shape), want_grad)
+        assert bool(torch.isfinite(dtok.float()).all())
+
+
+def test_step_empty_batch(xr):
+    b = orc.synth_batch(500, 4, 20, dim=384, seed=9)
+    b["pos_item_idx"][:] = 0          # no position has a positive: M = 0
+    emb = xr.models.ItemEmbeddings(torch.from_numpy(b["table"]), add_padding_row=False).cuda()
+    step = xr.PoolLossStep(emb, xr.InfoNCELoss(xr.LossConfig()), 4, 20)
+    loss, dtok = run_step(step, b, torch.bfloat16)
+    torch.cuda.synchronize()
+    assert step.row_counts()[1] == 0
+    assert float(loss) == 0.0 and not bool(dtok.any())
+
+
+def test_step_fp32_tokens_and_oracle(xr):
+    """fp32 encoder output: operands rounded to bf16 inside the gather; loss and gradient within
+    the bf16 tolerance (2e-3) of the oracle run on bf16-rounded operands and bf16 logits."""
+    b = orc.synth_batch(800, 6, 40, dim=384, seed=11)
+    emb = xr.models.ItemEmbeddings(torch.from_numpy(b["table"]), add_padding_row=False).cuda()
+    loss_fn = xr.InfoNCELoss(xr.LossConfig())
+    step = xr.PoolLossStep(emb, loss_fn, 6, 40, token_dtype=torch.float32, logits_bf16=True)
+    loss, dtok = run_step(step, b, torch.float32)
+    want = orc.compute_embeds(b["table"], b["token_embeddings"], b["history_item_idx"],
+                              b["pos_item_idx"], b["neg_item_idx"], dense=False)
+    ref, dq, _, _ = orc.lean_loss("InfoNCELoss", orc.round_bf16(want["query_embed"]),
+                                  orc.round_bf16(want["pos_embed"]), orc.round_bf16(want["neg_embed"]),
+                                  orc.Config(), with_grad=True, logits_dtype="bf16")
+    assert abs(float(loss) - ref) <= 2e-3 * abs(ref)
+    got = dtok.reshape(-1, 384).float().cpu().numpy()
+    mask = (b["history_item_idx"].reshape(-1) != 0) & (b["pos_item_idx"].reshape(-1) != 0)
+    assert not got[~mask].any()
+    err = np.abs(got[mask] - dq).max()
+    assert err <= 2e-3 * np.abs(dq).max(), err
+
+
+def test_step_rejects_what_it_does_not_serve(xr):
+    b = orc.synth_batch(100, 2, 8, dim=384, seed=1)
+    emb = xr.models.ItemEmbeddings(torch.from_numpy(b["table"]), add_padding_row=False).cuda()
+    with pytest.raises(NotImplementedError):
+        xr.PoolLossStep(emb, xr.AlignmentContrastiveLoss(xr.LossConfig()), 2, 8)
+    with pytest.raises(NotImplementedError):
+        xr.PoolLossStep(emb, xr.InfoNCELoss(xr.LossConfig(num_hard_negatives=5)), 2, 8)
+    with pytest.raises(xr._native.NativeError):
+        xr.PoolLossStep(xr.models.ItemEmbeddings(torch.from_numpy(b["table"]), add_padding_row=False),
+                        xr.InfoNCELoss(xr.LossConfig()), 2, 8)

@@ -62,7 +62,14 @@ constexpr int KIND_GMAX = 101;      // retrieval: max score of every 16-column g
 constexpr int NSCAL = 4;
 }  // namespace fk
 
+// shape + plan of one launch when they are only known on the device (xr_pool_step: the row counts
+// come out of the compaction kernel; nothing is read back to the host)
+struct FusedDyn {
+  int m, cn, nt_count, spl, tiles_per_split, n_items, rb_count, pad;
+};
+
 struct FusedParams {
+  const FusedDyn* dyn;   // nullable: overrides the seven fields below
   int m, cn, nt_count, spl, tiles_per_split, n_items;
   int mask_fn, logits_bf16, with_grad;
   float scale, margin;
@@ -192,6 +199,13 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool diag = (KIND == KIND_DIAG);
+  // shape and plan: launch constants, or read from device memory (sync-free step)
+  FusedDyn sh{p.m, p.cn, p.nt_count, p.spl, p.tiles_per_split, p.n_items, p.rb_count, 0};
+  if (p.dyn) {
+    const int4 a = __ldg(reinterpret_cast<const int4*>(p.dyn));
+    const int4 b = __ldg(reinterpret_cast<const int4*>(p.dyn) + 1);
+    sh = FusedDyn{a.x, a.y, a.z, a.w, b.x, b.y, b.z, 0};
+  }
   const bool grad = !diag && KIND != KIND_GMAX && p.with_grad;
   // S buffers: ONE with the gradient pass (the other 64 columns hold the W double buffer), two without
   const int nsb_shift = grad ? 0 : 1;
@@ -243,15 +257,15 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
     } else if (KIND == KIND_GMAX) {
       // row block fastest: CTAs that share a catalog range run side by side, so the second
       // query block finds the catalog tiles in L2 instead of re-reading HBM
-      rb = item % p.rb_count;
-      const int sp = item / p.rb_count;
-      t0 = sp * p.tiles_per_split;
-      t1 = min(p.nt_count, t0 + p.tiles_per_split);
+      rb = item % sh.rb_count;
+      const int sp = item / sh.rb_count;
+      t0 = sp * sh.tiles_per_split;
+      t1 = min(sh.nt_count, t0 + sh.tiles_per_split);
     } else {
-      rb = item / p.spl;
-      const int sp = item - rb * p.spl;
-      t0 = sp * p.tiles_per_split;
-      t1 = min(p.nt_count, t0 + p.tiles_per_split);
+      rb = item / sh.spl;
+      const int sp = item - rb * sh.spl;
+      t0 = sp * sh.tiles_per_split;
+      t1 = min(sh.nt_count, t0 + sh.tiles_per_split);
     }
   };
 
@@ -259,7 +273,7 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
     // ================================ TMA producer ================================
     // the whole warp walks the loop (warp-uniform control flow); one elected lane issues
     uint32_t g = 0, it = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < sh.n_items; item += gridDim.x, ++it) {
       int rb, t0, t1;
       item_tiles(item, rb, t0, t1);
       mbar_wait<STATS>(bar_q_empty, (it & 1) ^ 1, p.hang_flag, 1);
@@ -301,7 +315,7 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
     const uint64_t q_desc0 = umma_desc_sw128(q_smem, 16, 1024);
     const uint64_t ring_k_desc0 = umma_desc_sw128(ring, 16, 1024);
     uint32_t g = 0, tt = 0, it = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < sh.n_items; item += gridDim.x, ++it) {
       int rb, t0, t1;
       item_tiles(item, rb, t0, t1);
       const int T = t1 - t0;
@@ -352,7 +366,7 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
       // MN-major view of a pair: two 64-column atoms SUB_BYTES apart, 8-row groups of 1 KB
       const uint64_t ring_mn_desc0 = umma_desc_sw128(ring, SUB_BYTES, 1024);
       uint32_t g = 0, tt = 0, it = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      for (int item = blockIdx.x; item < sh.n_items; item += gridDim.x, ++it) {
         int rb, t0, t1;
         item_tiles(item, rb, t0, t1);
         const int T = t1 - t0;
@@ -396,12 +410,12 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
     const bool round_scaled = RBF && p.scale != 1.0f;
     const float scale2 = p.scale * kLog2e;
     uint32_t tt = 0, it = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < sh.n_items; item += gridDim.x, ++it) {
       int rb, t0, t1;
       item_tiles(item, rb, t0, t1);
       const int T = t1 - t0;
       const int row = rb * BM + r_local;
-      const bool row_ok = row < p.m;
+      const bool row_ok = row < sh.m;
       float t = 0.f, tm = 0.f, zref2 = 0.f, t_eff = 0.f;
       if (!diag && KIND != KIND_GMAX && row_ok) {
         t = p.t[row];
@@ -448,14 +462,14 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
               if (c == j) diag_val = __uint_as_float(v[j]);
           }
         } else if (KIND == KIND_GMAX) {
-          const int ncols = p.cn - rot_tile(t0, T, rb, tl) * BN - cg * 16;
+          const int ncols = sh.cn - rot_tile(t0, T, rb, tl) * BN - cg * 16;
           float mx = -CUDART_INF_F;
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             if (j < ncols) mx = fmaxf(mx, __uint_as_float(v[j]));
           if (row_ok) p.gmax[(long long)row * p.gmax_ld + (long long)rot_tile(t0, T, rb, tl) * CG + cg] = mx;
         } else {
-          const int ncols = p.cn - rot_tile(t0, T, rb, tl) * BN - cg * 16;   // valid candidates in this group
+          const int ncols = sh.cn - rot_tile(t0, T, rb, tl) * BN - cg * 16;   // valid candidates in this group
           uint32_t pk[8];
           if (ABL && (p.ablate & 2)) {
 #pragma unroll
@@ -537,8 +551,12 @@ fused_finalize_kernel(const float* __restrict__ part_o, const float* __restrict_
                       const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ pos,
                       const float* __restrict__ q_inv, int m, int spl, int kind, int logits_bf16,
                       float scale, float margin, float grad_scale, float* __restrict__ dq,
-                      float* __restrict__ row_loss) {
+                      float* __restrict__ row_loss, const FusedDyn* __restrict__ dyn) {
   using namespace fk;
+  if (dyn) {
+    m = dyn->m;
+    spl = dyn->spl;
+  }
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -629,8 +647,9 @@ fused_finalize_kernel(const float* __restrict__ part_o, const float* __restrict_
 // single block, fixed order: loss = sum_i row_loss[i]   (double accumulation)
 __global__ void __launch_bounds__(1024)
 sum_rows_kernel(const float* __restrict__ row_loss, int64_t m, double* __restrict__ out,
-                float* __restrict__ out_f32) {
+                float* __restrict__ out_f32, const FusedDyn* __restrict__ dyn) {
   __shared__ double s[32];
+  if (dyn) m = dyn->m;
   double acc = 0.0;
   for (int64_t i = threadIdx.x; i < m; i += blockDim.x) acc += (double)row_loss[i];
   acc = warp_sum(acc);
@@ -647,7 +666,8 @@ sum_rows_kernel(const float* __restrict__ row_loss, int64_t m, double* __restric
 // reference maximum when the false-negative mask is off (losses.py:283-287): by Cauchy-Schwarz
 // |s * q.n| <= |s| * ||q|| * max_j ||n_j||, and the target itself is in the set.
 __global__ void negnorm_max_kernel(const __nv_bfloat16* __restrict__ neg, int64_t cn,
-                                   unsigned* __restrict__ out_bits) {
+                                   unsigned* __restrict__ out_bits, const FusedDyn* __restrict__ dyn) {
+  if (dyn) cn = dyn->cn;
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -665,7 +685,9 @@ __global__ void negnorm_max_kernel(const __nv_bfloat16* __restrict__ neg, int64_
 }
 __global__ void zref_bound_kernel(const __nv_bfloat16* __restrict__ q, const float* __restrict__ t,
                                   const unsigned* __restrict__ maxnorm_bits, int64_t m, float scale,
-                                  int logits_bf16, float* __restrict__ zref) {
+                                  int logits_bf16, float* __restrict__ zref,
+                                  const FusedDyn* __restrict__ dyn) {
+  if (dyn) m = dyn->m;
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -725,22 +747,34 @@ int make_tmap_bf16_rows(CUtensorMap* out, const void* base, int64_t rows, int64_
 struct FusedPlan {
   int rb, nt, spl, tps, n_items;
 };
-static FusedPlan make_plan(int64_t m, int64_t cn, int n_sm) {
+// work items = (128-row block, split of the candidate tiles).  Chooses the split that minimises
+// (waves x (tiles per item + per-item overhead)) so the persistent grid of n_sm CTAs stays
+// balanced for any M, among the splits with at most max(4 n_sm, rb) items (bounds the partial
+// buffers).  Integer arithmetic only: the SAME function runs on the host (xr_fused_pool_loss) and
+// on the device (xr_pool_step), so both paths fold their partial sums in the same order.
+__host__ __device__ inline int fused_item_cap(int n_sm) { return 4 * n_sm; }
+__host__ __device__ inline FusedPlan make_plan(long long m, long long cn, int n_sm) {
   FusedPlan pl;
   pl.rb = (int)((m + fk::BM - 1) / fk::BM);
   pl.nt = (int)((cn + fk::BN - 1) / fk::BN);
-  // choose the split of the candidate tiles that minimises (waves x tiles per item + per-item
-  // overhead), so the persistent grid of n_sm CTAs stays balanced for any M
-  double best = 1e30;
+  if (pl.rb <= 0 || pl.nt <= 0) {
+    pl.rb = pl.rb > 0 ? pl.rb : 0;
+    pl.nt = pl.nt > 0 ? pl.nt : 0;
+    pl.spl = 1; pl.tps = pl.nt; pl.n_items = 0;
+    return pl;
+  }
+  const long long cap = fused_item_cap(n_sm) > pl.rb ? fused_item_cap(n_sm) : pl.rb;
+  long long best = -1;
   int best_spl = 1;
   const int max_spl = pl.nt < 64 ? pl.nt : 64;
   for (int s = 1; s <= max_spl; ++s) {
     const int tps = (pl.nt + s - 1) / s;
     const int s_eff = (pl.nt + tps - 1) / tps;
-    const int64_t items = (int64_t)pl.rb * s_eff;
-    const int64_t waves = (items + n_sm - 1) / n_sm;
-    const double cost = (double)waves * (tps + 3.0);
-    if (cost < best - 1e-9) {
+    const long long items = (long long)pl.rb * s_eff;
+    if (items > cap && s_eff > 1) continue;
+    const long long waves = (items + n_sm - 1) / n_sm;
+    const long long cost = waves * (tps + 3);
+    if (best < 0 || cost < best) {
       best = cost;
       best_spl = s_eff;
     }
@@ -750,6 +784,21 @@ static FusedPlan make_plan(int64_t m, int64_t cn, int n_sm) {
   pl.spl = (pl.nt + pl.tps - 1) / pl.tps;
   pl.n_items = pl.rb * pl.spl;
   return pl;
+}
+// upper bound of make_plan(m, cn).n_items over all m <= m_max (any cn)
+static long long max_plan_items(long long m_max, int n_sm) {
+  const long long rb = (m_max + fk::BM - 1) / fk::BM;
+  return fused_item_cap(n_sm) > rb ? fused_item_cap(n_sm) : rb;
+}
+
+// device-side planning for the sync-free step: counts[0] = M_a (pool rows), counts[1] = M (rows)
+__global__ void fused_plan_kernel(const int64_t* __restrict__ counts, int n_sm,
+                                  FusedDyn* __restrict__ dyn_main, FusedDyn* __restrict__ dyn_diag) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const long long cn = counts[0], m = counts[1];
+  const FusedPlan pl = make_plan(m, cn, n_sm);
+  *dyn_main = FusedDyn{(int)m, (int)cn, pl.nt, pl.spl, pl.tps, pl.n_items, pl.rb, 0};
+  *dyn_diag = FusedDyn{(int)m, (int)m, 0, 1, 2, pl.rb, pl.rb, 0};
 }
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
@@ -794,94 +843,82 @@ using namespace xr;
 
 extern "C" int xr_fused_available(void) { return 3; }  // bit 0: fused loss, bit 1: fused retrieval scoring
 
-extern "C" size_t xr_fused_pool_workspace_bytes(int64_t m, int64_t cn, int64_t dim) {
-  if (dim != fk::D || m <= 0 || cn <= 0) return 256;
-  const FusedPlan pl = make_plan(m, cn, sm_count());
-  size_t b = 0;
-  b += align256((size_t)m * 4);                                   // t
-  b += align256((size_t)m * 4);                                   // zref
-  b += align256((size_t)m * 4);                                   // row_loss
-  b += align256((size_t)pl.n_items * fk::CG * fk::BM * fk::NSCAL * 4);   // partial scalars
-  b += align256((size_t)pl.n_items * fk::BM * fk::D * 4);         // partial dQ
-  b += 256;                                                       // flags
-  return b;
+// workspace carve-up shared by xr_fused_pool_loss (exact shape) and xr_pool_step (bounds)
+struct FusedWs {
+  float *t, *zref, *rl, *part_s, *part_o;
+  int* flags;
+  FusedDyn* dyn;   // [2]: main, diag (used by the step only)
+  size_t bytes;
+};
+static FusedWs carve_fused_ws(void* workspace, long long m_max, long long max_items) {
+  FusedWs w;
+  uint8_t* p = (uint8_t*)workspace;
+  w.t = (float*)p;            p += align256((size_t)m_max * 4);
+  w.zref = (float*)p;         p += align256((size_t)m_max * 4);
+  w.rl = (float*)p;           p += align256((size_t)m_max * 4);
+  w.part_s = (float*)p;       p += align256((size_t)max_items * fk::CG * fk::BM * fk::NSCAL * 4);
+  w.part_o = (float*)p;       p += align256((size_t)max_items * fk::BM * fk::D * 4);
+  w.flags = (int*)p;          p += 256;
+  w.dyn = (FusedDyn*)p;       p += 256;
+  w.bytes = (size_t)(p - (uint8_t*)workspace);
+  return w;
 }
 
-extern "C" int xr_fused_pool_loss(const void* q, const void* pos, const void* neg, int64_t m,
-                                  int64_t cn, int64_t dim, int loss_kind,
-                                  const xr_loss_config* cfg, const float* q_inv_norm,
-                                  float grad_scale, float* dq, double* loss_out, float* row_loss,
-                                  void* workspace, size_t workspace_bytes, void* stream) {
-  XR_CHECK_ARG(q && pos && neg && cfg && loss_out && workspace, "xr_fused_pool_loss: null pointer");
-  XR_CHECK_ARG(dim == fk::D, "xr_fused_pool_loss: this build is specialised for dim = %d", fk::D);
-  XR_CHECK_ARG(m > 0 && cn > 0 && m < (1ll << 30) && cn < (1ll << 30),
-               "xr_fused_pool_loss: bad sizes");
-  XR_CHECK_ARG(cfg->num_hard_negatives == 0,
-               "xr_fused_pool_loss: hard-negative mining needs the materialised path");
-  XR_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)pos % 16 == 0) && ((uintptr_t)neg % 16 == 0),
-               "xr_fused_pool_loss: operands must be 16-byte aligned");
-  const bool cosine = loss_kind == XR_LOSS_CONTRASTIVE || loss_kind == XR_LOSS_ALIGNMENT_CONTRASTIVE;
-  XR_CHECK_ARG(loss_kind == XR_LOSS_INFONCE || loss_kind == XR_LOSS_NCE ||
-                   loss_kind == XR_LOSS_PAIRWISE_HINGE || loss_kind == XR_LOSS_PAIRWISE_LOGISTIC ||
-                   cosine,
-               "xr_fused_pool_loss: unsupported loss kind %d", loss_kind);
-  XR_CHECK_ARG(!cosine || !dq || q_inv_norm, "xr_fused_pool_loss: cosine kinds need q_inv_norm");
-  XR_CHECK_ARG(loss_kind != XR_LOSS_INFONCE || cfg->scale > 0.f,
-               "xr_fused_pool_loss: InfoNCE needs scale > 0");
-  XR_CHECK_ARG(workspace_bytes >= xr_fused_pool_workspace_bytes(m, cn, dim),
-               "xr_fused_pool_loss: workspace too small");
-  int dev = 0, major = 0;
-  XR_CUDA(cudaGetDevice(&dev));
-  XR_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
-  if (major != 10) {
-    set_error("xr_fused_pool_loss: needs an sm_100 device (tcgen05/TMEM), found sm_%d", major * 10);
-    return XR_E_UNSUPPORTED;
-  }
-  cudaStream_t s = as_stream(stream);
+extern "C" size_t xr_fused_pool_workspace_bytes(int64_t m, int64_t cn, int64_t dim) {
+  if (dim != fk::D || m <= 0 || cn <= 0) return 512;
+  const FusedPlan pl = make_plan(m, cn, sm_count());
+  return carve_fused_ws(nullptr, m, pl.n_items).bytes;
+}
+
+// The launch sequence of the fused loss: diagonal pass (target logits) -> [softmax reference
+// bound] -> fused contraction/loss/gradient -> finalize -> row sum.  With `dyn` == nullptr the
+// shape (m, cn) is exact; otherwise (m, cn) are upper bounds that size tensor maps and grids and
+// the kernels read the real shape and plan from ws.dyn (written by fused_plan_kernel earlier on
+// the same stream).
+static int fused_launch_all(const void* q, const void* pos, const void* neg, long long m,
+                            long long cn, int loss_kind, const xr_loss_config* cfg,
+                            const float* q_inv_norm, float grad_scale, float* dq, double* loss_out,
+                            float* row_loss, const FusedWs& ws, bool dynamic, cudaStream_t s) {
   const int n_sm = sm_count();
   const FusedPlan pl = make_plan(m, cn, n_sm);
-
-  uint8_t* w = (uint8_t*)workspace;
-  float* t_buf = (float*)w;            w += align256((size_t)m * 4);
-  float* zref_buf = (float*)w;         w += align256((size_t)m * 4);
-  float* rl_buf = (float*)w;           w += align256((size_t)m * 4);
-  float* part_s = (float*)w;           w += align256((size_t)pl.n_items * fk::CG * fk::BM * fk::NSCAL * 4);
-  float* part_o = (float*)w;           w += align256((size_t)pl.n_items * fk::BM * fk::D * 4);
-  int* flags = (int*)w;
-  XR_CUDA(cudaMemsetAsync(flags, 0, 256, s));
-
+  const FusedDyn* dyn_main = dynamic ? ws.dyn : nullptr;
+  const FusedDyn* dyn_diag = dynamic ? ws.dyn + 1 : nullptr;
+  XR_CUDA(cudaMemsetAsync(ws.flags, 0, 256, s));
 
   CUtensorMap tq, tp, tn;
   int rc;
-  if ((rc = make_tmap_bf16_rows(&tq, q, m, dim, dim, fk::BM))) return rc;
-  if ((rc = make_tmap_bf16_rows(&tp, pos, m, dim, dim, fk::BN))) return rc;
-  if ((rc = make_tmap_bf16_rows(&tn, neg, cn, dim, dim, fk::BN))) return rc;
+  if ((rc = make_tmap_bf16_rows(&tq, q, m, fk::D, fk::D, fk::BM))) return rc;
+  if ((rc = make_tmap_bf16_rows(&tp, pos, m, fk::D, fk::D, fk::BN))) return rc;
+  if ((rc = make_tmap_bf16_rows(&tn, neg, cn, fk::D, fk::D, fk::BN))) return rc;
 
   // pass 1: target logits q_i . pos_i from the diagonal of Q_blk . Pos_blk^T, through the SAME
   // MMA instruction sequence as every pool logit, so a pool entry equal to the row's positive
   // ties exactly and the strict '<' of losses.py:292 masks it (as one bmm does in the reference)
   FusedParams pd{};
+  pd.dyn = dyn_diag;
   pd.m = (int)m; pd.cn = (int)m; pd.nt_count = 0; pd.spl = 1; pd.tiles_per_split = 2;
-  pd.n_items = pl.rb; pd.t_out = t_buf; pd.hang_flag = flags;
+  pd.n_items = pl.rb; pd.t_out = ws.t; pd.hang_flag = ws.flags;
   if ((rc = launch_fused<fk::KIND_DIAG>(tq, tp, pd, pl.rb < n_sm ? pl.rb : n_sm, s))) return rc;
 
   const float* zref = nullptr;
   if (loss_kind == XR_LOSS_INFONCE && !cfg->mask_false_negatives) {
-    unsigned* nmax = (unsigned*)(flags + 8);
-    negnorm_max_kernel<<<n_sm * 4, 256, 0, s>>>((const __nv_bfloat16*)neg, cn, nmax);
+    unsigned* nmax = (unsigned*)(ws.flags + 8);
+    negnorm_max_kernel<<<n_sm * 4, 256, 0, s>>>((const __nv_bfloat16*)neg, cn, nmax, dyn_main);
     XR_LAUNCH_CHECK("negnorm_max");
-    zref_bound_kernel<<<n_sm * 4, 256, 0, s>>>((const __nv_bfloat16*)q, t_buf, nmax, m, cfg->scale,
-                                               cfg->logits_bf16, zref_buf);
+    zref_bound_kernel<<<n_sm * 4, 256, 0, s>>>((const __nv_bfloat16*)q, ws.t, nmax, m, cfg->scale,
+                                               cfg->logits_bf16, ws.zref, dyn_main);
     XR_LAUNCH_CHECK("zref_bound");
-    zref = zref_buf;
+    zref = ws.zref;
   }
 
   FusedParams p{};
+  p.dyn = dyn_main;
   p.m = (int)m; p.cn = (int)cn; p.nt_count = pl.nt; p.spl = pl.spl; p.tiles_per_split = pl.tps;
   p.n_items = pl.n_items; p.mask_fn = cfg->mask_false_negatives; p.logits_bf16 = cfg->logits_bf16;
   p.with_grad = dq != nullptr; p.scale = cfg->scale; p.margin = cfg->margin;
-  p.t = t_buf; p.zref = zref; p.part_o = part_o; p.part_s = part_s; p.hang_flag = flags;
-  const int grid = pl.n_items < n_sm ? pl.n_items : n_sm;
+  p.t = ws.t; p.zref = zref; p.part_o = ws.part_o; p.part_s = ws.part_s; p.hang_flag = ws.flags;
+  // dynamic: the item count is only known on the device; surplus CTAs find no item and exit
+  const int grid = dynamic ? n_sm : (pl.n_items < n_sm ? pl.n_items : n_sm);
   const bool prof = g_prof_on && g_prof_n < kProfRing;
   if (prof) cudaEventRecord(g_prof_ev[g_prof_n][0], s);
   switch (loss_kind) {
@@ -905,19 +942,218 @@ extern "C" int xr_fused_pool_loss(const void* q, const void* pos, const void* ne
   if (prof) cudaEventRecord(g_prof_ev[g_prof_n++][1], s);
   if (rc) return rc;
 
-  float* rl = row_loss ? row_loss : rl_buf;
+  float* rl = row_loss ? row_loss : ws.rl;
   fused_finalize_kernel<<<n_sm * 4, 256, 0, s>>>(
-      part_o, part_s, t_buf, zref, (const __nv_bfloat16*)q, (const __nv_bfloat16*)pos, q_inv_norm,
-      (int)m, pl.spl, loss_kind, cfg->logits_bf16, cfg->scale, cfg->margin, grad_scale, dq, rl);
+      ws.part_o, ws.part_s, ws.t, zref, (const __nv_bfloat16*)q, (const __nv_bfloat16*)pos,
+      q_inv_norm, (int)m, pl.spl, loss_kind, cfg->logits_bf16, cfg->scale, cfg->margin, grad_scale,
+      dq, rl, dyn_main);
   XR_LAUNCH_CHECK("fused_finalize");
   // loss_out[1] (if the caller left room) receives the fp32 copy the loss module returns
-  sum_rows_kernel<<<1, 1024, 0, s>>>(rl, m, loss_out, reinterpret_cast<float*>(loss_out + 1));
+  sum_rows_kernel<<<1, 1024, 0, s>>>(rl, m, loss_out, reinterpret_cast<float*>(loss_out + 1), dyn_main);
   XR_LAUNCH_CHECK("sum_rows");
   if (g_wait_stats || g_timeline) {
-    XR_CUDA(cudaMemcpyAsync(g_wait_host, flags + 16, sizeof(g_wait_host), cudaMemcpyDeviceToHost, s));
+    XR_CUDA(cudaMemcpyAsync(g_wait_host, ws.flags + 16, sizeof(g_wait_host), cudaMemcpyDeviceToHost, s));
     if (g_dbg_dev) XR_CUDA(cudaMemcpyAsync(g_dbg_host, g_dbg_dev, sizeof(g_dbg_host), cudaMemcpyDeviceToHost, s));
     XR_CUDA(cudaStreamSynchronize(s));
   }
+  return XR_OK;
+}
+
+static int check_fused_device(const char* who) {
+  int dev = 0, major = 0;
+  XR_CUDA(cudaGetDevice(&dev));
+  XR_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    set_error("%s: needs an sm_100 device (tcgen05/TMEM), found sm_%d", who, major * 10);
+    return XR_E_UNSUPPORTED;
+  }
+  return XR_OK;
+}
+
+static int check_fused_kind(const char* who, int loss_kind, const xr_loss_config* cfg) {
+  const bool cosine = loss_kind == XR_LOSS_CONTRASTIVE || loss_kind == XR_LOSS_ALIGNMENT_CONTRASTIVE;
+  XR_CHECK_ARG(cfg->num_hard_negatives == 0, "%s: hard-negative mining needs the materialised path", who);
+  XR_CHECK_ARG(loss_kind == XR_LOSS_INFONCE || loss_kind == XR_LOSS_NCE ||
+                   loss_kind == XR_LOSS_PAIRWISE_HINGE || loss_kind == XR_LOSS_PAIRWISE_LOGISTIC ||
+                   cosine,
+               "%s: unsupported loss kind %d", who, loss_kind);
+  XR_CHECK_ARG(loss_kind != XR_LOSS_INFONCE || cfg->scale > 0.f, "%s: InfoNCE needs scale > 0", who);
+  return XR_OK;
+}
+
+extern "C" int xr_fused_pool_loss(const void* q, const void* pos, const void* neg, int64_t m,
+                                  int64_t cn, int64_t dim, int loss_kind,
+                                  const xr_loss_config* cfg, const float* q_inv_norm,
+                                  float grad_scale, float* dq, double* loss_out, float* row_loss,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  XR_CHECK_ARG(q && pos && neg && cfg && loss_out && workspace, "xr_fused_pool_loss: null pointer");
+  XR_CHECK_ARG(dim == fk::D, "xr_fused_pool_loss: this build is specialised for dim = %d", fk::D);
+  XR_CHECK_ARG(m > 0 && cn > 0 && m < (1ll << 30) && cn < (1ll << 30),
+               "xr_fused_pool_loss: bad sizes");
+  XR_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)pos % 16 == 0) && ((uintptr_t)neg % 16 == 0),
+               "xr_fused_pool_loss: operands must be 16-byte aligned");
+  int rc;
+  if ((rc = check_fused_kind("xr_fused_pool_loss", loss_kind, cfg))) return rc;
+  const bool cosine = loss_kind == XR_LOSS_CONTRASTIVE || loss_kind == XR_LOSS_ALIGNMENT_CONTRASTIVE;
+  XR_CHECK_ARG(!cosine || !dq || q_inv_norm, "xr_fused_pool_loss: cosine kinds need q_inv_norm");
+  XR_CHECK_ARG(workspace_bytes >= xr_fused_pool_workspace_bytes(m, cn, dim),
+               "xr_fused_pool_loss: workspace too small");
+  if ((rc = check_fused_device("xr_fused_pool_loss"))) return rc;
+  const FusedPlan pl = make_plan(m, cn, sm_count());
+  const FusedWs ws = carve_fused_ws(workspace, m, pl.n_items);
+  return fused_launch_all(q, pos, neg, m, cn, loss_kind, cfg, q_inv_norm, grad_scale, dq, loss_out,
+                          row_loss, ws, false, as_stream(stream));
+}
+
+// ---- the whole scoring-and-loss step, sync-free -------------------------------------------------
+// compute_embeds (models.py:388-416) + EmbedLoss.forward (losses.py:128-155) + the backward to the
+// encoder output, for one SeqBatch of n_pos = B*L positions, without a single device->host copy:
+// the row counts stay on the device (fused_plan_kernel plans the tensor-core kernel there), every
+// buffer is sized by n_pos, so the call sequence is static and CUDA-graph capturable.
+__global__ void __launch_bounds__(256)
+step_gather_kernel(const char* __restrict__ tok, int tok_f32, const char* __restrict__ table,
+                   int64_t n_table_rows, const int64_t* __restrict__ pos_idx,
+                   const int64_t* __restrict__ neg_idx, const int64_t* __restrict__ sel_attn,
+                   const int64_t* __restrict__ sel_pos, const int64_t* __restrict__ counts,
+                   int64_t n_pos, char* __restrict__ q_out, char* __restrict__ pos_out,
+                   char* __restrict__ neg_out, int32_t* __restrict__ err_flag) {
+  // job 0: q = bf16(tok[sel_pos])   job 1: pos = table[pos_idx[sel_pos]]   job 2: neg = table[neg_idx[sel_attn]]
+  // rows [count, round_up(count, 128)) are zero-filled: the tensor maps cover n_pos rows, and a
+  // stale row inside the last tile would reach the gradient MMA as 0 x garbage
+  constexpr int VPR = fk::D * 2 / 16;   // 16-byte vectors per bf16 row
+  const int job = blockIdx.y;
+  const int64_t cnt = job == 2 ? counts[0] : counts[1];
+  int64_t padded = (cnt + 127) / 128 * 128;
+  if (padded > n_pos) padded = n_pos;
+  const int64_t* sel = job == 2 ? sel_attn : sel_pos;
+  const int64_t* idx = job == 1 ? pos_idx : neg_idx;
+  char* out = job == 0 ? q_out : (job == 1 ? pos_out : neg_out);
+  const int64_t total = padded * VPR;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += stride) {
+    const int64_t r = v / VPR;
+    const int c = (int)(v - r * VPR);
+    int4 o = make_int4(0, 0, 0, 0);
+    if (r < cnt) {
+      const int64_t position = sel[r];
+      if (job == 0) {
+        if (tok_f32) {
+          const int4 a = ld_stream16(reinterpret_cast<const int4*>(tok + position * (fk::D * 4)) + 2 * c);
+          const int4 b = ld_stream16(reinterpret_cast<const int4*>(tok + position * (fk::D * 4)) + 2 * c + 1);
+          const float* fa = reinterpret_cast<const float*>(&a);
+          const float* fb = reinterpret_cast<const float*>(&b);
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(fa[0], fa[1]), h1 = __floats2bfloat162_rn(fa[2], fa[3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(fb[0], fb[1]), h3 = __floats2bfloat162_rn(fb[2], fb[3]);
+          o.x = *reinterpret_cast<int*>(&h0); o.y = *reinterpret_cast<int*>(&h1);
+          o.z = *reinterpret_cast<int*>(&h2); o.w = *reinterpret_cast<int*>(&h3);
+        } else {
+          o = ld_stream16(reinterpret_cast<const int4*>(tok + position * (fk::D * 2)) + c);
+        }
+      } else {
+        const int64_t src = idx[position];
+        if (src < 0 || src >= n_table_rows) {
+          if (err_flag) *err_flag = 1;
+        } else {
+          o = __ldg(reinterpret_cast<const int4*>(table + src * (fk::D * 2)) + c);
+        }
+      }
+    }
+    st_stream16(reinterpret_cast<int4*>(out) + v, o);
+  }
+}
+
+struct StepWs {
+  int64_t *sel_attn, *sel_pos, *inv_pos;
+  uint8_t *attn, *pos_mask;
+  void* compact_ws;
+  __nv_bfloat16 *q, *pos, *neg;
+  float* dq;
+  int32_t* err;
+  FusedWs fused;
+  size_t bytes;
+};
+static StepWs carve_step_ws(void* workspace, long long n_pos) {
+  StepWs w;
+  uint8_t* p = (uint8_t*)workspace;
+  const size_t n = (size_t)n_pos;
+  w.sel_attn = (int64_t*)p;   p += align256(n * 8);
+  w.sel_pos = (int64_t*)p;    p += align256(n * 8);
+  w.inv_pos = (int64_t*)p;    p += align256(n * 8);
+  w.attn = p;                 p += align256(n);
+  w.pos_mask = p;             p += align256(n);
+  w.compact_ws = p;           p += align256(xr_compact_workspace_bytes(n_pos));
+  w.q = (__nv_bfloat16*)p;    p += align256(n * fk::D * 2);
+  w.pos = (__nv_bfloat16*)p;  p += align256(n * fk::D * 2);
+  w.neg = (__nv_bfloat16*)p;  p += align256(n * fk::D * 2);
+  w.dq = (float*)p;           p += align256(n * fk::D * 4);
+  w.err = (int32_t*)p;        p += 256;
+  const size_t off = (size_t)(p - (uint8_t*)workspace);
+  w.fused = carve_fused_ws(workspace ? p : nullptr, n_pos, max_plan_items(n_pos, sm_count()));
+  w.bytes = off + w.fused.bytes;
+  return w;
+}
+
+extern "C" size_t xr_pool_step_workspace_bytes(int64_t n_pos, int64_t dim) {
+  if (dim != fk::D || n_pos <= 0) return 512;
+  return carve_step_ws(nullptr, n_pos).bytes;
+}
+
+extern "C" int xr_pool_step(const int64_t* history_idx, const int64_t* pos_idx,
+                            const int64_t* neg_idx, int64_t n_pos, const void* tok, int tok_dtype,
+                            const void* table_bf16, const uint8_t* rownz, int64_t n_table_rows,
+                            int64_t dim, int loss_kind, const xr_loss_config* cfg, float grad_scale,
+                            void* dtok, int dtok_dtype, double* loss_out, int64_t* counts,
+                            int32_t* err_flag, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  XR_CHECK_ARG(history_idx && pos_idx && neg_idx && tok && table_bf16 && cfg && loss_out && counts &&
+                   workspace,
+               "xr_pool_step: null pointer");
+  XR_CHECK_ARG(dim == fk::D, "xr_pool_step: this build is specialised for dim = %d", fk::D);
+  XR_CHECK_ARG(n_pos > 0 && n_pos < (1ll << 30) && n_table_rows > 0, "xr_pool_step: bad sizes");
+  XR_CHECK_ARG((tok_dtype == XR_F32 || tok_dtype == XR_BF16) &&
+                   (!dtok || dtok_dtype == XR_F32 || dtok_dtype == XR_BF16),
+               "xr_pool_step: bad dtype");
+  XR_CHECK_ARG(((uintptr_t)tok % 16 == 0) && ((uintptr_t)table_bf16 % 16 == 0) &&
+                   ((uintptr_t)dtok % 16 == 0) && ((uintptr_t)workspace % 256 == 0),
+               "xr_pool_step: buffers must be 16-byte aligned (workspace 256)");
+  int rc;
+  if ((rc = check_fused_kind("xr_pool_step", loss_kind, cfg))) return rc;
+  XR_CHECK_ARG(loss_kind != XR_LOSS_CONTRASTIVE && loss_kind != XR_LOSS_ALIGNMENT_CONTRASTIVE,
+               "xr_pool_step: the cosine kinds go through compute_embeds + the loss modules");
+  XR_CHECK_ARG(workspace_bytes >= xr_pool_step_workspace_bytes(n_pos, dim),
+               "xr_pool_step: workspace too small");
+  if ((rc = check_fused_device("xr_pool_step"))) return rc;
+  cudaStream_t s = as_stream(stream);
+  const StepWs w = carve_step_ws(workspace, n_pos);
+  const int n_sm = sm_count();
+
+  // 1. positions -> row lists + counts (models.py:343, 390, 398, 404, 413-416), all on the device
+  if ((rc = xr_compact_positions(history_idx, pos_idx, rownz, n_table_rows, n_pos, w.attn, w.sel_attn,
+                                 w.sel_pos, w.pos_mask, w.inv_pos, counts, w.compact_ws, stream)))
+    return rc;
+  // 2. plan the tensor-core kernel for the real (M, M_a)
+  fused_plan_kernel<<<1, 32, 0, s>>>(counts, n_sm, w.fused.dyn, w.fused.dyn + 1);
+  XR_LAUNCH_CHECK("fused_plan");
+  // 3. the three gathers in one launch (models.py:392+415, :400+416, :406), bf16 operands
+  {
+    const int64_t per_job = (n_pos * (fk::D * 2 / 16) + 255) / 256;
+    int gx = (int)(per_job < (int64_t)n_sm * 4 ? per_job : (int64_t)n_sm * 4);
+    if (gx < 1) gx = 1;
+    step_gather_kernel<<<dim3(gx, 3), 256, 0, s>>>(
+        (const char*)tok, tok_dtype == XR_F32, (const char*)table_bf16, n_table_rows, pos_idx,
+        neg_idx, w.sel_attn, w.sel_pos, counts, n_pos, (char*)w.q, (char*)w.pos, (char*)w.neg,
+        err_flag);
+    XR_LAUNCH_CHECK("step_gather");
+  }
+  // 4. fused contraction + loss + dL/dquery (rows in compacted order)
+  if ((rc = fused_launch_all(w.q, w.pos, w.neg, n_pos, n_pos, loss_kind, cfg, nullptr, grad_scale,
+                             dtok ? w.dq : nullptr, loss_out, nullptr, w.fused, true, s)))
+    return rc;
+  // 5. back to the encoder-output layout: zero rows for unselected positions (autograd of
+  //    token_embeddings[mask][pos_mask], models.py:392, 415)
+  if (dtok)
+    if ((rc = xr_scatter_scaled(w.dq, w.inv_pos, nullptr, n_pos, dim, dtok, dtok_dtype, stream)))
+      return rc;
   return XR_OK;
 }
 

@@ -24,3 +24,10 @@ extern "C" int xr_score_groupmax(const void*, int64_t, const void*, int64_t, int
 }
 extern "C" int xr_fused_wait_stats(int, unsigned long long*) { return XR_E_UNSUPPORTED; }
 extern "C" int xr_fused_timeline(long long*) { return XR_E_UNSUPPORTED; }
+extern "C" size_t xr_pool_step_workspace_bytes(int64_t, int64_t) { return 0; }
+extern "C" int xr_pool_step(const int64_t*, const int64_t*, const int64_t*, int64_t, const void*, int,
+                            const void*, const uint8_t*, int64_t, int64_t, int, const xr_loss_config*,
+                            float, void*, int, double*, int64_t*, int32_t*, void*, size_t, void*) {
+  xr::set_error("xr_pool_step: tcgen05 kernels not compiled into this build");
+  return XR_E_UNSUPPORTED;
+}

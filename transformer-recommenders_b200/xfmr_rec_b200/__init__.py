@@ -6,11 +6,12 @@ yxtay/transformer-recommenders behind the reference's own Python interfaces.
     index    exact full-catalog search with the LanceIndex.search surface (index.py:214-255)
     metrics  compute_retrieval_metrics of xfmr_rec/metrics.py:17-79 (+ batched device version)
     dist     catalog sharding + NCCL all-gather merge, data-parallel loss reduction
+    step     the whole scoring-and-loss train step as one sync-free, CUDA-graph-replayed call
     ops      tensor-level wrappers over the C ABI (include/xfmr_b200.h)
 """
 
 from . import _native, ops  # noqa: F401
-from . import dist, index, losses, metrics, models, params  # noqa: F401
+from . import dist, index, losses, metrics, models, params, step  # noqa: F401
 from .losses import (  # noqa: F401
     LOSS_CLASSES,
     AlignmentContrastiveLoss,
@@ -27,5 +28,7 @@ from .losses import (  # noqa: F401
     PoolCandidates,
     SampledCandidates,
 )
+
+from .step import PoolLossStep  # noqa: F401,E402
 
 __version__ = "0.1.0"

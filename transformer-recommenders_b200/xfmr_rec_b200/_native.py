@@ -69,6 +69,9 @@ PROTOTYPES = {
     "xr_fused_profile": (_int, [_int]),
     "xr_fused_profile_read": (_int, [C.POINTER(C.c_float), _int]),
     "xr_fused_pool_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "xr_pool_step_workspace_bytes": (_sz, [_i64, _i64]),
+    "xr_pool_step": (_int, [_p, _p, _p, _i64, _p, _int, _p, _p, _i64, _i64, _int, _cfgp, C.c_float, _p,
+                            _int, _p, _p, _p, _p, _sz, _p]),
     "xr_fused_pool_loss": (_int, [_p, _p, _p, _i64, _i64, _i64, _int, _cfgp, _p, _f, _p, _p, _p, _p, _sz, _p]),
     "xr_topk_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "xr_topk": (_int, [_p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _sz, _p]),
