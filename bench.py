@@ -324,7 +324,7 @@ def main():
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
                 "note": "pinned host inputs copied every step (next batch's copy overlaps the "
                         "current batch's kernels), loss read back every step"},
-        "gpu_launches": 10 * args.steps,
+        "gpu_launches": 9 * args.steps,   # xr_pool_step: compaction x3, plan, gather, diagonal, fused, finalize, row sum
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "fused_pool_kernel<InfoNCE> (tcgen05)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",

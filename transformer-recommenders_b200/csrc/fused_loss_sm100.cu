@@ -551,22 +551,48 @@ fused_finalize_kernel(const float* __restrict__ part_o, const float* __restrict_
                       const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ pos,
                       const float* __restrict__ q_inv, int m, int spl, int kind, int logits_bf16,
                       float scale, float margin, float grad_scale, float* __restrict__ dq,
-                      float* __restrict__ row_loss, const FusedDyn* __restrict__ dyn) {
+                      float* __restrict__ row_loss, const FusedDyn* __restrict__ dyn,
+                      const int64_t* __restrict__ inv_pos, int64_t n_pos, void* __restrict__ dtok,
+                      int dtok_bf16) {
   using namespace fk;
   if (dyn) {
     m = dyn->m;
     spl = dyn->spl;
   }
+  // scatter mode (xr_pool_step): walk the B*L POSITIONS; position p holds row inv_pos[p] of the
+  // compacted order or none (zero gradient row) -- the autograd of token_embeddings[mask][pos_mask]
+  // (models.py:392, 415) folded into this kernel, in the encoder output's own layout and dtype
+  const bool scatter = dtok != nullptr;
+  const int64_t n_iter = scatter ? n_pos : (int64_t)m;
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const bool cosine = kind == XR_LOSS_CONTRASTIVE || kind == XR_LOSS_ALIGNMENT_CONTRASTIVE;
-  for (int64_t i = warp; i < m; i += nwarps) {
+  // each lane owns the column PAIRS {64 c + 2 lane, +1}: 8-byte partial loads, 4-byte bf16x2 /
+  // 8-byte fp32 stores -> full 128 / 256-byte warp transactions
+  constexpr int NP = D / 64;
+  for (int64_t it = warp; it < n_iter; it += nwarps) {
+    int64_t i = it;
+    if (scatter) {
+      i = inv_pos[it];
+      if (i < 0) {
+        if (dtok_bf16) {
+          uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(dtok) + it * D);
+#pragma unroll
+          for (int c = 0; c < NP; ++c) dst[c * 32 + lane] = 0u;
+        } else {
+          float2* dst = reinterpret_cast<float2*>(reinterpret_cast<float*>(dtok) + it * D);
+#pragma unroll
+          for (int c = 0; c < NP; ++c) dst[c * 32 + lane] = make_float2(0.f, 0.f);
+        }
+        continue;
+      }
+    }
     const int rb = (int)(i / BM), rl = (int)(i % BM);
     float cnt = 0.f, sum_a = 0.f, sum_w = 0.f;
-    float o[D / 32];
+    float2 o[NP];
 #pragma unroll
-    for (int c = 0; c < D / 32; ++c) o[c] = 0.f;
+    for (int c = 0; c < NP; ++c) o[c] = make_float2(0.f, 0.f);
     for (int sp = 0; sp < spl; ++sp) {   // fixed order: deterministic
       const size_t item = (size_t)rb * spl + sp;
 #pragma unroll
@@ -574,10 +600,14 @@ fused_finalize_kernel(const float* __restrict__ part_o, const float* __restrict_
         const float4 s = *reinterpret_cast<const float4*>(part_s + ((item * CG + cg) * BM + rl) * NSCAL);
         cnt += s.x; sum_a += s.y; sum_w += s.z;
       }
-      if (dq) {
-        const float* src = part_o + (item * BM + rl) * D;
+      if (dq || scatter) {
+        const float2* src = reinterpret_cast<const float2*>(part_o + (item * BM + rl) * D);
 #pragma unroll
-        for (int c = 0; c < D / 32; ++c) o[c] += src[c * 32 + lane];
+        for (int c = 0; c < NP; ++c) {
+          const float2 v = src[c * 32 + lane];
+          o[c].x += v.x;
+          o[c].y += v.y;
+        }
       }
     }
     float t = t_raw[i];
@@ -621,25 +651,46 @@ fused_finalize_kernel(const float* __restrict__ part_o, const float* __restrict_
         break;
     }
     if (lane == 0 && row_loss) row_loss[i] = loss;
-    if (dq) {
-      float g[D / 32], dot = 0.f;
+    if (dq || scatter) {
+      float2 g[NP];
+      float dot = 0.f;
+      const __nv_bfloat162* pos2 = reinterpret_cast<const __nv_bfloat162*>(pos + i * D);
+      const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(q + i * D);
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
-        const int d = c * 32 + lane;
-        g[c] = co * o[c] + cp * __bfloat162float(pos[i * D + d]);
-        if (cosine) dot = fmaf(g[c], __bfloat162float(q[i * D + d]), dot);
+      for (int c = 0; c < NP; ++c) {
+        const float2 pv = __bfloat1622float2(pos2[c * 32 + lane]);
+        g[c].x = co * o[c].x + cp * pv.x;
+        g[c].y = co * o[c].y + cp * pv.y;
+        if (cosine) {
+          const float2 qv = __bfloat1622float2(q2[c * 32 + lane]);
+          dot = fmaf(g[c].x, qv.x, dot);
+          dot = fmaf(g[c].y, qv.y, dot);
+        }
       }
       if (cosine) {
         dot = warp_sum(dot);
         const float inv = q_inv[i];
 #pragma unroll
-        for (int c = 0; c < D / 32; ++c) {
-          const int d = c * 32 + lane;
-          g[c] = inv * (g[c] - dot * __bfloat162float(q[i * D + d]));
+        for (int c = 0; c < NP; ++c) {
+          const float2 qv = __bfloat1622float2(q2[c * 32 + lane]);
+          g[c].x = inv * (g[c].x - dot * qv.x);
+          g[c].y = inv * (g[c].y - dot * qv.y);
         }
       }
+      if (!scatter) {
+        float2* dst = reinterpret_cast<float2*>(dq + i * D);
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) dq[i * D + c * 32 + lane] = g[c] * grad_scale;
+        for (int c = 0; c < NP; ++c) dst[c * 32 + lane] = make_float2(g[c].x * grad_scale, g[c].y * grad_scale);
+      } else if (dtok_bf16) {
+        __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(dtok) + it * D);
+#pragma unroll
+        for (int c = 0; c < NP; ++c)
+          dst[c * 32 + lane] = __floats2bfloat162_rn(g[c].x * grad_scale, g[c].y * grad_scale);
+      } else {
+        float2* dst = reinterpret_cast<float2*>(reinterpret_cast<float*>(dtok) + it * D);
+#pragma unroll
+        for (int c = 0; c < NP; ++c) dst[c * 32 + lane] = make_float2(g[c].x * grad_scale, g[c].y * grad_scale);
+      }
     }
   }
 }
@@ -753,37 +804,48 @@ struct FusedPlan {
 // buffers).  Integer arithmetic only: the SAME function runs on the host (xr_fused_pool_loss) and
 // on the device (xr_pool_step), so both paths fold their partial sums in the same order.
 __host__ __device__ inline int fused_item_cap(int n_sm) { return 4 * n_sm; }
-__host__ __device__ inline FusedPlan make_plan(long long m, long long cn, int n_sm) {
+// cost of splitting the nt candidate tiles s ways (-1: not allowed); s_eff = splits actually used
+__host__ __device__ inline long long plan_cost(int rb, int nt, int s, int n_sm, int& s_eff) {
+  const int tps = (nt + s - 1) / s;
+  s_eff = (nt + tps - 1) / tps;
+  const long long cap = fused_item_cap(n_sm) > rb ? fused_item_cap(n_sm) : rb;
+  const long long items = (long long)rb * s_eff;
+  if (items > cap && s_eff > 1) return -1;
+  const long long waves = (items + n_sm - 1) / n_sm;
+  return waves * (tps + 3);
+}
+__host__ __device__ inline FusedPlan finish_plan(int rb, int nt, int best_spl) {
   FusedPlan pl;
-  pl.rb = (int)((m + fk::BM - 1) / fk::BM);
-  pl.nt = (int)((cn + fk::BN - 1) / fk::BN);
-  if (pl.rb <= 0 || pl.nt <= 0) {
-    pl.rb = pl.rb > 0 ? pl.rb : 0;
-    pl.nt = pl.nt > 0 ? pl.nt : 0;
+  pl.rb = rb; pl.nt = nt;
+  pl.spl = best_spl;
+  pl.tps = (nt + pl.spl - 1) / pl.spl;
+  pl.spl = (nt + pl.tps - 1) / pl.tps;
+  pl.n_items = rb * pl.spl;
+  return pl;
+}
+__host__ __device__ inline FusedPlan make_plan(long long m, long long cn, int n_sm) {
+  const int rb = (int)((m + fk::BM - 1) / fk::BM);
+  const int nt = (int)((cn + fk::BN - 1) / fk::BN);
+  if (rb <= 0 || nt <= 0) {
+    FusedPlan pl;
+    pl.rb = rb > 0 ? rb : 0;
+    pl.nt = nt > 0 ? nt : 0;
     pl.spl = 1; pl.tps = pl.nt; pl.n_items = 0;
     return pl;
   }
-  const long long cap = fused_item_cap(n_sm) > pl.rb ? fused_item_cap(n_sm) : pl.rb;
   long long best = -1;
   int best_spl = 1;
-  const int max_spl = pl.nt < 64 ? pl.nt : 64;
-  for (int s = 1; s <= max_spl; ++s) {
-    const int tps = (pl.nt + s - 1) / s;
-    const int s_eff = (pl.nt + tps - 1) / tps;
-    const long long items = (long long)pl.rb * s_eff;
-    if (items > cap && s_eff > 1) continue;
-    const long long waves = (items + n_sm - 1) / n_sm;
-    const long long cost = waves * (tps + 3);
+  const int max_spl = nt < 64 ? nt : 64;
+  for (int s = 1; s <= max_spl; ++s) {   // first minimum wins (smallest s)
+    int s_eff;
+    const long long cost = plan_cost(rb, nt, s, n_sm, s_eff);
+    if (cost < 0) continue;
     if (best < 0 || cost < best) {
       best = cost;
       best_spl = s_eff;
     }
   }
-  pl.spl = best_spl;
-  pl.tps = (pl.nt + pl.spl - 1) / pl.spl;
-  pl.spl = (pl.nt + pl.tps - 1) / pl.tps;
-  pl.n_items = pl.rb * pl.spl;
-  return pl;
+  return finish_plan(rb, nt, best_spl);
 }
 // upper bound of make_plan(m, cn).n_items over all m <= m_max (any cn)
 static long long max_plan_items(long long m_max, int n_sm) {
@@ -791,14 +853,49 @@ static long long max_plan_items(long long m_max, int n_sm) {
   return fused_item_cap(n_sm) > rb ? fused_item_cap(n_sm) : rb;
 }
 
-// device-side planning for the sync-free step: counts[0] = M_a (pool rows), counts[1] = M (rows)
-__global__ void fused_plan_kernel(const int64_t* __restrict__ counts, int n_sm,
-                                  FusedDyn* __restrict__ dyn_main, FusedDyn* __restrict__ dyn_diag) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const long long cn = counts[0], m = counts[1];
-  const FusedPlan pl = make_plan(m, cn, n_sm);
-  *dyn_main = FusedDyn{(int)m, (int)cn, pl.nt, pl.spl, pl.tps, pl.n_items, pl.rb, 0};
-  *dyn_diag = FusedDyn{(int)m, (int)m, 0, 1, 2, pl.rb, pl.rb, 0};
+// device-side planning for the sync-free step from the row counts the compaction left on the
+// device (M_a pool rows, M rows): 64 threads evaluate the 64 candidate splits in
+// parallel, thread 0 picks the first minimum exactly as the host loop does
+struct PlanHook {
+  int n_sm;
+  FusedDyn* dyn_main;
+  FusedDyn* dyn_diag;
+  __device__ void operator()(int m_a, int m) const {
+    __shared__ long long s_cost[64];
+    __shared__ int s_eff_sh[64];
+    const int rb = (m + fk::BM - 1) / fk::BM, nt = (m_a + fk::BN - 1) / fk::BN;
+    const int t = threadIdx.x;
+    if (t < 64) {
+      int s_eff = 1;
+      long long cost = -1;
+      if (rb > 0 && nt > 0 && t + 1 <= (nt < 64 ? nt : 64)) cost = plan_cost(rb, nt, t + 1, n_sm, s_eff);
+      s_cost[t] = cost;
+      s_eff_sh[t] = s_eff;
+    }
+    __syncthreads();
+    if (t == 0) {
+      FusedPlan pl;
+      if (rb <= 0 || nt <= 0) {
+        pl.rb = rb > 0 ? rb : 0; pl.nt = nt > 0 ? nt : 0; pl.spl = 1; pl.tps = pl.nt; pl.n_items = 0;
+      } else {
+        long long best = -1;
+        int best_spl = 1;
+        for (int i = 0; i < 64; ++i) {
+          if (s_cost[i] < 0) continue;
+          if (best < 0 || s_cost[i] < best) {
+            best = s_cost[i];
+            best_spl = s_eff_sh[i];
+          }
+        }
+        pl = finish_plan(rb, nt, best_spl);
+      }
+      *dyn_main = FusedDyn{m, m_a, pl.nt, pl.spl, pl.tps, pl.n_items, pl.rb, 0};
+      *dyn_diag = FusedDyn{m, m, 0, 1, 2, pl.rb, pl.rb, 0};
+    }
+  }
+};
+__global__ void fused_plan_kernel(const int64_t* __restrict__ counts, PlanHook hook) {
+  hook((int)counts[0], (int)counts[1]);
 }
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
@@ -875,10 +972,17 @@ extern "C" size_t xr_fused_pool_workspace_bytes(int64_t m, int64_t cn, int64_t d
 // shape (m, cn) is exact; otherwise (m, cn) are upper bounds that size tensor maps and grids and
 // the kernels read the real shape and plan from ws.dyn (written by fused_plan_kernel earlier on
 // the same stream).
+struct StepScatter {   // xr_pool_step: write dL/dtok straight into the (n_pos, D) layout
+  const int64_t* inv_pos;
+  int64_t n_pos;
+  void* dtok;
+  int dtok_bf16;
+};
 static int fused_launch_all(const void* q, const void* pos, const void* neg, long long m,
                             long long cn, int loss_kind, const xr_loss_config* cfg,
                             const float* q_inv_norm, float grad_scale, float* dq, double* loss_out,
-                            float* row_loss, const FusedWs& ws, bool dynamic, cudaStream_t s) {
+                            float* row_loss, const FusedWs& ws, bool dynamic, cudaStream_t s,
+                            const StepScatter* sc = nullptr) {
   const int n_sm = sm_count();
   const FusedPlan pl = make_plan(m, cn, n_sm);
   const FusedDyn* dyn_main = dynamic ? ws.dyn : nullptr;
@@ -915,7 +1019,7 @@ static int fused_launch_all(const void* q, const void* pos, const void* neg, lon
   p.dyn = dyn_main;
   p.m = (int)m; p.cn = (int)cn; p.nt_count = pl.nt; p.spl = pl.spl; p.tiles_per_split = pl.tps;
   p.n_items = pl.n_items; p.mask_fn = cfg->mask_false_negatives; p.logits_bf16 = cfg->logits_bf16;
-  p.with_grad = dq != nullptr; p.scale = cfg->scale; p.margin = cfg->margin;
+  p.with_grad = dq != nullptr || (sc && sc->dtok); p.scale = cfg->scale; p.margin = cfg->margin;
   p.t = ws.t; p.zref = zref; p.part_o = ws.part_o; p.part_s = ws.part_s; p.hang_flag = ws.flags;
   // dynamic: the item count is only known on the device; surplus CTAs find no item and exit
   const int grid = dynamic ? n_sm : (pl.n_items < n_sm ? pl.n_items : n_sm);
@@ -946,7 +1050,8 @@ static int fused_launch_all(const void* q, const void* pos, const void* neg, lon
   fused_finalize_kernel<<<n_sm * 4, 256, 0, s>>>(
       ws.part_o, ws.part_s, ws.t, zref, (const __nv_bfloat16*)q, (const __nv_bfloat16*)pos,
       q_inv_norm, (int)m, pl.spl, loss_kind, cfg->logits_bf16, cfg->scale, cfg->margin, grad_scale,
-      dq, rl, dyn_main);
+      dq, rl, dyn_main, sc ? sc->inv_pos : nullptr, sc ? sc->n_pos : 0, sc ? sc->dtok : nullptr,
+      sc ? sc->dtok_bf16 : 0);
   XR_LAUNCH_CHECK("fused_finalize");
   // loss_out[1] (if the caller left room) receives the fp32 copy the loss module returns
   sum_rows_kernel<<<1, 1024, 0, s>>>(rl, m, loss_out, reinterpret_cast<float*>(loss_out + 1), dyn_main);
@@ -1067,7 +1172,6 @@ struct StepWs {
   uint8_t *attn, *pos_mask;
   void* compact_ws;
   __nv_bfloat16 *q, *pos, *neg;
-  float* dq;
   int32_t* err;
   FusedWs fused;
   size_t bytes;
@@ -1085,7 +1189,6 @@ static StepWs carve_step_ws(void* workspace, long long n_pos) {
   w.q = (__nv_bfloat16*)p;    p += align256(n * fk::D * 2);
   w.pos = (__nv_bfloat16*)p;  p += align256(n * fk::D * 2);
   w.neg = (__nv_bfloat16*)p;  p += align256(n * fk::D * 2);
-  w.dq = (float*)p;           p += align256(n * fk::D * 4);
   w.err = (int32_t*)p;        p += 256;
   const size_t off = (size_t)(p - (uint8_t*)workspace);
   w.fused = carve_fused_ws(workspace ? p : nullptr, n_pos, max_plan_items(n_pos, sm_count()));
@@ -1127,12 +1230,12 @@ extern "C" int xr_pool_step(const int64_t* history_idx, const int64_t* pos_idx,
   const StepWs w = carve_step_ws(workspace, n_pos);
   const int n_sm = sm_count();
 
-  // 1. positions -> row lists + counts (models.py:343, 390, 398, 404, 413-416), all on the device
+  // 1 + 2. positions -> row lists + counts (models.py:343, 390, 398, 404, 413-416), then the plan
+  //        of the tensor-core kernel for the real (M, M_a): 64 threads, all on the device
   if ((rc = xr_compact_positions(history_idx, pos_idx, rownz, n_table_rows, n_pos, w.attn, w.sel_attn,
                                  w.sel_pos, w.pos_mask, w.inv_pos, counts, w.compact_ws, stream)))
     return rc;
-  // 2. plan the tensor-core kernel for the real (M, M_a)
-  fused_plan_kernel<<<1, 32, 0, s>>>(counts, n_sm, w.fused.dyn, w.fused.dyn + 1);
+  fused_plan_kernel<<<1, 64, 0, s>>>(counts, PlanHook{n_sm, w.fused.dyn, w.fused.dyn + 1});
   XR_LAUNCH_CHECK("fused_plan");
   // 3. the three gathers in one launch (models.py:392+415, :400+416, :406), bf16 operands
   {
@@ -1145,15 +1248,13 @@ extern "C" int xr_pool_step(const int64_t* history_idx, const int64_t* pos_idx,
         err_flag);
     XR_LAUNCH_CHECK("step_gather");
   }
-  // 4. fused contraction + loss + dL/dquery (rows in compacted order)
-  if ((rc = fused_launch_all(w.q, w.pos, w.neg, n_pos, n_pos, loss_kind, cfg, nullptr, grad_scale,
-                             dtok ? w.dq : nullptr, loss_out, nullptr, w.fused, true, s)))
-    return rc;
-  // 5. back to the encoder-output layout: zero rows for unselected positions (autograd of
+  // 4. fused contraction + loss + dL/dtok: the finalize kernel writes the gradient in the encoder
+  //    output's layout (zero rows for unselected positions: autograd of
   //    token_embeddings[mask][pos_mask], models.py:392, 415)
-  if (dtok)
-    if ((rc = xr_scatter_scaled(w.dq, w.inv_pos, nullptr, n_pos, dim, dtok, dtok_dtype, stream)))
-      return rc;
+  const StepScatter sc{w.inv_pos, n_pos, dtok, dtok_dtype == XR_BF16};
+  if ((rc = fused_launch_all(w.q, w.pos, w.neg, n_pos, n_pos, loss_kind, cfg, nullptr, grad_scale,
+                             nullptr, loss_out, nullptr, w.fused, true, s, dtok ? &sc : nullptr)))
+    return rc;
   return XR_OK;
 }
 
