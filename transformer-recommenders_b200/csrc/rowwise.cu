@@ -140,6 +140,207 @@ row_dq_kernel(const float* __restrict__ g, int64_t ld, const T* __restrict__ qha
   }
 }
 
+// ---- fast path for the sampled candidates of BASELINE config 3 (D = 384) -------------------------
+// The table (67 MB bf16 / 134 MB fp32) mostly lives in L2; what bounds these kernels is how many
+// row reads are in flight.  Block per query row, warp per group of 4 candidates: every lane
+// issues its 16-byte vectors of all 4 rows before using any (8 loads in flight for bf16, 12 for
+// fp32), the query sits in registers, and the 4 dot products are reduced together (6 shuffles).
+constexpr int FD = 384;
+template <typename T>
+struct RowVec;   // 16-byte vector of a row -> floats
+template <>
+struct RowVec<__nv_bfloat16> {
+  static constexpr int E = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&o)[8]) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(p));
+    const uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      o[2 * k] = __uint_as_float(w[k] << 16);
+      o[2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
+    }
+  }
+};
+template <>
+struct RowVec<float> {
+  static constexpr int E = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&o)[4]) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(p));
+    o[0] = __int_as_float(v.x); o[1] = __int_as_float(v.y);
+    o[2] = __int_as_float(v.z); o[3] = __int_as_float(v.w);
+  }
+};
+
+// reduce 4 per-lane partials over the warp: lanes 0 / 8 / 16 / 24 end up with totals a / b / c / d
+__device__ __forceinline__ float warp_sum4(float a, float b, float c, float d, int lane) {
+  const bool hi16 = lane & 16, hi8 = lane & 8;
+  float p = (hi16 ? c : a) + __shfl_xor_sync(0xffffffffu, hi16 ? a : c, 16);
+  float q = (hi16 ? d : b) + __shfl_xor_sync(0xffffffffu, hi16 ? b : d, 16);
+  float r = (hi8 ? q : p) + __shfl_xor_sync(0xffffffffu, hi8 ? p : q, 8);
+  r += __shfl_xor_sync(0xffffffffu, r, 4);
+  r += __shfl_xor_sync(0xffffffffu, r, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(ROW_THREADS)
+sampled_logits384_kernel(const T* __restrict__ q, const T* __restrict__ table,
+                         const int64_t* __restrict__ cand_idx, int64_t n_table_rows, int64_t m,
+                         int64_t c, const float* __restrict__ q_inv,
+                         const float* __restrict__ table_inv, float* __restrict__ logits, int64_t ld) {
+  constexpr int E = RowVec<T>::E, VECS = FD / E, IT = (VECS + 31) / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = ROW_THREADS / 32;
+  for (int64_t i = blockIdx.x; i < m; i += gridDim.x) {
+    float qr[IT][E];
+#pragma unroll
+    for (int t = 0; t < IT; ++t) {
+      const int v = lane + 32 * t;
+      if (v < VECS) RowVec<T>::load(q + i * FD + v * E, qr[t]);
+      else
+#pragma unroll
+        for (int k = 0; k < E; ++k) qr[t][k] = 0.f;
+    }
+    const float qi = q_inv ? q_inv[i] : 1.f;
+    for (int64_t j0 = (int64_t)warp * 4; j0 < c; j0 += nwarp * 4) {
+      int64_t row[4];
+      bool valid[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t j = j0 + u;
+        row[u] = j < c ? cand_idx[i * c + j] : 0;
+        valid[u] = row[u] >= 0 && row[u] < n_table_rows;
+        if (!valid[u]) row[u] = 0;
+      }
+      float x[4][IT][E];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int t = 0; t < IT; ++t) {
+          const int v = lane + 32 * t;
+          if (v < VECS) RowVec<T>::load(table + row[u] * FD + v * E, x[u][t]);
+          else
+#pragma unroll
+            for (int k = 0; k < E; ++k) x[u][t][k] = 0.f;
+        }
+      float dot[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int t = 0; t < IT; ++t)
+#pragma unroll
+          for (int k = 0; k < E; ++k) dot[u] = fmaf(qr[t][k], x[u][t][k], dot[u]);
+      const float tot = warp_sum4(dot[0], dot[1], dot[2], dot[3], lane);
+      if ((lane & 7) == 0) {
+        const int u = lane >> 3;
+        const int64_t j = j0 + u;
+        int64_t r_sel = row[0];
+        bool v_sel = valid[0];
+#pragma unroll
+        for (int uu = 1; uu < 4; ++uu)   // static indexing keeps row[] / valid[] in registers
+          if (u == uu) {
+            r_sel = row[uu];
+            v_sel = valid[uu];
+          }
+        if (j < c) {
+          float scale = qi;
+          if (table_inv) scale *= table_inv[r_sel];
+          logits[i * ld + j] = v_sel ? tot * scale : CUDART_NAN_F;
+        }
+      }
+    }
+  }
+}
+
+// dq_i = sum_j g[i,j] * tinv(j) * table[idx[i,j]]  (+ cosine chain rule): warps split the
+// candidates (4 rows in flight each), lanes own fixed 16-byte column slices, partials are
+// folded across warps through shared memory in a fixed order (deterministic).
+template <typename T>
+__global__ void __launch_bounds__(ROW_THREADS)
+sampled_dq384_kernel(const float* __restrict__ g, int64_t ld, const T* __restrict__ q,
+                     const T* __restrict__ table, const int64_t* __restrict__ cand_idx,
+                     int64_t n_table_rows, int64_t m, int64_t c, const float* __restrict__ q_inv,
+                     const float* __restrict__ table_inv, int cosine, float* __restrict__ dq) {
+  constexpr int E = RowVec<T>::E, VECS = FD / E, IT = (VECS + 31) / 32;
+  constexpr int NW = ROW_THREADS / 32;
+  __shared__ float s_red[NW][FD];
+  __shared__ float s_part[NW];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t i = blockIdx.x; i < m; i += gridDim.x) {
+    float acc[IT][E];
+#pragma unroll
+    for (int t = 0; t < IT; ++t)
+#pragma unroll
+      for (int k = 0; k < E; ++k) acc[t][k] = 0.f;
+    for (int64_t j0 = (int64_t)warp * 4; j0 < c; j0 += NW * 4) {
+      float w[4];
+      int64_t row[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t j = j0 + u;
+        w[u] = j < c ? g[i * ld + j] : 0.f;
+        row[u] = (j < c && w[u] != 0.f) ? cand_idx[i * c + j] : -1;
+        if (row[u] < 0 || row[u] >= n_table_rows) {   // masked candidates: skip their bytes
+          w[u] = 0.f;
+          row[u] = -1;
+        } else if (table_inv) {
+          w[u] *= table_inv[row[u]];
+        }
+      }
+      if (w[0] == 0.f && w[1] == 0.f && w[2] == 0.f && w[3] == 0.f) continue;
+      float x[4][IT][E];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int t = 0; t < IT; ++t) {
+          const int v = lane + 32 * t;
+          if (v < VECS && row[u] >= 0) RowVec<T>::load(table + row[u] * FD + v * E, x[u][t]);
+          else
+#pragma unroll
+            for (int k = 0; k < E; ++k) x[u][t][k] = 0.f;
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)   // ascending j within the warp: fixed order
+#pragma unroll
+        for (int t = 0; t < IT; ++t)
+#pragma unroll
+          for (int k = 0; k < E; ++k) acc[t][k] = fmaf(w[u], x[u][t][k], acc[t][k]);
+    }
+#pragma unroll
+    for (int t = 0; t < IT; ++t) {
+      const int v = lane + 32 * t;
+      if (v < VECS)
+#pragma unroll
+        for (int k = 0; k < E; ++k) s_red[warp][v * E + k] = acc[t][k];
+    }
+    __syncthreads();
+    float dotgq = 0.f;
+    for (int d = threadIdx.x; d < FD; d += ROW_THREADS) {
+      float s = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < NW; ++w2) s += s_red[w2][d];   // fixed order
+      s_red[0][d] = s;
+      if (cosine) dotgq = fmaf(s, to_f32(q[i * FD + d]) * q_inv[i], dotgq);
+    }
+    if (cosine) {
+      dotgq = warp_sum(dotgq);
+      if (lane == 0) s_part[warp] = dotgq;
+    }
+    __syncthreads();
+    float s_dot = 0.f;
+    if (cosine) {
+#pragma unroll
+      for (int w2 = 0; w2 < NW; ++w2) s_dot += s_part[w2];
+    }
+    for (int d = threadIdx.x; d < FD; d += ROW_THREADS) {
+      float s = s_red[0][d];
+      if (cosine) s = q_inv[i] * (s - s_dot * to_f32(q[i * FD + d]) * q_inv[i]);
+      dq[i * FD + d] = s;
+    }
+    __syncthreads();
+  }
+}
+
 static inline int row_grid(int64_t m) {
   const int64_t cap = (int64_t)sm_count() * 8;
   return (int)(m < cap ? (m < 1 ? 1 : m) : cap);
@@ -210,6 +411,18 @@ extern "C" int xr_logits_sampled(const void* q, const void* table, int64_t n_row
   if (rc) return rc;
   if (m == 0 || c == 0) return XR_OK;
   cudaStream_t s = as_stream(stream);
+  if (dim == FD) {   // BASELINE config 3 shape: rows in flight instead of one row per warp
+    if (dtype == XR_F32)
+      sampled_logits384_kernel<float><<<row_grid(m), ROW_THREADS, 0, s>>>(
+          (const float*)q, (const float*)table, cand_idx, n_rows, m, c, q_inv_norm, table_inv_norm,
+          logits, ld);
+    else
+      sampled_logits384_kernel<__nv_bfloat16><<<row_grid(m), ROW_THREADS, 0, s>>>(
+          (const __nv_bfloat16*)q, (const __nv_bfloat16*)table, cand_idx, n_rows, m, c, q_inv_norm,
+          table_inv_norm, logits, ld);
+    XR_LAUNCH_CHECK("sampled_logits384");
+    return XR_OK;
+  }
   return dtype == XR_F32
              ? launch_row_logits<float>(q, table, cand_idx, n_rows, m, c, dim, q_inv_norm,
                                         table_inv_norm, nullptr, 0.f, logits, ld, s)
@@ -246,6 +459,18 @@ extern "C" int xr_dq_sampled(const float* dlogits, int64_t ld, const void* q, co
   if (rc) return rc;
   if (m == 0) return XR_OK;
   cudaStream_t s = as_stream(stream);
+  if (dim == FD) {
+    if (dtype == XR_F32)
+      sampled_dq384_kernel<float><<<row_grid(m), ROW_THREADS, 0, s>>>(
+          dlogits, ld, (const float*)q, (const float*)table, cand_idx, n_rows, m, c, q_inv_norm,
+          table_inv_norm, cosine, dq);
+    else
+      sampled_dq384_kernel<__nv_bfloat16><<<row_grid(m), ROW_THREADS, 0, s>>>(
+          dlogits, ld, (const __nv_bfloat16*)q, (const __nv_bfloat16*)table, cand_idx, n_rows, m, c,
+          q_inv_norm, table_inv_norm, cosine, dq);
+    XR_LAUNCH_CHECK("sampled_dq384");
+    return XR_OK;
+  }
   return dtype == XR_F32
              ? launch_row_dq<float>(dlogits, ld, q, table, cand_idx, n_rows, m, c, dim,
                                     q_inv_norm, table_inv_norm, nullptr, cosine, dq, s)
