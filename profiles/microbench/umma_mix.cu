@@ -147,7 +147,208 @@ __global__ void __launch_bounds__(128, 1) qdepth(long long* out, int n) {
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+// The fused kernel's ISSUE STRUCTURE around the same MMA stream: warp-uniform loop, per pair an
+// mbarrier wait (barriers completed in advance by a helper warp, so no wait ever blocks), fence,
+// elect, 8 MMAs, commit, __syncwarp.  variant 0: as in the kernel; 1: waits hoisted (all three pair
+// barriers polled before the first MMA of the tile); 2: no waits at all (upper bound).
+__global__ void __launch_bounds__(128, 1) k_struct(long long* out, int variant, int tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  __shared__ uint32_t tmem_ptr;
+  __shared__ __align__(8) unsigned long long bar, full[8], empty[8], sfull[2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
+    mbar_init(smem_u32(&sfull[0]), 1); mbar_init(smem_u32(&sfull[1]), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_ptr), 512);
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tmem = tmem_ptr;
+  const uint32_t q_smem = base, ring = base + 6 * QSUB;
+  constexpr uint32_t idesc_s = xr::sm100::umma_idesc_bf16(128, 64, 0, 0);
+  const uint64_t q_desc0 = umma_desc_sw128(q_smem, 16, 1024);
+  const uint64_t ring_k = umma_desc_sw128(ring, 16, 1024);
+  if (warp == 2) {
+    // helper "producer": keeps every full barrier one phase ahead (arrives as soon as empty fires)
+    for (uint32_t g = 0; g < (uint32_t)tiles * 3 && (variant < 2 || variant == 6 || variant == 10); ++g) {
+      const uint32_t s = g & 7;
+      mbar_wait(smem_u32(&empty[s]), ((g / 8) & 1) ^ 1, nullptr, 0);
+      if (lane == 0) mbar_arrive(smem_u32(&full[s]));
+      __syncwarp();
+    }
+  } else if (warp == 1 && variant < 6) {
+    long long t0 = clock64();
+    uint32_t g = 0;
+    for (int t = 0; t < tiles; ++t) {
+      const int b = t & 1;
+      if (variant == 1)
+        for (int pr = 0; pr < 3; ++pr) mbar_wait(smem_u32(&full[(g + pr) & 7]), ((g + pr) / 8) & 1, nullptr, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int pr = 0; pr < 3; ++pr, ++g) {
+        const uint32_t s = g & 7;
+        if (variant == 0) mbar_wait(smem_u32(&full[s]), (g / 8) & 1, nullptr, 0);
+        if (variant != 5) tc_fence_after();
+        if (elect_one()) {
+          const uint64_t a0 = q_desc0 + (uint64_t)(pr * ((2 * QSUB) >> 4));
+          const uint64_t b0 = ring_k + (uint64_t)(s * ((2 * SUB) >> 4));
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_ss(tmem + 384 + b * 64, a0 + h * (QSUB >> 4) + 2 * kk, b0 + h * (SUB >> 4) + 2 * kk,
+                      idesc_s, (pr | h | kk) ? 1u : 0u);
+          if (variant != 3 && variant != 5) umma_commit(smem_u32(&empty[s]));
+        }
+        if (variant != 4 && variant != 5) __syncwarp();
+      }
+      if (variant != 3 && variant != 5) {
+        if (elect_one()) umma_commit(smem_u32(&sfull[b]));
+        __syncwarp();
+      }
+    }
+    if (elect_one()) umma_commit(smem_u32(&bar));
+    __syncwarp();
+    mbar_wait(smem_u32(&bar), 0, nullptr, 0);
+    if (lane == 0) out[blockIdx.x] = clock64() - t0;
+  } else if (warp == 3 && variant >= 6) {
+    // ONE thread runs the whole issue loop: no elect / __syncwarp between MMA groups, and the
+    // barrier a group needs was polled right after the previous group was issued (while those
+    // MMAs were still queued), so the MMA stream never stops for a wait that is already satisfied
+    if (variant >= 10 ? elect_one() : (lane == 0)) {
+      long long t0 = clock64();
+      uint32_t g = 0;
+      if (variant == 6 || variant == 10) mbar_wait(smem_u32(&full[0]), 0, nullptr, 0);
+      for (int t = 0; t < tiles; ++t) {
+        const int b = t & 1;
+#pragma unroll
+        for (int pr = 0; pr < 3; ++pr, ++g) {
+          const uint32_t s = g & 7;
+          if (variant == 6 || variant == 8 || variant == 10) tc_fence_after();
+          const uint64_t a0 = q_desc0 + (uint64_t)(pr * ((2 * QSUB) >> 4));
+          const uint64_t b0 = ring_k + (uint64_t)(s * ((2 * SUB) >> 4));
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_ss(tmem + 384 + b * 64, a0 + h * (QSUB >> 4) + 2 * kk, b0 + h * (SUB >> 4) + 2 * kk,
+                      idesc_s, (pr | h | kk) ? 1u : 0u);
+          if (variant != 9) umma_commit(smem_u32(&empty[s]));
+          if (pr == 2 && variant != 9) umma_commit(smem_u32(&sfull[b]));
+          // poll the NEXT group's barrier now
+          const uint32_t gn = g + 1;
+          if ((variant == 6 || variant == 10) && gn < (uint32_t)tiles * 3) mbar_wait(smem_u32(&full[gn & 7]), (gn / 8) & 1, nullptr, 0);
+        }
+      }
+      umma_commit(smem_u32(&bar));
+      mbar_wait(smem_u32(&bar), 0, nullptr, 0);
+      out[blockIdx.x] = clock64() - t0;
+    }
+  }
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// candidate structure for the fused kernel's score issuer: the whole role runs in ONE elected thread
+template <bool WAITS>
+__global__ void __launch_bounds__(128, 1) k_elected(long long* out, int tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  __shared__ uint32_t tmem_ptr;
+  __shared__ __align__(8) unsigned long long bar, full[8], empty[8], sfull[2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
+    mbar_init(smem_u32(&sfull[0]), 1); mbar_init(smem_u32(&sfull[1]), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_ptr), 512);
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tmem = tmem_ptr;
+  const uint32_t q_smem = base, ring = base + 6 * QSUB;
+  constexpr uint32_t idesc_s = xr::sm100::umma_idesc_bf16(128, 64, 0, 0);
+  const uint64_t q_desc0 = umma_desc_sw128(q_smem, 16, 1024);
+  const uint64_t ring_k = umma_desc_sw128(ring, 16, 1024);
+  const uint32_t full0 = smem_u32(&full[0]), empty0 = smem_u32(&empty[0]), sfull0 = smem_u32(&sfull[0]);
+  if (warp == 2 && WAITS) {
+    for (uint32_t g = 0; g < (uint32_t)tiles * 3; ++g) {
+      const uint32_t s = g & 7;
+      mbar_wait(empty0 + 8 * s, ((g / 8) & 1) ^ 1, nullptr, 0);
+      if (lane == 0) mbar_arrive(full0 + 8 * s);
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      long long t0 = clock64();
+      uint32_t g = 0;
+      if (WAITS) mbar_wait(full0, 0, nullptr, 0);
+      for (int t = 0; t < tiles; ++t) {
+        const int b = t & 1;
+#pragma unroll
+        for (int pr = 0; pr < 3; ++pr, ++g) {
+          const uint32_t s = g & 7;
+          if (WAITS) tc_fence_after();
+          const uint64_t a0 = q_desc0 + (uint64_t)(pr * ((2 * QSUB) >> 4));
+          const uint64_t b0 = ring_k + (uint64_t)(s * ((2 * SUB) >> 4));
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_ss(tmem + 384 + b * 64, a0 + h * (QSUB >> 4) + 2 * kk, b0 + h * (SUB >> 4) + 2 * kk,
+                      idesc_s, (pr | h | kk) ? 1u : 0u);
+          umma_commit(empty0 + 8 * s);
+          if (pr == 2) umma_commit(sfull0 + 8 * b);
+          const uint32_t gn = g + 1;
+          if (WAITS && gn < (uint32_t)tiles * 3) mbar_wait(full0 + 8 * (gn & 7), (gn / 8) & 1, nullptr, 0);
+        }
+      }
+      umma_commit(smem_u32(&bar));
+      mbar_wait(smem_u32(&bar), 0, nullptr, 0);
+      out[blockIdx.x] = clock64() - t0;
+    }
+  }
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
 int main() {
+  {
+    long long* d; cudaMalloc(&d, 148 * 8);
+    const int smem = 6 * QSUB + 16 * SUB + 1024;
+    cudaFuncSetAttribute(k_elected<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_elected<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    for (int w = 0; w < 2; ++w) {
+      if (w) k_elected<true><<<148, 128, smem>>>(d, 400); else k_elected<false><<<148, 128, smem>>>(d, 400);
+      cudaError_t e = cudaDeviceSynchronize();
+      long long h[148]; cudaMemcpy(h, d, 148 * 8, cudaMemcpyDeviceToHost);
+      double avg = 0; for (int i = 0; i < 148; ++i) avg += h[i]; avg /= 148;
+      printf("S-only, whole issuer role in one ELECTED thread, %s: %7.1f cycles/tile  [%s]\n",
+             w ? "polled waits + commits" : "commits only          ", avg / 400, cudaGetErrorString(e));
+    }
+  }
+  {
+    long long* d; cudaMalloc(&d, 148 * 8);
+    const int smem = 6 * QSUB + 16 * SUB + 1024;
+    cudaFuncSetAttribute(k_struct, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const char* nm[] = {"kernel issue structure (wait/elect per pair)", "waits hoisted to the tile start",
+                        "no waits, no producer (commits + elect per pair)", "no waits, no commits (elect + syncwarp per pair)",
+                        "no waits, commits, no syncwarp per pair", "elect per pair only (no fence/commit/syncwarp)",
+                        "ONE issuing thread, next barrier polled behind each MMA group",
+                        "ONE thread: MMAs + commits only", "ONE thread: fence + MMAs + commits", "ONE thread: MMAs only", "ONE ELECTED thread: polled waits + fence + MMAs + commits",
+                        "ONE ELECTED thread: MMAs + commits"};
+    for (int v = 6; v < 12; ++v) {
+      k_struct<<<148, 128, smem>>>(d, v, 400);
+      cudaError_t e = cudaDeviceSynchronize();
+      long long h[148]; cudaMemcpy(h, d, 148 * 8, cudaMemcpyDeviceToHost);
+      double avg = 0; for (int i = 0; i < 148; ++i) avg += h[i]; avg /= 148;
+      printf("S-only, %-46s: %7.1f cycles/tile  [%s]\n", nm[v], avg / 400, cudaGetErrorString(e));
+    }
+  }
   {
     long long* d; cudaMalloc(&d, 16);
     cudaFuncSetAttribute(qdepth, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);

@@ -25,19 +25,23 @@ torch.cuda.synchronize()
 mask = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 mode = int(sys.argv[2]) if len(sys.argv) > 2 else 1   # 1 wait counters + timeline, 2 timeline only
 lib.xr_fused_wait_stats(mode | (mask << 8), None)
-fn(out["query_embed"], out["candidate_embed"])
+if len(sys.argv) > 3 and sys.argv[3] == "nograd":   # forward only (the retrieval kernel's structure)
+    with torch.no_grad():
+        fn(out["query_embed"], out["candidate_embed"])
+else:
+    fn(out["query_embed"], out["candidate_embed"])
 torch.cuda.synchronize()
 buf = (ctypes.c_uint64 * 16)()
 lib.xr_fused_wait_stats(0, buf)
 names = {1: "producer: q_empty", 2: "producer: ring slot free", 3: "grad issuer: p_full (weights ready)",
-         4: "score issuer: q_full", 5: "grad issuer: o_empty", 6: "score issuer: s_free",
+         4: "score issuer: q_full", 5: "grad issuer: o_empty", 6: "score issuer: s_read (S buffer handed back)",
          7: "score issuer: ring pair loaded", 8: "epilogue warps: s_full (x16 warps)",
-         9: "epilogue warps: o_full (x16 warps)"}
+         9: "epilogue warps: o_full (x16 warps)", 10: "epilogue warps: w_free (x16 warps)"}
 m, c = out["query_embed"].size(0), out["candidate_embed"].size(1)
 print(f"M={m} C={c}; wait cycles summed over 148 CTAs (per-CTA average in parentheses)")
 for t, n in names.items():
-    div = 148 * (16 if t in (8, 9) else 1)
-    print(f"  tag {t}: {buf[t]:>14d}  ({buf[t] / div:>10.0f} cycles/CTA{'/warp' if t in (8, 9) else ''})  {n}")
+    div = 148 * (16 if t in (8, 9, 10) else 1)
+    print(f"  tag {t}: {buf[t]:>14d}  ({buf[t] / div:>10.0f} cycles/CTA{'/warp' if t in (8, 9, 10) else ''})  {n}")
 
 tl = (ctypes.c_int64 * 512)()
 lib.xr_fused_timeline(tl)

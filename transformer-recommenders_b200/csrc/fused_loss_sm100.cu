@@ -324,33 +324,47 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const uint32_t tile = tt + tl;
         const uint32_t use = tile >> nsb_shift;            // how often this S buffer was used before
         const int sb = tile & ((1 << nsb_shift) - 1);
-        if (use >= 1) mbar_wait<STATS>(bar_s_read(sb), (use - 1) & 1, p.hang_flag, 6);
-        tc_fence_after();
         if (ABL && p.dbg && blockIdx.x == 0 && lane == 0 && tile < 64) p.dbg[tile * 8 + 0] = clock64();
-#pragma unroll 1
-        for (int pr = 0; pr < KB / 2; ++pr, ++g) {
-          const uint32_t s = g & (PAIRS - 1);
-          mbar_wait<STATS>(bar_full(s), (g / PAIRS) & 1, p.hang_flag, 7);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint64_t a0 = q_desc0 + (uint64_t)(pr * ((2 * QSUB_BYTES) >> 4));
-            const uint64_t b0 = ring_k_desc0 + (uint64_t)(s * ((2 * SUB_BYTES) >> 4));
-            if (!(ABL && (p.ablate & 4)))
+        // TWO elect blocks per tile (pairs 0+1, then pair 2): every interruption of the MMA issue
+        // stream (warp reconvergence, descriptor set-up, a wait) costs ~200 cycles of tensor pipe
+        // (profiles/microbench/umma_mix.cu).  The waits stay OUTSIDE the blocks, warp-uniform: a
+        // wait loop inside an elect block makes ptxas build every descriptor in vector registers
+        // (16+ R2UR per pair instead of UIADD3.64 on a uniform base).
+        auto issue_pair = [&](int pr) {
+          const uint32_t s = (g + pr) & (PAIRS - 1);
+          const uint64_t a0 = q_desc0 + (uint64_t)(pr * ((2 * QSUB_BYTES) >> 4));
+          const uint64_t b0 = ring_k_desc0 + (uint64_t)(s * ((2 * SUB_BYTES) >> 4));
+          if (!(ABL && (p.ablate & 4)))
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+          for (int h = 0; h < 2; ++h)
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_ss(tmem + COL_S + sb * BN, a0 + h * (QSUB_BYTES >> 4) + 2 * k,
-                        b0 + h * (SUB_BYTES >> 4) + 2 * k, idesc_s, (pr | h | k) ? 1u : 0u);
-            if (!grad) umma_commit(bar_empty(s));   // forward only: the pair is free after S
-          }
-          __syncwarp();
-        }
+            for (int k = 0; k < 4; ++k)
+              umma_ss(tmem + COL_S + sb * BN, a0 + h * (QSUB_BYTES >> 4) + 2 * k,
+                      b0 + h * (SUB_BYTES >> 4) + 2 * k, idesc_s, (pr | h | k) ? 1u : 0u);
+          if (!grad) umma_commit(bar_empty(s));   // forward only: the pair is free after S
+        };
+        if (use >= 1) mbar_wait<STATS>(bar_s_read(sb), (use - 1) & 1, p.hang_flag, 6);
+        mbar_wait<STATS>(bar_full(g & (PAIRS - 1)), (g / PAIRS) & 1, p.hang_flag, 7);
+        mbar_wait<STATS>(bar_full((g + 1) & (PAIRS - 1)), ((g + 1) / PAIRS) & 1, p.hang_flag, 7);
+        tc_fence_after();
         if (elect_one()) {
+#pragma unroll 1   // runtime pair index: keeps ptxas from hoisting 24 descriptors into vector registers
+          for (int pr = 0; pr < 2; ++pr) issue_pair(pr);
+        }
+        __syncwarp();
+        // (peeking at the third pair to issue the whole tile in one block measured slower: the
+        // extra try_wait + shuffle cost more than the saved reconvergence)
+        mbar_wait<STATS>(bar_full((g + 2) & (PAIRS - 1)), ((g + 2) / PAIRS) & 1, p.hang_flag, 7);
+        tc_fence_after();
+        if (elect_one()) {
+          int pr2 = 2;
+          asm volatile("" : "+r"(pr2));   // opaque to the optimiser for the same reason
+          issue_pair(pr2);
           umma_commit(bar_s_full(sb));
           if (tl == T - 1) umma_commit(bar_q_empty);   // Q is only read by the score MMAs
         }
         __syncwarp();
+        g += KB / 2;
         if (ABL && p.dbg && blockIdx.x == 0 && lane == 0 && tile < 64) p.dbg[tile * 8 + 1] = clock64();
       }
       tt += T;
