@@ -65,10 +65,45 @@ class ClockSampler:
         self.gpu, self.rows, self.proc = gpu_index, [], None
         self.t0 = self.t1 = None
 
+    def _start_nvml(self, phys: int) -> bool:
+        """Preferred: poll NVML from a thread every 2 ms (the timed region lasts tens of ms)."""
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = (("hw_slowdown", pynvml.nvmlClocksEventReasonHwSlowdown),
+                    ("hw_thermal_slowdown", pynvml.nvmlClocksEventReasonHwThermalSlowdown),
+                    ("sw_thermal_slowdown", pynvml.nvmlClocksEventReasonSwThermalSlowdown),
+                    ("sw_power_cap", pynvml.nvmlClocksEventReasonSwPowerCap))
+            pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            return False
+        self._stop_flag = False
+
+        def pump():
+            while not self._stop_flag:
+                try:
+                    sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                    r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    row = [str(sm), str(mx)] + ["Active" if r & b else "Not Active" for _, b in bits]
+                    self.rows.append((time.time(), row))
+                except Exception:
+                    pass
+                time.sleep(0.002)
+
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+        return True
+
     def start(self):
         vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
         ids = [x.strip() for x in vis.split(",")] if vis else []
         phys = ids[self.gpu] if self.gpu < len(ids) and ids[self.gpu].isdigit() else str(self.gpu)
+        self.thread = None
+        if self._start_nvml(int(phys)):
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={phys}", f"--query-gpu={self.Q}",
@@ -89,11 +124,15 @@ class ClockSampler:
         self.t1 = time.time()
 
     def stop(self):
-        if self.proc is None:
+        if self.thread is not None:
+            self._stop_flag = True
+            self.thread.join(timeout=1.0)
+        elif self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.05)
-        self.proc.terminate()
-        inside = [r for ts, r in self.rows if self.t0 - 0.03 <= ts <= self.t1 + 0.03]
+        else:
+            time.sleep(0.05)
+            self.proc.terminate()
+        inside = [r for ts, r in self.rows if self.t0 <= ts <= self.t1]
         window = "timed region"
         if not inside:  # region shorter than the sampling period: use the whole loaded run
             inside, window = [r for _, r in self.rows], "warm-up + timed region"
@@ -164,7 +203,7 @@ def reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-retrieval", action="store_true")
@@ -189,7 +228,8 @@ def main():
     from oracle import xfmr_oracle as orc  # synthetic inputs + cpu_baseline leg only
 
     all_cpus = os.sched_getaffinity(0)
-    bind_to_gpu_numa_node(local_rank)   # pinned staging buffers land next to this rank's GPU
+    if world > 1:
+        bind_to_gpu_numa_node(local_rank)   # pinned staging buffers land next to this rank's GPU
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
