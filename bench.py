@@ -473,7 +473,7 @@ def bench_retrieval(args, xr, dev, rank, world, peak_hbm):
         ms = float(t)
     out = {"metric": "full-catalog top-100 queries/sec", "value": u / (ms / 1e3), "unit": "queries/s",
            "catalog_rows": n, "queries": u, "k": k, "ms_per_batch": ms, "dtype": "bf16",
-           "path": "tcgen05 group-max scoring + top groups re-scored + merge (+ NCCL all-gather of (U,k) when sharded)"
+           "path": "tcgen05 cta_group::2 group-max scoring + top groups re-scored + merge (+ NCCL all-gather of (U,k) when sharded)"
            if fused else "scores (fp32-accumulate GEMM) + streaming top-k + merge",
            "catalog_bytes_per_rank": (hi - lo) * DIM * 2}
     if fused:
@@ -487,7 +487,7 @@ def bench_retrieval(args, xr, dev, rank, world, peak_hbm):
             flops = 2.0 * u * (hi - lo) * DIM
             byts = (hi - lo) * DIM * 2
             out["scoring_kernel"] = {
-                "kernel": "fused_pool_kernel<GMAX> (tcgen05)", "kernel_ms": k_ms,
+                "kernel": "score_gmax2_kernel (tcgen05 cta_group::2)" if u > 128 else "fused_pool_kernel<GMAX> (tcgen05)", "kernel_ms": k_ms,
                 "TFLOP/s": flops / (k_ms * 1e-3) / 1e12,
                 "catalog_GB/s": byts / (k_ms * 1e-3) / 1e9,
                 "frac_of_measured_hbm": byts / (k_ms * 1e-3) / 1e9 / peak_hbm,

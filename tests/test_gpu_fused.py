@@ -198,3 +198,30 @@ def test_groupmax_retrieval_random_cosine(xr):
     want_s, want_i = orc.exact_search(qn.float().cpu().numpy(), catn, k, None, metric="dot", dtype=np.float64)
     recall = np.mean([len(set(i1[r].tolist()) & set(want_i[r].tolist())) / k for r in range(u)])
     assert recall >= 0.999, recall
+
+
+@pytest.mark.parametrize("u,n", [(129, 1000), (256, 12800), (300, 4097), (1000, 130), (513, 64)])
+def test_groupmax_cta_pair_kernel_matches_reference(xr, u, n):
+    """u > 128 runs on CTA pairs (tcgen05 cta_group::2, 256 queries per pair); group maxima must
+    equal the maxima of the fp32-accumulated scores and agree with the single-CTA variant."""
+    from xfmr_rec_b200 import _native as N, ops
+
+    g = torch.Generator(device="cuda").manual_seed(u * 7 + n)
+    q = torch.randn((u, 384), generator=g, device="cuda").bfloat16()
+    cat = torch.randn((n, 384), generator=g, device="cuda").bfloat16()
+    ng = (n + 15) // 16
+    want = torch.full((u, ng * 16), float("-inf"), device="cuda")
+    want[:, :n] = q.float() @ cat.float().T
+    want = want.view(u, ng, 16).amax(-1)
+    lib = N.lib()
+    got_pair = ops.score_groupmax(q, cat)[:, :ng].clone()
+    lib.xr_fused_wait_stats(4, None)          # profiling switch: force the single-CTA kernel
+    try:
+        got_single = ops.score_groupmax(q, cat)[:, :ng].clone()
+    finally:
+        lib.xr_fused_wait_stats(0, None)
+    torch.testing.assert_close(got_pair, want, rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(got_single, want, rtol=2e-3, atol=2e-3)
+    # every group beyond the catalog is -inf (never selected)
+    full = ops.score_groupmax(q, cat)
+    assert bool((full[:, ng:8 * ((n + 127) // 128)] == float("-inf")).all())

@@ -952,6 +952,12 @@ static int launch_fused(const CUtensorMap& tq, const CUtensorMap& tb, const Fuse
 
 using namespace xr;
 
+namespace xr {
+int launch_score_gmax2(const void* q, int64_t u, const void* catalog, int64_t n, float* gmax, int64_t ld,
+                       int* hang_flag, cudaStream_t s);
+}
+static bool g_gmax_single = false;   // profiling aid: force the single-CTA retrieval kernel
+
 extern "C" int xr_fused_available(void) { return 3; }  // bit 0: fused loss, bit 1: fused retrieval scoring
 
 // workspace carve-up shared by xr_fused_pool_loss (exact shape) and xr_pool_step (bounds)
@@ -1284,6 +1290,8 @@ extern "C" int xr_score_groupmax(const void* q, int64_t u, const void* catalog, 
   XR_CHECK_ARG(u > 0 && n > 0 && u < (1ll << 30) && n < (1ll << 31), "xr_score_groupmax: bad sizes");
   const int64_t nt = (n + fk::BN - 1) / fk::BN;
   XR_CHECK_ARG(ld >= nt * fk::CG, "xr_score_groupmax: ld must be >= 4 * ceil(n / 64)");
+  XR_CHECK_ARG(u <= fk::BM || (ld >= 8 * ((n + 127) / 128) && ld % 2 == 0 && (uintptr_t)gmax % 8 == 0),
+               "xr_score_groupmax: for u > 128, ld must be even and >= 8 * ceil(n / 128), gmax 8-byte aligned");
   XR_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)catalog % 16 == 0),
                "xr_score_groupmax: operands must be 16-byte aligned");
   int dev = 0, major = 0;
@@ -1312,7 +1320,10 @@ extern "C" int xr_score_groupmax(const void* q, int64_t u, const void* catalog, 
   const int grid = pl.n_items < n_sm ? pl.n_items : n_sm;
   const bool prof = g_prof_on && g_prof_n < kProfRing;
   if (prof) cudaEventRecord(g_prof_ev[g_prof_n][0], s);
-  rc = launch_fused1<fk::KIND_GMAX, false>(tq, tc, p, grid, s);
+  if (u > fk::BM && !g_gmax_single)   // CTA pairs: 256 queries per pair, half the catalog bytes per SM
+    rc = launch_score_gmax2(q, u, catalog, n, gmax, ld, hang, s);
+  else
+    rc = launch_fused1<fk::KIND_GMAX, false>(tq, tc, p, grid, s);
   if (prof) cudaEventRecord(g_prof_ev[g_prof_n++][1], s);
   return rc;
 }
@@ -1332,6 +1343,7 @@ extern "C" int xr_fused_timeline(long long* out512_host) {
 extern "C" int xr_fused_wait_stats(int enable, unsigned long long* out16_host) {
   g_wait_stats = (enable & 1) != 0;
   g_timeline = (enable & 2) != 0;   // per-tile timestamps without the wait counters
+  g_gmax_single = (enable & 4) != 0;
   g_ablate = enable >> 8;   // ablation mask for timing experiments (results are garbage)
   if (out16_host) memcpy(out16_host, g_wait_host, sizeof(g_wait_host));
   return XR_OK;

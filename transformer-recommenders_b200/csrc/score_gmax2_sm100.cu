@@ -1,0 +1,320 @@
+// Retrieval scoring on CTA PAIRS (tcgen05 cta_group::2): gmax[u, g] = max over the 16 catalog rows
+// of group g of q_u . cat_c — the exact pre-filter of the full-catalog top-k (index.py:244-254
+// semantics, see xr_score_groupmax in fused_loss_sm100.cu for the single-CTA version).
+//
+// Why pairs: shared-memory ingest by TMA is ~35 B/cycle/SM whatever the ring depth or multicast
+// (profiles/microbench/tma_stream.cu), and a 128-query CTA needs 48 KB per 64 candidates = 1,400
+// cycles against 1,150 cycles of MMA work: the single-CTA kernel is ingest-bound.  With
+// cta_group::2 one MMA covers 256 queries (128 per CTA) x 128 candidates, and each CTA stages only
+// ITS half of the candidate tile (B is split along N across the pair): per SM the same 48 KB now
+// feed 1,536 cycles of MMA work on 128 x 128 outputs, at N = 128 where the SS MMA runs at pipe rate.
+//
+// Per CTA (640 threads): warp 0 TMA producer (own Q rows, own half of every catalog tile; every
+// load signals the LEADER CTA's mbarrier), warp 1 of the leader issues the MMAs for both SMs,
+// warps 4-19 epilogue over the CTA's own 128 TMEM lanes.  TMEM: 4 S buffers of 128 columns.
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace xr {
+
+using namespace sm100;
+
+namespace g2 {
+constexpr int BM = 128;            // query rows per CTA (256 per pair)
+constexpr int BNH = 64;            // catalog rows per CTA per tile (128 per pair)
+constexpr int BN = 2 * BNH;
+constexpr int D = 384;
+constexpr int KB = D / 64;
+constexpr int PAIRS = 8;           // ring of 16 KB slots: two adjacent 64x64 k-blocks
+constexpr int SUB_BYTES = BNH * 64 * 2;
+constexpr int QSUB_BYTES = BM * 64 * 2;
+constexpr int Q_BYTES = KB * QSUB_BYTES;
+constexpr int RING_BYTES = PAIRS * 2 * SUB_BYTES;
+constexpr int NSB = 4;             // S buffers (128 TMEM columns each)
+constexpr int BAR_OFF = Q_BYTES + RING_BYTES;
+constexpr int NBARS = 2 * PAIRS + 2 + 2 * NSB;
+constexpr int SMEM_BYTES = BAR_OFF + NBARS * 8 + 16 + 1024;
+constexpr int EPI_WARPS = 16;
+constexpr int THREADS = 128 + EPI_WARPS * 32;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // shared::cluster address of the pair's EVEN CTA
+}  // namespace g2
+
+struct Gmax2Params {
+  int u, n, nt_count, spl, tiles_per_split, n_items, qb_count;
+  float* gmax;
+  long long gmax_ld;
+  int* hang_flag;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes go to the mbarrier of the pair's leader (even) CTA
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst_smem, const void* tmap, uint32_t bar, int c0,
+                                                int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+      "{%3, %4}], [%2];" ::"r"(dst_smem),
+      "l"(tmap), "r"(bar & g2::PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem, both CTAs] (+)= A[smem of each CTA: its 128 rows] . B[smem of each CTA: its N/2 rows]
+__device__ __forceinline__ void umma_ss2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all MMAs issued so far -> one arrive on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit2(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+// arrive on the LEADER's copy of a barrier, from either CTA of the pair
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & g2::PEER_MASK) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::THREADS, 1)
+score_gmax2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
+                   const Gmax2Params p) {
+  using namespace g2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t q_smem = base, ring = base + Q_BYTES, bars = base + BAR_OFF;
+  auto bar_full = [&](uint32_t s) { return bars + 8u * s; };              // leader: pair s landed in BOTH CTAs
+  auto bar_empty = [&](uint32_t s) { return bars + 8u * (PAIRS + s); };   // each CTA: its slot s is free
+  const uint32_t bar_q_full = bars + 8u * (2 * PAIRS);                    // leader
+  const uint32_t bar_q_empty = bars + 8u * (2 * PAIRS + 1);               // each CTA
+  auto bar_s_full = [&](int b) { return bars + 8u * (2 * PAIRS + 2 + b); };        // each CTA
+  auto bar_s_free = [&](int b) { return bars + 8u * (2 * PAIRS + 2 + NSB + b); };  // leader
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + BAR_OFF + NBARS * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PAIRS; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    mbar_init(bar_q_full, 1);
+    mbar_init(bar_q_empty, 1);
+    for (int b = 0; b < NSB; ++b) {
+      mbar_init(bar_s_full(b), 1);
+      mbar_init(bar_s_free(b), 2 * EPI_WARPS);   // one elected arrive per epilogue warp of BOTH CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmap_q);
+    prefetch_tensormap(&tmap_c);
+  }
+  if (warp == 1) tmem_alloc2(smem_u32((const void*)tmem_ptr_smem), 512);
+  tc_fence_before();
+  cluster_sync_all();   // barriers of both CTAs initialised before anything crosses the pair
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_smem;
+
+  // work items of a CTA pair: (block of 256 queries, split of the 128-candidate tiles); query block
+  // fastest so that pairs sharing a catalog range run side by side (second read comes from L2)
+  auto item_tiles = [&](int item, int& qb, int& t0, int& t1) {
+    qb = item % p.qb_count;
+    const int sp = item / p.qb_count;
+    t0 = sp * p.tiles_per_split;
+    t1 = min(p.nt_count, t0 + p.tiles_per_split);
+  };
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ================================
+    uint32_t g = 0, it = 0;
+    for (int item = cluster_id; item < p.n_items; item += n_clusters, ++it) {
+      int qb, t0, t1;
+      item_tiles(item, qb, t0, t1);
+      mbar_wait(bar_q_empty, (it & 1) ^ 1, p.hang_flag, 1);
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(bar_q_full, 2 * Q_BYTES);
+        for (int kb = 0; kb < KB; ++kb)
+          tma_load_2d_2sm(q_smem + kb * QSUB_BYTES, &tmap_q, bar_q_full, kb * 64, qb * 2 * BM + (int)rank * BM);
+      }
+      __syncwarp();
+      for (int t = t0; t < t1; ++t) {
+#pragma unroll 1
+        for (int pr = 0; pr < KB / 2; ++pr, ++g) {
+          const uint32_t s = g & (PAIRS - 1);
+          mbar_wait(bar_empty(s), ((g / PAIRS) & 1) ^ 1, p.hang_flag, 2);
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(bar_full(s), 2 * 2 * SUB_BYTES);
+            const int row0 = t * BN + (int)rank * BNH;
+            tma_load_2d_2sm(ring + s * 2 * SUB_BYTES, &tmap_c, bar_full(s), pr * 128, row0);
+            tma_load_2d_2sm(ring + s * 2 * SUB_BYTES + SUB_BYTES, &tmap_c, bar_full(s), pr * 128 + 64, row0);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // ===================== MMA issuer (leader CTA, for both SMs) =====================
+    // waits stay outside the elect blocks and the pair index is a run-time value, so ptxas keeps
+    // the descriptors in uniform registers (see fused_loss_sm100.cu)
+    constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);
+    const uint64_t q_desc0 = umma_desc_sw128(q_smem, 16, 1024);
+    const uint64_t ring_desc0 = umma_desc_sw128(ring, 16, 1024);
+    uint32_t g = 0, tile = 0, it = 0;
+    for (int item = cluster_id; item < p.n_items; item += n_clusters, ++it) {
+      int qb, t0, t1;
+      item_tiles(item, qb, t0, t1);
+      const int T = t1 - t0;
+      mbar_wait(bar_q_full, it & 1, p.hang_flag, 4);
+      for (int tl = 0; tl < T; ++tl, ++tile) {
+        const int sb = tile % NSB;
+        const uint32_t use = tile / NSB;
+        if (use >= 1) mbar_wait(bar_s_free(sb), (use - 1) & 1, p.hang_flag, 6);
+        auto issue_pair = [&](int pr) {
+          const uint32_t s = (g + pr) & (PAIRS - 1);
+          const uint64_t a0 = q_desc0 + (uint64_t)(pr * ((2 * QSUB_BYTES) >> 4));
+          const uint64_t b0 = ring_desc0 + (uint64_t)(s * ((2 * SUB_BYTES) >> 4));
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_ss2(tmem + sb * BN, a0 + h * (QSUB_BYTES >> 4) + 2 * k, b0 + h * (SUB_BYTES >> 4) + 2 * k,
+                       idesc, (pr | h | k) ? 1u : 0u);
+          umma_commit2(bar_empty(s));   // the pair's slot is free in both CTAs once these MMAs are done
+        };
+        mbar_wait(bar_full(g & (PAIRS - 1)), (g / PAIRS) & 1, p.hang_flag, 7);
+        mbar_wait(bar_full((g + 1) & (PAIRS - 1)), ((g + 1) / PAIRS) & 1, p.hang_flag, 7);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll 1
+          for (int pr = 0; pr < 2; ++pr) issue_pair(pr);
+        }
+        __syncwarp();
+        mbar_wait(bar_full((g + 2) & (PAIRS - 1)), ((g + 2) / PAIRS) & 1, p.hang_flag, 7);
+        tc_fence_after();
+        if (elect_one()) {
+          int pr2 = 2;
+          asm volatile("" : "+r"(pr2));
+          issue_pair(pr2);
+          umma_commit2(bar_s_full(sb));
+          if (tl == T - 1) umma_commit2(bar_q_empty);
+        }
+        __syncwarp();
+        g += KB / 2;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue (both CTAs) ================================
+    const int quad = warp & 3, cg = (warp - 4) >> 2;   // TMEM lane quadrant, 32-column group
+    const int r_local = quad * 32 + lane;
+    const uint32_t tmem_lane = tmem + ((uint32_t)(quad * 32) << 16);
+    uint32_t tile = 0;
+    for (int item = cluster_id; item < p.n_items; item += n_clusters) {
+      int qb, t0, t1;
+      item_tiles(item, qb, t0, t1);
+      const int row = qb * 2 * BM + (int)rank * BM + r_local;
+      const bool row_ok = row < p.u;
+      float* out_row = p.gmax + (long long)row * p.gmax_ld;
+      for (int t = t0; t < t1; ++t, ++tile) {
+        const int sb = tile % NSB;
+        mbar_wait(bar_s_full(sb), (tile / NSB) & 1, p.hang_flag, 8);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(tmem_lane + sb * BN + cg * 32, v);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(bar_s_free(sb));   // the logits are in registers
+        const int c0 = t * BN + cg * 32;                       // first catalog row of this column group
+        float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (c0 + j < p.n) m0 = fmaxf(m0, __uint_as_float(v[j]));
+          if (c0 + 16 + j < p.n) m1 = fmaxf(m1, __uint_as_float(v[16 + j]));
+        }
+        if (row_ok) *reinterpret_cast<float2*>(out_row + (long long)t * (BN / 16) + cg * 2) = make_float2(m0, m1);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();   // neither CTA may leave (or free TMEM) while its peer can still touch it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem, 512);
+  }
+}
+
+int make_tmap_bf16_rows(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld_elems,
+                        int box_rows);
+
+// host: called by xr_score_groupmax for u > 128
+int launch_score_gmax2(const void* q, int64_t u, const void* catalog, int64_t n, float* gmax, int64_t ld,
+                       int* hang_flag, cudaStream_t s) {
+  using namespace g2;
+  const int n_sm = sm_count();
+  const int n_clusters = n_sm / 2;
+  Gmax2Params p{};
+  p.u = (int)u; p.n = (int)n;
+  p.qb_count = (int)((u + 2 * BM - 1) / (2 * BM));
+  p.nt_count = (int)((n + BN - 1) / BN);
+  // splits of the catalog so that qb_count x splits fills whole waves of CTA pairs
+  int best_spl = 1;
+  long long best = -1;
+  const int max_spl = p.nt_count < 4096 ? p.nt_count : 4096;
+  for (int sp = 1; sp <= max_spl; ++sp) {
+    const int tps = (p.nt_count + sp - 1) / sp;
+    const int s_eff = (p.nt_count + tps - 1) / tps;
+    const long long items = (long long)p.qb_count * s_eff;
+    const long long waves = (items + n_clusters - 1) / n_clusters;
+    const long long cost = waves * (tps + 4);
+    if (best < 0 || cost < best) {
+      best = cost;
+      best_spl = s_eff;
+    }
+    if (items > 8LL * n_clusters) break;
+  }
+  p.tiles_per_split = (p.nt_count + best_spl - 1) / best_spl;
+  p.spl = (p.nt_count + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.n_items = p.qb_count * p.spl;
+  p.gmax = gmax; p.gmax_ld = ld; p.hang_flag = hang_flag;
+  CUtensorMap tq, tc;
+  int rc;
+  if ((rc = make_tmap_bf16_rows(&tq, q, u, D, D, BM))) return rc;
+  if ((rc = make_tmap_bf16_rows(&tc, catalog, n, D, D, BNH))) return rc;
+  static bool configured = false;
+  if (!configured) {
+    XR_CUDA(cudaFuncSetAttribute(score_gmax2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured = true;
+  }
+  int pairs = p.n_items < n_clusters ? p.n_items : n_clusters;
+  score_gmax2_kernel<<<2 * pairs, THREADS, SMEM_BYTES, s>>>(tq, tc, p);
+  XR_LAUNCH_CHECK("score_gmax2_kernel");
+  return XR_OK;
+}
+
+}  // namespace xr

@@ -114,7 +114,7 @@ class ExactIndex:
         max_excl = 0
         if csr is not None:
             max_excl = int((csr[0][1:] - csr[0][:-1]).max().item()) if csr[0].numel() > 1 else 0
-        n_groups = 4 * ((n + 63) // 64)
+        n_groups = (n + 15) // 16
         kg = min(n_groups, top_k + max_excl + 28)
         if ops.score_groupmax_supported(q, cat) and kg <= 1024 and self.config.fused:
             s, i = self._search_groupmax(q, cat, csr, top_k, kg)
@@ -145,7 +145,7 @@ class ExactIndex:
         excluded id plus a margin, so the result equals the full scan."""
         n = cat.size(0)
         gmax = ops.score_groupmax(q, cat)
-        _, gi = ops.topk(gmax, kg)                                   # (U, kg) group ids, -1 = none
+        _, gi = ops.topk(gmax, kg, n=(n + 15) // 16)                 # (U, kg) group ids, -1 = none
         cols = gi[:, :, None] * 16 + torch.arange(16, device=gi.device)
         cols = torch.where(gi[:, :, None] >= 0, cols, torch.full_like(cols, -1)).reshape(gi.size(0), -1)
         valid = (cols >= 0) & (cols < n)

@@ -383,7 +383,7 @@ def score_groupmax(q, catalog):
     q, catalog = q.contiguous(), catalog.contiguous()
     u, d = q.shape
     n = catalog.size(0)
-    ld = 4 * ((n + 63) // 64)
+    ld = 8 * ((n + 127) // 128)   # >= ceil(n / 16) groups; both kernel variants fit
     gmax = torch.empty((u, ld), dtype=torch.float32, device=dev)
     with _on(dev):
         N.call("xr_score_groupmax", _p(q), u, _p(catalog), n, d, _p(gmax), ld, _stream())
