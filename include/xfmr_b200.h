@@ -273,6 +273,11 @@ int xr_score_groupmax(const void* q, int64_t u, const void* catalog, int64_t n, 
 int xr_mask_excluded_ids(float* scores, const int64_t* ids, int64_t u, int64_t c, int64_t ld,
                          int64_t id_lo, int64_t id_hi, const int64_t* excl_offsets,
                          const int64_t* excl_ids, void* stream);
+/* group ids (u, kg) chosen by xr_topk over the group maxima of xr_score_groupmax -> the 16 catalog
+ * rows of each group: cols (u, kg*16) local rows for the re-score gather (0 where there is no such
+ * row), ids (u, kg*16) global row ids = local + row_offset, -1 where there is no such row.     */
+int xr_groups_to_rows(const int64_t* group_ids, int64_t u, int64_t kg, int64_t n, int64_t row_offset,
+                      int64_t* cols, int64_t* ids, void* stream);
 
 /* fused tcgen05 scoring + top-k over one catalog shard (bf16, dim 384): scores = Q . Cat^T on the
  * tensor cores, threshold-filtered selection in the epilogue, no (U,N) score matrix in HBM.

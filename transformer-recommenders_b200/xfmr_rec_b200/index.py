@@ -146,11 +146,8 @@ class ExactIndex:
         n = cat.size(0)
         gmax = ops.score_groupmax(q, cat)
         _, gi = ops.topk(gmax, kg, n=(n + 15) // 16)                 # (U, kg) group ids, -1 = none
-        cols = gi[:, :, None] * 16 + torch.arange(16, device=gi.device)
-        cols = torch.where(gi[:, :, None] >= 0, cols, torch.full_like(cols, -1)).reshape(gi.size(0), -1)
-        valid = (cols >= 0) & (cols < n)
-        scores = ops.logits_sampled(q, cat, cols.clamp(0, n - 1).contiguous())
-        ids = torch.where(valid, cols + self.row_offset, torch.full_like(cols, -1)).contiguous()
+        cols, ids = ops.groups_to_rows(gi, n, self.row_offset)
+        scores = ops.logits_sampled(q, cat, cols)
         ops.mask_excluded_ids(scores, ids, self.row_offset, self.row_offset + n, csr)
         return ops.topk_merge(scores, ids, top_k)
 

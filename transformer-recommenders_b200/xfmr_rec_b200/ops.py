@@ -390,6 +390,18 @@ def score_groupmax(q, catalog):
     return gmax
 
 
+def groups_to_rows(group_ids, n, row_offset=0):
+    """(U, kg) group ids -> (cols, ids), both (U, kg*16) int64: gather rows and global ids (-1 = none)."""
+    dev = _require_cuda(group_ids)
+    group_ids = group_ids.contiguous()
+    u, kg = group_ids.shape
+    cols = torch.empty((u, kg * 16), dtype=torch.int64, device=dev)
+    ids = torch.empty((u, kg * 16), dtype=torch.int64, device=dev)
+    with _on(dev):
+        N.call("xr_groups_to_rows", _p(group_ids), u, kg, n, row_offset, _p(cols), _p(ids), _stream())
+    return cols, ids
+
+
 def mask_excluded_ids(score_mat, ids, id_lo, id_hi, exclude=None):
     dev = _require_cuda(score_mat, ids)
     offs, ex = (None, None) if exclude is None else exclude
