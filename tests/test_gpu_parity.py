@@ -386,3 +386,61 @@ def test_retrieval_metrics_match_oracle(xr):
     m = xr.metrics.compute_retrieval_metrics(["i10", "i3", "i7"], {"i3"}, top_k=3)
     assert list(m) == orc.METRIC_NAMES and float(m["retrieval_auroc"]) == pytest.approx(0.5)
     assert xr.metrics.compute_retrieval_metrics(["a"], set(), 3) == {}
+
+
+def test_config1_shape_full_size_matches_oracle(xr):
+    """BASELINE configs[0] at full size: ML-1M-shaped (3,706 items), B=128, L=50, fp32, InfoNCE with
+    the in-batch shared pool — compute_embeds + loss + backward against the numpy oracle
+    (the lean oracle at B=128; the verbatim (M, 1+M, D) tensor would need 2 x 63 GB)."""
+    b = orc.synth_batch(3706, 128, 50, dim=384, seed=0)
+    emb = xr.models.ItemEmbeddings(torch.from_numpy(b["table"]), add_padding_row=False).cuda()
+    tok = torch.from_numpy(b["token_embeddings"]).cuda().requires_grad_(True)
+    hist, pos, neg = (torch.from_numpy(b[k]).cuda() for k in
+                      ("history_item_idx", "pos_item_idx", "neg_item_idx"))
+    out = xr.models.compute_embeds(emb, tok, hist, pos, neg)
+    want = orc.compute_embeds(b["table"], b["token_embeddings"], b["history_item_idx"],
+                              b["pos_item_idx"], b["neg_item_idx"], dense=False)
+    assert np.array_equal(out["query_embed"].detach().cpu().numpy(), want["query_embed"])
+    assert np.array_equal(out["candidate_embed"].neg.cpu().numpy(), want["neg_embed"])
+    loss = xr.InfoNCELoss(xr.LossConfig())(out["query_embed"], out["candidate_embed"])
+    loss.backward()
+    ref, dq, _, _ = orc.lean_loss("InfoNCELoss", want["query_embed"], want["pos_embed"],
+                                  want["neg_embed"], orc.Config(), with_grad=True)
+    assert float(loss) == pytest.approx(ref, rel=FP32_REL)
+    mask = (b["history_item_idx"].reshape(-1) != 0) & (b["pos_item_idx"].reshape(-1) != 0)
+    g = tok.grad.reshape(-1, 384).cpu().numpy()
+    assert not g[~mask].any()
+    assert_close_grad(g[mask], dq, FP32_REL)
+
+
+def test_evaluate_batch_equals_per_user_loop(xr):
+    """the batched validation loop gives, user by user, what the reference's
+    validation_step computes (search with the history excluded, then the 7 metrics), and the
+    epoch means over the users that have targets."""
+    rng = np.random.default_rng(5)
+    n, u, k = 5000, 37, 20
+    cat = rng.standard_normal((n, 384)).astype(np.float32)
+    qs = rng.standard_normal((u, 384)).astype(np.float32)
+    hist = [list(map(int, rng.integers(0, n, size=int(rng.integers(0, 40))))) for _ in range(u)]
+    tgts = [list(map(int, rng.integers(0, n, size=int(rng.integers(0, 6))))) for _ in range(u)]
+    tgts[3] = []                                   # a user without targets: no metrics logged
+    ws, wi = orc.exact_search(qs, cat, k, hist, metric="cosine")
+    tgts[5] = [int(wi[5, 0]), int(wi[5, 7])]       # guaranteed hits
+    idx = xr.index.ExactIndex(xr.index.ExactIndexConfig(index_metric="cosine", dtype="fp32")).set_catalog(
+        torch.from_numpy(cat).cuda())
+    means, per_user, valid, rec = xr.evaluate.evaluate_batch(idx, torch.from_numpy(qs).cuda(), hist, tgts, k)
+    assert np.array_equal(rec.cpu().numpy(), wi)
+    names = xr.metrics.METRIC_NAMES
+    acc = np.zeros(7)
+    cnt = 0
+    for r in range(u):
+        want = orc.retrieval_metrics([str(x) for x in wi[r]], {str(x) for x in tgts[r]}, k)
+        assert bool(valid[r]) == bool(want)
+        if want:
+            got = per_user[r].cpu().numpy()
+            for j, name in enumerate(names):
+                assert got[j] == pytest.approx(want[name], rel=1e-5, abs=1e-6), (r, name)
+            acc += [want[name] for name in names]
+            cnt += 1
+    for j, name in enumerate(names):
+        assert float(means[f"val/{name}"]) == pytest.approx(acc[j] / cnt, rel=1e-5, abs=1e-6)

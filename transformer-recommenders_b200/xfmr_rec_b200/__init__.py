@@ -5,13 +5,14 @@ yxtay/transformer-recommenders behind the reference's own Python interfaces.
     models   compute_embeds of xfmr_rec/models.py:366-419 without the O(M^2 D) candidate copy
     index    exact full-catalog search with the LanceIndex.search surface (index.py:214-255)
     metrics  compute_retrieval_metrics of xfmr_rec/metrics.py:17-79 (+ batched device version)
+    evaluate batched validation loop: exact search with history excluded + the 7 metrics for U users
     dist     catalog sharding + NCCL all-gather merge, data-parallel loss reduction
     step     the whole scoring-and-loss train step as one sync-free, CUDA-graph-replayed call
     ops      tensor-level wrappers over the C ABI (include/xfmr_b200.h)
 """
 
 from . import _native, ops  # noqa: F401
-from . import dist, index, losses, metrics, models, params, step  # noqa: F401
+from . import dist, evaluate, index, losses, metrics, models, params, step  # noqa: F401
 from .losses import (  # noqa: F401
     LOSS_CLASSES,
     AlignmentContrastiveLoss,
