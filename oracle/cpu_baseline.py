@@ -8,6 +8,14 @@ tensor does not fit host RAM at the benchmark shape (62.9 GB per c
 so this is the "reference-lean" form of BASELINE.md §4: the reference's own
 check_target / mask_false_negatives / loss bodies (losses.py:289-292, 483-488) applied to
 ``[rowdot(q,pos) | Q.Neg^T]`` logits, forward + backward to dL/dquery, fp32.
+
+Two things to know about this port (oracle/time_reference_verbatim.py runs both on the build
+container, results in profiles/cpu_reference_r01.json): (1) it is 21-43x FASTER than the
+reference's own code path on the same CPU (the expand + cat of models.py:408-410 and the bmm over
+the materialised tensor dominate the reference), so the reported CPU baseline is conservative;
+(2) the positive logit comes from a row dot, not from the same GEMM as the pool logits, so a pool
+entry that IS the row's positive does not tie bit-exactly and may survive the `<` mask - a
+timing stand-in only; parity is judged against oracle/xfmr_oracle.py, which keeps exact ties.
 """
 
 from __future__ import annotations
