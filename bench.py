@@ -91,7 +91,7 @@ class ClockSampler:
                     self.rows.append((time.time(), row))
                 except Exception:
                     pass
-                time.sleep(0.002)
+                time.sleep(self.period)
 
         self.thread = threading.Thread(target=pump, daemon=True)
         self.thread.start()
@@ -102,6 +102,7 @@ class ClockSampler:
         ids = [x.strip() for x in vis.split(",")] if vis else []
         phys = ids[self.gpu] if self.gpu < len(ids) and ids[self.gpu].isdigit() else str(self.gpu)
         self.thread = None
+        self.period = float(os.environ.get("XR_BENCH_CLOCK_PERIOD_MS", "2")) / 1e3
         if self._start_nvml(int(phys)):
             return
         try:
@@ -228,17 +229,29 @@ def main():
     from oracle import xfmr_oracle as orc  # synthetic inputs + cpu_baseline leg only
 
     all_cpus = os.sched_getaffinity(0)
-    if world > 1:
+    if world > 1 and not os.environ.get("XR_BENCH_NO_BIND"):
         bind_to_gpu_numa_node(local_rank)   # pinned staging buffers land next to this rank's GPU
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     peak_tf, peak_hbm, peak_src = load_peaks()
 
-    # ---- synthetic inputs, per-rank seed = rank: weak scaling ----------------------
-    batch = orc.synth_batch(N_ITEMS, BATCH, SEQ_LEN, dim=DIM, seed=rank)
+    # ---- synthetic inputs, weak scaling ---------------------------------------------
+    # every rank gets the SAME sequence-length profile (so M, M_a and therefore the work per rank
+    # are identical: weak scaling measures the machine, not the luck of the length draw) but its
+    # own items and encoder outputs: a rank-specific permutation of the item ids and fresh tokens
+    batch = orc.synth_batch(N_ITEMS, BATCH, SEQ_LEN, dim=DIM, seed=0)
+    if rank > 0:
+        rng = np.random.default_rng(1000 + rank)
+        perm = np.concatenate([[0], rng.permutation(N_ITEMS) + 1]).astype(np.int64)
+        for key in ("history_item_idx", "pos_item_idx", "neg_item_idx"):
+            batch[key] = perm[batch[key]]
+        batch["token_embeddings"] = (rng.standard_normal(batch["token_embeddings"].shape)
+                                     / math.sqrt(DIM)).astype(np.float32)
     emb = xr.models.ItemEmbeddings(torch.from_numpy(batch["table"]), add_padding_row=False).to(dev)
     emb.weight_bf16(), emb.rownz()
     host = {k: torch.from_numpy(batch[k]).pin_memory() for k in
@@ -274,9 +287,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(ms):
+    per_rank = {}
+
+    def max_over_ranks(ms, tag=None):
         if world > 1:
             t = torch.tensor([ms], device=dev)
+            if tag:
+                allt = [torch.zeros_like(t) for _ in range(world)]
+                dist.all_gather(allt, t)
+                per_rank[tag] = [round(float(x), 4) for x in allt]
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t)
         return ms
@@ -300,7 +319,7 @@ def main():
         barrier()
         sampler.mark_end()
         clocks = sampler.stop()
-        return max_over_ranks(a.elapsed_time(b)), clocks, last
+        return max_over_ranks(a.elapsed_time(b), "value_region_ms"), clocks, last
 
     def timed_e2e(steps, warmup):
         """e2e: every step copies its inputs from pinned host memory and reads the loss back.
@@ -322,7 +341,7 @@ def main():
         vals = loop(steps)
         b.record()
         barrier()
-        return max_over_ranks(a.elapsed_time(b)), vals
+        return max_over_ranks(a.elapsed_time(b), "e2e_region_ms"), vals
 
     def timed_modular(steps, warmup, profile):
         for _ in range(warmup):
@@ -399,6 +418,7 @@ def main():
                      "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step if kern_ms else None,
                      "algorithmic_flops_per_launch": flops},
         "loss": loss_val,
+        "per_rank_region_ms": per_rank or None,
         "module_api": {"value": world * BATCH / (mod_ms / args.steps / 1e3), "unit": "seq/s",
                        "ms_per_step": mod_ms / args.steps,
                        "note": "same step through compute_embeds + InfoNCELoss + backward (the "

@@ -954,7 +954,7 @@ using namespace xr;
 
 namespace xr {
 int launch_score_gmax2(const void* q, int64_t u, const void* catalog, int64_t n, float* gmax, int64_t ld,
-                       int* hang_flag, cudaStream_t s);
+                       int* hang_flag, cudaStream_t s, int ablate);
 }
 static bool g_gmax_single = false;   // profiling aid: force the single-CTA retrieval kernel
 
@@ -1321,7 +1321,7 @@ extern "C" int xr_score_groupmax(const void* q, int64_t u, const void* catalog, 
   const bool prof = g_prof_on && g_prof_n < kProfRing;
   if (prof) cudaEventRecord(g_prof_ev[g_prof_n][0], s);
   if (u > fk::BM && !g_gmax_single)   // CTA pairs: 256 queries per pair, half the catalog bytes per SM
-    rc = launch_score_gmax2(q, u, catalog, n, gmax, ld, hang, s);
+    rc = launch_score_gmax2(q, u, catalog, n, gmax, ld, hang, s, g_ablate);
   else
     rc = launch_fused1<fk::KIND_GMAX, false>(tq, tc, p, grid, s);
   if (prof) cudaEventRecord(g_prof_ev[g_prof_n++][1], s);

@@ -44,6 +44,7 @@ struct Gmax2Params {
   float* gmax;
   long long gmax_ld;
   int* hang_flag;
+  int ablate;   // DBG instantiation only: 1 skip catalog TMA, 2 skip epilogue TMEM loads, 4 skip gmax stores, 8 skip MMAs
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -96,6 +97,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & g2::PEER_MASK) : "memory");
 }
 
+template <bool DBG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::THREADS, 1)
 score_gmax2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                    const Gmax2Params p) {
@@ -169,10 +171,14 @@ score_gmax2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           const uint32_t s = g & (PAIRS - 1);
           mbar_wait(bar_empty(s), ((g / PAIRS) & 1) ^ 1, p.hang_flag, 2);
           if (elect_one()) {
-            if (leader) mbar_expect_tx(bar_full(s), 2 * 2 * SUB_BYTES);
-            const int row0 = t * BN + (int)rank * BNH;
-            tma_load_2d_2sm(ring + s * 2 * SUB_BYTES, &tmap_c, bar_full(s), pr * 128, row0);
-            tma_load_2d_2sm(ring + s * 2 * SUB_BYTES + SUB_BYTES, &tmap_c, bar_full(s), pr * 128 + 64, row0);
+            if (DBG && (p.ablate & 1)) {
+              if (leader) mbar_arrive(bar_full(s));
+            } else {
+              if (leader) mbar_expect_tx(bar_full(s), 2 * 2 * SUB_BYTES);
+              const int row0 = t * BN + (int)rank * BNH;
+              tma_load_2d_2sm(ring + s * 2 * SUB_BYTES, &tmap_c, bar_full(s), pr * 128, row0);
+              tma_load_2d_2sm(ring + s * 2 * SUB_BYTES + SUB_BYTES, &tmap_c, bar_full(s), pr * 128 + 64, row0);
+            }
           }
           __syncwarp();
         }
@@ -199,6 +205,7 @@ score_gmax2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           const uint32_t s = (g + pr) & (PAIRS - 1);
           const uint64_t a0 = q_desc0 + (uint64_t)(pr * ((2 * QSUB_BYTES) >> 4));
           const uint64_t b0 = ring_desc0 + (uint64_t)(s * ((2 * SUB_BYTES) >> 4));
+          if (!(DBG && (p.ablate & 8)))
 #pragma unroll
           for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -245,8 +252,13 @@ score_gmax2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         mbar_wait(bar_s_full(sb), (tile / NSB) & 1, p.hang_flag, 8);
         tc_fence_after();
         uint32_t v[32];
-        tmem_ld32(tmem_lane + sb * BN + cg * 32, v);
-        tmem_wait_ld();
+        if (DBG && (p.ablate & 2)) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = tile + j;
+        } else {
+          tmem_ld32(tmem_lane + sb * BN + cg * 32, v);
+          tmem_wait_ld();
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(bar_s_free(sb));   // the logits are in registers
@@ -257,7 +269,7 @@ score_gmax2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           if (c0 + j < p.n) m0 = fmaxf(m0, __uint_as_float(v[j]));
           if (c0 + 16 + j < p.n) m1 = fmaxf(m1, __uint_as_float(v[16 + j]));
         }
-        if (row_ok) *reinterpret_cast<float2*>(out_row + (long long)t * (BN / 16) + cg * 2) = make_float2(m0, m1);
+        if (row_ok && !(DBG && (p.ablate & 4))) *reinterpret_cast<float2*>(out_row + (long long)t * (BN / 16) + cg * 2) = make_float2(m0, m1);
       }
     }
   }
@@ -274,7 +286,7 @@ int make_tmap_bf16_rows(CUtensorMap* out, const void* base, int64_t rows, int64_
 
 // host: called by xr_score_groupmax for u > 128
 int launch_score_gmax2(const void* q, int64_t u, const void* catalog, int64_t n, float* gmax, int64_t ld,
-                       int* hang_flag, cudaStream_t s) {
+                       int* hang_flag, cudaStream_t s, int ablate) {
   using namespace g2;
   const int n_sm = sm_count();
   const int n_clusters = n_sm / 2;
@@ -308,11 +320,14 @@ int launch_score_gmax2(const void* q, int64_t u, const void* catalog, int64_t n,
   if ((rc = make_tmap_bf16_rows(&tc, catalog, n, D, D, BNH))) return rc;
   static bool configured = false;
   if (!configured) {
-    XR_CUDA(cudaFuncSetAttribute(score_gmax2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    XR_CUDA(cudaFuncSetAttribute(score_gmax2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    XR_CUDA(cudaFuncSetAttribute(score_gmax2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
   int pairs = p.n_items < n_clusters ? p.n_items : n_clusters;
-  score_gmax2_kernel<<<2 * pairs, THREADS, SMEM_BYTES, s>>>(tq, tc, p);
+  p.ablate = ablate;
+  if (ablate) score_gmax2_kernel<true><<<2 * pairs, THREADS, SMEM_BYTES, s>>>(tq, tc, p);   // timing experiments
+  else score_gmax2_kernel<false><<<2 * pairs, THREADS, SMEM_BYTES, s>>>(tq, tc, p);
   XR_LAUNCH_CHECK("score_gmax2_kernel");
   return XR_OK;
 }
