@@ -277,7 +277,13 @@ int xr_mask_excluded_ids(float* scores, const int64_t* ids, int64_t u, int64_t c
  * rows of each group: cols (u, kg*16) local rows for the re-score gather (0 where there is no such
  * row), ids (u, kg*16) global row ids = local + row_offset, -1 where there is no such row.     */
 int xr_groups_to_rows(const int64_t* group_ids, int64_t u, int64_t kg, int64_t n, int64_t row_offset,
-                      int64_t* cols, int64_t* ids, void* stream);
+                      int64_t layout, int64_t* cols, int64_t* ids, void* stream);
+/* layout of xr_score_groupmax's output for (u, n): 0 = natural (storage column g = catalog rows
+ * [16 g, 16 g + 16)); > 0 = the CTA-pair kernel's layout with that stride (column
+ * cg * 2 L + 2 t + h = rows [128 t + 32 cg + 16 h, +16)); pass it to xr_groups_to_rows.
+ * xr_score_groupmax_ld = columns the output needs (all of them are written).                    */
+int xr_score_groupmax_layout(int64_t u, int64_t n);
+int64_t xr_score_groupmax_ld(int64_t u, int64_t n);
 
 /* fused tcgen05 scoring + top-k over one catalog shard (bf16, dim 384): scores = Q . Cat^T on the
  * tensor cores, threshold-filtered selection in the epilogue, no (U,N) score matrix in HBM.

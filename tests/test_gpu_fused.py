@@ -200,10 +200,11 @@ def test_groupmax_retrieval_random_cosine(xr):
     assert recall >= 0.999, recall
 
 
-@pytest.mark.parametrize("u,n", [(129, 1000), (256, 12800), (300, 4097), (1000, 130), (513, 64)])
+@pytest.mark.parametrize("u,n", [(129, 1000), (256, 12800), (300, 4097), (1000, 130), (513, 64), (260, 70000)])
 def test_groupmax_cta_pair_kernel_matches_reference(xr, u, n):
     """u > 128 runs on CTA pairs (tcgen05 cta_group::2, 256 queries per pair); group maxima must
-    equal the maxima of the fp32-accumulated scores and agree with the single-CTA variant."""
+    equal the maxima of the fp32-accumulated scores and agree with the single-CTA variant.  The
+    pair kernel stores them as [column group][tile][half] (xr_score_groupmax_layout)."""
     from xfmr_rec_b200 import _native as N, ops
 
     g = torch.Generator(device="cuda").manual_seed(u * 7 + n)
@@ -212,16 +213,24 @@ def test_groupmax_cta_pair_kernel_matches_reference(xr, u, n):
     ng = (n + 15) // 16
     want = torch.full((u, ng * 16), float("-inf"), device="cuda")
     want[:, :n] = q.float() @ cat.float().T
-    want = want.view(u, ng, 16).amax(-1)
+    want = want.view(u, ng, 16).amax(-1)                       # natural order: group g = rows [16g, 16g+16)
     lib = N.lib()
-    got_pair = ops.score_groupmax(q, cat)[:, :ng].clone()
+    got_pair, layout = ops.score_groupmax(q, cat)
+    assert layout > 0 and got_pair.size(1) == 8 * layout
+    # storage slot c = cg * 2L + 2t + h  ->  group (128 t + 32 cg + 16 h) / 16
+    c = torch.arange(got_pair.size(1), device="cuda")
+    cg, rem = c // (2 * layout), c % (2 * layout)
+    grp = (rem // 2) * 8 + cg * 2 + (rem % 2)
+    live = grp < ng
+    natural = torch.full((u, ng), float("nan"), device="cuda")
+    natural[:, grp[live]] = got_pair[:, live]
+    torch.testing.assert_close(natural, want, rtol=2e-3, atol=2e-3)
+    assert bool((got_pair[:, ~live] == float("-inf")).all())   # slots past the catalog: never selected
     lib.xr_fused_wait_stats(4, None)          # profiling switch: force the single-CTA kernel
     try:
-        got_single = ops.score_groupmax(q, cat)[:, :ng].clone()
+        got_single, layout1 = ops.score_groupmax(q, cat)
+        got_single = got_single[:, :ng].clone()
     finally:
         lib.xr_fused_wait_stats(0, None)
-    torch.testing.assert_close(got_pair, want, rtol=2e-3, atol=2e-3)
+    assert layout1 == 0
     torch.testing.assert_close(got_single, want, rtol=2e-3, atol=2e-3)
-    # every group beyond the catalog is -inf (never selected)
-    full = ops.score_groupmax(q, cat)
-    assert bool((full[:, ng:8 * ((n + 127) // 128)] == float("-inf")).all())

@@ -955,6 +955,7 @@ using namespace xr;
 namespace xr {
 int launch_score_gmax2(const void* q, int64_t u, const void* catalog, int64_t n, float* gmax, int64_t ld,
                        int* hang_flag, cudaStream_t s, int ablate);
+int gmax2_nt_pad(int64_t n);
 }
 static bool g_gmax_single = false;   // profiling aid: force the single-CTA retrieval kernel
 
@@ -1283,6 +1284,17 @@ extern "C" int xr_pool_step(const int64_t* history_idx, const int64_t* pos_idx,
 // group maximum of a row is a lower bound of its k-th largest score, and every score above it
 // lives in a group whose maximum is above it: the exact top-k only needs the top groups to be
 // re-scored (index.py:244-254 semantics, exact).  The (U, N) score matrix never reaches HBM.
+// Layout of the group maxima: 0 = natural (storage column g holds catalog rows [16 g, 16 g + 16)),
+// otherwise the pair kernel's layout with stride nt_pad: storage column c = cg * 2 nt_pad + 2 t + h
+// holds catalog rows [128 t + 32 cg + 16 h, +16).  xr_groups_to_rows takes the same number.
+extern "C" int xr_score_groupmax_layout(int64_t u, int64_t n) {
+  return (u > fk::BM && !g_gmax_single) ? gmax2_nt_pad(n) : 0;
+}
+extern "C" int64_t xr_score_groupmax_ld(int64_t u, int64_t n) {
+  const int nt_pad = xr_score_groupmax_layout(u, n);
+  return nt_pad ? 8 * (int64_t)nt_pad : 4 * ((n + fk::BN - 1) / fk::BN);
+}
+
 extern "C" int xr_score_groupmax(const void* q, int64_t u, const void* catalog, int64_t n,
                                  int64_t dim, float* gmax, int64_t ld, void* stream) {
   XR_CHECK_ARG(q && catalog && gmax, "xr_score_groupmax: null pointer");
@@ -1290,8 +1302,10 @@ extern "C" int xr_score_groupmax(const void* q, int64_t u, const void* catalog, 
   XR_CHECK_ARG(u > 0 && n > 0 && u < (1ll << 30) && n < (1ll << 31), "xr_score_groupmax: bad sizes");
   const int64_t nt = (n + fk::BN - 1) / fk::BN;
   XR_CHECK_ARG(ld >= nt * fk::CG, "xr_score_groupmax: ld must be >= 4 * ceil(n / 64)");
-  XR_CHECK_ARG(u <= fk::BM || (ld >= 8 * ((n + 127) / 128) && ld % 2 == 0 && (uintptr_t)gmax % 8 == 0),
-               "xr_score_groupmax: for u > 128, ld must be even and >= 8 * ceil(n / 128), gmax 8-byte aligned");
+  XR_CHECK_ARG(u <= fk::BM || g_gmax_single ||
+                   (ld >= 8 * gmax2_nt_pad(n) && ld % 4 == 0 && (uintptr_t)gmax % 16 == 0),
+               "xr_score_groupmax: for u > 128, ld must be a multiple of 4 and >= xr_score_groupmax_ld(u, n), "
+               "gmax 16-byte aligned");
   XR_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)catalog % 16 == 0),
                "xr_score_groupmax: operands must be 16-byte aligned");
   int dev = 0, major = 0;

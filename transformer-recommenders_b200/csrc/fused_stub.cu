@@ -31,3 +31,5 @@ extern "C" int xr_pool_step(const int64_t*, const int64_t*, const int64_t*, int6
   xr::set_error("xr_pool_step: tcgen05 kernels not compiled into this build");
   return XR_E_UNSUPPORTED;
 }
+extern "C" int xr_score_groupmax_layout(int64_t, int64_t) { return 0; }
+extern "C" int64_t xr_score_groupmax_ld(int64_t, int64_t n) { return 4 * ((n + 63) / 64); }

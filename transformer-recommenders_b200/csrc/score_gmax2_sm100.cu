@@ -40,7 +40,7 @@ constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // shared::cluster address of the 
 }  // namespace g2
 
 struct Gmax2Params {
-  int u, n, nt_count, spl, tiles_per_split, n_items, qb_count;
+  int u, n, nt_count, nt_pad, spl, tiles_per_split, n_items, qb_count;
   float* gmax;
   long long gmax_ld;
   int* hang_flag;
@@ -94,7 +94,10 @@ __device__ __forceinline__ void umma_commit2(uint32_t bar) {
 }
 // arrive on the LEADER's copy of a barrier, from either CTA of the pair
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & g2::PEER_MASK) : "memory");
+  // relaxed at cluster scope: a release.cluster arrive flushes L1 (~1,250 cycles, microbench
+  // tma_stream.cu); all this arrive publishes is "my tcgen05.ld has completed" (wait::ld before it)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & g2::PEER_MASK)
+               : "memory");
 }
 
 template <bool DBG>
@@ -247,6 +250,7 @@ score_gmax2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       const int row = qb * 2 * BM + (int)rank * BM + r_local;
       const bool row_ok = row < p.u;
       float* out_row = p.gmax + (long long)row * p.gmax_ld;
+      float buf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       for (int t = t0; t < t1; ++t, ++tile) {
         const int sb = tile % NSB;
         mbar_wait(bar_s_full(sb), (tile / NSB) & 1, p.hang_flag, 8);
@@ -269,7 +273,30 @@ score_gmax2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           if (c0 + j < p.n) m0 = fmaxf(m0, __uint_as_float(v[j]));
           if (c0 + 16 + j < p.n) m1 = fmaxf(m1, __uint_as_float(v[16 + j]));
         }
-        if (row_ok && !(DBG && (p.ablate & 4))) *reinterpret_cast<float2*>(out_row + (long long)t * (BN / 16) + cg * 2) = make_float2(m0, m1);
+        // "pair layout": row u stores its maxima as [column group cg][tile t][half h], so the two
+        // values a lane produces per tile are contiguous ACROSS tiles: four tiles are buffered and
+        // leave as two 16-byte stores (whole 32-byte sectors) instead of four scattered 8-byte ones
+        const int k = (t - t0) & 3;
+        if (k == 0) { buf[0] = m0; buf[1] = m1; }
+        else if (k == 1) { buf[2] = m0; buf[3] = m1; }
+        else if (k == 2) { buf[4] = m0; buf[5] = m1; }
+        else { buf[6] = m0; buf[7] = m1; }
+        const bool last = t == t1 - 1;
+        if ((k == 3 || last) && row_ok && !(DBG && (p.ablate & 4))) {
+          float* dst = out_row + (long long)cg * (2 * p.nt_pad) + 2 * (t - k);   // t0 is a multiple of 4
+          if (k == 3) {
+            *reinterpret_cast<float4*>(dst) = make_float4(buf[0], buf[1], buf[2], buf[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(buf[4], buf[5], buf[6], buf[7]);
+          } else {
+            *reinterpret_cast<float2*>(dst) = make_float2(buf[0], buf[1]);
+            if (k >= 1) *reinterpret_cast<float2*>(dst + 2) = make_float2(buf[2], buf[3]);
+            if (k >= 2) *reinterpret_cast<float2*>(dst + 4) = make_float2(buf[4], buf[5]);
+          }
+          if (last && t == p.nt_count - 1)   // padding tiles of the layout: never selected
+            for (int tp = p.nt_count; tp < p.nt_pad; ++tp)
+              *reinterpret_cast<float2*>(out_row + (long long)cg * (2 * p.nt_pad) + 2 * tp) =
+                  make_float2(-CUDART_INF_F, -CUDART_INF_F);
+        }
       }
     }
   }
@@ -283,6 +310,9 @@ score_gmax2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 
 int make_tmap_bf16_rows(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld_elems,
                         int box_rows);
+
+// tiles of 128 catalog rows, padded to a multiple of 2: the layout stride 2 * nt_pad stays 16-byte aligned
+int gmax2_nt_pad(int64_t n) { return (int)(((n + g2::BN - 1) / g2::BN + 1) / 2 * 2); }
 
 // host: called by xr_score_groupmax for u > 128
 int launch_score_gmax2(const void* q, int64_t u, const void* catalog, int64_t n, float* gmax, int64_t ld,
@@ -311,7 +341,9 @@ int launch_score_gmax2(const void* q, int64_t u, const void* catalog, int64_t n,
     if (items > 8LL * n_clusters) break;
   }
   p.tiles_per_split = (p.nt_count + best_spl - 1) / best_spl;
+  p.tiles_per_split = (p.tiles_per_split + 3) / 4 * 4;   // items start on a multiple of 4 tiles (16-byte stores)
   p.spl = (p.nt_count + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.nt_pad = gmax2_nt_pad(n);
   p.n_items = p.qb_count * p.spl;
   p.gmax = gmax; p.gmax_ld = ld; p.hang_flag = hang_flag;
   CUtensorMap tq, tc;

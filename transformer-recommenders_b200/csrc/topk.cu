@@ -366,12 +366,17 @@ __global__ void mask_excluded_ids_kernel(float* __restrict__ scores, const int64
 // group ids (U, kg) from the top-k over the group maxima -> the 16 catalog rows of every group:
 // local row numbers for the re-score gather (clamped into [0, n)) and global ids (-1 = no such row)
 __global__ void groups_to_rows_kernel(const int64_t* __restrict__ gi, int64_t total, int64_t n,
-                                      int64_t row_offset, int64_t* __restrict__ cols,
+                                      int64_t row_offset, int64_t nt_pad, int64_t* __restrict__ cols,
                                       int64_t* __restrict__ ids) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t g = gi[e >> 4];
-    const int64_t c = g * 16 + (e & 15);
+    int64_t first = g * 16;                       // natural layout
+    if (nt_pad > 0 && g >= 0) {                   // pair layout: [column group][tile][half]
+      const int64_t cg = g / (2 * nt_pad), rem = g - cg * 2 * nt_pad;
+      first = (rem >> 1) * 128 + cg * 32 + (rem & 1) * 16;
+    }
+    const int64_t c = first + (e & 15);
     const bool ok = g >= 0 && c < n;
     cols[e] = ok ? c : 0;
     ids[e] = ok ? c + row_offset : -1;
@@ -576,14 +581,15 @@ extern "C" int xr_mask_excluded_ids(float* scores, const int64_t* ids, int64_t u
 }
 
 extern "C" int xr_groups_to_rows(const int64_t* group_ids, int64_t u, int64_t kg, int64_t n,
-                                 int64_t row_offset, int64_t* cols, int64_t* ids, void* stream) {
+                                 int64_t row_offset, int64_t layout, int64_t* cols, int64_t* ids,
+                                 void* stream) {
   XR_CHECK_ARG(group_ids && cols && ids && u >= 0 && kg >= 0 && n > 0, "xr_groups_to_rows: bad arguments");
   const int64_t total = u * kg * 16;
   if (total == 0) return XR_OK;
   int64_t blocks = (total + 255) / 256;
   if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
   groups_to_rows_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(group_ids, total, n, row_offset,
-                                                                         cols, ids);
+                                                                         layout, cols, ids);
   XR_LAUNCH_CHECK("groups_to_rows");
   return XR_OK;
 }

@@ -144,9 +144,10 @@ class ExactIndex:
         largest score and every score above it sits in a group above it; `kg` adds one group per
         excluded id plus a margin, so the result equals the full scan."""
         n = cat.size(0)
-        gmax = ops.score_groupmax(q, cat)
-        _, gi = ops.topk(gmax, kg, n=(n + 15) // 16)                 # (U, kg) group ids, -1 = none
-        cols, ids = ops.groups_to_rows(gi, n, self.row_offset)
+        gmax, layout = ops.score_groupmax(q, cat)
+        n_slots = gmax.size(1) if layout else (n + 15) // 16         # every slot of the pair layout is written
+        _, gi = ops.topk(gmax, kg, n=n_slots)                        # (U, kg) group slots, -1 = none
+        cols, ids = ops.groups_to_rows(gi, n, self.row_offset, layout)
         scores = ops.logits_sampled(q, cat, cols)
         ops.mask_excluded_ids(scores, ids, self.row_offset, self.row_offset + n, csr)
         return ops.topk_merge(scores, ids, top_k)

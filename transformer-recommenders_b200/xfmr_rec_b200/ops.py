@@ -383,14 +383,15 @@ def score_groupmax(q, catalog):
     q, catalog = q.contiguous(), catalog.contiguous()
     u, d = q.shape
     n = catalog.size(0)
-    ld = 8 * ((n + 127) // 128)   # >= ceil(n / 16) groups; both kernel variants fit
+    layout = int(N.lib().xr_score_groupmax_layout(u, n))   # 0 natural, else the pair kernel's stride
+    ld = int(N.lib().xr_score_groupmax_ld(u, n))
     gmax = torch.empty((u, ld), dtype=torch.float32, device=dev)
     with _on(dev):
         N.call("xr_score_groupmax", _p(q), u, _p(catalog), n, d, _p(gmax), ld, _stream())
-    return gmax
+    return gmax, layout
 
 
-def groups_to_rows(group_ids, n, row_offset=0):
+def groups_to_rows(group_ids, n, row_offset=0, layout=0):
     """(U, kg) group ids -> (cols, ids), both (U, kg*16) int64: gather rows and global ids (-1 = none)."""
     dev = _require_cuda(group_ids)
     group_ids = group_ids.contiguous()
@@ -398,7 +399,8 @@ def groups_to_rows(group_ids, n, row_offset=0):
     cols = torch.empty((u, kg * 16), dtype=torch.int64, device=dev)
     ids = torch.empty((u, kg * 16), dtype=torch.int64, device=dev)
     with _on(dev):
-        N.call("xr_groups_to_rows", _p(group_ids), u, kg, n, row_offset, _p(cols), _p(ids), _stream())
+        N.call("xr_groups_to_rows", _p(group_ids), u, kg, n, row_offset, layout, _p(cols), _p(ids),
+               _stream())
     return cols, ids
 
 
