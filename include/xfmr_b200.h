@@ -208,6 +208,22 @@ int xr_fused_pool_loss(const void* q, const void* pos, const void* neg, int64_t 
                        const float* q_inv_norm, float grad_scale, float* dq, double* loss_out,
                        float* row_loss, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- family 2d: every loss of one logit family + LogitsStatistics in one tensor-core pass ----
+ * RecommenderLightningModule.compute_losses (trainer.py:250-263) evaluates LogitsStatistics
+ * (losses.py:383-405) and all seven losses on every training step: eight logit computations in
+ * the reference.  This call produces, forward only and without materialising the logits,
+ *   cosine == 0 (q/pos/neg as given, dot logits, losses.py:195): InfoNCE, NCE, PairwiseHinge,
+ *                PairwiseLogistic and the statistics block;
+ *   cosine != 0 (q/pos/neg pre-normalised rows, losses.py:206-208): Alignment, Contrastive,
+ *                AlignmentContrastive (statistics: density / counts / positives only --
+ *                LogitsStatistics is defined on the dot logits, losses.py:383-386),
+ * in the same float64[XR_NUM_LOSSES] / float64[XR_STATS_SLOTS] layout as xr_rowloss; entries
+ * of the other family are meaningless (as with xr_rowloss).  num_hard_negatives must be 0.   */
+size_t xr_fused_pool_all_workspace_bytes(int64_t m, int64_t cn, int64_t dim);
+int xr_fused_pool_all(const void* q, const void* pos, const void* neg, int64_t m, int64_t cn,
+                      int64_t dim, int cosine, const xr_loss_config* cfg, double* losses_out,
+                      double* stats_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- the whole scoring-and-loss step, sync-free ----------------------------------------------
  * RecommenderModel.compute_embeds (models.py:388-416) + EmbedLoss.forward (losses.py:128-155)
  * + the backward to the encoder output (autograd of models.py:392, 415), for ONE SeqBatch of

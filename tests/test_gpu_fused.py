@@ -234,3 +234,85 @@ def test_groupmax_cta_pair_kernel_matches_reference(xr, u, n):
         lib.xr_fused_wait_stats(0, None)
     assert layout1 == 0
     torch.testing.assert_close(got_single, want, rtol=2e-3, atol=2e-3)
+
+
+def _cfg(ops, logits_bf16=False, **kw):
+    class C:
+        pass
+
+    c = C()
+    for k, v in {**dict(mask_false_negatives=True, num_hard_negatives=0, scale=1.0, margin=0.5), **kw}.items():
+        setattr(c, k, v)
+    return ops.make_cfg(c, logits_bf16=logits_bf16)
+
+
+DOT_SLOTS = ["InfoNCELoss", "NCELoss", "PairwiseHingeLoss", "PairwiseLogisticLoss"]
+COS_SLOTS = ["AlignmentLoss", "ContrastiveLoss", "AlignmentContrastiveLoss"]
+
+
+@pytest.mark.parametrize("m,cn", [(1, 1), (128, 64), (130, 65), (301, 777), (700, 3000), (1500, 4200)])
+def test_fused_all_losses_and_stats_one_pass(xr, m, cn):
+    """xr_fused_pool_all: every loss of a logit family + the LogitsStatistics block from ONE
+    tensor-core pass (trainer.py:250-263) vs the oracle on the bf16 operands the kernel saw, and
+    vs the library's own materialised path (xr_logits_pool + xr_rowloss)."""
+    from xfmr_rec_b200 import _native as N, ops
+
+    q, pos, neg = make_inputs(m, cn, seed=m * 3 + cn)
+    for cfg_kw, lbf in [({}, True), ({"scale": 8.0, "margin": 0.2}, True), ({"mask_false_negatives": False}, False)]:
+        for cosine in (False, True):
+            lb = lbf and not cosine
+            cfg = _cfg(ops, logits_bf16=lb, **cfg_kw)
+            qt, pt, nt = bf(q), bf(pos), bf(neg)
+            if cosine:
+                qt, pt, nt = (ops.normalize_rows(torch.from_numpy(x).cuda(), 1e-8, torch.bfloat16)[0]
+                              for x in (q, pos, neg))
+            losses, stats = ops.fused_pool_all(qt, pt, nt, cfg, cosine)
+            # the materialised path of the same library on the same operands
+            logits = ops.logits_pool(qt, pt, nt)
+            l2, s2, _ = ops.rowloss(logits, cn + 1, cfg, N.TARGET_LAST, None, -1, want_stats=True)
+            losses, stats, l2, s2 = (t.cpu().numpy() for t in (losses, stats, l2, s2))
+            names = COS_SLOTS if cosine else DOT_SLOTS
+            for name in names:
+                k = N.LOSS_KIND[name]
+                assert losses[k] == pytest.approx(l2[k], rel=2e-3, abs=2e-3), (name, cfg_kw, cosine)
+            # oracle on the bf16 operands
+            qh, ph, nh = (t.float().cpu().numpy() for t in (qt, pt, nt))
+            ocfg = orc.Config(**cfg_kw)
+            lg = orc.lean_logits(qh, ph, nh)
+            lg = (orc.round_bf16(lg.astype(np.float32)) if lb else lg.astype(np.float32)).astype(np.float64)
+            tgt = np.zeros(m, np.int64)
+            mask = orc.mask_false_negatives(lg, tgt, ocfg)
+            for name in names:
+                want = orc.loss_from_logits(name, lg, tgt, mask, ocfg, with_grad=False)
+                assert losses[N.LOSS_KIND[name]] == pytest.approx(want, rel=2e-3, abs=2e-3), (name, cfg_kw)
+            # statistics block: density, rows, pos {sum, sumsq, min, max}, neg {count, sum, sumsq, min, max}
+            assert stats[1] == m and stats[11] == cn
+            # counts depend on '<' decisions at fp32-accumulation-order resolution: allow a few flips
+            assert abs(stats[6] - s2[6]) <= max(2.0, 2e-4 * s2[6]), (stats[6], s2[6])
+            np.testing.assert_allclose(stats[[0, 2, 3]], s2[[0, 2, 3]], rtol=2e-3, atol=2e-2)
+            np.testing.assert_allclose(stats[[4, 5]], s2[[4, 5]], rtol=1e-3, atol=1e-3)
+            if cosine:   # negative-logit statistics exist for the dot family only (losses.py:383-386)
+                continue
+            np.testing.assert_allclose(stats[[7, 8]], s2[[7, 8]], rtol=2e-3, atol=2e-2)
+            if s2[6] > 0:
+                np.testing.assert_allclose(stats[[9, 10]], s2[[9, 10]], rtol=1e-3, atol=2e-3)
+
+
+def test_evaluate_all_uses_two_passes_and_matches_modules(xr):
+    """evaluate_all (= compute_losses, trainer.py:213-264): same numbers as the seven loss modules
+    and LogitsStatistics called one by one."""
+    q, pos, neg = make_inputs(300, 1000, seed=11)
+    cfg = xr.LossConfig()
+    qt = bf(q).requires_grad_(True)
+    cand = xr.PoolCandidates(bf(pos), bf(neg))
+    out, stats = xr.losses.evaluate_all(cfg, qt, cand)
+    out["loss/InfoNCELoss"].backward()
+    assert qt.grad is not None and bool(torch.isfinite(qt.grad).all())
+    for name in orc.LOSS_NAMES:
+        want = float(getattr(xr, name)(cfg)(bf(q), cand))
+        assert float(out[f"loss/{name}"]) == pytest.approx(want, rel=2e-3, abs=2e-3), name
+    lb = orc.round_bf16(orc.lean_logits(orc.round_bf16(q), orc.round_bf16(pos), orc.round_bf16(neg)).astype(np.float32)).astype(np.float64)
+    tgt = np.zeros(q.shape[0], np.int64)
+    want_stats = orc.logits_statistics(lb, tgt, orc.mask_false_negatives(lb, tgt, orc.Config()), orc.Config())
+    for k, v in want_stats.items():
+        assert stats[k] == pytest.approx(v, rel=5e-3, abs=5e-3), k

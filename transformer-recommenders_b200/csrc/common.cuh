@@ -42,6 +42,16 @@ int sm_count();
 
 constexpr int kWarp = 32;
 
+// per-row slots (doubles) the loss passes leave for rowloss_reduce_kernel: the six per-row loss
+// values (losses.py:352-372, 420-543) and the LogitsStatistics ingredients (losses.py:383-405)
+constexpr int ROW_SLOTS = 20;
+enum RowSlot {
+  S_ALIGN = 0, S_CONTR, S_INFONCE, S_NCE, S_HINGE, S_LOGISTIC,
+  S_DENS, S_POS, S_NCOUNT, S_NSUM, S_NSQ, S_NMIN, S_NMAX, S_USED
+};
+int launch_rowloss_reduce(const double* row_out, int64_t m, int64_t c, int n_hard, double* losses_out,
+                          double* stats_out, cudaStream_t s);
+
 // ---- small device helpers --------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -59,7 +59,10 @@ constexpr int COL_O = 0, COL_S = 384;   // S: one 64-column buffer with the grad
 constexpr int COL_W = 448;              // W: two 32-column buffers of packed bf16 weights (gradient pass)
 constexpr int KIND_DIAG = 100;      // extract q_i . pos_i from the diagonal of Q_blk . Pos_blk^T
 constexpr int KIND_GMAX = 101;      // retrieval: max score of every 16-column group (no loss)
+constexpr int KIND_ALL_DOT = 102;   // forward of every dot-family loss + LogitsStatistics in one pass
+constexpr int KIND_ALL_COS = 103;   // forward of the cosine-family losses (+ statistics of the cosine logits)
 constexpr int NSCAL = 4;
+constexpr int NSCAL_ALL = 12;       // per (item, column group, row) scalars of the ALL kinds
 }  // namespace fk
 
 // shape + plan of one launch when they are only known on the device (xr_pool_step: the row counts
@@ -78,6 +81,7 @@ struct FusedParams {
   float* t_out;        // [m]                                      (KIND_DIAG)
   float* part_o;       // [n_items][128][384]
   float* part_s;       // [n_items][128][NSCAL]
+  float* part_all;     // [n_items][CG][128][NSCAL_ALL]            (KIND_ALL_*)
   float* gmax;         // [m][gmax_ld] group maxima                (KIND_GMAX)
   long long gmax_ld;
   int rb_count;
@@ -170,6 +174,59 @@ __device__ __forceinline__ void group_math(const uint32_t (&v)[16], uint32_t (&p
   }
 }
 
+// per-row accumulators of the ALL kinds (trainer.py:250-263 evaluates LogitsStatistics and all
+// seven losses every step; here ONE pass over the logits of a family feeds all of them)
+struct AllAcc {
+  float cnt, s_exp, s_sp, s_hinge, s_logi, s_contr, s_v, s_sq, vmin, vmax;
+  __device__ __forceinline__ void reset() {
+    cnt = s_exp = s_sp = s_hinge = s_logi = s_contr = s_v = s_sq = 0.f;
+    vmin = CUDART_INF_F;
+    vmax = -CUDART_INF_F;
+  }
+};
+
+// one column group (16 logits of one row) for the ALL kinds.  softplus(x) = relu(x) + ln(1 + e^-|x|);
+// the 16 factors (1 + e^-|x|) lie in (1, 2], so their PRODUCT (<= 65536) is taken first and one
+// lg2 per group replaces sixteen (the MUFU unit bounds this epilogue).
+template <bool COS, bool RBF, bool FULL>
+__device__ __forceinline__ void group_all(const uint32_t (&v)[16], int ncols, float t_eff, float tm,
+                                          float zref2, float scale2, float scale, float margin,
+                                          bool round_scaled, AllAcc& a) {
+  float prod_nce = 1.f, prod_logi = 1.f, relu_nce = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float l = __uint_as_float(v[j]);
+    if (RBF) l = bf16_round(l);
+    bool ok = l < t_eff;
+    if (!FULL) ok = ok && (j < ncols);
+    a.cnt += ok ? 1.f : 0.f;
+    if (COS) {   // LogitsStatistics is defined on the dot logits (losses.py:383-386): no neg stats here
+      a.s_contr += ok ? fmaxf(l - 1.0f + margin, 0.f) : 0.f;
+    } else {
+      const float lm = ok ? l : 0.f;
+      a.s_v += lm;
+      a.s_sq = fmaf(lm, lm, a.s_sq);
+      a.vmin = fminf(a.vmin, ok ? l : CUDART_INF_F);
+      a.vmax = fmaxf(a.vmax, ok ? l : -CUDART_INF_F);
+      float z2;
+      if (round_scaled) z2 = bf16_round(l * scale) * kLog2e;
+      else z2 = l * scale2;
+      a.s_exp += ok ? ex2f(z2 - zref2) : 0.f;
+      const float u1 = ex2f(-fabsf(l) * kLog2e);
+      prod_nce *= ok ? 1.0f + u1 : 1.0f;
+      relu_nce += ok ? fmaxf(l, 0.f) : 0.f;
+      const float x = l - tm;
+      const float u2 = ex2f(-fabsf(x) * kLog2e);
+      prod_logi *= ok ? 1.0f + u2 : 1.0f;
+      a.s_hinge += ok ? fmaxf(x, 0.f) : 0.f;
+    }
+  }
+  if (!COS) {
+    a.s_sp += relu_nce + lg2f(prod_nce) * kLn2;
+    a.s_logi += lg2f(prod_logi) * kLn2;   // + s_hinge (the relu part) in the finalize
+  }
+}
+
 template <int KIND, bool RBF, int DBG>
 __global__ void __launch_bounds__(fk::THREADS, 1)
 fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
@@ -206,7 +263,8 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
     const int4 b = __ldg(reinterpret_cast<const int4*>(p.dyn) + 1);
     sh = FusedDyn{a.x, a.y, a.z, a.w, b.x, b.y, b.z, 0};
   }
-  const bool grad = !diag && KIND != KIND_GMAX && p.with_grad;
+  constexpr bool all_kind = (KIND == KIND_ALL_DOT || KIND == KIND_ALL_COS);
+  const bool grad = !diag && KIND != KIND_GMAX && !all_kind && p.with_grad;
   // S buffers: ONE with the gradient pass (the other 64 columns hold the W double buffer), two without
   const int nsb_shift = grad ? 0 : 1;
 
@@ -442,6 +500,8 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
       t_eff = p.mask_fn ? t : CUDART_INF_F;
       float cnt = 0.f, sum_a = 0.f, sum_w = 0.f, diag_val = 0.f;
+      AllAcc acc;
+      acc.reset();
       for (int tl = 0; tl < T; ++tl) {
         const uint32_t tile = tt + tl;
         const uint32_t use = tile >> nsb_shift;
@@ -482,6 +542,14 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
           for (int j = 0; j < 16; ++j)
             if (j < ncols) mx = fmaxf(mx, __uint_as_float(v[j]));
           if (row_ok) p.gmax[(long long)row * p.gmax_ld + (long long)rot_tile(t0, T, rb, tl) * CG + cg] = mx;
+        } else if (all_kind) {
+          const int ncols = sh.cn - rot_tile(t0, T, rb, tl) * BN - cg * 16;
+          if (ncols >= 16)
+            group_all<KIND == KIND_ALL_COS, RBF, true>(v, ncols, t_eff, tm, zref2, scale2, p.scale,
+                                                       p.margin, round_scaled, acc);
+          else
+            group_all<KIND == KIND_ALL_COS, RBF, false>(v, ncols, t_eff, tm, zref2, scale2, p.scale,
+                                                        p.margin, round_scaled, acc);
         } else {
           const int ncols = sh.cn - rot_tile(t0, T, rb, tl) * BN - cg * 16;   // valid candidates in this group
           uint32_t pk[8];
@@ -521,6 +589,14 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (row_ok && (r_local & 63) >> 4 == cg) p.t_out[row] = diag_val;
       } else if (KIND == KIND_GMAX) {
         // nothing to flush: the group maxima were written tile by tile
+      } else if (all_kind) {
+        if (row_ok) {
+          float4* ds = reinterpret_cast<float4*>(
+              p.part_all + (((size_t)item * CG + cg) * BM + r_local) * NSCAL_ALL);
+          ds[0] = make_float4(acc.cnt, acc.s_exp, acc.s_sp, acc.s_hinge);
+          ds[1] = make_float4(acc.s_logi, acc.s_contr, acc.s_v, acc.s_sq);
+          ds[2] = make_float4(acc.vmin, acc.vmax, 0.f, 0.f);
+        }
       } else {
         if (grad) {
           mbar_wait<STATS>(bar_o_full, it & 1, p.hang_flag, 9);
@@ -707,6 +783,59 @@ fused_finalize_kernel(const float* __restrict__ part_o, const float* __restrict_
       }
     }
   }
+}
+
+// ---- finalize of the ALL kinds: fold the per-item scalars of every row (fixed order) into the row
+//      slots rowloss_reduce_kernel sums -- the same slots, formulas and float/double mix as
+//      rowloss_kernel (rowloss.cu), which is the materialised-logits implementation of this pass ----
+__global__ void __launch_bounds__(256)
+fused_finalize_all_kernel(const float* __restrict__ part_all, const float* __restrict__ t_raw,
+                          const float* __restrict__ zref, int m, int spl, int cosine, int logits_bf16,
+                          float scale, float margin, double* __restrict__ row_out) {
+  using namespace fk;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const int rb = i / BM, rl = i % BM;
+  double cnt = 0, s_exp = 0, s_sp = 0, s_hinge = 0, s_logi = 0, s_contr = 0, s_v = 0, s_sq = 0;
+  float vmin = CUDART_INF_F, vmax = -CUDART_INF_F;
+  for (int sp = 0; sp < spl; ++sp) {
+    const size_t item = (size_t)rb * spl + sp;
+#pragma unroll
+    for (int cg = 0; cg < CG; ++cg) {
+      const float4* src = reinterpret_cast<const float4*>(part_all + ((item * CG + cg) * BM + rl) * NSCAL_ALL);
+      const float4 a = src[0], b = src[1], c = src[2];
+      cnt += a.x; s_exp += a.y; s_sp += a.z; s_hinge += a.w;
+      s_logi += b.x; s_contr += b.y; s_v += b.z; s_sq += b.w;
+      vmin = fminf(vmin, c.x);
+      vmax = fmaxf(vmax, c.y);
+    }
+  }
+  float t = t_raw[i];
+  if (logits_bf16) t = bf16_round(t);
+  const float den = (float)cnt + 1e-9f;
+  double* o = row_out + (size_t)i * ROW_SLOTS;
+  o[S_ALIGN] = 1.0 - (double)t;
+  o[S_CONTR] = s_contr / (double)den;
+  double infonce = 0, nce = 0, hinge = 0, logi = 0;
+  if (!cosine) {
+    const float st = (logits_bf16 && scale != 1.0f) ? bf16_round(t * scale) : t * scale;
+    const float zr = zref ? zref[i] : st;
+    infonce = (double)zr + log(s_exp + (double)__expf(st - zr)) - (double)st;
+    nce = (double)(fmaxf(-t, 0.f) + log1pf(__expf(-fabsf(t)))) + s_sp / (double)den;
+    hinge = s_hinge / (double)den;
+    logi = (s_hinge + s_logi) / (double)den;
+  }
+  o[S_INFONCE] = infonce;
+  o[S_NCE] = nce;
+  o[S_HINGE] = hinge;
+  o[S_LOGISTIC] = logi;
+  o[S_DENS] = cnt;
+  o[S_POS] = (double)t;
+  o[S_NCOUNT] = cnt;
+  o[S_NSUM] = s_v;
+  o[S_NSQ] = s_sq;
+  o[S_NMIN] = (double)vmin;
+  o[S_NMAX] = (double)vmax;
 }
 
 // single block, fixed order: loss = sum_i row_loss[i]   (double accumulation)
@@ -1129,6 +1258,80 @@ extern "C" int xr_fused_pool_loss(const void* q, const void* pos, const void* ne
   const FusedWs ws = carve_fused_ws(workspace, m, pl.n_items);
   return fused_launch_all(q, pos, neg, m, cn, loss_kind, cfg, q_inv_norm, grad_scale, dq, loss_out,
                           row_loss, ws, false, as_stream(stream));
+}
+
+// ---- every loss of one logit family + LogitsStatistics in ONE pass over the pool ----------------
+// trainer.py:250-263 evaluates LogitsStatistics and all seven losses on every training step (eight
+// logit computations in the reference).  Forward only: diagonal pass -> [softmax reference bound]
+// -> fused_pool_kernel<KIND_ALL_*> -> fused_finalize_all_kernel -> rowloss_reduce_kernel, filling
+// the same losses[7] / stats[16] blocks as xr_rowloss does from materialised logits.
+// the per-item scalars (CG x 128 x NSCAL_ALL floats) alias the partial-dQ region (128 x 384 floats),
+// which the forward-only ALL kinds never write; the row slots follow the fused workspace
+static_assert(fk::CG * fk::NSCAL_ALL <= fk::D, "ALL-kind scalars must fit the partial-dQ region");
+static size_t fused_all_extra_bytes(long long m) { return align256((size_t)m * ROW_SLOTS * 8); }
+
+extern "C" size_t xr_fused_pool_all_workspace_bytes(int64_t m, int64_t cn, int64_t dim) {
+  if (dim != fk::D || m <= 0 || cn <= 0) return 512;
+  const FusedPlan pl = make_plan(m, cn, sm_count());
+  return carve_fused_ws(nullptr, m, pl.n_items).bytes + fused_all_extra_bytes(m);
+}
+
+extern "C" int xr_fused_pool_all(const void* q, const void* pos, const void* neg, int64_t m,
+                                 int64_t cn, int64_t dim, int cosine, const xr_loss_config* cfg,
+                                 double* losses_out, double* stats_out, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  XR_CHECK_ARG(q && pos && neg && cfg && losses_out && workspace, "xr_fused_pool_all: null pointer");
+  XR_CHECK_ARG(dim == fk::D, "xr_fused_pool_all: this build is specialised for dim = %d", fk::D);
+  XR_CHECK_ARG(m > 0 && cn > 0 && m < (1ll << 30) && cn < (1ll << 30), "xr_fused_pool_all: bad sizes");
+  XR_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)pos % 16 == 0) && ((uintptr_t)neg % 16 == 0),
+               "xr_fused_pool_all: operands must be 16-byte aligned");
+  XR_CHECK_ARG(cfg->num_hard_negatives == 0, "xr_fused_pool_all: hard-negative mining needs the materialised path");
+  XR_CHECK_ARG(cosine || cfg->scale > 0.f, "xr_fused_pool_all: InfoNCE needs scale > 0");
+  XR_CHECK_ARG(workspace_bytes >= xr_fused_pool_all_workspace_bytes(m, cn, dim),
+               "xr_fused_pool_all: workspace too small");
+  int rc;
+  if ((rc = check_fused_device("xr_fused_pool_all"))) return rc;
+  cudaStream_t s = as_stream(stream);
+  const int n_sm = sm_count();
+  const FusedPlan pl = make_plan(m, cn, n_sm);
+  const FusedWs ws = carve_fused_ws(workspace, m, pl.n_items);
+  double* row_out = (double*)((uint8_t*)workspace + ws.bytes);
+  XR_CUDA(cudaMemsetAsync(ws.flags, 0, 256, s));
+
+  CUtensorMap tq, tp, tn;
+  if ((rc = make_tmap_bf16_rows(&tq, q, m, fk::D, fk::D, fk::BM))) return rc;
+  if ((rc = make_tmap_bf16_rows(&tp, pos, m, fk::D, fk::D, fk::BN))) return rc;
+  if ((rc = make_tmap_bf16_rows(&tn, neg, cn, fk::D, fk::D, fk::BN))) return rc;
+  FusedParams pd{};
+  pd.m = (int)m; pd.cn = (int)m; pd.nt_count = 0; pd.spl = 1; pd.tiles_per_split = 2;
+  pd.n_items = pl.rb; pd.t_out = ws.t; pd.hang_flag = ws.flags;
+  if ((rc = launch_fused<fk::KIND_DIAG>(tq, tp, pd, pl.rb < n_sm ? pl.rb : n_sm, s))) return rc;
+  const float* zref = nullptr;
+  if (!cosine && !cfg->mask_false_negatives) {
+    unsigned* nmax = (unsigned*)(ws.flags + 8);
+    negnorm_max_kernel<<<n_sm * 4, 256, 0, s>>>((const __nv_bfloat16*)neg, cn, nmax, nullptr);
+    XR_LAUNCH_CHECK("negnorm_max");
+    zref_bound_kernel<<<n_sm * 4, 256, 0, s>>>((const __nv_bfloat16*)q, ws.t, nmax, m, cfg->scale,
+                                               cfg->logits_bf16, ws.zref, nullptr);
+    XR_LAUNCH_CHECK("zref_bound");
+    zref = ws.zref;
+  }
+  FusedParams p{};
+  p.m = (int)m; p.cn = (int)cn; p.nt_count = pl.nt; p.spl = pl.spl; p.tiles_per_split = pl.tps;
+  p.n_items = pl.n_items; p.mask_fn = cfg->mask_false_negatives; p.logits_bf16 = cfg->logits_bf16;
+  p.with_grad = 0; p.scale = cfg->scale; p.margin = cfg->margin;
+  p.t = ws.t; p.zref = zref; p.part_all = ws.part_o; p.hang_flag = ws.flags;
+  const int grid = pl.n_items < n_sm ? pl.n_items : n_sm;
+  const bool prof = g_prof_on && g_prof_n < kProfRing;
+  if (prof) cudaEventRecord(g_prof_ev[g_prof_n][0], s);
+  rc = cosine ? launch_fused<fk::KIND_ALL_COS>(tq, tn, p, grid, s)
+              : launch_fused<fk::KIND_ALL_DOT>(tq, tn, p, grid, s);
+  if (prof) cudaEventRecord(g_prof_ev[g_prof_n++][1], s);
+  if (rc) return rc;
+  fused_finalize_all_kernel<<<(int)((m + 255) / 256), 256, 0, s>>>(
+      ws.part_o, ws.t, zref, (int)m, pl.spl, cosine, cfg->logits_bf16, cfg->scale, cfg->margin, row_out);
+  XR_LAUNCH_CHECK("fused_finalize_all");
+  return launch_rowloss_reduce(row_out, m, cn + 1, 0, losses_out, stats_out, s);
 }
 
 // ---- the whole scoring-and-loss step, sync-free -------------------------------------------------

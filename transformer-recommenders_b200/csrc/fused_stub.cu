@@ -33,3 +33,9 @@ extern "C" int xr_pool_step(const int64_t*, const int64_t*, const int64_t*, int6
 }
 extern "C" int xr_score_groupmax_layout(int64_t, int64_t) { return 0; }
 extern "C" int64_t xr_score_groupmax_ld(int64_t, int64_t n) { return 4 * ((n + 63) / 64); }
+extern "C" size_t xr_fused_pool_all_workspace_bytes(int64_t, int64_t, int64_t) { return 0; }
+extern "C" int xr_fused_pool_all(const void*, const void*, const void*, int64_t, int64_t, int64_t, int,
+                                 const xr_loss_config*, double*, double*, void*, size_t, void*) {
+  xr::set_error("xr_fused_pool_all: tcgen05 kernels not compiled into this build");
+  return XR_E_UNSUPPORTED;
+}

@@ -13,12 +13,6 @@ namespace xr {
 
 constexpr int RL_THREADS = 256;
 constexpr int RL_WARPS = RL_THREADS / 32;
-constexpr int ROW_SLOTS = 20;  // doubles per row in the workspace
-
-enum RowSlot {
-  S_ALIGN = 0, S_CONTR, S_INFONCE, S_NCE, S_HINGE, S_LOGISTIC,  // per-row loss values
-  S_DENS, S_POS, S_NCOUNT, S_NSUM, S_NSQ, S_NMIN, S_NMAX, S_USED
-};
 
 __device__ __forceinline__ double block_sum(double v, double* s_buf) {
   v = warp_sum(v);
@@ -342,6 +336,14 @@ rowloss_reduce_kernel(const double* __restrict__ row_out, int64_t m, int64_t c, 
       for (int k = 12; k < XR_STATS_SLOTS; ++k) stats_out[k] = 0.0;
     }
   }
+}
+
+// shared with the tensor-core all-losses pass (fused_loss_sm100.cu), which fills the same row slots
+int launch_rowloss_reduce(const double* row_out, int64_t m, int64_t c, int n_hard, double* losses_out,
+                          double* stats_out, cudaStream_t s) {
+  rowloss_reduce_kernel<<<1, 1024, 0, s>>>(row_out, m, c, n_hard, losses_out, stats_out);
+  XR_LAUNCH_CHECK("rowloss_reduce");
+  return XR_OK;
 }
 
 static inline int rl_grid(int64_t m) {

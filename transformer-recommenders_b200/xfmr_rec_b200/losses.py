@@ -287,6 +287,11 @@ class EmbedLoss(torch.nn.Module, abc.ABC):
             q, pos, neg = (t.to(cdt).contiguous() for t in (q, pos, neg))
         fused_ok = (not want_stats and cfg.num_hard_negatives == 0 and neg.size(0) > 0
                     and type(self).__name__ in _FUSED_KINDS and ops.fused_pool_supported(q, neg))
+        if (want_stats and grad_kind < 0 and cfg.num_hard_negatives == 0 and neg.size(0) > 0
+                and ops.fused_pool_supported(q, neg)):
+            # every loss of this logit family + the statistics block from ONE tensor-core pass
+            losses, stats = ops.fused_pool_all(q, pos, neg, cfg, self.COSINE)
+            return losses, stats, None
         if fused_ok:
             loss, dq, _ = ops.fused_pool_loss(q, pos, neg, kind, cfg, q_inv=q_inv,
                                               want_grad=grad_kind >= 0)

@@ -295,6 +295,25 @@ def fused_pool_loss(q, pos, neg, loss_kind, cfg, q_inv=None, grad_scale=1.0, wan
     return loss, dq, row_loss
 
 
+def fused_pool_all(q, pos, neg, cfg, cosine):
+    """Forward of every loss of one logit family + the LogitsStatistics block in one tcgen05 pass
+    (xr_fused_pool_all).  bf16 inputs (pre-normalised rows when ``cosine``).
+    Returns (losses f64[7], stats f64[16]) as ``rowloss`` does."""
+    dev = _require_cuda(q, pos, neg)
+    assert q.dtype == pos.dtype == neg.dtype == torch.bfloat16
+    q, pos, neg = q.contiguous(), pos.contiguous(), neg.contiguous()
+    m, d = q.shape
+    cn = neg.size(0)
+    losses = torch.empty(N.XR_NUM_LOSSES, dtype=torch.float64, device=dev)
+    stats = torch.empty(N.XR_STATS_SLOTS, dtype=torch.float64, device=dev)
+    nbytes = N.lib().xr_fused_pool_all_workspace_bytes(m, cn, d)
+    ws = _ws(nbytes, dev)
+    with _on(dev):
+        N.call("xr_fused_pool_all", _p(q), _p(pos), _p(neg), m, cn, d, int(bool(cosine)),
+               C.byref(cfg), _p(losses), _p(stats), _p(ws), ws.numel(), _stream())
+    return losses, stats
+
+
 # ---------------------------------------------------------------------------------------------
 # family 3: scores / top-k / metrics
 # ---------------------------------------------------------------------------------------------
