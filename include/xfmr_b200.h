@@ -182,6 +182,26 @@ int xr_dq_sampled(const float* dlogits, int64_t ld, const void* q, const void* t
                   int dtype, const float* table_inv_norm, const float* q_inv_norm, float* dq,
                   void* stream);
 
+/* ---- SeqBatch construction (the step right before the path) ---------------
+ * SeqDataset.__getitem__ + collate (data.py:669-805) for a whole batch in one launch:
+ * sample_sequence (:669-689), sample_positives (:691-721), sample_negatives (:723-747),
+ * zero right-padding (:787-805).  Inputs are the per-user event histories in CSR form, resident
+ * on the device:
+ *   hist_off[H+1], items[total] (1-based item idx), labels[total], pos_prefix[total] (inclusive
+ *   count of positive labels inside each history), uniq_off[H+1] / uniq_items (ascending unique
+ *   items of each history), row_hist[R] (dataset row -> history, data.py:618-636; NULL = identity),
+ *   rows[n_batch] (the dataset rows of this batch).
+ * Outputs: history_out / pos_out / neg_out int64 (n_batch, max_seq_length), 0-padded;
+ *   seq_len_out int32[n_batch] (nullable).
+ * Randomness: Philox4x32-10 keyed by (seed, step, dataset row): deterministic, independent of
+ * the batch composition; oracle/xfmr_oracle.py:seq_sample_batch reproduces it bit for bit.     */
+int xr_seq_sample_batch(const int64_t* hist_off, const int64_t* items, const uint8_t* labels,
+                        const int32_t* pos_prefix, const int64_t* uniq_off,
+                        const int64_t* uniq_items, const int64_t* row_hist, const int64_t* rows,
+                        int64_t n_batch, int64_t n_items, int max_seq_length, int pos_lookahead,
+                        uint64_t seed, uint64_t step, int64_t* history_out, int64_t* pos_out,
+                        int64_t* neg_out, int32_t* seq_len_out, void* stream);
+
 /* ---- family 2c: fused contraction + loss + gradient (tcgen05/TMEM, bf16) -------------------
  * One pass over the shared negative pool: S = Q.Neg^T on the 5th-gen tensor cores, the loss
  * epilogue on the TMEM accumulator, dQ += W.Neg as a second UMMA — the M x C logits never

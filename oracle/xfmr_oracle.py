@@ -543,3 +543,210 @@ def synth_batch(n_items, batch, seq_len, dim=384, seed=0, pos_pad_frac=0.05, tab
     tokens = (rng.standard_normal((batch, seq_len, dim)) / math.sqrt(dim)).astype(np.float32)
     return {"table": table, "history_item_idx": hist, "pos_item_idx": pos,
             "neg_item_idx": neg, "token_embeddings": tokens}
+
+
+# ---------------------------------------------------------------------------
+# SeqBatch construction — SeqDataset.__getitem__ + collate, data.py:669-805
+# (SURVEY §8f rank 2).  Two layers:
+#   * seq_sample_batch: the SAME counter-based algorithm as csrc/seqbatch.cu in plain Python
+#     integers (Philox4x32-10 keyed by (seed, step, row)) -> bit-exact parity of the kernel;
+#   * check_seq_example: the reference's support constraints for one example (which positions /
+#     positives / negatives data.py:669-747 can ever return), independent of any RNG.
+# The reference draws from numpy's default_rng() (unseeded, data.py:574), so no fixed stream
+# exists to match: parity is support + distribution, pinned by the constraints below.
+# ---------------------------------------------------------------------------
+_M32 = 0xFFFFFFFF
+_M64 = 0xFFFFFFFFFFFFFFFF
+
+
+def _splitmix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
+    return x ^ (x >> 31)
+
+
+def philox4x32_10(counter, key):
+    """Philox4x32-10 (Salmon, Moraes, Dror, Shaw 2011).  counter: 4 words, key: 2 words."""
+    c0, c1, c2, c3 = (int(c) & _M32 for c in counter)
+    k0, k1 = (int(k) & _M32 for k in key)
+    for _ in range(10):
+        p0 = 0xD2511F53 * c0
+        p1 = 0xCD9E8D57 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & _M32, p1 & _M32, ((p0 >> 32) ^ c3 ^ k1) & _M32, p0 & _M32
+        k0 = (k0 + 0x9E3779B9) & _M32
+        k1 = (k1 + 0xBB67AE85) & _M32
+    return c0, c1, c2, c3
+
+
+def _uniform_below(words, n: int) -> int:
+    return ((((words[0] << 32) | words[1]) * n) >> 64)
+
+
+def seq_sample_example(history_item_idx, history_label, row, n_items, max_seq_length, pos_lookahead,
+                       seed, step):
+    """One example of data.py:749-785 with the device algorithm's randomness.
+    Returns (history[sel], positives, negatives) as int64 arrays of length seq_len."""
+    hist = np.asarray(history_item_idx, np.int64)
+    lab = np.asarray(history_label, bool)
+    n = len(hist)
+    key64 = _splitmix64(_splitmix64((seed ^ _splitmix64(step)) & _M64) ^ (row & _M64))
+    key = (key64 & _M32, key64 >> 32)
+    cand = max(n - 1, 0)
+    L = max_seq_length
+    # sample_sequence (data.py:669-689): all positions, or the L smallest random keys, sorted
+    if cand <= L:
+        sel = list(range(cand))
+    else:
+        keys = [philox4x32_10((p, 0, 0, 0), key)[0] for p in range(cand)]
+        order = sorted(range(cand), key=lambda p: (keys[p], p))
+        sel = sorted(order[:L])
+    seq_len = len(sel)
+    prefix = np.cumsum(lab.astype(np.int64))
+    # sample_positives (data.py:691-721)
+    positives = np.zeros(seq_len, np.int64)
+    for i, idx in enumerate(sel):
+        start = idx + 1
+        end = min(n, start + pos_lookahead) if pos_lookahead > 0 else n
+        base = int(prefix[start - 1])
+        cnt = int(prefix[end - 1]) - base if end > start else 0
+        if cnt > 0:
+            r = _uniform_below(philox4x32_10((i, 0, 1, 0), key), cnt)
+            j = int(np.searchsorted(prefix[start:end], base + 1 + r, side="left")) + start
+            positives[i] = hist[j]
+    # sample_negatives (data.py:723-747)
+    uniq = np.unique(hist)
+    n_cand = n_items - len(uniq)
+    if n_cand <= 0:
+        n_cand, uniq = n_items, uniq[:0]
+
+    def draw(i, att):
+        rank = _uniform_below(philox4x32_10((i, att, 2, 0), key), n_cand)
+        # rank-th item (0-based) not in the history: smallest k with uniq[k] - 1 - k > rank
+        k = int(np.searchsorted(uniq - 1 - np.arange(len(uniq)), rank, side="right"))
+        return rank + 1 + k
+
+    negatives = np.zeros(seq_len, np.int64)
+    if n_cand < seq_len:  # replace=True (data.py:745-747)
+        for i in range(seq_len):
+            negatives[i] = draw(i, 0)
+    else:
+        taken: set[int] = set()
+        attempt = [0] * seq_len
+        pending = list(range(seq_len))
+        while pending:
+            claims: dict[int, int] = {}
+            drawn = {}
+            for i in pending:
+                v = draw(i, attempt[i])
+                drawn[i] = v
+                if v not in taken and (v not in claims or i < claims[v]):
+                    claims[v] = i
+            nxt = []
+            for i in pending:
+                v = drawn[i]
+                if v not in taken and claims[v] == i:
+                    negatives[i] = v
+                else:
+                    attempt[i] += 1
+                    nxt.append(i)
+            taken.update(claims)
+            pending = nxt
+    return hist[sel] if seq_len else hist[:0], positives, negatives
+
+
+def seq_sample_batch(histories, labels, rows, n_items, max_seq_length, pos_lookahead, seed, step,
+                     row_hist=None):
+    """Batch + collate (data.py:787-805): right-padded with 0 to ``max_seq_length`` columns."""
+    B, L = len(rows), max_seq_length
+    out = {k: np.zeros((B, L), np.int64) for k in ("history_item_idx", "pos_item_idx", "neg_item_idx")}
+    lens = np.zeros(B, np.int32)
+    for b, row in enumerate(rows):
+        h = int(row_hist[row]) if row_hist is not None else int(row)
+        hs, ps, ns = seq_sample_example(histories[h], labels[h], int(row), n_items, L, pos_lookahead,
+                                        seed, step)
+        lens[b] = len(hs)
+        out["history_item_idx"][b, :len(hs)] = hs
+        out["pos_item_idx"][b, :len(hs)] = ps
+        out["neg_item_idx"][b, :len(hs)] = ns
+    out["seq_len"] = lens
+    return out
+
+
+def check_seq_example(history_item_idx, history_label, hist_out, pos_out, neg_out, n_items,
+                      max_seq_length, pos_lookahead):
+    """Support constraints of data.py:669-747 for ONE example (arrays already stripped of padding).
+    Raises AssertionError with the violated rule."""
+    hist = np.asarray(history_item_idx, np.int64)
+    lab = np.asarray(history_label, bool)
+    n = len(hist)
+    seq_len = min(max(n - 1, 0), max_seq_length)
+    assert len(hist_out) == len(pos_out) == len(neg_out) == seq_len, "sequence length (data.py:683-689)"
+    # the sampled history is an order-preserving subsequence of hist[:-1]; recover one embedding
+    # greedily and validate positives against EVERY embedding-consistent position set lazily:
+    # positions are identifiable when items are distinct; otherwise any consistent position works
+    pos_sets = []
+    j = 0
+    for v in hist_out:
+        while j < n - 1 and hist[j] != v:
+            j += 1
+        assert j < n - 1, "history is not a subsequence of the user's events (data.py:687-689)"
+        pos_sets.append(j)
+        j += 1
+    if n - 1 <= max_seq_length:
+        assert pos_sets == list(range(n - 1)), "short histories are taken whole (data.py:685-686)"
+    all_hist = set(hist.tolist())
+    for i, idx in enumerate(pos_sets):
+        start = idx + 1
+        end = start + pos_lookahead if pos_lookahead > 0 else None
+        cands = hist[start:end][lab[start:end]]
+        if len(cands) == 0:
+            # with duplicate items the greedy embedding may differ from the sampled one; accept a
+            # positive only if SOME occurrence of this item has it in its window
+            ok = pos_out[i] == 0
+            if not ok:
+                for alt in np.flatnonzero(hist[:n - 1] == hist_out[i]):
+                    s2 = alt + 1
+                    e2 = s2 + pos_lookahead if pos_lookahead > 0 else None
+                    if pos_out[i] in set(hist[s2:e2][lab[s2:e2]].tolist()):
+                        ok = True
+            assert ok, "positive for a position with no future positive must be 0 (data.py:710-721)"
+        else:
+            ok = pos_out[i] in set(cands.tolist())
+            if not ok:
+                for alt in np.flatnonzero(hist[:n - 1] == hist_out[i]):
+                    s2 = alt + 1
+                    e2 = s2 + pos_lookahead if pos_lookahead > 0 else None
+                    c2 = set(hist[s2:e2][lab[s2:e2]].tolist())
+                    if (pos_out[i] in c2) or (pos_out[i] == 0 and not c2):
+                        ok = True
+            assert ok, "positive must be a positively-labelled event in the window (data.py:712-719)"
+    neg_cands = set(range(1, n_items + 1)) - all_hist
+    if not neg_cands:
+        neg_cands = set(range(1, n_items + 1))
+    assert set(neg_out.tolist()) <= neg_cands, "negatives must avoid the history (data.py:739-742)"
+    if len(neg_cands) >= seq_len:
+        assert len(set(neg_out.tolist())) == seq_len, "negatives are drawn without replacement (data.py:745-747)"
+
+
+def seq_example_reference_style(rng, history_item_idx, history_label, all_idx, max_seq_length, pos_lookahead):
+    """data.py:669-785 written as the reference writes it (numpy Generator, Python loop over the
+    sampled positions, set difference over the whole catalog) — the CPU timing baseline of the
+    device sampler and a second source for distribution comparisons."""
+    hist = np.asarray(history_item_idx)
+    lab = np.asarray(history_label, bool)
+    indices = np.arange(len(hist) - 1)                                   # data.py:683
+    if len(indices) > max_seq_length:                                    # data.py:685-689
+        indices = np.sort(rng.choice(indices, size=max_seq_length, replace=False))
+    positives = np.zeros_like(indices)                                   # data.py:710-721
+    for i, idx in enumerate(indices):
+        start = idx + 1
+        end = start + pos_lookahead if pos_lookahead > 0 else None
+        cands = hist[start:end][lab[start:end]]
+        if len(cands) > 0:
+            positives[i] = rng.choice(cands)
+    neg_candidates = list(all_idx - set(hist.tolist()))                  # data.py:739-747
+    if len(neg_candidates) == 0:
+        neg_candidates = list(all_idx)
+    negatives = rng.choice(neg_candidates, len(indices), replace=len(neg_candidates) < len(indices))
+    return hist[indices], positives, negatives

@@ -63,6 +63,8 @@ PROTOTYPES = {
     "xr_dq_pool": (_int, [_p, _i64, _p, _p, _p, _i64, _i64, _i64, _int, _int, _p, _p, _p]),
     "xr_dq_dense": (_int, [_p, _i64, _p, _p, _i64, _i64, _i64, _int, _int, _p, _p, _p, _p]),
     "xr_dq_sampled": (_int, [_p, _i64, _p, _p, _i64, _p, _i64, _i64, _i64, _int, _p, _p, _p, _p]),
+    "xr_seq_sample_batch": (_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _int, _int, C.c_uint64,
+                                   C.c_uint64, _p, _p, _p, _p, _p]),
     "xr_fused_available": (_int, []),
     "xr_fused_wait_stats": (_int, [_int, C.POINTER(C.c_uint64)]),
     "xr_fused_timeline": (_int, [C.POINTER(C.c_int64)]),
