@@ -166,6 +166,20 @@ int xr_rowloss(const float* logits, int64_t m, int64_t c, int64_t ld, int target
                int grad_kind, float grad_scale, float* dlogits, double* losses_out,
                double* stats_out, int32_t* err_flag, void* workspace, void* stream);
 
+/* ---- sampled candidates in ONE pass (BASELINE config 3) --------------------------------------
+ * xr_logits_sampled + xr_rowloss (target = column 0) + xr_dq_sampled for one query row per
+ * thread block, the row's C logits and dL/dlogits kept in shared memory: the (M, C) logits and
+ * their gradient never reach HBM and the step is one launch plus the fixed-order reduction.
+ * D = 384, 1 <= c <= 8192.  cosine iff table_inv_norm / q_inv_norm are given (both or neither).
+ * dq: (M, D) fp32, written when grad_kind >= 0.  losses_out / stats_out as xr_rowloss.
+ * workspace: >= xr_sampled_step_workspace_bytes(m) bytes.                                      */
+size_t xr_sampled_step_workspace_bytes(int64_t m);
+int xr_sampled_step(const void* q, const void* table, int64_t n_rows, const int64_t* cand_idx,
+                    int64_t m, int64_t c, int64_t dim, int dtype, const float* table_inv_norm,
+                    const float* q_inv_norm, const xr_loss_config* cfg, int grad_kind,
+                    float grad_scale, float* dq, double* losses_out, double* stats_out,
+                    void* workspace, void* stream);
+
 /* ---- family 2b: dL/dquery from dL/dlogits ---------------------------------------------------
  * autograd of losses.py:195 / :206-208 w.r.t. query_embed (item table frozen, models.py:251).
  * xr_dq_pool, cosine != 0: q/pos/neg are the NORMALISED rows plus q_inv_norm; it applies

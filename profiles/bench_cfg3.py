@@ -73,10 +73,19 @@ for dt, bsz in ((torch.bfloat16, 2), (torch.float32, 4)):
             _, _, dl = ops.rowloss(logits, K + 1, cfg, N.TARGET_FIRST, None, kind)
             ms_dq = timeit(lambda: ops.dq_sampled(dl, q, table, idx, t_inv, q_inv))
             nz = float((dl != 0).float().mean())
+            ms_one = timeit(lambda: ops.sampled_step(q, table, idx, cfg, t_inv, q_inv, kind))
+            ms_one_fwd = timeit(lambda: ops.sampled_step(q, table, idx, cfg, t_inv, q_inv, -1))
+            xr.losses._SAMPLED_ONE_PASS = False
+            ms_three = timeit(step)
+            xr.losses._SAMPLED_ONE_PASS = True
             rec = {"config": "cfg3", "loss": name, "dtype": str(dt).replace("torch.", ""), "rows_M": m, "C": K + 1,
                    "step_ms": ms, "rows_per_s": m / ms * 1e3,
                    "logits_ms": ms_logits, "logits_GB/s": byts / ms_logits / 1e6,
                    "logits_frac_of_measured_hbm": byts / ms_logits / 1e6 / HBM,
+                   "one_pass_kernel_ms": ms_one, "one_pass_forward_only_ms": ms_one_fwd,
+                   "one_pass_GB/s": byts * (1 + nz) / ms_one / 1e6,
+                   "one_pass_frac_of_measured_hbm": byts * (1 + nz) / ms_one / 1e6 / HBM,
+                   "step_ms_three_launches": ms_three,
                    "rowloss_ms": ms_rowloss, "dq_ms": ms_dq, "dq_nonzero_weight_frac": nz,
                    "dq_GB/s_touched": byts * nz / ms_dq / 1e6}
             out.append(rec)

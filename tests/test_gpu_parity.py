@@ -218,6 +218,40 @@ def test_sampled_candidates_match_oracle(xr, name, dtype):
     assert np.abs(g - dq).max() <= tol * max(np.abs(dq).max(), 1e-6) + 1e-6
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("cfg_kw", [{}, {"num_hard_negatives": 7}, {"mask_false_negatives": False, "scale": 4.0}])
+def test_sampled_one_pass_equals_three_launches(xr, dtype, cfg_kw):
+    """xr_sampled_step (logits + pipeline + dq in one launch, logits in shared memory) against
+    xr_logits_sampled + xr_rowloss + xr_dq_sampled: same arithmetic, so the same bits."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n, m, c, d = 5000, 700, 513, 384
+    table = (torch.randn((n + 1, d), generator=g, device="cuda") / d ** 0.5).to(dtype)
+    table[0] = 0
+    q = (torch.randn((m, d), generator=g, device="cuda") / d ** 0.5).to(dtype)
+    idx = torch.randint(0, n + 1, (m, c), generator=g, device="cuda")
+    idx[3, 5] = idx[3, 0]
+    for name in orc.LOSS_NAMES:
+        res = []
+        for one_pass in (True, False):
+            xr.losses._SAMPLED_ONE_PASS = one_pass
+            try:
+                qt = q.clone().requires_grad_(True)
+                loss = getattr(xr, name)(xr.LossConfig(**cfg_kw))(qt, xr.SampledCandidates(table, idx))
+                loss.backward()
+                res.append((loss.detach().clone(), qt.grad.clone()))
+            finally:
+                xr.losses._SAMPLED_ONE_PASS = True
+        assert torch.equal(res[0][0], res[1][0]), name
+        assert torch.equal(res[0][1], res[1][1]), name
+    stats1 = xr.LogitsStatistics(xr.LossConfig(**cfg_kw))(q, xr.SampledCandidates(table, idx))
+    xr.losses._SAMPLED_ONE_PASS = False
+    try:
+        stats3 = xr.LogitsStatistics(xr.LossConfig(**cfg_kw))(q, xr.SampledCandidates(table, idx))
+    finally:
+        xr.losses._SAMPLED_ONE_PASS = True
+    assert stats1 == stats3
+
+
 def test_pool_large_fp32_matches_oracle(xr):
     """BASELINE config-1 shape class (fp32, shared pool), rows > one GEMM tile, ragged sizes."""
     rng = np.random.default_rng(11)

@@ -6,6 +6,7 @@
 //           (M,C,D) tensor of models.py:408-410 never exists.
 // Both share one kernel pair; the only difference is how candidate (i,j) is addressed.
 #include "common.cuh"
+#include "rowloss.cuh"
 
 namespace xr {
 
@@ -183,160 +184,222 @@ __device__ __forceinline__ float warp_sum4(float a, float b, float c, float d, i
   return r;
 }
 
+// one query row: out[j] = q . table[idx[j]] (* qi * table_inv) for j < c.  `out` may be global or
+// shared memory.  All ROW_THREADS threads call it together.
+template <typename T>
+__device__ __forceinline__ void sampled_logits384_row(const T* __restrict__ q_row,
+                                                      const T* __restrict__ table,
+                                                      const int64_t* __restrict__ idx_row,
+                                                      int64_t n_table_rows, int64_t c, float qi,
+                                                      const float* __restrict__ table_inv,
+                                                      float* out) {
+  constexpr int E = RowVec<T>::E, VECS = FD / E, IT = (VECS + 31) / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = ROW_THREADS / 32;
+  float qr[IT][E];
+#pragma unroll
+  for (int t = 0; t < IT; ++t) {
+    const int v = lane + 32 * t;
+    if (v < VECS) RowVec<T>::load(q_row + v * E, qr[t]);
+    else
+#pragma unroll
+      for (int k = 0; k < E; ++k) qr[t][k] = 0.f;
+  }
+  for (int64_t j0 = (int64_t)warp * 4; j0 < c; j0 += nwarp * 4) {
+    int64_t row[4];
+    bool valid[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t j = j0 + u;
+      row[u] = j < c ? idx_row[j] : 0;
+      valid[u] = row[u] >= 0 && row[u] < n_table_rows;
+      if (!valid[u]) row[u] = 0;
+    }
+    float x[4][IT][E];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int t = 0; t < IT; ++t) {
+        const int v = lane + 32 * t;
+        if (v < VECS) RowVec<T>::load(table + row[u] * FD + v * E, x[u][t]);
+        else
+#pragma unroll
+          for (int k = 0; k < E; ++k) x[u][t][k] = 0.f;
+      }
+    float dot[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int t = 0; t < IT; ++t)
+#pragma unroll
+        for (int k = 0; k < E; ++k) dot[u] = fmaf(qr[t][k], x[u][t][k], dot[u]);
+    const float tot = warp_sum4(dot[0], dot[1], dot[2], dot[3], lane);
+    if ((lane & 7) == 0) {
+      const int u = lane >> 3;
+      const int64_t j = j0 + u;
+      int64_t r_sel = row[0];
+      bool v_sel = valid[0];
+#pragma unroll
+      for (int uu = 1; uu < 4; ++uu)   // static indexing keeps row[] / valid[] in registers
+        if (u == uu) {
+          r_sel = row[uu];
+          v_sel = valid[uu];
+        }
+      if (j < c) {
+        float scale = qi;
+        if (table_inv) scale *= table_inv[r_sel];
+        out[j] = v_sel ? tot * scale : CUDART_NAN_F;
+      }
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(ROW_THREADS)
 sampled_logits384_kernel(const T* __restrict__ q, const T* __restrict__ table,
                          const int64_t* __restrict__ cand_idx, int64_t n_table_rows, int64_t m,
                          int64_t c, const float* __restrict__ q_inv,
                          const float* __restrict__ table_inv, float* __restrict__ logits, int64_t ld) {
-  constexpr int E = RowVec<T>::E, VECS = FD / E, IT = (VECS + 31) / 32;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = ROW_THREADS / 32;
-  for (int64_t i = blockIdx.x; i < m; i += gridDim.x) {
-    float qr[IT][E];
-#pragma unroll
-    for (int t = 0; t < IT; ++t) {
-      const int v = lane + 32 * t;
-      if (v < VECS) RowVec<T>::load(q + i * FD + v * E, qr[t]);
-      else
-#pragma unroll
-        for (int k = 0; k < E; ++k) qr[t][k] = 0.f;
-    }
-    const float qi = q_inv ? q_inv[i] : 1.f;
-    for (int64_t j0 = (int64_t)warp * 4; j0 < c; j0 += nwarp * 4) {
-      int64_t row[4];
-      bool valid[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int64_t j = j0 + u;
-        row[u] = j < c ? cand_idx[i * c + j] : 0;
-        valid[u] = row[u] >= 0 && row[u] < n_table_rows;
-        if (!valid[u]) row[u] = 0;
-      }
-      float x[4][IT][E];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int t = 0; t < IT; ++t) {
-          const int v = lane + 32 * t;
-          if (v < VECS) RowVec<T>::load(table + row[u] * FD + v * E, x[u][t]);
-          else
-#pragma unroll
-            for (int k = 0; k < E; ++k) x[u][t][k] = 0.f;
-        }
-      float dot[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int t = 0; t < IT; ++t)
-#pragma unroll
-          for (int k = 0; k < E; ++k) dot[u] = fmaf(qr[t][k], x[u][t][k], dot[u]);
-      const float tot = warp_sum4(dot[0], dot[1], dot[2], dot[3], lane);
-      if ((lane & 7) == 0) {
-        const int u = lane >> 3;
-        const int64_t j = j0 + u;
-        int64_t r_sel = row[0];
-        bool v_sel = valid[0];
-#pragma unroll
-        for (int uu = 1; uu < 4; ++uu)   // static indexing keeps row[] / valid[] in registers
-          if (u == uu) {
-            r_sel = row[uu];
-            v_sel = valid[uu];
-          }
-        if (j < c) {
-          float scale = qi;
-          if (table_inv) scale *= table_inv[r_sel];
-          logits[i * ld + j] = v_sel ? tot * scale : CUDART_NAN_F;
-        }
-      }
-    }
-  }
+  for (int64_t i = blockIdx.x; i < m; i += gridDim.x)
+    sampled_logits384_row<T>(q + i * FD, table, cand_idx + i * c, n_table_rows, c,
+                             q_inv ? q_inv[i] : 1.f, table_inv, logits + i * ld);
 }
 
-// dq_i = sum_j g[i,j] * tinv(j) * table[idx[i,j]]  (+ cosine chain rule): warps split the
+// dq_i = sum_j g[j] * tinv(j) * table[idx[j]]  (+ cosine chain rule): warps split the
 // candidates (4 rows in flight each), lanes own fixed 16-byte column slices, partials are
-// folded across warps through shared memory in a fixed order (deterministic).
+// folded across warps through shared memory in a fixed order (deterministic).  `g` may be global
+// or shared memory; s_red [ROW_THREADS/32][FD] and s_part [ROW_THREADS/32] are block scratch.
+template <typename T>
+__device__ __forceinline__ void sampled_dq384_row(const float* g, const T* __restrict__ q_row,
+                                                  const T* __restrict__ table,
+                                                  const int64_t* __restrict__ idx_row,
+                                                  int64_t n_table_rows, int64_t c, float q_inv_i,
+                                                  const float* __restrict__ table_inv, int cosine,
+                                                  float* __restrict__ dq_row,
+                                                  float (*s_red)[FD], float* s_part) {
+  constexpr int E = RowVec<T>::E, VECS = FD / E, IT = (VECS + 31) / 32;
+  constexpr int NW = ROW_THREADS / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc[IT][E];
+#pragma unroll
+  for (int t = 0; t < IT; ++t)
+#pragma unroll
+    for (int k = 0; k < E; ++k) acc[t][k] = 0.f;
+  for (int64_t j0 = (int64_t)warp * 4; j0 < c; j0 += NW * 4) {
+    float w[4];
+    int64_t row[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t j = j0 + u;
+      w[u] = j < c ? g[j] : 0.f;
+      row[u] = (j < c && w[u] != 0.f) ? idx_row[j] : -1;
+      if (row[u] < 0 || row[u] >= n_table_rows) {   // masked candidates: skip their bytes
+        w[u] = 0.f;
+        row[u] = -1;
+      } else if (table_inv) {
+        w[u] *= table_inv[row[u]];
+      }
+    }
+    if (w[0] == 0.f && w[1] == 0.f && w[2] == 0.f && w[3] == 0.f) continue;
+    float x[4][IT][E];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int t = 0; t < IT; ++t) {
+        const int v = lane + 32 * t;
+        if (v < VECS && row[u] >= 0) RowVec<T>::load(table + row[u] * FD + v * E, x[u][t]);
+        else
+#pragma unroll
+          for (int k = 0; k < E; ++k) x[u][t][k] = 0.f;
+      }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)   // ascending j within the warp: fixed order
+#pragma unroll
+      for (int t = 0; t < IT; ++t)
+#pragma unroll
+        for (int k = 0; k < E; ++k) acc[t][k] = fmaf(w[u], x[u][t][k], acc[t][k]);
+  }
+#pragma unroll
+  for (int t = 0; t < IT; ++t) {
+    const int v = lane + 32 * t;
+    if (v < VECS)
+#pragma unroll
+      for (int k = 0; k < E; ++k) s_red[warp][v * E + k] = acc[t][k];
+  }
+  __syncthreads();
+  float dotgq = 0.f;
+  for (int d = threadIdx.x; d < FD; d += ROW_THREADS) {
+    float s = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < NW; ++w2) s += s_red[w2][d];   // fixed order
+    s_red[0][d] = s;
+    if (cosine) dotgq = fmaf(s, to_f32(q_row[d]) * q_inv_i, dotgq);
+  }
+  if (cosine) {
+    dotgq = warp_sum(dotgq);
+    if (lane == 0) s_part[warp] = dotgq;
+  }
+  __syncthreads();
+  float s_dot = 0.f;
+  if (cosine) {
+#pragma unroll
+    for (int w2 = 0; w2 < NW; ++w2) s_dot += s_part[w2];
+  }
+  for (int d = threadIdx.x; d < FD; d += ROW_THREADS) {
+    float s = s_red[0][d];
+    if (cosine) s = q_inv_i * (s - s_dot * to_f32(q_row[d]) * q_inv_i);
+    dq_row[d] = s;
+  }
+  __syncthreads();
+}
+
 template <typename T>
 __global__ void __launch_bounds__(ROW_THREADS)
 sampled_dq384_kernel(const float* __restrict__ g, int64_t ld, const T* __restrict__ q,
                      const T* __restrict__ table, const int64_t* __restrict__ cand_idx,
                      int64_t n_table_rows, int64_t m, int64_t c, const float* __restrict__ q_inv,
                      const float* __restrict__ table_inv, int cosine, float* __restrict__ dq) {
-  constexpr int E = RowVec<T>::E, VECS = FD / E, IT = (VECS + 31) / 32;
-  constexpr int NW = ROW_THREADS / 32;
-  __shared__ float s_red[NW][FD];
-  __shared__ float s_part[NW];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ float s_red[ROW_THREADS / 32][FD];
+  __shared__ float s_part[ROW_THREADS / 32];
+  for (int64_t i = blockIdx.x; i < m; i += gridDim.x)
+    sampled_dq384_row<T>(g + i * ld, q + i * FD, table, cand_idx + i * c, n_table_rows, c,
+                         cosine ? q_inv[i] : 1.f, table_inv, cosine, dq + i * FD, s_red, s_part);
+}
+
+// ---- the sampled-candidate step in ONE pass (BASELINE config 3) --------------------------------
+// logits (fused gather + dot) -> EmbedLoss pipeline -> dL/dq for one query row per block, the
+// row's C logits and dL/dlogits living in shared memory: no (M, C) tensor reaches HBM and the
+// step is one launch (+ the fixed-order reduction) instead of three.  The second sweep over the
+// row's candidates (for dq) only touches candidates with a non-zero weight and finds them in L2.
+template <typename T>
+__global__ void __launch_bounds__(ROW_THREADS, 4)
+sampled_step384_kernel(const T* __restrict__ q, const T* __restrict__ table,
+                       const int64_t* __restrict__ cand_idx, int64_t n_table_rows, int64_t m,
+                       int64_t c, const float* __restrict__ q_inv,
+                       const float* __restrict__ table_inv, xr_loss_config cfg, int grad_kind,
+                       float grad_scale, float* __restrict__ dq, double* __restrict__ row_out) {
+  static_assert(ROW_THREADS == RL_THREADS, "the row helpers assume one block shape");
+  extern __shared__ float s_dyn[];   // logits[c] | dlogits[c] | hard-mining mask bytes[c]
+  float* s_logit = s_dyn;
+  float* s_g = s_dyn + c;
+  uint8_t* s_mask = reinterpret_cast<uint8_t*>(s_g + c);
+  __shared__ float s_red[ROW_THREADS / 32][FD];
+  __shared__ float s_part[ROW_THREADS / 32];
+  __shared__ double s_d[RL_WARPS];
+  __shared__ float s_f[RL_WARPS];
+  __shared__ unsigned s_hist[256];
+  __shared__ unsigned s_sel[4];
+  __shared__ int s_warp_cnt[RL_WARPS];
+  const int cosine = table_inv != nullptr;
   for (int64_t i = blockIdx.x; i < m; i += gridDim.x) {
-    float acc[IT][E];
-#pragma unroll
-    for (int t = 0; t < IT; ++t)
-#pragma unroll
-      for (int k = 0; k < E; ++k) acc[t][k] = 0.f;
-    for (int64_t j0 = (int64_t)warp * 4; j0 < c; j0 += NW * 4) {
-      float w[4];
-      int64_t row[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int64_t j = j0 + u;
-        w[u] = j < c ? g[i * ld + j] : 0.f;
-        row[u] = (j < c && w[u] != 0.f) ? cand_idx[i * c + j] : -1;
-        if (row[u] < 0 || row[u] >= n_table_rows) {   // masked candidates: skip their bytes
-          w[u] = 0.f;
-          row[u] = -1;
-        } else if (table_inv) {
-          w[u] *= table_inv[row[u]];
-        }
-      }
-      if (w[0] == 0.f && w[1] == 0.f && w[2] == 0.f && w[3] == 0.f) continue;
-      float x[4][IT][E];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int t = 0; t < IT; ++t) {
-          const int v = lane + 32 * t;
-          if (v < VECS && row[u] >= 0) RowVec<T>::load(table + row[u] * FD + v * E, x[u][t]);
-          else
-#pragma unroll
-            for (int k = 0; k < E; ++k) x[u][t][k] = 0.f;
-        }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)   // ascending j within the warp: fixed order
-#pragma unroll
-        for (int t = 0; t < IT; ++t)
-#pragma unroll
-          for (int k = 0; k < E; ++k) acc[t][k] = fmaf(w[u], x[u][t][k], acc[t][k]);
-    }
-#pragma unroll
-    for (int t = 0; t < IT; ++t) {
-      const int v = lane + 32 * t;
-      if (v < VECS)
-#pragma unroll
-        for (int k = 0; k < E; ++k) s_red[warp][v * E + k] = acc[t][k];
-    }
+    const float qi = q_inv ? q_inv[i] : 1.f;
+    sampled_logits384_row<T>(q + i * FD, table, cand_idx + i * c, n_table_rows, c, qi, table_inv, s_logit);
     __syncthreads();
-    float dotgq = 0.f;
-    for (int d = threadIdx.x; d < FD; d += ROW_THREADS) {
-      float s = 0.f;
-#pragma unroll
-      for (int w2 = 0; w2 < NW; ++w2) s += s_red[w2][d];   // fixed order
-      s_red[0][d] = s;
-      if (cosine) dotgq = fmaf(s, to_f32(q[i * FD + d]) * q_inv[i], dotgq);
-    }
-    if (cosine) {
-      dotgq = warp_sum(dotgq);
-      if (lane == 0) s_part[warp] = dotgq;
-    }
+    rowloss_row(s_logit, c, /*target column*/ 0, cfg, grad_kind, grad_scale, dq ? s_g : nullptr,
+                row_out + i * ROW_SLOTS, s_mask, RowLossScratch{s_d, s_f, s_hist, s_sel, s_warp_cnt});
     __syncthreads();
-    float s_dot = 0.f;
-    if (cosine) {
-#pragma unroll
-      for (int w2 = 0; w2 < NW; ++w2) s_dot += s_part[w2];
-    }
-    for (int d = threadIdx.x; d < FD; d += ROW_THREADS) {
-      float s = s_red[0][d];
-      if (cosine) s = q_inv[i] * (s - s_dot * to_f32(q[i * FD + d]) * q_inv[i]);
-      dq[i * FD + d] = s;
-    }
+    if (dq)
+      sampled_dq384_row<T>(s_g, q + i * FD, table, cand_idx + i * c, n_table_rows, c, qi, table_inv,
+                           cosine, dq + i * FD, s_red, s_part);
     __syncthreads();
   }
 }
@@ -476,4 +539,56 @@ extern "C" int xr_dq_sampled(const float* dlogits, int64_t ld, const void* q, co
                                     q_inv_norm, table_inv_norm, nullptr, cosine, dq, s)
              : launch_row_dq<__nv_bfloat16>(dlogits, ld, q, table, cand_idx, n_rows, m, c, dim,
                                             q_inv_norm, table_inv_norm, nullptr, cosine, dq, s);
+}
+
+// ---- BASELINE config 3 in one pass: logits + EmbedLoss pipeline + dL/dq per query row -----------
+extern "C" size_t xr_sampled_step_workspace_bytes(int64_t m) {
+  return (size_t)(m > 0 ? m : 1) * ROW_SLOTS * sizeof(double) + 256;
+}
+
+extern "C" int xr_sampled_step(const void* q, const void* table, int64_t n_rows,
+                               const int64_t* cand_idx, int64_t m, int64_t c, int64_t dim, int dtype,
+                               const float* table_inv_norm, const float* q_inv_norm,
+                               const xr_loss_config* cfg, int grad_kind, float grad_scale, float* dq,
+                               double* losses_out, double* stats_out, void* workspace,
+                               void* stream) {
+  XR_CHECK_ARG(q && table && cand_idx && cfg && workspace && n_rows > 0, "xr_sampled_step: bad arguments");
+  XR_CHECK_ARG(dim == FD, "xr_sampled_step: this build is specialised for dim = %d", FD);
+  XR_CHECK_ARG(c >= 1 && c <= 8192, "xr_sampled_step: 1 <= candidates per row <= 8192");
+  XR_CHECK_ARG(grad_kind < XR_NUM_LOSSES && (grad_kind < 0 || dq), "xr_sampled_step: bad grad_kind / dq");
+  XR_CHECK_ARG((table_inv_norm == nullptr) == (q_inv_norm == nullptr),
+               "xr_sampled_step: cosine needs both inverse norms");
+  int rc = check_row_args("xr_sampled_step", m, c, dim, dtype, q, table);
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  double* row_out = (double*)workspace;
+  if (m > 0) {
+    const size_t smem = (size_t)c * 9;   // two float arrays + the mask bytes
+    float* dq_arg = grad_kind >= 0 ? dq : nullptr;
+    if (dtype == XR_F32) {
+      static size_t conf = 0;
+      if (smem > conf) {
+        XR_CUDA(cudaFuncSetAttribute(sampled_step384_kernel<float>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 9));
+        conf = 8192 * 9;
+      }
+      sampled_step384_kernel<float><<<row_grid(m), ROW_THREADS, smem, s>>>(
+          (const float*)q, (const float*)table, cand_idx, n_rows, m, c, q_inv_norm, table_inv_norm,
+          *cfg, grad_kind, grad_scale, dq_arg, row_out);
+    } else {
+      static size_t conf = 0;
+      if (smem > conf) {
+        XR_CUDA(cudaFuncSetAttribute(sampled_step384_kernel<__nv_bfloat16>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 9));
+        conf = 8192 * 9;
+      }
+      sampled_step384_kernel<__nv_bfloat16><<<row_grid(m), ROW_THREADS, smem, s>>>(
+          (const __nv_bfloat16*)q, (const __nv_bfloat16*)table, cand_idx, n_rows, m, c, q_inv_norm,
+          table_inv_norm, *cfg, grad_kind, grad_scale, dq_arg, row_out);
+    }
+    XR_LAUNCH_CHECK("sampled_step384");
+  }
+  if (losses_out || stats_out)
+    return launch_rowloss_reduce(row_out, m, c, cfg->num_hard_negatives, losses_out, stats_out, s);
+  return XR_OK;
 }

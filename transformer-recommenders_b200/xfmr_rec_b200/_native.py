@@ -65,6 +65,9 @@ PROTOTYPES = {
     "xr_dq_sampled": (_int, [_p, _i64, _p, _p, _i64, _p, _i64, _i64, _i64, _int, _p, _p, _p, _p]),
     "xr_seq_sample_batch": (_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _int, _int, C.c_uint64,
                                    C.c_uint64, _p, _p, _p, _p, _p]),
+    "xr_sampled_step_workspace_bytes": (_sz, [_i64]),
+    "xr_sampled_step": (_int, [_p, _p, _i64, _p, _i64, _i64, _i64, _int, _p, _p, _cfgp, _int, _f, _p, _p,
+                               _p, _p, _p]),
     "xr_fused_available": (_int, []),
     "xr_fused_wait_stats": (_int, [_int, C.POINTER(C.c_uint64)]),
     "xr_fused_timeline": (_int, [C.POINTER(C.c_int64)]),

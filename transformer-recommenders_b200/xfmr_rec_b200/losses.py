@@ -92,6 +92,9 @@ class PoolCandidates(_CandidateHandle):
         return torch.cat([self.pos[:, None, :], self.neg[None].expand(m, -1, -1)], dim=1)
 
 
+_SAMPLED_ONE_PASS = True  # False: logits / rowloss / dq as three launches (kept for A/B timing and tests)
+
+
 class SampledCandidates(_CandidateHandle):
     """candidate_embed[i, j] = table[cand_idx[i, j]]; column 0 is the positive."""
 
@@ -323,6 +326,10 @@ class EmbedLoss(torch.nn.Module, abc.ABC):
             table_inv = cand.table_inv_norm
             if table_inv is None:
                 _, table_inv = ops.normalize_rows(table, 1e-8, want_y=False)
+        if q.size(1) == 384 and 1 <= idx.size(1) <= 8192 and _SAMPLED_ONE_PASS:
+            # one launch: the row's logits and their gradient never leave shared memory
+            return ops.sampled_step(q, table, idx, cfg, table_inv, q_inv, grad_kind,
+                                    want_stats=want_stats)
         logits = ops.logits_sampled(q, table, idx, table_inv, q_inv)
         losses, stats, dl = ops.rowloss(logits, idx.size(1), cfg, N.TARGET_FIRST, None, grad_kind,
                                         want_stats=want_stats)

@@ -268,6 +268,23 @@ def dq_sampled(dlogits, q, table, cand_idx, table_inv=None, q_inv=None):
     return dq
 
 
+def sampled_step(q, table, cand_idx, cfg, table_inv=None, q_inv=None, grad_kind=-1, grad_scale=1.0,
+                 want_stats=False):
+    """Sampled candidates in one pass (xr_sampled_step): logits + EmbedLoss pipeline + dL/dq with
+    the row's logits in shared memory.  Returns (losses f64[7], stats f64[16] | None, dq | None)."""
+    dev = _require_cuda(q, table, cand_idx)
+    m, c = cand_idx.shape
+    losses = torch.empty(N.XR_NUM_LOSSES, dtype=torch.float64, device=dev)
+    stats = torch.empty(N.XR_STATS_SLOTS, dtype=torch.float64, device=dev) if want_stats else None
+    dq = torch.empty((m, q.size(1)), dtype=torch.float32, device=dev) if grad_kind >= 0 else None
+    ws = _ws(N.lib().xr_sampled_step_workspace_bytes(m), dev)
+    with _on(dev):
+        N.call("xr_sampled_step", _p(q), _p(table), table.size(0), _p(cand_idx), m, c, q.size(1),
+               _dt(q), _p(table_inv), _p(q_inv), C.byref(cfg), grad_kind, float(grad_scale), _p(dq),
+               _p(losses), _p(stats), _p(ws), _stream())
+    return losses, stats, dq
+
+
 def fused_pool_supported(q, neg) -> bool:
     if not (q.is_cuda and q.dtype == torch.bfloat16 and q.size(1) == 384):
         return False
