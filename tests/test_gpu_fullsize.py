@@ -1,0 +1,167 @@
+"""BASELINE.json configurations at FULL size through size-independent properties (the oracle
+cannot run them in seconds): sortedness, planted answers, sharded == unsharded, fused == unfused
+on exact-arithmetic inputs, additivity over rows, linearity in grad_scale, determinism."""
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def xr():
+    import xfmr_rec_b200 as pkg
+
+    if not torch.cuda.is_available() or torch.cuda.get_device_capability()[0] != 10:
+        pytest.skip("needs an sm_100 device")
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip("needs 40 GB of free device memory")
+    return pkg
+
+
+def test_config4_full_catalog_properties(xr):
+    """configs[3]: top-100 over 10M x 384 bf16 items, U = 256, cosine."""
+    n, u, k, d = 10_000_000, 256, 100, 384
+    g = torch.Generator(device="cuda").manual_seed(4)
+    cat = torch.empty((n, d), dtype=torch.bfloat16, device="cuda")
+    for lo in range(0, n, 1_000_000):   # chunked: no 15 GB fp32 temporary
+        cat[lo:lo + 1_000_000] = torch.randn((1_000_000, d), generator=g, device="cuda").bfloat16()
+    q = torch.randn((u, d), generator=g, device="cuda")
+    # plant: query r's direction sits at row 37 + 39_001 r (and a duplicate 5 rows later: tie -> lower id)
+    planted = 37 + 39_001 * torch.arange(u, device="cuda")
+    cat[planted] = q.bfloat16()
+    cat[planted + 5] = q.bfloat16()
+    idx = xr.index.ExactIndex(xr.index.ExactIndexConfig(index_metric="cosine", dtype="bf16"))
+    idx.set_catalog(cat)
+    del cat
+    excl = [[int(planted[r]) + 5] if r % 2 else [] for r in range(u)]   # odd users exclude the twin
+    s, i = idx.search_batch(q, excl, k)
+    assert i.shape == (u, k) and int(i.min()) >= 0 and int(i.max()) < n
+    assert bool((s[:, :-1] >= s[:, 1:]).all()), "scores must be non-increasing"
+    ties = s[:, :-1] == s[:, 1:]
+    assert bool((i[:, :-1][ties] < i[:, 1:][ties]).all()), "ties -> lower item id first"
+    assert torch.equal(i[:, 0], planted), "the planted row must rank first (twin: higher id)"
+    even = torch.arange(u, device="cuda") % 2 == 0
+    assert torch.equal(i[even, 1], planted[even] + 5) and bool((i[~even, 1] != planted[~even] + 5).all())
+    assert bool((s[:, 0] > 0.99).all())
+    assert all(len(set(r.tolist())) == k for r in i[:8].cpu())
+    # every returned score is the cosine the index defines (re-scored in fp32 from the stored rows)
+    qn, _ = xr.ops.normalize_rows(q, 1e-12, torch.bfloat16)
+    rows = idx.catalog[i[:4].reshape(-1)].float().view(4, k, d)
+    want = torch.einsum("ukd,ud->uk", rows, qn[:4].float())
+    torch.testing.assert_close(s[:4], want, rtol=1e-5, atol=2e-6)
+    # nothing outside the result beats the k-th score: exact scan of a 400k-row slice
+    part = idx.catalog[3_000_000:3_400_000].float() @ qn[:16].float().T          # (400k, 16)
+    inside = (i[:16] >= 3_000_000) & (i[:16] < 3_400_000)
+    for r in range(16):
+        above = int((part[:, r] > s[r, -1]).sum())
+        assert above <= int(inside[r].sum()), "a better-scoring row was missed"
+    # sharded == unsharded: 8 contiguous shards searched separately, merged under the same order
+    all_s, all_i = [], []
+    for rank in range(8):
+        lo, hi = xr.dist.shard_range(n, rank, 8)
+        sh = xr.index.ExactIndex(xr.index.ExactIndexConfig(index_metric="cosine", dtype="bf16"), row_offset=lo)
+        sh.catalog = idx.catalog[lo:hi]      # rows already normalised
+        sh_excl = excl
+        ss, ii = sh.search_batch(q, sh_excl, k)
+        all_s.append(ss)
+        all_i.append(ii)
+    ms, mi = xr.ops.topk_merge(torch.cat(all_s, 1), torch.cat(all_i, 1), k)
+    assert torch.equal(mi, i) and torch.equal(ms, s)
+    # deterministic
+    s2, i2 = idx.search_batch(q, excl, k)
+    assert torch.equal(i2, i) and torch.equal(s2, s)
+
+
+def _cfg2_batch(seed=0, B=128, L=200, n_items=27278, d=384):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    lens = torch.randint(1, L + 1, (B,), generator=g, device="cuda")
+    valid = torch.arange(L, device="cuda")[None, :] < lens[:, None]
+    hist = torch.randint(1, n_items + 1, (B, L), generator=g, device="cuda") * valid
+    pos = torch.randint(1, n_items + 1, (B, L), generator=g, device="cuda") * valid
+    pos = pos * (torch.rand((B, L), generator=g, device="cuda") > 0.05)
+    neg = torch.randint(1, n_items + 1, (B, L), generator=g, device="cuda") * valid
+    table = torch.randn((n_items + 1, d), generator=g, device="cuda") / d ** 0.5
+    table[0] = 0
+    tok = (torch.randn((B, L, d), generator=g, device="cuda") / d ** 0.5).bfloat16()
+    return table, tok, hist, pos, neg
+
+
+def test_config2_full_size_properties(xr):
+    """configs[1]: ML-20M-shaped, B = 128 x L = 200, InfoNCE in-batch, bf16 (M ~ 12k rows x 12.7k
+    candidates): rows are independent given the pool, so the loss is ADDITIVE over row subsets and
+    each row's gradient does not depend on which other rows are evaluated; the gradient is linear
+    in grad_scale; repeated evaluation is bit-identical."""
+    table, tok, hist, pos, neg = _cfg2_batch()
+    emb = xr.models.ItemEmbeddings(table, add_padding_row=False).cuda()
+    t = tok.clone().requires_grad_(True)
+    out = xr.models.compute_embeds(emb, t, hist, pos, neg, candidate_dtype=torch.bfloat16)
+    q, cand = out["query_embed"], out["candidate_embed"]
+    m = q.size(0)
+    assert m > 10_000 and cand.neg.size(0) >= m
+    fn = xr.InfoNCELoss(xr.LossConfig())
+    loss = fn(q, cand)
+    loss.backward()
+    g_full = t.grad.clone()
+    assert torch.isfinite(loss) and bool(torch.isfinite(g_full).all())
+    # unselected positions get exactly zero gradient (autograd of token_embeddings[mask][pos_mask])
+    sel = ((hist != 0) & (pos != 0)).reshape(-1)
+    assert not bool(g_full.reshape(-1, 384)[~sel].any())
+    # additivity over rows + per-row gradients independent of the row subset
+    qd = q.detach()
+    cut = (m // 2 // 128) * 128 + 37          # ragged split, not a tile multiple
+    parts, grads = [], []
+    for lo, hi in ((0, cut), (cut, m)):
+        qq = qd[lo:hi].clone().requires_grad_(True)
+        l = fn(qq, xr.PoolCandidates(cand.pos[lo:hi], cand.neg))
+        l.backward()
+        parts.append(float(l))
+        grads.append(qq.grad)
+    assert float(loss) == pytest.approx(sum(parts), rel=1e-5)
+    qq = qd.clone().requires_grad_(True)
+    l2 = fn(qq, cand)
+    l2.backward()
+    assert float(l2) == float(loss)                       # deterministic
+    # the gradients are returned in the query's dtype (bf16): a different split of the pool changes
+    # the fp32 summation order, which can flip the last bf16 bit (2^-8 relative) of a few elements
+    ga, gb = torch.cat(grads).float(), qq.grad.float()
+    torch.testing.assert_close(ga, gb, rtol=2 ** -7, atol=1e-7)
+    assert float((ga != gb).float().mean()) < 1e-3
+    # linearity in the upstream gradient
+    qq3 = qd.clone().requires_grad_(True)
+    (fn(qq3, cand) * 3.0).backward()
+    torch.testing.assert_close(qq3.grad.float(), 3.0 * qq.grad.float(), rtol=2e-2, atol=1e-6)   # bf16 grads
+    # the sync-free graph-replayed step gives the module path's bits
+    step = xr.PoolLossStep(emb, fn, batch_size=hist.size(0), seq_len=hist.size(1))
+    l_step, dtok = step(tok, hist, pos, neg)
+    assert float(l_step) == float(loss)
+    assert torch.equal(dtok.reshape(g_full.shape), g_full)
+
+
+def test_config5_largest_point_properties(xr):
+    """configs[4] at its largest point: B = 8192 queries x 1M candidates, fused forward + backward
+    (the reference's logits matrix would be 32.8 GB): additivity over row halves, finite gradients,
+    BPR (PairwiseLogistic, margin 0) and InfoNCE."""
+    m, cn, d = 8192, 1_000_000, 384
+    g = torch.Generator(device="cuda").manual_seed(1)
+    q = (torch.randn((m, d), generator=g, device="cuda") / d ** 0.5).bfloat16()
+    pos = (torch.randn((m, d), generator=g, device="cuda") / d ** 0.5).bfloat16()
+    neg = (torch.randn((cn, d), generator=g, device="cuda") / d ** 0.5).bfloat16()
+    for name, kw in (("InfoNCELoss", {}), ("PairwiseLogisticLoss", {"margin": 0.0})):
+        fn = getattr(xr, name)(xr.LossConfig(**kw))
+        qq = q.clone().requires_grad_(True)
+        loss = fn(qq, xr.PoolCandidates(pos, neg))
+        loss.backward()
+        assert torch.isfinite(loss) and bool(torch.isfinite(qq.grad).all())
+        halves = sum(float(fn(q[lo:hi], xr.PoolCandidates(pos[lo:hi], neg))) for lo, hi in ((0, 4096), (4096, m)))
+        assert float(loss) == pytest.approx(halves, rel=1e-5), name
+        # a 1k-candidate slice evaluated by the materialised fp32-accumulate path of the library
+        sub = xr.PoolCandidates(pos[:256], neg[:1000])
+        a = float(fn(q[:256], sub))
+        from xfmr_rec_b200 import _native as N, ops
+        cfg = ops.make_cfg(xr.LossConfig(**kw), logits_bf16=True)
+        lg = ops.logits_pool(q[:256], pos[:256], neg[:1000])
+        l_mat, _, _ = ops.rowloss(lg, 1001, cfg, N.TARGET_LAST, None, -1)
+        assert a == pytest.approx(float(l_mat[N.LOSS_KIND[name]]), rel=2e-3), name

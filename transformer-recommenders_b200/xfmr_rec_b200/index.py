@@ -100,6 +100,8 @@ class ExactIndex:
         where fewer than k rows remain)."""
         assert self.catalog is not None, "index_data / set_catalog first"
         cat = self.catalog
+        if self.device is None:   # catalog installed directly (a view of a resident shard)
+            self.device = cat.device
         q = queries.to(self.device)
         if q.dim() == 1:
             q = q[None]

@@ -360,6 +360,7 @@ def _csr(lists, device):
 def mask_excluded(score_mat, n, exclude_lists, col_offset=0):
     dev = _require_cuda(score_mat)
     offs, ids = exclude_lists if isinstance(exclude_lists, tuple) else _csr(exclude_lists, dev)
+    _require_cuda(score_mat, offs, ids)
     with _on(dev):
         N.call("xr_mask_excluded", _p(score_mat), score_mat.size(0), n, score_mat.size(1),
                col_offset, _p(offs), _p(ids), _stream())
@@ -441,8 +442,8 @@ def groups_to_rows(group_ids, n, row_offset=0, layout=0):
 
 
 def mask_excluded_ids(score_mat, ids, id_lo, id_hi, exclude=None):
-    dev = _require_cuda(score_mat, ids)
     offs, ex = (None, None) if exclude is None else exclude
+    dev = _require_cuda(score_mat, ids, offs, ex)
     u, c = ids.shape
     with _on(dev):
         N.call("xr_mask_excluded_ids", _p(score_mat), _p(ids), u, c, score_mat.size(1), id_lo, id_hi,
