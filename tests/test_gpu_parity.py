@@ -223,8 +223,13 @@ def test_sampled_candidates_match_oracle(xr, name, dtype):
 def test_sampled_one_pass_equals_three_launches(xr, dtype, cfg_kw):
     """xr_sampled_step (logits + pipeline + dq in one launch, logits in shared memory) against
     xr_logits_sampled + xr_rowloss + xr_dq_sampled: same arithmetic, so the same bits."""
+    _one_pass_vs_three(xr, dtype, cfg_kw, 5000, 700, 513)
+    _one_pass_vs_three(xr, dtype, cfg_kw, 500, 33, 65)
+
+
+def _one_pass_vs_three(xr, dtype, cfg_kw, n, m, c):
     g = torch.Generator(device="cuda").manual_seed(5)
-    n, m, c, d = 5000, 700, 513, 384
+    d = 384
     table = (torch.randn((n + 1, d), generator=g, device="cuda") / d ** 0.5).to(dtype)
     table[0] = 0
     q = (torch.randn((m, d), generator=g, device="cuda") / d ** 0.5).to(dtype)

@@ -492,7 +492,7 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
       if (!diag && KIND != KIND_GMAX && row_ok) {
         t = p.t[row];
         if (RBF) t = bf16_round(t);
-        tm = t * (1.0f - p.margin);
+        tm = __fmul_rn(t, 1.0f - p.margin);   // rounded on its own: see rowloss.cuh
         float zr;
         if (p.zref) zr = p.zref[row];
         else zr = round_scaled ? bf16_round(t * p.scale) : t * p.scale;

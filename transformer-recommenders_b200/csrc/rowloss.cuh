@@ -166,14 +166,16 @@ __device__ __forceinline__ void rowloss_row(const float* lrow, int64_t c, int64_
   const float neg_max = block_max(vmax, s_f);
   const float neg_min = block_min(vmin, s_f);
   auto scaled = [&](float v) -> float {
-    const float z = v * scale;
+    const float z = __fmul_rn(v, scale);   // a separately rounded product, as torch's `logits * scale`
     return round_bf16 ? bf16_round(z) : z;  // autocast: `logits * scale` is a bf16 op (:486)
   };
   // reference max of the softmax set {valid} U {target}
   float zmax = scaled(t);
   if (n_valid > 0) zmax = fmaxf(zmax, fmaxf(scaled(neg_max), scaled(neg_min)));
   const float den = (float)n_valid + 1e-9f;
-  const float tm = t * (1.0f - margin);
+  // rounded on its own (torch: `(1 - margin) * target` is a tensor op): contracted into an FMA with the
+  // subtraction below, a negative whose logit EQUALS tm would get x != 0 and flip the hinge
+  const float tm = __fmul_rn(t, 1.0f - margin);
 
   // ---- pass 2: sums ----------------------------------------------------------------------------
   double a_exp = 0, a_sp = 0, a_hinge = 0, a_logi = 0, a_dlogi = 0, a_dhinge = 0, a_contr = 0,
@@ -239,11 +241,11 @@ __device__ __forceinline__ void rowloss_row(const float* lrow, int64_t c, int64_
           break;
         case XR_LOSS_PAIRWISE_HINGE:
           if (ok) g = (v - tm > 0.f) ? inv_den : 0.f;
-          if (j == ti) g += -(1.0f - margin) * (float)sum_dhinge * inv_den;
+          if (j == ti) g = __fadd_rn(g, __fmul_rn(__fmul_rn(-(1.0f - margin), (float)sum_dhinge), inv_den));
           break;
         case XR_LOSS_PAIRWISE_LOGISTIC:
           if (ok) g = sigmoidf(v - tm) * inv_den;
-          if (j == ti) g += -(1.0f - margin) * (float)sum_dlogi * inv_den;
+          if (j == ti) g = __fadd_rn(g, __fmul_rn(__fmul_rn(-(1.0f - margin), (float)sum_dlogi), inv_den));
           break;
         case XR_LOSS_ALIGNMENT:
           if (j == ti) g = -1.f;

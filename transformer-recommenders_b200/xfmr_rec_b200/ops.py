@@ -223,10 +223,12 @@ def rowloss(logits, c, cfg, target_mode, target=None, grad_kind=-1, grad_scale=1
     """EmbedLoss pipeline on logits (losses.py:211-330 + loss bodies).  Returns
     (losses float64[7] device tensor, stats float64[16] | None, dlogits | None)."""
     dev = _require_cuda(logits, target)
-    m, ld = logits.shape
+    if logits.stride(1) != 1:
+        logits = logits.contiguous()
+    m, ld = logits.size(0), logits.stride(0) if logits.size(0) > 1 else logits.size(1)
     losses = torch.empty(N.XR_NUM_LOSSES, dtype=torch.float64, device=dev)
     stats = torch.empty(N.XR_STATS_SLOTS, dtype=torch.float64, device=dev) if want_stats else None
-    dlogits = torch.empty_like(logits) if grad_kind >= 0 else None
+    dlogits = torch.empty((m, ld), dtype=torch.float32, device=dev) if grad_kind >= 0 else None
     err = torch.zeros(1, dtype=torch.int32, device=dev) if (check and target is not None) else None
     ws = _ws(N.lib().xr_rowloss_workspace_bytes(m, c, cfg.num_hard_negatives), dev)
     with _on(dev):
