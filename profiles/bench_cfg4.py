@@ -1,0 +1,76 @@
+"""BASELINE config 4 on ONE GPU: full-catalog top-100 over N x 384 bf16 items for U in {1, 256, 4096}
+(SURVEY 8d): search time, queries/s, scoring-kernel roofline (tensor for U >= 211, HBM below), and
+recall@100 of the bf16 index against an fp32 exact search on a 100k-item subsample.
+    python profiles/bench_cfg4.py [catalog_rows] > profiles/cfg4_r01.json"""
+import ctypes
+import json
+import pathlib
+import sys
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+sys.path[:0] = [str(ROOT), str(ROOT / "transformer-recommenders_b200")]
+import torch
+
+import xfmr_rec_b200 as xr
+from xfmr_rec_b200 import _native as N
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
+d, k = 384, 100
+peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+dev = torch.device("cuda", 0)
+g = torch.Generator(device=dev).manual_seed(1)
+raw = torch.empty((n, d), dtype=torch.bfloat16, device=dev)
+for lo in range(0, n, 1_000_000):
+    raw[lo:lo + 1_000_000] = torch.randn((min(1_000_000, n - lo), d), generator=g, device=dev).bfloat16()
+idx = xr.index.ExactIndex(xr.index.ExactIndexConfig(index_metric="cosine", dtype="bf16"), dev)
+idx.set_catalog(raw)
+lib = N.lib()
+out = {"catalog_rows": n, "dim": d, "k": k, "dtype": "bf16", "points": []}
+for u in (1, 16, 128, 256, 1024, 4096):
+    q = torch.randn((u, d), generator=g, device=dev)
+    excl = [torch.randint(0, n, (int(torch.randint(20, 201, (1,)).item()),)).tolist() for _ in range(u)]
+    csr = xr.ops._csr(excl, dev)
+    for _ in range(2):
+        s, i = idx.search_batch(q, csr, k)
+    torch.cuda.synchronize()
+    iters = 10 if u <= 1024 else 4
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lib.xr_fused_profile(1)
+    a.record()
+    for _ in range(iters):
+        s, i = idx.search_batch(q, csr, k)
+    b.record()
+    torch.cuda.synchronize()
+    buf = (ctypes.c_float * 64)()
+    cnt = lib.xr_fused_profile_read(buf, 64)
+    lib.xr_fused_profile(0)
+    ms = a.elapsed_time(b) / iters
+    kms = sum(buf[j] for j in range(cnt)) / max(cnt, 1) * (cnt / iters)   # scoring launches per search
+    flops, byts = 2.0 * u * n * d, n * d * 2.0
+    out["points"].append({
+        "queries": u, "ms_per_batch": ms, "queries_per_s": u / ms * 1e3, "exclusions_per_query": "20-200",
+        "scoring_ms": kms, "scoring_TFLOP/s": flops / kms / 1e9, "scoring_catalog_GB/s": byts / kms / 1e6,
+        "frac_of_measured_bf16": flops / kms / 1e9 / peaks["bf16_tflops_sustained"],
+        "frac_of_measured_hbm": byts / kms / 1e6 / peaks["hbm_gbs"],
+        "bound": "tensor" if u >= 211 else "hbm"})
+    print(json.dumps(out["points"][-1]), file=sys.stderr)
+# recall@100 of the bf16 index vs fp32 exact search on a 100k-item subsample (fp32 rows of the SAME items)
+sub = 100_000
+u = 256
+rows32 = raw[:sub].float()
+q = torch.randn((u, d), generator=g, device=dev)
+exact = xr.index.ExactIndex(xr.index.ExactIndexConfig(index_metric="cosine", dtype="fp32", fused=False), dev).set_catalog(rows32)
+bf = xr.index.ExactIndex(xr.index.ExactIndexConfig(index_metric="cosine", dtype="bf16"), dev).set_catalog(raw[:sub])
+_, ie = exact.search_batch(q, None, k)
+_, ib = bf.search_batch(q, None, k)
+rec = sum(len(set(ie[r].tolist()) & set(ib[r].tolist())) for r in range(u)) / (u * k)
+# against float64 on the host for 8 queries (the oracle's arithmetic)
+qn = torch.nn.functional.normalize(q[:8].double(), dim=-1)
+cn = torch.nn.functional.normalize(rows32.double(), dim=-1)
+i64 = (qn @ cn.T).topk(k, dim=-1).indices
+rec64 = sum(len(set(i64[r].tolist()) & set(ie[r].tolist())) for r in range(8)) / (8 * k)
+out["recall_at_100_bf16_index_vs_fp32_exact_100k_subsample"] = rec
+out["recall_at_100_fp32_exact_vs_float64_100k_subsample"] = rec64
+out["note"] = ("the catalog rows ARE bf16 values, so the fp32 exact search sees the same items; the only "
+               "difference is the bf16 rounding of the normalised rows / queries inside the bf16 index")
+print(json.dumps(out, indent=1))
