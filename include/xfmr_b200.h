@@ -196,6 +196,20 @@ int xr_dq_sampled(const float* dlogits, int64_t ld, const void* q, const void* t
                   int dtype, const float* table_inv_norm, const float* q_inv_norm, float* dq,
                   void* stream);
 
+/* ---- the monitoring half of compute_losses inside the sync-free step -------------------------
+ * trainer.py:250-263 logs LogitsStatistics and all seven losses on every training step.  Call
+ * right after xr_pool_step on the SAME stream with the SAME workspace (sized by
+ * xr_pool_step_monitor_workspace_bytes, which xr_pool_step accepts too): both all-losses passes
+ * (xr_fused_pool_all, dot and cosine family) run on the operands the step gathered, the shape
+ * stays on the device, nothing is copied to the host -- CUDA-graph capturable with the step.
+ *   losses_dot / losses_cos : float64[XR_NUM_LOSSES] (entries of the other family meaningless)
+ *   stats_out               : float64[XR_STATS_SLOTS] of the dot logits (losses.py:383-405)
+ * cfg->logits_bf16 applies to the dot family; cosine logits stay fp32.                          */
+size_t xr_pool_step_monitor_workspace_bytes(int64_t n_pos, int64_t dim);
+int xr_pool_step_monitor(int64_t n_pos, int64_t dim, const xr_loss_config* cfg, double* losses_dot,
+                         double* losses_cos, double* stats_out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* ---- SeqBatch construction (the step right before the path) ---------------
  * SeqDataset.__getitem__ + collate (data.py:669-805) for a whole batch in one launch:
  * sample_sequence (:669-689), sample_positives (:691-721), sample_negatives (:723-747),

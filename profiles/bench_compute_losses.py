@@ -69,6 +69,24 @@ def one_by_one():
     return out, st
 
 
+# the same through ONE sync-free, graph-replayed sequence (PoolLossStep(monitor=True)): needs a SeqBatch
+import numpy as np
+
+from oracle import xfmr_oracle as orc
+
+sb = orc.synth_batch(n_items, B, L, dim=d, seed=0)
+emb = xr.models.ItemEmbeddings(torch.from_numpy(sb["table"]), add_padding_row=False).to(dev)
+mstep = xr.PoolLossStep(emb, xr.InfoNCELoss(cfg), B, L, token_dtype=torch.bfloat16, monitor=True)
+pstep = xr.PoolLossStep(emb, xr.InfoNCELoss(cfg), B, L, token_dtype=torch.bfloat16)
+for st in (mstep, pstep):
+    st.load(torch.from_numpy(sb["token_embeddings"]).to(dev).bfloat16(),
+            *(torch.from_numpy(sb[k]).to(dev) for k in ("history_item_idx", "pos_item_idx", "neg_item_idx")))
+torch.cuda.synchronize()
+graph_monitor_ms = timed(lambda: mstep.run())
+graph_monitor_with_dict_ms = timed(lambda: (mstep.run(), mstep.loss_dict()))
+graph_plain_ms = timed(lambda: pstep.run())
+m_a_g, m_g = mstep.row_counts()
+
 lib = N.lib()
 c_cfg = ops.make_cfg(cfg, logits_bf16=True)
 kern = {}
@@ -94,6 +112,10 @@ res = {
     "workload": f"ML-20M-shaped, B={B} x L={L}: M={m} rows x C={m_a + 1} candidates, D=384, bf16",
     "compute_losses_evaluate_all_ms": timed(all_in_one),
     "compute_losses_modules_one_by_one_ms": timed(one_by_one),
+    "graph_step_with_monitor_ms": graph_monitor_ms,
+    "graph_step_with_monitor_and_host_dict_ms": graph_monitor_with_dict_ms,
+    "graph_step_train_loss_only_ms": graph_plain_ms,
+    "graph_step_shape": f"M={m_g} rows x C={m_a_g + 1} (the bench.py batch)",
     "kernels": kern,
     "note": "wall of the device work per call (CUDA events, L2 flushed between calls, host syncs of "
             "the reference's .item() reads included: evaluate_all has one)",

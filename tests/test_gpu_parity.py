@@ -483,3 +483,18 @@ def test_evaluate_batch_equals_per_user_loop(xr):
             cnt += 1
     for j, name in enumerate(names):
         assert float(means[f"val/{name}"]) == pytest.approx(acc[j] / cnt, rel=1e-5, abs=1e-6)
+
+
+def test_search_batch_query_blocks_equal_one_shot(xr):
+    """Large query sets run in blocks that bound the group-maxima buffer: same result."""
+    rng = np.random.default_rng(3)
+    n, u, k = 20000, 700, 50
+    cat = torch.from_numpy(rng.standard_normal((n, 384)).astype(np.float32)).cuda()
+    q = torch.from_numpy(rng.standard_normal((u, 384)).astype(np.float32)).cuda()
+    excl = [list(map(int, rng.integers(0, n, size=int(rng.integers(0, 30))))) for _ in range(u)]
+    one = xr.index.ExactIndex(xr.index.ExactIndexConfig()).set_catalog(cat)
+    blk = xr.index.ExactIndex(xr.index.ExactIndexConfig(max_groupmax_bytes=1)).set_catalog(cat)   # 256-query blocks
+    for ex in (excl, xr.ops._csr(excl, cat.device), None):
+        s1, i1 = one.search_batch(q, ex, k)
+        s2, i2 = blk.search_batch(q, ex, k)
+        assert torch.equal(i1, i2) and torch.equal(s1, s2)

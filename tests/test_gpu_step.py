@@ -134,3 +134,40 @@ def test_step_rejects_what_it_does_not_serve(xr):
     with pytest.raises(xr._native.NativeError):
         xr.PoolLossStep(xr.models.ItemEmbeddings(torch.from_numpy(b["table"]), add_padding_row=False),
                         xr.InfoNCELoss(xr.LossConfig()), 2, 8)
+
+
+@pytest.mark.parametrize("graph", [True, False])
+@pytest.mark.parametrize("cfg_kw", [{}, dict(mask_false_negatives=False, scale=4.0, margin=0.2)])
+def test_step_with_monitor_equals_evaluate_all(xr, graph, cfg_kw):
+    """PoolLossStep(monitor=True): the train loss + gradient AND everything compute_losses logs
+    (trainer.py:250-263: LogitsStatistics + all seven losses) from one sync-free sequence; same
+    numbers as evaluate_all on the module path (identical kernels on identical operands)."""
+    b = orc.synth_batch(3000, 16, 60, dim=384, seed=4)
+    emb = xr.models.ItemEmbeddings(torch.from_numpy(b["table"]), add_padding_row=False).cuda()
+    cfg = xr.LossConfig(**cfg_kw)
+    loss_fn = xr.InfoNCELoss(cfg)
+    step = xr.PoolLossStep(emb, loss_fn, 16, 60, use_graph=graph, monitor=True)
+    for rep in range(2):     # replay twice: no state may leak between steps
+        loss, dtok = run_step(step, b, torch.bfloat16)
+        got, got_stats = step.loss_dict()
+        tok = torch.from_numpy(b["token_embeddings"]).cuda().bfloat16().requires_grad_(True)
+        hist, pos, neg = (torch.from_numpy(b[k]).cuda() for k in
+                          ("history_item_idx", "pos_item_idx", "neg_item_idx"))
+        out = xr.models.compute_embeds(emb, tok, hist, pos, neg, candidate_dtype=torch.bfloat16)
+        want, want_stats = xr.losses.evaluate_all(cfg, out["query_embed"], out["candidate_embed"])
+        want["loss/InfoNCELoss"].backward()
+        assert torch.equal(loss, want["loss/InfoNCELoss"].detach())
+        assert torch.equal(dtok.reshape(tok.grad.shape), tok.grad)
+        for k, v in want.items():
+            assert float(got[k]) == pytest.approx(float(v), rel=1e-6, abs=1e-6), k
+        assert got_stats.keys() == want_stats.keys()
+        for k, v in want_stats.items():
+            assert got_stats[k] == pytest.approx(v, rel=1e-6, abs=1e-9), k
+    # and against the oracle on bf16-rounded logits
+    q = out["query_embed"].detach().float().cpu().numpy()
+    ps = out["candidate_embed"].pos.float().cpu().numpy()
+    ng = out["candidate_embed"].neg.float().cpu().numpy()
+    for name in orc.LOSS_NAMES:
+        lb = None if name in orc.COSINE_LOSSES else "bf16"
+        ref, _, _, _ = orc.lean_loss(name, q, ps, ng, orc.Config(**cfg_kw), with_grad=True, logits_dtype=lb)
+        assert float(got[f"loss/{name}"]) == pytest.approx(ref, rel=4e-3, abs=4e-3), name

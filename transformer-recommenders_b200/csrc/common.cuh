@@ -50,7 +50,7 @@ enum RowSlot {
   S_DENS, S_POS, S_NCOUNT, S_NSUM, S_NSQ, S_NMIN, S_NMAX, S_USED
 };
 int launch_rowloss_reduce(const double* row_out, int64_t m, int64_t c, int n_hard, double* losses_out,
-                          double* stats_out, cudaStream_t s);
+                          double* stats_out, cudaStream_t s, const int* dyn_m_cn = nullptr);
 
 // ---- small device helpers --------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

@@ -791,8 +791,13 @@ fused_finalize_kernel(const float* __restrict__ part_o, const float* __restrict_
 __global__ void __launch_bounds__(256)
 fused_finalize_all_kernel(const float* __restrict__ part_all, const float* __restrict__ t_raw,
                           const float* __restrict__ zref, int m, int spl, int cosine, int logits_bf16,
-                          float scale, float margin, double* __restrict__ row_out) {
+                          float scale, float margin, double* __restrict__ row_out,
+                          const FusedDyn* __restrict__ dyn) {
   using namespace fk;
+  if (dyn) {
+    m = dyn->m;
+    spl = dyn->spl;
+  }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const int rb = i / BM, rl = i % BM;
@@ -1287,6 +1292,57 @@ extern "C" size_t xr_fused_pool_all_workspace_bytes(int64_t m, int64_t cn, int64
   return carve_fused_ws(nullptr, m, pl.n_items).bytes + fused_all_extra_bytes(m);
 }
 
+// (m, cn) exact, or -- `dynamic` -- upper bounds with the real shape and plan in ws.dyn (written by
+// fused_plan_kernel earlier on the stream), exactly as fused_launch_all does for the train loss
+static int fused_all_launch(const void* q, const void* pos, const void* neg, long long m, long long cn,
+                            int cosine, const xr_loss_config* cfg, const FusedWs& ws, bool dynamic,
+                            double* row_out, double* losses_out, double* stats_out, cudaStream_t s) {
+  const int n_sm = sm_count();
+  const FusedPlan pl = make_plan(m, cn, n_sm);
+  const FusedDyn* dyn_main = dynamic ? ws.dyn : nullptr;
+  const FusedDyn* dyn_diag = dynamic ? ws.dyn + 1 : nullptr;
+  XR_CUDA(cudaMemsetAsync(ws.flags, 0, 256, s));
+  int rc;
+  CUtensorMap tq, tp, tn;
+  if ((rc = make_tmap_bf16_rows(&tq, q, m, fk::D, fk::D, fk::BM))) return rc;
+  if ((rc = make_tmap_bf16_rows(&tp, pos, m, fk::D, fk::D, fk::BN))) return rc;
+  if ((rc = make_tmap_bf16_rows(&tn, neg, cn, fk::D, fk::D, fk::BN))) return rc;
+  FusedParams pd{};
+  pd.dyn = dyn_diag;
+  pd.m = (int)m; pd.cn = (int)m; pd.nt_count = 0; pd.spl = 1; pd.tiles_per_split = 2;
+  pd.n_items = pl.rb; pd.t_out = ws.t; pd.hang_flag = ws.flags;
+  if ((rc = launch_fused<fk::KIND_DIAG>(tq, tp, pd, pl.rb < n_sm ? pl.rb : n_sm, s))) return rc;
+  const float* zref = nullptr;
+  if (!cosine && !cfg->mask_false_negatives) {
+    unsigned* nmax = (unsigned*)(ws.flags + 8);
+    negnorm_max_kernel<<<n_sm * 4, 256, 0, s>>>((const __nv_bfloat16*)neg, cn, nmax, dyn_main);
+    XR_LAUNCH_CHECK("negnorm_max");
+    zref_bound_kernel<<<n_sm * 4, 256, 0, s>>>((const __nv_bfloat16*)q, ws.t, nmax, m, cfg->scale,
+                                               cfg->logits_bf16, ws.zref, dyn_main);
+    XR_LAUNCH_CHECK("zref_bound");
+    zref = ws.zref;
+  }
+  FusedParams p{};
+  p.dyn = dyn_main;
+  p.m = (int)m; p.cn = (int)cn; p.nt_count = pl.nt; p.spl = pl.spl; p.tiles_per_split = pl.tps;
+  p.n_items = pl.n_items; p.mask_fn = cfg->mask_false_negatives; p.logits_bf16 = cfg->logits_bf16;
+  p.with_grad = 0; p.scale = cfg->scale; p.margin = cfg->margin;
+  p.t = ws.t; p.zref = zref; p.part_all = ws.part_o; p.hang_flag = ws.flags;
+  const int grid = dynamic ? n_sm : (pl.n_items < n_sm ? pl.n_items : n_sm);
+  const bool prof = g_prof_on && g_prof_n < kProfRing && !dynamic;
+  if (prof) cudaEventRecord(g_prof_ev[g_prof_n][0], s);
+  rc = cosine ? launch_fused<fk::KIND_ALL_COS>(tq, tn, p, grid, s)
+              : launch_fused<fk::KIND_ALL_DOT>(tq, tn, p, grid, s);
+  if (prof) cudaEventRecord(g_prof_ev[g_prof_n++][1], s);
+  if (rc) return rc;
+  fused_finalize_all_kernel<<<(int)((m + 255) / 256), 256, 0, s>>>(
+      ws.part_o, ws.t, zref, (int)m, pl.spl, cosine, cfg->logits_bf16, cfg->scale, cfg->margin, row_out,
+      dyn_main);
+  XR_LAUNCH_CHECK("fused_finalize_all");
+  return launch_rowloss_reduce(row_out, m, cn + 1, 0, losses_out, stats_out, s,
+                               reinterpret_cast<const int*>(dyn_main));
+}
+
 extern "C" int xr_fused_pool_all(const void* q, const void* pos, const void* neg, int64_t m,
                                  int64_t cn, int64_t dim, int cosine, const xr_loss_config* cfg,
                                  double* losses_out, double* stats_out, void* workspace,
@@ -1302,47 +1358,11 @@ extern "C" int xr_fused_pool_all(const void* q, const void* pos, const void* neg
                "xr_fused_pool_all: workspace too small");
   int rc;
   if ((rc = check_fused_device("xr_fused_pool_all"))) return rc;
-  cudaStream_t s = as_stream(stream);
-  const int n_sm = sm_count();
-  const FusedPlan pl = make_plan(m, cn, n_sm);
+  const FusedPlan pl = make_plan(m, cn, sm_count());
   const FusedWs ws = carve_fused_ws(workspace, m, pl.n_items);
   double* row_out = (double*)((uint8_t*)workspace + ws.bytes);
-  XR_CUDA(cudaMemsetAsync(ws.flags, 0, 256, s));
-
-  CUtensorMap tq, tp, tn;
-  if ((rc = make_tmap_bf16_rows(&tq, q, m, fk::D, fk::D, fk::BM))) return rc;
-  if ((rc = make_tmap_bf16_rows(&tp, pos, m, fk::D, fk::D, fk::BN))) return rc;
-  if ((rc = make_tmap_bf16_rows(&tn, neg, cn, fk::D, fk::D, fk::BN))) return rc;
-  FusedParams pd{};
-  pd.m = (int)m; pd.cn = (int)m; pd.nt_count = 0; pd.spl = 1; pd.tiles_per_split = 2;
-  pd.n_items = pl.rb; pd.t_out = ws.t; pd.hang_flag = ws.flags;
-  if ((rc = launch_fused<fk::KIND_DIAG>(tq, tp, pd, pl.rb < n_sm ? pl.rb : n_sm, s))) return rc;
-  const float* zref = nullptr;
-  if (!cosine && !cfg->mask_false_negatives) {
-    unsigned* nmax = (unsigned*)(ws.flags + 8);
-    negnorm_max_kernel<<<n_sm * 4, 256, 0, s>>>((const __nv_bfloat16*)neg, cn, nmax, nullptr);
-    XR_LAUNCH_CHECK("negnorm_max");
-    zref_bound_kernel<<<n_sm * 4, 256, 0, s>>>((const __nv_bfloat16*)q, ws.t, nmax, m, cfg->scale,
-                                               cfg->logits_bf16, ws.zref, nullptr);
-    XR_LAUNCH_CHECK("zref_bound");
-    zref = ws.zref;
-  }
-  FusedParams p{};
-  p.m = (int)m; p.cn = (int)cn; p.nt_count = pl.nt; p.spl = pl.spl; p.tiles_per_split = pl.tps;
-  p.n_items = pl.n_items; p.mask_fn = cfg->mask_false_negatives; p.logits_bf16 = cfg->logits_bf16;
-  p.with_grad = 0; p.scale = cfg->scale; p.margin = cfg->margin;
-  p.t = ws.t; p.zref = zref; p.part_all = ws.part_o; p.hang_flag = ws.flags;
-  const int grid = pl.n_items < n_sm ? pl.n_items : n_sm;
-  const bool prof = g_prof_on && g_prof_n < kProfRing;
-  if (prof) cudaEventRecord(g_prof_ev[g_prof_n][0], s);
-  rc = cosine ? launch_fused<fk::KIND_ALL_COS>(tq, tn, p, grid, s)
-              : launch_fused<fk::KIND_ALL_DOT>(tq, tn, p, grid, s);
-  if (prof) cudaEventRecord(g_prof_ev[g_prof_n++][1], s);
-  if (rc) return rc;
-  fused_finalize_all_kernel<<<(int)((m + 255) / 256), 256, 0, s>>>(
-      ws.part_o, ws.t, zref, (int)m, pl.spl, cosine, cfg->logits_bf16, cfg->scale, cfg->margin, row_out);
-  XR_LAUNCH_CHECK("fused_finalize_all");
-  return launch_rowloss_reduce(row_out, m, cn + 1, 0, losses_out, stats_out, s);
+  return fused_all_launch(q, pos, neg, m, cn, cosine, cfg, ws, false, row_out, losses_out, stats_out,
+                          as_stream(stream));
 }
 
 // ---- the whole scoring-and-loss step, sync-free -------------------------------------------------
@@ -1491,6 +1511,65 @@ extern "C" int xr_pool_step(const int64_t* history_idx, const int64_t* pos_idx,
                              nullptr, loss_out, nullptr, w.fused, true, s, dtok ? &sc : nullptr)))
     return rc;
   return XR_OK;
+}
+
+// ---- the monitoring half of compute_losses inside the same sync-free sequence --------------------
+// trainer.py:250-263 logs LogitsStatistics and all seven losses every step.  Called right after
+// xr_pool_step on the SAME stream and workspace, this runs both all-losses passes on the operands the
+// step gathered (dot: q / pos / neg as they are; cosine: their row-normalised copies,
+// losses.py:206-208), still without a device->host copy: CUDA-graph capturable together with the step.
+struct MonitorWs {
+  __nv_bfloat16 *qn, *pn, *nn;
+  float* inv;
+  double* row_out;
+  size_t bytes;
+};
+static MonitorWs carve_monitor_ws(void* base, long long n_pos) {
+  MonitorWs w;
+  uint8_t* p = (uint8_t*)base;
+  const size_t n = (size_t)n_pos;
+  w.qn = (__nv_bfloat16*)p;   p += align256(n * fk::D * 2);
+  w.pn = (__nv_bfloat16*)p;   p += align256(n * fk::D * 2);
+  w.nn = (__nv_bfloat16*)p;   p += align256(n * fk::D * 2);
+  w.inv = (float*)p;          p += align256(n * 4);
+  w.row_out = (double*)p;     p += align256(n * ROW_SLOTS * 8);
+  w.bytes = (size_t)(p - (uint8_t*)base);
+  return w;
+}
+
+extern "C" size_t xr_pool_step_monitor_workspace_bytes(int64_t n_pos, int64_t dim) {
+  if (dim != fk::D || n_pos <= 0) return 512;
+  return carve_step_ws(nullptr, n_pos).bytes + carve_monitor_ws(nullptr, n_pos).bytes;
+}
+
+extern "C" int xr_pool_step_monitor(int64_t n_pos, int64_t dim, const xr_loss_config* cfg,
+                                    double* losses_dot, double* losses_cos, double* stats_out,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  XR_CHECK_ARG(cfg && losses_dot && losses_cos && stats_out && workspace, "xr_pool_step_monitor: null pointer");
+  XR_CHECK_ARG(dim == fk::D && n_pos > 0 && n_pos < (1ll << 30), "xr_pool_step_monitor: bad sizes");
+  XR_CHECK_ARG(cfg->num_hard_negatives == 0 && cfg->scale > 0.f,
+               "xr_pool_step_monitor: needs num_hard_negatives == 0 and scale > 0");
+  XR_CHECK_ARG(workspace_bytes >= xr_pool_step_monitor_workspace_bytes(n_pos, dim) &&
+                   (uintptr_t)workspace % 256 == 0,
+               "xr_pool_step_monitor: workspace too small or misaligned");
+  int rc;
+  if ((rc = check_fused_device("xr_pool_step_monitor"))) return rc;
+  cudaStream_t s = as_stream(stream);
+  const StepWs w = carve_step_ws(workspace, n_pos);
+  const MonitorWs mw = carve_monitor_ws((uint8_t*)workspace + w.bytes, n_pos);
+  // dot family + statistics on the gathered operands
+  if ((rc = fused_all_launch(w.q, w.pos, w.neg, n_pos, n_pos, 0, cfg, w.fused, true, mw.row_out,
+                             losses_dot, stats_out, s)))
+    return rc;
+  // cosine family on the row-normalised copies (all n_pos rows: the buffers are sized by n_pos and
+  // rows past the counts are masked by the kernels)
+  if ((rc = xr_normalize_rows(w.q, n_pos, fk::D, XR_BF16, 1e-8f, mw.qn, XR_BF16, mw.inv, stream))) return rc;
+  if ((rc = xr_normalize_rows(w.pos, n_pos, fk::D, XR_BF16, 1e-8f, mw.pn, XR_BF16, mw.inv, stream))) return rc;
+  if ((rc = xr_normalize_rows(w.neg, n_pos, fk::D, XR_BF16, 1e-8f, mw.nn, XR_BF16, mw.inv, stream))) return rc;
+  xr_loss_config ccfg = *cfg;
+  ccfg.logits_bf16 = 0;   // cosine logits stay fp32 under autocast
+  return fused_all_launch(mw.qn, mw.pn, mw.nn, n_pos, n_pos, 1, &ccfg, w.fused, true, mw.row_out,
+                          losses_cos, nullptr, s);
 }
 
 // ---- retrieval: group maxima of Q . Cat^T on the tensor cores -----------------------------------

@@ -39,3 +39,9 @@ extern "C" int xr_fused_pool_all(const void*, const void*, const void*, int64_t,
   xr::set_error("xr_fused_pool_all: tcgen05 kernels not compiled into this build");
   return XR_E_UNSUPPORTED;
 }
+extern "C" size_t xr_pool_step_monitor_workspace_bytes(int64_t, int64_t) { return 0; }
+extern "C" int xr_pool_step_monitor(int64_t, int64_t, const xr_loss_config*, double*, double*, double*, void*,
+                                    size_t, void*) {
+  xr::set_error("xr_pool_step_monitor: tcgen05 kernels not compiled into this build");
+  return XR_E_UNSUPPORTED;
+}

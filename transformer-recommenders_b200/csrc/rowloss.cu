@@ -46,7 +46,12 @@ rowloss_kernel(const float* __restrict__ logits, int64_t m, int64_t c, int64_t l
 // single block, fixed order: fold the per-row slots into the 7 loss sums and the stats block
 __global__ void __launch_bounds__(1024)
 rowloss_reduce_kernel(const double* __restrict__ row_out, int64_t m, int64_t c, int n_hard,
-                      double* __restrict__ losses_out, double* __restrict__ stats_out) {
+                      double* __restrict__ losses_out, double* __restrict__ stats_out,
+                      const int* __restrict__ dyn_m_cn) {
+  if (dyn_m_cn) {   // shape known only on the device (sync-free step): {rows, pool size}
+    m = dyn_m_cn[0];
+    c = (int64_t)dyn_m_cn[1] + 1;
+  }
   constexpr int NS = 13;  // 6 losses + dens + pos sum + pos sq + ncount + nsum + nsq + (min/max apart)
   __shared__ double s_sum[32][NS];
   __shared__ double s_mm[32][4];
@@ -113,8 +118,8 @@ rowloss_reduce_kernel(const double* __restrict__ row_out, int64_t m, int64_t c, 
 
 // shared with the tensor-core all-losses pass (fused_loss_sm100.cu), which fills the same row slots
 int launch_rowloss_reduce(const double* row_out, int64_t m, int64_t c, int n_hard, double* losses_out,
-                          double* stats_out, cudaStream_t s) {
-  rowloss_reduce_kernel<<<1, 1024, 0, s>>>(row_out, m, c, n_hard, losses_out, stats_out);
+                          double* stats_out, cudaStream_t s, const int* dyn_m_cn) {
+  rowloss_reduce_kernel<<<1, 1024, 0, s>>>(row_out, m, c, n_hard, losses_out, stats_out, dyn_m_cn);
   XR_LAUNCH_CHECK("rowloss_reduce");
   return XR_OK;
 }
@@ -159,7 +164,7 @@ extern "C" int xr_rowloss(const float* logits, int64_t m, int64_t c, int64_t ld,
   }
   if (losses_out || stats_out) {
     rowloss_reduce_kernel<<<1, 1024, 0, s>>>(row_out, m, c, cfg->num_hard_negatives, losses_out,
-                                             stats_out);
+                                             stats_out, nullptr);
     XR_LAUNCH_CHECK("rowloss_reduce");
   }
   return XR_OK;

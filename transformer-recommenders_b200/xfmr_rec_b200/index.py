@@ -32,6 +32,7 @@ class ExactIndexConfig(pydantic.BaseModel):
     index_metric: Literal["dot", "cosine"] = "cosine"
     dtype: Literal["bf16", "fp32"] = "bf16"
     max_score_bytes: int = 1 << 30  # materialised-score budget of the unfused path
+    max_groupmax_bytes: int = 12 << 30  # group-maxima budget of the fused path: larger query sets run in blocks
     fused: bool = True  # tensor-core group-max path when the device / dtype allow it
 
 
@@ -110,6 +111,23 @@ class ExactIndex:
         else:
             q = q.to(cat.dtype).contiguous()
         u, n = q.size(0), cat.size(0)
+        # bound the group-maxima buffer (U x N/16 fp32): query blocks of at most max_groupmax_bytes
+        u_blk = max(256, (self.config.max_groupmax_bytes // max(1, (n + 15) // 16 * 4)) // 256 * 256)
+        if u > u_blk:
+            if exclude_rows is not None and isinstance(exclude_rows, tuple):
+                offs, flat = exclude_rows
+                offs_h = offs.tolist()
+            parts = []
+            for lo in range(0, u, u_blk):
+                hi = min(u, lo + u_blk)
+                if exclude_rows is None:
+                    ex = None
+                elif isinstance(exclude_rows, tuple):
+                    ex = (offs[lo:hi + 1] - offs_h[lo], flat[offs_h[lo]:max(offs_h[hi], offs_h[lo] + 1)])
+                else:
+                    ex = exclude_rows[lo:hi]
+                parts.append(self.search_batch(queries[lo:hi], ex, top_k))
+            return torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
         csr = None
         if exclude_rows is not None:
             csr = exclude_rows if isinstance(exclude_rows, tuple) else ops._csr(exclude_rows, self.device)

@@ -377,6 +377,25 @@ def _merge_stats(acc, s):
     return out
 
 
+def stats_dict(s: list[float]) -> dict[str, float]:
+    """The LogitsStatistics log dict (losses.py:392-404) from the device statistics block: keys and
+    empty-set behaviour as the reference (unbiased std; a single element gives nan)."""
+    rows = s[1]
+    out = {"logits/neg/density": (s[0] / rows) if rows > 0 else float("nan")}
+    for key, (cnt, tot, sq, mn, mx) in {
+        "pos": (rows, s[2], s[3], s[4], s[5]),
+        "neg": (s[6], s[7], s[8], s[9], s[10]),
+    }.items():
+        if cnt > 0:
+            mean = tot / cnt
+            var = (sq - cnt * mean * mean) / (cnt - 1) if cnt > 1 else float("nan")
+            out[f"logits/{key}/mean"] = mean
+            out[f"logits/{key}/std"] = max(var, 0.0) ** 0.5 if var == var else float("nan")
+            out[f"logits/{key}/min"] = mn
+            out[f"logits/{key}/max"] = mx
+    return out
+
+
 class LogitsStatistics(EmbedLoss):
     """Monitoring statistics over the dot-product logits (xfmr_rec/losses.py:375-405).
 
@@ -388,21 +407,7 @@ class LogitsStatistics(EmbedLoss):
     def forward(self, query_embed, candidate_embed, target=None) -> dict[str, float]:
         with torch.no_grad():
             _, stats, _ = self._evaluate(query_embed, candidate_embed, target, want_stats=True)
-        s = stats.tolist()  # the single host sync
-        rows = s[1]
-        out = {"logits/neg/density": (s[0] / rows) if rows > 0 else float("nan")}
-        for key, (cnt, tot, sq, mn, mx) in {
-            "pos": (rows, s[2], s[3], s[4], s[5]),
-            "neg": (s[6], s[7], s[8], s[9], s[10]),
-        }.items():
-            if cnt > 0:
-                mean = tot / cnt
-                var = (sq - cnt * mean * mean) / (cnt - 1) if cnt > 1 else float("nan")
-                out[f"logits/{key}/mean"] = mean
-                out[f"logits/{key}/std"] = max(var, 0.0) ** 0.5 if var == var else float("nan")
-                out[f"logits/{key}/min"] = mn
-                out[f"logits/{key}/max"] = mx
-        return out
+        return stats_dict(stats.tolist())  # the single host sync
 
 
 class AlignmentLoss(EmbedLoss):
@@ -478,18 +483,4 @@ def evaluate_all(config, query_embed, candidate_embed, target=None, *, train_los
     if torch.is_grad_enabled() and query_embed.requires_grad:
         train_cls = {c.__name__: c for c in LOSS_CLASSES}[train_loss]
         out[f"loss/{train_loss}"] = train_cls(config)(query_embed, candidate_embed, target)
-    stat_mod = LogitsStatistics(config)
-    s = stats.tolist()
-    rows = s[1]
-    sd = {"logits/neg/density": (s[0] / rows) if rows > 0 else float("nan")}
-    for key, (cnt, tot, sq, mn, mx) in {"pos": (rows, s[2], s[3], s[4], s[5]),
-                                        "neg": (s[6], s[7], s[8], s[9], s[10])}.items():
-        if cnt > 0:
-            mean = tot / cnt
-            var = (sq - cnt * mean * mean) / (cnt - 1) if cnt > 1 else float("nan")
-            sd[f"logits/{key}/mean"] = mean
-            sd[f"logits/{key}/std"] = max(var, 0.0) ** 0.5 if var == var else float("nan")
-            sd[f"logits/{key}/min"] = mn
-            sd[f"logits/{key}/max"] = mx
-    del stat_mod
-    return out, sd
+    return out, stats_dict(stats.tolist())

@@ -37,7 +37,7 @@ class PoolLossStep:
     def __init__(self, embeddings: ItemEmbeddings, loss: EmbedLoss, batch_size: int, seq_len: int, *,
                  token_dtype: torch.dtype = torch.bfloat16, grad_dtype: torch.dtype | None = None,
                  want_grad: bool = True, logits_bf16: bool | None = None, use_graph: bool = True,
-                 check_indices: bool = False) -> None:
+                 check_indices: bool = False, monitor: bool = False) -> None:
         name = type(loss).__name__
         if name not in _STEP_KINDS:
             raise NotImplementedError(
@@ -77,7 +77,13 @@ class PoolLossStep:
             self.loss_buf = torch.zeros(2, dtype=torch.float64, device=dev)
             self.counts = torch.zeros(2, dtype=torch.int64, device=dev)
             self.err = torch.zeros(1, dtype=torch.int32, device=dev) if check_indices else None
-            nbytes = N.lib().xr_pool_step_workspace_bytes(n, self.d)
+            nbytes = (N.lib().xr_pool_step_monitor_workspace_bytes(n, self.d) if monitor
+                      else N.lib().xr_pool_step_workspace_bytes(n, self.d))
+            # monitor: LogitsStatistics + all seven losses (trainer.py:250-263) in the same sequence
+            self.monitor = bool(monitor)
+            self.mon_dot = torch.zeros(N.XR_NUM_LOSSES, dtype=torch.float64, device=dev)
+            self.mon_cos = torch.zeros(N.XR_NUM_LOSSES, dtype=torch.float64, device=dev)
+            self.mon_stats = torch.zeros(N.XR_STATS_SLOTS, dtype=torch.float64, device=dev)
             self.ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
             off = (-self.ws.data_ptr()) % 256
             self._ws_ptr, self._ws_bytes = self.ws.data_ptr() + off, nbytes
@@ -97,6 +103,10 @@ class PoolLossStep:
                ops._DT[self.dtok.dtype] if self.dtok is not None else N.XR_F32, ops._p(self.loss_buf),
                ops._p(self.counts), ops._p(self.err), C.c_void_p(self._ws_ptr), self._ws_bytes,
                ops._stream())
+        if self.monitor:
+            N.call("xr_pool_step_monitor", self.n_pos, self.d, C.byref(self.cfg), ops._p(self.mon_dot),
+                   ops._p(self.mon_cos), ops._p(self.mon_stats), C.c_void_p(self._ws_ptr), self._ws_bytes,
+                   ops._stream())
 
     def _capture(self) -> None:
         with torch.cuda.device(self.device):
@@ -142,6 +152,21 @@ class PoolLossStep:
     def __call__(self, token_embeddings, history_item_idx, pos_item_idx, neg_item_idx):
         self.load(token_embeddings, history_item_idx, pos_item_idx, neg_item_idx)
         return self.run()
+
+    def loss_dict(self) -> tuple[dict[str, torch.Tensor], dict[str, float]]:
+        """What ``compute_losses`` logs (trainer.py:250-263) for the last ``run()`` of a
+        ``monitor=True`` step: ({"loss/<Name>": 0-dim fp32 tensor} for all seven losses, the
+        LogitsStatistics dict).  The tensors are device-side; building the statistics dict is the
+        only device->host copy (the reference does nine ``.item()`` syncs plus eight logit passes)."""
+        if not self.monitor:
+            raise RuntimeError("PoolLossStep(monitor=True) is needed for loss_dict()")
+        from .losses import LOSS_CLASSES, stats_dict
+
+        out = {}
+        for cls in LOSS_CLASSES:
+            src = self.mon_cos if cls.COSINE else self.mon_dot
+            out[f"loss/{cls.__name__}"] = src[N.LOSS_KIND[cls.__name__]].to(torch.float32)
+        return out, stats_dict(self.mon_stats.tolist())
 
     def row_counts(self) -> tuple[int, int]:
         """(M_a, M) of the last step — a device->host copy; not needed by the step itself."""
