@@ -315,6 +315,17 @@ size_t xr_topk_merge_workspace_bytes(int64_t u, int64_t k);
 int xr_topk_merge(const float* scores, const int64_t* ids, int64_t u, int64_t gk, int64_t k,
                   float* out_scores, int64_t* out_idx, void* workspace, void* stream);
 
+/* Sharded retrieval exchange as ONE kernel over peer memory: all-gather + merge without NCCL.
+ * peer_scores_host / peer_ids_host: HOST arrays of n_peers DEVICE pointers, entry g addressing
+ * rank g's (U, k) fp32 scores / int64 global ids (ids < 2^32, -1 = none) through a peer mapping
+ * (CUDA IPC / symmetric memory; entry `rank` is the caller's own buffer).  The caller orders the
+ * kernel after a cross-GPU barrier that follows every rank's writes.  Same total order as
+ * xr_topk_merge (score desc, id asc): the result equals the single-GPU search bit for bit.
+ * workspace: >= xr_topk_merge_workspace_bytes(u, k).                                          */
+int xr_topk_merge_peers(const void* const* peer_scores_host, const void* const* peer_ids_host,
+                        int n_peers, int64_t u, int64_t k, float* out_scores, int64_t* out_idx,
+                        void* workspace, void* stream);
+
 /* scores[u,n] = q_u . cat_n (* q_inv_norm[u] * cat_inv_norm[n] when given), fp32 accumulate;
  * exclusion: for every (u, e) pair in the CSR lists excl_offsets/excl_ids (global ids), the
  * score of column e - col_offset is set to -inf (the prefilter of index.py:239-247).          */

@@ -8,6 +8,8 @@
 #include "common.cuh"
 #include "rowloss.cuh"
 
+#include <cstdint>
+
 namespace xr {
 
 template <typename T>
@@ -192,7 +194,8 @@ __device__ __forceinline__ void sampled_logits384_row(const T* __restrict__ q_ro
                                                       const int64_t* __restrict__ idx_row,
                                                       int64_t n_table_rows, int64_t c, float qi,
                                                       const float* __restrict__ table_inv,
-                                                      float* out) {
+                                                      float* out, int64_t c_lo = 0,
+                                                      int64_t c_hi = INT64_MAX) {
   constexpr int E = RowVec<T>::E, VECS = FD / E, IT = (VECS + 31) / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = ROW_THREADS / 32;
   float qr[IT][E];
@@ -204,7 +207,8 @@ __device__ __forceinline__ void sampled_logits384_row(const T* __restrict__ q_ro
 #pragma unroll
       for (int k = 0; k < E; ++k) qr[t][k] = 0.f;
   }
-  for (int64_t j0 = (int64_t)warp * 4; j0 < c; j0 += nwarp * 4) {
+  if (c_hi < c) c = c_hi;   // this block's slice of the candidates [c_lo, c_hi)
+  for (int64_t j0 = c_lo + (int64_t)warp * 4; j0 < c; j0 += nwarp * 4) {
     int64_t row[4];
     bool valid[4];
 #pragma unroll
@@ -259,9 +263,13 @@ sampled_logits384_kernel(const T* __restrict__ q, const T* __restrict__ table,
                          const int64_t* __restrict__ cand_idx, int64_t n_table_rows, int64_t m,
                          int64_t c, const float* __restrict__ q_inv,
                          const float* __restrict__ table_inv, float* __restrict__ logits, int64_t ld) {
+  // few query rows with many candidates each (the retrieval re-score: 256 x 2,048): gridDim.y
+  // blocks share a row, each taking a contiguous slice of its candidates (a multiple of 32)
+  const int64_t per = ((c + gridDim.y - 1) / gridDim.y + 31) / 32 * 32;
+  const int64_t c_lo = (int64_t)blockIdx.y * per;
   for (int64_t i = blockIdx.x; i < m; i += gridDim.x)
     sampled_logits384_row<T>(q + i * FD, table, cand_idx + i * c, n_table_rows, c,
-                             q_inv ? q_inv[i] : 1.f, table_inv, logits + i * ld);
+                             q_inv ? q_inv[i] : 1.f, table_inv, logits + i * ld, c_lo, c_lo + per);
 }
 
 // dq_i = sum_j g[j] * tinv(j) * table[idx[j]]  (+ cosine chain rule): warps split the
@@ -475,12 +483,22 @@ extern "C" int xr_logits_sampled(const void* q, const void* table, int64_t n_row
   if (m == 0 || c == 0) return XR_OK;
   cudaStream_t s = as_stream(stream);
   if (dim == FD) {   // BASELINE config 3 shape: rows in flight instead of one row per warp
+    // fill the machine when there are fewer rows than ~8 blocks per SM: split the candidates
+    int gy = 1;
+    const int64_t want = (int64_t)sm_count() * 8;
+    if (m < want && c >= 256) {
+      gy = (int)((want + m - 1) / m);
+      const int max_gy = (int)(c / 128);   // at least 128 candidates per block
+      if (gy > max_gy) gy = max_gy;
+      if (gy < 1) gy = 1;
+    }
+    const dim3 grid((unsigned)row_grid(m), (unsigned)gy);
     if (dtype == XR_F32)
-      sampled_logits384_kernel<float><<<row_grid(m), ROW_THREADS, 0, s>>>(
+      sampled_logits384_kernel<float><<<grid, ROW_THREADS, 0, s>>>(
           (const float*)q, (const float*)table, cand_idx, n_rows, m, c, q_inv_norm, table_inv_norm,
           logits, ld);
     else
-      sampled_logits384_kernel<__nv_bfloat16><<<row_grid(m), ROW_THREADS, 0, s>>>(
+      sampled_logits384_kernel<__nv_bfloat16><<<grid, ROW_THREADS, 0, s>>>(
           (const __nv_bfloat16*)q, (const __nv_bfloat16*)table, cand_idx, n_rows, m, c, q_inv_norm,
           table_inv_norm, logits, ld);
     XR_LAUNCH_CHECK("sampled_logits384");

@@ -211,6 +211,57 @@ topk_generic_kernel(const float* __restrict__ scores, const int64_t* __restrict_
   for (int i = threadIdx.x; i < k; i += TK_THREADS) o[i] = i < cnt ? s_keys[i] : 0ull;
 }
 
+// ---- all-gather + merge as ONE kernel over peer memory (sharded retrieval) ----------------------
+// Every rank leaves its per-shard (U, k) {score, id} lists in a buffer its peers can address over
+// NVLink / NVSwitch (CUDA IPC / symmetric memory); after a cross-GPU barrier each rank's merge
+// kernel LOADS the G lists of a query straight from the peers -- volatile-free plain loads through
+// the peer mappings -- while building its selection keys: no NCCL all-gather, no staging copy, no
+// permute.  Block per query; the candidate e in [0, G k) lives at peer e / k, slot e % k.
+constexpr int TK_MAX_PEERS = 16;
+struct PeerLists {
+  const float* scores[TK_MAX_PEERS];     // each (U, k) fp32, row-major
+  const int64_t* ids[TK_MAX_PEERS];      // each (U, k) int64 global ids, -1 = none
+};
+__global__ void __launch_bounds__(TK_THREADS)
+topk_merge_peers_kernel(const PeerLists peers, int n_peers, int k, uint64_t* __restrict__ out_keys) {
+  __shared__ uint64_t s_keys[TK_CAP];
+  __shared__ int s_count;
+  __shared__ uint64_t s_tau;
+  TopkState st{s_keys, &s_count, &s_tau};
+  const int64_t u = blockIdx.x;
+  if (threadIdx.x == 0) {
+    s_count = 0;
+    s_tau = 0ull;
+  }
+  __syncthreads();
+  const int64_t total = (int64_t)n_peers * k;
+  const int64_t iters = (total + TK_PER_ITER - 1) / TK_PER_ITER;
+  for (int64_t it = 0; it < iters; ++it) {
+    if (*st.count > TK_CAP - TK_PER_ITER) compact_select(st, k);
+    const uint64_t tau = *st.tau;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int64_t e = it * TK_PER_ITER + r * TK_THREADS + threadIdx.x;
+      const bool in = e < total;
+      uint64_t key = 0;
+      if (in) {
+        const int g = (int)(e / k), j = (int)(e - (int64_t)g * k);
+        // peer memory is written by another GPU between launches: bypass the (non-coherent) L1
+        const int64_t id = __ldcg(peers.ids[g] + u * k + j);
+        const float sc = __ldcg(peers.scores[g] + u * k + j);
+        key = id < 0 ? 0ull : make_key(sc, (uint32_t)id);
+      }
+      offer(st, in && key > tau, key);
+    }
+    __syncthreads();
+  }
+  compact_select(st, k);
+  compact(st, k);
+  const int cnt = s_count < k ? s_count : k;
+  uint64_t* o = out_keys + u * (int64_t)k;
+  for (int i = threadIdx.x; i < k; i += TK_THREADS) o[i] = i < cnt ? s_keys[i] : 0ull;
+}
+
 // ---- streaming fast path over fp32 scores (16-byte aligned rows) --------------------------------
 // Super-blocks of 8 x 2048 scores with NO barrier inside: a score is compared against the float
 // threshold (one FSETP); the rare survivors build their 64-bit key, re-check it exactly and claim
@@ -546,6 +597,31 @@ extern "C" int xr_topk_merge(const float* scores, const int64_t* ids, int64_t u,
   topk_generic_kernel<2><<<dim3(1, (unsigned)u), TK_THREADS, 0, s>>>(
       scores, ids, nullptr, gk, gk, gk > 0 ? gk : 1, (int)k, final_keys);
   XR_LAUNCH_CHECK("topk_merge");
+  const int64_t total = u * k;
+  topk_emit_kernel<<<(unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0,
+                     s>>>(final_keys, total, 0, out_scores, out_idx);
+  XR_LAUNCH_CHECK("topk_emit");
+  return XR_OK;
+}
+
+extern "C" int xr_topk_merge_peers(const void* const* peer_scores_host, const void* const* peer_ids_host,
+                                   int n_peers, int64_t u, int64_t k, float* out_scores,
+                                   int64_t* out_idx, void* workspace, void* stream) {
+  XR_CHECK_ARG(peer_scores_host && peer_ids_host && out_scores && out_idx && workspace,
+               "xr_topk_merge_peers: null pointer");
+  XR_CHECK_ARG(n_peers >= 1 && n_peers <= TK_MAX_PEERS, "xr_topk_merge_peers: 1 <= n_peers <= %d", TK_MAX_PEERS);
+  XR_CHECK_ARG(u >= 0 && k >= 1 && k <= TK_MAX_K, "xr_topk_merge_peers: bad sizes");
+  if (u == 0) return XR_OK;
+  PeerLists pl{};
+  for (int g = 0; g < n_peers; ++g) {
+    XR_CHECK_ARG(peer_scores_host[g] && peer_ids_host[g], "xr_topk_merge_peers: null peer pointer");
+    pl.scores[g] = (const float*)peer_scores_host[g];
+    pl.ids[g] = (const int64_t*)peer_ids_host[g];
+  }
+  cudaStream_t s = as_stream(stream);
+  uint64_t* final_keys = (uint64_t*)workspace;
+  topk_merge_peers_kernel<<<(unsigned)u, TK_THREADS, 0, s>>>(pl, n_peers, (int)k, final_keys);
+  XR_LAUNCH_CHECK("topk_merge_peers");
   const int64_t total = u * k;
   topk_emit_kernel<<<(unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0,
                      s>>>(final_keys, total, 0, out_scores, out_idx);

@@ -86,6 +86,7 @@ PROTOTYPES = {
     "xr_topk": (_int, [_p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _sz, _p]),
     "xr_topk_merge_workspace_bytes": (_sz, [_i64, _i64]),
     "xr_topk_merge": (_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p]),
+    "xr_topk_merge_peers": (_int, [_p, _p, _int, _i64, _i64, _p, _p, _p, _p]),
     "xr_scores": (_int, [_p, _i64, _p, _i64, _i64, _int, _p, _p, _p, _i64, _p]),
     "xr_mask_excluded": (_int, [_p, _i64, _i64, _i64, _i64, _p, _p, _p]),
     "xr_score_groupmax": (_int, [_p, _i64, _p, _i64, _i64, _p, _i64, _p]),

@@ -48,13 +48,82 @@ def all_gather_merge(local_scores: torch.Tensor, local_ids: torch.Tensor, k: int
     return merge_fn(cat_s, cat_i, k)
 
 
-class ShardedIndex:
-    """Catalog sharded across the ranks of a process group."""
+class PeerExchange:
+    """The retrieval exchange over NVLink peer memory instead of NCCL: every rank keeps its per-shard
+    ``(U, k)`` lists in a symmetric-memory buffer (CUDA IPC mappings set up once by
+    ``torch.distributed._symmetric_memory``), one device-side barrier follows, and each rank's merge
+    kernel (``xr_topk_merge_peers``) loads all peers' lists straight through the peer mappings while
+    it selects: all-gather + merge in ONE kernel, no staging copy, no permute.
 
-    def __init__(self, local_index, *, group=None, merge_fn: Callable | None = None):
+    Two buffer sets alternate: search n+1's barrier on a rank is stream-ordered after its merge of
+    search n, so once barrier n+1 completes everywhere every merge of search n has finished and its
+    buffer set may be rewritten at search n+2 — one barrier per search is enough."""
+
+    def __init__(self, max_queries: int, k: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.u_max, self.k = int(max_queries), int(k)
+        self.slot_bytes = -(-(self.u_max * self.k * 12) // 256) * 256    # fp32 scores | int64 ids
+        self.buf = symm.empty(2 * self.slot_bytes, dtype=torch.uint8, device=device)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.turn = 0
+
+    def gather_merge(self, local_scores: torch.Tensor, local_ids: torch.Tensor, k: int):
+        import ctypes as C
+
+        from . import _native as N, ops
+
+        u = local_scores.size(0)
+        assert u <= self.u_max and k == self.k, "PeerExchange was sized for other (U, k)"
+        dev = local_scores.device
+        base = self.turn * self.slot_bytes
+        self.turn ^= 1
+        id_off = -(-(u * k * 4) // 16) * 16
+        mine_s = self.buf[base:base + u * k * 4].view(torch.float32).view(u, k)
+        mine_i = self.buf[base + id_off:base + id_off + u * k * 8].view(torch.int64).view(u, k)
+        mine_s.copy_(local_scores)
+        mine_i.copy_(local_ids)
+        self.hdl.barrier(channel=0)    # every rank's lists are in place (and search n-1's merges are done)
+        sp = (C.c_void_p * self.world)(*[p + base for p in self.ptrs])
+        ip = (C.c_void_p * self.world)(*[p + base + id_off for p in self.ptrs])
+        out_s = torch.empty((u, k), dtype=torch.float32, device=dev)
+        out_i = torch.empty((u, k), dtype=torch.int64, device=dev)
+        ws = ops._ws(N.lib().xr_topk_merge_workspace_bytes(u, k), dev)
+        with ops._on(dev):
+            N.call("xr_topk_merge_peers", sp, ip, self.world, u, k, ops._p(out_s), ops._p(out_i),
+                   ops._p(ws), ops._stream())
+        return out_s, out_i
+
+
+class ShardedIndex:
+    """Catalog sharded across the ranks of a process group.  ``exchange="peer"`` merges through
+    NVLink peer memory (:class:`PeerExchange`), ``"nccl"`` through two all-gathers + a merge;
+    ``"auto"`` tries peer memory first.  Both give the single-GPU result bit for bit."""
+
+    def __init__(self, local_index, *, group=None, merge_fn: Callable | None = None,
+                 exchange: str = "nccl"):
         self.local = local_index
         self.group = group
         self.merge_fn = merge_fn
+        self.exchange = exchange
+        self._peer: PeerExchange | None = None
+        self._peer_failed: str | None = None
+
+    def _peer_exchange(self, u: int, k: int, device):
+        if self._peer is not None and (u > self._peer.u_max or k != self._peer.k):
+            self._peer = None   # re-size (collective: every rank sees the same (U, k))
+        if self._peer is None and self._peer_failed is None:
+            try:
+                self._peer = PeerExchange(max(u, 256), k, device, self.group)
+            except Exception as e:  # symmetric memory not available on this system
+                if self.exchange == "peer":
+                    raise
+                self._peer_failed = f"{type(e).__name__}: {e}"
+        return self._peer
 
     @classmethod
     def from_catalog(cls, embeddings: torch.Tensor, config=None, device=None, *, group=None):
@@ -70,6 +139,11 @@ class ShardedIndex:
 
     def search_batch(self, queries: torch.Tensor, exclude_rows=None, top_k: int = 20):
         s, i = self.local.search_batch(queries, exclude_rows, top_k)
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if world > 1 and self.exchange in ("peer", "auto") and self.merge_fn is None and s.is_cuda:
+            px = self._peer_exchange(s.size(0), top_k, s.device)
+            if px is not None:
+                return px.gather_merge(s, i, top_k)
         return all_gather_merge(s, i, top_k, group=self.group, merge_fn=self.merge_fn)
 
 
