@@ -498,3 +498,37 @@ def test_search_batch_query_blocks_equal_one_shot(xr):
         s1, i1 = one.search_batch(q, ex, k)
         s2, i2 = blk.search_batch(q, ex, k)
         assert torch.equal(i1, i2) and torch.equal(s1, s2)
+
+
+def test_index_table_round_trip(xr, tmp_path):
+    """the items table in the reference's layout ({item_id, item_text, embedding:
+    fixed_size_list<float32>[D]}, Parquet) written by save_table and reopened by load_table gives the
+    same search results; a table produced WITHOUT this package (plain pyarrow, as the reference's data
+    pipeline writes it) opens too."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+
+    rng = np.random.default_rng(8)
+    n, d, k = 3000, 384, 20
+    emb = rng.standard_normal((n, d)).astype(np.float32)
+    data = {"item_id": [f"m{i}" for i in range(n)], "item_text": [f"title {i}" for i in range(n)],
+            "embedding": emb}
+    idx = xr.index.ExactIndex(xr.index.ExactIndexConfig(dtype="fp32")).index_data(data)
+    q = torch.from_numpy(rng.standard_normal((5, d)).astype(np.float32)).cuda()
+    s0, i0 = idx.search_batch(q, [[1, 2], [], [7], [], []], k)
+    p = tmp_path / "items.parquet"
+    idx.save_table(str(p), embeddings=torch.from_numpy(emb))
+    back = xr.index.ExactIndex.load_table(str(p))
+    assert back.config == idx.config and back.ids == idx.ids and back.columns == idx.columns
+    s1, i1 = back.search_batch(q, [[1, 2], [], [7], [], []], k)
+    assert torch.equal(i0, i1) and torch.equal(s0, s1)
+    one = back.search(emb[11], exclude_item_ids=["m11"], top_k=5)
+    assert "m11" not in one["item_id"] and one["item_text"][0].startswith("title ")
+    # a foreign table with the reference's columns
+    t = pa.table({"item_id": pa.array(data["item_id"]), "item_text": pa.array(data["item_text"]),
+                  "embedding": pa.FixedSizeListArray.from_arrays(pa.array(emb.reshape(-1)), d)})
+    p2 = tmp_path / "foreign.parquet"
+    pq.write_table(t, str(p2))
+    fx = xr.index.ExactIndex.load_table(str(p2), xr.index.ExactIndexConfig(dtype="fp32"))
+    s2, i2 = fx.search_batch(q, [[1, 2], [], [7], [], []], k)
+    assert torch.equal(i0, i2) and torch.equal(s0, s2)

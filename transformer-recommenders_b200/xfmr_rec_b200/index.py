@@ -214,6 +214,51 @@ class ExactIndex:
                     "row_offset": self.row_offset}, p / "exact_index.pt")
         (p / "config.json").write_text(json.dumps(self.config.model_dump()))
 
+    # -- persistence in the reference's table layout ----------------------------
+    # The reference keeps items as an Arrow table {item_id, item_text, embedding: fixed_size_list
+    # <float32>[D]} (the dataset handed to index_data, index.py:135-176, and what LanceDB stores).
+    # These two write / read exactly that layout as Parquet, so a catalog indexed by either side can
+    # be opened by the other; the search structure itself needs no persistence (there is none: the
+    # index IS the embedding matrix).
+    def save_table(self, path: str, *, embeddings: torch.Tensor | None = None) -> None:
+        """Write ``{id_col, stored columns..., embedding_col}`` as a Parquet file.  ``embeddings``:
+        the ORIGINAL fp32 rows if the caller still has them; otherwise the index's own rows (unit
+        norm and/or bf16-rounded for the cosine / bf16 configuration) are written."""
+        import pyarrow as pa
+        import pyarrow.parquet as pq
+
+        assert self.catalog is not None, "index_data / set_catalog first"
+        emb = (embeddings if embeddings is not None else self.catalog).detach().float().cpu().numpy()
+        n, d = emb.shape
+        ids = self.ids if self.ids is not None else [str(r + self.row_offset) for r in range(n)]
+        cols = {self.config.id_col: pa.array(ids, pa.string())}
+        for c, vals in self.columns.items():
+            cols[c] = pa.array(vals)
+        cols[self.config.embedding_col or "embedding"] = pa.FixedSizeListArray.from_arrays(
+            pa.array(np.ascontiguousarray(emb).reshape(-1), pa.float32()), d)
+        meta = {b"xfmr_rec_b200.config": self.config.model_dump_json().encode(),
+                b"xfmr_rec_b200.row_offset": str(self.row_offset).encode()}
+        pq.write_table(pa.table(cols).replace_schema_metadata(meta), path)
+
+    @classmethod
+    def load_table(cls, path: str, config: ExactIndexConfig | None = None, device=None) -> "ExactIndex":
+        """Open a Parquet / Arrow items table (written by ``save_table`` or by the reference's data
+        pipeline: ``item_id, item_text, embedding``) and index it."""
+        import pyarrow.parquet as pq
+
+        table = pq.read_table(path)
+        meta = table.schema.metadata or {}
+        if config is None and b"xfmr_rec_b200.config" in meta:
+            config = ExactIndexConfig(**json.loads(meta[b"xfmr_rec_b200.config"]))
+        self = cls(config, device, row_offset=int(meta.get(b"xfmr_rec_b200.row_offset", b"0")))
+        cfg = self.config
+        ecol = table.column(cfg.embedding_col).combine_chunks()
+        d = ecol.type.list_size if hasattr(ecol.type, "list_size") else len(ecol[0])
+        flat = ecol.flatten().to_numpy(zero_copy_only=False).astype(np.float32, copy=False)
+        data = {c: table.column(c).to_pylist() for c in table.column_names if c != cfg.embedding_col}
+        data[cfg.embedding_col] = torch.from_numpy(flat.reshape(-1, d).copy())
+        return self.index_data(data)
+
     @classmethod
     def load(cls, path: str, device=None) -> "ExactIndex":
         p = pathlib.Path(path)
