@@ -16,10 +16,18 @@ Pinning status
   ``xfmr_rec/losses.py`` executed in the build container; the vectors it
   produced are committed under ``tests/golden/losses_*.npz`` together with the
   generating script ``tests/golden/make_golden.py``.
-* candidate construction (``compute_embeds``): restated from
-  ``xfmr_rec/models.py:388-419`` (module not importable: sentence_transformers
-  absent); pinned only through torch's ``nn.Embedding`` semantics in the golden
-  script.
+* candidate construction (``compute_embeds``): PINNED — ``xfmr_rec/models.py`` is not importable here
+  (sentence_transformers absent), so ``tests/golden/make_golden_embeds.py`` executes the reference's
+  own ``RecommenderModel.forward`` / ``compute_embeds`` method definitions straight from its source
+  file (ast; bound to a stand-in object with a stub encoder) and stores inputs + outputs
+  (``tests/golden/embeds_*.npz``); the oracle reproduces them bit for bit.
+* SeqBatch construction (``seq_sample_*``): the reference draws from an unseeded generator
+  (data.py:574): no value-level golden can exist.  PINNED on support and distribution:
+  ``tests/golden/make_golden_seqbatch.py`` executes the reference's own ``sample_sequence`` /
+  ``sample_positives`` / ``sample_negatives`` (pure numpy, taken from the source file by ast) and
+  stores raw examples + marginal histograms of 6,000 draws per case; the oracle's constraints accept
+  every reference example and its counter-based algorithm matches the histograms (two-sample
+  chi-square).  The kernel matches the oracle's algorithm bit for bit.
 * exact retrieval: the reference's search is an approximate ANN index in
   un-vendored third-party code (lancedb 0.37.1 / faiss-cpu 1.15.0); the oracle
   is the exact computation those indexes approximate — parity unpinned (and

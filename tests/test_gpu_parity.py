@@ -104,6 +104,33 @@ def test_compute_embeds_matches_oracle(xr, batch, seq):
     assert np.array_equal(g, np.repeat(keep[:, None], 64, 1).astype(np.float32))
 
 
+@pytest.mark.parametrize("case", ["basic", "normalized", "truncated"])
+def test_compute_embeds_matches_reference_outputs(xr, golden_dir, case):
+    """Against the outputs of the reference's OWN forward + compute_embeds (models.py:306-345,
+    366-419; tests/golden/make_golden_embeds.py): rows bit-exact, masks equal, and the autograd
+    of the query selection back to the encoder output."""
+    z = np.load(golden_dir / f"embeds_{case}.npz")
+    emb = xr.models.ItemEmbeddings(torch.from_numpy(z["table"]), add_padding_row=False).cuda()
+    tok = torch.from_numpy(z["tokens"]).cuda().requires_grad_(True)
+    args = [torch.from_numpy(z[k]).cuda() for k in ("history_item_idx", "pos_item_idx", "neg_item_idx")]
+    norm = bool(z["is_normalized"])
+    out = xr.models.compute_embeds(emb, tok, *args, is_normalized=norm, dense=True)
+    assert np.array_equal(out["attention_mask"].cpu().numpy(), z["attention_mask"].astype(bool))
+    assert np.array_equal(out["positive_mask"].cpu().numpy(), z["positive_mask"].astype(bool))
+    assert np.array_equal(out["candidate_embed"].cpu().numpy(), z["candidate_embed"])
+    q = out["query_embed"]
+    if norm:
+        np.testing.assert_allclose(q.detach().cpu().numpy(), z["query_embed"], rtol=1e-6, atol=1e-7)
+    else:
+        assert np.array_equal(q.detach().cpu().numpy(), z["query_embed"])
+    (q * torch.from_numpy(z["upstream"]).cuda()).sum().backward()
+    np.testing.assert_allclose(tok.grad.cpu().numpy(), z["dtokens"], rtol=1e-5, atol=1e-7)
+    handle = xr.models.compute_embeds(emb, tok.detach(), *args, is_normalized=norm)["candidate_embed"]
+    assert np.array_equal(handle.pos.cpu().numpy(), z["candidate_embed"][:, 0])
+    if z["candidate_embed"].shape[0]:
+        assert np.array_equal(handle.neg.cpu().numpy(), z["candidate_embed"][0, 1:])
+
+
 def test_compute_embeds_dense_equals_reference_layout(xr):
     b = orc.synth_batch(60, 3, 7, dim=32, seed=5)
     want = orc.compute_embeds(b["table"], b["token_embeddings"], b["history_item_idx"],

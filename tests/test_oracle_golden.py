@@ -181,3 +181,23 @@ def test_retrieval_metrics_known_answers():
     assert m["retrieval_auroc"] == pytest.approx(3 / 4)
     idcg = 1 + 1 / math.log2(3) + 1 / math.log2(4)
     assert m["retrieval_normalized_dcg"] == pytest.approx((1 + 1 / math.log2(4)) / idcg)
+
+
+EMBED_CASES = ["basic", "normalized", "truncated"]
+
+
+@pytest.mark.parametrize("case", EMBED_CASES)
+def test_compute_embeds_oracle_matches_reference_outputs(golden_dir, case):
+    """The oracle's compute_embeds against the outputs of the reference's OWN
+    RecommenderModel.forward + compute_embeds (models.py:306-345, 366-419), executed from the
+    reference's source file by tests/golden/make_golden_embeds.py."""
+    z = np.load(golden_dir / f"embeds_{case}.npz")
+    out = orc.compute_embeds(z["table"], z["tokens"], z["history_item_idx"], z["pos_item_idx"],
+                             z["neg_item_idx"], dense=True, is_normalized=bool(z["is_normalized"]))
+    assert np.array_equal(out["attention_mask"], z["attention_mask"].astype(bool))
+    assert np.array_equal(out["positive_mask"], z["positive_mask"].astype(bool))
+    assert np.array_equal(out["candidate_embed"], z["candidate_embed"])          # gathered rows: bit-exact
+    if bool(z["is_normalized"]):
+        np.testing.assert_allclose(out["query_embed"], z["query_embed"], rtol=1e-6, atol=1e-7)
+    else:
+        assert np.array_equal(out["query_embed"], z["query_embed"])

@@ -190,3 +190,64 @@ def test_sampled_batch_feeds_the_train_step(xr):
     loss = xr.InfoNCELoss(xr.LossConfig())(out["query_embed"], out["candidate_embed"])
     loss.backward()
     assert torch.isfinite(loss) and float(loss) > 0 and tok.grad is not None
+
+
+# ---------------------------------------------------------------- against the reference's own sampler
+def _two_sample_chi2(a, b):
+    """Pearson two-sample statistic and its degrees of freedom over the cells either sample hit."""
+    a, b = np.asarray(a, float).ravel(), np.asarray(b, float).ravel()
+    keep = (a + b) > 0
+    a, b = a[keep], b[keep]
+    A, B = a.sum(), b.sum()
+    if A == 0 or B == 0 or keep.sum() < 2:
+        return 0.0, 0
+    stat = (((np.sqrt(B / A) * a - np.sqrt(A / B) * b) ** 2) / (a + b)).sum()
+    return float(stat), int(keep.sum() - 1)
+
+
+def test_reference_examples_satisfy_the_support_constraints(golden_dir):
+    """Everything the reference's OWN sample_sequence / sample_positives / sample_negatives produced
+    (data.py:669-747, executed by tests/golden/make_golden_seqbatch.py) passes check_seq_example: the
+    constraints the device sampler is tested against are not stricter than the reference."""
+    z = np.load(golden_dir / "seqbatch_reference_stats.npz")
+    n_items, L = int(z["n_items"]), int(z["max_seq_length"])
+    for look in (0, 3):
+        for u in range(6):
+            h, l = z[f"hist{u}"], z[f"label{u}"]
+            for ex in z[f"look{look}_user{u}_raw"]:
+                n = int((ex[0] >= 0).sum())
+                orc.check_seq_example(h, l, ex[0, :n], ex[1, :n], ex[2, :n], n_items, L, look)
+
+
+@pytest.mark.parametrize("look", [0, 3])
+def test_sampler_distribution_matches_the_reference(golden_dir, look):
+    """Marginal distributions of the counter-based algorithm (what the kernel computes, bit for bit)
+    against 6,000 draws of the reference's own sampler: which positions are kept, which positive each
+    kept position gets, which negatives are drawn — including the with-replacement case (fewer
+    candidates than positions) and a history that covers the whole catalog."""
+    z = np.load(golden_dir / "seqbatch_reference_stats.npz")
+    n_items, L, draws = int(z["n_items"]), int(z["max_seq_length"]), 1500
+    for u in range(6):
+        h, l = z[f"hist{u}"], z[f"label{u}"]
+        pos_cnt = np.zeros(len(h), np.int64)
+        positive_cnt = np.zeros((len(h), n_items + 1), np.int64)
+        neg_cnt = np.zeros(n_items + 1, np.int64)
+        distinct = len(set(h.tolist())) == len(h)
+        for step in range(draws):
+            ho, po, no = orc.seq_sample_example(h, l, row=u, n_items=n_items, max_seq_length=L,
+                                                pos_lookahead=look, seed=11, step=step)
+            np.add.at(neg_cnt, no, 1)
+            if distinct:     # positions are identifiable from the items
+                idx = [int(np.flatnonzero(h == v)[0]) for v in ho]
+                pos_cnt[idx] += 1
+                positive_cnt[idx, po] += 1
+        key = f"look{look}_user{u}"
+        stat, dof = _two_sample_chi2(neg_cnt, z[f"{key}_negatives"])
+        assert stat <= dof + 5 * np.sqrt(2 * max(dof, 1)) + 5, (key, "negatives", stat, dof)
+        if distinct:
+            stat, dof = _two_sample_chi2(pos_cnt, z[f"{key}_positions"])
+            assert stat <= dof + 5 * np.sqrt(2 * max(dof, 1)) + 5, (key, "positions", stat, dof)
+            # support of the positives is identical; frequencies agree
+            assert ((positive_cnt > 0) <= (z[f"{key}_positives"] > 0)).all(), key
+            stat, dof = _two_sample_chi2(positive_cnt, z[f"{key}_positives"])
+            assert stat <= dof + 5 * np.sqrt(2 * max(dof, 1)) + 5, (key, "positives", stat, dof)
