@@ -559,3 +559,30 @@ def test_index_table_round_trip(xr, tmp_path):
     fx = xr.index.ExactIndex.load_table(str(p2), xr.index.ExactIndexConfig(dtype="fp32"))
     s2, i2 = fx.search_batch(q, [[1, 2], [], [7], [], []], k)
     assert torch.equal(i0, i2) and torch.equal(s0, s2)
+
+
+@pytest.mark.parametrize("case", ["default", "scale_margin_nomask"])
+def test_compute_losses_matches_the_reference_trainer(xr, golden_dir, case):
+    """The whole training-step log dict against the reference's OWN
+    RecommenderLightningModule.compute_losses (trainer.py:213-264) run on its own compute_embeds and
+    loss classes (tests/golden/make_golden_compute_losses.py): same 30 keys in the same order, fp32
+    values within 1e-5, and the gradient of the train loss at the encoder output."""
+    z = np.load(golden_dir / f"compute_losses_{case}.npz")
+    cfg = xr.LossConfig(**json.loads(str(z["cfg"])))
+    want = json.loads(str(z["logged"]))
+    emb = xr.models.ItemEmbeddings(torch.from_numpy(z["table"]), add_padding_row=False).cuda()
+    tok = torch.from_numpy(z["tokens"]).cuda().requires_grad_(True)
+    args = [torch.from_numpy(z[k]).cuda() for k in ("history_item_idx", "pos_item_idx", "neg_item_idx")]
+    for dense in (False, True):
+        tok.grad = None
+        embeds = xr.models.compute_embeds(emb, tok, *args, dense=dense)
+        got = xr.losses.compute_losses(cfg, embeds)
+        assert list(got.keys()) == json.loads(str(z["keys"]))
+        for k, v in want.items():
+            g = float(got[k])
+            if v != v:
+                assert g != g, k
+            else:
+                assert g == pytest.approx(v, rel=FP32_REL, abs=1e-6), (k, dense)
+        got["loss/InfoNCELoss"].backward()
+        assert_close_grad(tok.grad.cpu().numpy(), z["dtokens"], FP32_REL)

@@ -484,3 +484,44 @@ def evaluate_all(config, query_embed, candidate_embed, target=None, *, train_los
         train_cls = {c.__name__: c for c in LOSS_CLASSES}[train_loss]
         out[f"loss/{train_loss}"] = train_cls(config)(query_embed, candidate_embed, target)
     return out, stats_dict(stats.tolist())
+
+
+def compute_losses(config, embeds: dict, *, train_loss: str = "InfoNCELoss") -> dict:
+    """``RecommenderLightningModule.compute_losses`` (xfmr_rec/trainer.py:213-264) from the output of
+    ``compute_embeds``: the SAME 30 keys in the same order — ``loss/<Name>`` and ``loss/<Name>Mean``
+    for every class in LOSS_CLASSES (0-dim tensors; ``loss/<train_loss>`` carries the autograd edge),
+    the seven ``batch/*`` numbers, the nine ``logits/*`` statistics (floats).  Two tensor-core passes
+    + the train loss's fused forward/backward and ONE device->host copy, instead of eight logit
+    computations and eleven ``.item()`` syncs."""
+    attention_mask = embeds["attention_mask"]
+    batch_size, seq_len = attention_mask.size()
+    numel = attention_mask.numel()
+    counts = torch.stack([attention_mask.count_nonzero(), embeds["positive_mask"].count_nonzero()])
+    q, cand = embeds["query_embed"], embeds["candidate_embed"]
+    dot, cos = InfoNCELoss(config), AlignmentContrastiveLoss(config)
+    with torch.no_grad():
+        l_dot, stats, _ = dot._evaluate(q, cand, None, want_stats=True)
+        l_cos, _, _ = cos._evaluate(q, cand, None, want_stats=True)
+    host = torch.cat([counts.to(torch.float64), stats]).tolist()     # the single host sync
+    attn_non_zero, pos_non_zero = int(host[0]), int(host[1])
+    losses: dict = {}
+    train_cls = {c.__name__: c for c in LOSS_CLASSES}[train_loss]
+    for cls in LOSS_CLASSES:
+        key = f"loss/{cls.__name__}"
+        if cls is train_cls and torch.is_grad_enabled() and q.requires_grad:
+            loss = cls(config)(q, cand)
+        else:
+            src = l_cos if cls.COSINE else l_dot
+            loss = src[N.LOSS_KIND[cls.__name__]].to(torch.float32)
+        losses[key] = loss
+        losses[f"{key}Mean"] = loss / (pos_non_zero + 1e-9)
+    metrics = {
+        "batch/size": batch_size,
+        "batch/seq_len": seq_len,
+        "batch/numel": numel,
+        "batch/attention_non_zero": attn_non_zero,
+        "batch/attention_density": attn_non_zero / (numel + 1e-9),
+        "batch/positive_non_zero": pos_non_zero,
+        "batch/positive_density": pos_non_zero / (attn_non_zero + 1e-9),
+    }
+    return losses | metrics | stats_dict(host[2:])
