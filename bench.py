@@ -39,8 +39,8 @@ for _p in (ROOT, ROOT / "transformer-recommenders_b200"):
     if str(_p) not in sys.path:
         sys.path.insert(0, str(_p))
 
-N_ITEMS, BATCH, SEQ_LEN, DIM = 27278, 128, 200, 384
-WORKLOAD = ("ML-20M-shaped synthetic (27,278 items, 384-d), B=128 x L=200, InfoNCE in-batch "
+N_ITEMS, BATCH, SEQ_LEN, DIM = 27278, int(os.environ.get("XR_BENCH_BATCH", "128")), 200, 384
+WORKLOAD = (f"ML-20M-shaped synthetic (27,278 items, 384-d), B={BATCH} x L=200, InfoNCE in-batch "
             "shared-pool negatives, bf16 (BASELINE configs[1])")
 
 
