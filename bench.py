@@ -285,6 +285,9 @@ def main():
 
     # the same kernels as ONE sync-free, graph-replayed call (xr_pool_step); two objects alternate
     # so that consecutive steps never reuse a buffer and the next H2D copy overlaps the kernels
+    # (PoolLossStep(pipelined=True) would also run the ingest kernels of batch i+1 under the compute of
+    # batch i; measured slower here -- 0.47 against 0.39 ms per e2e step -- because the small kernels
+    # delay CTAs of the persistent tensor-core kernel, and the e2e step is bound by the host link anyway)
     steps2 = [xr.PoolLossStep(emb, loss_fn, BATCH, SEQ_LEN, token_dtype=torch.bfloat16) for _ in range(2)]
     host_args = (host_tok, host["history_item_idx"], host["pos_item_idx"], host["neg_item_idx"])
     for st in steps2:   # device-resident inputs for the `value` leg
@@ -334,14 +337,23 @@ def main():
         """e2e: every step copies its inputs from pinned host memory and reads the loss back.
         The H2D copy of step i+1 is enqueued (copy stream) before the host blocks on the loss of
         step i, so it overlaps step i's kernels; timed as one region over all K steps."""
+        host_loss = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        read_ev = [torch.cuda.Event() for _ in range(2)]
+
         def loop(n):
             vals = []
             steps2[0].load(*host_args)
             for i in range(n):
-                loss, _ = steps2[i % 2].run()
+                loss, _ = steps2[i % 2].run()                        # compute phase of batch i
+                host_loss[i % 2].copy_(loss.reshape(1), non_blocking=True)   # device -> host read of its result
+                read_ev[i % 2].record()
                 if i + 1 < n:
-                    steps2[(i + 1) % 2].load(*host_args)
-                vals.append(float(loss))   # device -> host read of the step's result
+                    steps2[(i + 1) % 2].load(*host_args)             # H2D copies + ingest of batch i+1
+                if i >= 1:                                           # the host consumes loss i-1 while step i runs
+                    read_ev[(i - 1) % 2].synchronize()
+                    vals.append(float(host_loss[(i - 1) % 2]))
+            read_ev[(n - 1) % 2].synchronize()
+            vals.append(float(host_loss[(n - 1) % 2]))
             return vals
         loop(warmup)
         barrier()
@@ -432,8 +444,12 @@ def main():
                    "parallelism": f"dp{world} (independent batches, table replicated)"},
         "e2e": {"value": e2e_value, "unit": "seq/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
-                "note": "pinned host inputs copied every step (next batch's copy overlaps the "
-                        "current batch's kernels), loss read back every step"},
+                "note": "every step starts from pinned HOST inputs (H2D copy of batch i+1 on the copy stream "
+                        "under the kernels of batch i); the loss of every step is copied to pinned host "
+                        "memory and read by the host one step later (while the next step runs), as a "
+                        "training loop logs it.  Bound by the host link: 20.3 MB per step at ~52 GB/s = "
+                        "0.39 ms; a concurrent H2D stream also slows the tensor-core kernel (0.30 -> 0.37 ms "
+                        "per step, measured), a D2D copy of the same size does not"},
         "gpu_launches": 9 * args.steps,   # xr_pool_step: compaction x3, plan, gather, diagonal, fused, finalize, row sum
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "fused_pool_kernel<InfoNCE> (tcgen05)",

@@ -298,6 +298,20 @@ int xr_pool_step(const int64_t* history_idx, const int64_t* pos_idx, const int64
                  double* loss_out, int64_t* counts, int32_t* err_flag, void* workspace,
                  size_t workspace_bytes, void* stream);
 
+/* The same step in two phases for callers that pipeline batches: INGEST (index compaction, device
+ * plan, the three gathers: everything that reads the batch's inputs) and COMPUTE (diagonal pass,
+ * fused loss forward/backward, finalize, row sum).  xr_pool_step == ingest + compute on one stream.
+ * With two alternating workspaces the ingest of batch i+1 runs on a second stream under the compute
+ * of batch i.  `tok` may point to pinned HOST memory (UVA): the gather then pulls only the selected
+ * M rows over PCIe instead of a whole (B, L, D) copy.                                          */
+int xr_pool_step_ingest(const int64_t* history_idx, const int64_t* pos_idx, const int64_t* neg_idx,
+                        int64_t n_pos, const void* tok, int tok_dtype, const void* table_bf16,
+                        const uint8_t* rownz, int64_t n_table_rows, int64_t dim, int64_t* counts,
+                        int32_t* err_flag, void* workspace, size_t workspace_bytes, void* stream);
+int xr_pool_step_compute(int64_t n_pos, int64_t dim, int loss_kind, const xr_loss_config* cfg,
+                         float grad_scale, void* dtok, int dtok_dtype, double* loss_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- family 3: top-k -------------------------------------------------------------------------
  * Exact top-k of each row of a materialised (U,N) fp32 score matrix under the total order
  * (score descending, column ascending) — the result the reference's ANN search

@@ -171,3 +171,44 @@ def test_step_with_monitor_equals_evaluate_all(xr, graph, cfg_kw):
         lb = None if name in orc.COSINE_LOSSES else "bf16"
         ref, _, _, _ = orc.lean_loss(name, q, ps, ng, orc.Config(**cfg_kw), with_grad=True, logits_dtype=lb)
         assert float(got[f"loss/{name}"]) == pytest.approx(ref, rel=4e-3, abs=4e-3), name
+
+
+@pytest.mark.parametrize("tok_dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("graph", [True, False])
+def test_pipelined_step_with_in_place_host_tokens_is_bitwise_identical(xr, tok_dtype, graph):
+    """pipelined=True: load() runs the ingest phase (compaction, plan, gathers) on the copy stream and
+    the gather reads pinned HOST token embeddings in place (only the selected rows cross PCIe);
+    run() is the compute phase.  Same bits as the one-call step, for host and device inputs, across
+    alternating step objects and repeated batches."""
+    loss_fn = xr.InfoNCELoss(xr.LossConfig())
+    batches = [orc.synth_batch(3000, 16, 60, dim=384, seed=s) for s in (5, 6, 7)]
+    emb = xr.models.ItemEmbeddings(torch.from_numpy(batches[0]["table"]), add_padding_row=False).cuda()
+    for b in batches[1:]:
+        b["table"] = batches[0]["table"]
+    plain = xr.PoolLossStep(emb, loss_fn, 16, 60, token_dtype=tok_dtype, use_graph=graph)
+    pipes = [xr.PoolLossStep(emb, loss_fn, 16, 60, token_dtype=tok_dtype, use_graph=graph, pipelined=True,
+                             host_tokens_in_place=bool(k)) for k in range(2)]   # one copies, one reads in place
+    want = []
+    for b in batches:
+        l, g = run_step(plain, b, tok_dtype)
+        want.append((l.clone(), g.clone()))
+    host = [[torch.from_numpy(b["token_embeddings"]).to(tok_dtype).pin_memory()] +
+            [torch.from_numpy(b[k]).pin_memory() for k in ("history_item_idx", "pos_item_idx", "neg_item_idx")]
+            for b in batches]
+    # software pipeline: the load (ingest) of batch i+1 is enqueued before the result of batch i is read
+    pipes[0].load(*host[0])
+    got = []
+    for i in range(len(batches)):
+        l, g = pipes[i % 2].run()
+        if i + 1 < len(batches):
+            pipes[(i + 1) % 2].load(*host[i + 1])
+        got.append((l.clone(), g.clone()))
+    torch.cuda.synchronize()
+    for (l, g), (wl, wg) in zip(got, want):
+        assert torch.equal(l, wl) and torch.equal(g, wg)
+    # device-resident inputs through the pipelined object, and run() without a new load (full step)
+    dev_args = [t.cuda() for t in host[1]]
+    l, g = pipes[0](*dev_args)
+    assert torch.equal(l, want[1][0]) and torch.equal(g, want[1][1])
+    l2, g2 = pipes[0].run()
+    assert torch.equal(l2, want[1][0]) and torch.equal(g2, want[1][1])

@@ -1456,35 +1456,32 @@ extern "C" size_t xr_pool_step_workspace_bytes(int64_t n_pos, int64_t dim) {
   return carve_step_ws(nullptr, n_pos).bytes;
 }
 
-extern "C" int xr_pool_step(const int64_t* history_idx, const int64_t* pos_idx,
-                            const int64_t* neg_idx, int64_t n_pos, const void* tok, int tok_dtype,
-                            const void* table_bf16, const uint8_t* rownz, int64_t n_table_rows,
-                            int64_t dim, int loss_kind, const xr_loss_config* cfg, float grad_scale,
-                            void* dtok, int dtok_dtype, double* loss_out, int64_t* counts,
-                            int32_t* err_flag, void* workspace, size_t workspace_bytes,
-                            void* stream) {
-  XR_CHECK_ARG(history_idx && pos_idx && neg_idx && tok && table_bf16 && cfg && loss_out && counts &&
-                   workspace,
-               "xr_pool_step: null pointer");
-  XR_CHECK_ARG(dim == fk::D, "xr_pool_step: this build is specialised for dim = %d", fk::D);
-  XR_CHECK_ARG(n_pos > 0 && n_pos < (1ll << 30) && n_table_rows > 0, "xr_pool_step: bad sizes");
-  XR_CHECK_ARG((tok_dtype == XR_F32 || tok_dtype == XR_BF16) &&
-                   (!dtok || dtok_dtype == XR_F32 || dtok_dtype == XR_BF16),
-               "xr_pool_step: bad dtype");
+// The step in two phases, so that a caller with two alternating step objects can overlap the INGEST
+// of batch i+1 (index compaction, plan, the three gathers -- the only part that touches the batch's
+// inputs) with the COMPUTE of batch i on another stream.  `tok` may be pinned HOST memory (UVA): the
+// gather then pulls only the M selected rows over PCIe ("zero-copy": M x D x 2 bytes instead of a
+// B x L x D x 2 byte copy of the whole encoder output).
+extern "C" int xr_pool_step_ingest(const int64_t* history_idx, const int64_t* pos_idx,
+                                   const int64_t* neg_idx, int64_t n_pos, const void* tok,
+                                   int tok_dtype, const void* table_bf16, const uint8_t* rownz,
+                                   int64_t n_table_rows, int64_t dim, int64_t* counts,
+                                   int32_t* err_flag, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  XR_CHECK_ARG(history_idx && pos_idx && neg_idx && tok && table_bf16 && counts && workspace,
+               "xr_pool_step_ingest: null pointer");
+  XR_CHECK_ARG(dim == fk::D, "xr_pool_step_ingest: this build is specialised for dim = %d", fk::D);
+  XR_CHECK_ARG(n_pos > 0 && n_pos < (1ll << 30) && n_table_rows > 0, "xr_pool_step_ingest: bad sizes");
+  XR_CHECK_ARG(tok_dtype == XR_F32 || tok_dtype == XR_BF16, "xr_pool_step_ingest: bad dtype");
   XR_CHECK_ARG(((uintptr_t)tok % 16 == 0) && ((uintptr_t)table_bf16 % 16 == 0) &&
-                   ((uintptr_t)dtok % 16 == 0) && ((uintptr_t)workspace % 256 == 0),
-               "xr_pool_step: buffers must be 16-byte aligned (workspace 256)");
-  int rc;
-  if ((rc = check_fused_kind("xr_pool_step", loss_kind, cfg))) return rc;
-  XR_CHECK_ARG(loss_kind != XR_LOSS_CONTRASTIVE && loss_kind != XR_LOSS_ALIGNMENT_CONTRASTIVE,
-               "xr_pool_step: the cosine kinds go through compute_embeds + the loss modules");
+                   ((uintptr_t)workspace % 256 == 0),
+               "xr_pool_step_ingest: buffers must be 16-byte aligned (workspace 256)");
   XR_CHECK_ARG(workspace_bytes >= xr_pool_step_workspace_bytes(n_pos, dim),
-               "xr_pool_step: workspace too small");
-  if ((rc = check_fused_device("xr_pool_step"))) return rc;
+               "xr_pool_step_ingest: workspace too small");
+  int rc;
+  if ((rc = check_fused_device("xr_pool_step_ingest"))) return rc;
   cudaStream_t s = as_stream(stream);
   const StepWs w = carve_step_ws(workspace, n_pos);
   const int n_sm = sm_count();
-
   // 1 + 2. positions -> row lists + counts (models.py:343, 390, 398, 404, 413-416), then the plan
   //        of the tensor-core kernel for the real (M, M_a): 64 threads, all on the device
   if ((rc = xr_compact_positions(history_idx, pos_idx, rownz, n_table_rows, n_pos, w.attn, w.sel_attn,
@@ -1493,24 +1490,57 @@ extern "C" int xr_pool_step(const int64_t* history_idx, const int64_t* pos_idx,
   fused_plan_kernel<<<1, 64, 0, s>>>(counts, PlanHook{n_sm, w.fused.dyn, w.fused.dyn + 1});
   XR_LAUNCH_CHECK("fused_plan");
   // 3. the three gathers in one launch (models.py:392+415, :400+416, :406), bf16 operands
-  {
-    const int64_t per_job = (n_pos * (fk::D * 2 / 16) + 255) / 256;
-    int gx = (int)(per_job < (int64_t)n_sm * 4 ? per_job : (int64_t)n_sm * 4);
-    if (gx < 1) gx = 1;
-    step_gather_kernel<<<dim3(gx, 3), 256, 0, s>>>(
-        (const char*)tok, tok_dtype == XR_F32, (const char*)table_bf16, n_table_rows, pos_idx,
-        neg_idx, w.sel_attn, w.sel_pos, counts, n_pos, (char*)w.q, (char*)w.pos, (char*)w.neg,
-        err_flag);
-    XR_LAUNCH_CHECK("step_gather");
-  }
+  const int64_t per_job = (n_pos * (fk::D * 2 / 16) + 255) / 256;
+  int gx = (int)(per_job < (int64_t)n_sm * 4 ? per_job : (int64_t)n_sm * 4);
+  if (gx < 1) gx = 1;
+  step_gather_kernel<<<dim3(gx, 3), 256, 0, s>>>(
+      (const char*)tok, tok_dtype == XR_F32, (const char*)table_bf16, n_table_rows, pos_idx, neg_idx,
+      w.sel_attn, w.sel_pos, counts, n_pos, (char*)w.q, (char*)w.pos, (char*)w.neg, err_flag);
+  XR_LAUNCH_CHECK("step_gather");
+  return XR_OK;
+}
+
+extern "C" int xr_pool_step_compute(int64_t n_pos, int64_t dim, int loss_kind, const xr_loss_config* cfg,
+                                    float grad_scale, void* dtok, int dtok_dtype, double* loss_out,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  XR_CHECK_ARG(cfg && loss_out && workspace, "xr_pool_step_compute: null pointer");
+  XR_CHECK_ARG(dim == fk::D && n_pos > 0 && n_pos < (1ll << 30), "xr_pool_step_compute: bad sizes");
+  XR_CHECK_ARG(!dtok || dtok_dtype == XR_F32 || dtok_dtype == XR_BF16, "xr_pool_step_compute: bad dtype");
+  XR_CHECK_ARG(((uintptr_t)dtok % 16 == 0) && ((uintptr_t)workspace % 256 == 0),
+               "xr_pool_step_compute: buffers must be 16-byte aligned (workspace 256)");
+  int rc;
+  if ((rc = check_fused_kind("xr_pool_step_compute", loss_kind, cfg))) return rc;
+  XR_CHECK_ARG(loss_kind != XR_LOSS_CONTRASTIVE && loss_kind != XR_LOSS_ALIGNMENT_CONTRASTIVE,
+               "xr_pool_step: the cosine kinds go through compute_embeds + the loss modules");
+  XR_CHECK_ARG(workspace_bytes >= xr_pool_step_workspace_bytes(n_pos, dim),
+               "xr_pool_step_compute: workspace too small");
+  if ((rc = check_fused_device("xr_pool_step_compute"))) return rc;
+  const StepWs w = carve_step_ws(workspace, n_pos);
   // 4. fused contraction + loss + dL/dtok: the finalize kernel writes the gradient in the encoder
   //    output's layout (zero rows for unselected positions: autograd of
   //    token_embeddings[mask][pos_mask], models.py:392, 415)
   const StepScatter sc{w.inv_pos, n_pos, dtok, dtok_dtype == XR_BF16};
-  if ((rc = fused_launch_all(w.q, w.pos, w.neg, n_pos, n_pos, loss_kind, cfg, nullptr, grad_scale,
-                             nullptr, loss_out, nullptr, w.fused, true, s, dtok ? &sc : nullptr)))
+  return fused_launch_all(w.q, w.pos, w.neg, n_pos, n_pos, loss_kind, cfg, nullptr, grad_scale, nullptr,
+                          loss_out, nullptr, w.fused, true, as_stream(stream), dtok ? &sc : nullptr);
+}
+
+extern "C" int xr_pool_step(const int64_t* history_idx, const int64_t* pos_idx,
+                            const int64_t* neg_idx, int64_t n_pos, const void* tok, int tok_dtype,
+                            const void* table_bf16, const uint8_t* rownz, int64_t n_table_rows,
+                            int64_t dim, int loss_kind, const xr_loss_config* cfg, float grad_scale,
+                            void* dtok, int dtok_dtype, double* loss_out, int64_t* counts,
+                            int32_t* err_flag, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  XR_CHECK_ARG(cfg && loss_out, "xr_pool_step: null pointer");
+  int rc;
+  if ((rc = check_fused_kind("xr_pool_step", loss_kind, cfg))) return rc;   // before any launch
+  XR_CHECK_ARG(loss_kind != XR_LOSS_CONTRASTIVE && loss_kind != XR_LOSS_ALIGNMENT_CONTRASTIVE,
+               "xr_pool_step: the cosine kinds go through compute_embeds + the loss modules");
+  if ((rc = xr_pool_step_ingest(history_idx, pos_idx, neg_idx, n_pos, tok, tok_dtype, table_bf16, rownz,
+                                n_table_rows, dim, counts, err_flag, workspace, workspace_bytes, stream)))
     return rc;
-  return XR_OK;
+  return xr_pool_step_compute(n_pos, dim, loss_kind, cfg, grad_scale, dtok, dtok_dtype, loss_out,
+                              workspace, workspace_bytes, stream);
 }
 
 // ---- the monitoring half of compute_losses inside the same sync-free sequence --------------------

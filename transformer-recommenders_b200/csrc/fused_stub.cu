@@ -45,3 +45,14 @@ extern "C" int xr_pool_step_monitor(int64_t, int64_t, const xr_loss_config*, dou
   xr::set_error("xr_pool_step_monitor: tcgen05 kernels not compiled into this build");
   return XR_E_UNSUPPORTED;
 }
+extern "C" int xr_pool_step_ingest(const int64_t*, const int64_t*, const int64_t*, int64_t, const void*, int,
+                                   const void*, const uint8_t*, int64_t, int64_t, int64_t*, int32_t*, void*,
+                                   size_t, void*) {
+  xr::set_error("xr_pool_step_ingest: tcgen05 kernels not compiled into this build");
+  return XR_E_UNSUPPORTED;
+}
+extern "C" int xr_pool_step_compute(int64_t, int64_t, int, const xr_loss_config*, float, void*, int, double*,
+                                    void*, size_t, void*) {
+  xr::set_error("xr_pool_step_compute: tcgen05 kernels not compiled into this build");
+  return XR_E_UNSUPPORTED;
+}

@@ -37,7 +37,8 @@ class PoolLossStep:
     def __init__(self, embeddings: ItemEmbeddings, loss: EmbedLoss, batch_size: int, seq_len: int, *,
                  token_dtype: torch.dtype = torch.bfloat16, grad_dtype: torch.dtype | None = None,
                  want_grad: bool = True, logits_bf16: bool | None = None, use_graph: bool = True,
-                 check_indices: bool = False, monitor: bool = False) -> None:
+                 check_indices: bool = False, monitor: bool = False, pipelined: bool = False,
+                 host_tokens_in_place: bool = False) -> None:
         name = type(loss).__name__
         if name not in _STEP_KINDS:
             raise NotImplementedError(
@@ -91,7 +92,21 @@ class PoolLossStep:
             self._copied = torch.cuda.Event()
             self._done = torch.cuda.Event()
             self._done.record()
+        # pipelined: load() also runs the INGEST phase (compaction, plan, gathers) on the copy stream,
+        # run() only the COMPUTE phase -- with two alternating step objects the ingest of batch i+1
+        # overlaps the tensor-core kernel of batch i.  Bit-identical to the one-call step.  Measured on
+        # the B200 at BASELINE configs[1] it does NOT pay (0.47 against 0.39 ms per end-to-end step:
+        # the ingest kernels delay CTAs of the persistent tensor-core kernel), so it is off by default;
+        # it is the structure to use when the ingest side is heavier (fp32 tokens, longer sequences).  host_tokens_in_place: the gather reads pinned
+        # HOST token embeddings directly (only the selected rows cross the host link) instead of a DMA
+        # copy of the whole (B, L, D) tensor -- measured SLOWER on the B200 box (0.28 ms against
+        # 0.09 ms for the 20 MB copy: a kernel's reads of host memory are latency-bound), so it is off.
+        self.pipelined = bool(pipelined)
+        self.host_tokens_in_place = bool(host_tokens_in_place)
+        self._tok_src = None          # pinned host tensor the gather reads in place (kept alive)
+        self._ingested = False
         self.graph = None
+        self.graph_compute = None
         if use_graph:
             self._capture()
 
@@ -103,6 +118,22 @@ class PoolLossStep:
                ops._DT[self.dtok.dtype] if self.dtok is not None else N.XR_F32, ops._p(self.loss_buf),
                ops._p(self.counts), ops._p(self.err), C.c_void_p(self._ws_ptr), self._ws_bytes,
                ops._stream())
+        if self.monitor:
+            N.call("xr_pool_step_monitor", self.n_pos, self.d, C.byref(self.cfg), ops._p(self.mon_dot),
+                   ops._p(self.mon_cos), ops._p(self.mon_stats), C.c_void_p(self._ws_ptr), self._ws_bytes,
+                   ops._stream())
+
+    def _launch_ingest(self, tok_ptr=None, tok_dtype=None) -> None:
+        N.call("xr_pool_step_ingest", ops._p(self.hist), ops._p(self.pos), ops._p(self.neg), self.n_pos,
+               C.c_void_p(tok_ptr) if tok_ptr is not None else ops._p(self.tok),
+               ops._DT[tok_dtype if tok_dtype is not None else self.tok.dtype], ops._p(self.table),
+               ops._p(self.rownz), self.n_table_rows, self.d, ops._p(self.counts), ops._p(self.err),
+               C.c_void_p(self._ws_ptr), self._ws_bytes, ops._stream())
+
+    def _launch_compute(self) -> None:
+        N.call("xr_pool_step_compute", self.n_pos, self.d, self.kind, C.byref(self.cfg), 1.0,
+               ops._p(self.dtok), ops._DT[self.dtok.dtype] if self.dtok is not None else N.XR_F32,
+               ops._p(self.loss_buf), C.c_void_p(self._ws_ptr), self._ws_bytes, ops._stream())
         if self.monitor:
             N.call("xr_pool_step_monitor", self.n_pos, self.d, C.byref(self.cfg), ops._p(self.mon_dot),
                    ops._p(self.mon_cos), ops._p(self.mon_stats), C.c_void_p(self._ws_ptr), self._ws_bytes,
@@ -120,18 +151,37 @@ class PoolLossStep:
             with torch.cuda.graph(g):
                 self._launch()
             self.graph = g
+            if self.pipelined:   # the compute phase alone (the ingest is issued by load())
+                gc_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gc_):
+                    self._launch_compute()
+                self.graph_compute = gc_
 
     # ------------------------------------------------------------------------------------------
     def load(self, token_embeddings, history_item_idx, pos_item_idx, neg_item_idx) -> None:
         """Copy one SeqBatch (host pinned or device tensors) into the static buffers on the copy
         stream.  Waits for the previous run of THIS step object to finish with the buffers."""
         n = self.n_pos
-        with torch.cuda.stream(self.copy_stream):
+        with torch.cuda.device(self.device), torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self._done)
-            self.tok.copy_(token_embeddings.reshape(n, self.d), non_blocking=True)
             self.hist.copy_(history_item_idx.reshape(n), non_blocking=True)
             self.pos.copy_(pos_item_idx.reshape(n), non_blocking=True)
             self.neg.copy_(neg_item_idx.reshape(n), non_blocking=True)
+            tok2d = token_embeddings.reshape(n, self.d)
+            in_place = (self.pipelined and self.host_tokens_in_place and not tok2d.is_cuda
+                        and tok2d.is_pinned() and tok2d.is_contiguous()
+                        and tok2d.dtype in (torch.float32, torch.bfloat16) and tok2d.data_ptr() % 16 == 0)
+            if in_place:
+                self._tok_src = tok2d     # read in place by the gather kernel (kept alive until then)
+            else:
+                self._tok_src = None
+                self.tok.copy_(tok2d, non_blocking=True)
+            if self.pipelined:
+                if in_place:
+                    self._launch_ingest(tok2d.data_ptr(), tok2d.dtype)
+                else:
+                    self._launch_ingest()
+                self._ingested = True
             self._copied.record()
 
     def run(self):
@@ -140,7 +190,13 @@ class PoolLossStep:
         the next load()."""
         with torch.cuda.device(self.device):
             torch.cuda.current_stream().wait_event(self._copied)
-            if self.graph is not None:
+            if self.pipelined and self._ingested:     # load() already ran the ingest phase
+                if self.graph_compute is not None:
+                    self.graph_compute.replay()
+                else:
+                    self._launch_compute()
+                self._ingested = False
+            elif self.graph is not None:
                 self.graph.replay()
             else:
                 self._launch()
