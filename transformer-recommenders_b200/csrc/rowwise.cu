@@ -195,7 +195,8 @@ __device__ __forceinline__ void sampled_logits384_row(const T* __restrict__ q_ro
                                                       int64_t n_table_rows, int64_t c, float qi,
                                                       const float* __restrict__ table_inv,
                                                       float* out, int64_t c_lo = 0,
-                                                      int64_t c_hi = INT64_MAX) {
+                                                      int64_t c_hi = INT64_MAX,
+                                                      int64_t dense_base = 0) {
   constexpr int E = RowVec<T>::E, VECS = FD / E, IT = (VECS + 31) / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = ROW_THREADS / 32;
   float qr[IT][E];
@@ -214,7 +215,7 @@ __device__ __forceinline__ void sampled_logits384_row(const T* __restrict__ q_ro
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int64_t j = j0 + u;
-      row[u] = j < c ? idx_row[j] : 0;
+      row[u] = j < c ? (idx_row ? idx_row[j] : dense_base + j) : 0;   // dense (M,C,D): row i*C + j
       valid[u] = row[u] >= 0 && row[u] < n_table_rows;
       if (!valid[u]) row[u] = 0;
     }
@@ -268,8 +269,8 @@ sampled_logits384_kernel(const T* __restrict__ q, const T* __restrict__ table,
   const int64_t per = ((c + gridDim.y - 1) / gridDim.y + 31) / 32 * 32;
   const int64_t c_lo = (int64_t)blockIdx.y * per;
   for (int64_t i = blockIdx.x; i < m; i += gridDim.x)
-    sampled_logits384_row<T>(q + i * FD, table, cand_idx + i * c, n_table_rows, c,
-                             q_inv ? q_inv[i] : 1.f, table_inv, logits + i * ld, c_lo, c_lo + per);
+    sampled_logits384_row<T>(q + i * FD, table, cand_idx ? cand_idx + i * c : nullptr, n_table_rows, c,
+                             q_inv ? q_inv[i] : 1.f, table_inv, logits + i * ld, c_lo, c_lo + per, i * c);
 }
 
 // dq_i = sum_j g[j] * tinv(j) * table[idx[j]]  (+ cosine chain rule): warps split the
@@ -283,7 +284,8 @@ __device__ __forceinline__ void sampled_dq384_row(const float* g, const T* __res
                                                   int64_t n_table_rows, int64_t c, float q_inv_i,
                                                   const float* __restrict__ table_inv, int cosine,
                                                   float* __restrict__ dq_row,
-                                                  float (*s_red)[FD], float* s_part) {
+                                                  float (*s_red)[FD], float* s_part,
+                                                  int64_t dense_base = 0) {
   constexpr int E = RowVec<T>::E, VECS = FD / E, IT = (VECS + 31) / 32;
   constexpr int NW = ROW_THREADS / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -299,7 +301,7 @@ __device__ __forceinline__ void sampled_dq384_row(const float* g, const T* __res
     for (int u = 0; u < 4; ++u) {
       const int64_t j = j0 + u;
       w[u] = j < c ? g[j] : 0.f;
-      row[u] = (j < c && w[u] != 0.f) ? idx_row[j] : -1;
+      row[u] = (j < c && w[u] != 0.f) ? (idx_row ? idx_row[j] : dense_base + j) : -1;
       if (row[u] < 0 || row[u] >= n_table_rows) {   // masked candidates: skip their bytes
         w[u] = 0.f;
         row[u] = -1;
@@ -369,8 +371,9 @@ sampled_dq384_kernel(const float* __restrict__ g, int64_t ld, const T* __restric
   __shared__ float s_red[ROW_THREADS / 32][FD];
   __shared__ float s_part[ROW_THREADS / 32];
   for (int64_t i = blockIdx.x; i < m; i += gridDim.x)
-    sampled_dq384_row<T>(g + i * ld, q + i * FD, table, cand_idx + i * c, n_table_rows, c,
-                         cosine ? q_inv[i] : 1.f, table_inv, cosine, dq + i * FD, s_red, s_part);
+    sampled_dq384_row<T>(g + i * ld, q + i * FD, table, cand_idx ? cand_idx + i * c : nullptr,
+                         n_table_rows, c, cosine ? q_inv[i] : 1.f, table_inv, cosine, dq + i * FD, s_red,
+                         s_part, i * c);
 }
 
 // ---- the sampled-candidate step in ONE pass (BASELINE config 3) --------------------------------
@@ -465,6 +468,15 @@ extern "C" int xr_logits_dense(const void* q, const void* cand, int64_t m, int64
   if (rc) return rc;
   if (m == 0 || c == 0) return XR_OK;
   cudaStream_t s = as_stream(stream);
+  if (dim == FD && dtype == XR_BF16 && !q_inv_norm && !cand_inv_norm_out) {
+    // dot logits of a bf16 (M, C, 384) tensor: the 16-byte-load / 4-rows-in-flight kernel of the
+    // sampled path with implicit rows i*C + j (the generic kernel's 8-byte bf16 loads reach 0.5 of HBM)
+    sampled_logits384_kernel<__nv_bfloat16><<<dim3((unsigned)row_grid(m), 1), ROW_THREADS, 0, s>>>(
+        (const __nv_bfloat16*)q, (const __nv_bfloat16*)cand, nullptr, m * c, m, c, nullptr, nullptr,
+        logits, ld);
+    XR_LAUNCH_CHECK("dense_logits384");
+    return XR_OK;
+  }
   return dtype == XR_F32
              ? launch_row_logits<float>(q, cand, nullptr, 0, m, c, dim, q_inv_norm, nullptr,
                                         cand_inv_norm_out, eps, logits, ld, s)
@@ -521,6 +533,17 @@ extern "C" int xr_dq_dense(const float* dlogits, int64_t ld, const void* q, cons
   if (rc) return rc;
   if (m == 0) return XR_OK;
   cudaStream_t s = as_stream(stream);
+  if (dim == FD && !cosine) {   // 16-byte loads, 4 candidate rows in flight per warp, zero weights skipped
+    if (dtype == XR_BF16)
+      sampled_dq384_kernel<__nv_bfloat16><<<row_grid(m), ROW_THREADS, 0, s>>>(
+          dlogits, ld, (const __nv_bfloat16*)q, (const __nv_bfloat16*)cand, nullptr, m * c, m, c, nullptr,
+          nullptr, 0, dq);
+    else
+      sampled_dq384_kernel<float><<<row_grid(m), ROW_THREADS, 0, s>>>(
+          dlogits, ld, (const float*)q, (const float*)cand, nullptr, m * c, m, c, nullptr, nullptr, 0, dq);
+    XR_LAUNCH_CHECK("dense_dq384");
+    return XR_OK;
+  }
   return dtype == XR_F32
              ? launch_row_dq<float>(dlogits, ld, q, cand, nullptr, 0, m, c, dim, q_inv_norm,
                                     nullptr, cosine ? cand_inv_norm : nullptr, cosine, dq, s)
