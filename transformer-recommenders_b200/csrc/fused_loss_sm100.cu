@@ -952,6 +952,7 @@ struct FusedPlan {
 // buffers).  Integer arithmetic only: the SAME function runs on the host (xr_fused_pool_loss) and
 // on the device (xr_pool_step), so both paths fold their partial sums in the same order.
 __host__ __device__ inline int fused_item_cap(int n_sm) { return 4 * n_sm; }
+constexpr int kMaxSplits = 160;   // >= the SM count: one or two row blocks can still fill the machine
 // cost of splitting the nt candidate tiles s ways (-1: not allowed); s_eff = splits actually used
 __host__ __device__ inline long long plan_cost(int rb, int nt, int s, int n_sm, int& s_eff) {
   const int tps = (nt + s - 1) / s;
@@ -983,7 +984,7 @@ __host__ __device__ inline FusedPlan make_plan(long long m, long long cn, int n_
   }
   long long best = -1;
   int best_spl = 1;
-  const int max_spl = nt < 64 ? nt : 64;
+  const int max_spl = nt < kMaxSplits ? nt : kMaxSplits;
   for (int s = 1; s <= max_spl; ++s) {   // first minimum wins (smallest s)
     int s_eff;
     const long long cost = plan_cost(rb, nt, s, n_sm, s_eff);
@@ -1020,17 +1021,18 @@ struct PlanHook {
   FusedDyn* dyn_main;
   FusedDyn* dyn_diag;
   __device__ void operator()(int m_a, int m) const {
-    __shared__ long long s_cost[64];
-    __shared__ int s_eff_sh[64];
+    __shared__ long long s_cost[kMaxSplits];
+    __shared__ int s_eff_sh[kMaxSplits];
     const int rb = (m + fk::BM - 1) / fk::BM, nt = (m_a + fk::BN - 1) / fk::BN;
-    const int t = threadIdx.x;
-    if (t < 64) {
+    for (int t = threadIdx.x; t < kMaxSplits; t += blockDim.x) {
       int s_eff = 1;
       long long cost = -1;
-      if (rb > 0 && nt > 0 && t + 1 <= (nt < 64 ? nt : 64)) cost = plan_cost(rb, nt, t + 1, n_sm, s_eff);
+      if (rb > 0 && nt > 0 && t + 1 <= (nt < kMaxSplits ? nt : kMaxSplits))
+        cost = plan_cost(rb, nt, t + 1, n_sm, s_eff);
       s_cost[t] = cost;
       s_eff_sh[t] = s_eff;
     }
+    const int t = threadIdx.x;
     __syncthreads();
     if (t == 0) {
       FusedPlan pl;
@@ -1039,7 +1041,7 @@ struct PlanHook {
       } else {
         long long best = -1;
         int best_spl = 1;
-        for (int i = 0; i < 64; ++i) {
+        for (int i = 0; i < kMaxSplits; ++i) {
           if (s_cost[i] < 0) continue;
           if (best < 0 || s_cost[i] < best) {
             best = s_cost[i];
