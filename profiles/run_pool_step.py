@@ -1,6 +1,6 @@
 """Small driver for ncu: a few sync-free train steps (xr_pool_step, issued without graph capture so
 every kernel shows up as its own launch) of the bench workload.
-    python profiles/run_pool_step.py [steps] [batch]"""
+    python profiles/run_pool_step.py [steps] [batch] [--monitor]"""
 import pathlib
 import sys
 
@@ -16,7 +16,8 @@ batch_size = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 b = orc.synth_batch(27278, batch_size, 200, dim=384, seed=0)
 dev = torch.device("cuda", 0)
 emb = xr.models.ItemEmbeddings(torch.from_numpy(b["table"]), add_padding_row=False).to(dev)
-step = xr.PoolLossStep(emb, xr.InfoNCELoss(xr.LossConfig()), batch_size, 200, use_graph=False)
+step = xr.PoolLossStep(emb, xr.InfoNCELoss(xr.LossConfig()), batch_size, 200, use_graph=False,
+                       monitor="--monitor" in sys.argv)
 tok = torch.from_numpy(b["token_embeddings"]).to(dev).bfloat16()
 idx = [torch.from_numpy(b[k]).to(dev) for k in ("history_item_idx", "pos_item_idx", "neg_item_idx")]
 for _ in range(steps):
