@@ -1218,7 +1218,7 @@ static int fused_launch_all(const void* q, const void* pos, const void* neg, lon
   if (rc) return rc;
 
   float* rl = row_loss ? row_loss : ws.rl;
-  fused_finalize_kernel<<<n_sm * 6, 256, 0, s>>>(
+  fused_finalize_kernel<<<n_sm * 4, 256, 0, s>>>(
       ws.part_o, ws.part_s, ws.t, zref, (const __nv_bfloat16*)q, (const __nv_bfloat16*)pos,
       q_inv_norm, (int)m, pl.spl, loss_kind, cfg->logits_bf16, cfg->scale, cfg->margin, grad_scale,
       dq, rl, dyn_main, sc ? sc->inv_pos : nullptr, sc ? sc->n_pos : 0, sc ? sc->dtok : nullptr,
