@@ -519,7 +519,8 @@ def bench_retrieval(args, xr, dev, rank, world, peak_hbm):
     del shard
     # sharded exchange over NVLink peer memory (all-gather + merge in one kernel); NCCL all-gather if
     # symmetric memory cannot be set up on this box
-    sharded = ShardedIndex(idx, exchange="auto" if world > 1 else "nccl")
+    sharded = ShardedIndex(idx, exchange="auto" if world > 1 else "nccl",
+                           use_plan=os.environ.get("XR_BENCH_PLAN", "1") == "1")   # local search = one graph replay
     gq = torch.Generator(device=dev).manual_seed(99)
     q = torch.randn((u, DIM), generator=gq, device=dev)
     excl = None
@@ -527,7 +528,7 @@ def bench_retrieval(args, xr, dev, rank, world, peak_hbm):
         sharded.search_batch(q, excl, k)
     torch.cuda.synchronize()
     fused = xr.ops.score_groupmax_supported(q.bfloat16(), idx.catalog)
-    if fused:
+    if fused and not sharded.use_plan:   # (the event hook cannot be recorded inside a captured graph)
         xr._native.lib().xr_fused_profile(1)
     reps = 12
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
@@ -562,7 +563,7 @@ def bench_retrieval(args, xr, dev, rank, world, peak_hbm):
            "ms_per_batch_min_max": [per_rep[0], per_rep[-1]], "timing": "median of 12 searches, CUDA events per search",
            "ms_per_search_in_order": [round(x, 4) for x in in_order],
            "dtype": "bf16",
-           "path": "tcgen05 cta_group::2 group-max scoring + top groups re-scored + merge (+ NCCL all-gather of (U,k) when sharded)"
+           "path": "tcgen05 cta_group::2 group-max scoring + top groups re-scored + merge, local search as one CUDA-graph replay (+ exchange of (U,k) when sharded)"
            if fused else "scores (fp32-accumulate GEMM) + streaming top-k + merge",
            "catalog_bytes_per_rank": (hi - lo) * DIM * 2,
            "exchange": ("none (one GPU)" if world == 1 else
@@ -571,6 +572,11 @@ def bench_retrieval(args, xr, dev, rank, world, peak_hbm):
     if fused:
         import ctypes
 
+        if sharded.use_plan:   # scoring-kernel time from a few eagerly issued local searches
+            xr._native.lib().xr_fused_profile(1)
+            for _ in range(4):
+                idx.search_batch(q, None, k)
+            torch.cuda.synchronize()
         buf = (ctypes.c_float * 512)()
         cnt = xr._native.lib().xr_fused_profile_read(buf, 512)
         xr._native.lib().xr_fused_profile(0)

@@ -53,6 +53,20 @@ for u in (1, 16, 128, 256, 1024, 4096):
         "frac_of_measured_bf16": flops / kms / 1e9 / peaks["bf16_tflops_sustained"],
         "frac_of_measured_hbm": byts / kms / 1e6 / peaks["hbm_gbs"],
         "bound": "tensor" if u >= 211 else "hbm"})
+    # the same search as one CUDA-graph replay (ExactIndex.compile_search), exclusions through static buffers
+    plan = idx.compile_search(u, k, max_exclusions=200)
+    for _ in range(3):
+        ps, pi = plan(q, csr)
+    torch.cuda.synchronize()
+    assert torch.equal(pi, i) and torch.equal(ps, s)
+    a.record()
+    for _ in range(iters):
+        plan(q, csr)
+    b.record()
+    torch.cuda.synchronize()
+    out["points"][-1]["ms_per_batch_graph_replay"] = a.elapsed_time(b) / iters
+    out["points"][-1]["queries_per_s_graph_replay"] = u / (a.elapsed_time(b) / iters) * 1e3
+    del plan
     print(json.dumps(out["points"][-1]), file=sys.stderr)
 # recall@100 of the bf16 index vs fp32 exact search on a 100k-item subsample (fp32 rows of the SAME items)
 sub = 100_000

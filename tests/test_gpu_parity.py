@@ -586,3 +586,29 @@ def test_compute_losses_matches_the_reference_trainer(xr, golden_dir, case):
                 assert g == pytest.approx(v, rel=FP32_REL, abs=1e-6), (k, dense)
         got["loss/InfoNCELoss"].backward()
         assert_close_grad(tok.grad.cpu().numpy(), z["dtokens"], FP32_REL)
+
+
+@pytest.mark.parametrize("u", [1, 7, 200])
+def test_compiled_search_plan_equals_search_batch(xr, u):
+    """ExactIndex.compile_search: the whole search as one CUDA-graph replay, same result as
+    search_batch for every replay (different queries / exclusion lists through the static buffers)."""
+    if torch.cuda.get_device_capability()[0] != 10:
+        pytest.skip("needs an sm_100 device")
+    rng = np.random.default_rng(u)
+    n, k = 50_000, 20
+    cat = torch.from_numpy(rng.standard_normal((n, 384)).astype(np.float32)).cuda()
+    idx = xr.index.ExactIndex(xr.index.ExactIndexConfig()).set_catalog(cat)
+    plan = idx.compile_search(u, k, max_exclusions=40)
+    plain = idx.compile_search(u, k)
+    for rep in range(3):
+        q = torch.from_numpy(rng.standard_normal((u, 384)).astype(np.float32)).cuda()
+        excl = [list(map(int, rng.integers(0, n, size=int(rng.integers(0, 41))))) for _ in range(u)]
+        csr = xr.ops._csr(excl, cat.device)
+        want_s, want_i = idx.search_batch(q, csr, k)
+        got_s, got_i = plan(q, csr)
+        assert torch.equal(got_i, want_i) and torch.equal(got_s, want_s)
+        want_s, want_i = idx.search_batch(q, None, k)
+        got_s, got_i = plan(q, None)
+        assert torch.equal(got_i, want_i) and torch.equal(got_s, want_s)
+        got_s, got_i = plain(q)
+        assert torch.equal(got_i, want_i) and torch.equal(got_s, want_s)

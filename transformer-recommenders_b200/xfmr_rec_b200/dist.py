@@ -105,11 +105,15 @@ class ShardedIndex:
     ``"auto"`` tries peer memory first.  Both give the single-GPU result bit for bit."""
 
     def __init__(self, local_index, *, group=None, merge_fn: Callable | None = None,
-                 exchange: str = "nccl"):
+                 exchange: str = "nccl", use_plan: bool = False):
         self.local = local_index
         self.group = group
         self.merge_fn = merge_fn
         self.exchange = exchange
+        # use_plan: the local search of exclusion-free query batches runs as one CUDA-graph replay
+        # (ExactIndex.compile_search), compiled once per (U, top_k)
+        self.use_plan = use_plan
+        self._plans: dict = {}
         self._peer: PeerExchange | None = None
         self._peer_failed: str | None = None
 
@@ -138,7 +142,13 @@ class ShardedIndex:
         return cls(idx, group=group)
 
     def search_batch(self, queries: torch.Tensor, exclude_rows=None, top_k: int = 20):
-        s, i = self.local.search_batch(queries, exclude_rows, top_k)
+        if self.use_plan and exclude_rows is None and queries.dim() == 2:
+            key = (queries.size(0), top_k)
+            if key not in self._plans:
+                self._plans[key] = self.local.compile_search(queries.size(0), top_k)
+            s, i = self._plans[key](queries)
+        else:
+            s, i = self.local.search_batch(queries, exclude_rows, top_k)
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         if world > 1 and self.exchange in ("peer", "auto") and self.merge_fn is None and s.is_cuda:
             px = self._peer_exchange(s.size(0), top_k, s.device)

@@ -172,6 +172,13 @@ class ExactIndex:
         ops.mask_excluded_ids(scores, ids, self.row_offset, self.row_offset + n, csr)
         return ops.topk_merge(scores, ids, top_k)
 
+    def compile_search(self, n_queries: int, top_k: int = TOP_K, max_exclusions: int = 0) -> "SearchPlan":
+        """The whole search for a FIXED shape ``(n_queries, top_k)`` and at most ``max_exclusions``
+        excluded rows per query as one CUDA-graph replay: ~15 launches and their Python / ctypes
+        dispatch become one ``cudaGraphLaunch`` (the per-user validation loop of trainer.py:293-298
+        and the serving path call search once per query: host dispatch, not the GPU, bounds them)."""
+        return SearchPlan(self, n_queries, top_k, max_exclusions)
+
     def search(self, embedding, exclude_item_ids: list[str] | None = None, top_k: int = TOP_K):
         """``LanceIndex.search`` (index.py:214-255): one query vector in, a
         ``datasets.Dataset`` with ``item_id`` / ``score`` (+ stored columns) out, rank order."""
@@ -271,3 +278,69 @@ class ExactIndex:
         self.id2row = None if self.ids is None else {k: i for i, k in enumerate(self.ids)}
         self.columns = blob["columns"]
         return self
+
+
+class SearchPlan:
+    """CUDA-graph replay of ``ExactIndex.search_batch`` for a fixed ``(U, top_k, max_exclusions)``.
+
+    ``plan(queries, exclude)``: ``queries`` (U, D) on the device; ``exclude`` = None or a CSR pair
+    ``(offsets (U+1,), rows (n,))`` of device int64 tensors with at most ``max_exclusions`` rows per
+    query (checked on the host only if the offsets are a host list).  Returns views of the plan's
+    static output buffers ``(scores (U, k), rows (U, k))`` — valid until the next call."""
+
+    def __init__(self, index: ExactIndex, n_queries: int, top_k: int, max_exclusions: int = 0):
+        assert index.catalog is not None, "index_data / set_catalog first"
+        self.index, self.u, self.k, self.max_excl = index, int(n_queries), int(top_k), int(max_exclusions)
+        dev = index.catalog.device
+        cat = index.catalog
+        n = cat.size(0)
+        probe = torch.empty((1, cat.size(1)), dtype=cat.dtype, device=dev)
+        if not (ops.score_groupmax_supported(probe, cat) and index.config.fused):
+            raise ops.N.NativeError("compile_search needs the tensor-core group-max path "
+                                    "(bf16 catalog, D = 384, sm_100)")
+        n_groups = (n + 15) // 16
+        self.kg = min(n_groups, self.k + self.max_excl + 28)
+        if self.kg > 1024:
+            raise ValueError("top_k + max_exclusions too large for the group-max path")
+        self.q = torch.zeros((self.u, cat.size(1)), dtype=torch.float32, device=dev)
+        self.offs = torch.zeros(self.u + 1, dtype=torch.int64, device=dev)
+        self.rows = torch.zeros(max(1, self.u * self.max_excl), dtype=torch.int64, device=dev)
+        self.device = dev
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):      # warm-up outside capture (one-time kernel attributes)
+                self._run()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out_s, self.out_i = self._run()
+
+    def _run(self):
+        idx = self.index
+        cat = idx.catalog
+        if idx.config.index_metric == "cosine":
+            q, _ = ops.normalize_rows(self.q, 1e-12, cat.dtype)
+        else:
+            q = self.q.to(cat.dtype)
+        csr = (self.offs, self.rows) if self.max_excl > 0 else None
+        s, i = idx._search_groupmax(q, cat, csr, self.k, self.kg)
+        dead = s == float("-inf")
+        return s, torch.where(dead, torch.full_like(i, -1), i)
+
+    def __call__(self, queries: torch.Tensor, exclude=None):
+        assert queries.shape == self.q.shape, f"plan was compiled for {tuple(self.q.shape)} queries"
+        self.q.copy_(queries, non_blocking=True)
+        if self.max_excl > 0:
+            if exclude is None:
+                self.offs.zero_()
+            else:
+                offs, rows = exclude
+                assert offs.numel() == self.u + 1 and rows.numel() <= self.rows.numel()
+                self.offs.copy_(offs, non_blocking=True)
+                self.rows[: rows.numel()].copy_(rows, non_blocking=True)
+        else:
+            assert exclude is None, "plan was compiled with max_exclusions = 0"
+        self.graph.replay()
+        return self.out_s, self.out_i
