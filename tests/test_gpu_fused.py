@@ -316,3 +316,34 @@ def test_evaluate_all_uses_two_passes_and_matches_modules(xr):
     want_stats = orc.logits_statistics(lb, tgt, orc.mask_false_negatives(lb, tgt, orc.Config()), orc.Config())
     for k, v in want_stats.items():
         assert stats[k] == pytest.approx(v, rel=5e-3, abs=5e-3), k
+
+
+@pytest.mark.parametrize("u,n,k", [(5, 40000, 20), (140, 30000, 50)])
+def test_groupmax_two_phase_rescore_with_adversarial_exclusions(xr, u, n, k):
+    """Exclusion lists: phase 1 re-scores top_k + 28 groups, phase 2 the conservative remainder only
+    for queries whose k-th surviving score does not clear the next group maximum.  Adversarial case:
+    the excluded rows ARE the best-scoring rows (a user's history scores high), so phase 2 must run;
+    exact-arithmetic inputs -> indices identical to the stable-sort oracle, ties included."""
+    rng = np.random.default_rng(n + u)
+    cat = rng.integers(-2, 3, size=(n, 384)).astype(np.float32)
+    cat[7] = cat[3]
+    qs = rng.integers(-2, 3, size=(u, 384)).astype(np.float32)
+    _, top = orc.exact_search(qs, cat, 160, None, metric="dot")
+    excl = []
+    for r in range(u):
+        if r % 3 == 0:
+            excl.append([int(x) for x in top[r, :150]])               # everything phase 1 would find
+        elif r % 3 == 1:
+            excl.append([int(x) for x in top[r, ::2][:60]])           # every other top row
+        else:
+            excl.append([int(x) for x in rng.integers(0, n, size=30)])  # random: phase 1 suffices
+    idx = xr.index.ExactIndex(xr.index.ExactIndexConfig(index_metric="dot", dtype="bf16")).set_catalog(
+        torch.from_numpy(cat).cuda())
+    q = torch.from_numpy(qs).cuda()
+    s, i = idx.search_batch(q, excl, k)
+    want_s, want_i = orc.exact_search(qs, cat, k, excl, metric="dot")
+    assert np.array_equal(i.cpu().numpy(), want_i)
+    assert np.array_equal(s.cpu().numpy(), want_s)
+    plan = idx.compile_search(u, k, max_exclusions=150)
+    ps, pi = plan(q, xr.ops._csr(excl, q.device))
+    assert torch.equal(pi, i) and torch.equal(ps, s)

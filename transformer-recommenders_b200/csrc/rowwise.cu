@@ -225,7 +225,7 @@ __device__ __forceinline__ void sampled_logits384_row(const T* __restrict__ q_ro
 #pragma unroll
       for (int t = 0; t < IT; ++t) {
         const int v = lane + 32 * t;
-        if (v < VECS) RowVec<T>::load(table + row[u] * FD + v * E, x[u][t]);
+        if (v < VECS && valid[u]) RowVec<T>::load(table + row[u] * FD + v * E, x[u][t]);   // invalid: no bytes read
         else
 #pragma unroll
           for (int k = 0; k < E; ++k) x[u][t][k] = 0.f;

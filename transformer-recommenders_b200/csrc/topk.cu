@@ -429,7 +429,7 @@ __global__ void groups_to_rows_kernel(const int64_t* __restrict__ gi, int64_t to
     }
     const int64_t c = first + (e & 15);
     const bool ok = g >= 0 && c < n;
-    cols[e] = ok ? c : 0;
+    cols[e] = ok ? c : -1;                        // -1: the re-score gather reads nothing for it
     ids[e] = ok ? c + row_offset : -1;
   }
 }

@@ -162,15 +162,34 @@ class ExactIndex:
         """Tensor-core path: group maxima (tcgen05) -> top groups -> exact re-score of their rows
         -> merge under (score desc, row asc).  The k-th largest group maximum lower-bounds the k-th
         largest score and every score above it sits in a group above it; `kg` adds one group per
-        excluded id plus a margin, so the result equals the full scan."""
+        excluded id plus a margin, so the result equals the full scan.
+
+        With exclusion lists the conservative `kg` (one extra group per excluded id) is rarely
+        needed: phase 1 re-scores only the first ``top_k + 28`` groups; a query is DONE when its k-th
+        surviving score is strictly above the next group maximum (no row outside can reach it, ties
+        included).  Phase 2 re-scores the remaining groups for the other queries only (their group
+        ids are replaced by -1 for finished queries, which the gather skips) — no host sync, same
+        result as re-scoring all `kg` groups."""
         n = cat.size(0)
         gmax, layout = ops.score_groupmax(q, cat)
         n_slots = gmax.size(1) if layout else (n + 15) // 16         # every slot of the pair layout is written
-        _, gi = ops.topk(gmax, kg, n=n_slots)                        # (U, kg) group slots, -1 = none
-        cols, ids = ops.groups_to_rows(gi, n, self.row_offset, layout)
-        scores = ops.logits_sampled(q, cat, cols)
-        ops.mask_excluded_ids(scores, ids, self.row_offset, self.row_offset + n, csr)
-        return ops.topk_merge(scores, ids, top_k)
+        gv, gi = ops.topk(gmax, kg, n=n_slots)                       # (U, kg) group maxima / slots, -1 = none
+        kg1 = min(kg, top_k + 28)
+
+        def rescore(slots):
+            cols, ids = ops.groups_to_rows(slots, n, self.row_offset, layout)
+            scores = ops.logits_sampled(q, cat, cols)
+            ops.mask_excluded_ids(scores, ids, self.row_offset, self.row_offset + n, csr)
+            return ops.topk_merge(scores, ids, top_k)
+
+        if csr is None or kg1 >= kg:
+            return rescore(gi)
+        s1, i1 = rescore(gi[:, :kg1].contiguous())
+        bound = gv[:, kg1]                                           # best score any row outside phase 1 can have
+        done = s1[:, top_k - 1] > bound if s1.size(1) >= top_k else torch.zeros_like(bound, dtype=torch.bool)
+        rest = torch.where(done[:, None], torch.full_like(gi[:, kg1:], -1), gi[:, kg1:]).contiguous()
+        s2, i2 = rescore(rest)
+        return ops.topk_merge(torch.cat([s1, s2], 1), torch.cat([i1, i2], 1), top_k)
 
     def compile_search(self, n_queries: int, top_k: int = TOP_K, max_exclusions: int = 0) -> "SearchPlan":
         """The whole search for a FIXED shape ``(n_queries, top_k)`` and at most ``max_exclusions``
