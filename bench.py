@@ -487,6 +487,13 @@ def main():
         b0 = orc.synth_batch(N_ITEMS, BATCH, SEQ_LEN, dim=DIM, seed=0)
         times = cpu_baseline.time_train_steps(b0, args.cpu_steps, warmup=1)
         cpu_ms = 1e3 * sum(times) / len(times)
+        if world == 1:   # the trainer's whole compute_losses on the host cores (one full step)
+            cl_times, _ = cpu_baseline.time_compute_losses(b0, 1, warmup=0)
+            line["compute_losses"]["cpu_baseline"] = {
+                "value": BATCH / cl_times[0], "unit": "seq/s", "ms_per_step": 1e3 * cl_times[0],
+                "cores": os.cpu_count(), "kind": "port",
+                "sample": "1 full step (B=%d): LogitsStatistics + all seven losses + InfoNCE backward, "
+                          "reference-lean torch CPU ops, fp32" % BATCH}
         line["cpu_baseline"] = {"value": BATCH / (cpu_ms / 1e3), "unit": "seq/s",
                                 "cores": os.cpu_count(), "kind": "port",
                                 "sample": f"{args.cpu_steps} full steps (B={BATCH}) of the same "
@@ -495,6 +502,17 @@ def main():
 
     if not args.no_retrieval:
         line["retrieval"] = bench_retrieval(args, xr, dev, rank, world, peak_hbm)
+        if rank == 0 and world == 1:   # exact cosine top-k on the host cores, bounded sample
+            from oracle import cpu_baseline
+
+            rows_s, q_s = min(args.catalog, 1_000_000), args.queries
+            dt = cpu_baseline.time_exact_search(rows_s, q_s, 100, dim=DIM)
+            line["retrieval"]["cpu_baseline"] = {
+                "value": q_s / dt * rows_s / args.catalog, "unit": "queries/s", "cores": os.cpu_count(),
+                "kind": "port",
+                "sample": f"{q_s} queries x {rows_s} fp32 rows (chunked matmul + stable sort, torch CPU ops) in "
+                          f"{dt:.2f} s = {q_s / dt:.1f} queries/s at that size, scaled linearly in the "
+                          f"number of rows to the {args.catalog}-row catalog"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

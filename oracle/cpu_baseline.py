@@ -88,3 +88,76 @@ def time_train_steps(batch, steps, warmup=1):
         train_step(*args)
         times.append(time.perf_counter() - t0)
     return times
+
+
+def _weighted_mean(values, weights):
+    """losses.py:90-111."""
+    return (values * weights).sum(-1) / (weights.sum(-1) + 1e-9)
+
+
+def compute_losses_lean(table, tokens, hist, pos, neg, margin=0.5, scale=1.0):
+    """What ``RecommenderLightningModule.compute_losses`` evaluates per step (trainer.py:250-263):
+    LogitsStatistics + all seven losses (the reference recomputes the logits for each of them: eight
+    passes; here each family's logits are computed once per loss as the reference does, in the lean
+    ``[rowdot | Q.Neg^T]`` form) + the backward of InfoNCE.  torch CPU ops, fp32."""
+    tokens = tokens.detach().requires_grad_(True)
+    q, p, n = compute_embeds_lean(table, tokens, hist, pos, neg)
+
+    def dot_logits():
+        return torch.cat([(q * p).sum(-1, keepdim=True), q @ n.T], dim=1)                 # losses.py:195
+
+    def cos_logits():
+        qn, pn, nn_ = F.normalize(q, dim=-1, eps=1e-8), F.normalize(p, dim=-1, eps=1e-8), F.normalize(n, dim=-1, eps=1e-8)
+        return torch.cat([(qn * pn).sum(-1, keepdim=True), qn @ nn_.T], dim=1)            # losses.py:206-208
+
+    def mask(l):
+        return (l < l[:, :1]).float()                                                    # losses.py:289-292
+
+    out = {}
+    l = dot_logits()                                                                     # LogitsStatistics
+    m = mask(l)
+    negs = l[m.bool()]
+    out["stats"] = (float(m.sum(1).mean()), float(l[:, 0].mean()), float(l[:, 0].std()), float(negs.mean()),
+                    float(negs.std()), float(negs.min()), float(negs.max()))
+    l = cos_logits(); out["AlignmentLoss"] = (1 - l[:, 0]).sum()                          # losses.py:352-353
+    l = cos_logits(); m = mask(l)
+    out["AlignmentContrastiveLoss"] = (1 - l[:, 0]).sum() + _weighted_mean(F.relu(l - 1 + margin), m).sum()
+    l = cos_logits(); m = mask(l); out["ContrastiveLoss"] = _weighted_mean(F.relu(l - 1 + margin), m).sum()
+    out["InfoNCELoss"] = infonce_lean(q, p, n, scale)                                     # losses.py:479-488
+    l = dot_logits(); m = mask(l)
+    out["NCELoss"] = (F.softplus(-l[:, 0]) + _weighted_mean(F.softplus(l), m)).sum()      # losses.py:498-511
+    l = dot_logits(); m = mask(l)
+    out["PairwiseHingeLoss"] = _weighted_mean(F.relu(l - (1 - margin) * l[:, :1]), m).sum()
+    l = dot_logits(); m = mask(l)
+    out["PairwiseLogisticLoss"] = _weighted_mean(F.softplus(l - (1 - margin) * l[:, :1]), m).sum()
+    out["InfoNCELoss"].backward()
+    return {k: (float(v.detach()) if torch.is_tensor(v) else v) for k, v in out.items()}
+
+
+def time_compute_losses(batch, steps=1, warmup=0):
+    import os
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    args = [torch.from_numpy(batch[k]) for k in
+            ("table", "token_embeddings", "history_item_idx", "pos_item_idx", "neg_item_idx")]
+    for _ in range(warmup):
+        compute_losses_lean(*args)
+    times, last = [], None
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        last = compute_losses_lean(*args)
+        times.append(time.perf_counter() - t0)
+    return times, last
+
+
+def time_exact_search(n_rows, n_queries, k, dim=384, seed=0):
+    """Exact cosine top-k of `n_queries` queries over an `n_rows` fp32 catalog on the host cores."""
+    import os
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(seed)
+    cat = F.normalize(torch.randn((n_rows, dim), generator=g), dim=-1)
+    q = torch.randn((n_queries, dim), generator=g)
+    t0 = time.perf_counter()
+    s, i = exact_search(q, cat, k)
+    return time.perf_counter() - t0
