@@ -475,6 +475,13 @@ def main():
                                "reference's call sequence; one host sync for the row counts)"},
     }
 
+    if not args.no_retrieval:
+        line["retrieval"] = bench_retrieval(args, xr, dev, rank, world, peak_hbm)
+    # every GPU leg is done: leave the process group BEFORE the CPU legs (only rank 0 runs them; they use
+    # all host cores, and an earlier version that ran them before the retrieval leg made rank 0 stall
+    # for tens of milliseconds inside the timed searches while the other ranks waited in the exchange)
+    if world > 1:
+        dist.destroy_process_group()
     if rank == 0:
         # ---- CPU baseline: same workload, reference arithmetic on the host cores ------------------
         from oracle import cpu_baseline
@@ -501,7 +508,6 @@ def main():
                                 "ms_per_step": cpu_ms}
 
     if not args.no_retrieval:
-        line["retrieval"] = bench_retrieval(args, xr, dev, rank, world, peak_hbm)
         if rank == 0 and world == 1:   # exact cosine top-k on the host cores, bounded sample
             from oracle import cpu_baseline
 
@@ -515,8 +521,6 @@ def main():
                           f"number of rows to the {args.catalog}-row catalog"}
     if rank == 0:
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def bench_retrieval(args, xr, dev, rank, world, peak_hbm):

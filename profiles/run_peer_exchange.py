@@ -51,10 +51,12 @@ for mode in ("nccl", "peer"):
         b.record()
     torch.cuda.synchronize()
     ok = ok and bool(torch.equal(i, want_i) and torch.equal(s, want_s))
-    ms = sorted(a.elapsed_time(b) for a, b in evs)
+    in_order = [round(a.elapsed_time(b), 3) for a, b in evs]
+    ms = sorted(in_order)
     t = torch.tensor([ms[len(ms) // 2], 0.0 if ok else 1.0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    res[mode] = {"ms_per_search_median_max_over_ranks": float(t[0]), "equals_unsharded": float(t[1]) == 0.0}
+    res[mode] = {"ms_per_search_median_max_over_ranks": float(t[0]), "equals_unsharded": float(t[1]) == 0.0,
+                 "rank0_ms_in_order": in_order}
 if rank == 0:
     print(json.dumps({"world": world, "catalog_rows": n, "queries": u, "k": k, **res}))
 bad = [m for m, r in res.items() if not r["equals_unsharded"]]
