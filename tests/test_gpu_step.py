@@ -10,7 +10,8 @@ from oracle import xfmr_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
-KINDS = ["InfoNCELoss", "NCELoss", "PairwiseHingeLoss", "PairwiseLogisticLoss"]
+KINDS = ["InfoNCELoss", "NCELoss", "PairwiseHingeLoss", "PairwiseLogisticLoss",
+         "ContrastiveLoss", "AlignmentContrastiveLoss"]   # dot family + the cosine (CCL) family
 
 
 @pytest.fixture(scope="module")
@@ -128,7 +129,7 @@ def test_step_rejects_what_it_does_not_serve(xr):
     b = orc.synth_batch(100, 2, 8, dim=384, seed=1)
     emb = xr.models.ItemEmbeddings(torch.from_numpy(b["table"]), add_padding_row=False).cuda()
     with pytest.raises(NotImplementedError):
-        xr.PoolLossStep(emb, xr.AlignmentContrastiveLoss(xr.LossConfig()), 2, 8)
+        xr.PoolLossStep(emb, xr.AlignmentLoss(xr.LossConfig()), 2, 8)     # no negatives: nothing to fuse
     with pytest.raises(NotImplementedError):
         xr.PoolLossStep(emb, xr.InfoNCELoss(xr.LossConfig(num_hard_negatives=5)), 2, 8)
     with pytest.raises(xr._native.NativeError):

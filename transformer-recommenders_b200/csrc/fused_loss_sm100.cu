@@ -1461,6 +1461,31 @@ extern "C" size_t xr_pool_step_workspace_bytes(int64_t n_pos, int64_t dim) {
   return carve_step_ws(nullptr, n_pos).bytes;
 }
 
+// extra buffers of the cosine kinds and of the monitoring pass: row-normalised operand copies
+struct MonitorWs {
+  __nv_bfloat16 *qn, *pn, *nn;
+  float *inv, *inv_q;   // inv: scratch for pos / neg norms; inv_q: 1/||q|| kept for the cosine chain rule
+  double* row_out;
+  size_t bytes;
+};
+static MonitorWs carve_monitor_ws(void* base, long long n_pos) {
+  MonitorWs w;
+  uint8_t* p = (uint8_t*)base;
+  const size_t n = (size_t)n_pos;
+  w.qn = (__nv_bfloat16*)p;   p += align256(n * fk::D * 2);
+  w.pn = (__nv_bfloat16*)p;   p += align256(n * fk::D * 2);
+  w.nn = (__nv_bfloat16*)p;   p += align256(n * fk::D * 2);
+  w.inv = (float*)p;          p += align256(n * 4);
+  w.inv_q = (float*)p;        p += align256(n * 4);
+  w.row_out = (double*)p;     p += align256(n * ROW_SLOTS * 8);
+  w.bytes = (size_t)(p - (uint8_t*)base);
+  return w;
+}
+
+static size_t step_ws_bytes_with_normalised(long long n_pos) {
+  return carve_step_ws(nullptr, n_pos).bytes + carve_monitor_ws(nullptr, n_pos).bytes;
+}
+
 // The step in two phases, so that a caller with two alternating step objects can overlap the INGEST
 // of batch i+1 (index compaction, plan, the three gathers -- the only part that touches the batch's
 // inputs) with the COMPUTE of batch i on another stream.  `tok` may be pinned HOST memory (UVA): the
@@ -1515,17 +1540,29 @@ extern "C" int xr_pool_step_compute(int64_t n_pos, int64_t dim, int loss_kind, c
                "xr_pool_step_compute: buffers must be 16-byte aligned (workspace 256)");
   int rc;
   if ((rc = check_fused_kind("xr_pool_step_compute", loss_kind, cfg))) return rc;
-  XR_CHECK_ARG(loss_kind != XR_LOSS_CONTRASTIVE && loss_kind != XR_LOSS_ALIGNMENT_CONTRASTIVE,
-               "xr_pool_step: the cosine kinds go through compute_embeds + the loss modules");
-  XR_CHECK_ARG(workspace_bytes >= xr_pool_step_workspace_bytes(n_pos, dim),
-               "xr_pool_step_compute: workspace too small");
+  const bool cosine = loss_kind == XR_LOSS_CONTRASTIVE || loss_kind == XR_LOSS_ALIGNMENT_CONTRASTIVE;
+  XR_CHECK_ARG(workspace_bytes >= (cosine ? step_ws_bytes_with_normalised(n_pos)
+                                          : xr_pool_step_workspace_bytes(n_pos, dim)),
+               "xr_pool_step_compute: workspace too small (the cosine kinds need "
+               "xr_pool_step_monitor_workspace_bytes)");
   if ((rc = check_fused_device("xr_pool_step_compute"))) return rc;
   const StepWs w = carve_step_ws(workspace, n_pos);
   // 4. fused contraction + loss + dL/dtok: the finalize kernel writes the gradient in the encoder
   //    output's layout (zero rows for unselected positions: autograd of
   //    token_embeddings[mask][pos_mask], models.py:392, 415)
   const StepScatter sc{w.inv_pos, n_pos, dtok, dtok_dtype == XR_BF16};
-  return fused_launch_all(w.q, w.pos, w.neg, n_pos, n_pos, loss_kind, cfg, nullptr, grad_scale, nullptr,
+  if (!cosine)
+    return fused_launch_all(w.q, w.pos, w.neg, n_pos, n_pos, loss_kind, cfg, nullptr, grad_scale, nullptr,
+                            loss_out, nullptr, w.fused, true, as_stream(stream), dtok ? &sc : nullptr);
+  // cosine kinds (CCL, losses.py:206-208, 338-372): row-normalised copies of the three operands (all
+  // n_pos rows: static shapes), 1/||q|| kept for the chain rule through the query normalisation
+  const MonitorWs mw = carve_monitor_ws((uint8_t*)workspace + w.bytes, n_pos);
+  if ((rc = xr_normalize_rows(w.q, n_pos, fk::D, XR_BF16, 1e-8f, mw.qn, XR_BF16, mw.inv_q, stream))) return rc;
+  if ((rc = xr_normalize_rows(w.pos, n_pos, fk::D, XR_BF16, 1e-8f, mw.pn, XR_BF16, mw.inv, stream))) return rc;
+  if ((rc = xr_normalize_rows(w.neg, n_pos, fk::D, XR_BF16, 1e-8f, mw.nn, XR_BF16, mw.inv, stream))) return rc;
+  xr_loss_config ccfg = *cfg;
+  ccfg.logits_bf16 = 0;   // cosine logits stay fp32 under autocast
+  return fused_launch_all(mw.qn, mw.pn, mw.nn, n_pos, n_pos, loss_kind, &ccfg, mw.inv_q, grad_scale, nullptr,
                           loss_out, nullptr, w.fused, true, as_stream(stream), dtok ? &sc : nullptr);
 }
 
@@ -1539,8 +1576,11 @@ extern "C" int xr_pool_step(const int64_t* history_idx, const int64_t* pos_idx,
   XR_CHECK_ARG(cfg && loss_out, "xr_pool_step: null pointer");
   int rc;
   if ((rc = check_fused_kind("xr_pool_step", loss_kind, cfg))) return rc;   // before any launch
-  XR_CHECK_ARG(loss_kind != XR_LOSS_CONTRASTIVE && loss_kind != XR_LOSS_ALIGNMENT_CONTRASTIVE,
-               "xr_pool_step: the cosine kinds go through compute_embeds + the loss modules");
+  {
+    const bool cosine = loss_kind == XR_LOSS_CONTRASTIVE || loss_kind == XR_LOSS_ALIGNMENT_CONTRASTIVE;
+    XR_CHECK_ARG(!cosine || (dim == fk::D && n_pos > 0 && workspace_bytes >= step_ws_bytes_with_normalised(n_pos)),
+                 "xr_pool_step: the cosine kinds need a workspace of xr_pool_step_monitor_workspace_bytes");
+  }
   if ((rc = xr_pool_step_ingest(history_idx, pos_idx, neg_idx, n_pos, tok, tok_dtype, table_bf16, rownz,
                                 n_table_rows, dim, counts, err_flag, workspace, workspace_bytes, stream)))
     return rc;
@@ -1553,28 +1593,9 @@ extern "C" int xr_pool_step(const int64_t* history_idx, const int64_t* pos_idx,
 // xr_pool_step on the SAME stream and workspace, this runs both all-losses passes on the operands the
 // step gathered (dot: q / pos / neg as they are; cosine: their row-normalised copies,
 // losses.py:206-208), still without a device->host copy: CUDA-graph capturable together with the step.
-struct MonitorWs {
-  __nv_bfloat16 *qn, *pn, *nn;
-  float* inv;
-  double* row_out;
-  size_t bytes;
-};
-static MonitorWs carve_monitor_ws(void* base, long long n_pos) {
-  MonitorWs w;
-  uint8_t* p = (uint8_t*)base;
-  const size_t n = (size_t)n_pos;
-  w.qn = (__nv_bfloat16*)p;   p += align256(n * fk::D * 2);
-  w.pn = (__nv_bfloat16*)p;   p += align256(n * fk::D * 2);
-  w.nn = (__nv_bfloat16*)p;   p += align256(n * fk::D * 2);
-  w.inv = (float*)p;          p += align256(n * 4);
-  w.row_out = (double*)p;     p += align256(n * ROW_SLOTS * 8);
-  w.bytes = (size_t)(p - (uint8_t*)base);
-  return w;
-}
-
 extern "C" size_t xr_pool_step_monitor_workspace_bytes(int64_t n_pos, int64_t dim) {
   if (dim != fk::D || n_pos <= 0) return 512;
-  return carve_step_ws(nullptr, n_pos).bytes + carve_monitor_ws(nullptr, n_pos).bytes;
+  return step_ws_bytes_with_normalised(n_pos);
 }
 
 extern "C" int xr_pool_step_monitor(int64_t n_pos, int64_t dim, const xr_loss_config* cfg,

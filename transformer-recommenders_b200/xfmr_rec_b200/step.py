@@ -30,7 +30,9 @@ from . import ops
 from .losses import EmbedLoss, _autocast_bf16
 from .models import ItemEmbeddings
 
-_STEP_KINDS = ("InfoNCELoss", "NCELoss", "PairwiseHingeLoss", "PairwiseLogisticLoss")
+_STEP_KINDS = ("InfoNCELoss", "NCELoss", "PairwiseHingeLoss", "PairwiseLogisticLoss",
+               "ContrastiveLoss", "AlignmentContrastiveLoss")
+_COSINE_KINDS = ("ContrastiveLoss", "AlignmentContrastiveLoss")
 
 
 class PoolLossStep:
@@ -42,8 +44,7 @@ class PoolLossStep:
         name = type(loss).__name__
         if name not in _STEP_KINDS:
             raise NotImplementedError(
-                f"PoolLossStep serves the dot-product losses {_STEP_KINDS}; {name} goes through "
-                "compute_embeds + the loss module")
+                f"PoolLossStep serves {_STEP_KINDS}; {name} goes through compute_embeds + the loss module")
         cfg = loss.config
         if cfg.target_position != "first":
             raise NotImplementedError("PoolLossStep: candidates are [positive | shared pool] "
@@ -60,6 +61,9 @@ class PoolLossStep:
         self.d = embeddings.embedding_dim
         self.kind = N.LOSS_KIND[name]
         # dot logits are bf16 under bf16-mixed autocast or for bf16 encoder output (losses.py:195)
+        self.cosine = name in _COSINE_KINDS      # CCL family: row-normalised operands, fp32 logits
+        if self.cosine:
+            logits_bf16 = False
         if logits_bf16 is None:
             logits_bf16 = token_dtype == torch.bfloat16 or _autocast_bf16()
         self.cfg = ops.make_cfg(cfg, logits_bf16=bool(logits_bf16))
@@ -78,7 +82,7 @@ class PoolLossStep:
             self.loss_buf = torch.zeros(2, dtype=torch.float64, device=dev)
             self.counts = torch.zeros(2, dtype=torch.int64, device=dev)
             self.err = torch.zeros(1, dtype=torch.int32, device=dev) if check_indices else None
-            nbytes = (N.lib().xr_pool_step_monitor_workspace_bytes(n, self.d) if monitor
+            nbytes = (N.lib().xr_pool_step_monitor_workspace_bytes(n, self.d) if (monitor or self.cosine)
                       else N.lib().xr_pool_step_workspace_bytes(n, self.d))
             # monitor: LogitsStatistics + all seven losses (trainer.py:250-263) in the same sequence
             self.monitor = bool(monitor)
