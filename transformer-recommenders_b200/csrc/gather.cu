@@ -243,6 +243,92 @@ compact_write_kernel(const int64_t* __restrict__ history_idx, const int64_t* __r
   }
 }
 
+// The same compaction as ONE kernel when every chunk's block is resident at once (nchunks <= SM
+// count: up to ~300k positions): each block scans its chunk, publishes its two totals as one 64-bit
+// word (bit 63 = valid), waits for the words of the blocks before it, and writes its rows at the
+// resulting offsets; the last block writes the two totals.  Same ordered result as the three-kernel
+// form (count / scan / write), two launches fewer on the train step's critical path.
+__global__ void __launch_bounds__(kCompactThreads)
+compact_fused_kernel(const int64_t* __restrict__ history_idx, const int64_t* __restrict__ pos_idx,
+                     const uint8_t* __restrict__ rownz, int64_t n_table_rows, int64_t n_pos,
+                     unsigned long long* __restrict__ chunk_tot /* [nchunks], zeroed */,
+                     uint8_t* __restrict__ attn, int64_t* __restrict__ sel_attn,
+                     int64_t* __restrict__ sel_pos, uint8_t* __restrict__ pos_mask,
+                     int64_t* __restrict__ inv_pos, int64_t* __restrict__ counts) {
+  constexpr int PER = kChunk / kCompactThreads;
+  __shared__ int s_a[kCompactThreads], s_q[kCompactThreads];
+  __shared__ unsigned long long s_before;
+  const int64_t base = (int64_t)blockIdx.x * kChunk + (int64_t)threadIdx.x * PER;
+  bool fa[PER], fq[PER];
+  int ca = 0, cq = 0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int64_t p = base + i;
+    fa[i] = fq[i] = false;
+    if (p < n_pos) {
+      position_flags(history_idx, pos_idx, rownz, n_table_rows, p, fa[i], fq[i]);
+      attn[p] = fa[i];
+    }
+    ca += fa[i];
+    cq += fq[i];
+  }
+  s_a[threadIdx.x] = ca;
+  s_q[threadIdx.x] = cq;
+  if (threadIdx.x == 0) s_before = 0ull;
+  __syncthreads();
+  for (int off = 1; off < kCompactThreads; off <<= 1) {   // Hillis-Steele inclusive scan
+    int va = 0, vq = 0;
+    if ((int)threadIdx.x >= off) {
+      va = s_a[threadIdx.x - off];
+      vq = s_q[threadIdx.x - off];
+    }
+    __syncthreads();
+    s_a[threadIdx.x] += va;
+    s_q[threadIdx.x] += vq;
+    __syncthreads();
+  }
+  const unsigned long long mine =
+      ((unsigned long long)s_a[kCompactThreads - 1] << 32) | (unsigned long long)s_q[kCompactThreads - 1];
+  if (threadIdx.x == 0) {
+    // one 64-bit store carries data + valid bit: no separate flag, no fence ordering to get wrong
+    atomicExch(chunk_tot + blockIdx.x, mine | 0x8000000000000000ull);
+  }
+  // totals of the chunks before this one (all blocks are resident: the spin cannot starve anyone)
+  unsigned long long acc = 0ull;
+  for (int b = threadIdx.x; b < (int)blockIdx.x; b += kCompactThreads) {
+    unsigned long long v;
+    do {
+      v = *reinterpret_cast<volatile unsigned long long*>(chunk_tot + b);
+    } while (!(v >> 63));
+    acc += v & 0x7FFFFFFFFFFFFFFFull;   // the (a, q) halves never carry into each other: a, q < 2^31
+  }
+  if (acc) atomicAdd(&s_before, acc);
+  __syncthreads();
+  const unsigned long long before = s_before;
+  int64_t oa = (int64_t)(before >> 32) + s_a[threadIdx.x] - ca;
+  int64_t oq = (int64_t)(before & 0xFFFFFFFFull) + s_q[threadIdx.x] - cq;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int64_t p = base + i;
+    if (fa[i]) {
+      sel_attn[oa] = p;
+      pos_mask[oa] = fq[i];
+      ++oa;
+    }
+    if (fq[i]) {
+      if (inv_pos) inv_pos[p] = oq;
+      sel_pos[oq++] = p;
+    } else if (inv_pos && p < n_pos) {
+      inv_pos[p] = -1;
+    }
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+    const unsigned long long tot = before + mine;
+    counts[0] = (int64_t)(tot >> 32);
+    counts[1] = (int64_t)(tot & 0xFFFFFFFFull);
+  }
+}
+
 // dst[p,:] = inv[p] >= 0 ? cast(src[inv[p],:] * *scale) : 0  — the whole backward of the query
 // compaction (models.py:392, 415) in one pass: zero fill + scatter + grad_output scale + cast.
 template <typename TO>
@@ -431,6 +517,14 @@ extern "C" int xr_compact_positions(const int64_t* history_idx, const int64_t* p
   }
   const int64_t nchunks = (n_pos + kChunk - 1) / kChunk;
   int64_t* cc = (int64_t*)workspace;
+  if (nchunks <= sm_count()) {   // every block resident at once: single-pass form
+    XR_CUDA(cudaMemsetAsync(cc, 0, (size_t)nchunks * sizeof(int64_t), s));
+    compact_fused_kernel<<<(unsigned)nchunks, kCompactThreads, 0, s>>>(
+        history_idx, pos_idx, rownz, n_table_rows, n_pos, reinterpret_cast<unsigned long long*>(cc), attn,
+        sel_attn, sel_pos, pos_mask, inv_pos, counts);
+    XR_LAUNCH_CHECK("compact_fused");
+    return XR_OK;
+  }
   compact_count_kernel<<<(unsigned)nchunks, kCompactThreads, 0, s>>>(
       history_idx, pos_idx, rownz, n_table_rows, n_pos, cc, nchunks);
   XR_LAUNCH_CHECK("compact_count");
