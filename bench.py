@@ -450,7 +450,7 @@ def main():
                         "training loop logs it.  Bound by the host link: 20.3 MB per step at ~52 GB/s = "
                         "0.39 ms; a concurrent H2D stream also slows the tensor-core kernel (0.30 -> 0.37 ms "
                         "per step, measured), a D2D copy of the same size does not"},
-        "gpu_launches": 9 * args.steps,   # xr_pool_step: compaction x3, plan, gather, diagonal, fused, finalize, row sum
+        "gpu_launches": 7 * args.steps,   # xr_pool_step: compaction, plan, gather, diagonal, fused, finalize, row sum
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "fused_pool_kernel<InfoNCE> (tcgen05)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
