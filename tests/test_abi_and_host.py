@@ -133,3 +133,29 @@ def test_sharded_merge_world2_gloo():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     assert all(out[r] for r in range(world))
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the driver's reference arm): one JSON line with the base contract's
+    keys, `impl: reference`, a cpu_baseline describing the run and a zero-copy e2e block; runs on
+    the host cores only."""
+    import json
+    import pathlib
+    import subprocess
+    import sys
+
+    root = pathlib.Path(__file__).resolve().parent.parent
+    env = dict(__import__("os").environ, XR_BENCH_BATCH="8")   # a small batch keeps the CPU suite fast
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--gpus", "1",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600,
+                         env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "seq/s"
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

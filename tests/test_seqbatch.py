@@ -251,3 +251,25 @@ def test_sampler_distribution_matches_the_reference(golden_dir, look):
             assert ((positive_cnt > 0) <= (z[f"{key}_positives"] > 0)).all(), key
             stat, dof = _two_sample_chi2(positive_cnt, z[f"{key}_positives"])
             assert stat <= dof + 5 * np.sqrt(2 * max(dof, 1)) + 5, (key, "positives", stat, dof)
+
+
+def test_history_csr_layout_follows_process_events():
+    """build_history_csr = the host-side part of SeqDataset.process_events (data.py:638-657): empty
+    histories dropped, one dataset row per started block of max_seq_length events (duplicate_rows,
+    data.py:618-636), per-history prefix counts of positive labels and sorted unique items."""
+    from xfmr_rec_b200.data import build_history_csr
+
+    hs = [np.array([5, 3, 5, 9]), np.array([], np.int64), np.array([2]), np.arange(1, 12)]
+    ls = [np.array([1, 0, 1, 1], bool), np.array([], bool), np.array([1], bool), np.ones(11, bool)]
+    c = build_history_csr(hs, ls, num_items=20, max_seq_length=4)
+    assert c["kept"] == [0, 2, 3]
+    assert c["hist_off"].tolist() == [0, 4, 5, 16]
+    assert c["items"].tolist() == [5, 3, 5, 9, 2] + list(range(1, 12))
+    assert c["pos_prefix"].tolist()[:5] == [1, 1, 2, 3, 1]
+    assert c["uniq_off"].tolist() == [0, 3, 4, 15] and c["uniq_items"].tolist()[:4] == [3, 5, 9, 2]
+    # rows: ceil-style (len - 1) // L + 1  ->  1, 1, 3
+    assert c["row_hist"].tolist() == [0, 1, 2, 2, 2]
+    with pytest.raises(IndexError):
+        build_history_csr([np.array([0, 1])], [np.array([1, 1], bool)], 20, 4)
+    with pytest.raises(IndexError):
+        build_history_csr([np.array([21])], [np.array([1], bool)], 20, 4)

@@ -33,6 +33,39 @@ class SeqDataConfig:
     pos_lookahead: int = 0
 
 
+def build_history_csr(histories, labels, num_items: int, max_seq_length: int) -> dict:
+    """Host-side layout of the per-user histories for ``xr_seq_sample_batch`` (pure numpy):
+    empty histories dropped (data.py:652), CSR offsets / items / labels, the inclusive count of
+    positive labels inside each history, the sorted unique items of each history, and the dataset-row
+    -> history map of ``duplicate_rows`` (data.py:618-636: ``(len - 1) // max_seq_length + 1`` rows per
+    history)."""
+    keep = [i for i, h in enumerate(histories) if len(h) > 0]
+    hs = [np.asarray(histories[i], np.int64) for i in keep]
+    ls = [np.asarray(labels[i], bool) for i in keep]
+    for h, l in zip(hs, ls):
+        if len(h) != len(l):
+            raise ValueError("history and label arrays differ in length")
+        if h.min() < 1 or h.max() > num_items:
+            raise IndexError("history item index out of range [1, num_items]")
+    lens = np.array([len(h) for h in hs], np.int64)
+    off = np.zeros(len(hs) + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    uniq = [np.unique(h) for h in hs]
+    uoff = np.zeros(len(hs) + 1, np.int64)
+    np.cumsum([len(u) for u in uniq], out=uoff[1:])
+    copies = (lens - 1) // int(max_seq_length) + 1
+    return {
+        "kept": keep,
+        "hist_off": off,
+        "items": np.concatenate(hs) if hs else np.zeros(0, np.int64),
+        "labels": np.concatenate(ls).astype(np.uint8) if ls else np.zeros(0, np.uint8),
+        "pos_prefix": np.concatenate([np.cumsum(l, dtype=np.int32) for l in ls]) if ls else np.zeros(0, np.int32),
+        "uniq_off": uoff,
+        "uniq_items": np.concatenate(uniq) if uniq else np.zeros(0, np.int64),
+        "row_hist": np.repeat(np.arange(len(hs), dtype=np.int64), copies),
+    }
+
+
 class SeqBatchSampler:
     """Device-resident stand-in for ``SeqDataset`` + ``collate``.
 
@@ -50,30 +83,14 @@ class SeqBatchSampler:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise N.NativeError("SeqBatchSampler needs a CUDA device; there is no CPU fallback")
-        L = int(config.max_seq_length)
-        keep = [i for i, h in enumerate(histories) if len(h) > 0]  # data.py:652
-        hs = [np.asarray(histories[i], np.int64) for i in keep]
-        ls = [np.asarray(labels[i], bool) for i in keep]
-        for h in hs:
-            if h.min() < 1 or h.max() > self.num_items:
-                raise IndexError("history item index out of range [1, num_items]")
-        lens = np.array([len(h) for h in hs], np.int64)
-        off = np.zeros(len(hs) + 1, np.int64)
-        np.cumsum(lens, out=off[1:])
-        items = np.concatenate(hs) if hs else np.zeros(0, np.int64)
-        labs = np.concatenate(ls).astype(np.uint8) if ls else np.zeros(0, np.uint8)
-        prefix = np.concatenate([np.cumsum(l, dtype=np.int32) for l in ls]) if ls else np.zeros(0, np.int32)
-        uniq = [np.unique(h) for h in hs]
-        uoff = np.zeros(len(hs) + 1, np.int64)
-        np.cumsum([len(u) for u in uniq], out=uoff[1:])
-        uitems = np.concatenate(uniq) if uniq else np.zeros(0, np.int64)
-        copies = (lens - 1) // L + 1  # duplicate_rows, data.py:631-635
-        row_hist = np.repeat(np.arange(len(hs), dtype=np.int64), copies)
-        self.kept_histories = keep
-        self.num_histories = len(hs)
+        csr = build_history_csr(histories, labels, self.num_items, int(config.max_seq_length))
+        self.kept_histories = csr["kept"]
+        self.num_histories = len(csr["kept"])
         up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)  # noqa: E731
-        self.hist_off, self.items, self.labels, self.pos_prefix = up(off), up(items), up(labs), up(prefix)
-        self.uniq_off, self.uniq_items, self.row_hist = up(uoff), up(uitems), up(row_hist)
+        self.hist_off, self.items = up(csr["hist_off"]), up(csr["items"])
+        self.labels, self.pos_prefix = up(csr["labels"]), up(csr["pos_prefix"])
+        self.uniq_off, self.uniq_items, self.row_hist = up(csr["uniq_off"]), up(csr["uniq_items"]), up(csr["row_hist"])
+        row_hist = csr["row_hist"]
         self._row_hist_host = row_hist
 
     def __len__(self) -> int:  # data.py:659-666
