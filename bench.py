@@ -456,8 +456,9 @@ def main():
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf if kern_ms else None,
                      # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full
-                     # capture of this kernel on this workload (profiles/ncu_fused_pool_kernel_r01b_raw.txt)
-                     "traffic": 25.09e6 if BATCH == 128 else None, "traffic_unit": "bytes",
+                     # capture of this kernel on this workload (profiles/ncu_fused_pool_kernel_r01c_raw.txt:
+                     # 19.57 MB read + 6.43 MB written; algorithmic operand bytes 28.3 MB, partial dQ stays in L2)
+                     "traffic": 26.0e6 if BATCH == 128 else None, "traffic_unit": "bytes",
                      "peak_source": f"{peak_src} sustained bf16 (MEASURED_PEAKS.json)",
                      "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step if kern_ms else None,
                      "algorithmic_flops_per_launch": flops},

@@ -21,6 +21,7 @@ import types
 import numpy as np
 import torch
 
+sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent))   # make_golden_embeds lives beside this file
 sys.path.insert(0, "/root/reference")
 from xfmr_rec import losses as ref_losses  # noqa: E402
 
