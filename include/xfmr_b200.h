@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define XR_ABI_VERSION 1
+#define XR_ABI_VERSION 2
 
 #define XR_F32 0
 #define XR_BF16 1
@@ -350,40 +350,61 @@ int xr_mask_excluded(float* scores, int64_t u, int64_t n, int64_t ld, int64_t co
                      const int64_t* excl_offsets, const int64_t* excl_ids, void* stream);
 
 /* Retrieval scoring on the tensor cores without materialising the (U, N) score matrix:
- *   gmax[u, g] = max over catalog rows c in [16g, 16g+16) of q_u . cat_c   (fp32; -inf past n)
- * q (U, 384) and catalog (N, 384) bf16 (pre-normalised rows for the cosine metric, index.py:47);
- * gmax is (U, ld) fp32 with ld >= 4 * ceil(N / 64).  The k-th largest group maximum of a row
- * lower-bounds its k-th largest score, so the exact top-k (index.py:244-254, `.limit(top_k)`)
- * only needs the top groups re-scored (xr_logits_sampled) and merged (xr_topk_merge).          */
+ *   gmax[u, g] = max over the 16 catalog rows of group g of q_u . cat_c   (fp32; -inf past n)
+ * q (U, 384) and catalog (N, 384) bf16 (pre-normalised rows for the cosine metric, index.py:47).
+ * Tiles of T catalog rows (T = 128 for U > 128 — the cta_group::2 kernel — else 64); with
+ * tile_stride = s only every s-th tile is scored (a SAMPLE of the catalog).  Storage column
+ * (T/16) t + g of gmax (U, ld) holds rows [T t s + 16 g, +16): for s = 1 column c = rows [16 c, +16), so
+ * xr_topk's (maximum desc, column asc) order is (maximum desc, first row asc).
+ * The k-th largest group maximum of a row — of the whole catalog or of any sample of it — is a lower
+ * bound of the row's k-th largest score (index.py:244-254, `.limit(top_k)`, exact).
+ * ld: even, >= xr_score_groupmax_ld(u, n, tile_stride); every one of those columns is written.       */
+int64_t xr_score_groupmax_ld(int64_t u, int64_t n, int64_t tile_stride);
 int xr_score_groupmax(const void* q, int64_t u, const void* catalog, int64_t n, int64_t dim,
-                      float* gmax, int64_t ld, void* stream);
+                      int64_t tile_stride, float* gmax, int64_t ld, void* stream);
+/* Threshold filter in the scoring epilogue: every (score, local row) with
+ * q_u . cat_c >= thresh[u * thresh_stride] is appended to query u's list (cand_scores / cand_rows,
+ * (U, cap), unordered).  cand_count[u] (zeroed by the caller) counts the survivors and keeps counting
+ * past cap: count > cap means the list is incomplete.  Nothing of size U x N reaches HBM.            */
+int xr_score_filter(const void* q, int64_t u, const void* catalog, int64_t n, int64_t dim,
+                    const float* thresh, int64_t thresh_stride, float* cand_scores, int32_t* cand_rows,
+                    int32_t* cand_count, int64_t cap, void* stream);
+/* Survivor lists -> the exact top-k (block per query): the k_sel best survivors under
+ * (score desc, row asc) are re-scored with the arithmetic of xr_logits_sampled, rows in query u's CSR
+ * exclusion list (GLOBAL ids; nullable) are dropped (the prefilter of index.py:239-247), the rest is
+ * ranked by (score desc, global id asc).  out_scores (U, k) fp32 / out_idx (U, k) int64 = local row +
+ * row_offset (-inf / -1 where fewer than k remain).  flags[0] |= 1 if a list overflowed (count > cap),
+ * |= 2 if a query has more than max_excl excluded ids: the result is then not guaranteed exact and the
+ * caller must take another path.  k_sel <= 1024.                                                    */
+int xr_filter_finalize(const void* q, int64_t u, const void* catalog, int64_t n, int64_t dim,
+                       const float* cand_scores, const int32_t* cand_rows, const int32_t* cand_count,
+                       int64_t cap, int64_t k_sel, int64_t k, int64_t row_offset,
+                       const int64_t* excl_offsets, const int64_t* excl_ids, int64_t max_excl,
+                       float* out_scores, int64_t* out_idx, int32_t* flags, void* stream);
 /* scores[u, j] = -inf where ids[u, j] lies outside [id_lo, id_hi) or in row u's CSR exclusion
  * list (nullable) — the prefilter of index.py:239-247 applied to re-scored candidate lists.     */
 int xr_mask_excluded_ids(float* scores, const int64_t* ids, int64_t u, int64_t c, int64_t ld,
                          int64_t id_lo, int64_t id_hi, const int64_t* excl_offsets,
                          const int64_t* excl_ids, void* stream);
-/* group ids (u, kg) chosen by xr_topk over the group maxima of xr_score_groupmax -> the 16 catalog
- * rows of each group: cols (u, kg*16) local rows for the re-score gather (0 where there is no such
- * row), ids (u, kg*16) global row ids = local + row_offset, -1 where there is no such row.     */
+/* group ids (u, kg) chosen by xr_topk over the group maxima of xr_score_groupmax (tile_stride 1) ->
+ * the 16 catalog rows of each group: cols (u, kg*16) local rows for the re-score gather (-1 where
+ * there is no such row), ids (u, kg*16) global row ids = local + row_offset, -1 where none.     */
 int xr_groups_to_rows(const int64_t* group_ids, int64_t u, int64_t kg, int64_t n, int64_t row_offset,
-                      int64_t layout, int64_t* cols, int64_t* ids, void* stream);
-/* layout of xr_score_groupmax's output for (u, n): 0 = natural (storage column g = catalog rows
- * [16 g, 16 g + 16)); > 0 = the CTA-pair kernel's layout with that stride (column
- * cg * 2 L + 2 t + h = rows [128 t + 32 cg + 16 h, +16)); pass it to xr_groups_to_rows.
- * xr_score_groupmax_ld = columns the output needs (all of them are written).                    */
-int xr_score_groupmax_layout(int64_t u, int64_t n);
-int64_t xr_score_groupmax_ld(int64_t u, int64_t n);
+                      int64_t* cols, int64_t* ids, void* stream);
 
-/* fused tcgen05 scoring + top-k over one catalog shard (bf16, dim 384): scores = Q . Cat^T on the
- * tensor cores, threshold-filtered selection in the epilogue, no (U,N) score matrix in HBM.
- * Same result as xr_scores + xr_mask_excluded + xr_topk.  Returns XR_E_UNSUPPORTED when the
- * kernel is not part of the build (xr_fused_available() bit 1).                                */
-size_t xr_score_topk_workspace_bytes(int64_t u, int64_t n, int64_t k);
-int xr_score_topk(const void* q, int64_t u, const void* catalog, int64_t n, int64_t dim,
-                  const float* q_inv_norm, const float* cat_inv_norm, int64_t k,
-                  int64_t col_offset, const int64_t* excl_offsets, const int64_t* excl_ids,
-                  float* out_scores, int64_t* out_idx, void* workspace, size_t workspace_bytes,
-                  void* stream);
+/* The whole local search of one catalog shard as ONE call (bf16, dim 384) — LanceIndex.search /
+ * FaissIndex.search, index.py:214-255 / 439-474, exact and batched over U queries:
+ *   sample group maxima (xr_score_groupmax, tile_stride s) -> the (k + max_excl + 28)-th largest per
+ *   query = threshold (xr_topk) -> xr_score_filter over the whole shard -> xr_filter_finalize.
+ * Same result as xr_scores + xr_mask_excluded + xr_topk unless flags[0] != 0 afterwards (see
+ * xr_filter_finalize; flags is NOT cleared by the call, so one word can watch many searches).
+ * q / catalog rows pre-normalised for the cosine metric.  excl_*: nullable CSR of GLOBAL ids, at most
+ * max_excl per query.  workspace: >= xr_score_topk_workspace_bytes(u, n, k, max_excl), 256-byte aligned. */
+size_t xr_score_topk_workspace_bytes(int64_t u, int64_t n, int64_t k, int64_t max_excl);
+int xr_score_topk(const void* q, int64_t u, const void* catalog, int64_t n, int64_t dim, int64_t k,
+                  int64_t row_offset, const int64_t* excl_offsets, const int64_t* excl_ids,
+                  int64_t max_excl, float* out_scores, int64_t* out_idx, int32_t* flags,
+                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- retrieval metrics -------------------------------------------------------------------------
  * compute_retrieval_metrics, metrics.py:62-79 (+ torchmetrics 1.9.0 functional definitions),

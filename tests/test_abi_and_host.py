@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared <= set(_native.PROTOTYPES), declared - set(_native.PROTOTYPES)
-    assert lib.xr_abi_version() == 1
+    assert lib.xr_abi_version() == 2
 
 
 def test_no_cpu_fallback():

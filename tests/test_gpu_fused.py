@@ -203,8 +203,9 @@ def test_groupmax_retrieval_random_cosine(xr):
 @pytest.mark.parametrize("u,n", [(129, 1000), (256, 12800), (300, 4097), (1000, 130), (513, 64), (260, 70000)])
 def test_groupmax_cta_pair_kernel_matches_reference(xr, u, n):
     """u > 128 runs on CTA pairs (tcgen05 cta_group::2, 256 queries per pair); group maxima must
-    equal the maxima of the fp32-accumulated scores and agree with the single-CTA variant.  The
-    pair kernel stores them as [column group][tile][half] (xr_score_groupmax_layout)."""
+    equal the maxima of the fp32-accumulated scores, in NATURAL order (column c = rows [16c, 16c+16),
+    so that top-k ties between groups resolve towards the lower row), and agree with the single-CTA
+    variant."""
     from xfmr_rec_b200 import _native as N, ops
 
     g = torch.Generator(device="cuda").manual_seed(u * 7 + n)
@@ -215,25 +216,106 @@ def test_groupmax_cta_pair_kernel_matches_reference(xr, u, n):
     want[:, :n] = q.float() @ cat.float().T
     want = want.view(u, ng, 16).amax(-1)                       # natural order: group g = rows [16g, 16g+16)
     lib = N.lib()
-    got_pair, layout = ops.score_groupmax(q, cat)
-    assert layout > 0 and got_pair.size(1) == 8 * layout
-    # storage slot c = cg * 2L + 2t + h  ->  group (128 t + 32 cg + 16 h) / 16
-    c = torch.arange(got_pair.size(1), device="cuda")
-    cg, rem = c // (2 * layout), c % (2 * layout)
-    grp = (rem // 2) * 8 + cg * 2 + (rem % 2)
-    live = grp < ng
-    natural = torch.full((u, ng), float("nan"), device="cuda")
-    natural[:, grp[live]] = got_pair[:, live]
-    torch.testing.assert_close(natural, want, rtol=2e-3, atol=2e-3)
-    assert bool((got_pair[:, ~live] == float("-inf")).all())   # slots past the catalog: never selected
+    got_pair = ops.score_groupmax(q, cat)
+    assert got_pair.size(1) >= ng
+    torch.testing.assert_close(got_pair[:, :ng], want, rtol=2e-3, atol=2e-3)
+    assert bool((got_pair[:, ng:] == float("-inf")).all())     # columns past the catalog: never selected
     lib.xr_fused_wait_stats(4, None)          # profiling switch: force the single-CTA kernel
     try:
-        got_single, layout1 = ops.score_groupmax(q, cat)
-        got_single = got_single[:, :ng].clone()
+        got_single = ops.score_groupmax(q, cat)[:, :ng].clone()
     finally:
         lib.xr_fused_wait_stats(0, None)
-    assert layout1 == 0
     torch.testing.assert_close(got_single, want, rtol=2e-3, atol=2e-3)
+    assert torch.equal(got_single, got_pair[:, :ng])           # same MMA arithmetic in both kernels
+
+
+@pytest.mark.parametrize("u,n,stride", [(5, 70000, 7), (64, 4097, 3), (200, 70000, 5), (300, 200000, 32)])
+def test_groupmax_sampled_tiles(xr, u, n, stride):
+    """tile_stride = s: only every s-th tile (64 rows for U <= 128, 128 above) is scored; column
+    (T/16) t + g holds rows [T t s + 16 g, +16).  The sample's maxima are maxima of real catalog rows,
+    which is all the threshold logic needs."""
+    from xfmr_rec_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(u + n)
+    q = torch.randn((u, 384), generator=g, device="cuda").bfloat16()
+    cat = torch.randn((n, 384), generator=g, device="cuda").bfloat16()
+    T = 128 if u > 128 else 64
+    nt = ((n + T - 1) // T + stride - 1) // stride
+    full = torch.full((u, (n + T * stride) // 16 * 16 + T * stride), float("-inf"), device="cuda")
+    full[:, :n] = q.float() @ cat.float().T
+    rows = (torch.arange(nt, device="cuda")[:, None] * (T * stride) + torch.arange(T, device="cuda")[None]).reshape(-1)
+    want = full[:, rows].view(u, nt * T // 16, 16).amax(-1)
+    got = ops.score_groupmax(q, cat, stride)
+    assert got.size(1) >= want.size(1)
+    torch.testing.assert_close(got[:, :want.size(1)], want, rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("u,n", [(3, 9000), (128, 30001), (129, 30001), (400, 12800)])
+def test_score_filter_survivors(xr, u, n):
+    """xr_score_filter: the survivor list of a query is EXACTLY the set of rows whose score is >= its
+    threshold (exact-arithmetic inputs), whatever order the scoring CTAs append them in; the
+    finalize step turns it into the oracle's top-k."""
+    from xfmr_rec_b200 import ops
+
+    rng = np.random.default_rng(u * 31 + n)
+    cat = rng.integers(-2, 3, size=(n, 384)).astype(np.float32)
+    qs = rng.integers(-2, 3, size=(u, 384)).astype(np.float32)
+    scores = qs @ cat.T
+    th = np.sort(scores, axis=1)[:, -150].copy()               # ~150+ survivors per query (ties included)
+    th[0] = -np.inf if n <= 16384 else th[0]                    # a query that keeps everything
+    th[-1] = np.inf                                             # and one that keeps nothing
+    cap = 16384
+    cs, cr, cnt = ops.score_filter(torch.from_numpy(qs).cuda().bfloat16(), torch.from_numpy(cat).cuda().bfloat16(),
+                                   torch.from_numpy(th).cuda(), cap)
+    cs, cr, cnt = cs.cpu().numpy(), cr.cpu().numpy(), cnt.cpu().numpy()
+    for r in range(u):
+        want = np.nonzero(scores[r] >= th[r])[0]
+        assert cnt[r] == len(want), (r, cnt[r], len(want))
+        order = np.argsort(cr[r, :cnt[r]])
+        assert np.array_equal(cr[r, :cnt[r]][order], want)
+        assert np.array_equal(cs[r, :cnt[r]][order], scores[r, want])
+    k = 20
+    q16, c16 = torch.from_numpy(qs).cuda().bfloat16(), torch.from_numpy(cat).cuda().bfloat16()
+    s, i, flags = ops.filter_finalize(q16, c16, torch.from_numpy(cs).cuda(), torch.from_numpy(cr).cuda(),
+                                      torch.from_numpy(cnt).cuda(), 60, k, row_offset=1000)
+    assert int(flags.item()) == 0
+    want_s, want_i = orc.exact_search(qs[:-1], cat, k, None, metric="dot")
+    assert np.array_equal(i.cpu().numpy()[:-1], want_i + 1000)
+    assert np.array_equal(s.cpu().numpy()[:-1], want_s)
+    assert bool((i[-1] == -1).all())
+
+
+@pytest.mark.parametrize("u", [64, 256])
+@pytest.mark.parametrize("n,case", [(20000, "identical"), (50000, "identical"), (120000, "dups")])
+def test_exact_index_ties_resolve_to_lowest_rows(xr, u, n, case):
+    """Heavy ties on the bf16 tensor-core path, U <= 128 (single-CTA kernel) and U > 128 (CTA pairs):
+    a catalog of identical rows, and 4,096 scattered duplicates of the best row.  The result must be
+    the LOWEST row ids (north_star: ties broken by lower item id).  20,000 identical rows all survive
+    the filter; 50,000 overflow the survivor lists and take the materialised path; both are exact."""
+    rng = np.random.default_rng(n + u)
+    k = 100
+    qs = rng.standard_normal((u, 384)).astype(np.float32)
+    if case == "identical":
+        cat = np.tile(rng.standard_normal((1, 384)).astype(np.float32), (n, 1))
+        want = np.tile(np.arange(k), (u, 1))
+    else:
+        cat = rng.standard_normal((n, 384)).astype(np.float32) * 0.1
+        dup_rows = np.sort(rng.choice(n, size=4096, replace=False))
+        cat[dup_rows] = qs.mean(0, keepdims=True) * 50.0        # far better than any random row, for every query
+        want = np.tile(dup_rows[:k], (u, 1))
+        ok = 50.0 * (qs @ qs.mean(0)) > 15.0                     # queries for which the duplicates are the best rows
+        assert ok.mean() > 0.5
+    idx = xr.index.ExactIndex(xr.index.ExactIndexConfig(index_metric="dot", dtype="bf16")).set_catalog(
+        torch.from_numpy(cat).cuda())
+    s, i = idx.search_batch(torch.from_numpy(qs).cuda(), None, k)
+    got = i.cpu().numpy()
+    if case == "identical":
+        assert np.array_equal(got, want)
+    else:
+        assert np.array_equal(got[ok], want[ok])
+    plan = idx.compile_search(u, k)
+    ps, pi = plan(torch.from_numpy(qs).cuda())
+    assert torch.equal(pi, i) and torch.equal(ps, s)
 
 
 def _cfg(ops, logits_bf16=False, **kw):

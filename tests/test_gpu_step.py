@@ -213,3 +213,30 @@ def test_pipelined_step_with_in_place_host_tokens_is_bitwise_identical(xr, tok_d
     assert torch.equal(l, want[1][0]) and torch.equal(g, want[1][1])
     l2, g2 = pipes[0].run()
     assert torch.equal(l2, want[1][0]) and torch.equal(g2, want[1][1])
+
+
+def test_step_orders_after_the_producer_stream(xr):
+    """Device-resident inputs that are still being WRITTEN on the caller's stream when step(...) is
+    called (the encoder output of the same training step): the copy stream must wait for the
+    producer.  A long-running kernel delays the write of the token embeddings; without the
+    ordering the step would read the stale (zero) buffer."""
+    b = orc.synth_batch(2500, 12, 80, dim=384, seed=11)
+    emb = xr.models.ItemEmbeddings(torch.from_numpy(b["table"]), add_padding_row=False).cuda()
+    loss_fn = xr.InfoNCELoss(xr.LossConfig())
+    want_loss, want_grad, _, _ = modular(xr, emb, loss_fn, b, torch.bfloat16)
+    step = xr.PoolLossStep(emb, loss_fn, 12, 80)
+    hist, pos, neg = (torch.from_numpy(b[k]).cuda() for k in
+                      ("history_item_idx", "pos_item_idx", "neg_item_idx"))
+    src = torch.from_numpy(b["token_embeddings"]).cuda().bfloat16()
+    burn = torch.randn(4096, 4096, device="cuda")
+    torch.cuda.synchronize()
+    for _ in range(3):
+        tok = torch.zeros_like(src)
+        for _ in range(40):            # ~tens of ms of queued work ahead of the write below
+            burn = (burn @ burn).clamp_(-1, 1)
+        tok.copy_(src)                 # "the encoder" finishes on the current stream
+        loss, dtok = step(tok, hist, pos, neg)
+        del tok                        # the allocator may recycle the block: record_stream guards it
+        torch.cuda.synchronize()
+        assert torch.equal(loss, want_loss), (float(loss), float(want_loss))
+        assert torch.equal(dtok.reshape(want_grad.shape), want_grad)

@@ -61,6 +61,7 @@ constexpr int KIND_DIAG = 100;      // extract q_i . pos_i from the diagonal of 
 constexpr int KIND_GMAX = 101;      // retrieval: max score of every 16-column group (no loss)
 constexpr int KIND_ALL_DOT = 102;   // forward of every dot-family loss + LogitsStatistics in one pass
 constexpr int KIND_ALL_COS = 103;   // forward of the cosine-family losses (+ statistics of the cosine logits)
+constexpr int KIND_FILTER = 104;    // retrieval: append every (score, row) with score >= thresh[u] (no loss)
 constexpr int NSCAL = 4;
 constexpr int NSCAL_ALL = 12;       // per (item, column group, row) scalars of the ALL kinds
 }  // namespace fk
@@ -84,6 +85,13 @@ struct FusedParams {
   float* part_all;     // [n_items][CG][128][NSCAL_ALL]            (KIND_ALL_*)
   float* gmax;         // [m][gmax_ld] group maxima                (KIND_GMAX)
   long long gmax_ld;
+  int tile_stride;     // KIND_GMAX: only every tile_stride-th 64-row catalog tile is scored (0 = 1)
+  const float* thresh; // KIND_FILTER: thresh[u * thresh_stride]
+  long long thresh_stride;
+  float* cand_scores;  // (m, cap)
+  int32_t* cand_rows;  // (m, cap) local catalog rows
+  int32_t* cand_count; // (m)
+  int cap;
   int rb_count;
   int* hang_flag;
   long long* dbg;      // STATS builds: per-tile timestamps of CTA 0 (profiling aid)
@@ -267,7 +275,9 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
     sh = FusedDyn{a.x, a.y, a.z, a.w, b.x, b.y, b.z, 0};
   }
   constexpr bool all_kind = (KIND == KIND_ALL_DOT || KIND == KIND_ALL_COS);
-  const bool grad = !diag && KIND != KIND_GMAX && !all_kind && p.with_grad;
+  constexpr bool retr = (KIND == KIND_GMAX || KIND == KIND_FILTER);   // retrieval scoring: no loss, no gradient
+  const int ts = (KIND == KIND_GMAX && p.tile_stride > 1) ? p.tile_stride : 1;
+  const bool grad = !diag && !retr && !all_kind && p.with_grad;
   // S buffers: ONE with the gradient pass (the other 64 columns hold the W double buffer), two without
   const int nsb_shift = grad ? 0 : 1;
 
@@ -304,7 +314,7 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
   // the tiles of an item are visited in a rotated order that depends on the row block, so the
   // CTAs sweeping the same candidate range do not hammer the same L2 lines in lockstep
   auto rot_tile = [&](int t0, int T, int rb, int tl) {
-    if (diag || KIND == KIND_GMAX) return t0 + tl;   // GMAX: row blocks share catalog tiles via L2
+    if (diag || retr) return t0 + tl;   // retrieval: row blocks share catalog tiles via L2
     const int r = (int)(((unsigned)rb * 29u) % (unsigned)T);
     int x = tl + r;
     if (x >= T) x -= T;
@@ -315,7 +325,7 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
       rb = item;
       t0 = 2 * rb;
       t1 = t0 + 2;
-    } else if (KIND == KIND_GMAX) {
+    } else if (retr) {
       // row block fastest: CTAs that share a catalog range run side by side, so the second
       // query block finds the catalog tiles in L2 instead of re-reading HBM
       rb = item % sh.rb_count;
@@ -355,8 +365,8 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
               mbar_arrive(bar_full(s));
             } else {
               mbar_expect_tx(bar_full(s), 2 * SUB_BYTES);
-              tma_load_2d(ring + s * 2 * SUB_BYTES, &tmap_b, bar_full(s), pr * 128, t * BN);
-              tma_load_2d(ring + s * 2 * SUB_BYTES + SUB_BYTES, &tmap_b, bar_full(s), pr * 128 + 64, t * BN);
+              tma_load_2d(ring + s * 2 * SUB_BYTES, &tmap_b, bar_full(s), pr * 128, t * ts * BN);
+              tma_load_2d(ring + s * 2 * SUB_BYTES + SUB_BYTES, &tmap_b, bar_full(s), pr * 128 + 64, t * ts * BN);
             }
           }
           __syncwarp();
@@ -492,7 +502,7 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int row = rb * BM + r_local;
       const bool row_ok = row < sh.m;
       float t = 0.f, tm = 0.f, zref2 = 0.f, t_eff = 0.f;
-      if (!diag && KIND != KIND_GMAX && row_ok) {
+      if (!diag && !retr && row_ok) {
         t = p.t[row];
         if (RBF) t = bf16_round(t);
         tm = __fmul_rn(t, 1.0f - p.margin);   // rounded on its own: see rowloss.cuh
@@ -502,6 +512,8 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
         zref2 = zr * kLog2e;
       }
       t_eff = p.mask_fn ? t : CUDART_INF_F;
+      if (KIND == KIND_FILTER)   // a row past m never passes; thresholds are group maxima (never NaN)
+        t_eff = row_ok ? __ldg(p.thresh + (long long)row * p.thresh_stride) : CUDART_INF_F;
       float cnt = 0.f, sum_a = 0.f, sum_w = 0.f, diag_val = 0.f;
       AllAcc acc;
       acc.reset();
@@ -539,12 +551,34 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
               if (c == j) diag_val = __uint_as_float(v[j]);
           }
         } else if (KIND == KIND_GMAX) {
-          const int ncols = sh.cn - rot_tile(t0, T, rb, tl) * BN - cg * 16;
+          // storage column 4 t + cg = catalog rows [64 t ts + 16 cg, +16): natural order for ts = 1
+          const int ncols = sh.cn - (t0 + tl) * ts * BN - cg * 16;
           float mx = -CUDART_INF_F;
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             if (j < ncols) mx = fmaxf(mx, __uint_as_float(v[j]));
-          if (row_ok) p.gmax[(long long)row * p.gmax_ld + (long long)rot_tile(t0, T, rb, tl) * CG + cg] = mx;
+          if (row_ok) p.gmax[(long long)row * p.gmax_ld + (long long)(t0 + tl) * CG + cg] = mx;
+        } else if (KIND == KIND_FILTER) {
+          // one test for the 16 scores: almost no lane-tile holds a survivor at the sample's threshold
+          const int c0 = (t0 + tl) * BN + cg * 16;
+          float mx = __uint_as_float(v[0]);
+#pragma unroll
+          for (int j = 1; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+          if (mx >= t_eff) {
+            float* cs = p.cand_scores + (long long)row * p.cap;
+            int32_t* cr = p.cand_rows + (long long)row * p.cap;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float sc = __uint_as_float(v[j]);
+              if (sc >= t_eff && c0 + j < sh.cn) {   // rows past cn are TMA zero fill, not catalog rows
+                const int slot = atomicAdd(p.cand_count + row, 1);
+                if (slot < p.cap) {
+                  cs[slot] = sc;
+                  cr[slot] = c0 + j;
+                }
+              }
+            }
+          }
         } else if (all_kind) {
           const int ncols = sh.cn - rot_tile(t0, T, rb, tl) * BN - cg * 16;
           if (ncols >= 16)
@@ -590,8 +624,8 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
       if (diag) {
         if (row_ok && (r_local & 63) >> 4 == cg) p.t_out[row] = diag_val;
-      } else if (KIND == KIND_GMAX) {
-        // nothing to flush: the group maxima were written tile by tile
+      } else if (retr) {
+        // nothing to flush: group maxima / survivors were written tile by tile
       } else if (all_kind) {
         if (row_ok) {
           float4* ds = reinterpret_cast<float4*>(
@@ -1103,12 +1137,12 @@ static int launch_fused(const CUtensorMap& tq, const CUtensorMap& tb, const Fuse
 using namespace xr;
 
 namespace xr {
-int launch_score_gmax2(const void* q, int64_t u, const void* catalog, int64_t n, float* gmax, int64_t ld,
-                       int* hang_flag, cudaStream_t s, int ablate);
-int gmax2_nt_pad(int64_t n);
+int launch_score_gmax2(const void* q, int64_t u, const void* catalog, int64_t n, int tile_stride, float* gmax,
+                       int64_t ld, int* hang_flag, cudaStream_t s, int ablate);
+int launch_score_filter2(const void* q, int64_t u, const void* catalog, int64_t n, const float* thresh,
+                         int64_t thresh_stride, float* cand_scores, int32_t* cand_rows, int32_t* cand_count,
+                         int64_t cap, int* hang_flag, cudaStream_t s);
 }
-static bool g_gmax_single = false;   // profiling aid: force the single-CTA retrieval kernel
-
 extern "C" int xr_fused_available(void) { return 3; }  // bit 0: fused loss, bit 1: fused retrieval scoring
 
 // workspace carve-up shared by xr_fused_pool_loss (exact shape) and xr_pool_step (bounds)
@@ -1629,64 +1663,107 @@ extern "C" int xr_pool_step_monitor(int64_t n_pos, int64_t dim, const xr_loss_co
 }
 
 // ---- retrieval: group maxima of Q . Cat^T on the tensor cores -----------------------------------
-// gmax[u, g] = max_{c in [16g, 16g+16)} q_u . cat_c   (columns >= n give -inf).  The k-th largest
-// group maximum of a row is a lower bound of its k-th largest score, and every score above it
-// lives in a group whose maximum is above it: the exact top-k only needs the top groups to be
-// re-scored (index.py:244-254 semantics, exact).  The (U, N) score matrix never reaches HBM.
-// Layout of the group maxima: 0 = natural (storage column g holds catalog rows [16 g, 16 g + 16)),
-// otherwise the pair kernel's layout with stride nt_pad: storage column c = cg * 2 nt_pad + 2 t + h
-// holds catalog rows [128 t + 32 cg + 16 h, +16).  xr_groups_to_rows takes the same number.
-extern "C" int xr_score_groupmax_layout(int64_t u, int64_t n) {
-  return (u > fk::BM && !g_gmax_single) ? gmax2_nt_pad(n) : 0;
+// gmax[u, g] = max_{c in group g} q_u . cat_c   (rows >= n give -inf).  The k-th largest group maximum
+// of a row is a lower bound of its k-th largest score (index.py:244-254 semantics, exact).  With
+// tile_stride = s > 1 only every s-th tile of T rows is scored (T = 128 for u > 128, the CTA-pair kernel;
+// 64 otherwise): the SAMPLE that gives xr_score_filter its thresholds.  Storage column
+// (T / 16) * t + g = catalog rows [T * t * s + 16 g, +16): natural order [16 c, 16 c + 16) for s = 1.
+static bool g_gmax_single = false;   // profiling aid: force the single-CTA retrieval kernel
+static int retr_tile_rows(int64_t u) { return (u > fk::BM && !g_gmax_single) ? 128 : fk::BN; }
+
+extern "C" int64_t xr_score_groupmax_ld(int64_t u, int64_t n, int64_t tile_stride) {
+  if (tile_stride < 1) tile_stride = 1;
+  const int64_t T = retr_tile_rows(u);
+  const int64_t nt = ((n + T - 1) / T + tile_stride - 1) / tile_stride;
+  return nt * (T / 16);
 }
-extern "C" int64_t xr_score_groupmax_ld(int64_t u, int64_t n) {
-  const int nt_pad = xr_score_groupmax_layout(u, n);
-  return nt_pad ? 8 * (int64_t)nt_pad : 4 * ((n + fk::BN - 1) / fk::BN);
+
+static int* retr_hang_flag() {   // device word for the bounded-wait diagnostics
+  static int* hang = nullptr;
+  if (!hang) {
+    if (cudaMalloc(&hang, 256) != cudaSuccess) return nullptr;
+    cudaMemset(hang, 0, 256);
+  }
+  return hang;
+}
+
+static int check_retr_args(const char* who, const void* q, int64_t u, const void* catalog, int64_t n,
+                           int64_t dim) {
+  XR_CHECK_ARG(q && catalog, "%s: null pointer", who);
+  XR_CHECK_ARG(dim == fk::D, "%s: this build is specialised for dim = %d", who, fk::D);
+  XR_CHECK_ARG(u > 0 && n > 0 && u < (1ll << 30) && n < (1ll << 31) - 4096, "%s: bad sizes", who);
+  XR_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)catalog % 16 == 0),
+               "%s: operands must be 16-byte aligned", who);
+  return check_fused_device(who);
 }
 
 extern "C" int xr_score_groupmax(const void* q, int64_t u, const void* catalog, int64_t n,
-                                 int64_t dim, float* gmax, int64_t ld, void* stream) {
-  XR_CHECK_ARG(q && catalog && gmax, "xr_score_groupmax: null pointer");
-  XR_CHECK_ARG(dim == fk::D, "xr_score_groupmax: this build is specialised for dim = %d", fk::D);
-  XR_CHECK_ARG(u > 0 && n > 0 && u < (1ll << 30) && n < (1ll << 31), "xr_score_groupmax: bad sizes");
-  const int64_t nt = (n + fk::BN - 1) / fk::BN;
-  XR_CHECK_ARG(ld >= nt * fk::CG, "xr_score_groupmax: ld must be >= 4 * ceil(n / 64)");
-  XR_CHECK_ARG(u <= fk::BM || g_gmax_single ||
-                   (ld >= 8 * gmax2_nt_pad(n) && ld % 4 == 0 && (uintptr_t)gmax % 16 == 0),
-               "xr_score_groupmax: for u > 128, ld must be a multiple of 4 and >= xr_score_groupmax_ld(u, n), "
-               "gmax 16-byte aligned");
-  XR_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)catalog % 16 == 0),
-               "xr_score_groupmax: operands must be 16-byte aligned");
-  int dev = 0, major = 0;
-  XR_CUDA(cudaGetDevice(&dev));
-  XR_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
-  if (major != 10) {
-    set_error("xr_score_groupmax: needs an sm_100 device (tcgen05/TMEM)");
-    return XR_E_UNSUPPORTED;
-  }
-  cudaStream_t s = as_stream(stream);
-  const int n_sm = sm_count();
-  const FusedPlan pl = make_gmax_plan(u, n, n_sm);
-  CUtensorMap tq, tc;
+                                 int64_t dim, int64_t tile_stride, float* gmax, int64_t ld, void* stream) {
   int rc;
-  if ((rc = make_tmap_bf16_rows(&tq, q, u, dim, dim, fk::BM))) return rc;
-  if ((rc = make_tmap_bf16_rows(&tc, catalog, n, dim, dim, fk::BN))) return rc;
-  FusedParams p{};
-  p.m = (int)u; p.cn = (int)n; p.nt_count = pl.nt; p.spl = pl.spl; p.tiles_per_split = pl.tps;
-  p.n_items = pl.n_items; p.rb_count = pl.rb; p.gmax = gmax; p.gmax_ld = ld;
-  static int* hang = nullptr;   // device word for the bounded-wait diagnostics
-  if (!hang) {
-    XR_CUDA(cudaMalloc(&hang, 256));
-    XR_CUDA(cudaMemset(hang, 0, 256));
-  }
-  p.hang_flag = hang;
-  const int grid = pl.n_items < n_sm ? pl.n_items : n_sm;
+  if ((rc = check_retr_args("xr_score_groupmax", q, u, catalog, n, dim))) return rc;
+  XR_CHECK_ARG(gmax && tile_stride >= 1 && tile_stride <= 4096, "xr_score_groupmax: bad arguments");
+  XR_CHECK_ARG(ld >= xr_score_groupmax_ld(u, n, tile_stride) && ld % 2 == 0 && (uintptr_t)gmax % 8 == 0,
+               "xr_score_groupmax: ld must be even and >= xr_score_groupmax_ld(u, n, tile_stride), gmax 8-byte aligned");
+  cudaStream_t s = as_stream(stream);
+  int* hang = retr_hang_flag();
+  XR_CHECK_ARG(hang, "xr_score_groupmax: out of device memory");
   const bool prof = g_prof_on && g_prof_n < kProfRing;
   if (prof) cudaEventRecord(g_prof_ev[g_prof_n][0], s);
-  if (u > fk::BM && !g_gmax_single)   // CTA pairs: 256 queries per pair, half the catalog bytes per SM
-    rc = launch_score_gmax2(q, u, catalog, n, gmax, ld, hang, s, g_ablate);
-  else
-    rc = launch_fused1<fk::KIND_GMAX, false>(tq, tc, p, grid, s);
+  if (retr_tile_rows(u) == 128) {   // CTA pairs: 256 queries per pair, half the catalog bytes per SM
+    rc = launch_score_gmax2(q, u, catalog, n, (int)tile_stride, gmax, ld, hang, s, g_ablate);
+  } else {
+    const int n_sm = sm_count();
+    const int64_t nt = ((n + fk::BN - 1) / fk::BN + tile_stride - 1) / tile_stride;   // sampled tiles
+    const FusedPlan pl = make_gmax_plan(u, nt * fk::BN, n_sm);
+    CUtensorMap tq, tc;
+    if ((rc = make_tmap_bf16_rows(&tq, q, u, dim, dim, fk::BM))) return rc;
+    if ((rc = make_tmap_bf16_rows(&tc, catalog, n, dim, dim, fk::BN))) return rc;
+    FusedParams p{};
+    p.m = (int)u; p.cn = (int)n; p.nt_count = pl.nt; p.spl = pl.spl; p.tiles_per_split = pl.tps;
+    p.n_items = pl.n_items; p.rb_count = pl.rb; p.gmax = gmax; p.gmax_ld = ld; p.tile_stride = (int)tile_stride;
+    p.hang_flag = hang;
+    rc = launch_fused1<fk::KIND_GMAX, false>(tq, tc, p, pl.n_items < n_sm ? pl.n_items : n_sm, s);
+  }
+  if (prof) cudaEventRecord(g_prof_ev[g_prof_n++][1], s);
+  return rc;
+}
+
+// ---- retrieval: threshold filter in the scoring epilogue ---------------------------------------------
+// Every (score, local row) with score >= thresh[u * thresh_stride] is appended to query u's list
+// (cand_scores / cand_rows, `cap` slots per query, unordered); cand_count[u] (zeroed by the caller) counts
+// the survivors and keeps counting past `cap`, which is how the consumer detects an overflow.  With
+// thresholds from a sample (xr_score_groupmax with tile_stride = s: the (k+E)-th largest group maximum of
+// the sample is <= the (k+E)-th largest score of the catalog) about (k+E) * s rows survive per query, so
+// nothing of size U x N ever reaches HBM: the catalog is read once and ~KBs per query are written.
+extern "C" int xr_score_filter(const void* q, int64_t u, const void* catalog, int64_t n, int64_t dim,
+                               const float* thresh, int64_t thresh_stride, float* cand_scores,
+                               int32_t* cand_rows, int32_t* cand_count, int64_t cap, void* stream) {
+  int rc;
+  if ((rc = check_retr_args("xr_score_filter", q, u, catalog, n, dim))) return rc;
+  XR_CHECK_ARG(thresh && cand_scores && cand_rows && cand_count && cap >= 1 && cap < (1ll << 30) &&
+                   thresh_stride >= 0,
+               "xr_score_filter: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  int* hang = retr_hang_flag();
+  XR_CHECK_ARG(hang, "xr_score_filter: out of device memory");
+  const bool prof = g_prof_on && g_prof_n < kProfRing;
+  if (prof) cudaEventRecord(g_prof_ev[g_prof_n][0], s);
+  if (retr_tile_rows(u) == 128) {
+    rc = launch_score_filter2(q, u, catalog, n, thresh, thresh_stride, cand_scores, cand_rows, cand_count,
+                              cap, hang, s);
+  } else {
+    const int n_sm = sm_count();
+    const FusedPlan pl = make_gmax_plan(u, n, n_sm);
+    CUtensorMap tq, tc;
+    if ((rc = make_tmap_bf16_rows(&tq, q, u, dim, dim, fk::BM))) return rc;
+    if ((rc = make_tmap_bf16_rows(&tc, catalog, n, dim, dim, fk::BN))) return rc;
+    FusedParams p{};
+    p.m = (int)u; p.cn = (int)n; p.nt_count = pl.nt; p.spl = pl.spl; p.tiles_per_split = pl.tps;
+    p.n_items = pl.n_items; p.rb_count = pl.rb; p.hang_flag = hang;
+    p.thresh = thresh; p.thresh_stride = thresh_stride; p.cand_scores = cand_scores;
+    p.cand_rows = cand_rows; p.cand_count = cand_count; p.cap = (int)cap;
+    rc = launch_fused1<fk::KIND_FILTER, false>(tq, tc, p, pl.n_items < n_sm ? pl.n_items : n_sm, s);
+  }
   if (prof) cudaEventRecord(g_prof_ev[g_prof_n++][1], s);
   return rc;
 }
@@ -1735,13 +1812,3 @@ extern "C" int xr_fused_profile_read(float* ms_out_host, int max_n) {
   return n;
 }
 
-// score + top-k fusion is provided by score_topk_sm100.cu when present
-#ifndef XR_HAVE_SCORE_TOPK
-extern "C" size_t xr_score_topk_workspace_bytes(int64_t, int64_t, int64_t) { return 0; }
-extern "C" int xr_score_topk(const void*, int64_t, const void*, int64_t, int64_t, const float*,
-                             const float*, int64_t, int64_t, const int64_t*, const int64_t*, float*,
-                             int64_t*, void*, size_t, void*) {
-  xr::set_error("xr_score_topk: not compiled into this build");
-  return XR_E_UNSUPPORTED;
-}
-#endif

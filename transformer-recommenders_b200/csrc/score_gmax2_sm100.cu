@@ -1,6 +1,10 @@
-// Retrieval scoring on CTA PAIRS (tcgen05 cta_group::2): gmax[u, g] = max over the 16 catalog rows
-// of group g of q_u . cat_c — the exact pre-filter of the full-catalog top-k (index.py:244-254
-// semantics, see xr_score_groupmax in fused_loss_sm100.cu for the single-CTA version).
+// Retrieval scoring on CTA PAIRS (tcgen05 cta_group::2), two epilogues over the same MMA pipeline
+// (index.py:244-254 semantics, exact; fused_loss_sm100.cu holds the single-CTA versions for U <= 128):
+//   MODE_GMAX    gmax[u, g] = max over the 16 catalog rows of group g of q_u . cat_c, optionally over
+//                every `tile_stride`-th 128-row tile only (the SAMPLE whose (k+E)-th largest maximum is
+//                a lower bound of the (k+E)-th largest score of the whole catalog);
+//   MODE_FILTER  every (score, row) with score >= thresh[u] is appended to query u's candidate list:
+//                the (U, N) score matrix never reaches HBM, and neither does anything of size U x N / 16.
 //
 // Why pairs: shared-memory ingest by TMA is ~35 B/cycle/SM whatever the ring depth or multicast
 // (profiles/microbench/tma_stream.cu), and a 128-query CTA needs 48 KB per 64 candidates = 1,400
@@ -39,10 +43,18 @@ constexpr int THREADS = 128 + EPI_WARPS * 32;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // shared::cluster address of the pair's EVEN CTA
 }  // namespace g2
 
+constexpr int MODE_GMAX = 0, MODE_FILTER = 1;
+
 struct Gmax2Params {
-  int u, n, nt_count, nt_pad, spl, tiles_per_split, n_items, qb_count;
-  float* gmax;
+  int u, n, nt_count, tile_stride, spl, tiles_per_split, n_items, qb_count;
+  float* gmax;           // MODE_GMAX: (u, gmax_ld), natural order: column 8 t + g = rows [128 t s + 16 g, +16)
   long long gmax_ld;
+  const float* thresh;   // MODE_FILTER: thresh[u * thresh_stride]
+  long long thresh_stride;
+  float* cand_scores;    // (u, cap)
+  int32_t* cand_rows;    // (u, cap) local catalog rows
+  int32_t* cand_count;   // (u): appended so far; may run past cap (overflow is detected by the consumer)
+  int cap;
   int* hang_flag;
   int ablate;   // DBG instantiation only: 1 skip catalog TMA, 2 skip epilogue TMEM loads, 4 skip gmax stores, 8 skip MMAs
 };
@@ -100,7 +112,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
                : "memory");
 }
 
-template <bool DBG>
+template <int MODE, bool DBG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::THREADS, 1)
 score_gmax2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                    const Gmax2Params p) {
@@ -178,7 +190,7 @@ score_gmax2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
               if (leader) mbar_arrive(bar_full(s));
             } else {
               if (leader) mbar_expect_tx(bar_full(s), 2 * 2 * SUB_BYTES);
-              const int row0 = t * BN + (int)rank * BNH;
+              const int row0 = t * p.tile_stride * BN + (int)rank * BNH;
               tma_load_2d_2sm(ring + s * 2 * SUB_BYTES, &tmap_c, bar_full(s), pr * 128, row0);
               tma_load_2d_2sm(ring + s * 2 * SUB_BYTES + SUB_BYTES, &tmap_c, bar_full(s), pr * 128 + 64, row0);
             }
@@ -249,8 +261,10 @@ score_gmax2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       item_tiles(item, qb, t0, t1);
       const int row = qb * 2 * BM + (int)rank * BM + r_local;
       const bool row_ok = row < p.u;
-      float* out_row = p.gmax + (long long)row * p.gmax_ld;
-      float buf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      float* out_row = MODE == MODE_GMAX ? p.gmax + (long long)row * p.gmax_ld : nullptr;
+      // a row past u never passes the filter; NaN thresholds cannot occur (they are group maxima)
+      const float th = (MODE == MODE_FILTER && row_ok) ? __ldg(p.thresh + (long long)row * p.thresh_stride)
+                                                       : CUDART_INF_F;
       for (int t = t0; t < t1; ++t, ++tile) {
         const int sb = tile % NSB;
         mbar_wait(bar_s_full(sb), (tile / NSB) & 1, p.hang_flag, 8);
@@ -266,36 +280,40 @@ score_gmax2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(bar_s_free(sb));   // the logits are in registers
-        const int c0 = t * BN + cg * 32;                       // first catalog row of this column group
-        float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F;
+        const int c0 = t * p.tile_stride * BN + cg * 32;       // first catalog row of this column group
+        if (MODE == MODE_GMAX) {
+          float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (c0 + j < p.n) m0 = fmaxf(m0, __uint_as_float(v[j]));
-          if (c0 + 16 + j < p.n) m1 = fmaxf(m1, __uint_as_float(v[16 + j]));
-        }
-        // "pair layout": row u stores its maxima as [column group cg][tile t][half h], so the two
-        // values a lane produces per tile are contiguous ACROSS tiles: four tiles are buffered and
-        // leave as two 16-byte stores (whole 32-byte sectors) instead of four scattered 8-byte ones
-        const int k = (t - t0) & 3;
-        if (k == 0) { buf[0] = m0; buf[1] = m1; }
-        else if (k == 1) { buf[2] = m0; buf[3] = m1; }
-        else if (k == 2) { buf[4] = m0; buf[5] = m1; }
-        else { buf[6] = m0; buf[7] = m1; }
-        const bool last = t == t1 - 1;
-        if ((k == 3 || last) && row_ok && !(DBG && (p.ablate & 4))) {
-          float* dst = out_row + (long long)cg * (2 * p.nt_pad) + 2 * (t - k);   // t0 is a multiple of 4
-          if (k == 3) {
-            *reinterpret_cast<float4*>(dst) = make_float4(buf[0], buf[1], buf[2], buf[3]);
-            *reinterpret_cast<float4*>(dst + 4) = make_float4(buf[4], buf[5], buf[6], buf[7]);
-          } else {
-            *reinterpret_cast<float2*>(dst) = make_float2(buf[0], buf[1]);
-            if (k >= 1) *reinterpret_cast<float2*>(dst + 2) = make_float2(buf[2], buf[3]);
-            if (k >= 2) *reinterpret_cast<float2*>(dst + 4) = make_float2(buf[4], buf[5]);
+          for (int j = 0; j < 16; ++j) {
+            if (c0 + j < p.n) m0 = fmaxf(m0, __uint_as_float(v[j]));
+            if (c0 + 16 + j < p.n) m1 = fmaxf(m1, __uint_as_float(v[16 + j]));
           }
-          if (last && t == p.nt_count - 1)   // padding tiles of the layout: never selected
-            for (int tp = p.nt_count; tp < p.nt_pad; ++tp)
-              *reinterpret_cast<float2*>(out_row + (long long)cg * (2 * p.nt_pad) + 2 * tp) =
-                  make_float2(-CUDART_INF_F, -CUDART_INF_F);
+          // natural order: storage column 8 t + 2 cg + h holds the rows [c0 + 16 h, +16), so that the
+          // (maximum desc, column asc) order of xr_topk is (maximum desc, first row asc); the four
+          // column-group warps of a row fill one 32-byte sector per tile between them
+          if (row_ok && !(DBG && (p.ablate & 4)))
+            *reinterpret_cast<float2*>(out_row + 8ll * t + 2 * cg) = make_float2(m0, m1);
+        } else {
+          // one test for the 32 scores keeps the common case (no survivor: ~99 % of the lane-tiles
+          // at the thresholds the sample gives) at one instruction per score
+          float mx = __uint_as_float(v[0]);
+#pragma unroll
+          for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+          if (mx >= th) {
+            float* cs = p.cand_scores + (long long)row * p.cap;
+            int32_t* cr = p.cand_rows + (long long)row * p.cap;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float sc = __uint_as_float(v[j]);
+              if (sc >= th && c0 + j < p.n) {   // rows past n are TMA zero fill, not catalog rows
+                const int slot = atomicAdd(p.cand_count + row, 1);
+                if (slot < p.cap) {
+                  cs[slot] = sc;
+                  cr[slot] = c0 + j;
+                }
+              }
+            }
+          }
         }
       }
     }
@@ -311,20 +329,19 @@ score_gmax2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 int make_tmap_bf16_rows(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld_elems,
                         int box_rows);
 
-// tiles of 128 catalog rows, padded to a multiple of 2: the layout stride 2 * nt_pad stays 16-byte aligned
-int gmax2_nt_pad(int64_t n) { return (int)(((n + g2::BN - 1) / g2::BN + 1) / 2 * 2); }
+// sampled tiles of 128 catalog rows: every tile_stride-th one
+int gmax2_tiles(int64_t n, int tile_stride) {
+  const int64_t nt = (n + g2::BN - 1) / g2::BN;
+  return (int)((nt + tile_stride - 1) / tile_stride);
+}
 
-// host: called by xr_score_groupmax for u > 128
-int launch_score_gmax2(const void* q, int64_t u, const void* catalog, int64_t n, float* gmax, int64_t ld,
-                       int* hang_flag, cudaStream_t s, int ablate) {
+// work items of the CTA pairs: query blocks x splits of the (sampled) tiles, whole waves of pairs
+static void plan_gmax2(Gmax2Params& p, int64_t u, int64_t n, int tile_stride, int n_clusters) {
   using namespace g2;
-  const int n_sm = sm_count();
-  const int n_clusters = n_sm / 2;
-  Gmax2Params p{};
   p.u = (int)u; p.n = (int)n;
+  p.tile_stride = tile_stride;
   p.qb_count = (int)((u + 2 * BM - 1) / (2 * BM));
-  p.nt_count = (int)((n + BN - 1) / BN);
-  // splits of the catalog so that qb_count x splits fills whole waves of CTA pairs
+  p.nt_count = gmax2_tiles(n, tile_stride);
   int best_spl = 1;
   long long best = -1;
   const int max_spl = p.nt_count < 4096 ? p.nt_count : 4096;
@@ -341,27 +358,52 @@ int launch_score_gmax2(const void* q, int64_t u, const void* catalog, int64_t n,
     if (items > 8LL * n_clusters) break;
   }
   p.tiles_per_split = (p.nt_count + best_spl - 1) / best_spl;
-  p.tiles_per_split = (p.tiles_per_split + 3) / 4 * 4;   // items start on a multiple of 4 tiles (16-byte stores)
   p.spl = (p.nt_count + p.tiles_per_split - 1) / p.tiles_per_split;
-  p.nt_pad = gmax2_nt_pad(n);
   p.n_items = p.qb_count * p.spl;
-  p.gmax = gmax; p.gmax_ld = ld; p.hang_flag = hang_flag;
+}
+
+template <int MODE>
+static int launch_gmax2_mode(const void* q, int64_t u, const void* catalog, int64_t n, Gmax2Params& p,
+                             cudaStream_t s, int ablate) {
+  using namespace g2;
+  const int n_clusters = sm_count() / 2;
   CUtensorMap tq, tc;
   int rc;
   if ((rc = make_tmap_bf16_rows(&tq, q, u, D, D, BM))) return rc;
   if ((rc = make_tmap_bf16_rows(&tc, catalog, n, D, D, BNH))) return rc;
   static bool configured = false;
   if (!configured) {
-    XR_CUDA(cudaFuncSetAttribute(score_gmax2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    XR_CUDA(cudaFuncSetAttribute(score_gmax2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    XR_CUDA(cudaFuncSetAttribute(score_gmax2_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    XR_CUDA(cudaFuncSetAttribute(score_gmax2_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
-  int pairs = p.n_items < n_clusters ? p.n_items : n_clusters;
+  const int pairs = p.n_items < n_clusters ? p.n_items : n_clusters;
   p.ablate = ablate;
-  if (ablate) score_gmax2_kernel<true><<<2 * pairs, THREADS, SMEM_BYTES, s>>>(tq, tc, p);   // timing experiments
-  else score_gmax2_kernel<false><<<2 * pairs, THREADS, SMEM_BYTES, s>>>(tq, tc, p);
+  if (ablate) score_gmax2_kernel<MODE, true><<<2 * pairs, THREADS, SMEM_BYTES, s>>>(tq, tc, p);   // timing experiments
+  else score_gmax2_kernel<MODE, false><<<2 * pairs, THREADS, SMEM_BYTES, s>>>(tq, tc, p);
   XR_LAUNCH_CHECK("score_gmax2_kernel");
   return XR_OK;
+}
+
+// host: called by xr_score_groupmax for u > 128
+int launch_score_gmax2(const void* q, int64_t u, const void* catalog, int64_t n, int tile_stride, float* gmax,
+                       int64_t ld, int* hang_flag, cudaStream_t s, int ablate) {
+  Gmax2Params p{};
+  plan_gmax2(p, u, n, tile_stride, sm_count() / 2);
+  p.gmax = gmax; p.gmax_ld = ld; p.hang_flag = hang_flag;
+  return launch_gmax2_mode<MODE_GMAX>(q, u, catalog, n, p, s, ablate);
+}
+
+// host: called by xr_score_filter for u > 128
+int launch_score_filter2(const void* q, int64_t u, const void* catalog, int64_t n, const float* thresh,
+                         int64_t thresh_stride, float* cand_scores, int32_t* cand_rows, int32_t* cand_count,
+                         int64_t cap, int* hang_flag, cudaStream_t s) {
+  Gmax2Params p{};
+  plan_gmax2(p, u, n, 1, sm_count() / 2);
+  p.thresh = thresh; p.thresh_stride = thresh_stride;
+  p.cand_scores = cand_scores; p.cand_rows = cand_rows; p.cand_count = cand_count; p.cap = (int)cap;
+  p.hang_flag = hang_flag;
+  return launch_gmax2_mode<MODE_FILTER>(q, u, catalog, n, p, s, 0);
 }
 
 }  // namespace xr

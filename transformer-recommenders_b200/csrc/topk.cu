@@ -12,10 +12,12 @@
 // threshold.  Chunks of a row are merged by the same kernel running over the partial keys.
 // Selection on a strict total order makes single-GPU, chunked and sharded results identical.
 #include "common.cuh"
+#include "rowdot.cuh"
 
 namespace xr {
 
 constexpr int TK_THREADS = 256;
+static_assert(TK_THREADS == ROW_THREADS, "the finalize kernel runs the gather-dot with the top-k block shape");
 constexpr int TK_CAP = 2048;        // candidate buffer (keys)
 constexpr int TK_PER_ITER = 1024;   // worst-case appends per iteration
 constexpr int TK_MAX_K = TK_CAP - TK_PER_ITER;
@@ -417,20 +419,93 @@ __global__ void mask_excluded_ids_kernel(float* __restrict__ scores, const int64
 // group ids (U, kg) from the top-k over the group maxima -> the 16 catalog rows of every group:
 // local row numbers for the re-score gather (clamped into [0, n)) and global ids (-1 = no such row)
 __global__ void groups_to_rows_kernel(const int64_t* __restrict__ gi, int64_t total, int64_t n,
-                                      int64_t row_offset, int64_t nt_pad, int64_t* __restrict__ cols,
+                                      int64_t row_offset, int64_t* __restrict__ cols,
                                       int64_t* __restrict__ ids) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t g = gi[e >> 4];
-    int64_t first = g * 16;                       // natural layout
-    if (nt_pad > 0 && g >= 0) {                   // pair layout: [column group][tile][half]
-      const int64_t cg = g / (2 * nt_pad), rem = g - cg * 2 * nt_pad;
-      first = (rem >> 1) * 128 + cg * 32 + (rem & 1) * 16;
-    }
-    const int64_t c = first + (e & 15);
+    const int64_t c = g * 16 + (e & 15);          // group g = catalog rows [16 g, 16 g + 16)
     const bool ok = g >= 0 && c < n;
     cols[e] = ok ? c : -1;                        // -1: the re-score gather reads nothing for it
     ids[e] = ok ? c + row_offset : -1;
+  }
+}
+
+// ---- survivors of the scoring filter -> exact top-k (block per query) --------------------------------
+// 1. the k_sel best survivors under (tensor-core score desc, row asc) -- a total order, so the choice
+//    does not depend on the order the scoring CTAs appended them in; 2. their scores recomputed with the
+//    gather-dot arithmetic of xr_logits_sampled (the arithmetic every other search path reports);
+//    3. the query's exclusion list dropped (index.py:239-247); 4. ranked by (score desc, global id asc).
+__global__ void __launch_bounds__(TK_THREADS)
+filter_finalize_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ cat, int64_t n,
+                       const float* __restrict__ cand_scores, const int32_t* __restrict__ cand_rows,
+                       const int32_t* __restrict__ cand_count, int64_t cap, int k_sel, int k,
+                       int64_t row_offset, const int64_t* __restrict__ offs,
+                       const int64_t* __restrict__ excl, int64_t max_excl, float* __restrict__ out_scores,
+                       int64_t* __restrict__ out_idx, int32_t* __restrict__ flags) {
+  __shared__ uint64_t s_keys[TK_CAP];
+  __shared__ int s_count;
+  __shared__ uint64_t s_tau;
+  __shared__ int64_t s_rows[TK_MAX_K];
+  __shared__ float s_sc[TK_MAX_K];
+  TopkState st{s_keys, &s_count, &s_tau};
+  const int64_t u = blockIdx.x;
+  const int64_t cnt_raw = cand_count[u];
+  const int64_t cnt = cnt_raw < cap ? cnt_raw : cap;
+  if (threadIdx.x == 0) {
+    s_count = 0;
+    s_tau = 0ull;
+    int bad = cnt_raw > cap ? 1 : 0;                                   // survivors were dropped
+    if (offs && offs[u + 1] - offs[u] > max_excl) bad |= 2;            // thresholds assumed fewer exclusions
+    if (bad) atomicOr(flags, bad);
+  }
+  __syncthreads();
+  const float* cs = cand_scores + u * cap;
+  const int32_t* cr = cand_rows + u * cap;
+  const int64_t iters = (cnt + TK_PER_ITER - 1) / TK_PER_ITER;
+  for (int64_t it = 0; it < iters; ++it) {
+    if (*st.count > TK_CAP - TK_PER_ITER) compact_select(st, k_sel);
+    const uint64_t tau = *st.tau;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int64_t e = it * TK_PER_ITER + r * TK_THREADS + threadIdx.x;
+      const bool in = e < cnt;
+      const uint64_t key = in ? make_key(__ldcg(cs + e), (uint32_t)__ldcg(cr + e)) : 0ull;
+      offer(st, in && key > tau, key);
+    }
+    __syncthreads();
+  }
+  compact_select(st, k_sel);
+  compact(st, k_sel);   // s_keys[0, c) in descending key order
+  const int c = s_count < k_sel ? s_count : k_sel;
+  for (int i = threadIdx.x; i < c; i += TK_THREADS) s_rows[i] = (int64_t)(0xFFFFFFFFu - (uint32_t)s_keys[i]);
+  __syncthreads();
+  sampled_logits384_row<__nv_bfloat16>(q + u * FD, cat, s_rows, n, c, 1.f, nullptr, s_sc);
+  __syncthreads();
+  const int64_t x0 = offs ? offs[u] : 0, x1 = offs ? offs[u + 1] : 0;
+  int n2 = 2;
+  while (n2 < c) n2 <<= 1;
+  for (int i = threadIdx.x; i < n2; i += TK_THREADS) {
+    uint64_t key = 0ull;
+    if (i < c) {
+      const int64_t id = s_rows[i] + row_offset;
+      bool dead = false;
+      for (int64_t x = x0; x < x1; ++x) dead |= (excl[x] == id);
+      if (!dead) key = make_key(s_sc[i], (uint32_t)id);
+    }
+    s_keys[i] = key;
+  }
+  __syncthreads();
+  bitonic_desc(s_keys, n2);
+  for (int i = threadIdx.x; i < k; i += TK_THREADS) {
+    const uint64_t key = i < n2 ? s_keys[i] : 0ull;
+    if (key == 0ull) {
+      out_scores[u * k + i] = -CUDART_INF_F;
+      out_idx[u * k + i] = -1;
+    } else {
+      out_scores[u * k + i] = key_float((uint32_t)(key >> 32));
+      out_idx[u * k + i] = (int64_t)(0xFFFFFFFFu - (uint32_t)key);
+    }
   }
 }
 
@@ -657,17 +732,122 @@ extern "C" int xr_mask_excluded_ids(float* scores, const int64_t* ids, int64_t u
 }
 
 extern "C" int xr_groups_to_rows(const int64_t* group_ids, int64_t u, int64_t kg, int64_t n,
-                                 int64_t row_offset, int64_t layout, int64_t* cols, int64_t* ids,
-                                 void* stream) {
+                                 int64_t row_offset, int64_t* cols, int64_t* ids, void* stream) {
   XR_CHECK_ARG(group_ids && cols && ids && u >= 0 && kg >= 0 && n > 0, "xr_groups_to_rows: bad arguments");
   const int64_t total = u * kg * 16;
   if (total == 0) return XR_OK;
   int64_t blocks = (total + 255) / 256;
   if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
   groups_to_rows_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(group_ids, total, n, row_offset,
-                                                                         layout, cols, ids);
+                                                                         cols, ids);
   XR_LAUNCH_CHECK("groups_to_rows");
   return XR_OK;
+}
+
+extern "C" int xr_filter_finalize(const void* q, int64_t u, const void* catalog, int64_t n, int64_t dim,
+                                  const float* cand_scores, const int32_t* cand_rows,
+                                  const int32_t* cand_count, int64_t cap, int64_t k_sel, int64_t k,
+                                  int64_t row_offset, const int64_t* excl_offsets, const int64_t* excl_ids,
+                                  int64_t max_excl, float* out_scores, int64_t* out_idx, int32_t* flags,
+                                  void* stream) {
+  XR_CHECK_ARG(q && catalog && cand_scores && cand_rows && cand_count && out_scores && out_idx && flags,
+               "xr_filter_finalize: null pointer");
+  XR_CHECK_ARG(dim == FD, "xr_filter_finalize: this build is specialised for dim = %d", FD);
+  XR_CHECK_ARG(u >= 0 && n > 0 && cap >= 1 && k >= 1 && k_sel >= k && k_sel <= TK_MAX_K,
+               "xr_filter_finalize: needs 1 <= k <= k_sel <= %d", TK_MAX_K);
+  XR_CHECK_ARG(row_offset >= 0 && row_offset + n <= (1ll << 32), "xr_filter_finalize: global ids must be < 2^32");
+  XR_CHECK_ARG(!excl_offsets || excl_ids, "xr_filter_finalize: excl_offsets without excl_ids");
+  if (u == 0) return XR_OK;
+  filter_finalize_kernel<<<(unsigned)u, TK_THREADS, 0, as_stream(stream)>>>(
+      (const __nv_bfloat16*)q, (const __nv_bfloat16*)catalog, n, cand_scores, cand_rows, cand_count, cap,
+      (int)k_sel, (int)k, row_offset, excl_offsets, excl_ids, max_excl, out_scores, out_idx, flags);
+  XR_LAUNCH_CHECK("filter_finalize");
+  return XR_OK;
+}
+
+// ---- the whole local search as one call ------------------------------------------------------------
+namespace xr {
+constexpr int64_t kFilterCap = 32768;   // survivor slots per query
+constexpr int kFilterMargin = 28;       // rank positions of slack between the two score arithmetics
+struct ScoreTopkPlan {
+  int64_t kk, stride, ld_s, cap;
+  size_t off_gmax, off_tkws, off_vals, off_idx, off_cs, off_cr, off_cnt, bytes, tkws_bytes;
+};
+static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
+static ScoreTopkPlan plan_score_topk(int64_t u, int64_t n, int64_t k, int64_t max_excl) {
+  ScoreTopkPlan pl{};
+  pl.kk = k + max_excl + kFilterMargin;
+  pl.cap = kFilterCap;
+  // sample stride (in tiles of the scoring kernel): the expected number of survivors is ~kk * stride, so
+  // kk * stride * 3 <= cap; and the sample keeps at least 4 kk groups so that its kk-th maximum exists
+  int64_t s = pl.cap / (3 * pl.kk);
+  if (s > 32) s = 32;
+  const int64_t groups = (n + 15) / 16;
+  while (s > 1 && groups / s < 4 * pl.kk) --s;
+  if (s < 1) s = 1;
+  pl.stride = s;
+  pl.ld_s = (xr_score_groupmax_ld(u, n, s) + 3) / 4 * 4;   // 16-byte aligned rows: the streaming top-k path
+  size_t o = 0;
+  pl.off_gmax = o; o += al256((size_t)u * pl.ld_s * 4);
+  pl.tkws_bytes = xr_topk_workspace_bytes(u, pl.ld_s, pl.kk);
+  pl.off_tkws = o; o += al256(pl.tkws_bytes);
+  pl.off_vals = o; o += al256((size_t)u * pl.kk * 4);
+  pl.off_idx = o;  o += al256((size_t)u * pl.kk * 8);
+  pl.off_cs = o;   o += al256((size_t)u * pl.cap * 4);
+  pl.off_cr = o;   o += al256((size_t)u * pl.cap * 4);
+  pl.off_cnt = o;  o += al256((size_t)u * 4);
+  pl.bytes = o;
+  return pl;
+}
+__global__ void fill_neg_inf_kernel(float* __restrict__ p, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = -CUDART_INF_F;
+}
+}  // namespace xr
+
+extern "C" size_t xr_score_topk_workspace_bytes(int64_t u, int64_t n, int64_t k, int64_t max_excl) {
+  if (u <= 0 || n <= 0 || k < 1 || max_excl < 0 || k + max_excl + kFilterMargin > TK_MAX_K) return 256;
+  return plan_score_topk(u, n, k, max_excl).bytes;
+}
+
+extern "C" int xr_score_topk(const void* q, int64_t u, const void* catalog, int64_t n, int64_t dim, int64_t k,
+                             int64_t row_offset, const int64_t* excl_offsets, const int64_t* excl_ids,
+                             int64_t max_excl, float* out_scores, int64_t* out_idx, int32_t* flags,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  XR_CHECK_ARG(q && catalog && out_scores && out_idx && flags && workspace, "xr_score_topk: null pointer");
+  XR_CHECK_ARG(u > 0 && u <= 65535 && n > 0 && k >= 1 && max_excl >= 0, "xr_score_topk: bad sizes (u <= 65535 per call)");
+  XR_CHECK_ARG(k + max_excl + kFilterMargin <= TK_MAX_K, "xr_score_topk: k + max_excl must be <= %d",
+               TK_MAX_K - kFilterMargin);
+  XR_CHECK_ARG((uintptr_t)workspace % 256 == 0, "xr_score_topk: workspace must be 256-byte aligned");
+  const ScoreTopkPlan pl = plan_score_topk(u, n, k, max_excl);
+  XR_CHECK_ARG(workspace_bytes >= pl.bytes, "xr_score_topk: workspace too small");
+  uint8_t* w = (uint8_t*)workspace;
+  float* gmax = (float*)(w + pl.off_gmax);
+  float* vals = (float*)(w + pl.off_vals);
+  int64_t* idx = (int64_t*)(w + pl.off_idx);
+  float* cs = (float*)(w + pl.off_cs);
+  int32_t* cr = (int32_t*)(w + pl.off_cr);
+  int32_t* cnt = (int32_t*)(w + pl.off_cnt);
+  cudaStream_t s = as_stream(stream);
+  int rc;
+  // 1. thresholds: the kk-th largest group maximum of a strided sample of the shard (-inf when the sample
+  //    has fewer groups: every row then survives, and cap >= n in that regime)
+  const int64_t ld_used = xr_score_groupmax_ld(u, n, pl.stride);
+  if (ld_used < pl.ld_s) {   // padding columns of the aligned row stride
+    fill_neg_inf_kernel<<<(unsigned)((u * pl.ld_s + 255) / 256 < 1184 ? (u * pl.ld_s + 255) / 256 : 1184), 256, 0, s>>>(
+        gmax, u * pl.ld_s);
+    XR_LAUNCH_CHECK("fill_neg_inf");
+  }
+  if ((rc = xr_score_groupmax(q, u, catalog, n, dim, pl.stride, gmax, pl.ld_s, stream))) return rc;
+  if ((rc = xr_topk(gmax, u, pl.ld_s, pl.ld_s, pl.kk, 0, vals, idx, w + pl.off_tkws, pl.tkws_bytes, stream)))
+    return rc;
+  // 2. one pass over the shard: survivors of the filter
+  XR_CUDA(cudaMemsetAsync(cnt, 0, (size_t)u * 4, s));
+  if ((rc = xr_score_filter(q, u, catalog, n, dim, vals + (pl.kk - 1), pl.kk, cs, cr, cnt, pl.cap, stream)))
+    return rc;
+  // 3. survivors -> exact top-k
+  return xr_filter_finalize(q, u, catalog, n, dim, cs, cr, cnt, pl.cap, pl.kk, k, row_offset, excl_offsets,
+                            excl_ids, max_excl, out_scores, out_idx, flags, stream);
 }
 
 extern "C" int xr_retrieval_metrics(const int64_t* rec, int64_t u, int64_t k,

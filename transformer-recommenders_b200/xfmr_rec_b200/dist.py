@@ -105,14 +105,16 @@ class ShardedIndex:
     ``"auto"`` tries peer memory first.  Both give the single-GPU result bit for bit."""
 
     def __init__(self, local_index, *, group=None, merge_fn: Callable | None = None,
-                 exchange: str = "nccl", use_plan: bool = False):
+                 exchange: str = "nccl", use_plan: bool = False, plan_max_exclusions: int = 0):
         self.local = local_index
         self.group = group
         self.merge_fn = merge_fn
         self.exchange = exchange
-        # use_plan: the local search of exclusion-free query batches runs as one CUDA-graph replay
-        # (ExactIndex.compile_search), compiled once per (U, top_k)
+        # use_plan: the local search runs as one CUDA-graph replay (ExactIndex.compile_search), compiled
+        # once per (U, top_k); exclusion lists (CSR tensor pairs of at most plan_max_exclusions ids per
+        # query) pass through the plan's static buffers
         self.use_plan = use_plan
+        self.plan_max_exclusions = int(plan_max_exclusions)
         self._plans: dict = {}
         self._peer: PeerExchange | None = None
         self._peer_failed: str | None = None
@@ -141,12 +143,20 @@ class ShardedIndex:
         idx.set_catalog(embeddings[lo:hi])
         return cls(idx, group=group)
 
-    def search_batch(self, queries: torch.Tensor, exclude_rows=None, top_k: int = 20):
-        if self.use_plan and exclude_rows is None and queries.dim() == 2:
-            key = (queries.size(0), top_k)
+    def plans_overflowed(self) -> bool:
+        """True if a graph-replayed local search issued with ``check=False`` could not be served exactly
+        (see ``SearchPlan``); clears the flags."""
+        return any([p.overflowed() for p in self._plans.values()])
+
+    def search_batch(self, queries: torch.Tensor, exclude_rows=None, top_k: int = 20, *, check: bool = True):
+        planned = (self.use_plan and queries.dim() == 2 and
+                   (exclude_rows is None or (isinstance(exclude_rows, tuple) and self.plan_max_exclusions > 0)))
+        if planned:
+            mx = self.plan_max_exclusions if exclude_rows is not None else 0
+            key = (queries.size(0), top_k, mx)
             if key not in self._plans:
-                self._plans[key] = self.local.compile_search(queries.size(0), top_k)
-            s, i = self._plans[key](queries)
+                self._plans[key] = self.local.compile_search(queries.size(0), top_k, mx)
+            s, i = self._plans[key](queries, exclude_rows, check=check)
         else:
             s, i = self.local.search_batch(queries, exclude_rows, top_k)
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1

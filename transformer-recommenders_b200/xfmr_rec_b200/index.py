@@ -32,8 +32,8 @@ class ExactIndexConfig(pydantic.BaseModel):
     index_metric: Literal["dot", "cosine"] = "cosine"
     dtype: Literal["bf16", "fp32"] = "bf16"
     max_score_bytes: int = 1 << 30  # materialised-score budget of the unfused path
-    max_groupmax_bytes: int = 12 << 30  # group-maxima budget of the fused path: larger query sets run in blocks
-    fused: bool = True  # tensor-core group-max path when the device / dtype allow it
+    max_groupmax_bytes: int = 4 << 30  # workspace budget of the fused path (survivor lists: 256 KB per query): larger query sets run in blocks
+    fused: bool = True  # tensor-core filter path (xr_score_topk) when the device / dtype allow it
 
 
 class ExactIndex:
@@ -95,11 +95,7 @@ class ExactIndex:
         return self.ids[row] if self.ids is not None else str(row + self.row_offset)
 
     # -- search -------------------------------------------------------------------------------
-    def search_batch(self, queries: torch.Tensor, exclude_rows=None, top_k: int = TOP_K):
-        """queries (U, D) on the device; exclude_rows: per-query lists of GLOBAL catalog rows
-        (or a CSR tensor pair).  Returns (scores (U,k) fp32, rows (U,k) int64 global; -1/-inf
-        where fewer than k rows remain)."""
-        assert self.catalog is not None, "index_data / set_catalog first"
+    def _prep_queries(self, queries: torch.Tensor) -> torch.Tensor:
         cat = self.catalog
         if self.device is None:   # catalog installed directly (a view of a resident shard)
             self.device = cat.device
@@ -110,92 +106,82 @@ class ExactIndex:
             q, _ = ops.normalize_rows(q.float(), 1e-12, cat.dtype)
         else:
             q = q.to(cat.dtype).contiguous()
+        return q
+
+    def search_batch(self, queries: torch.Tensor, exclude_rows=None, top_k: int = TOP_K, *,
+                     max_exclusions: int | None = None):
+        """queries (U, D) on the device; exclude_rows: per-query lists of GLOBAL catalog rows
+        (or a CSR tensor pair; then ``max_exclusions`` saves a device->host read of the longest list).
+        Returns (scores (U,k) fp32, rows (U,k) int64 global; -1/-inf where fewer than k rows remain)."""
+        assert self.catalog is not None, "index_data / set_catalog first"
+        cat = self.catalog
+        q = self._prep_queries(queries)
         u, n = q.size(0), cat.size(0)
-        # bound the group-maxima buffer (U x N/16 fp32): query blocks of at most max_groupmax_bytes
-        u_blk = max(256, (self.config.max_groupmax_bytes // max(1, (n + 15) // 16 * 4)) // 256 * 256)
-        if u > u_blk:
-            if exclude_rows is not None and isinstance(exclude_rows, tuple):
-                offs, flat = exclude_rows
-                offs_h = offs.tolist()
-            parts = []
-            for lo in range(0, u, u_blk):
-                hi = min(u, lo + u_blk)
-                if exclude_rows is None:
-                    ex = None
-                elif isinstance(exclude_rows, tuple):
-                    ex = (offs[lo:hi + 1] - offs_h[lo], flat[offs_h[lo]:max(offs_h[hi], offs_h[lo] + 1)])
-                else:
-                    ex = exclude_rows[lo:hi]
-                parts.append(self.search_batch(queries[lo:hi], ex, top_k))
-            return torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
         csr = None
         if exclude_rows is not None:
-            csr = exclude_rows if isinstance(exclude_rows, tuple) else ops._csr(exclude_rows, self.device)
-        max_excl = 0
-        if csr is not None:
-            max_excl = int((csr[0][1:] - csr[0][:-1]).max().item()) if csr[0].numel() > 1 else 0
-        n_groups = (n + 15) // 16
-        kg = min(n_groups, top_k + max_excl + 28)
-        if ops.score_groupmax_supported(q, cat) and kg <= 1024 and self.config.fused:
-            s, i = self._search_groupmax(q, cat, csr, top_k, kg)
-        else:
-            chunk = max(4096, min(n, self.config.max_score_bytes // (4 * max(u, 1)) // 4 * 4))
-            parts_s, parts_i = [], []
-            for lo in range(0, n, chunk):
-                blk = cat[lo:lo + chunk]
-                sc = ops.scores(q, blk)
-                if csr is not None:
-                    ops.mask_excluded(sc, blk.size(0), csr, col_offset=self.row_offset + lo)
-                ps, pi = ops.topk(sc, top_k, n=blk.size(0), col_offset=self.row_offset + lo)
-                parts_s.append(ps)
-                parts_i.append(pi)
-            if len(parts_s) == 1:
-                s, i = parts_s[0], parts_i[0]
+            if isinstance(exclude_rows, tuple):
+                csr = exclude_rows
+                if max_exclusions is None:
+                    max_exclusions = int((csr[0][1:] - csr[0][:-1]).max().item()) if csr[0].numel() > 1 else 0
             else:
-                s, i = ops.topk_merge(torch.cat(parts_s, 1), torch.cat(parts_i, 1), top_k)
+                if max_exclusions is None:
+                    max_exclusions = max((len(l) for l in exclude_rows), default=0)
+                csr = ops._csr(exclude_rows, self.device)
+        max_excl = int(max_exclusions or 0) if csr is not None else 0
+        fused = (self.config.fused and ops.score_topk_supported(q, cat)
+                 and top_k + max_excl <= ops.SCORE_TOPK_MAX_K)
+        if not fused:
+            return self._finish(*self._search_materialised(q, cat, csr, top_k))
+        # workspace budget: query blocks (the survivor lists take 256 KB per query)
+        per_q = max(1, ops.N.lib().xr_score_topk_workspace_bytes(256, n, top_k, max_excl) // 256)
+        u_blk = int(min(65535, max(256, self.config.max_groupmax_bytes // per_q // 256 * 256)))
+        flags = torch.zeros(1, dtype=torch.int32, device=self.device)
+        parts = []
+        offs_h = csr[0].tolist() if (csr is not None and u > u_blk) else None
+        for lo in range(0, u, u_blk):
+            hi = min(u, lo + u_blk)
+            ex = csr
+            if csr is not None and offs_h is not None:
+                ex = (csr[0][lo:hi + 1] - offs_h[lo], csr[1][offs_h[lo]:max(offs_h[hi], offs_h[lo] + 1)])
+            s, i, _ = ops.score_topk(q[lo:hi], cat, top_k, self.row_offset, ex, max_excl, flags)
+            parts.append((s, i))
+        s = parts[0][0] if len(parts) == 1 else torch.cat([p[0] for p in parts])
+        i = parts[0][1] if len(parts) == 1 else torch.cat([p[1] for p in parts])
+        if int(flags.item()):
+            # a survivor list overflowed (more than 32,768 rows tie with or beat the sample's threshold:
+            # massively duplicated rows): the materialised scan is exact for any input
+            s, i = self._search_materialised(q, cat, csr, top_k)
+        return self._finish(s, i)
+
+    @staticmethod
+    def _finish(s, i):
         # excluded rows carry -inf: they are filtered out, never returned (index.py:246)
         dead = s == float("-inf")
-        i = torch.where(dead, torch.full_like(i, -1), i)
-        return s, i
+        return s, torch.where(dead, torch.full_like(i, -1), i)
 
-    def _search_groupmax(self, q, cat, csr, top_k, kg):
-        """Tensor-core path: group maxima (tcgen05) -> top groups -> exact re-score of their rows
-        -> merge under (score desc, row asc).  The k-th largest group maximum lower-bounds the k-th
-        largest score and every score above it sits in a group above it; `kg` adds one group per
-        excluded id plus a margin, so the result equals the full scan.
-
-        With exclusion lists the conservative `kg` (one extra group per excluded id) is rarely
-        needed: phase 1 re-scores only the first ``top_k + 28`` groups; a query is DONE when its k-th
-        surviving score is strictly above the next group maximum (no row outside can reach it, ties
-        included).  Phase 2 re-scores the remaining groups for the other queries only (their group
-        ids are replaced by -1 for finished queries, which the gather skips) — no host sync, same
-        result as re-scoring all `kg` groups."""
-        n = cat.size(0)
-        gmax, layout = ops.score_groupmax(q, cat)
-        n_slots = gmax.size(1) if layout else (n + 15) // 16         # every slot of the pair layout is written
-        gv, gi = ops.topk(gmax, kg, n=n_slots)                       # (U, kg) group maxima / slots, -1 = none
-        kg1 = min(kg, top_k + 28)
-
-        def rescore(slots):
-            cols, ids = ops.groups_to_rows(slots, n, self.row_offset, layout)
-            scores = ops.logits_sampled(q, cat, cols)
-            ops.mask_excluded_ids(scores, ids, self.row_offset, self.row_offset + n, csr)
-            return ops.topk_merge(scores, ids, top_k)
-
-        if csr is None or kg1 >= kg:
-            return rescore(gi)
-        s1, i1 = rescore(gi[:, :kg1].contiguous())
-        bound = gv[:, kg1]                                           # best score any row outside phase 1 can have
-        done = s1[:, top_k - 1] > bound if s1.size(1) >= top_k else torch.zeros_like(bound, dtype=torch.bool)
-        rest = torch.where(done[:, None], torch.full_like(gi[:, kg1:], -1), gi[:, kg1:]).contiguous()
-        s2, i2 = rescore(rest)
-        return ops.topk_merge(torch.cat([s1, s2], 1), torch.cat([i1, i2], 1), top_k)
+    def _search_materialised(self, q, cat, csr, top_k):
+        """Scores of catalog chunks in HBM -> exclusion mask -> streaming top-k -> merge: exact for any
+        input (fp32 / D != 384 catalogs, and the fallback of the filter path)."""
+        u, n = q.size(0), cat.size(0)
+        chunk = max(4096, min(n, self.config.max_score_bytes // (4 * max(u, 1)) // 4 * 4))
+        parts_s, parts_i = [], []
+        for lo in range(0, n, chunk):
+            blk = cat[lo:lo + chunk]
+            sc = ops.scores(q, blk)
+            if csr is not None:
+                ops.mask_excluded(sc, blk.size(0), csr, col_offset=self.row_offset + lo)
+            ps, pi = ops.topk(sc, top_k, n=blk.size(0), col_offset=self.row_offset + lo)
+            parts_s.append(ps)
+            parts_i.append(pi)
+        if len(parts_s) == 1:
+            return parts_s[0], parts_i[0]
+        return ops.topk_merge(torch.cat(parts_s, 1), torch.cat(parts_i, 1), top_k)
 
     def compile_search(self, n_queries: int, top_k: int = TOP_K, max_exclusions: int = 0) -> "SearchPlan":
         """The whole search for a FIXED shape ``(n_queries, top_k)`` and at most ``max_exclusions``
-        excluded rows per query as one CUDA-graph replay: ~15 launches and their Python / ctypes
-        dispatch become one ``cudaGraphLaunch`` (the per-user validation loop of trainer.py:293-298
-        and the serving path call search once per query: host dispatch, not the GPU, bounds them)."""
+        excluded rows per query as one CUDA-graph replay (the per-user validation loop of
+        trainer.py:293-298 and the serving path call search once per query: host dispatch, not the
+        GPU, bounds them)."""
         return SearchPlan(self, n_queries, top_k, max_exclusions)
 
     def search(self, embedding, exclude_item_ids: list[str] | None = None, top_k: int = TOP_K):
@@ -304,8 +290,13 @@ class SearchPlan:
 
     ``plan(queries, exclude)``: ``queries`` (U, D) on the device; ``exclude`` = None or a CSR pair
     ``(offsets (U+1,), rows (n,))`` of device int64 tensors with at most ``max_exclusions`` rows per
-    query (checked on the host only if the offsets are a host list).  Returns views of the plan's
-    static output buffers ``(scores (U, k), rows (U, k))`` — valid until the next call."""
+    query (checked on the DEVICE: a longer list raises the plan's flag).  Returns views of the plan's
+    static output buffers ``(scores (U, k), rows (U, k))`` — valid until the next call.
+
+    ``check=True`` (default) reads the plan's flag word after the replay (one device->host copy) and
+    re-runs the search through the materialised path if a survivor list overflowed, so the result is
+    exact for any input.  ``check=False`` keeps the call asynchronous; the caller then asks
+    :meth:`overflowed` once after a series of searches (the flag is sticky)."""
 
     def __init__(self, index: ExactIndex, n_queries: int, top_k: int, max_exclusions: int = 0):
         assert index.catalog is not None, "index_data / set_catalog first"
@@ -314,16 +305,18 @@ class SearchPlan:
         cat = index.catalog
         n = cat.size(0)
         probe = torch.empty((1, cat.size(1)), dtype=cat.dtype, device=dev)
-        if not (ops.score_groupmax_supported(probe, cat) and index.config.fused):
-            raise ops.N.NativeError("compile_search needs the tensor-core group-max path "
+        if not (ops.score_topk_supported(probe, cat) and index.config.fused):
+            raise ops.N.NativeError("compile_search needs the tensor-core scoring path "
                                     "(bf16 catalog, D = 384, sm_100)")
-        n_groups = (n + 15) // 16
-        self.kg = min(n_groups, self.k + self.max_excl + 28)
-        if self.kg > 1024:
-            raise ValueError("top_k + max_exclusions too large for the group-max path")
+        if self.k + self.max_excl > ops.SCORE_TOPK_MAX_K or self.u > 65535:
+            raise ValueError("top_k + max_exclusions (or the number of queries) too large for one plan")
         self.q = torch.zeros((self.u, cat.size(1)), dtype=torch.float32, device=dev)
         self.offs = torch.zeros(self.u + 1, dtype=torch.int64, device=dev)
         self.rows = torch.zeros(max(1, self.u * self.max_excl), dtype=torch.int64, device=dev)
+        self.flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.ws = ops.score_topk_workspace(self.u, n, self.k, self.max_excl, dev)
+        self.out = (torch.empty((self.u, self.k), dtype=torch.float32, device=dev),
+                    torch.empty((self.u, self.k), dtype=torch.int64, device=dev))
         self.device = dev
         with torch.cuda.device(dev):
             side = torch.cuda.Stream(device=dev)
@@ -332,6 +325,7 @@ class SearchPlan:
                 self._run()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize(dev)
+            self.flags.zero_()
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.out_s, self.out_i = self._run()
@@ -344,11 +338,18 @@ class SearchPlan:
         else:
             q = self.q.to(cat.dtype)
         csr = (self.offs, self.rows) if self.max_excl > 0 else None
-        s, i = idx._search_groupmax(q, cat, csr, self.k, self.kg)
-        dead = s == float("-inf")
-        return s, torch.where(dead, torch.full_like(i, -1), i)
+        s, i, _ = ops.score_topk(q, cat, self.k, idx.row_offset, csr, self.max_excl, self.flags,
+                                 out=self.out, ws=self.ws)
+        return ExactIndex._finish(s, i)
 
-    def __call__(self, queries: torch.Tensor, exclude=None):
+    def overflowed(self, *, clear: bool = True) -> bool:
+        """True if any search since the last clear could not be served exactly by the filter path."""
+        bad = bool(int(self.flags.item()))
+        if bad and clear:
+            self.flags.zero_()
+        return bad
+
+    def __call__(self, queries: torch.Tensor, exclude=None, *, check: bool = True):
         assert queries.shape == self.q.shape, f"plan was compiled for {tuple(self.q.shape)} queries"
         self.q.copy_(queries, non_blocking=True)
         if self.max_excl > 0:
@@ -362,4 +363,8 @@ class SearchPlan:
         else:
             assert exclude is None, "plan was compiled with max_exclusions = 0"
         self.graph.replay()
+        if check and self.overflowed():
+            cat = self.index.catalog
+            s, i = self.index._search_materialised(self.index._prep_queries(queries), cat, exclude, self.k)
+            return ExactIndex._finish(s, i)
         return self.out_s, self.out_i

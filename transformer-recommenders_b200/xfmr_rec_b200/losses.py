@@ -288,10 +288,13 @@ class EmbedLoss(torch.nn.Module, abc.ABC):
             neg = ops.normalize_rows(neg, 1e-8, cdt)[0] if neg.size(0) else neg.to(cdt)
         else:
             q, pos, neg = (t.to(cdt).contiguous() for t in (q, pos, neg))
+        # the fused softmax takes scale * target as its reference maximum, which needs scale > 0; the
+        # reference accepts any scale (losses.py:483-488), so those configs use the materialised path
         fused_ok = (not want_stats and cfg.num_hard_negatives == 0 and neg.size(0) > 0
-                    and type(self).__name__ in _FUSED_KINDS and ops.fused_pool_supported(q, neg))
+                    and type(self).__name__ in _FUSED_KINDS and ops.fused_pool_supported(q, neg)
+                    and (type(self).__name__ != "InfoNCELoss" or cfg.scale > 0))
         if (want_stats and grad_kind < 0 and cfg.num_hard_negatives == 0 and neg.size(0) > 0
-                and ops.fused_pool_supported(q, neg)):
+                and ops.fused_pool_supported(q, neg) and (self.COSINE or cfg.scale > 0)):
             # every loss of this logit family + the statistics block from ONE tensor-core pass
             losses, stats = ops.fused_pool_all(q, pos, neg, cfg, self.COSINE)
             return losses, stats, None

@@ -401,10 +401,13 @@ def topk_merge(cand_scores, cand_ids, k):
     u, gk = cand_scores.shape
     out_s = torch.empty((u, k), dtype=torch.float32, device=dev)
     out_i = torch.empty((u, k), dtype=torch.int64, device=dev)
-    ws = _ws(N.lib().xr_topk_merge_workspace_bytes(u, k), dev)
-    with _on(dev):
-        N.call("xr_topk_merge", _p(cand_scores), _p(cand_ids), u, gk, k, _p(out_s), _p(out_i),
-               _p(ws), _stream())
+    step = 65535   # grid.y limit of the merge kernel, as in topk()
+    for lo in range(0, u, step):
+        uu = min(step, u - lo)
+        ws = _ws(N.lib().xr_topk_merge_workspace_bytes(uu, k), dev)
+        with _on(dev):
+            N.call("xr_topk_merge", _p(cand_scores[lo:]), _p(cand_ids[lo:]), uu, gk, k, _p(out_s[lo:]),
+                   _p(out_i[lo:]), _p(ws), _stream())
     return out_s, out_i
 
 
@@ -416,21 +419,23 @@ def score_groupmax_supported(q, catalog) -> bool:
     return major == 10 and bool(N.lib().xr_fused_available() & 2)
 
 
-def score_groupmax(q, catalog):
-    """tcgen05 scoring without the (U,N) matrix: max score of every 16-row catalog group."""
+def score_groupmax(q, catalog, tile_stride=1):
+    """tcgen05 scoring without the (U,N) matrix: max score of every 16-row catalog group, natural
+    order (column c = rows [16c, 16c+16)); with ``tile_stride`` = s > 1 only every s-th tile of T rows
+    (T = 128 for U > 128, else 64) is scored and column (T/16) t + g = rows [T t s + 16 g, +16)."""
     dev = _require_cuda(q, catalog)
     q, catalog = q.contiguous(), catalog.contiguous()
     u, d = q.shape
     n = catalog.size(0)
-    layout = int(N.lib().xr_score_groupmax_layout(u, n))   # 0 natural, else the pair kernel's stride
-    ld = int(N.lib().xr_score_groupmax_ld(u, n))
+    ld = int(N.lib().xr_score_groupmax_ld(u, n, tile_stride))
+    ld += ld % 2
     gmax = torch.empty((u, ld), dtype=torch.float32, device=dev)
     with _on(dev):
-        N.call("xr_score_groupmax", _p(q), u, _p(catalog), n, d, _p(gmax), ld, _stream())
-    return gmax, layout
+        N.call("xr_score_groupmax", _p(q), u, _p(catalog), n, d, tile_stride, _p(gmax), ld, _stream())
+    return gmax
 
 
-def groups_to_rows(group_ids, n, row_offset=0, layout=0):
+def groups_to_rows(group_ids, n, row_offset=0):
     """(U, kg) group ids -> (cols, ids), both (U, kg*16) int64: gather rows and global ids (-1 = none)."""
     dev = _require_cuda(group_ids)
     group_ids = group_ids.contiguous()
@@ -438,8 +443,7 @@ def groups_to_rows(group_ids, n, row_offset=0, layout=0):
     cols = torch.empty((u, kg * 16), dtype=torch.int64, device=dev)
     ids = torch.empty((u, kg * 16), dtype=torch.int64, device=dev)
     with _on(dev):
-        N.call("xr_groups_to_rows", _p(group_ids), u, kg, n, row_offset, layout, _p(cols), _p(ids),
-               _stream())
+        N.call("xr_groups_to_rows", _p(group_ids), u, kg, n, row_offset, _p(cols), _p(ids), _stream())
     return cols, ids
 
 
@@ -453,30 +457,72 @@ def mask_excluded_ids(score_mat, ids, id_lo, id_hi, exclude=None):
     return score_mat
 
 
+def score_filter(q, catalog, thresh, cap):
+    """Scoring pass with the threshold filter in the epilogue (xr_score_filter): returns the unordered
+    survivor lists (scores (U, cap) fp32, rows (U, cap) int32, counts (U,) int32 — a count above
+    ``cap`` means that query's list is incomplete)."""
+    dev = _require_cuda(q, catalog, thresh)
+    q, catalog = q.contiguous(), catalog.contiguous()
+    thresh = thresh.contiguous().float()
+    u = q.size(0)
+    cs = torch.empty((u, cap), dtype=torch.float32, device=dev)
+    cr = torch.empty((u, cap), dtype=torch.int32, device=dev)
+    cnt = torch.zeros(u, dtype=torch.int32, device=dev)
+    with _on(dev):
+        N.call("xr_score_filter", _p(q), u, _p(catalog), catalog.size(0), q.size(1), _p(thresh), 1,
+               _p(cs), _p(cr), _p(cnt), cap, _stream())
+    return cs, cr, cnt
+
+
+def filter_finalize(q, catalog, cs, cr, cnt, k_sel, k, row_offset=0, exclude=None, max_excl=0, flags=None):
+    dev = _require_cuda(q, catalog, cs, cr, cnt)
+    offs, ex = (None, None) if exclude is None else exclude
+    u = q.size(0)
+    out_s = torch.empty((u, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((u, k), dtype=torch.int64, device=dev)
+    if flags is None:
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    with _on(dev):
+        N.call("xr_filter_finalize", _p(q), u, _p(catalog), catalog.size(0), q.size(1), _p(cs), _p(cr),
+               _p(cnt), cs.size(1), k_sel, k, row_offset, _p(offs), _p(ex), max_excl, _p(out_s), _p(out_i),
+               _p(flags), _stream())
+    return out_s, out_i, flags
+
+
+SCORE_TOPK_MAX_K = 1024 - 28   # k + max_excl the one-call search serves (xr_score_topk)
+
+
 def score_topk_supported(q, catalog) -> bool:
-    if not (q.is_cuda and q.dtype == torch.bfloat16 and catalog.dtype == torch.bfloat16
-            and q.size(1) == 384):
-        return False
-    major, _ = torch.cuda.get_device_capability(q.device)
-    return False  # superseded by the group-max path (score_groupmax + re-score + merge)
+    return score_groupmax_supported(q, catalog)
 
 
-def score_topk(q, catalog, k, q_inv=None, cat_inv=None, exclude=None, col_offset=0):
-    """Fused tcgen05 scoring + top-k over one catalog shard (xr_score_topk)."""
+def score_topk(q, catalog, k, row_offset=0, exclude=None, max_excl=0, flags=None, out=None, ws=None):
+    """The whole local search of one catalog shard in one call (xr_score_topk): sample thresholds ->
+    filter in the scoring epilogue -> exact top-k of the survivors.  ``exclude``: CSR pair of GLOBAL
+    ids with at most ``max_excl`` per query.  ``flags`` (int32[1], sticky) becomes non-zero when the
+    result is not guaranteed exact (survivor list overflow / more exclusions than announced): the
+    caller then takes the materialised path.  Returns (scores (U,k), ids (U,k) global, flags)."""
     dev = _require_cuda(q, catalog)
     q, catalog = q.contiguous(), catalog.contiguous()
     u, d = q.shape
     n = catalog.size(0)
-    offs, ids = (None, None)
-    if exclude is not None:
-        offs, ids = exclude if isinstance(exclude, tuple) else _csr(exclude, dev)
-    out_s = torch.empty((u, k), dtype=torch.float32, device=dev)
-    out_i = torch.empty((u, k), dtype=torch.int64, device=dev)
-    ws = _ws(N.lib().xr_score_topk_workspace_bytes(u, n, k), dev)
+    offs, ids = (None, None) if exclude is None else exclude
+    if out is None:
+        out = (torch.empty((u, k), dtype=torch.float32, device=dev),
+               torch.empty((u, k), dtype=torch.int64, device=dev))
+    if flags is None:
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    if ws is None:
+        ws = score_topk_workspace(u, n, k, max_excl, dev)
+    ptr = ws.data_ptr() + (-ws.data_ptr()) % 256
     with _on(dev):
-        N.call("xr_score_topk", _p(q), u, _p(catalog), n, d, _p(q_inv), _p(cat_inv), k, col_offset,
-               _p(offs), _p(ids), _p(out_s), _p(out_i), _p(ws), ws.numel(), _stream())
-    return out_s, out_i
+        N.call("xr_score_topk", _p(q), u, _p(catalog), n, d, k, row_offset, _p(offs), _p(ids), max_excl,
+               _p(out[0]), _p(out[1]), _p(flags), C.c_void_p(ptr), ws.numel() - 256, _stream())
+    return out[0], out[1], flags
+
+
+def score_topk_workspace(u, n, k, max_excl, device):
+    return _ws(N.lib().xr_score_topk_workspace_bytes(u, n, k, max_excl) + 256, device)
 
 
 def retrieval_metrics(rec_idx, target_lists, top_k):

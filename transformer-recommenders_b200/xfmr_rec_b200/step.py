@@ -51,6 +51,9 @@ class PoolLossStep:
                                       "(target_position='first', models.py:410)")
         if cfg.num_hard_negatives:
             raise NotImplementedError("PoolLossStep: hard-negative mining needs the materialised path")
+        if cfg.scale <= 0 and (name == "InfoNCELoss" or monitor):
+            raise NotImplementedError("PoolLossStep: the fused softmax needs scale > 0 "
+                                      "(other scales go through compute_embeds + the loss module)")
         dev = embeddings.weight.device
         if dev.type != "cuda":
             raise N.NativeError("PoolLossStep needs the item table on a CUDA device; there is no CPU fallback")
@@ -166,8 +169,19 @@ class PoolLossStep:
         """Copy one SeqBatch (host pinned or device tensors) into the static buffers on the copy
         stream.  Waits for the previous run of THIS step object to finish with the buffers."""
         n = self.n_pos
+        inputs = (token_embeddings, history_item_idx, pos_item_idx, neg_item_idx)
+        dev_inputs = [t for t in inputs if t.is_cuda]
+        with torch.cuda.device(self.device):
+            producer = torch.cuda.current_stream()
         with torch.cuda.device(self.device), torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self._done)
+            if dev_inputs:
+                # device-resident inputs (the encoder output of THIS step) are still being written on
+                # the caller's stream: order the copies after it, and keep the caching allocator from
+                # recycling the blocks while the copy stream reads them
+                self.copy_stream.wait_stream(producer)
+                for t in dev_inputs:
+                    t.record_stream(self.copy_stream)
             self.hist.copy_(history_item_idx.reshape(n), non_blocking=True)
             self.pos.copy_(pos_item_idx.reshape(n), non_blocking=True)
             self.neg.copy_(neg_item_idx.reshape(n), non_blocking=True)
