@@ -373,12 +373,15 @@ int xr_score_filter(const void* q, int64_t u, const void* catalog, int64_t n, in
  * (score desc, row asc) are re-scored with the arithmetic of xr_logits_sampled, rows in query u's CSR
  * exclusion list (GLOBAL ids; nullable) are dropped (the prefilter of index.py:239-247), the rest is
  * ranked by (score desc, global id asc).  out_scores (U, k) fp32 / out_idx (U, k) int64 = local row +
- * row_offset (-inf / -1 where fewer than k remain).  flags[0] |= 1 if a list overflowed (count > cap),
- * |= 2 if a query has more than max_excl excluded ids: the result is then not guaranteed exact and the
- * caller must take another path.  k_sel <= 1024.                                                    */
+ * row_offset (-inf / -1 where fewer than k remain).  thresh = the thresholds the lists were filtered
+ * with.  flags[0] |= 1 if a list overflowed (count > cap), |= 2 if a query has more than max_excl
+ * excluded ids, |= 4 if fewer than k_sel - max_excl non-excluded rows survived a finite threshold: the
+ * result is then not guaranteed exact and the caller must take another path.
+ * k + max_excl <= k_sel <= 1024.                                                                    */
 int xr_filter_finalize(const void* q, int64_t u, const void* catalog, int64_t n, int64_t dim,
                        const float* cand_scores, const int32_t* cand_rows, const int32_t* cand_count,
-                       int64_t cap, int64_t k_sel, int64_t k, int64_t row_offset,
+                       int64_t cap, const float* thresh, int64_t thresh_stride, int64_t k_sel, int64_t k,
+                       int64_t row_offset,
                        const int64_t* excl_offsets, const int64_t* excl_ids, int64_t max_excl,
                        float* out_scores, int64_t* out_idx, int32_t* flags, void* stream);
 /* scores[u, j] = -inf where ids[u, j] lies outside [id_lo, id_hi) or in row u's CSR exclusion
@@ -394,8 +397,9 @@ int xr_groups_to_rows(const int64_t* group_ids, int64_t u, int64_t kg, int64_t n
 
 /* The whole local search of one catalog shard as ONE call (bf16, dim 384) — LanceIndex.search /
  * FaissIndex.search, index.py:214-255 / 439-474, exact and batched over U queries:
- *   sample group maxima (xr_score_groupmax, tile_stride s) -> the (k + max_excl + 28)-th largest per
- *   query = threshold (xr_topk) -> xr_score_filter over the whole shard -> xr_filter_finalize.
+ *   sample group maxima (xr_score_groupmax, tile_stride s) -> the (k + 28)-th largest per query =
+ *   threshold (xr_topk) -> xr_score_filter over the whole shard -> xr_filter_finalize with
+ *   k_sel = k + max_excl + 28.
  * Same result as xr_scores + xr_mask_excluded + xr_topk unless flags[0] != 0 afterwards (see
  * xr_filter_finalize; flags is NOT cleared by the call, so one word can watch many searches).
  * q / catalog rows pre-normalised for the cosine metric.  excl_*: nullable CSR of GLOBAL ids, at most

@@ -60,9 +60,11 @@ for u in us:
     t_t, (tv, ti) = timed(lambda: ops.topk(gm, kk), iters)
     th = tv[:, kk - 1].contiguous()
     t_f, (cs, cr, cnt) = timed(lambda: ops.score_filter(qn, cat, th, 32768), iters)
-    t_z, _ = timed(lambda: ops.filter_finalize(qn, cat, cs, cr, cnt, kk, k), iters)
+    t_z, _ = timed(lambda: ops.filter_finalize(qn, cat, cs, cr, cnt, th, kk, k), iters)
+    t_inf, _ = timed(lambda: ops.score_filter(qn, cat, torch.full_like(th, float("inf")), 32768), iters)
     pt["stages_ms"] = {"sample_groupmax": round(t_g, 4), "topk_threshold": round(t_t, 4),
-                       "score_filter": round(t_f, 4), "finalize": round(t_z, 4)}
+                       "score_filter": round(t_f, 4), "finalize": round(t_z, 4),
+                       "score_filter_no_survivors": round(t_inf, 4)}
     pt["survivors_per_query"] = {"mean": float(cnt.float().mean()), "max": int(cnt.max())}
     pt["filter_TFLOPs"] = round(2.0 * u * n * d / t_f / 1e9, 1)
     pt["filter_catalog_GBs"] = round(n * d * 2.0 / t_f / 1e6, 1)

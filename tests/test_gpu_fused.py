@@ -277,8 +277,9 @@ def test_score_filter_survivors(xr, u, n):
     k = 20
     q16, c16 = torch.from_numpy(qs).cuda().bfloat16(), torch.from_numpy(cat).cuda().bfloat16()
     s, i, flags = ops.filter_finalize(q16, c16, torch.from_numpy(cs).cuda(), torch.from_numpy(cr).cuda(),
-                                      torch.from_numpy(cnt).cuda(), 60, k, row_offset=1000)
-    assert int(flags.item()) == 0
+                                      torch.from_numpy(cnt).cuda(), torch.from_numpy(th).cuda(), 60, k, row_offset=1000)
+    # the last query kept nothing: it cannot vouch for the rows below its (infinite) threshold -> flag 4
+    assert int(flags.item()) == 4
     want_s, want_i = orc.exact_search(qs[:-1], cat, k, None, metric="dot")
     assert np.array_equal(i.cpu().numpy()[:-1], want_i + 1000)
     assert np.array_equal(s.cpu().numpy()[:-1], want_s)

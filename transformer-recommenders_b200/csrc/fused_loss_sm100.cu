@@ -559,23 +559,30 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
             if (j < ncols) mx = fmaxf(mx, __uint_as_float(v[j]));
           if (row_ok) p.gmax[(long long)row * p.gmax_ld + (long long)(t0 + tl) * CG + cg] = mx;
         } else if (KIND == KIND_FILTER) {
-          // one test for the 16 scores: almost no lane-tile holds a survivor at the sample's threshold
+          // one test for the 16 scores: almost no lane-tile holds a survivor at the sample's threshold; a
+          // lane with survivors claims its slots with ONE atomic, then stores (see score_gmax2_sm100.cu)
           const int c0 = (t0 + tl) * BN + cg * 16;
-          float mx = __uint_as_float(v[0]);
+          const int lim = sh.cn - c0;               // rows past cn are TMA zero fill, not catalog rows
+          float mx = -CUDART_INF_F;
 #pragma unroll
-          for (int j = 1; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-          if (mx >= t_eff) {
+          for (int j = 0; j < 16; ++j)
+            if (j < lim) mx = fmaxf(mx, __uint_as_float(v[j]));
+          if (mx >= t_eff && lim > 0) {
+            int cnt = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) cnt += (__uint_as_float(v[j]) >= t_eff && j < lim) ? 1 : 0;
+            int w = atomicAdd(p.cand_count + row, cnt);
             float* cs = p.cand_scores + (long long)row * p.cap;
             int32_t* cr = p.cand_rows + (long long)row * p.cap;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float sc = __uint_as_float(v[j]);
-              if (sc >= t_eff && c0 + j < sh.cn) {   // rows past cn are TMA zero fill, not catalog rows
-                const int slot = atomicAdd(p.cand_count + row, 1);
-                if (slot < p.cap) {
-                  cs[slot] = sc;
-                  cr[slot] = c0 + j;
+              if (sc >= t_eff && j < lim) {
+                if (w < p.cap) {
+                  cs[w] = sc;
+                  cr[w] = c0 + j;
                 }
+                ++w;
               }
             }
           }

@@ -294,23 +294,34 @@ score_gmax2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           if (row_ok && !(DBG && (p.ablate & 4)))
             *reinterpret_cast<float2*>(out_row + 8ll * t + 2 * cg) = make_float2(m0, m1);
         } else {
-          // one test for the 32 scores keeps the common case (no survivor: ~99 % of the lane-tiles
-          // at the thresholds the sample gives) at one instruction per score
+          // one test for the 32 scores keeps the common case (no survivor) at one instruction per score;
+          // a lane with survivors counts them, claims its slots with ONE atomic (the L2 round trip is
+          // paid once per lane-tile, concurrently for all lanes of the warp) and then stores
+          const int lim = p.n - c0;                 // rows past n are TMA zero fill, not catalog rows
+          if (lim < 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j >= lim) v[j] = 0xFF800000u;     // -inf: never a survivor (thresholds are > -inf or all-pass)
+          }
           float mx = __uint_as_float(v[0]);
 #pragma unroll
           for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-          if (mx >= th) {
+          if (mx >= th && lim > 0) {
+            int cnt = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cnt += (__uint_as_float(v[j]) >= th && j < lim) ? 1 : 0;
+            int w = atomicAdd(p.cand_count + row, cnt);
             float* cs = p.cand_scores + (long long)row * p.cap;
             int32_t* cr = p.cand_rows + (long long)row * p.cap;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float sc = __uint_as_float(v[j]);
-              if (sc >= th && c0 + j < p.n) {   // rows past n are TMA zero fill, not catalog rows
-                const int slot = atomicAdd(p.cand_count + row, 1);
-                if (slot < p.cap) {
-                  cs[slot] = sc;
-                  cr[slot] = c0 + j;
+              if (sc >= th && j < lim) {
+                if (w < p.cap) {
+                  cs[w] = sc;
+                  cr[w] = c0 + j;
                 }
+                ++w;
               }
             }
           }

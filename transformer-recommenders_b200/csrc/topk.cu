@@ -436,10 +436,16 @@ __global__ void groups_to_rows_kernel(const int64_t* __restrict__ gi, int64_t to
 //    does not depend on the order the scoring CTAs appended them in; 2. their scores recomputed with the
 //    gather-dot arithmetic of xr_logits_sampled (the arithmetic every other search path reports);
 //    3. the query's exclusion list dropped (index.py:239-247); 4. ranked by (score desc, global id asc).
+// Exactness: the survivors are ALL rows scoring >= the query's threshold.  With k_sel = k + max_excl +
+// margin selected and at most max_excl of them excluded, k + margin non-excluded rows remain and every
+// row left out scores below all of them.  When fewer than k_sel rows survived (all were selected) the
+// same holds only if k + margin of them are not excluded -- or if the threshold was -inf (nothing was
+// filtered): otherwise flag 4 tells the caller to take another path.
 __global__ void __launch_bounds__(TK_THREADS)
 filter_finalize_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ cat, int64_t n,
                        const float* __restrict__ cand_scores, const int32_t* __restrict__ cand_rows,
-                       const int32_t* __restrict__ cand_count, int64_t cap, int k_sel, int k,
+                       const int32_t* __restrict__ cand_count, int64_t cap,
+                       const float* __restrict__ thresh, int64_t thresh_stride, int k_sel, int k,
                        int64_t row_offset, const int64_t* __restrict__ offs,
                        const int64_t* __restrict__ excl, int64_t max_excl, float* __restrict__ out_scores,
                        int64_t* __restrict__ out_idx, int32_t* __restrict__ flags) {
@@ -448,6 +454,7 @@ filter_finalize_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16*
   __shared__ uint64_t s_tau;
   __shared__ int64_t s_rows[TK_MAX_K];
   __shared__ float s_sc[TK_MAX_K];
+  __shared__ int s_alive;
   TopkState st{s_keys, &s_count, &s_tau};
   const int64_t u = blockIdx.x;
   const int64_t cnt_raw = cand_count[u];
@@ -455,6 +462,7 @@ filter_finalize_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16*
   if (threadIdx.x == 0) {
     s_count = 0;
     s_tau = 0ull;
+    s_alive = 0;
     int bad = cnt_raw > cap ? 1 : 0;                                   // survivors were dropped
     if (offs && offs[u + 1] - offs[u] > max_excl) bad |= 2;            // thresholds assumed fewer exclusions
     if (bad) atomicOr(flags, bad);
@@ -485,17 +493,26 @@ filter_finalize_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16*
   const int64_t x0 = offs ? offs[u] : 0, x1 = offs ? offs[u + 1] : 0;
   int n2 = 2;
   while (n2 < c) n2 <<= 1;
+  int alive = 0;
   for (int i = threadIdx.x; i < n2; i += TK_THREADS) {
     uint64_t key = 0ull;
     if (i < c) {
       const int64_t id = s_rows[i] + row_offset;
       bool dead = false;
       for (int64_t x = x0; x < x1; ++x) dead |= (excl[x] == id);
-      if (!dead) key = make_key(s_sc[i], (uint32_t)id);
+      if (!dead) {
+        key = make_key(s_sc[i], (uint32_t)id);
+        ++alive;
+      }
     }
     s_keys[i] = key;
   }
+  alive = __reduce_add_sync(0xffffffffu, alive);
+  if ((threadIdx.x & 31) == 0 && alive) atomicAdd(&s_alive, alive);
   __syncthreads();
+  if (threadIdx.x == 0 && cnt_raw <= k_sel && s_alive < k_sel - (int)max_excl &&
+      thresh[u * thresh_stride] > -CUDART_INF_F)
+    atomicOr(flags, 4);   // too few non-excluded survivors to vouch for the rows below the threshold
   bitonic_desc(s_keys, n2);
   for (int i = threadIdx.x; i < k; i += TK_THREADS) {
     const uint64_t key = i < n2 ? s_keys[i] : 0ull;
@@ -746,12 +763,14 @@ extern "C" int xr_groups_to_rows(const int64_t* group_ids, int64_t u, int64_t kg
 
 extern "C" int xr_filter_finalize(const void* q, int64_t u, const void* catalog, int64_t n, int64_t dim,
                                   const float* cand_scores, const int32_t* cand_rows,
-                                  const int32_t* cand_count, int64_t cap, int64_t k_sel, int64_t k,
+                                  const int32_t* cand_count, int64_t cap, const float* thresh,
+                                  int64_t thresh_stride, int64_t k_sel, int64_t k,
                                   int64_t row_offset, const int64_t* excl_offsets, const int64_t* excl_ids,
                                   int64_t max_excl, float* out_scores, int64_t* out_idx, int32_t* flags,
                                   void* stream) {
-  XR_CHECK_ARG(q && catalog && cand_scores && cand_rows && cand_count && out_scores && out_idx && flags,
+  XR_CHECK_ARG(q && catalog && cand_scores && cand_rows && cand_count && thresh && out_scores && out_idx && flags,
                "xr_filter_finalize: null pointer");
+  XR_CHECK_ARG(max_excl >= 0 && k_sel >= k + max_excl, "xr_filter_finalize: k_sel must be >= k + max_excl");
   XR_CHECK_ARG(dim == FD, "xr_filter_finalize: this build is specialised for dim = %d", FD);
   XR_CHECK_ARG(u >= 0 && n > 0 && cap >= 1 && k >= 1 && k_sel >= k && k_sel <= TK_MAX_K,
                "xr_filter_finalize: needs 1 <= k <= k_sel <= %d", TK_MAX_K);
@@ -760,7 +779,7 @@ extern "C" int xr_filter_finalize(const void* q, int64_t u, const void* catalog,
   if (u == 0) return XR_OK;
   filter_finalize_kernel<<<(unsigned)u, TK_THREADS, 0, as_stream(stream)>>>(
       (const __nv_bfloat16*)q, (const __nv_bfloat16*)catalog, n, cand_scores, cand_rows, cand_count, cap,
-      (int)k_sel, (int)k, row_offset, excl_offsets, excl_ids, max_excl, out_scores, out_idx, flags);
+      thresh, thresh_stride, (int)k_sel, (int)k, row_offset, excl_offsets, excl_ids, max_excl, out_scores, out_idx, flags);
   XR_LAUNCH_CHECK("filter_finalize");
   return XR_OK;
 }
@@ -770,13 +789,16 @@ namespace xr {
 constexpr int64_t kFilterCap = 32768;   // survivor slots per query
 constexpr int kFilterMargin = 28;       // rank positions of slack between the two score arithmetics
 struct ScoreTopkPlan {
-  int64_t kk, stride, ld_s, cap;
+  int64_t kk, k_sel, stride, ld_s, cap;
   size_t off_gmax, off_tkws, off_vals, off_idx, off_cs, off_cr, off_cnt, bytes, tkws_bytes;
 };
 static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 static ScoreTopkPlan plan_score_topk(int64_t u, int64_t n, int64_t k, int64_t max_excl) {
   ScoreTopkPlan pl{};
-  pl.kk = k + max_excl + kFilterMargin;
+  // threshold = the (k + margin)-th largest group maximum of the sample, whatever the exclusion lists:
+  // ~ (k + margin) * stride rows survive, of which at most max_excl are excluded afterwards
+  pl.kk = k + kFilterMargin;
+  pl.k_sel = k + max_excl + kFilterMargin;
   pl.cap = kFilterCap;
   // sample stride (in tiles of the scoring kernel): the expected number of survivors is ~kk * stride, so
   // kk * stride * 3 <= cap; and the sample keeps at least 4 kk groups so that its kk-th maximum exists
@@ -846,8 +868,8 @@ extern "C" int xr_score_topk(const void* q, int64_t u, const void* catalog, int6
   if ((rc = xr_score_filter(q, u, catalog, n, dim, vals + (pl.kk - 1), pl.kk, cs, cr, cnt, pl.cap, stream)))
     return rc;
   // 3. survivors -> exact top-k
-  return xr_filter_finalize(q, u, catalog, n, dim, cs, cr, cnt, pl.cap, pl.kk, k, row_offset, excl_offsets,
-                            excl_ids, max_excl, out_scores, out_idx, flags, stream);
+  return xr_filter_finalize(q, u, catalog, n, dim, cs, cr, cnt, pl.cap, vals + (pl.kk - 1), pl.kk, pl.k_sel, k,
+                            row_offset, excl_offsets, excl_ids, max_excl, out_scores, out_idx, flags, stream);
 }
 
 extern "C" int xr_retrieval_metrics(const int64_t* rec, int64_t u, int64_t k,

@@ -474,8 +474,10 @@ def score_filter(q, catalog, thresh, cap):
     return cs, cr, cnt
 
 
-def filter_finalize(q, catalog, cs, cr, cnt, k_sel, k, row_offset=0, exclude=None, max_excl=0, flags=None):
-    dev = _require_cuda(q, catalog, cs, cr, cnt)
+def filter_finalize(q, catalog, cs, cr, cnt, thresh, k_sel, k, row_offset=0, exclude=None, max_excl=0,
+                    flags=None):
+    dev = _require_cuda(q, catalog, cs, cr, cnt, thresh)
+    thresh = thresh.contiguous().float()
     offs, ex = (None, None) if exclude is None else exclude
     u = q.size(0)
     out_s = torch.empty((u, k), dtype=torch.float32, device=dev)
@@ -484,8 +486,8 @@ def filter_finalize(q, catalog, cs, cr, cnt, k_sel, k, row_offset=0, exclude=Non
         flags = torch.zeros(1, dtype=torch.int32, device=dev)
     with _on(dev):
         N.call("xr_filter_finalize", _p(q), u, _p(catalog), catalog.size(0), q.size(1), _p(cs), _p(cr),
-               _p(cnt), cs.size(1), k_sel, k, row_offset, _p(offs), _p(ex), max_excl, _p(out_s), _p(out_i),
-               _p(flags), _stream())
+               _p(cnt), cs.size(1), _p(thresh), 1, k_sel, k, row_offset, _p(offs), _p(ex), max_excl,
+               _p(out_s), _p(out_i), _p(flags), _stream())
     return out_s, out_i, flags
 
 
