@@ -43,7 +43,7 @@ for t, n in names.items():
     div = 148 * (16 if t in (8, 9, 10) else 1)
     print(f"  tag {t}: {buf[t]:>14d}  ({buf[t] / div:>10.0f} cycles/CTA{'/warp' if t in (8, 9, 10) else ''})  {n}")
 
-tl = (ctypes.c_int64 * 512)()
+tl = (ctypes.c_int64 * 576)()
 lib.xr_fused_timeline(tl)
 base = tl[0]
 print(f"ablate mask {mask}")
@@ -51,3 +51,12 @@ print("tile: score_issue_start  issued  | epi_wake  ld_done  math_done st_done p
 for t in range(16):
     r = [tl[t * 8 + k] - base if tl[t * 8 + k] else -1 for k in range(8)]
     print(f"{t:3d}: {r[0]:8d} {r[1]:8d} | {r[2]:8d} {r[3]:8d} {r[6]:8d} {r[7]:8d} {r[4]:8d} | {r[5]:8d}")
+issued = [tl[t * 8 + 1] - base for t in range(64)]
+print("score 'issued' time of tiles 0..63, deltas:", [issued[t] - issued[t - 1] for t in range(1, 64)])
+
+k0, g0, k1, g1 = tl[512], tl[513], tl[514], tl[515]
+print(f"CTA 0: score issuer entry -> exit {k1 - k0} cycles in {g1 - g0} ns = {(k1 - k0) / max(g1 - g0, 1):.3f} GHz")
+print("item: q_loads_issued  first_q_full  last_tile_issued  drain_start  drain_end  grad_o_empty   (cycles rel. to entry)")
+for it in range(6):
+    r = [tl[520 + it * 8 + k] - k0 if tl[520 + it * 8 + k] else -1 for k in range(6)]
+    print(f"{it:3d}: {r[4]:9d} {r[0]:9d} {r[1]:9d} {r[2]:9d} {r[3]:9d} {r[5]:9d}")

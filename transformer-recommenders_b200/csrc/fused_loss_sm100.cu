@@ -80,9 +80,9 @@ struct FusedParams {
   const float* t;      // [m] target logits (raw fp32)           (loss modes)
   const float* zref;   // [m] softmax reference maximum, nullable (defaults to scaled t)
   float* t_out;        // [m]                                      (KIND_DIAG)
-  float* part_o;       // [n_items][128][384]
-  float* part_s;       // [n_items][128][NSCAL]
-  float* part_all;     // [n_items][CG][128][NSCAL_ALL]            (KIND_ALL_*)
+  float* part_o;       // [slots][96 four-column groups][128 rows][4]  partial dQ of every segment
+  float* part_s;       // [slots][CG][128][NSCAL]
+  float* part_all;     // [slots][CG][128][NSCAL_ALL]              (KIND_ALL_*)
   float* gmax;         // [m][gmax_ld] group maxima                (KIND_GMAX)
   long long gmax_ld;
   int tile_stride;     // KIND_GMAX: only every tile_stride-th 64-row catalog tile is scored (0 = 1)
@@ -95,6 +95,7 @@ struct FusedParams {
   int rb_count;
   int* hang_flag;
   long long* dbg;      // STATS builds: per-tile timestamps of CTA 0 (profiling aid)
+  int ctrl_low;        // profiling aid: control roles on hardware warps 0-3 (the round-1 placement)
   int ablate;          // STATS builds: 1 skip TMA loads, 2 skip epilogue math, 4 skip score MMAs, 8 skip dQ MMAs, 16 skip epilogue TMEM ld/st
 };
 
@@ -265,7 +266,13 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
   auto bar_w_free = [&](int b) { return bars + 8u * (2 * PAIRS + 10 + b); };  // dQ(tile) consumed W
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + BAR_OFF + NBARS * 8);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // `warp` is the ROLE index (0 TMA producer, 1 score issuer + TMEM owner, 2 gradient issuer, 3 spare,
+  // 4..19 epilogue).  The warp scheduler serves the highest warp id first among eligible warps, so the
+  // control roles sit on hardware warps 16-19: the epilogue's instruction bursts must not starve the MMA
+  // issue stream (an interrupted stream costs ~200 cycles of tensor pipe each time).  Epilogue warp w
+  // keeps w % 4 = its TMEM lane quadrant either way.
+  const int hw_warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = p.ctrl_low ? hw_warp : (hw_warp >= EPI_WARPS ? hw_warp - EPI_WARPS : hw_warp + 4);
   constexpr bool diag = (KIND == KIND_DIAG);
   // shape and plan: launch constants, or read from device memory (sync-free step)
   FusedDyn sh{p.m, p.cn, p.nt_count, p.spl, p.tiles_per_split, p.n_items, p.rb_count, 0};
@@ -277,6 +284,22 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
   constexpr bool all_kind = (KIND == KIND_ALL_DOT || KIND == KIND_ALL_COS);
   constexpr bool retr = (KIND == KIND_GMAX || KIND == KIND_FILTER);   // retrieval scoring: no loss, no gradient
   const int ts = (KIND == KIND_GMAX && p.tile_stride > 1) ? p.tile_stride : 1;
+  // Loss kinds ("pool" kinds: train + all-losses) run STREAM-K: the rb_count x nt_count (row block, tile)
+  // pairs form one linear range, split evenly over the CTAs, so every CTA sweeps the same number of tiles
+  // (+-1) whatever M and C are (the (row block, split) items of round 1 left a ragged second wave: 134
+  // tiles on the busiest CTA against 127.7 on average at configs[1]).  A CTA's range crosses row-block
+  // boundaries; each piece inside one row block is a SEGMENT with its own partial sums in slot
+  // blockIdx.x + rb -- unique, because along the linear order either the CTA or the row block advances.
+  constexpr bool pool = !diag && !retr;
+  long long sk_lo = 0, sk_hi = 0;
+  if (pool) {
+    const long long TT = (long long)sh.rb_count * sh.nt_count;
+    const long long G = TT < (long long)gridDim.x ? TT : (long long)gridDim.x;
+    if ((long long)blockIdx.x < G) {
+      sk_lo = TT * blockIdx.x / G;
+      sk_hi = TT * (blockIdx.x + 1) / G;
+    }
+  }
   const bool grad = !diag && !retr && !all_kind && p.with_grad;
   // S buffers: ONE with the gradient pass (the other 64 columns hold the W double buffer), two without
   const int nsb_shift = grad ? 0 : 1;
@@ -309,17 +332,23 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_smem;
+  auto gtime = [] {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return (long long)t;
+  };
+  const bool dbg0 = ABL && p.dbg && blockIdx.x == 0 && lane == 0;
+  if (dbg0 && warp == 1) {
+    p.dbg[512 + 0] = clock64();
+    p.dbg[512 + 1] = gtime();
+  }
 
   // work items: (row block, split of the candidate tiles); identical iteration in every role
   // the tiles of an item are visited in a rotated order that depends on the row block, so the
   // CTAs sweeping the same candidate range do not hammer the same L2 lines in lockstep
-  auto rot_tile = [&](int t0, int T, int rb, int tl) {
-    if (diag || retr) return t0 + tl;   // retrieval: row blocks share catalog tiles via L2
-    const int r = (int)(((unsigned)rb * 29u) % (unsigned)T);
-    int x = tl + r;
-    if (x >= T) x -= T;
-    return t0 + x;
-  };
+  // (stream-K segments of neighbouring CTAs start ~nt/G tiles apart, so CTAs do not sweep the pool in
+  //  lockstep; retrieval row blocks WANT to share catalog tiles through L2)
+  auto rot_tile = [&](int t0, int, int, int tl) { return t0 + tl; };
   auto item_tiles = [&](int item, int& rb, int& t0, int& t1) {
     if (diag) {
       rb = item;
@@ -340,13 +369,35 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
   };
 
+  struct WorkIt {
+    long long x;
+    int item;
+  };
+  auto work_next = [&](WorkIt& w, int& rb, int& t0, int& t1, int& slot) -> bool {
+    if (pool) {
+      if (w.x >= sk_hi) return false;
+      rb = (int)(w.x / sh.nt_count);
+      t0 = (int)(w.x - (long long)rb * sh.nt_count);
+      const long long rem = sk_hi - w.x;
+      t1 = (long long)t0 + rem < (long long)sh.nt_count ? t0 + (int)rem : sh.nt_count;
+      slot = (int)blockIdx.x + rb;
+      w.x += t1 - t0;
+      return true;
+    }
+    if (w.item >= sh.n_items) return false;
+    item_tiles(w.item, rb, t0, t1);
+    slot = w.item;
+    w.item += gridDim.x;
+    return true;
+  };
+  WorkIt wk{sk_lo, (int)blockIdx.x};
+  int rb, t0, t1, slot;
+
   if (warp == 0) {
     // ================================ TMA producer ================================
     // the whole warp walks the loop (warp-uniform control flow); one elected lane issues
     uint32_t g = 0, it = 0;
-    for (int item = blockIdx.x; item < sh.n_items; item += gridDim.x, ++it) {
-      int rb, t0, t1;
-      item_tiles(item, rb, t0, t1);
+    for (; work_next(wk, rb, t0, t1, slot); ++it) {
       mbar_wait<STATS>(bar_q_empty, (it & 1) ^ 1, p.hang_flag, 1);
       if (elect_one()) {
         mbar_expect_tx(bar_q_full, Q_BYTES);
@@ -354,6 +405,7 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
           tma_load_2d(q_smem + kb * QSUB_BYTES, &tmap_q, bar_q_full, kb * 64, rb * BM);
       }
       __syncwarp();
+      if (dbg0 && it < 6) p.dbg[520 + it * 8 + 4] = clock64();
       for (int tl = 0; tl < t1 - t0; ++tl) {
         const int t = rot_tile(t0, t1 - t0, rb, tl);
 #pragma unroll 1
@@ -386,11 +438,10 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
     const uint64_t q_desc0 = umma_desc_sw128(q_smem, 16, 1024);
     const uint64_t ring_k_desc0 = umma_desc_sw128(ring, 16, 1024);
     uint32_t g = 0, tt = 0, it = 0;
-    for (int item = blockIdx.x; item < sh.n_items; item += gridDim.x, ++it) {
-      int rb, t0, t1;
-      item_tiles(item, rb, t0, t1);
+    for (; work_next(wk, rb, t0, t1, slot); ++it) {
       const int T = t1 - t0;
       mbar_wait<STATS>(bar_q_full, it & 1, p.hang_flag, 4);
+      if (dbg0 && it < 6) p.dbg[520 + it * 8 + 0] = clock64();
       for (int tl = 0; tl < T; ++tl) {
         const uint32_t tile = tt + tl;
         const uint32_t use = tile >> nsb_shift;            // how often this S buffer was used before
@@ -437,8 +488,13 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
         __syncwarp();
         g += KB / 2;
         if (ABL && p.dbg && blockIdx.x == 0 && lane == 0 && tile < 64) p.dbg[tile * 8 + 1] = clock64();
+        if (dbg0 && it < 6 && tl == T - 1) p.dbg[520 + it * 8 + 1] = clock64();
       }
       tt += T;
+    }
+    if (dbg0) {
+      p.dbg[512 + 2] = clock64();
+      p.dbg[512 + 3] = gtime();
     }
   } else if (warp == 2) {
     // ========================= gradient MMA issuer: dQ += W . Neg =========================
@@ -451,11 +507,10 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
       // MN-major view of a pair: two 64-column atoms SUB_BYTES apart, 8-row groups of 1 KB
       const uint64_t ring_mn_desc0 = umma_desc_sw128(ring, SUB_BYTES, 1024);
       uint32_t g = 0, tt = 0, it = 0;
-      for (int item = blockIdx.x; item < sh.n_items; item += gridDim.x, ++it) {
-        int rb, t0, t1;
-        item_tiles(item, rb, t0, t1);
+      for (; work_next(wk, rb, t0, t1, slot); ++it) {
         const int T = t1 - t0;
         mbar_wait<STATS>(bar_o_empty, (it & 1) ^ 1, p.hang_flag, 5);   // epilogue drained the last dQ
+        if (dbg0 && it < 6) p.dbg[520 + it * 8 + 5] = clock64();
         for (int tl = 0; tl < T; ++tl, g += KB / 2) {
           const uint32_t tile = tt + tl;
           const int wb = tile & 1;
@@ -495,9 +550,7 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
     const bool round_scaled = RBF && p.scale != 1.0f;
     const float scale2 = p.scale * kLog2e;
     uint32_t tt = 0, it = 0;
-    for (int item = blockIdx.x; item < sh.n_items; item += gridDim.x, ++it) {
-      int rb, t0, t1;
-      item_tiles(item, rb, t0, t1);
+    for (; work_next(wk, rb, t0, t1, slot); ++it) {
       const int T = t1 - t0;
       const int row = rb * BM + r_local;
       const bool row_ok = row < sh.m;
@@ -636,7 +689,7 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
       } else if (all_kind) {
         if (row_ok) {
           float4* ds = reinterpret_cast<float4*>(
-              p.part_all + (((size_t)item * CG + cg) * BM + r_local) * NSCAL_ALL);
+              p.part_all + (((size_t)slot * CG + cg) * BM + r_local) * NSCAL_ALL);
           ds[0] = make_float4(acc.cnt, acc.s_exp, acc.s_sp, acc.s_hinge);
           ds[1] = make_float4(acc.s_logi, acc.s_contr, acc.s_v, acc.s_sq);
           ds[2] = make_float4(acc.vmin, acc.vmax, 0.f, 0.f);
@@ -645,24 +698,31 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (grad) {
           mbar_wait<STATS>(bar_o_full, it & 1, p.hang_flag, 9);
           tc_fence_after();
-          float* dst = p.part_o + ((size_t)item * BM + r_local) * D + cg * (D / CG);
+          if (dbg0 && warp == 4 && it < 6) p.dbg[520 + it * 8 + 2] = clock64();
+          // the partial dQ leaves in a BLOCKED layout [4-column group (96)][row (128)][4 floats]: lane =
+          // row, so the 16-byte stores of a warp are 512 contiguous bytes.  (Row-major rows scattered
+          // every store instruction over 32 lines: 22k cycles per drain, 12 % of the kernel, measured.)
+          float* dst = p.part_o + (size_t)slot * BM * D + (size_t)r_local * 4;
 #pragma unroll 1
           for (int c = 0; c < D / CG / 32; ++c) {
             uint32_t o[32];
             tmem_ld32(tmem_lane + COL_O + cg * (D / CG) + c * 32, o);
             tmem_wait_ld();
             if (row_ok) {
+              const int c4 = (cg * (D / CG) + c * 32) / 4;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<uint4*>(dst + c * 32 + j) = make_uint4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4*>(dst + (size_t)(c4 + j) * (BM * 4)) =
+                    make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
             }
           }
           tc_fence_before();
           __syncwarp();
+          if (dbg0 && warp == 4 && it < 6) p.dbg[520 + it * 8 + 3] = clock64();
           if (lane == 0) mbar_arrive(bar_o_empty);
         }
         if (row_ok) {
-          float* ds = p.part_s + (((size_t)item * CG + cg) * BM + r_local) * NSCAL;
+          float* ds = p.part_s + (((size_t)slot * CG + cg) * BM + r_local) * NSCAL;
           *reinterpret_cast<float4*>(ds) = make_float4(cnt, sum_a, sum_w, 0.f);
         }
       }
@@ -677,153 +737,192 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
   }
 }
 
-// ---- finalize: fold the per-item partials, apply the per-row normalisers and the positive's
-//      term, chain through the query normalisation for the cosine kinds (one warp per row) ------
+// stream-K bookkeeping shared by the kernel above and the finalize kernels: CTA c of G sweeps the linear
+// tile range [TT c / G, TT (c + 1) / G); the CTA that holds linear tile x is the largest c whose range
+// starts at or before x
+__host__ __device__ inline int sk_owner(long long x, long long TT, long long G) {
+  return (int)(((x + 1) * G + TT - 1) / TT - 1);
+}
+struct SkRange {
+  int c_first, c_last;
+};
+__device__ __forceinline__ SkRange sk_segments(int rb, int nt, int rb_count, int grid) {
+  const long long TT = (long long)rb_count * nt;
+  const long long G = TT < (long long)grid ? TT : (long long)grid;
+  return SkRange{sk_owner((long long)rb * nt, TT, G), sk_owner((long long)(rb + 1) * nt - 1, TT, G)};
+}
+
+// ---- finalize: fold the per-segment partials, apply the per-row normalisers and the positive's
+//      term, chain through the query normalisation for the cosine kinds.  A block takes FR consecutive
+//      rows: phase A sums their partial dQ over the segments of their row block (fixed order:
+//      deterministic) straight from the blocked layout -- 16-byte loads, 256 contiguous bytes per
+//      half-warp -- into shared memory; phase B finishes the rows, one warp per row ------------------
+constexpr int FR = 16;
 __global__ void __launch_bounds__(256)
 fused_finalize_kernel(const float* __restrict__ part_o, const float* __restrict__ part_s,
                       const float* __restrict__ t_raw, const float* __restrict__ zref,
                       const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ pos,
-                      const float* __restrict__ q_inv, int m, int spl, int kind, int logits_bf16,
+                      const float* __restrict__ q_inv, int m, int cn, int grid, int kind, int logits_bf16,
                       float scale, float margin, float grad_scale, float* __restrict__ dq,
                       float* __restrict__ row_loss, const FusedDyn* __restrict__ dyn,
-                      const int64_t* __restrict__ inv_pos, int64_t n_pos, void* __restrict__ dtok,
-                      int dtok_bf16) {
+                      const int64_t* __restrict__ inv_pos, const int64_t* __restrict__ sel_pos,
+                      int64_t n_pos, void* __restrict__ dtok, int dtok_bf16) {
   using namespace fk;
+  __shared__ float s_o[FR][D + 4];
+  __shared__ float s_sc[FR][4];
   if (dyn) {
     m = dyn->m;
-    spl = dyn->spl;
+    cn = dyn->cn;
   }
-  // scatter mode (xr_pool_step): walk the B*L POSITIONS; position p holds row inv_pos[p] of the
-  // compacted order or none (zero gradient row) -- the autograd of token_embeddings[mask][pos_mask]
-  // (models.py:392, 415) folded into this kernel, in the encoder output's own layout and dtype
+  const int rb_count = (m + BM - 1) / BM, nt = (cn + BN - 1) / BN;
+  // scatter mode (xr_pool_step): row i of the compacted order goes to position sel_pos[i] of the
+  // encoder output's own layout and dtype; positions that hold no row get a zero gradient row -- the
+  // autograd of token_embeddings[mask][pos_mask] (models.py:392, 415) folded into this kernel
   const bool scatter = dtok != nullptr;
-  const int64_t n_iter = scatter ? n_pos : (int64_t)m;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool want_o = dq || scatter;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool cosine = kind == XR_LOSS_CONTRASTIVE || kind == XR_LOSS_ALIGNMENT_CONTRASTIVE;
-  // each lane owns the column PAIRS {64 c + 2 lane, +1}: 8-byte partial loads, 4-byte bf16x2 /
-  // 8-byte fp32 stores -> full 128 / 256-byte warp transactions
-  constexpr int NP = D / 64;
-  for (int64_t it = warp; it < n_iter; it += nwarps) {
-    int64_t i = it;
-    if (scatter) {
-      i = inv_pos[it];
-      if (i < 0) {
-        if (dtok_bf16) {
-          uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(dtok) + it * D);
-#pragma unroll
-          for (int c = 0; c < NP; ++c) dst[c * 32 + lane] = 0u;
-        } else {
-          float2* dst = reinterpret_cast<float2*>(reinterpret_cast<float*>(dtok) + it * D);
-#pragma unroll
-          for (int c = 0; c < NP; ++c) dst[c * 32 + lane] = make_float2(0.f, 0.f);
+  constexpr int NP = D / 64;   // each lane owns the column PAIRS {64 c + 2 lane, +1}
+  const int n_groups = (m + FR - 1) / FR;
+  for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+    const int row0 = g * FR;
+    const int rb = row0 / BM, rl0 = row0 % BM;
+    const SkRange sr = sk_segments(rb, nt, rb_count, grid);
+    // ---- phase A ----
+    if (want_o) {
+      const int r = threadIdx.x & (FR - 1);
+      for (int c4 = threadIdx.x / FR; c4 < D / 4; c4 += 256 / FR) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = sr.c_first; c <= sr.c_last; ++c) {   // fixed order: deterministic
+          const float4 v = *reinterpret_cast<const float4*>(
+              part_o + (size_t)(c + rb) * BM * D + ((size_t)c4 * BM + rl0 + r) * 4);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
-        continue;
+        *reinterpret_cast<float4*>(&s_o[r][c4 * 4]) = acc;
       }
     }
-    const int rb = (int)(i / BM), rl = (int)(i % BM);
-    float cnt = 0.f, sum_a = 0.f, sum_w = 0.f;
-    float2 o[NP];
+    if (threadIdx.x < FR) {
+      float cnt = 0.f, sum_a = 0.f, sum_w = 0.f;
+      for (int c = sr.c_first; c <= sr.c_last; ++c) {
 #pragma unroll
-    for (int c = 0; c < NP; ++c) o[c] = make_float2(0.f, 0.f);
-    for (int sp = 0; sp < spl; ++sp) {   // fixed order: deterministic
-      const size_t item = (size_t)rb * spl + sp;
-#pragma unroll
-      for (int cg = 0; cg < CG; ++cg) {
-        const float4 s = *reinterpret_cast<const float4*>(part_s + ((item * CG + cg) * BM + rl) * NSCAL);
-        cnt += s.x; sum_a += s.y; sum_w += s.z;
+        for (int cg = 0; cg < CG; ++cg) {
+          const float4 v = *reinterpret_cast<const float4*>(
+              part_s + (((size_t)(c + rb) * CG + cg) * BM + rl0 + threadIdx.x) * NSCAL);
+          cnt += v.x; sum_a += v.y; sum_w += v.z;
+        }
       }
-      if (dq || scatter) {
-        const float2* src = reinterpret_cast<const float2*>(part_o + (item * BM + rl) * D);
+      s_sc[threadIdx.x][0] = cnt;
+      s_sc[threadIdx.x][1] = sum_a;
+      s_sc[threadIdx.x][2] = sum_w;
+    }
+    __syncthreads();
+    // ---- phase B ----
+    for (int r = warp; r < FR; r += 8) {
+      const int64_t i = row0 + r;
+      if (i >= m) break;
+      const float cnt = s_sc[r][0], sum_a = s_sc[r][1], sum_w = s_sc[r][2];
+      float t = t_raw[i];
+      if (logits_bf16) t = bf16_round(t);
+      const float den = cnt + 1e-9f;
+      float loss = 0.f, co = 0.f, cp = 0.f;   // dq = co * O + cp * pos
+      switch (kind) {
+        case XR_LOSS_INFONCE: {
+          const float st = (logits_bf16 && scale != 1.0f) ? bf16_round(t * scale) : t * scale;
+          const float zr = zref ? zref[i] : st;
+          const float et = __expf(st - zr);
+          const float zall = sum_w + et;
+          loss = zr + __logf(zall) - st;
+          co = scale / zall;
+          cp = scale * (et / zall - 1.0f);
+          break;
+        }
+        case XR_LOSS_NCE: {
+          const float at = fabsf(t);
+          loss = fmaxf(-t, 0.f) + log1pf(__expf(-at)) + sum_a / den;
+          co = 1.0f / den;
+          cp = -1.0f / (1.0f + __expf(t));
+          break;
+        }
+        case XR_LOSS_PAIRWISE_HINGE:
+        case XR_LOSS_PAIRWISE_LOGISTIC:
+          loss = sum_a / den;
+          co = 1.0f / den;
+          cp = -(1.0f - margin) * sum_w / den;
+          break;
+        case XR_LOSS_CONTRASTIVE:
+          loss = sum_a / den;
+          co = 1.0f / den;
+          break;
+        case XR_LOSS_ALIGNMENT_CONTRASTIVE:
+          loss = sum_a / den + (1.0f - t);
+          co = 1.0f / den;
+          cp = -1.0f;
+          break;
+        default:
+          break;
+      }
+      if (lane == 0 && row_loss) row_loss[i] = loss;
+      if (want_o) {
+        float2 gr[NP];
+        float dot = 0.f;
+        const __nv_bfloat162* pos2 = reinterpret_cast<const __nv_bfloat162*>(pos + i * D);
+        const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(q + i * D);
 #pragma unroll
         for (int c = 0; c < NP; ++c) {
-          const float2 v = src[c * 32 + lane];
-          o[c].x += v.x;
-          o[c].y += v.y;
+          const float2 o = *reinterpret_cast<const float2*>(&s_o[r][c * 64 + 2 * lane]);
+          const float2 pv = __bfloat1622float2(pos2[c * 32 + lane]);
+          gr[c].x = co * o.x + cp * pv.x;
+          gr[c].y = co * o.y + cp * pv.y;
+          if (cosine) {
+            const float2 qv = __bfloat1622float2(q2[c * 32 + lane]);
+            dot = fmaf(gr[c].x, qv.x, dot);
+            dot = fmaf(gr[c].y, qv.y, dot);
+          }
         }
-      }
-    }
-    float t = t_raw[i];
-    if (logits_bf16) t = bf16_round(t);
-    const float den = cnt + 1e-9f;
-    float loss = 0.f, co = 0.f, cp = 0.f;   // dq = co * O + cp * pos
-    switch (kind) {
-      case XR_LOSS_INFONCE: {
-        const float st = (logits_bf16 && scale != 1.0f) ? bf16_round(t * scale) : t * scale;
-        const float zr = zref ? zref[i] : st;
-        const float et = __expf(st - zr);
-        const float zall = sum_w + et;
-        loss = zr + __logf(zall) - st;
-        co = scale / zall;
-        cp = scale * (et / zall - 1.0f);
-        break;
-      }
-      case XR_LOSS_NCE: {
-        const float at = fabsf(t);
-        loss = fmaxf(-t, 0.f) + log1pf(__expf(-at)) + sum_a / den;
-        co = 1.0f / den;
-        cp = -1.0f / (1.0f + __expf(t));
-        break;
-      }
-      case XR_LOSS_PAIRWISE_HINGE:
-      case XR_LOSS_PAIRWISE_LOGISTIC:
-        loss = sum_a / den;
-        co = 1.0f / den;
-        cp = -(1.0f - margin) * sum_w / den;
-        break;
-      case XR_LOSS_CONTRASTIVE:
-        loss = sum_a / den;
-        co = 1.0f / den;
-        break;
-      case XR_LOSS_ALIGNMENT_CONTRASTIVE:
-        loss = sum_a / den + (1.0f - t);
-        co = 1.0f / den;
-        cp = -1.0f;
-        break;
-      default:
-        break;
-    }
-    if (lane == 0 && row_loss) row_loss[i] = loss;
-    if (dq || scatter) {
-      float2 g[NP];
-      float dot = 0.f;
-      const __nv_bfloat162* pos2 = reinterpret_cast<const __nv_bfloat162*>(pos + i * D);
-      const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(q + i * D);
-#pragma unroll
-      for (int c = 0; c < NP; ++c) {
-        const float2 pv = __bfloat1622float2(pos2[c * 32 + lane]);
-        g[c].x = co * o[c].x + cp * pv.x;
-        g[c].y = co * o[c].y + cp * pv.y;
         if (cosine) {
-          const float2 qv = __bfloat1622float2(q2[c * 32 + lane]);
-          dot = fmaf(g[c].x, qv.x, dot);
-          dot = fmaf(g[c].y, qv.y, dot);
+          dot = warp_sum(dot);
+          const float inv = q_inv[i];
+#pragma unroll
+          for (int c = 0; c < NP; ++c) {
+            const float2 qv = __bfloat1622float2(q2[c * 32 + lane]);
+            gr[c].x = inv * (gr[c].x - dot * qv.x);
+            gr[c].y = inv * (gr[c].y - dot * qv.y);
+          }
+        }
+        if (!scatter) {
+          float2* dst = reinterpret_cast<float2*>(dq + i * D);
+#pragma unroll
+          for (int c = 0; c < NP; ++c) dst[c * 32 + lane] = make_float2(gr[c].x * grad_scale, gr[c].y * grad_scale);
+        } else {
+          const int64_t where = sel_pos[i];
+          if (dtok_bf16) {
+            __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(dtok) + where * D);
+#pragma unroll
+            for (int c = 0; c < NP; ++c)
+              dst[c * 32 + lane] = __floats2bfloat162_rn(gr[c].x * grad_scale, gr[c].y * grad_scale);
+          } else {
+            float2* dst = reinterpret_cast<float2*>(reinterpret_cast<float*>(dtok) + where * D);
+#pragma unroll
+            for (int c = 0; c < NP; ++c) dst[c * 32 + lane] = make_float2(gr[c].x * grad_scale, gr[c].y * grad_scale);
+          }
         }
       }
-      if (cosine) {
-        dot = warp_sum(dot);
-        const float inv = q_inv[i];
+    }
+    __syncthreads();
+  }
+  if (scatter) {   // zero rows for the positions that hold no row
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t it = gw; it < n_pos; it += nw) {
+      if (inv_pos[it] >= 0) continue;
+      if (dtok_bf16) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(dtok) + it * D);
 #pragma unroll
-        for (int c = 0; c < NP; ++c) {
-          const float2 qv = __bfloat1622float2(q2[c * 32 + lane]);
-          g[c].x = inv * (g[c].x - dot * qv.x);
-          g[c].y = inv * (g[c].y - dot * qv.y);
-        }
-      }
-      if (!scatter) {
-        float2* dst = reinterpret_cast<float2*>(dq + i * D);
-#pragma unroll
-        for (int c = 0; c < NP; ++c) dst[c * 32 + lane] = make_float2(g[c].x * grad_scale, g[c].y * grad_scale);
-      } else if (dtok_bf16) {
-        __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(dtok) + it * D);
-#pragma unroll
-        for (int c = 0; c < NP; ++c)
-          dst[c * 32 + lane] = __floats2bfloat162_rn(g[c].x * grad_scale, g[c].y * grad_scale);
+        for (int c = 0; c < NP; ++c) dst[c * 32 + lane] = 0u;
       } else {
         float2* dst = reinterpret_cast<float2*>(reinterpret_cast<float*>(dtok) + it * D);
 #pragma unroll
-        for (int c = 0; c < NP; ++c) dst[c * 32 + lane] = make_float2(g[c].x * grad_scale, g[c].y * grad_scale);
+        for (int c = 0; c < NP; ++c) dst[c * 32 + lane] = make_float2(0.f, 0.f);
       }
     }
   }
@@ -834,21 +933,22 @@ fused_finalize_kernel(const float* __restrict__ part_o, const float* __restrict_
 //      rowloss_kernel (rowloss.cu), which is the materialised-logits implementation of this pass ----
 __global__ void __launch_bounds__(256)
 fused_finalize_all_kernel(const float* __restrict__ part_all, const float* __restrict__ t_raw,
-                          const float* __restrict__ zref, int m, int spl, int cosine, int logits_bf16,
+                          const float* __restrict__ zref, int m, int cn, int grid, int cosine, int logits_bf16,
                           float scale, float margin, double* __restrict__ row_out,
                           const FusedDyn* __restrict__ dyn) {
   using namespace fk;
   if (dyn) {
     m = dyn->m;
-    spl = dyn->spl;
+    cn = dyn->cn;
   }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const int rb = i / BM, rl = i % BM;
+  const SkRange sr = sk_segments(rb, (cn + BN - 1) / BN, (m + BM - 1) / BM, grid);
   double cnt = 0, s_exp = 0, s_sp = 0, s_hinge = 0, s_logi = 0, s_contr = 0, s_v = 0, s_sq = 0;
   float vmin = CUDART_INF_F, vmax = -CUDART_INF_F;
-  for (int sp = 0; sp < spl; ++sp) {
-    const size_t item = (size_t)rb * spl + sp;
+  for (int seg = sr.c_first; seg <= sr.c_last; ++seg) {   // the segments of this row block, fixed order
+    const size_t item = (size_t)(seg + rb);
 #pragma unroll
     for (int cg = 0; cg < CG; ++cg) {
       const float4* src = reinterpret_cast<const float4*>(part_all + ((item * CG + cg) * BM + rl) * NSCAL_ALL);
@@ -987,115 +1087,58 @@ int make_tmap_bf16_rows(CUtensorMap* out, const void* base, int64_t rows, int64_
   return XR_OK;
 }
 
+// Loss kinds: stream-K (see the kernel).  Nothing to search for: the plan is the shape itself.
+//   rb row blocks x nt candidate tiles = `tiles` units, split evenly over grid = min(#SMs, tiles) CTAs;
+//   segment slots (partial sums) = grid + rb - 1.  The same integer arithmetic runs in the kernels.
 struct FusedPlan {
-  int rb, nt, spl, tps, n_items;
+  int rb, nt, grid, slots;
+  long long tiles;
 };
-// work items = (128-row block, split of the candidate tiles).  Chooses the split that minimises
-// (waves x (tiles per item + per-item overhead)) so the persistent grid of n_sm CTAs stays
-// balanced for any M, among the splits with at most max(4 n_sm, rb) items (bounds the partial
-// buffers).  Integer arithmetic only: the SAME function runs on the host (xr_fused_pool_loss) and
-// on the device (xr_pool_step), so both paths fold their partial sums in the same order.
-__host__ __device__ inline int fused_item_cap(int n_sm) { return 4 * n_sm; }
-constexpr int kMaxSplits = 160;   // >= the SM count: one or two row blocks can still fill the machine
-// cost of splitting the nt candidate tiles s ways (-1: not allowed); s_eff = splits actually used
-__host__ __device__ inline long long plan_cost(int rb, int nt, int s, int n_sm, int& s_eff) {
-  const int tps = (nt + s - 1) / s;
-  s_eff = (nt + tps - 1) / tps;
-  const long long cap = fused_item_cap(n_sm) > rb ? fused_item_cap(n_sm) : rb;
-  const long long items = (long long)rb * s_eff;
-  if (items > cap && s_eff > 1) return -1;
-  const long long waves = (items + n_sm - 1) / n_sm;
-  return waves * (tps + 3);
-}
-__host__ __device__ inline FusedPlan finish_plan(int rb, int nt, int best_spl) {
+static inline FusedPlan make_plan(long long m, long long cn, int n_sm) {
   FusedPlan pl;
-  pl.rb = rb; pl.nt = nt;
-  pl.spl = best_spl;
-  pl.tps = (nt + pl.spl - 1) / pl.spl;
-  pl.spl = (nt + pl.tps - 1) / pl.tps;
-  pl.n_items = rb * pl.spl;
+  pl.rb = (int)((m + fk::BM - 1) / fk::BM);
+  pl.nt = (int)((cn + fk::BN - 1) / fk::BN);
+  if (pl.rb < 0) pl.rb = 0;
+  if (pl.nt < 0) pl.nt = 0;
+  pl.tiles = (long long)pl.rb * pl.nt;
+  pl.grid = (int)(pl.tiles < n_sm ? pl.tiles : n_sm);
+  if (pl.grid < 1) pl.grid = 1;
+  pl.slots = pl.grid + (pl.rb > 0 ? pl.rb - 1 : 0);
   return pl;
 }
-__host__ __device__ inline FusedPlan make_plan(long long m, long long cn, int n_sm) {
-  const int rb = (int)((m + fk::BM - 1) / fk::BM);
-  const int nt = (int)((cn + fk::BN - 1) / fk::BN);
-  if (rb <= 0 || nt <= 0) {
-    FusedPlan pl;
-    pl.rb = rb > 0 ? rb : 0;
-    pl.nt = nt > 0 ? nt : 0;
-    pl.spl = 1; pl.tps = pl.nt; pl.n_items = 0;
-    return pl;
-  }
-  long long best = -1;
-  int best_spl = 1;
-  const int max_spl = nt < kMaxSplits ? nt : kMaxSplits;
-  for (int s = 1; s <= max_spl; ++s) {   // first minimum wins (smallest s)
-    int s_eff;
-    const long long cost = plan_cost(rb, nt, s, n_sm, s_eff);
-    if (cost < 0) continue;
-    if (best < 0 || cost < best) {
-      best = cost;
-      best_spl = s_eff;
-    }
-  }
-  return finish_plan(rb, nt, best_spl);
-}
-// retrieval scoring (KIND_GMAX) writes no partial sums, so nothing bounds the number of splits: a
-// few work items per SM whatever the number of query blocks (make_plan's 64-split limit left 84 of
-// 148 SMs idle for U <= 128: 3.5 TB/s of catalog instead of HBM speed)
-static inline FusedPlan make_gmax_plan(long long u, long long n, int n_sm) {
-  const int rb = (int)((u + fk::BM - 1) / fk::BM);
-  const int nt = (int)((n + fk::BN - 1) / fk::BN);
-  long long spl = ((long long)n_sm * 4 + rb - 1) / rb;
-  if (spl > nt) spl = nt;
-  if (spl < 1) spl = 1;
-  return finish_plan(rb, nt, (int)spl);
-}
-// upper bound of make_plan(m, cn).n_items over all m <= m_max (any cn)
-static long long max_plan_items(long long m_max, int n_sm) {
-  const long long rb = (m_max + fk::BM - 1) / fk::BM;
-  return fused_item_cap(n_sm) > rb ? fused_item_cap(n_sm) : rb;
+// upper bound of make_plan(m, cn).slots over all m <= m_max (any cn)
+static long long max_plan_slots(long long m_max, int n_sm) {
+  return (long long)n_sm + (m_max + fk::BM - 1) / fk::BM;
 }
 
-// device-side planning for the sync-free step from the row counts the compaction left on the
-// device (M_a pool rows, M rows): 64 threads evaluate the 64 candidate splits in
-// parallel, thread 0 picks the first minimum exactly as the host loop does
+// retrieval scoring (KIND_GMAX / KIND_FILTER) writes no partial sums: (query block, split of the catalog
+// tiles) work items, a few per SM whatever the number of query blocks
+struct GmaxPlan {
+  int rb, nt, spl, tps, n_items;
+};
+static inline GmaxPlan make_gmax_plan(long long u, long long n, int n_sm) {
+  GmaxPlan pl;
+  pl.rb = (int)((u + fk::BM - 1) / fk::BM);
+  pl.nt = (int)((n + fk::BN - 1) / fk::BN);
+  long long spl = ((long long)n_sm * 4 + pl.rb - 1) / pl.rb;
+  if (spl > pl.nt) spl = pl.nt;
+  if (spl < 1) spl = 1;
+  pl.tps = (int)((pl.nt + spl - 1) / spl);
+  pl.spl = (pl.nt + pl.tps - 1) / pl.tps;
+  pl.n_items = pl.rb * pl.spl;
+  return pl;
+}
+
+// device-side shape record for the sync-free step, from the row counts the compaction left on the
+// device (M_a pool rows, M rows)
 struct PlanHook {
-  int n_sm;
   FusedDyn* dyn_main;
   FusedDyn* dyn_diag;
   __device__ void operator()(int m_a, int m) const {
-    __shared__ long long s_cost[kMaxSplits];
-    __shared__ int s_eff_sh[kMaxSplits];
-    const int rb = (m + fk::BM - 1) / fk::BM, nt = (m_a + fk::BN - 1) / fk::BN;
-    for (int t = threadIdx.x; t < kMaxSplits; t += blockDim.x) {
-      int s_eff = 1;
-      long long cost = -1;
-      if (rb > 0 && nt > 0 && t + 1 <= (nt < kMaxSplits ? nt : kMaxSplits))
-        cost = plan_cost(rb, nt, t + 1, n_sm, s_eff);
-      s_cost[t] = cost;
-      s_eff_sh[t] = s_eff;
-    }
-    const int t = threadIdx.x;
-    __syncthreads();
-    if (t == 0) {
-      FusedPlan pl;
-      if (rb <= 0 || nt <= 0) {
-        pl.rb = rb > 0 ? rb : 0; pl.nt = nt > 0 ? nt : 0; pl.spl = 1; pl.tps = pl.nt; pl.n_items = 0;
-      } else {
-        long long best = -1;
-        int best_spl = 1;
-        for (int i = 0; i < kMaxSplits; ++i) {
-          if (s_cost[i] < 0) continue;
-          if (best < 0 || s_cost[i] < best) {
-            best = s_cost[i];
-            best_spl = s_eff_sh[i];
-          }
-        }
-        pl = finish_plan(rb, nt, best_spl);
-      }
-      *dyn_main = FusedDyn{m, m_a, pl.nt, pl.spl, pl.tps, pl.n_items, pl.rb, 0};
-      *dyn_diag = FusedDyn{m, m, 0, 1, 2, pl.rb, pl.rb, 0};
+    if (threadIdx.x == 0) {
+      const int rb = m > 0 ? (m + fk::BM - 1) / fk::BM : 0, nt = m_a > 0 ? (m_a + fk::BN - 1) / fk::BN : 0;
+      *dyn_main = FusedDyn{m, m_a, nt, 1, nt, 0, rb, 0};
+      *dyn_diag = FusedDyn{m, m, 0, 1, 2, rb, rb, 0};
     }
   }
 };
@@ -1107,11 +1150,12 @@ static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 // optional per-launch timing of the main fused kernel (bench.py's roofline leg): a ring of
 // CUDA event pairs recorded on the launching stream; nothing is synchronised until it is read.
+bool g_ctrl_low = false;   // profiling aid (xr_fused_wait_stats bit 3)
 static bool g_wait_stats = false;
 static int g_ablate = 0;
 static bool g_timeline = false;
 static long long* g_dbg_dev = nullptr;
-static long long g_dbg_host[64 * 8];
+static long long g_dbg_host[64 * 8 + 64];   // per-tile stamps of CTA 0 + its kernel / item level stamps
 static unsigned long long g_wait_host[16];
 constexpr int kProfRing = 512;
 static bool g_prof_on = false;
@@ -1128,7 +1172,9 @@ static int launch_fused1(const CUtensorMap& tq, const CUtensorMap& tb, const Fus
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, fk::SMEM_BYTES));
     configured = true;
   }
-  fused_pool_kernel<KIND, RBF, DBG><<<grid, fk::THREADS, fk::SMEM_BYTES, s>>>(tq, tb, p);
+  FusedParams pp = p;
+  pp.ctrl_low = g_ctrl_low;
+  fused_pool_kernel<KIND, RBF, DBG><<<grid, fk::THREADS, fk::SMEM_BYTES, s>>>(tq, tb, pp);
   XR_LAUNCH_CHECK("fused_pool_kernel");
   return XR_OK;
 }
@@ -1159,7 +1205,7 @@ struct FusedWs {
   FusedDyn* dyn;   // [2]: main, diag (used by the step only)
   size_t bytes;
 };
-static FusedWs carve_fused_ws(void* workspace, long long m_max, long long max_items) {
+static FusedWs carve_fused_ws(void* workspace, long long m_max, long long max_items /* segment slots */) {
   FusedWs w;
   uint8_t* p = (uint8_t*)workspace;
   w.t = (float*)p;            p += align256((size_t)m_max * 4);
@@ -1176,7 +1222,7 @@ static FusedWs carve_fused_ws(void* workspace, long long m_max, long long max_it
 extern "C" size_t xr_fused_pool_workspace_bytes(int64_t m, int64_t cn, int64_t dim) {
   if (dim != fk::D || m <= 0 || cn <= 0) return 512;
   const FusedPlan pl = make_plan(m, cn, sm_count());
-  return carve_fused_ws(nullptr, m, pl.n_items).bytes;
+  return carve_fused_ws(nullptr, m, pl.slots).bytes;
 }
 
 // The launch sequence of the fused loss: diagonal pass (target logits) -> [softmax reference
@@ -1186,6 +1232,7 @@ extern "C" size_t xr_fused_pool_workspace_bytes(int64_t m, int64_t cn, int64_t d
 // the same stream).
 struct StepScatter {   // xr_pool_step: write dL/dtok straight into the (n_pos, D) layout
   const int64_t* inv_pos;
+  const int64_t* sel_pos;
   int64_t n_pos;
   void* dtok;
   int dtok_bf16;
@@ -1213,7 +1260,7 @@ static int fused_launch_all(const void* q, const void* pos, const void* neg, lon
   FusedParams pd{};
   pd.dyn = dyn_diag;
   pd.m = (int)m; pd.cn = (int)m; pd.nt_count = 0; pd.spl = 1; pd.tiles_per_split = 2;
-  pd.n_items = pl.rb; pd.t_out = ws.t; pd.hang_flag = ws.flags;
+  pd.n_items = pl.rb; pd.rb_count = pl.rb; pd.t_out = ws.t; pd.hang_flag = ws.flags;
   if ((rc = launch_fused<fk::KIND_DIAG>(tq, tp, pd, pl.rb < n_sm ? pl.rb : n_sm, s))) return rc;
 
   const float* zref = nullptr;
@@ -1229,12 +1276,13 @@ static int fused_launch_all(const void* q, const void* pos, const void* neg, lon
 
   FusedParams p{};
   p.dyn = dyn_main;
-  p.m = (int)m; p.cn = (int)cn; p.nt_count = pl.nt; p.spl = pl.spl; p.tiles_per_split = pl.tps;
-  p.n_items = pl.n_items; p.mask_fn = cfg->mask_false_negatives; p.logits_bf16 = cfg->logits_bf16;
+  p.m = (int)m; p.cn = (int)cn; p.nt_count = pl.nt; p.rb_count = pl.rb;
+  p.mask_fn = cfg->mask_false_negatives; p.logits_bf16 = cfg->logits_bf16;
   p.with_grad = dq != nullptr || (sc && sc->dtok); p.scale = cfg->scale; p.margin = cfg->margin;
   p.t = ws.t; p.zref = zref; p.part_o = ws.part_o; p.part_s = ws.part_s; p.hang_flag = ws.flags;
-  // dynamic: the item count is only known on the device; surplus CTAs find no item and exit
-  const int grid = dynamic ? n_sm : (pl.n_items < n_sm ? pl.n_items : n_sm);
+  // dynamic: the tile count is only known on the device; surplus CTAs get an empty range and exit.
+  // The finalize kernels derive the segments of a row block from (m, cn, grid) exactly as the kernel does.
+  const int grid = dynamic ? n_sm : pl.grid;
   const bool prof = g_prof_on && g_prof_n < kProfRing;
   if (prof) cudaEventRecord(g_prof_ev[g_prof_n][0], s);
   switch (loss_kind) {
@@ -1261,9 +1309,9 @@ static int fused_launch_all(const void* q, const void* pos, const void* neg, lon
   float* rl = row_loss ? row_loss : ws.rl;
   fused_finalize_kernel<<<n_sm * 4, 256, 0, s>>>(
       ws.part_o, ws.part_s, ws.t, zref, (const __nv_bfloat16*)q, (const __nv_bfloat16*)pos,
-      q_inv_norm, (int)m, pl.spl, loss_kind, cfg->logits_bf16, cfg->scale, cfg->margin, grad_scale,
-      dq, rl, dyn_main, sc ? sc->inv_pos : nullptr, sc ? sc->n_pos : 0, sc ? sc->dtok : nullptr,
-      sc ? sc->dtok_bf16 : 0);
+      q_inv_norm, (int)m, (int)cn, grid, loss_kind, cfg->logits_bf16, cfg->scale, cfg->margin, grad_scale,
+      dq, rl, dyn_main, sc ? sc->inv_pos : nullptr, sc ? sc->sel_pos : nullptr, sc ? sc->n_pos : 0,
+      sc ? sc->dtok : nullptr, sc ? sc->dtok_bf16 : 0);
   XR_LAUNCH_CHECK("fused_finalize");
   // loss_out[1] (if the caller left room) receives the fp32 copy the loss module returns
   sum_rows_kernel<<<1, 1024, 0, s>>>(rl, m, loss_out, reinterpret_cast<float*>(loss_out + 1), dyn_main);
@@ -1317,7 +1365,7 @@ extern "C" int xr_fused_pool_loss(const void* q, const void* pos, const void* ne
                "xr_fused_pool_loss: workspace too small");
   if ((rc = check_fused_device("xr_fused_pool_loss"))) return rc;
   const FusedPlan pl = make_plan(m, cn, sm_count());
-  const FusedWs ws = carve_fused_ws(workspace, m, pl.n_items);
+  const FusedWs ws = carve_fused_ws(workspace, m, pl.slots);
   return fused_launch_all(q, pos, neg, m, cn, loss_kind, cfg, q_inv_norm, grad_scale, dq, loss_out,
                           row_loss, ws, false, as_stream(stream));
 }
@@ -1335,7 +1383,7 @@ static size_t fused_all_extra_bytes(long long m) { return align256((size_t)m * R
 extern "C" size_t xr_fused_pool_all_workspace_bytes(int64_t m, int64_t cn, int64_t dim) {
   if (dim != fk::D || m <= 0 || cn <= 0) return 512;
   const FusedPlan pl = make_plan(m, cn, sm_count());
-  return carve_fused_ws(nullptr, m, pl.n_items).bytes + fused_all_extra_bytes(m);
+  return carve_fused_ws(nullptr, m, pl.slots).bytes + fused_all_extra_bytes(m);
 }
 
 // (m, cn) exact, or -- `dynamic` -- upper bounds with the real shape and plan in ws.dyn (written by
@@ -1356,7 +1404,7 @@ static int fused_all_launch(const void* q, const void* pos, const void* neg, lon
   FusedParams pd{};
   pd.dyn = dyn_diag;
   pd.m = (int)m; pd.cn = (int)m; pd.nt_count = 0; pd.spl = 1; pd.tiles_per_split = 2;
-  pd.n_items = pl.rb; pd.t_out = ws.t; pd.hang_flag = ws.flags;
+  pd.n_items = pl.rb; pd.rb_count = pl.rb; pd.t_out = ws.t; pd.hang_flag = ws.flags;
   if ((rc = launch_fused<fk::KIND_DIAG>(tq, tp, pd, pl.rb < n_sm ? pl.rb : n_sm, s))) return rc;
   const float* zref = nullptr;
   if (!cosine && !cfg->mask_false_negatives) {
@@ -1370,11 +1418,11 @@ static int fused_all_launch(const void* q, const void* pos, const void* neg, lon
   }
   FusedParams p{};
   p.dyn = dyn_main;
-  p.m = (int)m; p.cn = (int)cn; p.nt_count = pl.nt; p.spl = pl.spl; p.tiles_per_split = pl.tps;
-  p.n_items = pl.n_items; p.mask_fn = cfg->mask_false_negatives; p.logits_bf16 = cfg->logits_bf16;
+  p.m = (int)m; p.cn = (int)cn; p.nt_count = pl.nt; p.rb_count = pl.rb;
+  p.mask_fn = cfg->mask_false_negatives; p.logits_bf16 = cfg->logits_bf16;
   p.with_grad = 0; p.scale = cfg->scale; p.margin = cfg->margin;
   p.t = ws.t; p.zref = zref; p.part_all = ws.part_o; p.hang_flag = ws.flags;
-  const int grid = dynamic ? n_sm : (pl.n_items < n_sm ? pl.n_items : n_sm);
+  const int grid = dynamic ? n_sm : pl.grid;
   const bool prof = g_prof_on && g_prof_n < kProfRing && !dynamic;
   if (prof) cudaEventRecord(g_prof_ev[g_prof_n][0], s);
   rc = cosine ? launch_fused<fk::KIND_ALL_COS>(tq, tn, p, grid, s)
@@ -1382,7 +1430,7 @@ static int fused_all_launch(const void* q, const void* pos, const void* neg, lon
   if (prof) cudaEventRecord(g_prof_ev[g_prof_n++][1], s);
   if (rc) return rc;
   fused_finalize_all_kernel<<<(int)((m + 255) / 256), 256, 0, s>>>(
-      ws.part_o, ws.t, zref, (int)m, pl.spl, cosine, cfg->logits_bf16, cfg->scale, cfg->margin, row_out,
+      ws.part_o, ws.t, zref, (int)m, (int)cn, grid, cosine, cfg->logits_bf16, cfg->scale, cfg->margin, row_out,
       dyn_main);
   XR_LAUNCH_CHECK("fused_finalize_all");
   return launch_rowloss_reduce(row_out, m, cn + 1, 0, losses_out, stats_out, s,
@@ -1405,7 +1453,7 @@ extern "C" int xr_fused_pool_all(const void* q, const void* pos, const void* neg
   int rc;
   if ((rc = check_fused_device("xr_fused_pool_all"))) return rc;
   const FusedPlan pl = make_plan(m, cn, sm_count());
-  const FusedWs ws = carve_fused_ws(workspace, m, pl.n_items);
+  const FusedWs ws = carve_fused_ws(workspace, m, pl.slots);
   double* row_out = (double*)((uint8_t*)workspace + ws.bytes);
   return fused_all_launch(q, pos, neg, m, cn, cosine, cfg, ws, false, row_out, losses_out, stats_out,
                           as_stream(stream));
@@ -1492,7 +1540,7 @@ static StepWs carve_step_ws(void* workspace, long long n_pos) {
   w.neg = (__nv_bfloat16*)p;  p += align256(n * fk::D * 2);
   w.err = (int32_t*)p;        p += 256;
   const size_t off = (size_t)(p - (uint8_t*)workspace);
-  w.fused = carve_fused_ws(workspace ? p : nullptr, n_pos, max_plan_items(n_pos, sm_count()));
+  w.fused = carve_fused_ws(workspace ? p : nullptr, n_pos, max_plan_slots(n_pos, sm_count()));
   w.bytes = off + w.fused.bytes;
   return w;
 }
@@ -1558,7 +1606,7 @@ extern "C" int xr_pool_step_ingest(const int64_t* history_idx, const int64_t* po
   if ((rc = xr_compact_positions(history_idx, pos_idx, rownz, n_table_rows, n_pos, w.attn, w.sel_attn,
                                  w.sel_pos, w.pos_mask, w.inv_pos, counts, w.compact_ws, stream)))
     return rc;
-  fused_plan_kernel<<<1, 64, 0, s>>>(counts, PlanHook{n_sm, w.fused.dyn, w.fused.dyn + 1});
+  fused_plan_kernel<<<1, 32, 0, s>>>(counts, PlanHook{w.fused.dyn, w.fused.dyn + 1});
   XR_LAUNCH_CHECK("fused_plan");
   // 3. the three gathers in one launch (models.py:392+415, :400+416, :406), bf16 operands
   const int64_t per_job = (n_pos * (fk::D * 2 / 16) + 255) / 256;
@@ -1591,7 +1639,7 @@ extern "C" int xr_pool_step_compute(int64_t n_pos, int64_t dim, int loss_kind, c
   // 4. fused contraction + loss + dL/dtok: the finalize kernel writes the gradient in the encoder
   //    output's layout (zero rows for unselected positions: autograd of
   //    token_embeddings[mask][pos_mask], models.py:392, 415)
-  const StepScatter sc{w.inv_pos, n_pos, dtok, dtok_dtype == XR_BF16};
+  const StepScatter sc{w.inv_pos, w.sel_pos, n_pos, dtok, dtok_dtype == XR_BF16};
   if (!cosine)
     return fused_launch_all(w.q, w.pos, w.neg, n_pos, n_pos, loss_kind, cfg, nullptr, grad_scale, nullptr,
                             loss_out, nullptr, w.fused, true, as_stream(stream), dtok ? &sc : nullptr);
@@ -1721,7 +1769,7 @@ extern "C" int xr_score_groupmax(const void* q, int64_t u, const void* catalog, 
   } else {
     const int n_sm = sm_count();
     const int64_t nt = ((n + fk::BN - 1) / fk::BN + tile_stride - 1) / tile_stride;   // sampled tiles
-    const FusedPlan pl = make_gmax_plan(u, nt * fk::BN, n_sm);
+    const GmaxPlan pl = make_gmax_plan(u, nt * fk::BN, n_sm);
     CUtensorMap tq, tc;
     if ((rc = make_tmap_bf16_rows(&tq, q, u, dim, dim, fk::BM))) return rc;
     if ((rc = make_tmap_bf16_rows(&tc, catalog, n, dim, dim, fk::BN))) return rc;
@@ -1760,7 +1808,7 @@ extern "C" int xr_score_filter(const void* q, int64_t u, const void* catalog, in
                               cap, hang, s);
   } else {
     const int n_sm = sm_count();
-    const FusedPlan pl = make_gmax_plan(u, n, n_sm);
+    const GmaxPlan pl = make_gmax_plan(u, n, n_sm);
     CUtensorMap tq, tc;
     if ((rc = make_tmap_bf16_rows(&tq, q, u, dim, dim, fk::BM))) return rc;
     if ((rc = make_tmap_bf16_rows(&tc, catalog, n, dim, dim, fk::BN))) return rc;
@@ -1783,7 +1831,7 @@ extern "C" int xr_score_filter(const void* q, int64_t u, const void* catalog, in
 // [0] score issue start [1] score issued+committed [2] epilogue woke on s_full [3] tcgen05.ld done
 // [4] weights stored + p_full arrive [5] gradient issuer woke on p_full
 extern "C" int xr_fused_timeline(long long* out512_host) {
-  memcpy(out512_host, g_dbg_host, sizeof(g_dbg_host));
+  memcpy(out512_host, g_dbg_host, sizeof(g_dbg_host));   // 576 entries
   return XR_OK;
 }
 
@@ -1791,6 +1839,7 @@ extern "C" int xr_fused_wait_stats(int enable, unsigned long long* out16_host) {
   g_wait_stats = (enable & 1) != 0;
   g_timeline = (enable & 2) != 0;   // per-tile timestamps without the wait counters
   g_gmax_single = (enable & 4) != 0;
+  g_ctrl_low = (enable & 8) != 0;
   g_ablate = enable >> 8;   // ablation mask for timing experiments (results are garbage)
   if (out16_host) memcpy(out16_host, g_wait_host, sizeof(g_wait_host));
   return XR_OK;

@@ -23,6 +23,8 @@ namespace xr {
 
 using namespace sm100;
 
+extern bool g_ctrl_low;
+
 namespace g2 {
 constexpr int BM = 128;            // query rows per CTA (256 per pair)
 constexpr int BNH = 64;            // catalog rows per CTA per tile (128 per pair)
@@ -56,6 +58,7 @@ struct Gmax2Params {
   int32_t* cand_count;   // (u): appended so far; may run past cap (overflow is detected by the consumer)
   int cap;
   int* hang_flag;
+  int ctrl_low;
   int ablate;   // DBG instantiation only: 1 skip catalog TMA, 2 skip epilogue TMEM loads, 4 skip gmax stores, 8 skip MMAs
 };
 
@@ -130,7 +133,9 @@ score_gmax2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   auto bar_s_free = [&](int b) { return bars + 8u * (2 * PAIRS + 2 + NSB + b); };  // leader
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + BAR_OFF + NBARS * 8);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // `warp` is the ROLE index; control roles on the highest hardware warps (see fused_loss_sm100.cu)
+  const int hw_warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = p.ctrl_low ? hw_warp : (hw_warp >= EPI_WARPS ? hw_warp - EPI_WARPS : hw_warp + 4);
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
@@ -390,6 +395,7 @@ static int launch_gmax2_mode(const void* q, int64_t u, const void* catalog, int6
   }
   const int pairs = p.n_items < n_clusters ? p.n_items : n_clusters;
   p.ablate = ablate;
+  p.ctrl_low = g_ctrl_low;
   if (ablate) score_gmax2_kernel<MODE, true><<<2 * pairs, THREADS, SMEM_BYTES, s>>>(tq, tc, p);   // timing experiments
   else score_gmax2_kernel<MODE, false><<<2 * pairs, THREADS, SMEM_BYTES, s>>>(tq, tc, p);
   XR_LAUNCH_CHECK("score_gmax2_kernel");
