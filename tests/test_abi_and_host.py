@@ -159,3 +159,58 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "seq/s"
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_torch_library_ops_registered_with_fake_impls():
+    """SURVEY 8b: the entry points are dispatcher-visible ``xfmr_b200::*`` ops registered at import,
+    each with a fake (meta) implementation; CUDA is the only backend (no CPU fallback)."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    import xfmr_rec_b200 as xr
+
+    for name in xr.ops.CUSTOM_OPS:
+        assert hasattr(torch.ops.xfmr_b200, name), name
+    with FakeTensorMode():
+        q = torch.empty((10, 384), dtype=torch.bfloat16, device="cuda")
+        neg = torch.empty((33, 384), dtype=torch.bfloat16, device="cuda")
+        loss, dq = torch.ops.xfmr_b200.pool_loss(q, q, neg, 3, True, 1.0, 0.5, True)
+        assert loss.shape == () and dq.shape == (10, 384) and dq.dtype == torch.float32
+        s, i = torch.ops.xfmr_b200.score_topk(q, neg, 5)
+        assert s.shape == (10, 5) and i.dtype == torch.int64
+        g = torch.ops.xfmr_b200.gather_rows(neg, torch.empty((4, 7), dtype=torch.int64, device="cuda"))
+        assert g.shape == (4, 7, 384)
+        m, v = torch.ops.xfmr_b200.retrieval_metrics(torch.empty((6, 20), dtype=torch.int64, device="cuda"),
+                                                     torch.empty(7, dtype=torch.int64, device="cuda"),
+                                                     torch.empty(9, dtype=torch.int64, device="cuda"), 20)
+        assert m.shape == (6, 7) and v.shape == (6,)
+    with pytest.raises(NotImplementedError):
+        torch.ops.xfmr_b200.topk(torch.zeros(2, 5), 2)
+
+
+def test_service_wire_types_round_trip():
+    """service.py:30-72: same field names / defaults, arrays travel as float lists."""
+    from xfmr_rec_b200 import service as S
+
+    q = S.Query(embedding=[0.1, 0.2], exclude_item_ids=["3"], top_k=5)
+    assert S.Query().top_k == 20 and S.Query().embedding is None
+    back = S.Query.model_validate_json(q.model_dump_json())
+    assert isinstance(back.embedding, np.ndarray) and back.embedding.dtype == np.float32
+    assert back.exclude_item_ids == ["3"] and back.top_k == 5
+    c = S.ItemCandidate(item_id="1", item_text="x", score=0.5)
+    assert c.model_dump() == {"item_id": "1", "item_text": "x", "score": 0.5}
+    u = S.UserQuery(history=S.Activity(item_id=["1"], item_text=["a"]))
+    assert u.user_id == "0" and u.history.item_id == ["1"] and u.target is None
+    i = S.ItemQuery.model_validate({"item_id": "7", "item_text": "t", "embedding": np.ones(3)})
+    assert i.model_dump()["embedding"] == [1.0, 1.0, 1.0]
+
+
+def test_synthetic_batch_generators_agree():
+    """bench.py draws its inputs from the package's generator; the parity tests use the oracle's: same
+    algorithm, same arrays."""
+    from oracle import xfmr_oracle as orc
+    from xfmr_rec_b200.data import synthetic_batch
+
+    a, b = orc.synth_batch(300, 5, 17, dim=32, seed=4), synthetic_batch(300, 5, 17, dim=32, seed=4)
+    assert a.keys() == b.keys()
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k

@@ -612,3 +612,76 @@ def test_compiled_search_plan_equals_search_batch(xr, u):
         assert torch.equal(got_i, want_i) and torch.equal(got_s, want_s)
         got_s, got_i = plain(q)
         assert torch.equal(got_i, want_i) and torch.equal(got_s, want_s)
+
+
+def test_torch_library_ops_match_the_wrappers(xr):
+    """torch.ops.xfmr_b200.* (SURVEY 8b): same results as the ctypes wrappers; ::pool_loss carries the
+    autograd edge (backward = the gradient the fused kernel produced, scaled by grad_output)."""
+    if torch.cuda.get_device_capability()[0] != 10:
+        pytest.skip("needs an sm_100 device")
+    from xfmr_rec_b200 import _native as N, ops
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    table = torch.randn((500, 384), generator=g, device="cuda")
+    idx = torch.randint(0, 500, (7, 9), generator=g, device="cuda")
+    assert torch.equal(torch.ops.xfmr_b200.gather_rows(table, idx), table[idx])
+    q = (torch.randn((300, 384), generator=g, device="cuda") / 20).bfloat16()
+    pos = (torch.randn((300, 384), generator=g, device="cuda") / 20).bfloat16()
+    neg = (torch.randn((777, 384), generator=g, device="cuda") / 20).bfloat16()
+    kind = N.LOSS_KIND["InfoNCELoss"]
+    loss, dq = torch.ops.xfmr_b200.score_loss_fwd_bwd(q, pos, neg, kind, True, 1.0, 0.5, True)
+    want = xr.InfoNCELoss(xr.LossConfig())(q.clone().requires_grad_(True), xr.PoolCandidates(pos, neg))
+    assert torch.equal(loss, want.detach())
+    qg = q.clone().requires_grad_(True)
+    l2, _ = torch.ops.xfmr_b200.pool_loss(qg, pos, neg, kind, True, 1.0, 0.5, True)
+    (3.0 * l2).backward()
+    assert torch.equal(qg.grad, (dq * 3.0).to(torch.bfloat16))
+    sc = torch.randn((5, 3000), generator=g, device="cuda")
+    s1, i1 = torch.ops.xfmr_b200.topk(sc, 10)
+    s2, i2 = ops.topk(sc, 10)
+    assert torch.equal(s1, s2) and torch.equal(i1, i2)
+    cat, _ = ops.normalize_rows(torch.randn((20000, 384), generator=g, device="cuda"), 1e-12, torch.bfloat16)
+    qq, _ = ops.normalize_rows(torch.randn((9, 384), generator=g, device="cuda"), 1e-12, torch.bfloat16)
+    s3, i3 = torch.ops.xfmr_b200.score_topk(qq, cat, 20)
+    idx2 = xr.index.ExactIndex(xr.index.ExactIndexConfig(index_metric="dot")).set_catalog(cat)
+    s4, i4 = idx2.search_batch(qq, None, 20)
+    assert torch.equal(i3, i4) and torch.equal(s3, s4)
+    offs = torch.tensor([0, 2, 3], device="cuda")
+    ids = torch.tensor([int(i3[0, 1]), 5, int(i3[1, 0])], device="cuda")
+    m1, v1 = torch.ops.xfmr_b200.retrieval_metrics(i3[:2].contiguous(), offs, ids, 20)
+    m2, v2 = ops.retrieval_metrics(i3[:2].contiguous(), (offs, ids), 20)
+    assert torch.equal(m1, m2) and torch.equal(v1, v2)
+
+
+def test_item_index_service_wire_format(xr):
+    """service.py:137-180 over ExactIndex: Query -> list[ItemCandidate] equals index.search, batched
+    search_many equals the per-query calls, get_id / get_ids return ItemQuery rows (embedding included,
+    the ORIGINAL rows with store_embeddings) and unknown ids raise NotFound."""
+    from xfmr_rec_b200 import service as S
+
+    rng = np.random.default_rng(2)
+    n = 3000
+    emb = rng.standard_normal((n, 384)).astype(np.float32)
+    data = {"item_id": [f"i{j}" for j in range(n)], "item_text": [f"text {j}" for j in range(n)],
+            "embedding": torch.from_numpy(emb)}
+    idx = xr.index.ExactIndex(xr.index.ExactIndexConfig(store_embeddings=True)).index_data(data)
+    svc = S.ItemIndexService(idx)
+    qs = [S.Query(embedding=rng.standard_normal(384).astype(np.float32), exclude_item_ids=[f"i{j}" for j in range(r * 3)],
+                  top_k=5 + r) for r in range(4)]
+    many = svc.search_many(qs)
+    for q, got in zip(qs, many):
+        one = svc.search(q)
+        ref = idx.search(q.embedding, q.exclude_item_ids, q.top_k)
+        assert [c.item_id for c in got] == [c.item_id for c in one] == list(ref["item_id"])
+        assert len(got) == q.top_k and all(isinstance(c, S.ItemCandidate) for c in got)
+        assert [c.item_text for c in got] == list(ref["item_text"])
+        assert not set(c.item_id for c in got) & set(q.exclude_item_ids or [])
+        np.testing.assert_allclose([c.score for c in got], ref["score"], rtol=1e-6)
+    item = svc.get_id("i7")
+    assert item.item_id == "i7" and item.item_text == "text 7"
+    np.testing.assert_array_equal(item.embedding, emb[7])
+    assert set(svc.get_ids(["i1", "i2", "nope"])) == {"i1", "i2"}
+    with pytest.raises(S.NotFound):
+        svc.get_id("nope")
+    wire = S.Query.model_validate_json(qs[1].model_dump_json())       # JSON round trip of a request
+    assert [c.item_id for c in svc.search(wire)] == [c.item_id for c in many[1]]

@@ -130,3 +130,33 @@ class SeqBatchSampler:
         n_batches = n // batch_size if drop_last else -(-n // batch_size)
         for i in range(n_batches):
             yield self.sample(perm[i * batch_size:(i + 1) * batch_size], step=epoch * n_batches + i)
+
+
+def synthetic_batch(n_items: int, batch: int, seq_len: int, dim: int = 384, seed: int = 0,
+                    pos_pad_frac: float = 0.05, table=None) -> dict:
+    """MovieLens-shaped synthetic SeqBatch + item table + encoder-output stand-in: table
+    rows ~ N(0, 1/dim) with a zero padding row 0; sequence lengths uniform in [1, seq_len], right-padded
+    with 0 as ``pad_sequence`` does (data.py:801); 5 % of the positives set to 0 (positions with no
+    future positive, data.py:710-721).  numpy arrays; deterministic in ``seed``."""
+    import math
+
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    if table is None:
+        table = (rng.standard_normal((n_items + 1, dim)) / math.sqrt(dim)).astype(np.float32)
+        table[0] = 0.0
+    lens = rng.integers(1, seq_len + 1, size=batch)
+    hist = np.zeros((batch, seq_len), np.int64)
+    pos = np.zeros((batch, seq_len), np.int64)
+    neg = np.zeros((batch, seq_len), np.int64)
+    for b in range(batch):
+        n = int(lens[b])
+        hist[b, :n] = rng.integers(1, n_items + 1, size=n)
+        pos[b, :n] = rng.integers(1, n_items + 1, size=n)
+        neg[b, :n] = rng.integers(1, n_items + 1, size=n)
+        drop = rng.random(n) < pos_pad_frac
+        pos[b, :n][drop] = 0
+    tokens = (rng.standard_normal((batch, seq_len, dim)) / math.sqrt(dim)).astype(np.float32)
+    return {"table": table, "history_item_idx": hist, "pos_item_idx": pos,
+            "neg_item_idx": neg, "token_embeddings": tokens}

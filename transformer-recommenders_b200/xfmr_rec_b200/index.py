@@ -34,6 +34,7 @@ class ExactIndexConfig(pydantic.BaseModel):
     max_score_bytes: int = 1 << 30  # materialised-score budget of the unfused path
     max_groupmax_bytes: int = 4 << 30  # workspace budget of the fused path (survivor lists: 256 KB per query): larger query sets run in blocks
     fused: bool = True  # tensor-core filter path (xr_score_topk) when the device / dtype allow it
+    store_embeddings: bool = False  # keep the ORIGINAL fp32 rows on the host for get_ids / get_id (serving)
 
 
 class ExactIndex:
@@ -44,6 +45,7 @@ class ExactIndex:
         self.id2row: dict[str, int] | None = None
         self.catalog: torch.Tensor | None = None  # (N, D), rows normalised for the cosine metric
         self.columns: dict[str, list] = {}
+        self.embeddings: torch.Tensor | None = None  # original fp32 rows (host), config.store_embeddings
         self.row_offset = row_offset  # global row of local row 0 (catalog shards)
 
     # -- construction -------------------------------------------------------------------------
@@ -67,6 +69,8 @@ class ExactIndex:
         if self.device is None:
             self.device = embeddings.device if embeddings.is_cuda else torch.device(
                 "cuda", torch.cuda.current_device())
+        if self.config.store_embeddings:
+            self.embeddings = embeddings.detach().float().cpu()
         emb = embeddings.to(self.device)
         dt = torch.bfloat16 if self.config.dtype == "bf16" else torch.float32
         if self.config.index_metric == "cosine":
@@ -210,6 +214,12 @@ class ExactIndex:
         out: dict[str, list] = {self.config.id_col: [self._id_of(r) for r in rows]}
         for c, vals in self.columns.items():
             out[c] = [vals[r] for r in rows]
+        if self.config.embedding_col and self.catalog is not None:
+            # the reference returns whole table rows (index.py:257-273), embedding included: the original
+            # rows when they were kept (store_embeddings), else the index's own (normalised / bf16) rows
+            src = self.embeddings if self.embeddings is not None else self.catalog
+            sel = torch.as_tensor(rows, dtype=torch.int64, device=src.device)
+            out[self.config.embedding_col] = src[sel].float().cpu().tolist() if rows else []
         return datasets.Dataset.from_dict(out)
 
     def get_id(self, id_val: str | None) -> dict[str, Any]:

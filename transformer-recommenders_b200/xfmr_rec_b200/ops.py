@@ -2,9 +2,10 @@
 
 PyTorch is plumbing here: it owns device memory and the current stream; every function
 hands raw device pointers to libxfmr_b200.so.  Inputs must live on a CUDA device — there is
-no CPU path.  The main entry points are also registered as ``torch.library`` custom ops
-(``xfmr_b200::gather_rows``, ``::pool_loss_fwd_bwd``, ``::topk``, ``::score_topk``,
-``::retrieval_metrics``) so they compose with the dispatcher / autograd machinery.
+no CPU path.  The main entry points are also registered (at import) as ``torch.library`` custom ops
+(``xfmr_b200::gather_rows``, ``::score_loss_fwd_bwd``, ``::pool_loss``, ``::topk``, ``::score_topk``,
+``::retrieval_metrics``) with fake implementations and an autograd formula, so they compose with
+the dispatcher / autograd / FakeTensor machinery.
 """
 
 from __future__ import annotations
@@ -542,30 +543,104 @@ def retrieval_metrics(rec_idx, target_lists, top_k):
 
 
 # ---------------------------------------------------------------------------------------------
-# torch.library registration (dispatcher-visible names of SURVEY §8b)
+# torch.library registration (the dispatcher-visible names of SURVEY §8b), done at import:
+#   xfmr_b200::gather_rows, ::score_loss_fwd_bwd, ::pool_loss (autograd), ::topk, ::score_topk,
+#   ::retrieval_metrics.  Each has a fake (meta) implementation, so the ops trace under FakeTensor /
+#   torch.export, and ::pool_loss carries an autograd formula (the gradient is produced by the same
+#   kernel launch as the loss; backward only scales it).  CUDA is the only backend registered: on any
+#   other device the dispatcher raises, as everywhere in this package there is no fallback.
 # ---------------------------------------------------------------------------------------------
-_registered = False
+def _lossname_to_cfg(mask_fn: bool, scale: float, margin: float, logits_bf16: bool) -> N.XrLossConfig:
+    return N.XrLossConfig(int(mask_fn), 0, float(scale), float(margin), int(logits_bf16))
 
 
-def register_custom_ops() -> None:
-    global _registered
-    if _registered:
-        return
-    _registered = True
-    lib = torch.library.Library("xfmr_b200", "DEF")
-    lib.define("gather_rows(Tensor table, Tensor idx) -> Tensor")
-    lib.define("topk(Tensor scores, int k) -> (Tensor, Tensor)")
-    lib.define("score_topk(Tensor q, Tensor catalog, int k) -> (Tensor, Tensor)")
-    lib.define("pool_loss_fwd_bwd(Tensor q, Tensor pos, Tensor neg, int loss_kind, bool mask_fn, "
-               "float scale, float margin, bool logits_bf16) -> (Tensor, Tensor)")
-    lib.impl("gather_rows", lambda table, idx: gather_rows(table, idx), "CUDA")
-    lib.impl("topk", lambda s, k: topk(s, k), "CUDA")
-    lib.impl("score_topk", lambda q, c, k: score_topk(q, c, k), "CUDA")
+@torch.library.custom_op("xfmr_b200::gather_rows", mutates_args=(), device_types="cuda")
+def _op_gather_rows(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    return gather_rows(table, idx)
 
-    def _pool(q, pos, neg, loss_kind, mask_fn, scale, margin, logits_bf16):
-        cfg = N.XrLossConfig(int(mask_fn), 0, scale, margin, int(logits_bf16))
-        loss, dq, _ = fused_pool_loss(q, pos, neg, loss_kind, cfg)
-        return loss, dq
 
-    lib.impl("pool_loss_fwd_bwd", _pool, "CUDA")
-    globals()["_torch_lib"] = lib  # keep alive
+@_op_gather_rows.register_fake
+def _(table, idx):
+    return table.new_empty((*idx.shape, table.size(1)))
+
+
+@torch.library.custom_op("xfmr_b200::score_loss_fwd_bwd", mutates_args=(), device_types="cuda")
+def _op_score_loss_fwd_bwd(q: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor, loss_kind: int,
+                           mask_fn: bool, scale: float, margin: float,
+                           logits_bf16: bool) -> tuple[torch.Tensor, torch.Tensor]:
+    """Fused contraction + loss + dL/dq over a shared negative pool (bf16 operands, D = 384):
+    (loss 0-dim fp32, dq (M, D) fp32)."""
+    loss, dq, _ = fused_pool_loss(q, pos, neg, loss_kind, _lossname_to_cfg(mask_fn, scale, margin, logits_bf16))
+    return loss.view(torch.float32)[2].clone(), dq
+
+
+@_op_score_loss_fwd_bwd.register_fake
+def _(q, pos, neg, loss_kind, mask_fn, scale, margin, logits_bf16):
+    return q.new_empty((), dtype=torch.float32), q.new_empty(q.shape, dtype=torch.float32)
+
+
+@torch.library.custom_op("xfmr_b200::pool_loss", mutates_args=(), device_types="cuda")
+def _op_pool_loss(q: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor, loss_kind: int, mask_fn: bool,
+                  scale: float, margin: float, logits_bf16: bool) -> tuple[torch.Tensor, torch.Tensor]:
+    """Differentiable form: returns (loss, dq); dq is saved for backward (autograd formula below)."""
+    return torch.ops.xfmr_b200.score_loss_fwd_bwd(q, pos, neg, loss_kind, mask_fn, scale, margin, logits_bf16)
+
+
+@_op_pool_loss.register_fake
+def _(q, pos, neg, loss_kind, mask_fn, scale, margin, logits_bf16):
+    return q.new_empty((), dtype=torch.float32), q.new_empty(q.shape, dtype=torch.float32)
+
+
+def _pool_loss_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[1])
+    ctx.q_dtype = inputs[0].dtype
+
+
+def _pool_loss_backward(ctx, grad_loss, grad_dq):
+    (dq,) = ctx.saved_tensors
+    return (dq * grad_loss).to(ctx.q_dtype), None, None, None, None, None, None, None
+
+
+_op_pool_loss.register_autograd(_pool_loss_backward, setup_context=_pool_loss_setup)
+
+
+@torch.library.custom_op("xfmr_b200::topk", mutates_args=(), device_types="cuda")
+def _op_topk(scores: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor]:
+    return topk(scores, k)
+
+
+@_op_topk.register_fake
+def _(scores, k):
+    return (scores.new_empty((scores.size(0), k), dtype=torch.float32),
+            scores.new_empty((scores.size(0), k), dtype=torch.int64))
+
+
+@torch.library.custom_op("xfmr_b200::score_topk", mutates_args=(), device_types="cuda")
+def _op_score_topk(q: torch.Tensor, catalog: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """Whole local search of one catalog shard (bf16, D = 384, rows pre-normalised for cosine).  Falls
+    back to NOTHING: if the filter path cannot vouch for the result the op raises."""
+    s, i, flags = score_topk(q, catalog, k)
+    if int(flags.item()):
+        raise N.NativeError("xfmr_b200::score_topk: survivor list overflow (massively tied scores); "
+                            "use ExactIndex.search_batch, which takes the materialised path")
+    return s, i
+
+
+@_op_score_topk.register_fake
+def _(q, catalog, k):
+    return (q.new_empty((q.size(0), k), dtype=torch.float32), q.new_empty((q.size(0), k), dtype=torch.int64))
+
+
+@torch.library.custom_op("xfmr_b200::retrieval_metrics", mutates_args=(), device_types="cuda")
+def _op_retrieval_metrics(rec_idx: torch.Tensor, target_offsets: torch.Tensor, target_ids: torch.Tensor,
+                          top_k: int) -> tuple[torch.Tensor, torch.Tensor]:
+    return retrieval_metrics(rec_idx, (target_offsets, target_ids), top_k)
+
+
+@_op_retrieval_metrics.register_fake
+def _(rec_idx, target_offsets, target_ids, top_k):
+    return (rec_idx.new_empty((rec_idx.size(0), 7), dtype=torch.float32),
+            rec_idx.new_empty((rec_idx.size(0),), dtype=torch.bool))
+
+
+CUSTOM_OPS = ("gather_rows", "score_loss_fwd_bwd", "pool_loss", "topk", "score_topk", "retrieval_metrics")
