@@ -145,10 +145,8 @@ def test_bench_reference_arm_prints_the_contract_line():
     import sys
 
     root = pathlib.Path(__file__).resolve().parent.parent
-    env = dict(__import__("os").environ, XR_BENCH_BATCH="8")   # a small batch keeps the CPU suite fast
     out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--gpus", "1",
-                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600,
-                         env=env)
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -159,6 +157,10 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "seq/s"
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    sys.path.insert(0, str(root))
+    import bench
+
+    assert d["config"] == bench.config_dict(1) and d["metric"] == bench.METRIC   # same config in both arms
 
 
 def test_torch_library_ops_registered_with_fake_impls():

@@ -96,8 +96,12 @@ def test_fused_matches_oracle(xr, name, m, cn):
         want, want_dq = oracle_on_bf16(name, qh, ph, nh, q_inv, cfg_kw, lbf)
         assert loss == pytest.approx(want, rel=2e-3, abs=2e-3), (name, cfg_kw, loss, want)
         scale = max(np.abs(want_dq).max(), 1e-6)
-        assert np.abs(dq - want_dq).max() <= 2e-2 * scale + 1e-6, (name, cfg_kw)
-        assert np.linalg.norm(dq - want_dq) <= 5e-3 * np.linalg.norm(want_dq) + 1e-6, (name, cfg_kw)
+        # north_star: 2e-3 in bf16.  The kernel rounds the softmax / sigmoid weights to bf16 for the
+        # gradient MMA (2^-9 per weight, averaging out over the candidates); measured 1.4e-4 .. 4.2e-4
+        # norm-wise, <= 1.8e-3 of the largest element (profiles/grad_error_r02.json) -- the reference's
+        # own bf16-autocast gradient is 2.0e-3 .. 2.6e-3 / 3.6e-3 .. 4.1e-3 from the same oracle
+        assert np.linalg.norm(dq - want_dq) <= 2e-3 * np.linalg.norm(want_dq) + 1e-6, (name, cfg_kw)
+        assert np.abs(dq - want_dq).max() <= 6e-3 * scale + 1e-6, (name, cfg_kw)
 
 
 def test_fused_forward_only_equals_forward_backward(xr):
@@ -430,3 +434,27 @@ def test_groupmax_two_phase_rescore_with_adversarial_exclusions(xr, u, n, k):
     plan = idx.compile_search(u, k, max_exclusions=150)
     ps, pi = plan(q, xr.ops._csr(excl, q.device))
     assert torch.equal(pi, i) and torch.equal(ps, s)
+
+
+def test_fused_bf16_gradient_vs_the_references_own_autocast(xr, golden_dir):
+    """The reference under bf16-mixed autocast (trainer.py:450) executed at D = 384 (tests/golden/
+    make_golden_autocast_d384.py): its losses are reproduced to 1e-6, and the fused kernel's fp32 gradient
+    is CLOSER to the float64 oracle (same bf16-rounded operands and logits) than the reference's own
+    autocast gradient, whose bmm backward rounds dlogits and dq to bf16."""
+    from xfmr_rec_b200 import _native as N, ops
+
+    z = np.load(golden_dir / "losses_pool_autocast_bf16_d384.npz")
+    q, p, n = z["query"], z["pos"], z["neg"]
+    for name in ("InfoNCELoss", "NCELoss", "PairwiseHingeLoss", "PairwiseLogisticLoss"):
+        want, want_dq, _, _ = orc.lean_loss(name, q, p, n, orc.Config(), with_grad=True, logits_dtype="bf16")
+        loss, dq, _ = ops.fused_pool_loss(bf(q), bf(p), bf(n), N.LOSS_KIND[name],
+                                          ops.make_cfg(xr.LossConfig(), logits_bf16=True))
+        loss = float(loss.view(torch.float32)[2])
+        assert loss == pytest.approx(float(z[f"autocast/loss/{name}"]), rel=5e-5), name
+        assert loss == pytest.approx(want, rel=1e-6), name
+        dq = dq.cpu().numpy().astype(np.float64)
+        ref = z[f"autocast/dq/{name}"].astype(np.float64)
+        e_ours = np.linalg.norm(dq - want_dq) / np.linalg.norm(want_dq)
+        e_ref = np.linalg.norm(ref - want_dq) / np.linalg.norm(want_dq)
+        assert e_ours <= 1e-3 and e_ours < e_ref, (name, e_ours, e_ref)
+        assert np.linalg.norm(dq - ref) <= 4e-3 * np.linalg.norm(ref), name

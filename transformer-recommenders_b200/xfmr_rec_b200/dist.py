@@ -160,6 +160,8 @@ class ShardedIndex:
         else:
             s, i = self.local.search_batch(queries, exclude_rows, top_k)
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if world == 1 and self.merge_fn is None:
+            return s, i          # one shard: the local result is the result
         if world > 1 and self.exchange in ("peer", "auto") and self.merge_fn is None and s.is_cuda:
             px = self._peer_exchange(s.size(0), top_k, s.device)
             if px is not None:
