@@ -363,27 +363,38 @@ int64_t xr_score_groupmax_ld(int64_t u, int64_t n, int64_t tile_stride);
 int xr_score_groupmax(const void* q, int64_t u, const void* catalog, int64_t n, int64_t dim,
                       int64_t tile_stride, float* gmax, int64_t ld, void* stream);
 /* Threshold filter in the scoring epilogue: every (score, local row) with
- * q_u . cat_c >= thresh[u * thresh_stride] is appended to query u's list (cand_scores / cand_rows,
- * (U, cap), unordered).  cand_count[u] (zeroed by the caller) counts the survivors and keeps counting
- * past cap: count > cap means the list is incomplete.  Nothing of size U x N reaches HBM.            */
+ * q_u . cat_c >= thresh[u * thresh_stride] is kept.  Storage per query: n_sub sub-buckets of cap_b slots
+ * (bucket_scores / bucket_rows, (U, n_sub, cap_b)), one per (catalog split of the scoring plan, column
+ * group) — each filled by ONE lane of the scoring kernel from a register counter, no atomics — plus an
+ * overflow list of ovf_cap slots for sub-buckets that run full.  bucket_count[u][s] = survivors
+ * sub-bucket s saw (> cap_b: the excess is in the overflow list); ovf_count[u] (zeroed by the caller)
+ * keeps counting past ovf_cap: ovf_count > ovf_cap means survivors were lost.  n_sub must be the value
+ * xr_score_filter_layout returns for (u, n); cap_b is the caller's choice (the layout call suggests
+ * ~4x the expected fill).  Nothing of size U x N reaches HBM.                                          */
+int xr_score_filter_layout(int64_t u, int64_t n, int64_t expected_survivors, int64_t* n_sub,
+                           int64_t* cap_b);
 int xr_score_filter(const void* q, int64_t u, const void* catalog, int64_t n, int64_t dim,
-                    const float* thresh, int64_t thresh_stride, float* cand_scores, int32_t* cand_rows,
-                    int32_t* cand_count, int64_t cap, void* stream);
-/* Survivor lists -> the exact top-k (block per query): the k_sel best survivors under
+                    const float* thresh, int64_t thresh_stride, float* bucket_scores,
+                    int32_t* bucket_rows, int32_t* bucket_count, int64_t n_sub, int64_t cap_b,
+                    float* ovf_scores, int32_t* ovf_rows, int32_t* ovf_count, int64_t ovf_cap,
+                    void* stream);
+/* Survivors -> the exact top-k (block per query): the k_sel best survivors under
  * (score desc, row asc) are re-scored with the arithmetic of xr_logits_sampled, rows in query u's CSR
  * exclusion list (GLOBAL ids; nullable) are dropped (the prefilter of index.py:239-247), the rest is
  * ranked by (score desc, global id asc).  out_scores (U, k) fp32 / out_idx (U, k) int64 = local row +
- * row_offset (-inf / -1 where fewer than k remain).  thresh = the thresholds the lists were filtered
- * with.  flags[0] |= 1 if a list overflowed (count > cap), |= 2 if a query has more than max_excl
- * excluded ids, |= 4 if fewer than k_sel - max_excl non-excluded rows survived a finite threshold: the
- * result is then not guaranteed exact and the caller must take another path.
+ * row_offset (-inf / -1 where fewer than k remain).  thresh = the thresholds the survivors were filtered
+ * with.  flags[0] |= 1 if survivors were lost (ovf_count > ovf_cap), |= 2 if a query has more than
+ * max_excl excluded ids, |= 4 if fewer than k_sel - max_excl non-excluded rows survived a finite
+ * threshold: the result is then not guaranteed exact and the caller must take another path.
  * k + max_excl <= k_sel <= 1024.                                                                    */
 int xr_filter_finalize(const void* q, int64_t u, const void* catalog, int64_t n, int64_t dim,
-                       const float* cand_scores, const int32_t* cand_rows, const int32_t* cand_count,
-                       int64_t cap, const float* thresh, int64_t thresh_stride, int64_t k_sel, int64_t k,
-                       int64_t row_offset,
-                       const int64_t* excl_offsets, const int64_t* excl_ids, int64_t max_excl,
-                       float* out_scores, int64_t* out_idx, int32_t* flags, void* stream);
+                       const float* bucket_scores, const int32_t* bucket_rows,
+                       const int32_t* bucket_count, int64_t n_sub, int64_t cap_b,
+                       const float* ovf_scores, const int32_t* ovf_rows, const int32_t* ovf_count,
+                       int64_t ovf_cap, const float* thresh, int64_t thresh_stride, int64_t k_sel,
+                       int64_t k, int64_t row_offset, const int64_t* excl_offsets,
+                       const int64_t* excl_ids, int64_t max_excl, float* out_scores, int64_t* out_idx,
+                       int32_t* flags, void* stream);
 /* scores[u, j] = -inf where ids[u, j] lies outside [id_lo, id_hi) or in row u's CSR exclusion
  * list (nullable) — the prefilter of index.py:239-247 applied to re-scored candidate lists.     */
 int xr_mask_excluded_ids(float* scores, const int64_t* ids, int64_t u, int64_t c, int64_t ld,

@@ -59,13 +59,15 @@ for u in us:
     t_g, gm = timed(lambda: ops.score_groupmax(qn, cat, stride), iters)
     t_t, (tv, ti) = timed(lambda: ops.topk(gm, kk), iters)
     th = tv[:, kk - 1].contiguous()
-    t_f, (cs, cr, cnt) = timed(lambda: ops.score_filter(qn, cat, th, 32768), iters)
-    t_z, _ = timed(lambda: ops.filter_finalize(qn, cat, cs, cr, cnt, th, kk, k), iters)
-    t_inf, _ = timed(lambda: ops.score_filter(qn, cat, torch.full_like(th, float("inf")), 32768), iters)
+    t_f, fs = timed(lambda: ops.score_filter(qn, cat, th), iters)
+    t_z, _ = timed(lambda: ops.filter_finalize(qn, cat, fs, th, kk, k), iters)
+    t_inf, _ = timed(lambda: ops.score_filter(qn, cat, torch.full_like(th, float("inf"))), iters)
+    cnt = fs.counts()
     pt["stages_ms"] = {"sample_groupmax": round(t_g, 4), "topk_threshold": round(t_t, 4),
                        "score_filter": round(t_f, 4), "finalize": round(t_z, 4),
                        "score_filter_no_survivors": round(t_inf, 4)}
-    pt["survivors_per_query"] = {"mean": float(cnt.float().mean()), "max": int(cnt.max())}
+    pt["survivors_per_query"] = {"mean": float(cnt.float().mean()), "max": int(cnt.max()),
+                                 "spilled_to_overflow_max": int(fs.o_count.max()), "n_sub": fs.n_sub, "cap_b": fs.cap_b}
     pt["filter_TFLOPs"] = round(2.0 * u * n * d / t_f / 1e9, 1)
     pt["filter_catalog_GBs"] = round(n * d * 2.0 / t_f / 1e6, 1)
     print(json.dumps(pt), flush=True)

@@ -254,11 +254,13 @@ def test_groupmax_sampled_tiles(xr, u, n, stride):
     torch.testing.assert_close(got[:, :want.size(1)], want, rtol=2e-3, atol=2e-3)
 
 
+@pytest.mark.parametrize("cap_b", [None, 8])
 @pytest.mark.parametrize("u,n", [(3, 9000), (128, 30001), (129, 30001), (400, 12800)])
-def test_score_filter_survivors(xr, u, n):
-    """xr_score_filter: the survivor list of a query is EXACTLY the set of rows whose score is >= its
-    threshold (exact-arithmetic inputs), whatever order the scoring CTAs append them in; the
-    finalize step turns it into the oracle's top-k."""
+def test_score_filter_survivors(xr, u, n, cap_b):
+    """xr_score_filter: the survivors of a query are EXACTLY the rows whose score is >= its threshold
+    (exact-arithmetic inputs), wherever the scoring kernel stored them: sub-buckets filled without atomics
+    by their owning lanes, and -- with cap_b = 8 slots, which most sub-buckets overrun -- the query's
+    overflow list.  The finalize step turns them into the oracle's top-k."""
     from xfmr_rec_b200 import ops
 
     rng = np.random.default_rng(u * 31 + n)
@@ -266,22 +268,23 @@ def test_score_filter_survivors(xr, u, n):
     qs = rng.integers(-2, 3, size=(u, 384)).astype(np.float32)
     scores = qs @ cat.T
     th = np.sort(scores, axis=1)[:, -150].copy()               # ~150+ survivors per query (ties included)
-    th[0] = -np.inf if n <= 16384 else th[0]                    # a query that keeps everything
+    if n <= 16384:
+        th[0] = -np.inf                                         # a query that keeps everything
     th[-1] = np.inf                                             # and one that keeps nothing
-    cap = 16384
-    cs, cr, cnt = ops.score_filter(torch.from_numpy(qs).cuda().bfloat16(), torch.from_numpy(cat).cuda().bfloat16(),
-                                   torch.from_numpy(th).cuda(), cap)
-    cs, cr, cnt = cs.cpu().numpy(), cr.cpu().numpy(), cnt.cpu().numpy()
-    for r in range(u):
-        want = np.nonzero(scores[r] >= th[r])[0]
-        assert cnt[r] == len(want), (r, cnt[r], len(want))
-        order = np.argsort(cr[r, :cnt[r]])
-        assert np.array_equal(cr[r, :cnt[r]][order], want)
-        assert np.array_equal(cs[r, :cnt[r]][order], scores[r, want])
-    k = 20
     q16, c16 = torch.from_numpy(qs).cuda().bfloat16(), torch.from_numpy(cat).cuda().bfloat16()
-    s, i, flags = ops.filter_finalize(q16, c16, torch.from_numpy(cs).cuda(), torch.from_numpy(cr).cuda(),
-                                      torch.from_numpy(cnt).cuda(), torch.from_numpy(th).cuda(), 60, k, row_offset=1000)
+    tht = torch.from_numpy(th).cuda()
+    fs = ops.score_filter(q16, c16, tht, expected_survivors=n if n <= 16384 else 600, cap_b=cap_b, ovf_cap=16384)
+    counts = fs.counts().cpu().numpy()
+    for r, (sc, ro) in enumerate(fs.lists()):
+        want = np.nonzero(scores[r] >= th[r])[0]
+        assert counts[r] == len(want), (r, counts[r], len(want))
+        order = np.argsort(ro)
+        assert np.array_equal(ro[order], want)
+        assert np.array_equal(sc[order], scores[r, want])
+    if cap_b is not None:
+        assert int(fs.o_count.max()) > 0                        # the overflow tier was exercised
+    k = 20
+    s, i, flags = ops.filter_finalize(q16, c16, fs, tht, 60, k, row_offset=1000)
     # the last query kept nothing: it cannot vouch for the rows below its (infinite) threshold -> flag 4
     assert int(flags.item()) == 4
     want_s, want_i = orc.exact_search(qs[:-1], cat, k, None, metric="dot")

@@ -30,6 +30,7 @@
 // cycles, an mbarrier arrive -> waiter hand-off ~130.
 #include "common.cuh"
 #include "sm100.cuh"
+#include "filter.cuh"
 
 #include <cstring>
 
@@ -88,10 +89,7 @@ struct FusedParams {
   int tile_stride;     // KIND_GMAX: only every tile_stride-th 64-row catalog tile is scored (0 = 1)
   const float* thresh; // KIND_FILTER: thresh[u * thresh_stride]
   long long thresh_stride;
-  float* cand_scores;  // (m, cap)
-  int32_t* cand_rows;  // (m, cap) local catalog rows
-  int32_t* cand_count; // (m)
-  int cap;
+  FilterOut fo;        // KIND_FILTER: survivor storage (filter.cuh)
   int rb_count;
   int* hang_flag;
   long long* dbg;      // STATS builds: per-tile timestamps of CTA 0 (profiling aid)
@@ -570,6 +568,17 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
       float cnt = 0.f, sum_a = 0.f, sum_w = 0.f, diag_val = 0.f;
       AllAcc acc;
       acc.reset();
+      // KIND_FILTER: this lane's sub-bucket for the item = (row, catalog split, column group); its fill
+      // count lives in a register (see score_gmax2_sm100.cu)
+      const int sub = KIND == KIND_FILTER ? (slot / sh.rb_count) * CG + cg : 0;
+      float* b_scores = nullptr;
+      int32_t* b_rows = nullptr;
+      int bcount = 0;
+      if (KIND == KIND_FILTER && row_ok) {
+        const long long off = ((long long)row * p.fo.n_sub + sub) * p.fo.cap_b;
+        b_scores = p.fo.b_scores + off;
+        b_rows = p.fo.b_rows + off;
+      }
       for (int tl = 0; tl < T; ++tl) {
         const uint32_t tile = tt + tl;
         const uint32_t use = tile >> nsb_shift;
@@ -612,8 +621,7 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
             if (j < ncols) mx = fmaxf(mx, __uint_as_float(v[j]));
           if (row_ok) p.gmax[(long long)row * p.gmax_ld + (long long)(t0 + tl) * CG + cg] = mx;
         } else if (KIND == KIND_FILTER) {
-          // one test for the 16 scores: almost no lane-tile holds a survivor at the sample's threshold; a
-          // lane with survivors claims its slots with ONE atomic, then stores (see score_gmax2_sm100.cu)
+          // one test for the 16 scores: almost no lane-tile holds a survivor at the sample's threshold
           const int c0 = (t0 + tl) * BN + cg * 16;
           const int lim = sh.cn - c0;               // rows past cn are TMA zero fill, not catalog rows
           float mx = -CUDART_INF_F;
@@ -621,22 +629,10 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
           for (int j = 0; j < 16; ++j)
             if (j < lim) mx = fmaxf(mx, __uint_as_float(v[j]));
           if (mx >= t_eff && lim > 0) {
-            int cnt = 0;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) cnt += (__uint_as_float(v[j]) >= t_eff && j < lim) ? 1 : 0;
-            int w = atomicAdd(p.cand_count + row, cnt);
-            float* cs = p.cand_scores + (long long)row * p.cap;
-            int32_t* cr = p.cand_rows + (long long)row * p.cap;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float sc = __uint_as_float(v[j]);
-              if (sc >= t_eff && j < lim) {
-                if (w < p.cap) {
-                  cs[w] = sc;
-                  cr[w] = c0 + j;
-                }
-                ++w;
-              }
+              if (sc >= t_eff && j < lim) filter_keep(p.fo, row, b_scores, b_rows, bcount, sc, c0 + j);
             }
           }
         } else if (all_kind) {
@@ -685,7 +681,8 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
       if (diag) {
         if (row_ok && (r_local & 63) >> 4 == cg) p.t_out[row] = diag_val;
       } else if (retr) {
-        // nothing to flush: group maxima / survivors were written tile by tile
+        // group maxima / survivors were written tile by tile; the filter leaves its sub-bucket's count
+        if (KIND == KIND_FILTER && row_ok) p.fo.b_count[(long long)row * p.fo.n_sub + sub] = bcount;
       } else if (all_kind) {
         if (row_ok) {
           float4* ds = reinterpret_cast<float4*>(
@@ -1193,8 +1190,8 @@ namespace xr {
 int launch_score_gmax2(const void* q, int64_t u, const void* catalog, int64_t n, int tile_stride, float* gmax,
                        int64_t ld, int* hang_flag, cudaStream_t s, int ablate);
 int launch_score_filter2(const void* q, int64_t u, const void* catalog, int64_t n, const float* thresh,
-                         int64_t thresh_stride, float* cand_scores, int32_t* cand_rows, int32_t* cand_count,
-                         int64_t cap, int* hang_flag, cudaStream_t s);
+                         int64_t thresh_stride, const FilterOut& fo, int* hang_flag, cudaStream_t s);
+int gmax2_splits(int64_t u, int64_t n);
 }
 extern "C" int xr_fused_available(void) { return 3; }  // bit 0: fused loss, bit 1: fused retrieval scoring
 
@@ -1784,39 +1781,62 @@ extern "C" int xr_score_groupmax(const void* q, int64_t u, const void* catalog, 
 }
 
 // ---- retrieval: threshold filter in the scoring epilogue ---------------------------------------------
-// Every (score, local row) with score >= thresh[u * thresh_stride] is appended to query u's list
-// (cand_scores / cand_rows, `cap` slots per query, unordered); cand_count[u] (zeroed by the caller) counts
-// the survivors and keeps counting past `cap`, which is how the consumer detects an overflow.  With
-// thresholds from a sample (xr_score_groupmax with tile_stride = s: the (k+E)-th largest group maximum of
-// the sample is <= the (k+E)-th largest score of the catalog) about (k+E) * s rows survive per query, so
-// nothing of size U x N ever reaches HBM: the catalog is read once and ~KBs per query are written.
+// Every (score, local row) with score >= thresh[u * thresh_stride] is kept.  Storage: n_sub sub-buckets
+// of cap_b slots per query, one per (catalog split of the scoring plan, column group) -- each owned by a
+// single lane, filled without atomics -- plus one overflow list of ovf_cap slots per query for sub-buckets
+// that run full (clustered catalogs).  b_count[u][s] = survivors sub-bucket s saw (> cap_b: the excess is
+// in the overflow list), o_count[u] (zeroed by the caller) keeps counting past ovf_cap, which is how the
+// consumer detects a loss.  With thresholds from a sample (xr_score_groupmax with tile_stride = s: the
+// (k+28)-th largest group maximum of the sample is <= the (k+28)-th largest score of the catalog) about
+// (k+28) * s rows survive per query: the catalog is read once and ~KBs per query are written.
+extern "C" int xr_score_filter_layout(int64_t u, int64_t n, int64_t expected_survivors, int64_t* n_sub,
+                                      int64_t* cap_b) {
+  XR_CHECK_ARG(u > 0 && n > 0 && n_sub && cap_b && expected_survivors >= 0, "xr_score_filter_layout: bad arguments");
+  int64_t subs;
+  if (retr_tile_rows(u) == 128) subs = 4ll * gmax2_splits(u, n);
+  else subs = (int64_t)fk::CG * make_gmax_plan(u, n, sm_count()).spl;
+  *n_sub = subs;
+  // four times the expected fill (+ slack), multiples of 8 slots: random catalogs never spill
+  int64_t c = (4 * expected_survivors + subs - 1) / subs + 8;
+  c = (c + 7) / 8 * 8;
+  if (c < 16) c = 16;
+  if (c > 4096) c = 4096;
+  *cap_b = c;
+  return XR_OK;
+}
+
 extern "C" int xr_score_filter(const void* q, int64_t u, const void* catalog, int64_t n, int64_t dim,
-                               const float* thresh, int64_t thresh_stride, float* cand_scores,
-                               int32_t* cand_rows, int32_t* cand_count, int64_t cap, void* stream) {
+                               const float* thresh, int64_t thresh_stride, float* bucket_scores,
+                               int32_t* bucket_rows, int32_t* bucket_count, int64_t n_sub, int64_t cap_b,
+                               float* ovf_scores, int32_t* ovf_rows, int32_t* ovf_count, int64_t ovf_cap,
+                               void* stream) {
   int rc;
   if ((rc = check_retr_args("xr_score_filter", q, u, catalog, n, dim))) return rc;
-  XR_CHECK_ARG(thresh && cand_scores && cand_rows && cand_count && cap >= 1 && cap < (1ll << 30) &&
+  XR_CHECK_ARG(thresh && bucket_scores && bucket_rows && bucket_count && ovf_scores && ovf_rows && ovf_count &&
+                   n_sub >= 1 && cap_b >= 1 && cap_b <= (1 << 20) && ovf_cap >= 1 && ovf_cap < (1ll << 30) &&
                    thresh_stride >= 0,
                "xr_score_filter: bad arguments");
   cudaStream_t s = as_stream(stream);
   int* hang = retr_hang_flag();
   XR_CHECK_ARG(hang, "xr_score_filter: out of device memory");
+  const FilterOut fo{bucket_scores, bucket_rows, bucket_count, ovf_scores, ovf_rows, ovf_count,
+                     (int)n_sub, (int)cap_b, (int)ovf_cap};
   const bool prof = g_prof_on && g_prof_n < kProfRing;
   if (prof) cudaEventRecord(g_prof_ev[g_prof_n][0], s);
   if (retr_tile_rows(u) == 128) {
-    rc = launch_score_filter2(q, u, catalog, n, thresh, thresh_stride, cand_scores, cand_rows, cand_count,
-                              cap, hang, s);
+    rc = launch_score_filter2(q, u, catalog, n, thresh, thresh_stride, fo, hang, s);
   } else {
     const int n_sm = sm_count();
     const GmaxPlan pl = make_gmax_plan(u, n, n_sm);
+    XR_CHECK_ARG(n_sub == (int64_t)fk::CG * pl.spl, "xr_score_filter: n_sub must be %d for this (u, n) (xr_score_filter_layout)",
+                 fk::CG * pl.spl);
     CUtensorMap tq, tc;
     if ((rc = make_tmap_bf16_rows(&tq, q, u, dim, dim, fk::BM))) return rc;
     if ((rc = make_tmap_bf16_rows(&tc, catalog, n, dim, dim, fk::BN))) return rc;
     FusedParams p{};
     p.m = (int)u; p.cn = (int)n; p.nt_count = pl.nt; p.spl = pl.spl; p.tiles_per_split = pl.tps;
     p.n_items = pl.n_items; p.rb_count = pl.rb; p.hang_flag = hang;
-    p.thresh = thresh; p.thresh_stride = thresh_stride; p.cand_scores = cand_scores;
-    p.cand_rows = cand_rows; p.cand_count = cand_count; p.cap = (int)cap;
+    p.thresh = thresh; p.thresh_stride = thresh_stride; p.fo = fo;
     rc = launch_fused1<fk::KIND_FILTER, false>(tq, tc, p, pl.n_items < n_sm ? pl.n_items : n_sm, s);
   }
   if (prof) cudaEventRecord(g_prof_ev[g_prof_n++][1], s);

@@ -3,8 +3,12 @@
 //   MODE_GMAX    gmax[u, g] = max over the 16 catalog rows of group g of q_u . cat_c, optionally over
 //                every `tile_stride`-th 128-row tile only (the SAMPLE whose (k+E)-th largest maximum is
 //                a lower bound of the (k+E)-th largest score of the whole catalog);
-//   MODE_FILTER  every (score, row) with score >= thresh[u] is appended to query u's candidate list:
-//                the (U, N) score matrix never reaches HBM, and neither does anything of size U x N / 16.
+//   MODE_FILTER  every (score, row) with score >= thresh[u] is kept: the (U, N) score matrix never reaches
+//                HBM, and neither does anything of size U x N / 16.  Survivors go to SUB-BUCKETS owned by
+//                one (row, catalog split, column group) each, i.e. by exactly one lane of one warp, whose
+//                fill count lives in a register: no atomic, no L2 round trip on the scoring path (a
+//                returning global atomic per survivor cost 0.2 ms of a 1.6 ms kernel).  A full sub-bucket
+//                spills to the query's overflow list, the only place an atomic is left.
 //
 // Why pairs: shared-memory ingest by TMA is ~35 B/cycle/SM whatever the ring depth or multicast
 // (profiles/microbench/tma_stream.cu), and a 128-query CTA needs 48 KB per 64 candidates = 1,400
@@ -18,6 +22,7 @@
 // warps 4-19 epilogue over the CTA's own 128 TMEM lanes.  TMEM: 4 S buffers of 128 columns.
 #include "common.cuh"
 #include "sm100.cuh"
+#include "filter.cuh"
 
 namespace xr {
 
@@ -53,10 +58,7 @@ struct Gmax2Params {
   long long gmax_ld;
   const float* thresh;   // MODE_FILTER: thresh[u * thresh_stride]
   long long thresh_stride;
-  float* cand_scores;    // (u, cap)
-  int32_t* cand_rows;    // (u, cap) local catalog rows
-  int32_t* cand_count;   // (u): appended so far; may run past cap (overflow is detected by the consumer)
-  int cap;
+  FilterOut fo;          // MODE_FILTER: survivor storage (filter.cuh)
   int* hang_flag;
   int ctrl_low;
   int ablate;   // DBG instantiation only: 1 skip catalog TMA, 2 skip epilogue TMEM loads, 4 skip gmax stores, 8 skip MMAs
@@ -270,6 +272,16 @@ score_gmax2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       // a row past u never passes the filter; NaN thresholds cannot occur (they are group maxima)
       const float th = (MODE == MODE_FILTER && row_ok) ? __ldg(p.thresh + (long long)row * p.thresh_stride)
                                                        : CUDART_INF_F;
+      // this lane's sub-bucket for the item: (row, split of the catalog, column group)
+      const int sub = (item / p.qb_count) * 4 + cg;
+      float* b_scores = nullptr;
+      int32_t* b_rows = nullptr;
+      int bcount = 0;
+      if (MODE == MODE_FILTER && row_ok) {
+        const long long off = ((long long)row * p.fo.n_sub + sub) * p.fo.cap_b;
+        b_scores = p.fo.b_scores + off;
+        b_rows = p.fo.b_rows + off;
+      }
       for (int t = t0; t < t1; ++t, ++tile) {
         const int sb = tile % NSB;
         mbar_wait(bar_s_full(sb), (tile / NSB) & 1, p.hang_flag, 8);
@@ -299,9 +311,7 @@ score_gmax2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           if (row_ok && !(DBG && (p.ablate & 4)))
             *reinterpret_cast<float2*>(out_row + 8ll * t + 2 * cg) = make_float2(m0, m1);
         } else {
-          // one test for the 32 scores keeps the common case (no survivor) at one instruction per score;
-          // a lane with survivors counts them, claims its slots with ONE atomic (the L2 round trip is
-          // paid once per lane-tile, concurrently for all lanes of the warp) and then stores
+          // one test for the 32 scores keeps the common case (no survivor) at one instruction per score
           const int lim = p.n - c0;                 // rows past n are TMA zero fill, not catalog rows
           if (lim < 32) {
 #pragma unroll
@@ -312,26 +322,15 @@ score_gmax2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 #pragma unroll
           for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
           if (mx >= th && lim > 0) {
-            int cnt = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) cnt += (__uint_as_float(v[j]) >= th && j < lim) ? 1 : 0;
-            int w = atomicAdd(p.cand_count + row, cnt);
-            float* cs = p.cand_scores + (long long)row * p.cap;
-            int32_t* cr = p.cand_rows + (long long)row * p.cap;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float sc = __uint_as_float(v[j]);
-              if (sc >= th && j < lim) {
-                if (w < p.cap) {
-                  cs[w] = sc;
-                  cr[w] = c0 + j;
-                }
-                ++w;
-              }
+              if (sc >= th && j < lim) filter_keep(p.fo, row, b_scores, b_rows, bcount, sc, c0 + j);
             }
           }
         }
       }
+      if (MODE == MODE_FILTER && row_ok) p.fo.b_count[(long long)row * p.fo.n_sub + sub] = bcount;
     }
   }
   tc_fence_before();
@@ -411,14 +410,24 @@ int launch_score_gmax2(const void* q, int64_t u, const void* catalog, int64_t n,
   return launch_gmax2_mode<MODE_GMAX>(q, u, catalog, n, p, s, ablate);
 }
 
-// host: called by xr_score_filter for u > 128
-int launch_score_filter2(const void* q, int64_t u, const void* catalog, int64_t n, const float* thresh,
-                         int64_t thresh_stride, float* cand_scores, int32_t* cand_rows, int32_t* cand_count,
-                         int64_t cap, int* hang_flag, cudaStream_t s) {
+// catalog splits of the pair kernel for (u, n): the number of sub-buckets per query is 4 x this
+int gmax2_splits(int64_t u, int64_t n) {
   Gmax2Params p{};
   plan_gmax2(p, u, n, 1, sm_count() / 2);
+  return p.spl;
+}
+
+// host: called by xr_score_filter for u > 128
+int launch_score_filter2(const void* q, int64_t u, const void* catalog, int64_t n, const float* thresh,
+                         int64_t thresh_stride, const FilterOut& fo, int* hang_flag, cudaStream_t s) {
+  Gmax2Params p{};
+  plan_gmax2(p, u, n, 1, sm_count() / 2);
+  if (fo.n_sub != p.spl * 4) {
+    set_error("xr_score_filter: n_sub must be %d for this (u, n) (xr_score_filter_layout)", p.spl * 4);
+    return XR_E_INVALID;
+  }
   p.thresh = thresh; p.thresh_stride = thresh_stride;
-  p.cand_scores = cand_scores; p.cand_rows = cand_rows; p.cand_count = cand_count; p.cap = (int)cap;
+  p.fo = fo;
   p.hang_flag = hang_flag;
   return launch_gmax2_mode<MODE_FILTER>(q, u, catalog, n, p, s, 0);
 }

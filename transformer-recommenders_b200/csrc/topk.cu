@@ -13,6 +13,7 @@
 // Selection on a strict total order makes single-GPU, chunked and sharded results identical.
 #include "common.cuh"
 #include "rowdot.cuh"
+#include "filter.cuh"
 
 namespace xr {
 
@@ -443,10 +444,8 @@ __global__ void groups_to_rows_kernel(const int64_t* __restrict__ gi, int64_t to
 // filtered): otherwise flag 4 tells the caller to take another path.
 __global__ void __launch_bounds__(TK_THREADS)
 filter_finalize_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ cat, int64_t n,
-                       const float* __restrict__ cand_scores, const int32_t* __restrict__ cand_rows,
-                       const int32_t* __restrict__ cand_count, int64_t cap,
-                       const float* __restrict__ thresh, int64_t thresh_stride, int k_sel, int k,
-                       int64_t row_offset, const int64_t* __restrict__ offs,
+                       const FilterOut fo, const float* __restrict__ thresh, int64_t thresh_stride, int k_sel,
+                       int k, int64_t row_offset, const int64_t* __restrict__ offs,
                        const int64_t* __restrict__ excl, int64_t max_excl, float* __restrict__ out_scores,
                        int64_t* __restrict__ out_idx, int32_t* __restrict__ flags) {
   __shared__ uint64_t s_keys[TK_CAP];
@@ -455,34 +454,64 @@ filter_finalize_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16*
   __shared__ int64_t s_rows[TK_MAX_K];
   __shared__ float s_sc[TK_MAX_K];
   __shared__ int s_alive;
+  __shared__ int s_total;
   TopkState st{s_keys, &s_count, &s_tau};
   const int64_t u = blockIdx.x;
-  const int64_t cnt_raw = cand_count[u];
-  const int64_t cnt = cnt_raw < cap ? cnt_raw : cap;
+  const int64_t ovf_raw = fo.o_count[u];
+  const int64_t n_ovf = ovf_raw < fo.ovf_cap ? ovf_raw : fo.ovf_cap;
   if (threadIdx.x == 0) {
     s_count = 0;
     s_tau = 0ull;
     s_alive = 0;
-    int bad = cnt_raw > cap ? 1 : 0;                                   // survivors were dropped
+    s_total = 0;
+    int bad = ovf_raw > fo.ovf_cap ? 1 : 0;                            // survivors were dropped
     if (offs && offs[u + 1] - offs[u] > max_excl) bad |= 2;            // thresholds assumed fewer exclusions
     if (bad) atomicOr(flags, bad);
   }
   __syncthreads();
-  const float* cs = cand_scores + u * cap;
-  const int32_t* cr = cand_rows + u * cap;
-  const int64_t iters = (cnt + TK_PER_ITER - 1) / TK_PER_ITER;
-  for (int64_t it = 0; it < iters; ++it) {
-    if (*st.count > TK_CAP - TK_PER_ITER) compact_select(st, k_sel);
-    const uint64_t tau = *st.tau;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int64_t e = it * TK_PER_ITER + r * TK_THREADS + threadIdx.x;
-      const bool in = e < cnt;
-      const uint64_t key = in ? make_key(__ldcg(cs + e), (uint32_t)__ldcg(cr + e)) : 0ull;
+  // survivors of the sub-buckets: every thread walks one sub-bucket at a time (the fill counts differ, so
+  // the loop runs to the longest one of the round; a round is 256 sub-buckets)
+  int my_total = 0;
+  for (int base = 0; base < fo.n_sub; base += TK_THREADS) {
+    const int sb = base + threadIdx.x;
+    int c = 0;
+    const float* bs = nullptr;
+    const int32_t* br = nullptr;
+    if (sb < fo.n_sub) {
+      c = __ldcg(fo.b_count + u * fo.n_sub + sb);
+      my_total += c;
+      if (c > fo.cap_b) c = fo.cap_b;                                  // the excess is in the overflow list
+      bs = fo.b_scores + (u * fo.n_sub + sb) * fo.cap_b;
+      br = fo.b_rows + (u * fo.n_sub + sb) * fo.cap_b;
+    }
+    for (int e = 0; __syncthreads_or(e < c); ++e) {
+      if (*st.count > TK_CAP - TK_THREADS) compact_select(st, k_sel);
+      const uint64_t tau = *st.tau;
+      const bool in = e < c;
+      const uint64_t key = in ? make_key(__ldcg(bs + e), (uint32_t)__ldcg(br + e)) : 0ull;
       offer(st, in && key > tau, key);
     }
-    __syncthreads();
   }
+  __syncthreads();
+  {  // the overflow list
+    const float* cs = fo.o_scores + u * fo.ovf_cap;
+    const int32_t* cr = fo.o_rows + u * fo.ovf_cap;
+    const int64_t iters = (n_ovf + TK_PER_ITER - 1) / TK_PER_ITER;
+    for (int64_t it = 0; it < iters; ++it) {
+      if (*st.count > TK_CAP - TK_PER_ITER) compact_select(st, k_sel);
+      const uint64_t tau = *st.tau;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int64_t e = it * TK_PER_ITER + r * TK_THREADS + threadIdx.x;
+        const bool in = e < n_ovf;
+        const uint64_t key = in ? make_key(__ldcg(cs + e), (uint32_t)__ldcg(cr + e)) : 0ull;
+        offer(st, in && key > tau, key);
+      }
+      __syncthreads();
+    }
+  }
+  my_total = __reduce_add_sync(0xffffffffu, my_total);
+  if ((threadIdx.x & 31) == 0 && my_total) atomicAdd(&s_total, my_total);
   compact_select(st, k_sel);
   compact(st, k_sel);   // s_keys[0, c) in descending key order
   const int c = s_count < k_sel ? s_count : k_sel;
@@ -510,7 +539,7 @@ filter_finalize_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16*
   alive = __reduce_add_sync(0xffffffffu, alive);
   if ((threadIdx.x & 31) == 0 && alive) atomicAdd(&s_alive, alive);
   __syncthreads();
-  if (threadIdx.x == 0 && cnt_raw <= k_sel && s_alive < k_sel - (int)max_excl &&
+  if (threadIdx.x == 0 && s_total <= k_sel && s_alive < k_sel - (int)max_excl &&
       thresh[u * thresh_stride] > -CUDART_INF_F)
     atomicOr(flags, 4);   // too few non-excluded survivors to vouch for the rows below the threshold
   bitonic_desc(s_keys, n2);
@@ -762,35 +791,43 @@ extern "C" int xr_groups_to_rows(const int64_t* group_ids, int64_t u, int64_t kg
 }
 
 extern "C" int xr_filter_finalize(const void* q, int64_t u, const void* catalog, int64_t n, int64_t dim,
-                                  const float* cand_scores, const int32_t* cand_rows,
-                                  const int32_t* cand_count, int64_t cap, const float* thresh,
-                                  int64_t thresh_stride, int64_t k_sel, int64_t k,
-                                  int64_t row_offset, const int64_t* excl_offsets, const int64_t* excl_ids,
-                                  int64_t max_excl, float* out_scores, int64_t* out_idx, int32_t* flags,
-                                  void* stream) {
-  XR_CHECK_ARG(q && catalog && cand_scores && cand_rows && cand_count && thresh && out_scores && out_idx && flags,
+                                  const float* bucket_scores, const int32_t* bucket_rows,
+                                  const int32_t* bucket_count, int64_t n_sub, int64_t cap_b,
+                                  const float* ovf_scores, const int32_t* ovf_rows, const int32_t* ovf_count,
+                                  int64_t ovf_cap, const float* thresh, int64_t thresh_stride, int64_t k_sel,
+                                  int64_t k, int64_t row_offset, const int64_t* excl_offsets,
+                                  const int64_t* excl_ids, int64_t max_excl, float* out_scores,
+                                  int64_t* out_idx, int32_t* flags, void* stream) {
+  XR_CHECK_ARG(q && catalog && bucket_scores && bucket_rows && bucket_count && ovf_scores && ovf_rows &&
+                   ovf_count && thresh && out_scores && out_idx && flags,
                "xr_filter_finalize: null pointer");
-  XR_CHECK_ARG(max_excl >= 0 && k_sel >= k + max_excl, "xr_filter_finalize: k_sel must be >= k + max_excl");
   XR_CHECK_ARG(dim == FD, "xr_filter_finalize: this build is specialised for dim = %d", FD);
-  XR_CHECK_ARG(u >= 0 && n > 0 && cap >= 1 && k >= 1 && k_sel >= k && k_sel <= TK_MAX_K,
+  XR_CHECK_ARG(u >= 0 && n > 0 && n_sub >= 1 && cap_b >= 1 && ovf_cap >= 1 && k >= 1 && k_sel >= k &&
+                   k_sel <= TK_MAX_K,
                "xr_filter_finalize: needs 1 <= k <= k_sel <= %d", TK_MAX_K);
+  XR_CHECK_ARG(max_excl >= 0 && k_sel >= k + max_excl, "xr_filter_finalize: k_sel must be >= k + max_excl");
   XR_CHECK_ARG(row_offset >= 0 && row_offset + n <= (1ll << 32), "xr_filter_finalize: global ids must be < 2^32");
   XR_CHECK_ARG(!excl_offsets || excl_ids, "xr_filter_finalize: excl_offsets without excl_ids");
   if (u == 0) return XR_OK;
+  const FilterOut fo{const_cast<float*>(bucket_scores), const_cast<int32_t*>(bucket_rows),
+                     const_cast<int32_t*>(bucket_count), const_cast<float*>(ovf_scores),
+                     const_cast<int32_t*>(ovf_rows), const_cast<int32_t*>(ovf_count), (int)n_sub, (int)cap_b,
+                     (int)ovf_cap};
   filter_finalize_kernel<<<(unsigned)u, TK_THREADS, 0, as_stream(stream)>>>(
-      (const __nv_bfloat16*)q, (const __nv_bfloat16*)catalog, n, cand_scores, cand_rows, cand_count, cap,
-      thresh, thresh_stride, (int)k_sel, (int)k, row_offset, excl_offsets, excl_ids, max_excl, out_scores, out_idx, flags);
+      (const __nv_bfloat16*)q, (const __nv_bfloat16*)catalog, n, fo, thresh, thresh_stride, (int)k_sel, (int)k,
+      row_offset, excl_offsets, excl_ids, max_excl, out_scores, out_idx, flags);
   XR_LAUNCH_CHECK("filter_finalize");
   return XR_OK;
 }
 
 // ---- the whole local search as one call ------------------------------------------------------------
 namespace xr {
-constexpr int64_t kFilterCap = 32768;   // survivor slots per query
-constexpr int kFilterMargin = 28;       // rank positions of slack between the two score arithmetics
+constexpr int64_t kFilterOvfCap = 8192;   // overflow slots per query (sub-buckets that run full spill here)
+constexpr int64_t kFilterTarget = 4096;   // survivors per query the sample stride aims at
+constexpr int kFilterMargin = 28;         // rank positions of slack between the two score arithmetics
 struct ScoreTopkPlan {
-  int64_t kk, k_sel, stride, ld_s, cap;
-  size_t off_gmax, off_tkws, off_vals, off_idx, off_cs, off_cr, off_cnt, bytes, tkws_bytes;
+  int64_t kk, k_sel, stride, ld_s, n_sub, cap_b;
+  size_t off_gmax, off_tkws, off_vals, off_idx, off_bs, off_br, off_bc, off_os, off_or, off_oc, bytes, tkws_bytes;
 };
 static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 static ScoreTopkPlan plan_score_topk(int64_t u, int64_t n, int64_t k, int64_t max_excl) {
@@ -799,25 +836,30 @@ static ScoreTopkPlan plan_score_topk(int64_t u, int64_t n, int64_t k, int64_t ma
   // ~ (k + margin) * stride rows survive, of which at most max_excl are excluded afterwards
   pl.kk = k + kFilterMargin;
   pl.k_sel = k + max_excl + kFilterMargin;
-  pl.cap = kFilterCap;
-  // sample stride (in tiles of the scoring kernel): the expected number of survivors is ~kk * stride, so
-  // kk * stride * 3 <= cap; and the sample keeps at least 4 kk groups so that its kk-th maximum exists
-  int64_t s = pl.cap / (3 * pl.kk);
+  // sample stride (in tiles of the scoring kernel): ~kk * stride survivors per query, and the sample keeps
+  // at least 4 kk groups so that its kk-th maximum exists
+  int64_t s = kFilterTarget / pl.kk;
   if (s > 32) s = 32;
   const int64_t groups = (n + 15) / 16;
   while (s > 1 && groups / s < 4 * pl.kk) --s;
   if (s < 1) s = 1;
   pl.stride = s;
   pl.ld_s = (xr_score_groupmax_ld(u, n, s) + 3) / 4 * 4;   // 16-byte aligned rows: the streaming top-k path
+  // tiny catalogs: the threshold may be -inf (fewer sample groups than kk) and EVERY row survives
+  const int64_t expect = groups < 4 * pl.kk * s ? n : pl.kk * s;
+  xr_score_filter_layout(u, n, expect, &pl.n_sub, &pl.cap_b);
   size_t o = 0;
   pl.off_gmax = o; o += al256((size_t)u * pl.ld_s * 4);
   pl.tkws_bytes = xr_topk_workspace_bytes(u, pl.ld_s, pl.kk);
   pl.off_tkws = o; o += al256(pl.tkws_bytes);
   pl.off_vals = o; o += al256((size_t)u * pl.kk * 4);
   pl.off_idx = o;  o += al256((size_t)u * pl.kk * 8);
-  pl.off_cs = o;   o += al256((size_t)u * pl.cap * 4);
-  pl.off_cr = o;   o += al256((size_t)u * pl.cap * 4);
-  pl.off_cnt = o;  o += al256((size_t)u * 4);
+  pl.off_bs = o;   o += al256((size_t)u * pl.n_sub * pl.cap_b * 4);
+  pl.off_br = o;   o += al256((size_t)u * pl.n_sub * pl.cap_b * 4);
+  pl.off_bc = o;   o += al256((size_t)u * pl.n_sub * 4);
+  pl.off_os = o;   o += al256((size_t)u * kFilterOvfCap * 4);
+  pl.off_or = o;   o += al256((size_t)u * kFilterOvfCap * 4);
+  pl.off_oc = o;   o += al256((size_t)u * 4);
   pl.bytes = o;
   return pl;
 }
@@ -847,13 +889,16 @@ extern "C" int xr_score_topk(const void* q, int64_t u, const void* catalog, int6
   float* gmax = (float*)(w + pl.off_gmax);
   float* vals = (float*)(w + pl.off_vals);
   int64_t* idx = (int64_t*)(w + pl.off_idx);
-  float* cs = (float*)(w + pl.off_cs);
-  int32_t* cr = (int32_t*)(w + pl.off_cr);
-  int32_t* cnt = (int32_t*)(w + pl.off_cnt);
+  float* bs = (float*)(w + pl.off_bs);
+  int32_t* br = (int32_t*)(w + pl.off_br);
+  int32_t* bc = (int32_t*)(w + pl.off_bc);
+  float* os = (float*)(w + pl.off_os);
+  int32_t* orows = (int32_t*)(w + pl.off_or);
+  int32_t* oc = (int32_t*)(w + pl.off_oc);
   cudaStream_t s = as_stream(stream);
   int rc;
   // 1. thresholds: the kk-th largest group maximum of a strided sample of the shard (-inf when the sample
-  //    has fewer groups: every row then survives, and cap >= n in that regime)
+  //    has fewer groups: every row then survives; the sub-buckets are sized for that regime)
   const int64_t ld_used = xr_score_groupmax_ld(u, n, pl.stride);
   if (ld_used < pl.ld_s) {   // padding columns of the aligned row stride
     fill_neg_inf_kernel<<<(unsigned)((u * pl.ld_s + 255) / 256 < 1184 ? (u * pl.ld_s + 255) / 256 : 1184), 256, 0, s>>>(
@@ -864,12 +909,14 @@ extern "C" int xr_score_topk(const void* q, int64_t u, const void* catalog, int6
   if ((rc = xr_topk(gmax, u, pl.ld_s, pl.ld_s, pl.kk, 0, vals, idx, w + pl.off_tkws, pl.tkws_bytes, stream)))
     return rc;
   // 2. one pass over the shard: survivors of the filter
-  XR_CUDA(cudaMemsetAsync(cnt, 0, (size_t)u * 4, s));
-  if ((rc = xr_score_filter(q, u, catalog, n, dim, vals + (pl.kk - 1), pl.kk, cs, cr, cnt, pl.cap, stream)))
+  XR_CUDA(cudaMemsetAsync(oc, 0, (size_t)u * 4, s));
+  if ((rc = xr_score_filter(q, u, catalog, n, dim, vals + (pl.kk - 1), pl.kk, bs, br, bc, pl.n_sub, pl.cap_b, os,
+                            orows, oc, kFilterOvfCap, stream)))
     return rc;
   // 3. survivors -> exact top-k
-  return xr_filter_finalize(q, u, catalog, n, dim, cs, cr, cnt, pl.cap, vals + (pl.kk - 1), pl.kk, pl.k_sel, k,
-                            row_offset, excl_offsets, excl_ids, max_excl, out_scores, out_idx, flags, stream);
+  return xr_filter_finalize(q, u, catalog, n, dim, bs, br, bc, pl.n_sub, pl.cap_b, os, orows, oc, kFilterOvfCap,
+                            vals + (pl.kk - 1), pl.kk, pl.k_sel, k, row_offset, excl_offsets, excl_ids, max_excl,
+                            out_scores, out_idx, flags, stream);
 }
 
 extern "C" int xr_retrieval_metrics(const int64_t* rec, int64_t u, int64_t k,

@@ -458,26 +458,58 @@ def mask_excluded_ids(score_mat, ids, id_lo, id_hi, exclude=None):
     return score_mat
 
 
-def score_filter(q, catalog, thresh, cap):
-    """Scoring pass with the threshold filter in the epilogue (xr_score_filter): returns the unordered
-    survivor lists (scores (U, cap) fp32, rows (U, cap) int32, counts (U,) int32 — a count above
-    ``cap`` means that query's list is incomplete)."""
+class FilterSurvivors:
+    """Survivor storage of xr_score_filter: ``n_sub`` sub-buckets of ``cap_b`` slots per query (each filled
+    by one lane of the scoring kernel, no atomics) + one overflow list per query."""
+
+    def __init__(self, u, n_sub, cap_b, ovf_cap, device):
+        self.u, self.n_sub, self.cap_b, self.ovf_cap = u, n_sub, cap_b, ovf_cap
+        self.b_scores = torch.empty((u, n_sub, cap_b), dtype=torch.float32, device=device)
+        self.b_rows = torch.empty((u, n_sub, cap_b), dtype=torch.int32, device=device)
+        self.b_count = torch.empty((u, n_sub), dtype=torch.int32, device=device)
+        self.o_scores = torch.empty((u, ovf_cap), dtype=torch.float32, device=device)
+        self.o_rows = torch.empty((u, ovf_cap), dtype=torch.int32, device=device)
+        self.o_count = torch.zeros(u, dtype=torch.int32, device=device)
+
+    def counts(self) -> torch.Tensor:
+        """survivors per query (sub-bucket counts include what spilled to the overflow list)"""
+        return self.b_count.sum(1)
+
+    def lists(self):
+        """per query: (scores, rows) numpy arrays of every stored survivor (tests / diagnostics)."""
+        bc = self.b_count.cpu().numpy()
+        bs, br = self.b_scores.cpu().numpy(), self.b_rows.cpu().numpy()
+        oc = self.o_count.cpu().numpy()
+        os_, or_ = self.o_scores.cpu().numpy(), self.o_rows.cpu().numpy()
+        import numpy as np
+
+        out = []
+        for r in range(self.u):
+            sc = [bs[r, s, :min(c, self.cap_b)] for s, c in enumerate(bc[r])] + [os_[r, :min(oc[r], self.ovf_cap)]]
+            ro = [br[r, s, :min(c, self.cap_b)] for s, c in enumerate(bc[r])] + [or_[r, :min(oc[r], self.ovf_cap)]]
+            out.append((np.concatenate(sc), np.concatenate(ro)))
+        return out
+
+
+def score_filter(q, catalog, thresh, expected_survivors=4096, cap_b=None, ovf_cap=8192):
+    """Scoring pass with the threshold filter in the epilogue (xr_score_filter): returns the survivor
+    storage (:class:`FilterSurvivors`)."""
     dev = _require_cuda(q, catalog, thresh)
     q, catalog = q.contiguous(), catalog.contiguous()
     thresh = thresh.contiguous().float()
-    u = q.size(0)
-    cs = torch.empty((u, cap), dtype=torch.float32, device=dev)
-    cr = torch.empty((u, cap), dtype=torch.int32, device=dev)
-    cnt = torch.zeros(u, dtype=torch.int32, device=dev)
+    u, n = q.size(0), catalog.size(0)
+    n_sub, cb = C.c_int64(), C.c_int64()
+    N.call("xr_score_filter_layout", u, n, expected_survivors, C.byref(n_sub), C.byref(cb))
+    fs = FilterSurvivors(u, n_sub.value, cap_b or cb.value, ovf_cap, dev)
     with _on(dev):
-        N.call("xr_score_filter", _p(q), u, _p(catalog), catalog.size(0), q.size(1), _p(thresh), 1,
-               _p(cs), _p(cr), _p(cnt), cap, _stream())
-    return cs, cr, cnt
+        N.call("xr_score_filter", _p(q), u, _p(catalog), n, q.size(1), _p(thresh), 1, _p(fs.b_scores),
+               _p(fs.b_rows), _p(fs.b_count), fs.n_sub, fs.cap_b, _p(fs.o_scores), _p(fs.o_rows),
+               _p(fs.o_count), fs.ovf_cap, _stream())
+    return fs
 
 
-def filter_finalize(q, catalog, cs, cr, cnt, thresh, k_sel, k, row_offset=0, exclude=None, max_excl=0,
-                    flags=None):
-    dev = _require_cuda(q, catalog, cs, cr, cnt, thresh)
+def filter_finalize(q, catalog, fs, thresh, k_sel, k, row_offset=0, exclude=None, max_excl=0, flags=None):
+    dev = _require_cuda(q, catalog, thresh)
     thresh = thresh.contiguous().float()
     offs, ex = (None, None) if exclude is None else exclude
     u = q.size(0)
@@ -486,8 +518,9 @@ def filter_finalize(q, catalog, cs, cr, cnt, thresh, k_sel, k, row_offset=0, exc
     if flags is None:
         flags = torch.zeros(1, dtype=torch.int32, device=dev)
     with _on(dev):
-        N.call("xr_filter_finalize", _p(q), u, _p(catalog), catalog.size(0), q.size(1), _p(cs), _p(cr),
-               _p(cnt), cs.size(1), _p(thresh), 1, k_sel, k, row_offset, _p(offs), _p(ex), max_excl,
+        N.call("xr_filter_finalize", _p(q), u, _p(catalog), catalog.size(0), q.size(1), _p(fs.b_scores),
+               _p(fs.b_rows), _p(fs.b_count), fs.n_sub, fs.cap_b, _p(fs.o_scores), _p(fs.o_rows),
+               _p(fs.o_count), fs.ovf_cap, _p(thresh), 1, k_sel, k, row_offset, _p(offs), _p(ex), max_excl,
                _p(out_s), _p(out_i), _p(flags), _stream())
     return out_s, out_i, flags
 
