@@ -281,8 +281,8 @@ def test_score_filter_survivors(xr, u, n, cap_b):
         order = np.argsort(ro)
         assert np.array_equal(ro[order], want)
         assert np.array_equal(sc[order], scores[r, want])
-    if cap_b is not None:
-        assert int(fs.o_count.max()) > 0                        # the overflow tier was exercised
+    if cap_b is not None and n <= 16384:
+        assert int(fs.o_count.max()) > 0                        # the keep-everything query spilled: overflow tier exercised
     k = 20
     s, i, flags = ops.filter_finalize(q16, c16, fs, tht, 60, k, row_offset=1000)
     # the last query kept nothing: it cannot vouch for the rows below its (infinite) threshold -> flag 4
