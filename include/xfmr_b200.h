@@ -379,22 +379,25 @@ int xr_score_filter(const void* q, int64_t u, const void* catalog, int64_t n, in
                     float* ovf_scores, int32_t* ovf_rows, int32_t* ovf_count, int64_t ovf_cap,
                     void* stream);
 /* Survivors -> the exact top-k (block per query): the k_sel best survivors under
- * (score desc, row asc) are re-scored with the arithmetic of xr_logits_sampled, rows in query u's CSR
- * exclusion list (GLOBAL ids; nullable) are dropped (the prefilter of index.py:239-247), the rest is
- * ranked by (score desc, global id asc).  out_scores (U, k) fp32 / out_idx (U, k) int64 = local row +
- * row_offset (-inf / -1 where fewer than k remain).  thresh = the thresholds the survivors were filtered
- * with.  flags[0] |= 1 if survivors were lost (ovf_count > ovf_cap), |= 2 if a query has more than
- * max_excl excluded ids, |= 4 if fewer than k_sel - max_excl non-excluded rows survived a finite
- * threshold: the result is then not guaranteed exact and the caller must take another path.
- * k + max_excl <= k_sel <= 1024.                                                                    */
-int xr_filter_finalize(const void* q, int64_t u, const void* catalog, int64_t n, int64_t dim,
-                       const float* bucket_scores, const int32_t* bucket_rows,
+ * (score desc, row asc) are kept (one radix select in shared memory), rows in query u's CSR exclusion
+ * list (GLOBAL ids; nullable) are dropped (the prefilter of index.py:239-247), the rest is ranked by
+ * (score desc, global id asc).  The scores reported are the tensor-core scores the filter stored: the
+ * threshold, the selection and the ranking share one arithmetic.  out_scores (U, k) fp32 / out_idx (U, k)
+ * int64 = local row + row_offset (-inf / -1 where fewer than k remain).  thresh = the thresholds the
+ * survivors were filtered with.  flags[0] |= 1 if survivors were lost (ovf_count > ovf_cap), |= 2 if a
+ * query has more than max_excl excluded ids, |= 4 if fewer than k non-excluded rows survived a finite
+ * threshold that kept at most k_sel rows: the result is then not guaranteed exact and the caller must
+ * take another path.  k + max_excl <= k_sel <= 1024; n = catalog rows (global ids must be < 2^32).      */
+int xr_filter_finalize(int64_t u, int64_t n, const float* bucket_scores, const int32_t* bucket_rows,
                        const int32_t* bucket_count, int64_t n_sub, int64_t cap_b,
                        const float* ovf_scores, const int32_t* ovf_rows, const int32_t* ovf_count,
                        int64_t ovf_cap, const float* thresh, int64_t thresh_stride, int64_t k_sel,
                        int64_t k, int64_t row_offset, const int64_t* excl_offsets,
                        const int64_t* excl_ids, int64_t max_excl, float* out_scores, int64_t* out_idx,
                        int32_t* flags, void* stream);
+/* out[r] = the kth largest of x[r, 0..n) (fp32, NaN ranks first), -inf when n < kth: the thresholds of the
+ * filter from the sample's group maxima, one block per row.                                            */
+int xr_kth_largest(const float* x, int64_t u, int64_t n, int64_t ld, int64_t kth, float* out, void* stream);
 /* scores[u, j] = -inf where ids[u, j] lies outside [id_lo, id_hi) or in row u's CSR exclusion
  * list (nullable) — the prefilter of index.py:239-247 applied to re-scored candidate lists.     */
 int xr_mask_excluded_ids(float* scores, const int64_t* ids, int64_t u, int64_t c, int64_t ld,
@@ -409,8 +412,8 @@ int xr_groups_to_rows(const int64_t* group_ids, int64_t u, int64_t kg, int64_t n
 /* The whole local search of one catalog shard as ONE call (bf16, dim 384) — LanceIndex.search /
  * FaissIndex.search, index.py:214-255 / 439-474, exact and batched over U queries:
  *   sample group maxima (xr_score_groupmax, tile_stride s) -> the (k + 28)-th largest per query =
- *   threshold (xr_topk) -> xr_score_filter over the whole shard -> xr_filter_finalize with
- *   k_sel = k + max_excl + 28.
+ *   threshold (xr_kth_largest) -> xr_score_filter over the whole shard -> xr_filter_finalize with
+ *   k_sel = k + max_excl.
  * Same result as xr_scores + xr_mask_excluded + xr_topk unless flags[0] != 0 afterwards (see
  * xr_filter_finalize; flags is NOT cleared by the call, so one word can watch many searches).
  * q / catalog rows pre-normalised for the cosine metric.  excl_*: nullable CSR of GLOBAL ids, at most

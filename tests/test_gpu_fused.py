@@ -284,7 +284,7 @@ def test_score_filter_survivors(xr, u, n, cap_b):
     if cap_b is not None and n <= 16384:
         assert int(fs.o_count.max()) > 0                        # the keep-everything query spilled: overflow tier exercised
     k = 20
-    s, i, flags = ops.filter_finalize(q16, c16, fs, tht, 60, k, row_offset=1000)
+    s, i, flags = ops.filter_finalize(fs, n, tht, 60, k, row_offset=1000)
     # the last query kept nothing: it cannot vouch for the rows below its (infinite) threshold -> flag 4
     assert int(flags.item()) == 4
     want_s, want_i = orc.exact_search(qs[:-1], cat, k, None, metric="dot")

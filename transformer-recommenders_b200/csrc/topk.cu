@@ -12,13 +12,11 @@
 // threshold.  Chunks of a row are merged by the same kernel running over the partial keys.
 // Selection on a strict total order makes single-GPU, chunked and sharded results identical.
 #include "common.cuh"
-#include "rowdot.cuh"
 #include "filter.cuh"
 
 namespace xr {
 
 constexpr int TK_THREADS = 256;
-static_assert(TK_THREADS == ROW_THREADS, "the finalize kernel runs the gather-dot with the top-k block shape");
 constexpr int TK_CAP = 2048;        // candidate buffer (keys)
 constexpr int TK_PER_ITER = 1024;   // worst-case appends per iteration
 constexpr int TK_MAX_K = TK_CAP - TK_PER_ITER;
@@ -433,92 +431,166 @@ __global__ void groups_to_rows_kernel(const int64_t* __restrict__ gi, int64_t to
 }
 
 // ---- survivors of the scoring filter -> exact top-k (block per query) --------------------------------
-// 1. the k_sel best survivors under (tensor-core score desc, row asc) -- a total order, so the choice
-//    does not depend on the order the scoring CTAs appended them in; 2. their scores recomputed with the
-//    gather-dot arithmetic of xr_logits_sampled (the arithmetic every other search path reports);
-//    3. the query's exclusion list dropped (index.py:239-247); 4. ranked by (score desc, global id asc).
-// Exactness: the survivors are ALL rows scoring >= the query's threshold.  With k_sel = k + max_excl +
-// margin selected and at most max_excl of them excluded, k + margin non-excluded rows remain and every
-// row left out scores below all of them.  When fewer than k_sel rows survived (all were selected) the
-// same holds only if k + margin of them are not excluded -- or if the threshold was -inf (nothing was
-// filtered): otherwise flag 4 tells the caller to take another path.
+// The survivors are ALL rows whose tensor-core score is >= the query's threshold.  They are gathered
+// into shared memory as 64-bit keys (score desc, row asc: a total order, so the result does not depend on
+// which lane stored what where), ONE radix select keeps the k_sel = k + max_excl best, the query's
+// exclusion list is dropped (index.py:239-247) and the rest is sorted.  The reported scores are the
+// tensor-core scores themselves: threshold, selection and ranking use one arithmetic, so no margin between
+// two arithmetics is needed anywhere.
+// Exactness: with k_sel selected and at most max_excl of them excluded, k non-excluded rows remain and every
+// row left out ranks below all of them.  When fewer than k_sel rows survived (all were selected) the result
+// is exact if k of them are not excluded -- or if the threshold was -inf (nothing was filtered): otherwise
+// flag 4 tells the caller to take another path.
+constexpr int FF_CAP = 8192;   // keys held in shared memory at a time (64 KB)
+
+// MSB-first radix select (8-bit digits) of the `want`-th largest of keys[0, n) (unique keys, want <= n);
+// block-uniform call; s_hist[256], s_pick[2] are block scratch
+__device__ __forceinline__ uint64_t radix_select_smem(const uint64_t* keys, int n, unsigned want,
+                                                      unsigned* s_hist, unsigned* s_pick) {
+  uint64_t prefix = 0ull, mask = 0ull;
+  const int lane = threadIdx.x & 31;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    s_hist[threadIdx.x] = 0u;   // TK_THREADS == 256 bins
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += TK_THREADS) {
+      const uint64_t key = keys[i];
+      if ((key & mask) == prefix) atomicAdd(&s_hist[(unsigned)(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {   // warp 0 walks the 256 bins from the top
+      unsigned c[8], tot = 0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        c[b] = s_hist[255 - (lane * 8 + b)];
+        tot += c[b];
+      }
+      unsigned incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      unsigned acc = incl - tot;
+      if (acc < want && want <= incl) {
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          if (acc < want && want <= acc + c[b]) {
+            s_pick[0] = 255u - (unsigned)(lane * 8 + b);
+            s_pick[1] = want - acc;
+          }
+          acc += c[b];
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= (uint64_t)s_pick[0] << shift;
+    mask |= 0xFFull << shift;
+    want = s_pick[1];
+  }
+  return prefix;
+}
+
 __global__ void __launch_bounds__(TK_THREADS)
-filter_finalize_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ cat, int64_t n,
-                       const FilterOut fo, const float* __restrict__ thresh, int64_t thresh_stride, int k_sel,
+filter_finalize_kernel(const FilterOut fo, const float* __restrict__ thresh, int64_t thresh_stride, int k_sel,
                        int k, int64_t row_offset, const int64_t* __restrict__ offs,
                        const int64_t* __restrict__ excl, int64_t max_excl, float* __restrict__ out_scores,
                        int64_t* __restrict__ out_idx, int32_t* __restrict__ flags) {
-  __shared__ uint64_t s_keys[TK_CAP];
-  __shared__ int s_count;
-  __shared__ uint64_t s_tau;
-  __shared__ int64_t s_rows[TK_MAX_K];
-  __shared__ float s_sc[TK_MAX_K];
-  __shared__ int s_alive;
-  __shared__ int s_total;
-  TopkState st{s_keys, &s_count, &s_tau};
+  extern __shared__ uint64_t ff_keys[];          // [FF_CAP] gathered keys | [TK_MAX_K] selected keys
+  uint64_t* s_sel = ff_keys + FF_CAP;
+  __shared__ unsigned s_hist[256];
+  __shared__ unsigned s_pick[2];
+  __shared__ int s_scan[TK_THREADS / 32];
+  __shared__ int s_fill, s_cnt, s_alive, s_total;
   const int64_t u = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t ovf_raw = fo.o_count[u];
-  const int64_t n_ovf = ovf_raw < fo.ovf_cap ? ovf_raw : fo.ovf_cap;
+  const int n_ovf = (int)(ovf_raw < fo.ovf_cap ? ovf_raw : fo.ovf_cap);
   if (threadIdx.x == 0) {
-    s_count = 0;
-    s_tau = 0ull;
+    s_fill = 0;
     s_alive = 0;
     s_total = 0;
     int bad = ovf_raw > fo.ovf_cap ? 1 : 0;                            // survivors were dropped
-    if (offs && offs[u + 1] - offs[u] > max_excl) bad |= 2;            // thresholds assumed fewer exclusions
+    if (offs && offs[u + 1] - offs[u] > max_excl) bad |= 2;            // k_sel assumed fewer exclusions
     if (bad) atomicOr(flags, bad);
   }
   __syncthreads();
-  // survivors of the sub-buckets: every thread walks one sub-bucket at a time (the fill counts differ, so
-  // the loop runs to the longest one of the round; a round is 256 sub-buckets)
+
+  // keep the k_sel best of ff_keys[0, s_fill) at the front (block-uniform)
+  auto shrink = [&]() {
+    const int fill = s_fill;
+    if (fill <= k_sel) return;
+    const uint64_t kth = radix_select_smem(ff_keys, fill, (unsigned)k_sel, s_hist, s_pick);
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < fill; i += TK_THREADS) {
+      const uint64_t key = ff_keys[i];
+      if (key >= kth) s_sel[atomicAdd(&s_cnt, 1)] = key;               // exactly k_sel keys (they are unique)
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < k_sel; i += TK_THREADS) ff_keys[i] = s_sel[i];
+    if (threadIdx.x == 0) s_fill = k_sel;
+    __syncthreads();
+  };
+  // append `c` keys per thread (src(e) gives the e-th) behind the current fill: a block scan places them
+  auto append = [&](int c, auto src) {
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < TK_THREADS / 32; ++w) {
+      if (w < warp) before += s_scan[w];
+      total += s_scan[w];
+    }
+    if (s_fill + total > FF_CAP) shrink();                             // block-uniform: make room first
+    int at = s_fill + before + incl - c;
+    for (int e = 0; e < c; ++e) ff_keys[at + e] = src(e);
+    __syncthreads();
+    if (threadIdx.x == 0) s_fill += total;
+    __syncthreads();
+  };
+
+  // sub-buckets, `per` of them per round so that a round never exceeds the free room after a shrink
+  int per = (FF_CAP - TK_MAX_K) / fo.cap_b;
+  if (per > TK_THREADS) per = TK_THREADS;
+  if (per < 1) per = 1;
   int my_total = 0;
-  for (int base = 0; base < fo.n_sub; base += TK_THREADS) {
+  const int cap_eff = fo.cap_b < FF_CAP - TK_MAX_K ? fo.cap_b : FF_CAP - TK_MAX_K;
+  for (int base = 0; base < fo.n_sub; base += per) {
     const int sb = base + threadIdx.x;
     int c = 0;
     const float* bs = nullptr;
     const int32_t* br = nullptr;
-    if (sb < fo.n_sub) {
+    if (threadIdx.x < per && sb < fo.n_sub) {
       c = __ldcg(fo.b_count + u * fo.n_sub + sb);
       my_total += c;
-      if (c > fo.cap_b) c = fo.cap_b;                                  // the excess is in the overflow list
+      if (c > cap_eff) c = cap_eff;                                    // beyond cap_b: in the overflow list
       bs = fo.b_scores + (u * fo.n_sub + sb) * fo.cap_b;
       br = fo.b_rows + (u * fo.n_sub + sb) * fo.cap_b;
     }
-    for (int e = 0; __syncthreads_or(e < c); ++e) {
-      if (*st.count > TK_CAP - TK_THREADS) compact_select(st, k_sel);
-      const uint64_t tau = *st.tau;
-      const bool in = e < c;
-      const uint64_t key = in ? make_key(__ldcg(bs + e), (uint32_t)__ldcg(br + e)) : 0ull;
-      offer(st, in && key > tau, key);
-    }
+    append(c, [&](int e) { return make_key(__ldcg(bs + e), (uint32_t)__ldcg(br + e)); });
   }
-  __syncthreads();
-  {  // the overflow list
+  {  // the overflow list, FF_CAP - TK_MAX_K entries at a time
     const float* cs = fo.o_scores + u * fo.ovf_cap;
     const int32_t* cr = fo.o_rows + u * fo.ovf_cap;
-    const int64_t iters = (n_ovf + TK_PER_ITER - 1) / TK_PER_ITER;
-    for (int64_t it = 0; it < iters; ++it) {
-      if (*st.count > TK_CAP - TK_PER_ITER) compact_select(st, k_sel);
-      const uint64_t tau = *st.tau;
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int64_t e = it * TK_PER_ITER + r * TK_THREADS + threadIdx.x;
-        const bool in = e < n_ovf;
-        const uint64_t key = in ? make_key(__ldcg(cs + e), (uint32_t)__ldcg(cr + e)) : 0ull;
-        offer(st, in && key > tau, key);
-      }
-      __syncthreads();
+    constexpr int CH = (FF_CAP - TK_MAX_K) / TK_THREADS;               // entries per thread per round
+    for (int base = 0; base < n_ovf; base += CH * TK_THREADS) {
+      const int lo = base + threadIdx.x * CH;
+      int c = n_ovf - lo;
+      c = c < 0 ? 0 : (c > CH ? CH : c);
+      append(c, [&](int e) { return make_key(__ldcg(cs + lo + e), (uint32_t)__ldcg(cr + lo + e)); });
     }
   }
   my_total = __reduce_add_sync(0xffffffffu, my_total);
-  if ((threadIdx.x & 31) == 0 && my_total) atomicAdd(&s_total, my_total);
-  compact_select(st, k_sel);
-  compact(st, k_sel);   // s_keys[0, c) in descending key order
-  const int c = s_count < k_sel ? s_count : k_sel;
-  for (int i = threadIdx.x; i < c; i += TK_THREADS) s_rows[i] = (int64_t)(0xFFFFFFFFu - (uint32_t)s_keys[i]);
-  __syncthreads();
-  sampled_logits384_row<__nv_bfloat16>(q + u * FD, cat, s_rows, n, c, 1.f, nullptr, s_sc);
-  __syncthreads();
+  if (lane == 0 && my_total) atomicAdd(&s_total, my_total);
+  shrink();
+  const int c = s_fill;                                                // min(k_sel, survivors stored)
+  // exclusion list, then the final order
   const int64_t x0 = offs ? offs[u] : 0, x1 = offs ? offs[u + 1] : 0;
   int n2 = 2;
   while (n2 < c) n2 <<= 1;
@@ -526,25 +598,24 @@ filter_finalize_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16*
   for (int i = threadIdx.x; i < n2; i += TK_THREADS) {
     uint64_t key = 0ull;
     if (i < c) {
-      const int64_t id = s_rows[i] + row_offset;
+      key = ff_keys[i];
+      const int64_t id = (int64_t)(0xFFFFFFFFu - (uint32_t)key) + row_offset;
       bool dead = false;
       for (int64_t x = x0; x < x1; ++x) dead |= (excl[x] == id);
-      if (!dead) {
-        key = make_key(s_sc[i], (uint32_t)id);
-        ++alive;
-      }
+      // the low word of the final key is the GLOBAL id: shards then merge under one total order
+      key = dead ? 0ull : ((key & 0xFFFFFFFF00000000ull) | (uint64_t)(0xFFFFFFFFu - (uint32_t)id));
+      alive += dead ? 0 : 1;
     }
-    s_keys[i] = key;
+    s_sel[i] = key;
   }
   alive = __reduce_add_sync(0xffffffffu, alive);
-  if ((threadIdx.x & 31) == 0 && alive) atomicAdd(&s_alive, alive);
+  if (lane == 0 && alive) atomicAdd(&s_alive, alive);
   __syncthreads();
-  if (threadIdx.x == 0 && s_total <= k_sel && s_alive < k_sel - (int)max_excl &&
-      thresh[u * thresh_stride] > -CUDART_INF_F)
+  if (threadIdx.x == 0 && s_total <= k_sel && s_alive < k && thresh[u * thresh_stride] > -CUDART_INF_F)
     atomicOr(flags, 4);   // too few non-excluded survivors to vouch for the rows below the threshold
-  bitonic_desc(s_keys, n2);
+  bitonic_desc(s_sel, n2);
   for (int i = threadIdx.x; i < k; i += TK_THREADS) {
-    const uint64_t key = i < n2 ? s_keys[i] : 0ull;
+    const uint64_t key = i < n2 ? s_sel[i] : 0ull;
     if (key == 0ull) {
       out_scores[u * k + i] = -CUDART_INF_F;
       out_idx[u * k + i] = -1;
@@ -553,6 +624,61 @@ filter_finalize_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16*
       out_idx[u * k + i] = (int64_t)(0xFFFFFFFFu - (uint32_t)key);
     }
   }
+}
+
+// ---- k-th largest of every row (the thresholds of the scoring filter): block per row, 4-pass radix
+//      select on the order-preserving 32-bit keys; the row (tens of KB) is re-read from L2 per pass ------
+__global__ void __launch_bounds__(TK_THREADS)
+kth_largest_kernel(const float* __restrict__ x, int64_t n, int64_t ld, int kth, float* __restrict__ out) {
+  __shared__ unsigned s_hist[256];
+  __shared__ unsigned s_pick[2];
+  const float* row = x + (int64_t)blockIdx.x * ld;
+  const int lane = threadIdx.x & 31;
+  if (kth > n) {   // fewer values than the rank asked for: nothing bounds the k-th score from below
+    if (threadIdx.x == 0) out[blockIdx.x] = -CUDART_INF_F;
+    return;
+  }
+  uint32_t prefix = 0u, mask = 0u;
+  unsigned want = (unsigned)kth;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    s_hist[threadIdx.x] = 0u;
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < n; i += TK_THREADS) {
+      const uint32_t key = float_key(__ldg(row + i));
+      if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      unsigned c[8], tot = 0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        c[b] = s_hist[255 - (lane * 8 + b)];
+        tot += c[b];
+      }
+      unsigned incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      unsigned acc = incl - tot;
+      if (acc < want && want <= incl) {
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          if (acc < want && want <= acc + c[b]) {
+            s_pick[0] = 255u - (unsigned)(lane * 8 + b);
+            s_pick[1] = want - acc;
+          }
+          acc += c[b];
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= s_pick[0] << shift;
+    mask |= 0xFFu << shift;
+    want = s_pick[1];
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = key_float(prefix);
 }
 
 // ---- retrieval metrics: metrics.py:62-79, one thread per user ---------------------------------
@@ -790,18 +916,16 @@ extern "C" int xr_groups_to_rows(const int64_t* group_ids, int64_t u, int64_t kg
   return XR_OK;
 }
 
-extern "C" int xr_filter_finalize(const void* q, int64_t u, const void* catalog, int64_t n, int64_t dim,
-                                  const float* bucket_scores, const int32_t* bucket_rows,
+extern "C" int xr_filter_finalize(int64_t u, int64_t n, const float* bucket_scores, const int32_t* bucket_rows,
                                   const int32_t* bucket_count, int64_t n_sub, int64_t cap_b,
                                   const float* ovf_scores, const int32_t* ovf_rows, const int32_t* ovf_count,
                                   int64_t ovf_cap, const float* thresh, int64_t thresh_stride, int64_t k_sel,
                                   int64_t k, int64_t row_offset, const int64_t* excl_offsets,
                                   const int64_t* excl_ids, int64_t max_excl, float* out_scores,
                                   int64_t* out_idx, int32_t* flags, void* stream) {
-  XR_CHECK_ARG(q && catalog && bucket_scores && bucket_rows && bucket_count && ovf_scores && ovf_rows &&
-                   ovf_count && thresh && out_scores && out_idx && flags,
+  XR_CHECK_ARG(bucket_scores && bucket_rows && bucket_count && ovf_scores && ovf_rows && ovf_count && thresh &&
+                   out_scores && out_idx && flags,
                "xr_filter_finalize: null pointer");
-  XR_CHECK_ARG(dim == FD, "xr_filter_finalize: this build is specialised for dim = %d", FD);
   XR_CHECK_ARG(u >= 0 && n > 0 && n_sub >= 1 && cap_b >= 1 && ovf_cap >= 1 && k >= 1 && k_sel >= k &&
                    k_sel <= TK_MAX_K,
                "xr_filter_finalize: needs 1 <= k <= k_sel <= %d", TK_MAX_K);
@@ -813,10 +937,25 @@ extern "C" int xr_filter_finalize(const void* q, int64_t u, const void* catalog,
                      const_cast<int32_t*>(bucket_count), const_cast<float*>(ovf_scores),
                      const_cast<int32_t*>(ovf_rows), const_cast<int32_t*>(ovf_count), (int)n_sub, (int)cap_b,
                      (int)ovf_cap};
-  filter_finalize_kernel<<<(unsigned)u, TK_THREADS, 0, as_stream(stream)>>>(
-      (const __nv_bfloat16*)q, (const __nv_bfloat16*)catalog, n, fo, thresh, thresh_stride, (int)k_sel, (int)k,
-      row_offset, excl_offsets, excl_ids, max_excl, out_scores, out_idx, flags);
+  constexpr int kSmem = (FF_CAP + TK_MAX_K) * 8;
+  static bool configured = false;
+  if (!configured) {
+    XR_CUDA(cudaFuncSetAttribute(filter_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    configured = true;
+  }
+  filter_finalize_kernel<<<(unsigned)u, TK_THREADS, kSmem, as_stream(stream)>>>(
+      fo, thresh, thresh_stride, (int)k_sel, (int)k, row_offset, excl_offsets, excl_ids, max_excl, out_scores,
+      out_idx, flags);
   XR_LAUNCH_CHECK("filter_finalize");
+  return XR_OK;
+}
+
+extern "C" int xr_kth_largest(const float* x, int64_t u, int64_t n, int64_t ld, int64_t kth, float* out,
+                              void* stream) {
+  XR_CHECK_ARG(x && out && u >= 0 && n >= 0 && ld >= n && kth >= 1, "xr_kth_largest: bad arguments");
+  if (u == 0) return XR_OK;
+  kth_largest_kernel<<<(unsigned)u, TK_THREADS, 0, as_stream(stream)>>>(x, n, ld, (int)kth, out);
+  XR_LAUNCH_CHECK("kth_largest");
   return XR_OK;
 }
 
@@ -827,15 +966,16 @@ constexpr int64_t kFilterTarget = 4096;   // survivors per query the sample stri
 constexpr int kFilterMargin = 28;         // rank positions of slack between the two score arithmetics
 struct ScoreTopkPlan {
   int64_t kk, k_sel, stride, ld_s, n_sub, cap_b;
-  size_t off_gmax, off_tkws, off_vals, off_idx, off_bs, off_br, off_bc, off_os, off_or, off_oc, bytes, tkws_bytes;
+  size_t off_gmax, off_thr, off_bs, off_br, off_bc, off_os, off_or, off_oc, bytes;
 };
 static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 static ScoreTopkPlan plan_score_topk(int64_t u, int64_t n, int64_t k, int64_t max_excl) {
   ScoreTopkPlan pl{};
-  // threshold = the (k + margin)-th largest group maximum of the sample, whatever the exclusion lists:
-  // ~ (k + margin) * stride rows survive, of which at most max_excl are excluded afterwards
+  // threshold = the (k + slack)-th largest group maximum of the sample, whatever the exclusion lists:
+  // ~ (k + slack) * stride rows survive, of which at most max_excl are excluded afterwards (the slack only
+  // keeps a query with a few excluded top rows off the slow path)
   pl.kk = k + kFilterMargin;
-  pl.k_sel = k + max_excl + kFilterMargin;
+  pl.k_sel = k + max_excl;
   // sample stride (in tiles of the scoring kernel): ~kk * stride survivors per query, and the sample keeps
   // at least 4 kk groups so that its kk-th maximum exists
   int64_t s = kFilterTarget / pl.kk;
@@ -844,16 +984,13 @@ static ScoreTopkPlan plan_score_topk(int64_t u, int64_t n, int64_t k, int64_t ma
   while (s > 1 && groups / s < 4 * pl.kk) --s;
   if (s < 1) s = 1;
   pl.stride = s;
-  pl.ld_s = (xr_score_groupmax_ld(u, n, s) + 3) / 4 * 4;   // 16-byte aligned rows: the streaming top-k path
+  pl.ld_s = (xr_score_groupmax_ld(u, n, s) + 1) / 2 * 2;
   // tiny catalogs: the threshold may be -inf (fewer sample groups than kk) and EVERY row survives
   const int64_t expect = groups < 4 * pl.kk * s ? n : pl.kk * s;
   xr_score_filter_layout(u, n, expect, &pl.n_sub, &pl.cap_b);
   size_t o = 0;
   pl.off_gmax = o; o += al256((size_t)u * pl.ld_s * 4);
-  pl.tkws_bytes = xr_topk_workspace_bytes(u, pl.ld_s, pl.kk);
-  pl.off_tkws = o; o += al256(pl.tkws_bytes);
-  pl.off_vals = o; o += al256((size_t)u * pl.kk * 4);
-  pl.off_idx = o;  o += al256((size_t)u * pl.kk * 8);
+  pl.off_thr = o;  o += al256((size_t)u * 4);
   pl.off_bs = o;   o += al256((size_t)u * pl.n_sub * pl.cap_b * 4);
   pl.off_br = o;   o += al256((size_t)u * pl.n_sub * pl.cap_b * 4);
   pl.off_bc = o;   o += al256((size_t)u * pl.n_sub * 4);
@@ -863,14 +1000,10 @@ static ScoreTopkPlan plan_score_topk(int64_t u, int64_t n, int64_t k, int64_t ma
   pl.bytes = o;
   return pl;
 }
-__global__ void fill_neg_inf_kernel(float* __restrict__ p, int64_t total) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
-    p[i] = -CUDART_INF_F;
-}
 }  // namespace xr
 
 extern "C" size_t xr_score_topk_workspace_bytes(int64_t u, int64_t n, int64_t k, int64_t max_excl) {
-  if (u <= 0 || n <= 0 || k < 1 || max_excl < 0 || k + max_excl + kFilterMargin > TK_MAX_K) return 256;
+  if (u <= 0 || n <= 0 || k < 1 || max_excl < 0 || k + max_excl > TK_MAX_K) return 256;
   return plan_score_topk(u, n, k, max_excl).bytes;
 }
 
@@ -880,15 +1013,13 @@ extern "C" int xr_score_topk(const void* q, int64_t u, const void* catalog, int6
                              void* workspace, size_t workspace_bytes, void* stream) {
   XR_CHECK_ARG(q && catalog && out_scores && out_idx && flags && workspace, "xr_score_topk: null pointer");
   XR_CHECK_ARG(u > 0 && u <= 65535 && n > 0 && k >= 1 && max_excl >= 0, "xr_score_topk: bad sizes (u <= 65535 per call)");
-  XR_CHECK_ARG(k + max_excl + kFilterMargin <= TK_MAX_K, "xr_score_topk: k + max_excl must be <= %d",
-               TK_MAX_K - kFilterMargin);
+  XR_CHECK_ARG(k + max_excl <= TK_MAX_K, "xr_score_topk: k + max_excl must be <= %d", TK_MAX_K);
   XR_CHECK_ARG((uintptr_t)workspace % 256 == 0, "xr_score_topk: workspace must be 256-byte aligned");
   const ScoreTopkPlan pl = plan_score_topk(u, n, k, max_excl);
   XR_CHECK_ARG(workspace_bytes >= pl.bytes, "xr_score_topk: workspace too small");
   uint8_t* w = (uint8_t*)workspace;
   float* gmax = (float*)(w + pl.off_gmax);
-  float* vals = (float*)(w + pl.off_vals);
-  int64_t* idx = (int64_t*)(w + pl.off_idx);
+  float* thr = (float*)(w + pl.off_thr);
   float* bs = (float*)(w + pl.off_bs);
   int32_t* br = (int32_t*)(w + pl.off_br);
   int32_t* bc = (int32_t*)(w + pl.off_bc);
@@ -900,23 +1031,16 @@ extern "C" int xr_score_topk(const void* q, int64_t u, const void* catalog, int6
   // 1. thresholds: the kk-th largest group maximum of a strided sample of the shard (-inf when the sample
   //    has fewer groups: every row then survives; the sub-buckets are sized for that regime)
   const int64_t ld_used = xr_score_groupmax_ld(u, n, pl.stride);
-  if (ld_used < pl.ld_s) {   // padding columns of the aligned row stride
-    fill_neg_inf_kernel<<<(unsigned)((u * pl.ld_s + 255) / 256 < 1184 ? (u * pl.ld_s + 255) / 256 : 1184), 256, 0, s>>>(
-        gmax, u * pl.ld_s);
-    XR_LAUNCH_CHECK("fill_neg_inf");
-  }
   if ((rc = xr_score_groupmax(q, u, catalog, n, dim, pl.stride, gmax, pl.ld_s, stream))) return rc;
-  if ((rc = xr_topk(gmax, u, pl.ld_s, pl.ld_s, pl.kk, 0, vals, idx, w + pl.off_tkws, pl.tkws_bytes, stream)))
-    return rc;
+  if ((rc = xr_kth_largest(gmax, u, ld_used, pl.ld_s, pl.kk, thr, stream))) return rc;
   // 2. one pass over the shard: survivors of the filter
   XR_CUDA(cudaMemsetAsync(oc, 0, (size_t)u * 4, s));
-  if ((rc = xr_score_filter(q, u, catalog, n, dim, vals + (pl.kk - 1), pl.kk, bs, br, bc, pl.n_sub, pl.cap_b, os,
-                            orows, oc, kFilterOvfCap, stream)))
+  if ((rc = xr_score_filter(q, u, catalog, n, dim, thr, 1, bs, br, bc, pl.n_sub, pl.cap_b, os, orows, oc,
+                            kFilterOvfCap, stream)))
     return rc;
   // 3. survivors -> exact top-k
-  return xr_filter_finalize(q, u, catalog, n, dim, bs, br, bc, pl.n_sub, pl.cap_b, os, orows, oc, kFilterOvfCap,
-                            vals + (pl.kk - 1), pl.kk, pl.k_sel, k, row_offset, excl_offsets, excl_ids, max_excl,
-                            out_scores, out_idx, flags, stream);
+  return xr_filter_finalize(u, n, bs, br, bc, pl.n_sub, pl.cap_b, os, orows, oc, kFilterOvfCap, thr, 1, pl.k_sel, k,
+                            row_offset, excl_offsets, excl_ids, max_excl, out_scores, out_idx, flags, stream);
 }
 
 extern "C" int xr_retrieval_metrics(const int64_t* rec, int64_t u, int64_t k,

@@ -94,8 +94,9 @@ PROTOTYPES = {
     "xr_score_groupmax": (_int, [_p, _i64, _p, _i64, _i64, _i64, _p, _i64, _p]),
     "xr_score_filter_layout": (_int, [_i64, _i64, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
     "xr_score_filter": (_int, [_p, _i64, _p, _i64, _i64, _p, _i64, _p, _p, _p, _i64, _i64, _p, _p, _p, _i64, _p]),
-    "xr_filter_finalize": (_int, [_p, _i64, _p, _i64, _i64, _p, _p, _p, _i64, _i64, _p, _p, _p, _i64, _p, _i64, _i64,
-                                  _i64, _i64, _p, _p, _i64, _p, _p, _p, _p]),
+    "xr_filter_finalize": (_int, [_i64, _i64, _p, _p, _p, _i64, _i64, _p, _p, _p, _i64, _p, _i64, _i64, _i64, _i64,
+                                  _p, _p, _i64, _p, _p, _p, _p]),
+    "xr_kth_largest": (_int, [_p, _i64, _i64, _i64, _i64, _p, _p]),
     "xr_mask_excluded_ids": (_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p]),
     "xr_groups_to_rows": (_int, [_p, _i64, _i64, _i64, _i64, _p, _p, _p]),
     "xr_score_groupmax_ld": (_i64, [_i64, _i64, _i64]),

@@ -152,10 +152,11 @@ class ExactIndex:
         s = parts[0][0] if len(parts) == 1 else torch.cat([p[0] for p in parts])
         i = parts[0][1] if len(parts) == 1 else torch.cat([p[1] for p in parts])
         if int(flags.item()):
-            # a survivor list overflowed (more than 32,768 rows tie with or beat the sample's threshold:
-            # massively duplicated rows): the materialised scan is exact for any input
-            s, i = self._search_materialised(q, cat, csr, top_k)
-        return self._finish(s, i)
+            # the filter could not vouch for the result (survivors lost: more rows tie with or beat the
+            # sample's threshold than the sub-buckets and the overflow list hold -- massively duplicated
+            # rows; or the exclusions ate the survivors): the materialised scan is exact for any input
+            return self._finish(*self._search_materialised(q, cat, csr, top_k))
+        return s, i          # xr_filter_finalize already reports -inf / -1 where fewer than k rows remain
 
     @staticmethod
     def _finish(s, i):
@@ -350,7 +351,7 @@ class SearchPlan:
         csr = (self.offs, self.rows) if self.max_excl > 0 else None
         s, i, _ = ops.score_topk(q, cat, self.k, idx.row_offset, csr, self.max_excl, self.flags,
                                  out=self.out, ws=self.ws)
-        return ExactIndex._finish(s, i)
+        return s, i
 
     def overflowed(self, *, clear: bool = True) -> bool:
         """True if any search since the last clear could not be served exactly by the filter path."""

@@ -508,24 +508,35 @@ def score_filter(q, catalog, thresh, expected_survivors=4096, cap_b=None, ovf_ca
     return fs
 
 
-def filter_finalize(q, catalog, fs, thresh, k_sel, k, row_offset=0, exclude=None, max_excl=0, flags=None):
-    dev = _require_cuda(q, catalog, thresh)
+def filter_finalize(fs, n, thresh, k_sel, k, row_offset=0, exclude=None, max_excl=0, flags=None):
+    dev = _require_cuda(fs.b_scores, thresh)
     thresh = thresh.contiguous().float()
     offs, ex = (None, None) if exclude is None else exclude
-    u = q.size(0)
+    u = fs.u
     out_s = torch.empty((u, k), dtype=torch.float32, device=dev)
     out_i = torch.empty((u, k), dtype=torch.int64, device=dev)
     if flags is None:
         flags = torch.zeros(1, dtype=torch.int32, device=dev)
     with _on(dev):
-        N.call("xr_filter_finalize", _p(q), u, _p(catalog), catalog.size(0), q.size(1), _p(fs.b_scores),
-               _p(fs.b_rows), _p(fs.b_count), fs.n_sub, fs.cap_b, _p(fs.o_scores), _p(fs.o_rows),
-               _p(fs.o_count), fs.ovf_cap, _p(thresh), 1, k_sel, k, row_offset, _p(offs), _p(ex), max_excl,
-               _p(out_s), _p(out_i), _p(flags), _stream())
+        N.call("xr_filter_finalize", u, n, _p(fs.b_scores), _p(fs.b_rows), _p(fs.b_count), fs.n_sub, fs.cap_b,
+               _p(fs.o_scores), _p(fs.o_rows), _p(fs.o_count), fs.ovf_cap, _p(thresh), 1, k_sel, k, row_offset,
+               _p(offs), _p(ex), max_excl, _p(out_s), _p(out_i), _p(flags), _stream())
     return out_s, out_i, flags
 
 
-SCORE_TOPK_MAX_K = 1024 - 28   # k + max_excl the one-call search serves (xr_score_topk)
+def kth_largest(x, kth, n=None):
+    """kth largest of every row of a (U, ld) fp32 matrix (first n columns): xr_kth_largest."""
+    dev = _require_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    u = x.size(0)
+    n = x.size(1) if n is None else n
+    out = torch.empty(u, dtype=torch.float32, device=dev)
+    with _on(dev):
+        N.call("xr_kth_largest", _p(x), u, n, x.stride(0) if u > 1 else x.size(1), kth, _p(out), _stream())
+    return out
+
+
+SCORE_TOPK_MAX_K = 1024   # k + max_excl the one-call search serves (xr_score_topk)
 
 
 def score_topk_supported(q, catalog) -> bool:
