@@ -442,6 +442,7 @@ __global__ void groups_to_rows_kernel(const int64_t* __restrict__ gi, int64_t to
 // is exact if k of them are not excluded -- or if the threshold was -inf (nothing was filtered): otherwise
 // flag 4 tells the caller to take another path.
 constexpr int FF_CAP = 8192;   // keys held in shared memory at a time (64 KB)
+constexpr int FF_PCH = 4096;   // sub-buckets whose fill-count prefix sums are held at a time
 
 // MSB-first radix select (8-bit digits) of the `want`-th largest of keys[0, n) (unique keys, want <= n);
 // block-uniform call; s_hist[256], s_pick[2] are block scratch
@@ -500,6 +501,7 @@ filter_finalize_kernel(const FilterOut fo, const float* __restrict__ thresh, int
   __shared__ unsigned s_hist[256];
   __shared__ unsigned s_pick[2];
   __shared__ int s_scan[TK_THREADS / 32];
+  __shared__ int s_pref[FF_PCH + 1];
   __shared__ int s_fill, s_cnt, s_alive, s_total;
   const int64_t u = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -531,9 +533,44 @@ filter_finalize_kernel(const FilterOut fo, const float* __restrict__ thresh, int
     if (threadIdx.x == 0) s_fill = k_sel;
     __syncthreads();
   };
-  // append `c` keys per thread (src(e) gives the e-th) behind the current fill: a block scan places them
-  auto append = [&](int c, auto src) {
-    int incl = c;
+  // copy `total` keys, key j = src(j), behind the current fill; shrinks whenever the buffer runs full
+  // (block-uniform; every thread takes every 256th key: independent loads, full memory parallelism)
+  auto append = [&](int total, auto src) {
+    int pos = 0;
+    while (pos < total) {
+      if (s_fill + (total - pos) > FF_CAP && s_fill > k_sel) shrink();
+      const int fill = s_fill;
+      int take = total - pos;
+      if (take > FF_CAP - fill) take = FF_CAP - fill;
+      for (int j = threadIdx.x; j < take; j += TK_THREADS) ff_keys[fill + j] = src(pos + j);
+      __syncthreads();
+      if (threadIdx.x == 0) s_fill = fill + take;
+      __syncthreads();
+      pos += take;
+    }
+  };
+
+  // sub-buckets, FF_PCH at a time: exclusive prefix of their (clamped) fill counts in shared memory, then
+  // the flattened (sub-bucket, entry) range is copied with a binary search per key
+  int my_total = 0;
+  for (int c0 = 0; c0 < fo.n_sub; c0 += FF_PCH) {
+    const int nch = fo.n_sub - c0 < FF_PCH ? fo.n_sub - c0 : FF_PCH;
+    const int it = (nch + TK_THREADS - 1) / TK_THREADS;                // consecutive sub-buckets per thread
+    int cnt[FF_PCH / TK_THREADS];
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < FF_PCH / TK_THREADS; ++j) {
+      const int sb = threadIdx.x * it + j;
+      int c = 0;
+      if (j < it && sb < nch) {
+        c = __ldcg(fo.b_count + u * fo.n_sub + c0 + sb);
+        my_total += c;
+        if (c > fo.cap_b) c = fo.cap_b;                                // beyond cap_b: in the overflow list
+      }
+      cnt[j] = c;
+      mine += c;
+    }
+    int incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -547,44 +584,32 @@ filter_finalize_kernel(const FilterOut fo, const float* __restrict__ thresh, int
       if (w < warp) before += s_scan[w];
       total += s_scan[w];
     }
-    if (s_fill + total > FF_CAP) shrink();                             // block-uniform: make room first
-    int at = s_fill + before + incl - c;
-    for (int e = 0; e < c; ++e) ff_keys[at + e] = src(e);
-    __syncthreads();
-    if (threadIdx.x == 0) s_fill += total;
-    __syncthreads();
-  };
-
-  // sub-buckets, `per` of them per round so that a round never exceeds the free room after a shrink
-  int per = (FF_CAP - TK_MAX_K) / fo.cap_b;
-  if (per > TK_THREADS) per = TK_THREADS;
-  if (per < 1) per = 1;
-  int my_total = 0;
-  const int cap_eff = fo.cap_b < FF_CAP - TK_MAX_K ? fo.cap_b : FF_CAP - TK_MAX_K;
-  for (int base = 0; base < fo.n_sub; base += per) {
-    const int sb = base + threadIdx.x;
-    int c = 0;
-    const float* bs = nullptr;
-    const int32_t* br = nullptr;
-    if (threadIdx.x < per && sb < fo.n_sub) {
-      c = __ldcg(fo.b_count + u * fo.n_sub + sb);
-      my_total += c;
-      if (c > cap_eff) c = cap_eff;                                    // beyond cap_b: in the overflow list
-      bs = fo.b_scores + (u * fo.n_sub + sb) * fo.cap_b;
-      br = fo.b_rows + (u * fo.n_sub + sb) * fo.cap_b;
+    int run = before + incl - mine;
+#pragma unroll
+    for (int j = 0; j < FF_PCH / TK_THREADS; ++j) {
+      const int sb = threadIdx.x * it + j;
+      if (j < it && sb < nch) s_pref[sb] = run;
+      run += cnt[j];
     }
-    append(c, [&](int e) { return make_key(__ldcg(bs + e), (uint32_t)__ldcg(br + e)); });
+    if (threadIdx.x == 0) s_pref[nch] = total;
+    __syncthreads();
+    const float* bs = fo.b_scores + (u * fo.n_sub + c0) * fo.cap_b;
+    const int32_t* br = fo.b_rows + (u * fo.n_sub + c0) * fo.cap_b;
+    append(total, [&](int j) {
+      int lo = 0, hi = nch;                                            // last sub-bucket with s_pref[sb] <= j
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_pref[mid] <= j) lo = mid;
+        else hi = mid;
+      }
+      const long long at = (long long)lo * fo.cap_b + (j - s_pref[lo]);
+      return make_key(__ldcg(bs + at), (uint32_t)__ldcg(br + at));
+    });
   }
-  {  // the overflow list, FF_CAP - TK_MAX_K entries at a time
+  {  // the overflow list
     const float* cs = fo.o_scores + u * fo.ovf_cap;
     const int32_t* cr = fo.o_rows + u * fo.ovf_cap;
-    constexpr int CH = (FF_CAP - TK_MAX_K) / TK_THREADS;               // entries per thread per round
-    for (int base = 0; base < n_ovf; base += CH * TK_THREADS) {
-      const int lo = base + threadIdx.x * CH;
-      int c = n_ovf - lo;
-      c = c < 0 ? 0 : (c > CH ? CH : c);
-      append(c, [&](int e) { return make_key(__ldcg(cs + lo + e), (uint32_t)__ldcg(cr + lo + e)); });
-    }
+    append(n_ovf, [&](int j) { return make_key(__ldcg(cs + j), (uint32_t)__ldcg(cr + j)); });
   }
   my_total = __reduce_add_sync(0xffffffffu, my_total);
   if (lane == 0 && my_total) atomicAdd(&s_total, my_total);
