@@ -256,7 +256,13 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: ONE JSON line
+        # the per-step collectives run UNDER the next step's kernels: the persistent tensor-core kernel
+        # leaves `reserve` SMs free for NCCL's CTAs (dist.reserve_sms) and NCCL is told to use that many
+        reserve = int(os.environ.get("XR_BENCH_RESERVE_SMS", "8"))
+        if reserve > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(reserve))
         dist.init_process_group("nccl", device_id=dev)
+        xr.dist.reserve_sms(reserve)
     peaks = load_peaks()
     lib = xr._native.lib()
 
@@ -524,7 +530,9 @@ def main():
                                "reference's call sequence; one host sync for the row counts)"},
     }
     if world > 1:
+        xr.dist.reserve_sms(0)      # the retrieval leg has no collective running beside its kernels
         line["dp_collectives"] = {
+            "reserved_sms": reserve,
             "per_step": ["all_reduce(sum) loss scalar (dist.reduce_loss)", "all_reduce(sum) 16 MB fp32 (encoder-gradient sized)"],
             "ms_per_step_with": ms_per_step, "ms_per_step_without": no_coll_ms,
             "value_without": world * BATCH / (no_coll_ms / 1e3)}

@@ -72,6 +72,11 @@ const char* xr_last_error(void);
 int xr_abi_version(void);
 /* sm count, compute capability and whether the tcgen05 kernels can run on the current device */
 int xr_device_info(int* sm_count, int* cc_major, int* cc_minor, int* has_tcgen05);
+/* Leave `n_reserved` SMs free: the persistent kernels (one CTA per SM) size their grids with the physical
+ * SM count minus this, so that kernels of OTHER streams -- the NCCL all-reduce of the data-parallel
+ * trainer's encoder gradients -- find a place to run under them instead of behind them.  Returns the
+ * previous value; n_reserved < 0 only reads it.  Process-wide; set it before capturing CUDA graphs.      */
+int xr_reserve_sms(int n_reserved);
 
 /* ---- family 1: embedding row gathers ------------------------------------------------------
  * nn.Embedding.forward — models.py:336-338 (history), :400 (positives), :406 (negatives).

@@ -19,7 +19,9 @@ int cuda_fail(cudaError_t e, const char* what) {
   return XR_E_CUDA;
 }
 
-int sm_count() {
+static int g_reserved_sms = 0;   // SMs left free for concurrent kernels (xr_reserve_sms)
+
+int sm_count_max() {
   static thread_local int cached_dev = -1, cached = 148;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
@@ -32,10 +34,24 @@ int sm_count() {
   return cached;
 }
 
+// what the persistent kernels size their grids with: the physical SM count minus the reservation
+// (kept even: CTA pairs); workspaces are always sized with sm_count_max()
+int sm_count() {
+  int n = sm_count_max() - g_reserved_sms;
+  if (n < 2) n = 2;
+  return n & ~1;
+}
+
 }  // namespace xr
 
 extern "C" const char* xr_last_error(void) { return xr::g_err; }
 extern "C" int xr_abi_version(void) { return XR_ABI_VERSION; }
+
+extern "C" int xr_reserve_sms(int n_reserved) {
+  const int prev = xr::g_reserved_sms;
+  if (n_reserved >= 0) xr::g_reserved_sms = n_reserved;
+  return prev;
+}
 
 extern "C" int xr_device_info(int* sm_count, int* cc_major, int* cc_minor, int* has_tcgen05) {
   int dev = 0;

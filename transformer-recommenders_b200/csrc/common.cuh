@@ -38,7 +38,8 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
-int sm_count();
+int sm_count();       // SMs the persistent kernels may fill (physical count minus xr_reserve_sms)
+int sm_count_max();   // physical SM count: workspace sizing
 
 constexpr int kWarp = 32;
 

@@ -1218,7 +1218,7 @@ static FusedWs carve_fused_ws(void* workspace, long long m_max, long long max_it
 
 extern "C" size_t xr_fused_pool_workspace_bytes(int64_t m, int64_t cn, int64_t dim) {
   if (dim != fk::D || m <= 0 || cn <= 0) return 512;
-  const FusedPlan pl = make_plan(m, cn, sm_count());
+  const FusedPlan pl = make_plan(m, cn, sm_count_max());
   return carve_fused_ws(nullptr, m, pl.slots).bytes;
 }
 
@@ -1379,7 +1379,7 @@ static size_t fused_all_extra_bytes(long long m) { return align256((size_t)m * R
 
 extern "C" size_t xr_fused_pool_all_workspace_bytes(int64_t m, int64_t cn, int64_t dim) {
   if (dim != fk::D || m <= 0 || cn <= 0) return 512;
-  const FusedPlan pl = make_plan(m, cn, sm_count());
+  const FusedPlan pl = make_plan(m, cn, sm_count_max());
   return carve_fused_ws(nullptr, m, pl.slots).bytes + fused_all_extra_bytes(m);
 }
 
@@ -1449,8 +1449,7 @@ extern "C" int xr_fused_pool_all(const void* q, const void* pos, const void* neg
                "xr_fused_pool_all: workspace too small");
   int rc;
   if ((rc = check_fused_device("xr_fused_pool_all"))) return rc;
-  const FusedPlan pl = make_plan(m, cn, sm_count());
-  const FusedWs ws = carve_fused_ws(workspace, m, pl.slots);
+  const FusedWs ws = carve_fused_ws(workspace, m, make_plan(m, cn, sm_count_max()).slots);
   double* row_out = (double*)((uint8_t*)workspace + ws.bytes);
   return fused_all_launch(q, pos, neg, m, cn, cosine, cfg, ws, false, row_out, losses_out, stats_out,
                           as_stream(stream));
@@ -1537,7 +1536,7 @@ static StepWs carve_step_ws(void* workspace, long long n_pos) {
   w.neg = (__nv_bfloat16*)p;  p += align256(n * fk::D * 2);
   w.err = (int32_t*)p;        p += 256;
   const size_t off = (size_t)(p - (uint8_t*)workspace);
-  w.fused = carve_fused_ws(workspace ? p : nullptr, n_pos, max_plan_slots(n_pos, sm_count()));
+  w.fused = carve_fused_ws(workspace ? p : nullptr, n_pos, max_plan_slots(n_pos, sm_count_max()));
   w.bytes = off + w.fused.bytes;
   return w;
 }

@@ -48,6 +48,7 @@ PROTOTYPES = {
     "xr_last_error": (C.c_char_p, []),
     "xr_abi_version": (_int, []),
     "xr_device_info": (_int, [C.POINTER(_int)] * 4),
+    "xr_reserve_sms": (_int, [_int]),
     "xr_gather_rows": (_int, [_p, _i64, _i64, _int, _p, _p, _i64, _p, _int, _p, _p]),
     "xr_scatter_rows": (_int, [_p, _i64, _i64, _p, _p, _i64, _p]),
     "xr_row_nonzero": (_int, [_p, _i64, _i64, _int, _p, _p]),

@@ -169,6 +169,15 @@ class ShardedIndex:
         return all_gather_merge(s, i, top_k, group=self.group, merge_fn=self.merge_fn)
 
 
+def reserve_sms(n: int) -> int:
+    """Leave ``n`` SMs free for concurrent kernels (the NCCL all-reduce of the trainer's DDP wrapper): the
+    persistent tensor-core kernels of this package then launch ``#SMs - n`` CTAs.  Call before building
+    ``PoolLossStep`` / ``SearchPlan`` objects (their CUDA graphs bake the grid).  Returns the previous value."""
+    from . import _native as N
+
+    return int(N.lib().xr_reserve_sms(int(n)))
+
+
 def reduce_loss(loss: torch.Tensor, *, group=None) -> torch.Tensor:
     """Global summed loss for logging: the reference's losses are sums over rows
     (losses.py:146-147), so ranks add."""
