@@ -50,8 +50,9 @@ enum RowSlot {
   S_ALIGN = 0, S_CONTR, S_INFONCE, S_NCE, S_HINGE, S_LOGISTIC,
   S_DENS, S_POS, S_NCOUNT, S_NSUM, S_NSQ, S_NMIN, S_NMAX, S_USED
 };
+constexpr size_t kRowlossPartialBytes = 16384;   // scratch of the two-launch row-slot reduction
 int launch_rowloss_reduce(const double* row_out, int64_t m, int64_t c, int n_hard, double* losses_out,
-                          double* stats_out, cudaStream_t s, const int* dyn_m_cn = nullptr);
+                          double* stats_out, cudaStream_t s, const int* dyn_m_cn, double* partial);
 
 // ---- small device helpers --------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

@@ -31,6 +31,7 @@
 #include "common.cuh"
 #include "sm100.cuh"
 #include "filter.cuh"
+#include "rownorm.cuh"
 
 #include <cstring>
 
@@ -1375,7 +1376,7 @@ extern "C" int xr_fused_pool_loss(const void* q, const void* pos, const void* ne
 // the per-item scalars (CG x 128 x NSCAL_ALL floats) alias the partial-dQ region (128 x 384 floats),
 // which the forward-only ALL kinds never write; the row slots follow the fused workspace
 static_assert(fk::CG * fk::NSCAL_ALL <= fk::D, "ALL-kind scalars must fit the partial-dQ region");
-static size_t fused_all_extra_bytes(long long m) { return align256((size_t)m * ROW_SLOTS * 8); }
+static size_t fused_all_extra_bytes(long long m) { return align256((size_t)m * ROW_SLOTS * 8) + kRowlossPartialBytes; }
 
 extern "C" size_t xr_fused_pool_all_workspace_bytes(int64_t m, int64_t cn, int64_t dim) {
   if (dim != fk::D || m <= 0 || cn <= 0) return 512;
@@ -1430,8 +1431,10 @@ static int fused_all_launch(const void* q, const void* pos, const void* neg, lon
       ws.part_o, ws.t, zref, (int)m, (int)cn, grid, cosine, cfg->logits_bf16, cfg->scale, cfg->margin, row_out,
       dyn_main);
   XR_LAUNCH_CHECK("fused_finalize_all");
+  // (row_out spans the upper bound m rows; the reduction's scratch follows it)
   return launch_rowloss_reduce(row_out, m, cn + 1, 0, losses_out, stats_out, s,
-                               reinterpret_cast<const int*>(dyn_main));
+                               reinterpret_cast<const int*>(dyn_main),
+                               reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(row_out) + align256((size_t)m * ROW_SLOTS * 8)));
 }
 
 extern "C" int xr_fused_pool_all(const void* q, const void* pos, const void* neg, int64_t m,
@@ -1512,6 +1515,40 @@ step_gather_kernel(const char* __restrict__ tok, int tok_f32, const char* __rest
   }
 }
 
+// row-normalised bf16 copies of the step's three operand buffers in ONE launch (losses.py:206-208: both
+// sides normalised, norms clamped at eps): job 0 q -> qn (+ 1/||q|| for the chain rule), job 1 pos -> pn,
+// job 2 neg -> nn.  Warp per row; only the rows the tensor maps can reach are touched (up to the next
+// multiple of 128 past the device-side row counts).
+__global__ void __launch_bounds__(256)
+step_normalize3_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ pos,
+                       const __nv_bfloat16* __restrict__ neg, const FusedDyn* __restrict__ dyn,
+                       int64_t n_pos, float eps, __nv_bfloat16* __restrict__ qn,
+                       __nv_bfloat16* __restrict__ pn, __nv_bfloat16* __restrict__ nn,
+                       float* __restrict__ inv_q) {
+  const int job = blockIdx.y;
+  const __nv_bfloat16* x = job == 0 ? q : (job == 1 ? pos : neg);
+  __nv_bfloat16* y = job == 0 ? qn : (job == 1 ? pn : nn);
+  int64_t rows = ((int64_t)(job == 2 ? dyn->cn : dyn->m) + 127) / 128 * 128;
+  if (rows > n_pos) rows = n_pos;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const float inv = normalize_row384_bf16(x + r * fk::D, y + r * fk::D, eps, lane);
+    if (job == 0 && lane == 0) inv_q[r] = inv;
+  }
+}
+static int launch_step_normalize3(const __nv_bfloat16* q, const __nv_bfloat16* pos, const __nv_bfloat16* neg,
+                                  const FusedDyn* dyn, int64_t n_pos, __nv_bfloat16* qn, __nv_bfloat16* pn,
+                                  __nv_bfloat16* nn, float* inv_q, cudaStream_t s) {
+  int64_t gx = (n_pos * 32 + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 4;
+  if (gx > cap) gx = cap;
+  step_normalize3_kernel<<<dim3((unsigned)gx, 3), 256, 0, s>>>(q, pos, neg, dyn, n_pos, 1e-8f, qn, pn, nn, inv_q);
+  XR_LAUNCH_CHECK("step_normalize3");
+  return XR_OK;
+}
+
 struct StepWs {
   int64_t *sel_attn, *sel_pos, *inv_pos;
   uint8_t *attn, *pos_mask;
@@ -1562,7 +1599,7 @@ static MonitorWs carve_monitor_ws(void* base, long long n_pos) {
   w.nn = (__nv_bfloat16*)p;   p += align256(n * fk::D * 2);
   w.inv = (float*)p;          p += align256(n * 4);
   w.inv_q = (float*)p;        p += align256(n * 4);
-  w.row_out = (double*)p;     p += align256(n * ROW_SLOTS * 8);
+  w.row_out = (double*)p;     p += align256(n * ROW_SLOTS * 8) + kRowlossPartialBytes;
   w.bytes = (size_t)(p - (uint8_t*)base);
   return w;
 }
@@ -1642,9 +1679,9 @@ extern "C" int xr_pool_step_compute(int64_t n_pos, int64_t dim, int loss_kind, c
   // cosine kinds (CCL, losses.py:206-208, 338-372): row-normalised copies of the three operands (all
   // n_pos rows: static shapes), 1/||q|| kept for the chain rule through the query normalisation
   const MonitorWs mw = carve_monitor_ws((uint8_t*)workspace + w.bytes, n_pos);
-  if ((rc = xr_normalize_rows(w.q, n_pos, fk::D, XR_BF16, 1e-8f, mw.qn, XR_BF16, mw.inv_q, stream))) return rc;
-  if ((rc = xr_normalize_rows(w.pos, n_pos, fk::D, XR_BF16, 1e-8f, mw.pn, XR_BF16, mw.inv, stream))) return rc;
-  if ((rc = xr_normalize_rows(w.neg, n_pos, fk::D, XR_BF16, 1e-8f, mw.nn, XR_BF16, mw.inv, stream))) return rc;
+  if ((rc = launch_step_normalize3(w.q, w.pos, w.neg, w.fused.dyn, n_pos, mw.qn, mw.pn, mw.nn, mw.inv_q,
+                                   as_stream(stream))))
+    return rc;
   xr_loss_config ccfg = *cfg;
   ccfg.logits_bf16 = 0;   // cosine logits stay fp32 under autocast
   return fused_launch_all(mw.qn, mw.pn, mw.nn, n_pos, n_pos, loss_kind, &ccfg, mw.inv_q, grad_scale, nullptr,
@@ -1704,9 +1741,7 @@ extern "C" int xr_pool_step_monitor(int64_t n_pos, int64_t dim, const xr_loss_co
     return rc;
   // cosine family on the row-normalised copies (all n_pos rows: the buffers are sized by n_pos and
   // rows past the counts are masked by the kernels)
-  if ((rc = xr_normalize_rows(w.q, n_pos, fk::D, XR_BF16, 1e-8f, mw.qn, XR_BF16, mw.inv, stream))) return rc;
-  if ((rc = xr_normalize_rows(w.pos, n_pos, fk::D, XR_BF16, 1e-8f, mw.pn, XR_BF16, mw.inv, stream))) return rc;
-  if ((rc = xr_normalize_rows(w.neg, n_pos, fk::D, XR_BF16, 1e-8f, mw.nn, XR_BF16, mw.inv, stream))) return rc;
+  if ((rc = launch_step_normalize3(w.q, w.pos, w.neg, w.fused.dyn, n_pos, mw.qn, mw.pn, mw.nn, mw.inv, s))) return rc;
   xr_loss_config ccfg = *cfg;
   ccfg.logits_bf16 = 0;   // cosine logits stay fp32 under autocast
   return fused_all_launch(mw.qn, mw.pn, mw.nn, n_pos, n_pos, 1, &ccfg, w.fused, true, mw.row_out,

@@ -5,6 +5,7 @@
 // HBM-bound byte movers: 128-bit accesses, several independent loads in flight per thread,
 // grids sized in multiples of the SM count.
 #include "common.cuh"
+#include "rownorm.cuh"
 
 namespace xr {
 
@@ -392,6 +393,19 @@ __global__ void normalize_rows_kernel(const TI* __restrict__ x, int64_t n_rows, 
   }
 }
 
+// D = 384, bf16 -> bf16: the vectorised row routine the sync-free step uses as well (same bits)
+__global__ void __launch_bounds__(256)
+normalize_rows384_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t n_rows, float eps,
+                              __nv_bfloat16* __restrict__ y, float* __restrict__ inv_norm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n_rows; r += nwarps) {
+    const float inv = normalize_row384_bf16(x + r * 384, y ? y + r * 384 : nullptr, eps, lane);
+    if (inv_norm && lane == 0) inv_norm[r] = inv;
+  }
+}
+
 static inline int grid_for(int64_t work_items, int threads, int per_sm = 8) {
   int64_t blocks = (work_items + threads - 1) / threads;
   const int64_t cap = (int64_t)sm_count() * per_sm;
@@ -550,6 +564,10 @@ extern "C" int xr_normalize_rows(const void* x, int64_t n_rows, int64_t dim, int
   else if (x_dtype == XR_F32 && y_dtype == XR_BF16)
     normalize_rows_kernel<float, __nv_bfloat16><<<grid, 256, 0, s>>>(
         (const float*)x, n_rows, dim, eps, (__nv_bfloat16*)y, inv_norm);
+  else if (x_dtype == XR_BF16 && y_dtype == XR_BF16 && dim == 384 && (uintptr_t)x % 16 == 0 &&
+           (uintptr_t)y % 16 == 0)
+    normalize_rows384_bf16_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, n_rows, eps,
+                                                       (__nv_bfloat16*)y, inv_norm);
   else if (x_dtype == XR_BF16 && y_dtype == XR_BF16)
     normalize_rows_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>(
         (const __nv_bfloat16*)x, n_rows, dim, eps, (__nv_bfloat16*)y, inv_norm);

@@ -43,25 +43,29 @@ rowloss_kernel(const float* __restrict__ logits, int64_t m, int64_t c, int64_t l
     __syncthreads();
   }
 }
-// single block, fixed order: fold the per-row slots into the 7 loss sums and the stats block
-__global__ void __launch_bounds__(1024)
-rowloss_reduce_kernel(const double* __restrict__ row_out, int64_t m, int64_t c, int n_hard,
-                      double* __restrict__ losses_out, double* __restrict__ stats_out,
-                      const int* __restrict__ dyn_m_cn) {
+// fold the per-row slots into the 7 loss sums and the stats block.  Two launches, both in a fixed order
+// (deterministic): RR_BLOCKS blocks reduce contiguous row ranges into partials (the 1.9 MB of row slots at
+// configs[1] took 46 us through ONE SM), one block folds the partials.
+constexpr int RR_BLOCKS = 64, RR_THREADS = 256, RR_NS = 13;   // 6 losses + dens + pos sum/sq + ncount + nsum + nsq
+constexpr int RR_STRIDE = RR_NS + 4;                          // + pos min/max, neg min/max
+__global__ void __launch_bounds__(RR_THREADS)
+rowloss_partial_kernel(const double* __restrict__ row_out, int64_t m, int64_t c, int n_hard,
+                       double* __restrict__ partial, const int* __restrict__ dyn_m_cn) {
   if (dyn_m_cn) {   // shape known only on the device (sync-free step): {rows, pool size}
     m = dyn_m_cn[0];
     c = (int64_t)dyn_m_cn[1] + 1;
   }
-  constexpr int NS = 13;  // 6 losses + dens + pos sum + pos sq + ncount + nsum + nsq + (min/max apart)
-  __shared__ double s_sum[32][NS];
-  __shared__ double s_mm[32][4];
-  double acc[NS];
+  __shared__ double s_sum[RR_THREADS / 32][RR_NS];
+  __shared__ double s_mm[RR_THREADS / 32][4];
+  double acc[RR_NS];
 #pragma unroll
-  for (int k = 0; k < NS; ++k) acc[k] = 0.0;
+  for (int k = 0; k < RR_NS; ++k) acc[k] = 0.0;
   double pmin = CUDART_INF, pmax = -CUDART_INF, nmin = CUDART_INF, nmax = -CUDART_INF;
   double num_neg = (double)(c - 1);
   if (n_hard > 0 && (double)n_hard < num_neg) num_neg = (double)n_hard;  // losses.py:387-389
-  for (int64_t i = threadIdx.x; i < m; i += blockDim.x) {
+  const int64_t per = (m + RR_BLOCKS - 1) / RR_BLOCKS;
+  const int64_t lo = (int64_t)blockIdx.x * per, hi = lo + per < m ? lo + per : m;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += RR_THREADS) {
     const double* o = row_out + i * ROW_SLOTS;
     acc[0] += o[S_ALIGN]; acc[1] += o[S_CONTR]; acc[2] += o[S_INFONCE]; acc[3] += o[S_NCE];
     acc[4] += o[S_HINGE]; acc[5] += o[S_LOGISTIC];
@@ -73,7 +77,7 @@ rowloss_reduce_kernel(const double* __restrict__ row_out, int64_t m, int64_t c, 
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k < NS; ++k) acc[k] = warp_sum(acc[k]);
+  for (int k = 0; k < RR_NS; ++k) acc[k] = warp_sum(acc[k]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     pmin = fmin(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
@@ -83,43 +87,69 @@ rowloss_reduce_kernel(const double* __restrict__ row_out, int64_t m, int64_t c, 
   }
   if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < NS; ++k) s_sum[warp][k] = acc[k];
+    for (int k = 0; k < RR_NS; ++k) s_sum[warp][k] = acc[k];
     s_mm[warp][0] = pmin; s_mm[warp][1] = pmax; s_mm[warp][2] = nmin; s_mm[warp][3] = nmax;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double tot[NS];
-    for (int k = 0; k < NS; ++k) tot[k] = 0.0;
-    const int nw = blockDim.x >> 5;
-    for (int w = 0; w < nw; ++w) {
-      for (int k = 0; k < NS; ++k) tot[k] += s_sum[w][k];
+    double tot[RR_NS];
+    for (int k = 0; k < RR_NS; ++k) tot[k] = 0.0;
+    for (int w = 0; w < RR_THREADS / 32; ++w) {
+      for (int k = 0; k < RR_NS; ++k) tot[k] += s_sum[w][k];
       pmin = fmin(pmin, s_mm[w][0]); pmax = fmax(pmax, s_mm[w][1]);
       nmin = fmin(nmin, s_mm[w][2]); nmax = fmax(nmax, s_mm[w][3]);
     }
-    if (losses_out) {
-      losses_out[XR_LOSS_ALIGNMENT] = tot[0];
-      losses_out[XR_LOSS_CONTRASTIVE] = tot[1];
-      losses_out[XR_LOSS_ALIGNMENT_CONTRASTIVE] = tot[0] + tot[1];
-      losses_out[XR_LOSS_INFONCE] = tot[2];
-      losses_out[XR_LOSS_NCE] = tot[3];
-      losses_out[XR_LOSS_PAIRWISE_HINGE] = tot[4];
-      losses_out[XR_LOSS_PAIRWISE_LOGISTIC] = tot[5];
-    }
-    if (stats_out) {
-      stats_out[0] = tot[6];
-      stats_out[1] = (double)m;
-      stats_out[2] = tot[7]; stats_out[3] = tot[8]; stats_out[4] = pmin; stats_out[5] = pmax;
-      stats_out[6] = tot[9]; stats_out[7] = tot[10]; stats_out[8] = tot[11];
-      stats_out[9] = nmin; stats_out[10] = nmax; stats_out[11] = num_neg;
-      for (int k = 12; k < XR_STATS_SLOTS; ++k) stats_out[k] = 0.0;
-    }
+    double* o = partial + (size_t)blockIdx.x * RR_STRIDE;
+    for (int k = 0; k < RR_NS; ++k) o[k] = tot[k];
+    o[RR_NS] = pmin; o[RR_NS + 1] = pmax; o[RR_NS + 2] = nmin; o[RR_NS + 3] = nmax;
   }
 }
 
-// shared with the tensor-core all-losses pass (fused_loss_sm100.cu), which fills the same row slots
+__global__ void rowloss_reduce_kernel(const double* __restrict__ partial, int64_t m, int64_t c, int n_hard,
+                                      double* __restrict__ losses_out, double* __restrict__ stats_out,
+                                      const int* __restrict__ dyn_m_cn) {
+  if (dyn_m_cn) {
+    m = dyn_m_cn[0];
+    c = (int64_t)dyn_m_cn[1] + 1;
+  }
+  if (threadIdx.x != 0) return;
+  double num_neg = (double)(c - 1);
+  if (n_hard > 0 && (double)n_hard < num_neg) num_neg = (double)n_hard;
+  double tot[RR_NS];
+  for (int k = 0; k < RR_NS; ++k) tot[k] = 0.0;
+  double pmin = CUDART_INF, pmax = -CUDART_INF, nmin = CUDART_INF, nmax = -CUDART_INF;
+  for (int b = 0; b < RR_BLOCKS; ++b) {   // fixed order
+    const double* o = partial + (size_t)b * RR_STRIDE;
+    for (int k = 0; k < RR_NS; ++k) tot[k] += o[k];
+    pmin = fmin(pmin, o[RR_NS]); pmax = fmax(pmax, o[RR_NS + 1]);
+    nmin = fmin(nmin, o[RR_NS + 2]); nmax = fmax(nmax, o[RR_NS + 3]);
+  }
+  if (losses_out) {
+    losses_out[XR_LOSS_ALIGNMENT] = tot[0];
+    losses_out[XR_LOSS_CONTRASTIVE] = tot[1];
+    losses_out[XR_LOSS_ALIGNMENT_CONTRASTIVE] = tot[0] + tot[1];
+    losses_out[XR_LOSS_INFONCE] = tot[2];
+    losses_out[XR_LOSS_NCE] = tot[3];
+    losses_out[XR_LOSS_PAIRWISE_HINGE] = tot[4];
+    losses_out[XR_LOSS_PAIRWISE_LOGISTIC] = tot[5];
+  }
+  if (stats_out) {
+    stats_out[0] = tot[6];
+    stats_out[1] = (double)m;
+    stats_out[2] = tot[7]; stats_out[3] = tot[8]; stats_out[4] = pmin; stats_out[5] = pmax;
+    stats_out[6] = tot[9]; stats_out[7] = tot[10]; stats_out[8] = tot[11];
+    stats_out[9] = nmin; stats_out[10] = nmax; stats_out[11] = num_neg;
+    for (int k = 12; k < XR_STATS_SLOTS; ++k) stats_out[k] = 0.0;
+  }
+}
+
+// shared with the tensor-core all-losses pass (fused_loss_sm100.cu), which fills the same row slots.
+// `partial`: kRowlossPartialBytes of scratch.
 int launch_rowloss_reduce(const double* row_out, int64_t m, int64_t c, int n_hard, double* losses_out,
-                          double* stats_out, cudaStream_t s, const int* dyn_m_cn) {
-  rowloss_reduce_kernel<<<1, 1024, 0, s>>>(row_out, m, c, n_hard, losses_out, stats_out, dyn_m_cn);
+                          double* stats_out, cudaStream_t s, const int* dyn_m_cn, double* partial) {
+  rowloss_partial_kernel<<<RR_BLOCKS, RR_THREADS, 0, s>>>(row_out, m, c, n_hard, partial, dyn_m_cn);
+  XR_LAUNCH_CHECK("rowloss_partial");
+  rowloss_reduce_kernel<<<1, 32, 0, s>>>(partial, m, c, n_hard, losses_out, stats_out, dyn_m_cn);
   XR_LAUNCH_CHECK("rowloss_reduce");
   return XR_OK;
 }
@@ -134,7 +164,7 @@ static inline int rl_grid(int64_t m) {
 using namespace xr;
 
 extern "C" size_t xr_rowloss_workspace_bytes(int64_t m, int64_t c, int num_hard_negatives) {
-  size_t b = (size_t)(m > 0 ? m : 1) * ROW_SLOTS * sizeof(double) + 256;
+  size_t b = (size_t)(m > 0 ? m : 1) * ROW_SLOTS * sizeof(double) + 256 + kRowlossPartialBytes;
   if (num_hard_negatives > 0 && num_hard_negatives < c)
     b += (size_t)rl_grid(m) * (size_t)c + 256;
   return b;
@@ -155,7 +185,8 @@ extern "C" int xr_rowloss(const float* logits, int64_t m, int64_t c, int64_t ld,
   XR_CHECK_ARG(grad_kind < 0 || dlogits, "xr_rowloss: dlogits is null");
   cudaStream_t s = as_stream(stream);
   double* row_out = (double*)workspace;
-  uint8_t* maskbuf = (uint8_t*)workspace + (((size_t)(m > 0 ? m : 1) * ROW_SLOTS * sizeof(double) + 255) / 256) * 256;
+  double* partial = (double*)((uint8_t*)workspace + (((size_t)(m > 0 ? m : 1) * ROW_SLOTS * sizeof(double) + 255) / 256) * 256);
+  uint8_t* maskbuf = (uint8_t*)partial + kRowlossPartialBytes;
   if (m > 0) {
     rowloss_kernel<<<rl_grid(m), RL_THREADS, 0, s>>>(logits, m, c, ld, target_mode, target, *cfg,
                                                      loss_mask, grad_kind, grad_scale, dlogits,
@@ -163,9 +194,8 @@ extern "C" int xr_rowloss(const float* logits, int64_t m, int64_t c, int64_t ld,
     XR_LAUNCH_CHECK("rowloss");
   }
   if (losses_out || stats_out) {
-    rowloss_reduce_kernel<<<1, 1024, 0, s>>>(row_out, m, c, cfg->num_hard_negatives, losses_out,
-                                             stats_out, nullptr);
-    XR_LAUNCH_CHECK("rowloss_reduce");
+    int rc = launch_rowloss_reduce(row_out, m, c, cfg->num_hard_negatives, losses_out, stats_out, s, nullptr, partial);
+    if (rc) return rc;
   }
   return XR_OK;
 }

@@ -474,7 +474,7 @@ extern "C" int xr_dq_sampled(const float* dlogits, int64_t ld, const void* q, co
 
 // ---- BASELINE config 3 in one pass: logits + EmbedLoss pipeline + dL/dq per query row -----------
 extern "C" size_t xr_sampled_step_workspace_bytes(int64_t m) {
-  return (size_t)(m > 0 ? m : 1) * ROW_SLOTS * sizeof(double) + 256;
+  return ((size_t)(m > 0 ? m : 1) * ROW_SLOTS * sizeof(double) + 255) / 256 * 256 + kRowlossPartialBytes;
 }
 
 extern "C" int xr_sampled_step(const void* q, const void* table, int64_t n_rows,
@@ -520,6 +520,8 @@ extern "C" int xr_sampled_step(const void* q, const void* table, int64_t n_rows,
     XR_LAUNCH_CHECK("sampled_step384");
   }
   if (losses_out || stats_out)
-    return launch_rowloss_reduce(row_out, m, c, cfg->num_hard_negatives, losses_out, stats_out, s);
+    return launch_rowloss_reduce(row_out, m, c, cfg->num_hard_negatives, losses_out, stats_out, s, nullptr,
+                                 (double*)((uint8_t*)workspace +
+                                           ((size_t)(m > 0 ? m : 1) * ROW_SLOTS * sizeof(double) + 255) / 256 * 256));
   return XR_OK;
 }
