@@ -438,6 +438,42 @@ int xr_retrieval_metrics(const int64_t* rec, int64_t u, int64_t k, const int64_t
                          const int64_t* tgt_ids, int64_t top_k, float* out, uint8_t* valid,
                          void* stream);
 
+/* ---- sequence encoder -------------------------------------------------------------
+ * The reference's encoder is a HuggingFace BertModel(is_decoder=True) fed `inputs_embeds` from the frozen
+ * item table (models.py:51-102, 306-345).  These are the fused kernels around its linear layers (which
+ * are plain GEMMs and stay with cuBLAS): hidden size 384, head_dim 32, sequences of at most 384 positions.
+ * Activations `dtype`: XR_F32 or XR_BF16; LayerNorm statistics, softmax and every reduction are fp32.
+ *
+ * embed_ln: out[b,l,:] = LayerNorm(table[idx[b,l]] + pos_emb[l] + type_emb[0:H]) (BertEmbeddings with
+ * inputs_embeds; the history gather of models.py:336-338 fused in), stats (B*L, 2) = {mean, rstd},
+ * mask[b,l] = any(table[idx[b,l]] != 0) (the attention mask of models.py:343).                           */
+size_t xr_enc_ln_workspace_bytes(int64_t n_tok);
+int xr_enc_embed_ln_fwd(const float* table, int64_t n_table_rows, const int64_t* idx, const float* pos_emb,
+                        const float* type_emb, const float* gamma, const float* beta, int64_t batch,
+                        int64_t seq_len, int64_t dim, float eps, float* out, float* stats, uint8_t* mask,
+                        int32_t* err_flag, void* stream);
+/* gradients of the position embeddings (seq_len, H), token-type row 0 (H), LayerNorm weight / bias; the item
+ * table is frozen (models.py:251-253).  workspace: xr_enc_ln_workspace_bytes(batch * seq_len).            */
+int xr_enc_embed_ln_bwd(const float* table, int64_t n_table_rows, const int64_t* idx, const float* pos_emb,
+                        const float* type_emb, const float* gamma, const float* stats, const float* dout,
+                        int64_t batch, int64_t seq_len, int64_t dim, float* dpos, float* dtype0, float* dgamma,
+                        float* dbeta, void* workspace, void* stream);
+/* out = LayerNorm(y + residual) (BertSelfOutput / BertOutput; y = the dense layer's output incl. bias).
+ * Backward: dresidual (fp32) and dy (y's dtype) both receive the LayerNorm input gradient.                */
+int xr_enc_add_ln_fwd(const void* y, int y_dtype, const float* residual, const float* gamma, const float* beta,
+                      int64_t n_tok, int64_t dim, float eps, float* out, float* stats, void* stream);
+int xr_enc_add_ln_bwd(const void* y, int y_dtype, const float* residual, const float* gamma, const float* stats,
+                      const float* dout, int64_t n_tok, int64_t dim, float* dresidual, void* dy, float* dgamma,
+                      float* dbeta, void* workspace, void* stream);
+/* exact (erf) GELU: dy == NULL -> out = gelu(x); else out = dy * gelu'(x).                               */
+int xr_enc_gelu(const void* x, const void* dy, int64_t n, int dtype, void* out, void* stream);
+/* causal + key-padding multi-head self-attention on qkv (B, L, 3 * n_heads * 32) = [Q | K | V]; keymask
+ * (B, L) bytes.  dctx == NULL: forward, out = ctx (B, L, n_heads * 32), lse (B, n_heads, L) written.
+ * dctx != NULL: backward, out = dqkv, lse and ctx from the forward.  Deterministic (no atomics).          */
+int xr_enc_attention(const void* qkv, const uint8_t* keymask, const void* ctx, const void* dctx, float* lse,
+                     int64_t batch, int64_t seq_len, int64_t n_heads, int64_t head_dim, int dtype, void* out,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,173 @@
+"""Sequence encoder against golden vectors produced by executing the reference's own
+encoder class — transformers' BertModel(is_decoder=True) on inputs_embeds, built and called as
+xfmr_rec/models.py:92-101, 336-345 do (tests/golden/make_golden_encoder.py)."""
+
+import numpy as np
+import pytest
+import torch
+
+HF_KEYS_LAYER = [
+    "attention.self.query.weight", "attention.self.query.bias", "attention.self.key.weight",
+    "attention.self.key.bias", "attention.self.value.weight", "attention.self.value.bias",
+    "attention.output.dense.weight", "attention.output.dense.bias", "attention.output.LayerNorm.weight",
+    "attention.output.LayerNorm.bias", "intermediate.dense.weight", "intermediate.dense.bias",
+    "output.dense.weight", "output.dense.bias", "output.LayerNorm.weight", "output.LayerNorm.bias"]
+HF_KEYS = ["embeddings.word_embeddings.weight", "embeddings.position_embeddings.weight",
+           "embeddings.token_type_embeddings.weight", "embeddings.LayerNorm.weight", "embeddings.LayerNorm.bias",
+           "pooler.dense.weight", "pooler.dense.bias"]
+
+
+def seeded_state_dict(ref_sd: dict, seed: int) -> dict:
+    """The SAME fill as tests/golden/make_golden_encoder.py (the fixture stores no weights)."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k in sorted(ref_sd):
+        shape = tuple(ref_sd[k].shape)
+        if k.endswith("LayerNorm.weight"):
+            out[k] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        else:
+            out[k] = 0.05 * torch.randn(shape, generator=g)
+    return out
+
+
+def test_state_dict_keys_are_huggingface_bert_keys():
+    """A BertModel checkpoint (the auto_model inside the SentenceTransformer the reference saves,
+    models.py:258-266) must load unchanged: same parameter names and shapes."""
+    from xfmr_rec_b200.encoder import EncoderConfig, SeqEncoder
+
+    enc = SeqEncoder(EncoderConfig(num_hidden_layers=2, intermediate_size=128, max_seq_length=24))
+    want = set(HF_KEYS) | {f"encoder.layer.{i}.{k}" for i in range(2) for k in HF_KEYS_LAYER}
+    assert set(enc.state_dict()) == want
+    sd = enc.state_dict()
+    assert sd["encoder.layer.1.intermediate.dense.weight"].shape == (128, 384)
+    assert sd["embeddings.position_embeddings.weight"].shape == (24, 384)
+    assert sd["embeddings.token_type_embeddings.weight"].shape == (2, 384)
+
+
+def test_encoder_has_no_cpu_fallback():
+    from xfmr_rec_b200 import _native
+    from xfmr_rec_b200.encoder import SeqEncoder
+
+    with pytest.raises(_native.NativeError):
+        SeqEncoder()(torch.zeros((2, 5), dtype=torch.int64), torch.zeros((4, 384)))
+
+
+def _load(golden_dir, tag):
+    from xfmr_rec_b200.encoder import EncoderConfig, SeqEncoder
+
+    z = np.load(golden_dir / f"encoder_{tag}.npz")
+    layers, inter, max_pos, seed = (int(v) for v in z["config"])
+    enc = SeqEncoder(EncoderConfig(num_hidden_layers=layers, intermediate_size=inter, max_seq_length=max_pos))
+    enc.load_state_dict(seeded_state_dict(enc.state_dict(), seed))
+    return z, enc.cuda()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["default_1layer", "2layer_i128"])
+def test_encoder_fp32_matches_the_reference_bert(golden_dir, tag):
+    """fp32: token embeddings, pooled sentence embeddings and every parameter gradient against
+    BertModel's own outputs (1e-5 relative: north_star's fp32 tolerance; gradients 1e-4 of their scale)."""
+    z, enc = _load(golden_dir, tag)
+    idx, table = torch.from_numpy(z["idx"]).cuda(), torch.from_numpy(z["table"]).cuda()
+    out = enc(idx, table)
+    tok = out["token_embeddings"]
+    want = z["token_embeddings"]
+    valid = (z["idx"] != 0)
+    assert np.array_equal(out["attention_mask"].cpu().numpy(), valid.astype(np.int64))
+    np.testing.assert_allclose(tok.detach().cpu().numpy()[valid], want[valid], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(out["sentence_embedding"].detach().cpu().numpy(), z["sentence_embedding"],
+                               rtol=1e-4, atol=2e-5)
+    (tok * torch.from_numpy(z["upstream"]).cuda()).sum().backward()
+    grads = dict(enc.named_parameters())
+    checked = 0
+    for key in z.files:
+        if key.startswith("grad/"):
+            got, ref = grads[key[5:]].grad.cpu().numpy(), z[key]
+            if "position_embeddings" in key:
+                got = got[: ref.shape[0]]
+        elif key.startswith("gradsub/"):
+            full = grads[key[8:]].grad
+            assert float(full.norm()) == pytest.approx(float(z["gradnorm/" + key[8:]]), rel=1e-4), key
+            got, ref = full[::8, ::8].cpu().numpy(), z[key]
+        else:
+            continue
+        scale = max(np.abs(ref).max(), 1e-6)
+        assert np.abs(got - ref).max() <= 2e-4 * scale, (key, np.abs(got - ref).max(), scale)
+        checked += 1
+    assert checked >= 20
+    assert enc.pooler.dense.weight.grad is None and enc.embeddings.word_embeddings.weight.grad is None
+
+
+@pytest.mark.gpu
+def test_encoder_bf16_mixed_is_close_to_fp32(golden_dir):
+    """compute_dtype=bfloat16 (Lightning's bf16-mixed policy: bf16 GEMMs / attention / GELU, fp32 residual
+    stream, LayerNorm and softmax): within bf16 tolerance of the fp32 reference."""
+    from xfmr_rec_b200.encoder import SeqEncoder
+
+    z, enc = _load(golden_dir, "2layer_i128")
+    enc16 = SeqEncoder(enc.config, compute_dtype=torch.bfloat16).cuda()
+    enc16.load_state_dict(enc.state_dict())
+    idx, table = torch.from_numpy(z["idx"]).cuda(), torch.from_numpy(z["table"]).cuda()
+    tok = enc16(idx, table)["token_embeddings"]
+    valid = (z["idx"] != 0)
+    got, want = tok.detach().cpu().numpy()[valid], z["token_embeddings"][valid]
+    assert np.linalg.norm(got - want) <= 2e-2 * np.linalg.norm(want)
+    (tok * torch.from_numpy(z["upstream"]).cuda()).sum().backward()
+    for key in z.files:
+        if key.startswith("grad/") and "position" not in key:
+            got, ref = dict(enc16.named_parameters())[key[5:]].grad.cpu().numpy(), z[key]
+            assert np.linalg.norm(got - ref) <= 5e-2 * np.linalg.norm(ref) + 1e-4, key
+
+
+@pytest.mark.gpu
+def test_encoder_is_deterministic_and_truncates(golden_dir):
+    """Backward without atomics: two runs give the same bits.  Histories longer than max_seq_length keep
+    their LAST max_seq_length positions (models.py:334-337)."""
+    z, enc = _load(golden_dir, "default_1layer")
+    idx, table = torch.from_numpy(z["idx"]).cuda(), torch.from_numpy(z["table"]).cuda()
+    res = []
+    for _ in range(2):
+        enc.zero_grad()
+        tok = enc(idx, table)["token_embeddings"]
+        (tok * torch.from_numpy(z["upstream"]).cuda()).sum().backward()
+        res.append([tok.detach().clone()] + [p.grad.clone() for p in enc.parameters() if p.grad is not None])
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+    long_idx = torch.cat([torch.randint(1, 60, (idx.size(0), 40), device="cuda"), idx], 1)[:, -60:]
+    a = enc(long_idx, table)["token_embeddings"]
+    b = enc(long_idx[:, -32:], table)["token_embeddings"]
+    assert a.shape[1] == 32 and torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_encoder_train_step_feeds_the_loss_step_gradient_in_place(golden_dir):
+    """encoder forward -> PoolLossStep (sync-free scoring-and-loss step) -> encoder backward with the
+    step's dL/d token_embeddings as the upstream gradient: same parameter gradients as the module path
+    (compute_embeds + loss module + autograd through the same encoder)."""
+    import xfmr_rec_b200 as xr
+    from xfmr_rec_b200.encoder import EncoderConfig, SeqEncoder, encoder_train_step
+
+    torch.manual_seed(3)
+    b, l, n = 6, 24, 500
+    table = torch.randn(n + 1, 384, device="cuda") / 384 ** 0.5
+    table[0] = 0
+    emb = xr.models.ItemEmbeddings(table, add_padding_row=False).cuda()
+    lens = torch.randint(2, l + 1, (b,), device="cuda")
+    valid = torch.arange(l, device="cuda")[None] < lens[:, None]
+    hist = torch.randint(1, n + 1, (b, l), device="cuda") * valid
+    pos = torch.randint(1, n + 1, (b, l), device="cuda") * valid
+    neg = torch.randint(1, n + 1, (b, l), device="cuda") * valid
+    enc = SeqEncoder(EncoderConfig(num_hidden_layers=2, intermediate_size=96, max_seq_length=l)).cuda()
+    loss_fn = xr.InfoNCELoss(xr.LossConfig())
+    step = xr.PoolLossStep(emb, loss_fn, b, l, token_dtype=torch.float32)
+    loss = encoder_train_step(enc, step, table, hist, pos, neg)
+    got = {k: p.grad.clone() for k, p in enc.named_parameters() if p.grad is not None}
+    enc.zero_grad()
+    tok = enc(hist, table)["token_embeddings"]
+    out = xr.models.compute_embeds(emb, tok, hist, pos, neg, candidate_dtype=torch.bfloat16)
+    l2 = loss_fn(out["query_embed"].bfloat16(), out["candidate_embed"])
+    l2.backward()
+    assert float(loss) == pytest.approx(float(l2), rel=1e-5)
+    for k, p in enc.named_parameters():
+        if p.grad is not None:
+            assert torch.allclose(got[k], p.grad, rtol=2e-2, atol=1e-4 * float(p.grad.abs().max())), k

@@ -1,0 +1,594 @@
+// Sequence encoder of the reference (xfmr_rec/models.py:51-102, 306-345): a HuggingFace BertModel built with
+// is_decoder=True (causal self-attention) fed `inputs_embeds` from the frozen item table.  This file holds
+// the hand-written kernels around the encoder's linear layers:
+//
+//   embed_ln        x0 = LayerNorm(table[idx] + position_emb[l] + token_type_emb[0])   -- the history gather
+//                   of models.py:336-338 fused into the first layer's input, + the attention mask of :343
+//   attention       causal + key-padding multi-head self-attention, head_dim 32, forward and backward
+//                   (deterministic: one pass per query for dQ, one pass per key for dK / dV, no atomics)
+//   gelu            exact (erf) GELU forward / backward on the FFN's intermediate activations
+//   add_ln          LayerNorm(y + residual) forward / backward (BertSelfOutput / BertOutput)
+//
+// The linear layers themselves (QKV, attention output, FFN up / down and their weight / input gradients)
+// are plain GEMMs and go through cuBLAS (torch.nn.functional.linear) in xfmr_rec_b200/encoder.py.
+// Activations are fp32 or bf16 (template parameter); all reductions are fp32.
+#include "common.cuh"
+
+namespace xr {
+
+namespace enc {
+constexpr int H = 384;           // hidden size (all-MiniLM-L6-v2, params.py:11)
+constexpr int HD = 32;           // head dim (12 heads)
+constexpr int PER = H / 32;      // hidden elements per lane of a warp-per-token kernel
+constexpr int MAX_L = 384;      // the backward keeps Q, K, V, dO of one head in shared memory (206 KB at 384)
+}  // namespace enc
+
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) {
+  return v;
+}
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+// warp-per-token LayerNorm over x[PER] (lane-strided columns c = lane + 32 k), HF semantics: biased variance
+__device__ __forceinline__ void ln_row(const float (&x)[enc::PER], const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float eps, int lane, float (&y)[enc::PER],
+                                       float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < enc::PER; ++k) s += x[k];
+  mean = warp_sum(s) * (1.0f / enc::H);
+  float v = 0.f;
+#pragma unroll
+  for (int k = 0; k < enc::PER; ++k) {
+    const float d = x[k] - mean;
+    v = fmaf(d, d, v);
+  }
+  rstd = rsqrtf(warp_sum(v) * (1.0f / enc::H) + eps);
+#pragma unroll
+  for (int k = 0; k < enc::PER; ++k) {
+    const int c = lane + 32 * k;
+    y[k] = (x[k] - mean) * rstd * gamma[c] + beta[c];
+  }
+}
+
+// ---- embeddings: gather + position + token type + LayerNorm ------------------------------------------------
+__global__ void __launch_bounds__(256)
+enc_embed_ln_fwd_kernel(const float* __restrict__ table, int64_t n_table_rows, const int64_t* __restrict__ idx,
+                        const float* __restrict__ pos_emb, const float* __restrict__ type_emb,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, int64_t n_tok, int seq_len,
+                        float eps, float* __restrict__ out, float* __restrict__ stats, uint8_t* __restrict__ mask,
+                        int32_t* __restrict__ err_flag) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t t = warp; t < n_tok; t += nwarps) {
+    int64_t row = idx[t];
+    if (row < 0 || row >= n_table_rows) {
+      if (err_flag) *err_flag = 1;
+      row = 0;
+    }
+    const int l = (int)(t % seq_len);
+    float x[enc::PER], y[enc::PER];
+    bool nz = false;
+#pragma unroll
+    for (int k = 0; k < enc::PER; ++k) {
+      const int c = lane + 32 * k;
+      const float e = __ldg(table + row * enc::H + c);
+      nz |= (e != 0.f);
+      x[k] = e + pos_emb[(int64_t)l * enc::H + c] + type_emb[c];
+    }
+    nz = __any_sync(0xffffffffu, nz);     // models.py:343: (inputs_embeds != 0).any(-1)
+    float mean, rstd;
+    ln_row(x, gamma, beta, eps, lane, y, mean, rstd);
+#pragma unroll
+    for (int k = 0; k < enc::PER; ++k) out[t * enc::H + lane + 32 * k] = y[k];
+    if (lane == 0) {
+      stats[2 * t] = mean;
+      stats[2 * t + 1] = rstd;
+      mask[t] = nz ? 1 : 0;
+    }
+  }
+}
+
+// LayerNorm backward of one token row: dx (returned in registers) + this warp's contributions to dgamma / dbeta
+__device__ __forceinline__ void ln_row_bwd(const float (&x)[enc::PER], const float (&dy)[enc::PER],
+                                           const float* __restrict__ gamma, float mean, float rstd, int lane,
+                                           float (&dx)[enc::PER], float (&dg)[enc::PER], float (&db)[enc::PER]) {
+  float xh[enc::PER], dxh[enc::PER];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < enc::PER; ++k) {
+    const int c = lane + 32 * k;
+    xh[k] = (x[k] - mean) * rstd;
+    dxh[k] = dy[k] * gamma[c];
+    s1 += dxh[k];
+    s2 = fmaf(dxh[k], xh[k], s2);
+    dg[k] += dy[k] * xh[k];
+    db[k] += dy[k];
+  }
+  s1 = warp_sum(s1) * (1.0f / enc::H);
+  s2 = warp_sum(s2) * (1.0f / enc::H);
+#pragma unroll
+  for (int k = 0; k < enc::PER; ++k) dx[k] = rstd * (dxh[k] - s1 - xh[k] * s2);
+}
+
+constexpr int LNB_BLOCKS = 296;   // partial rows of the parameter-gradient reductions (two per SM)
+
+// fold per-warp dgamma / dbeta (registers) into the block's partial row: fixed order inside the block
+__device__ __forceinline__ void ln_param_partials(const float (&dg)[enc::PER], const float (&db)[enc::PER],
+                                                  float* __restrict__ part /* [gridDim.x][2][H] */) {
+  __shared__ float s_g[8][enc::H], s_b[8][enc::H];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < enc::PER; ++k) {
+    s_g[warp][lane + 32 * k] = dg[k];
+    s_b[warp][lane + 32 * k] = db[k];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < enc::H; c += blockDim.x) {
+    float g = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      g += s_g[w][c];
+      b += s_b[w][c];
+    }
+    part[((size_t)blockIdx.x * 2) * enc::H + c] = g;
+    part[((size_t)blockIdx.x * 2 + 1) * enc::H + c] = b;
+  }
+}
+
+// out[j][c] = sum over the n_part partial rows, fixed order (deterministic)
+__global__ void enc_fold_partials_kernel(const float* __restrict__ part, int n_part, int n_vec, int width,
+                                         float* __restrict__ out0, float* __restrict__ out1) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= width) return;
+  for (int j = 0; j < n_vec; ++j) {
+    float s = 0.f;
+    for (int p = 0; p < n_part; ++p) s += part[((size_t)p * n_vec + j) * width + c];
+    (j == 0 ? out0 : out1)[c] = s;
+  }
+}
+
+// backward of embed_ln: dgamma, dbeta (partials), d position_emb[l] (sum over the batch), d token_type_emb[0]
+// (sum over all tokens).  The table is frozen (models.py:251-253): no gradient for it.  dx rows are written
+// to dx_out (scratch) so that the column reductions over the batch run as a second, coalesced kernel.
+__global__ void __launch_bounds__(256)
+enc_embed_ln_bwd_kernel(const float* __restrict__ table, int64_t n_table_rows, const int64_t* __restrict__ idx,
+                        const float* __restrict__ pos_emb, const float* __restrict__ type_emb,
+                        const float* __restrict__ gamma, const float* __restrict__ stats,
+                        const float* __restrict__ dout, int64_t n_tok, int seq_len, float* __restrict__ dx_out,
+                        float* __restrict__ part) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float dg[enc::PER], db[enc::PER];
+#pragma unroll
+  for (int k = 0; k < enc::PER; ++k) dg[k] = db[k] = 0.f;
+  for (int64_t t = warp; t < n_tok; t += nwarps) {
+    int64_t row = idx[t];
+    if (row < 0 || row >= n_table_rows) row = 0;
+    const int l = (int)(t % seq_len);
+    float x[enc::PER], dy[enc::PER], dx[enc::PER];
+#pragma unroll
+    for (int k = 0; k < enc::PER; ++k) {
+      const int c = lane + 32 * k;
+      x[k] = __ldg(table + row * enc::H + c) + pos_emb[(int64_t)l * enc::H + c] + type_emb[c];
+      dy[k] = dout[t * enc::H + c];
+    }
+    ln_row_bwd(x, dy, gamma, stats[2 * t], stats[2 * t + 1], lane, dx, dg, db);
+#pragma unroll
+    for (int k = 0; k < enc::PER; ++k) dx_out[t * enc::H + lane + 32 * k] = dx[k];
+  }
+  ln_param_partials(dg, db, part);
+}
+
+// dpos[l][c] = sum_b dx[b][l][c]  (fixed order over b); one thread per (l, c)
+__global__ void enc_sum_over_batch_kernel(const float* __restrict__ dx, int batch, int seq_len,
+                                          float* __restrict__ dpos) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)seq_len * enc::H) return;
+  float s = 0.f;
+  for (int b = 0; b < batch; ++b) s += dx[(int64_t)b * seq_len * enc::H + e];
+  dpos[e] = s;
+}
+// dtype0[c] = sum_l dpos[l][c]
+__global__ void enc_sum_rows_kernel(const float* __restrict__ x, int rows, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= enc::H) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) s += x[(int64_t)r * enc::H + c];
+  out[c] = s;
+}
+
+// ---- LayerNorm(y + residual): BertSelfOutput / BertOutput ------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+enc_add_ln_fwd_kernel(const T* __restrict__ y, const float* __restrict__ res, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, int64_t n_tok, float eps, float* __restrict__ out,
+                      float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t t = warp; t < n_tok; t += nwarps) {
+    float x[enc::PER], o[enc::PER];
+#pragma unroll
+    for (int k = 0; k < enc::PER; ++k) {
+      const int c = lane + 32 * k;
+      x[k] = to_f32(y[t * enc::H + c]) + res[t * enc::H + c];
+    }
+    float mean, rstd;
+    ln_row(x, gamma, beta, eps, lane, o, mean, rstd);
+#pragma unroll
+    for (int k = 0; k < enc::PER; ++k) out[t * enc::H + lane + 32 * k] = o[k];
+    if (lane == 0) {
+      stats[2 * t] = mean;
+      stats[2 * t + 1] = rstd;
+    }
+  }
+}
+
+// dx = dLN (the gradient of BOTH y and the residual); dgamma / dbeta partials
+template <typename T>
+__global__ void __launch_bounds__(256)
+enc_add_ln_bwd_kernel(const T* __restrict__ y, const float* __restrict__ res, const float* __restrict__ gamma,
+                      const float* __restrict__ stats, const float* __restrict__ dout, int64_t n_tok,
+                      float* __restrict__ dx_out, T* __restrict__ dy_out, float* __restrict__ part) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float dg[enc::PER], db[enc::PER];
+#pragma unroll
+  for (int k = 0; k < enc::PER; ++k) dg[k] = db[k] = 0.f;
+  for (int64_t t = warp; t < n_tok; t += nwarps) {
+    float x[enc::PER], dy[enc::PER], dx[enc::PER];
+#pragma unroll
+    for (int k = 0; k < enc::PER; ++k) {
+      const int c = lane + 32 * k;
+      x[k] = to_f32(y[t * enc::H + c]) + res[t * enc::H + c];
+      dy[k] = dout[t * enc::H + c];
+    }
+    ln_row_bwd(x, dy, gamma, stats[2 * t], stats[2 * t + 1], lane, dx, dg, db);
+#pragma unroll
+    for (int k = 0; k < enc::PER; ++k) {
+      const int c = lane + 32 * k;
+      dx_out[t * enc::H + c] = dx[k];                 // gradient of the residual stream (fp32)
+      dy_out[t * enc::H + c] = from_f32<T>(dx[k]);    // gradient of the linear layer's output (its dtype)
+    }
+  }
+  ln_param_partials(dg, db, part);
+}
+
+// ---- exact GELU (BertIntermediate, hidden_act = "gelu") ----------------------------------------------------
+template <typename T>
+__global__ void enc_gelu_fwd_kernel(const T* __restrict__ x, int64_t n, T* __restrict__ y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = to_f32(x[i]);
+    y[i] = from_f32<T>(0.5f * v * (1.0f + erff(v * 0.70710678118654752f)));
+  }
+}
+template <typename T>
+__global__ void enc_gelu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, int64_t n,
+                                    T* __restrict__ dx) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = to_f32(x[i]);
+    const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * v * v);
+    dx[i] = from_f32<T>(to_f32(dy[i]) * (cdf + v * pdf));
+  }
+}
+
+// ---- causal multi-head self-attention, head_dim 32 ---------------------------------------------------------
+// qkv: (B, L, 3 * H) rows = [Q | K | V], each H = n_heads * 32; keymask (B, L) bytes (models.py:343).  One
+// block per (sequence, head): K and V of the head live in shared memory (rows padded to 33 floats: lane j
+// reads row j), a warp owns one query at a time: lane = key for the scores, lane = dim for the output.
+// Query i attends keys j <= i with keymask[j] (BertModel is_decoder=True: causal mask AND padding mask);
+// scores are scaled by 1/sqrt(32).  lse (B, n_heads, L): log-sum-exp of every query row, for the backward.
+template <typename T>
+__global__ void __launch_bounds__(256)
+enc_attn_fwd_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ keymask, int seq_len, int n_heads,
+                    T* __restrict__ ctx, float* __restrict__ lse) {
+  extern __shared__ float sm[];
+  float* sK = sm;                                   // [L][33]
+  float* sV = sm + (size_t)seq_len * 33;            // [L][33]
+  __shared__ uint8_t s_mask[enc::MAX_L];
+  const int b = blockIdx.x / n_heads, h = blockIdx.x % n_heads;
+  const int hid = n_heads * enc::HD;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const T* base = qkv + (int64_t)b * seq_len * 3 * hid;
+  for (int e = threadIdx.x; e < seq_len * enc::HD; e += blockDim.x) {
+    const int j = e >> 5, d = e & 31;
+    sK[j * 33 + d] = to_f32(base[(int64_t)j * 3 * hid + hid + h * enc::HD + d]);
+    sV[j * 33 + d] = to_f32(base[(int64_t)j * 3 * hid + 2 * hid + h * enc::HD + d]);
+  }
+  for (int j = threadIdx.x; j < seq_len; j += blockDim.x) s_mask[j] = keymask[(int64_t)b * seq_len + j];
+  __syncthreads();
+  const float scale = 0.17677669529663687f;   // 1 / sqrt(32)
+  for (int i = warp; i < seq_len; i += nw) {
+    const float qd = to_f32(base[(int64_t)i * 3 * hid + h * enc::HD + lane]) * scale;   // lane = dim
+    float m = -CUDART_INF_F, l = 0.f, o = 0.f;                                          // o: lane = dim
+    for (int j0 = 0; j0 <= i; j0 += 32) {
+      const int j = j0 + lane;
+      const bool ok = j <= i && s_mask[j < seq_len ? j : 0];
+      float s = 0.f;
+      const float* kr = sK + (size_t)(j < seq_len ? j : 0) * 33;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) s = fmaf(__shfl_sync(0xffffffffu, qd, d), kr[d], s);
+      s = ok ? s : -CUDART_INF_F;
+      const float mnew = fmaxf(m, warp_max(s));
+      if (mnew == -CUDART_INF_F) continue;          // no valid key so far
+      const float p = ok ? __expf(s - mnew) : 0.f;
+      const float corr = __expf(m - mnew);          // exp(-inf) = 0 on the first valid chunk
+      l = l * corr + warp_sum(p);
+      o *= corr;
+      const int jn = min(32, i + 1 - j0);
+      for (int jj = 0; jj < jn; ++jj) o = fmaf(__shfl_sync(0xffffffffu, p, jj), sV[(size_t)(j0 + jj) * 33 + lane], o);
+      m = mnew;
+    }
+    const int64_t t = (int64_t)b * seq_len + i;
+    ctx[t * hid + h * enc::HD + lane] = from_f32<T>(l > 0.f ? o / l : 0.f);
+    if (lane == 0) lse[((int64_t)b * n_heads + h) * seq_len + i] = l > 0.f ? m + __logf(l) : CUDART_INF_F;
+  }
+}
+
+// backward, pass A (warp per query): delta_i = dO_i . O_i, dQ_i = scale * sum_j dS_ij K_j with
+// dS_ij = P_ij (dO_i . V_j - delta_i), P_ij = exp(scale q_i . k_j - lse_i)
+// pass B (warp per key): dK_j = scale * sum_i dS_ij Q_i, dV_j = sum_i P_ij dO_i.  Both recompute P; no atomics.
+template <typename T>
+__global__ void __launch_bounds__(256)
+enc_attn_bwd_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ keymask, const T* __restrict__ ctx,
+                    const T* __restrict__ dctx, const float* __restrict__ lse, int seq_len, int n_heads,
+                    T* __restrict__ dqkv) {
+  extern __shared__ float sm[];
+  float* sQ = sm;                                   // [L][33] scaled queries
+  float* sK = sQ + (size_t)seq_len * 33;
+  float* sV = sK + (size_t)seq_len * 33;
+  float* sdO = sV + (size_t)seq_len * 33;
+  float* s_lse = sdO + (size_t)seq_len * 33;        // [L]
+  float* s_delta = s_lse + seq_len;                 // [L]
+  __shared__ uint8_t s_mask[enc::MAX_L];
+  const int b = blockIdx.x / n_heads, h = blockIdx.x % n_heads;
+  const int hid = n_heads * enc::HD;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float scale = 0.17677669529663687f;
+  const T* base = qkv + (int64_t)b * seq_len * 3 * hid;
+  T* dbase = dqkv + (int64_t)b * seq_len * 3 * hid;
+  for (int e = threadIdx.x; e < seq_len * enc::HD; e += blockDim.x) {
+    const int j = e >> 5, d = e & 31;
+    const int64_t t = (int64_t)b * seq_len + j;
+    sQ[j * 33 + d] = to_f32(base[(int64_t)j * 3 * hid + h * enc::HD + d]) * scale;
+    sK[j * 33 + d] = to_f32(base[(int64_t)j * 3 * hid + hid + h * enc::HD + d]);
+    sV[j * 33 + d] = to_f32(base[(int64_t)j * 3 * hid + 2 * hid + h * enc::HD + d]);
+    sdO[j * 33 + d] = to_f32(dctx[t * hid + h * enc::HD + d]);
+  }
+  for (int j = threadIdx.x; j < seq_len; j += blockDim.x) {
+    s_mask[j] = keymask[(int64_t)b * seq_len + j];
+    s_lse[j] = lse[((int64_t)b * n_heads + h) * seq_len + j];
+  }
+  __syncthreads();
+  // delta_i = dO_i . O_i  (warp per query, lane = dim)
+  for (int i = warp; i < seq_len; i += nw) {
+    const int64_t t = (int64_t)b * seq_len + i;
+    const float v = sdO[i * 33 + lane] * to_f32(ctx[t * hid + h * enc::HD + lane]);
+    const float d = warp_sum(v);
+    if (lane == 0) s_delta[i] = d;
+  }
+  __syncthreads();
+  // pass A: dQ
+  for (int i = warp; i < seq_len; i += nw) {
+    const float lse_i = s_lse[i], delta_i = s_delta[i];
+    float dq = 0.f;                                                   // lane = dim
+    if (lse_i != CUDART_INF_F) {
+      for (int j0 = 0; j0 <= i; j0 += 32) {
+        const int j = j0 + lane;
+        const int jc = j < seq_len ? j : 0;
+        const bool ok = j <= i && s_mask[jc];
+        float s = 0.f, dp = 0.f;
+#pragma unroll
+        for (int d = 0; d < 32; ++d) {
+          s = fmaf(sQ[i * 33 + d], sK[jc * 33 + d], s);
+          dp = fmaf(sdO[i * 33 + d], sV[jc * 33 + d], dp);
+        }
+        const float ds = ok ? __expf(s - lse_i) * (dp - delta_i) : 0.f;   // lane = key
+        const int jn = min(32, i + 1 - j0);
+        for (int jj = 0; jj < jn; ++jj) dq = fmaf(__shfl_sync(0xffffffffu, ds, jj), sK[(size_t)(j0 + jj) * 33 + lane], dq);
+      }
+    }
+    dbase[(int64_t)i * 3 * hid + h * enc::HD + lane] = from_f32<T>(dq * scale);
+  }
+  // pass B: dK, dV (warp per key j; queries i >= j in chunks of 32, lane = query)
+  for (int j = warp; j < seq_len; j += nw) {
+    float dk = 0.f, dv = 0.f;                                         // lane = dim
+    if (s_mask[j]) {
+      for (int i0 = j; i0 < seq_len; i0 += 32) {
+        const int i = i0 + lane;
+        const int ic = i < seq_len ? i : 0;
+        const bool ok = i < seq_len && s_lse[ic] != CUDART_INF_F;
+        float s = 0.f, dp = 0.f;
+#pragma unroll
+        for (int d = 0; d < 32; ++d) {
+          s = fmaf(sQ[ic * 33 + d], sK[j * 33 + d], s);
+          dp = fmaf(sdO[ic * 33 + d], sV[j * 33 + d], dp);
+        }
+        const float p = ok ? __expf(s - s_lse[ic]) : 0.f;             // lane = query
+        const float ds = p * (dp - s_delta[ic]);
+        const int in = min(32, seq_len - i0);
+        for (int ii = 0; ii < in; ++ii) {
+          const float pb = __shfl_sync(0xffffffffu, p, ii), dsb = __shfl_sync(0xffffffffu, ds, ii);
+          dv = fmaf(pb, sdO[(size_t)(i0 + ii) * 33 + lane], dv);
+          dk = fmaf(dsb, sQ[(size_t)(i0 + ii) * 33 + lane], dk);      // sQ already carries the 1/sqrt(d) scale
+        }
+      }
+    }
+    dbase[(int64_t)j * 3 * hid + hid + h * enc::HD + lane] = from_f32<T>(dk);
+    dbase[(int64_t)j * 3 * hid + 2 * hid + h * enc::HD + lane] = from_f32<T>(dv);
+  }
+}
+
+static inline int enc_grid(int64_t warps_needed) {
+  int64_t blocks = (warps_needed + 7) / 8;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace xr
+
+using namespace xr;
+
+extern "C" size_t xr_enc_ln_workspace_bytes(int64_t n_tok) {
+  // partial rows of the parameter-gradient reductions + one (n_tok, H) fp32 scratch for the embedding backward
+  return (size_t)LNB_BLOCKS * 2 * enc::H * 4 + (size_t)(n_tok > 0 ? n_tok : 1) * enc::H * 4 + 512;
+}
+
+extern "C" int xr_enc_embed_ln_fwd(const float* table, int64_t n_table_rows, const int64_t* idx,
+                                   const float* pos_emb, const float* type_emb, const float* gamma,
+                                   const float* beta, int64_t batch, int64_t seq_len, int64_t dim, float eps,
+                                   float* out, float* stats, uint8_t* mask, int32_t* err_flag, void* stream) {
+  XR_CHECK_ARG(table && idx && pos_emb && type_emb && gamma && beta && out && stats && mask,
+               "xr_enc_embed_ln_fwd: null pointer");
+  XR_CHECK_ARG(dim == enc::H, "xr_enc_embed_ln_fwd: this build is specialised for hidden size %d", enc::H);
+  XR_CHECK_ARG(batch >= 0 && seq_len >= 1 && n_table_rows > 0, "xr_enc_embed_ln_fwd: bad sizes");
+  const int64_t n_tok = batch * seq_len;
+  if (n_tok == 0) return XR_OK;
+  enc_embed_ln_fwd_kernel<<<enc_grid(n_tok), 256, 0, as_stream(stream)>>>(
+      table, n_table_rows, idx, pos_emb, type_emb, gamma, beta, n_tok, (int)seq_len, eps, out, stats, mask, err_flag);
+  XR_LAUNCH_CHECK("enc_embed_ln_fwd");
+  return XR_OK;
+}
+
+extern "C" int xr_enc_embed_ln_bwd(const float* table, int64_t n_table_rows, const int64_t* idx,
+                                   const float* pos_emb, const float* type_emb, const float* gamma,
+                                   const float* stats, const float* dout, int64_t batch, int64_t seq_len,
+                                   int64_t dim, float* dpos, float* dtype0, float* dgamma, float* dbeta,
+                                   void* workspace, void* stream) {
+  XR_CHECK_ARG(table && idx && pos_emb && type_emb && gamma && stats && dout && dpos && dtype0 && dgamma && dbeta &&
+                   workspace,
+               "xr_enc_embed_ln_bwd: null pointer");
+  XR_CHECK_ARG(dim == enc::H && batch >= 1 && seq_len >= 1, "xr_enc_embed_ln_bwd: bad sizes");
+  cudaStream_t s = as_stream(stream);
+  const int64_t n_tok = batch * seq_len;
+  float* part = (float*)workspace;
+  float* dx = part + (size_t)LNB_BLOCKS * 2 * enc::H;
+  enc_embed_ln_bwd_kernel<<<LNB_BLOCKS, 256, 0, s>>>(table, n_table_rows, idx, pos_emb, type_emb, gamma, stats, dout,
+                                                     n_tok, (int)seq_len, dx, part);
+  XR_LAUNCH_CHECK("enc_embed_ln_bwd");
+  enc_fold_partials_kernel<<<(enc::H + 127) / 128, 128, 0, s>>>(part, LNB_BLOCKS, 2, enc::H, dgamma, dbeta);
+  XR_LAUNCH_CHECK("enc_fold_partials");
+  const int64_t n = seq_len * enc::H;
+  enc_sum_over_batch_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dx, (int)batch, (int)seq_len, dpos);
+  XR_LAUNCH_CHECK("enc_sum_over_batch");
+  enc_sum_rows_kernel<<<(enc::H + 127) / 128, 128, 0, s>>>(dpos, (int)seq_len, dtype0);
+  XR_LAUNCH_CHECK("enc_sum_rows");
+  return XR_OK;
+}
+
+extern "C" int xr_enc_add_ln_fwd(const void* y, int y_dtype, const float* residual, const float* gamma,
+                                 const float* beta, int64_t n_tok, int64_t dim, float eps, float* out,
+                                 float* stats, void* stream) {
+  XR_CHECK_ARG(y && residual && gamma && beta && out && stats, "xr_enc_add_ln_fwd: null pointer");
+  XR_CHECK_ARG(dim == enc::H && n_tok >= 0, "xr_enc_add_ln_fwd: bad sizes");
+  if (n_tok == 0) return XR_OK;
+  cudaStream_t s = as_stream(stream);
+  if (y_dtype == XR_F32)
+    enc_add_ln_fwd_kernel<float><<<enc_grid(n_tok), 256, 0, s>>>((const float*)y, residual, gamma, beta, n_tok, eps, out, stats);
+  else if (y_dtype == XR_BF16)
+    enc_add_ln_fwd_kernel<__nv_bfloat16><<<enc_grid(n_tok), 256, 0, s>>>((const __nv_bfloat16*)y, residual, gamma, beta, n_tok, eps, out, stats);
+  else
+    XR_CHECK_ARG(false, "xr_enc_add_ln_fwd: bad dtype");
+  XR_LAUNCH_CHECK("enc_add_ln_fwd");
+  return XR_OK;
+}
+
+extern "C" int xr_enc_add_ln_bwd(const void* y, int y_dtype, const float* residual, const float* gamma,
+                                 const float* stats, const float* dout, int64_t n_tok, int64_t dim,
+                                 float* dresidual, void* dy, float* dgamma, float* dbeta, void* workspace,
+                                 void* stream) {
+  XR_CHECK_ARG(y && residual && gamma && stats && dout && dresidual && dy && dgamma && dbeta && workspace,
+               "xr_enc_add_ln_bwd: null pointer");
+  XR_CHECK_ARG(dim == enc::H && n_tok >= 1, "xr_enc_add_ln_bwd: bad sizes");
+  cudaStream_t s = as_stream(stream);
+  float* part = (float*)workspace;
+  if (y_dtype == XR_F32)
+    enc_add_ln_bwd_kernel<float><<<LNB_BLOCKS, 256, 0, s>>>((const float*)y, residual, gamma, stats, dout, n_tok,
+                                                            dresidual, (float*)dy, part);
+  else if (y_dtype == XR_BF16)
+    enc_add_ln_bwd_kernel<__nv_bfloat16><<<LNB_BLOCKS, 256, 0, s>>>((const __nv_bfloat16*)y, residual, gamma, stats, dout,
+                                                                    n_tok, dresidual, (__nv_bfloat16*)dy, part);
+  else
+    XR_CHECK_ARG(false, "xr_enc_add_ln_bwd: bad dtype");
+  XR_LAUNCH_CHECK("enc_add_ln_bwd");
+  enc_fold_partials_kernel<<<(enc::H + 127) / 128, 128, 0, s>>>(part, LNB_BLOCKS, 2, enc::H, dgamma, dbeta);
+  XR_LAUNCH_CHECK("enc_fold_partials");
+  return XR_OK;
+}
+
+extern "C" int xr_enc_gelu(const void* x, const void* dy, int64_t n, int dtype, void* out, void* stream) {
+  XR_CHECK_ARG(x && out && n >= 0, "xr_enc_gelu: bad arguments");
+  if (n == 0) return XR_OK;
+  cudaStream_t s = as_stream(stream);
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (dtype == XR_F32) {
+    if (dy) enc_gelu_bwd_kernel<float><<<(unsigned)blocks, 256, 0, s>>>((const float*)x, (const float*)dy, n, (float*)out);
+    else enc_gelu_fwd_kernel<float><<<(unsigned)blocks, 256, 0, s>>>((const float*)x, n, (float*)out);
+  } else if (dtype == XR_BF16) {
+    if (dy) enc_gelu_bwd_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, n, (__nv_bfloat16*)out);
+    else enc_gelu_fwd_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>((const __nv_bfloat16*)x, n, (__nv_bfloat16*)out);
+  } else {
+    XR_CHECK_ARG(false, "xr_enc_gelu: bad dtype");
+  }
+  XR_LAUNCH_CHECK("enc_gelu");
+  return XR_OK;
+}
+
+template <typename T>
+static int enc_attention_launch(const void* qkv, const uint8_t* keymask, const void* ctx, const void* dctx,
+                                float* lse, int64_t batch, int seq_len, int n_heads, void* out, cudaStream_t s) {
+  const unsigned grid = (unsigned)(batch * n_heads);
+  if (!dctx) {
+    const size_t smem = (size_t)seq_len * 33 * 2 * 4;
+    static size_t conf = 0;
+    if (smem > 48 * 1024 && smem > conf) {
+      XR_CUDA(cudaFuncSetAttribute(enc_attn_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(enc::MAX_L * 33 * 2 * 4)));
+      conf = enc::MAX_L * 33 * 2 * 4;
+    }
+    enc_attn_fwd_kernel<T><<<grid, 256, smem, s>>>((const T*)qkv, keymask, seq_len, n_heads, (T*)out, lse);
+    XR_LAUNCH_CHECK("enc_attn_fwd");
+  } else {
+    const size_t smem = ((size_t)seq_len * 33 * 4 + 2 * (size_t)seq_len) * 4;
+    static size_t conf = 0;
+    if (smem > 48 * 1024 && smem > conf) {
+      XR_CUDA(cudaFuncSetAttribute(enc_attn_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)((enc::MAX_L * 33 * 4 + 2 * enc::MAX_L) * 4)));
+      conf = (enc::MAX_L * 33 * 4 + 2 * enc::MAX_L) * 4;
+    }
+    enc_attn_bwd_kernel<T><<<grid, 256, smem, s>>>((const T*)qkv, keymask, (const T*)ctx, (const T*)dctx, lse, seq_len,
+                                                   n_heads, (T*)out);
+    XR_LAUNCH_CHECK("enc_attn_bwd");
+  }
+  return XR_OK;
+}
+
+extern "C" int xr_enc_attention(const void* qkv, const uint8_t* keymask, const void* ctx, const void* dctx,
+                                float* lse, int64_t batch, int64_t seq_len, int64_t n_heads, int64_t head_dim,
+                                int dtype, void* out, void* stream) {
+  XR_CHECK_ARG(qkv && keymask && lse && out, "xr_enc_attention: null pointer");
+  XR_CHECK_ARG(head_dim == enc::HD, "xr_enc_attention: this build is specialised for head_dim = %d", enc::HD);
+  XR_CHECK_ARG(batch >= 0 && seq_len >= 1 && seq_len <= enc::MAX_L && n_heads >= 1,
+               "xr_enc_attention: needs 1 <= seq_len <= %d", enc::MAX_L);
+  XR_CHECK_ARG(!dctx || ctx, "xr_enc_attention: the backward needs ctx");
+  if (batch == 0) return XR_OK;
+  cudaStream_t s = as_stream(stream);
+  if (dtype == XR_F32)
+    return enc_attention_launch<float>(qkv, keymask, ctx, dctx, lse, batch, (int)seq_len, (int)n_heads, out, s);
+  if (dtype == XR_BF16)
+    return enc_attention_launch<__nv_bfloat16>(qkv, keymask, ctx, dctx, lse, batch, (int)seq_len, (int)n_heads, out, s);
+  XR_CHECK_ARG(false, "xr_enc_attention: bad dtype");
+  return XR_E_INVALID;
+}

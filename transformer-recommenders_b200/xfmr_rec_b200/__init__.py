@@ -9,12 +9,13 @@ yxtay/transformer-recommenders behind the reference's own Python interfaces.
     dist     catalog sharding + NCCL all-gather merge, data-parallel loss reduction
     step     the whole scoring-and-loss train step as one sync-free, CUDA-graph-replayed call
     data     SeqBatch construction on the device (SeqDataset sampling + collate, data.py:669-805)
+    encoder  the sequence encoder (BertModel(is_decoder=True) on item embeddings), forward + backward
     service  request / response types of xfmr_rec/service.py and the ItemIndex service surface
     ops      tensor-level wrappers over the C ABI (include/xfmr_b200.h)
 """
 
 from . import _native, ops  # noqa: F401
-from . import data, dist, evaluate, index, losses, metrics, models, params, service, step  # noqa: F401
+from . import data, dist, encoder, evaluate, index, losses, metrics, models, params, service, step  # noqa: F401
 from .losses import (  # noqa: F401
     LOSS_CLASSES,
     AlignmentContrastiveLoss,

@@ -1,0 +1,332 @@
+"""Sequence encoder: the reference's ``BertModel(is_decoder=True)`` on ``inputs_embeds``
+from the frozen item table (xfmr_rec/models.py:51-102, 306-345), forward and backward.
+
+Same parameter names and shapes as the HuggingFace module the reference builds (``embeddings.*``,
+``encoder.layer.N.attention.self.query.weight`` ...), so a ``BertModel.state_dict()`` — e.g. the
+``auto_model`` inside the SentenceTransformer the reference saves (models.py:258-266) — loads with
+``load_state_dict`` and vice versa.  ``forward`` returns what the reference's ``RecommenderModel.forward``
+returns: ``token_embeddings`` (B, L, H), ``sentence_embedding`` (pooled) and the ``attention_mask``.
+
+What runs where: everything around the linear layers is a hand-written CUDA kernel in
+``csrc/encoder.cu`` — the history gather fused with the position / token-type embeddings and the first
+LayerNorm, causal multi-head attention (forward and a deterministic backward), exact GELU, and
+``LayerNorm(dense_out + residual)`` forward / backward.  The linear layers are plain GEMMs and go through
+cuBLAS (``torch.nn.functional.linear``).  ``compute_dtype=torch.bfloat16`` reproduces Lightning's
+``bf16-mixed`` policy: bf16 GEMMs / attention / GELU, fp32 residual stream, LayerNorm and softmax.
+
+Not implemented: dropout (HF default 0.1 in training mode) — the module behaves as ``BertModel.eval()``
+does and as training with ``hidden_dropout_prob = attention_probs_dropout_prob = 0``.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Literal
+
+import pydantic
+import torch
+import torch.nn.functional as F
+
+from . import _native as N
+from . import ops
+
+
+class EncoderConfig(pydantic.BaseModel):
+    """The ``ModelConfig`` fields that shape the encoder (models.py:22-48); ``hidden_size`` is the item
+    embedding width (384 for all-MiniLM-L6-v2, params.py:11)."""
+
+    hidden_size: int = 384
+    num_hidden_layers: int = 1
+    num_attention_heads: int = 12
+    intermediate_size: int = 48
+    max_seq_length: int = 32
+    layer_norm_eps: float = 1e-12
+    pooling_mode: Literal["mean", "max", "cls", "lasttoken"] = "mean"
+    is_normalized: bool = False
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+class _EmbedLN(torch.autograd.Function):
+    """x0 = LayerNorm(table[idx] + position_emb[l] + token_type_emb[0]); mask = any(table[idx] != 0)."""
+
+    @staticmethod
+    def forward(ctx, table, idx, pos_w, type_w, ln_w, ln_b, eps):
+        dev = ops._require_cuda(table, idx, pos_w, type_w, ln_w, ln_b)
+        b, l = idx.shape
+        h = table.size(1)
+        assert table.dtype == torch.float32 and l <= pos_w.size(0)
+        table, idx = table.contiguous(), idx.contiguous()
+        out = torch.empty((b, l, h), dtype=torch.float32, device=dev)
+        stats = torch.empty((b * l, 2), dtype=torch.float32, device=dev)
+        mask = torch.empty((b, l), dtype=torch.uint8, device=dev)
+        with ops._on(dev):
+            N.call("xr_enc_embed_ln_fwd", ops._p(table), table.size(0), ops._p(idx), ops._p(pos_w), ops._p(type_w),
+                   ops._p(ln_w), ops._p(ln_b), b, l, h, float(eps), ops._p(out), ops._p(stats), ops._p(mask), None,
+                   ops._stream())
+        ctx.save_for_backward(table, idx, pos_w, type_w, ln_w, stats)
+        ctx.mark_non_differentiable(mask)
+        return out, mask
+
+    @staticmethod
+    def backward(ctx, dout, _dmask):
+        table, idx, pos_w, type_w, ln_w, stats = ctx.saved_tensors
+        dev = dout.device
+        b, l = idx.shape
+        h = table.size(1)
+        dout = dout.contiguous().float()
+        dpos = torch.zeros_like(pos_w)
+        dtype = torch.zeros_like(type_w)
+        dg, db = torch.empty_like(ln_w), torch.empty_like(ln_w)
+        ws = _ws(N.lib().xr_enc_ln_workspace_bytes(b * l), dev)
+        dpos_l = torch.empty((l, h), dtype=torch.float32, device=dev)
+        dt0 = torch.empty(h, dtype=torch.float32, device=dev)
+        with ops._on(dev):
+            N.call("xr_enc_embed_ln_bwd", ops._p(table), table.size(0), ops._p(idx), ops._p(pos_w), ops._p(type_w),
+                   ops._p(ln_w), ops._p(stats), ops._p(dout), b, l, h, ops._p(dpos_l), ops._p(dt0), ops._p(dg),
+                   ops._p(db), ops._p(ws), ops._stream())
+        dpos[:l] = dpos_l
+        dtype[0] = dt0
+        return None, None, dpos, dtype, dg, db, None
+
+
+class _AddLN(torch.autograd.Function):
+    """LayerNorm(y + residual): BertSelfOutput / BertOutput (dropout p = 0)."""
+
+    @staticmethod
+    def forward(ctx, y, residual, ln_w, ln_b, eps):
+        dev = ops._require_cuda(y, residual, ln_w, ln_b)
+        y, residual = y.contiguous(), residual.contiguous()
+        assert residual.dtype == torch.float32
+        n_tok, h = y.numel() // y.size(-1), y.size(-1)
+        out = torch.empty(residual.shape, dtype=torch.float32, device=dev)
+        stats = torch.empty((n_tok, 2), dtype=torch.float32, device=dev)
+        with ops._on(dev):
+            N.call("xr_enc_add_ln_fwd", ops._p(y), ops._dt(y), ops._p(residual), ops._p(ln_w), ops._p(ln_b), n_tok, h,
+                   float(eps), ops._p(out), ops._p(stats), ops._stream())
+        ctx.save_for_backward(y, residual, ln_w, stats)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, residual, ln_w, stats = ctx.saved_tensors
+        dev = dout.device
+        n_tok, h = y.numel() // y.size(-1), y.size(-1)
+        dout = dout.contiguous().float()
+        dres = torch.empty_like(residual)
+        dy = torch.empty_like(y)
+        dg, db = torch.empty_like(ln_w), torch.empty_like(ln_w)
+        ws = _ws(N.lib().xr_enc_ln_workspace_bytes(1), dev)
+        with ops._on(dev):
+            N.call("xr_enc_add_ln_bwd", ops._p(y), ops._dt(y), ops._p(residual), ops._p(ln_w), ops._p(stats),
+                   ops._p(dout), n_tok, h, ops._p(dres), ops._p(dy), ops._p(dg), ops._p(db), ops._p(ws), ops._stream())
+        return dy, dres, dg, db, None
+
+
+class _Gelu(torch.autograd.Function):
+    """Exact (erf) GELU, hidden_act = "gelu"."""
+
+    @staticmethod
+    def forward(ctx, x):
+        dev = ops._require_cuda(x)
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        with ops._on(dev):
+            N.call("xr_enc_gelu", ops._p(x), None, x.numel(), ops._dt(x), ops._p(out), ops._stream())
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = dy.contiguous().to(x.dtype)
+        dx = torch.empty_like(x)
+        with ops._on(x.device):
+            N.call("xr_enc_gelu", ops._p(x), ops._p(dy), x.numel(), ops._dt(x), ops._p(dx), ops._stream())
+        return dx
+
+
+class _Attention(torch.autograd.Function):
+    """Causal + key-padding multi-head self-attention on packed qkv (B, L, 3H), head_dim 32."""
+
+    @staticmethod
+    def forward(ctx, qkv, mask, n_heads):
+        dev = ops._require_cuda(qkv, mask)
+        qkv, mask = qkv.contiguous(), mask.contiguous()
+        b, l, h3 = qkv.shape
+        hid = h3 // 3
+        out = torch.empty((b, l, hid), dtype=qkv.dtype, device=dev)
+        lse = torch.empty((b, n_heads, l), dtype=torch.float32, device=dev)
+        with ops._on(dev):
+            N.call("xr_enc_attention", ops._p(qkv), ops._p(mask), None, None, ops._p(lse), b, l, n_heads,
+                   hid // n_heads, ops._dt(qkv), ops._p(out), ops._stream())
+        ctx.save_for_backward(qkv, mask, out, lse)
+        ctx.n_heads = n_heads
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, mask, out, lse = ctx.saved_tensors
+        b, l, h3 = qkv.shape
+        hid = h3 // 3
+        dout = dout.contiguous().to(qkv.dtype)
+        dqkv = torch.empty_like(qkv)
+        with ops._on(qkv.device):
+            N.call("xr_enc_attention", ops._p(qkv), ops._p(mask), ops._p(out), ops._p(dout), ops._p(lse), b, l,
+                   ctx.n_heads, hid // ctx.n_heads, ops._dt(qkv), ops._p(dqkv), ops._stream())
+        return dqkv, None, None
+
+
+# ---- module tree with HuggingFace BertModel's parameter names -------------------------------------------
+class _Embeddings(torch.nn.Module):
+    def __init__(self, cfg: EncoderConfig):
+        super().__init__()
+        self.word_embeddings = torch.nn.Embedding(1, cfg.hidden_size)          # vocab_size = 1 (models.py:39): unused
+        self.position_embeddings = torch.nn.Embedding(cfg.max_seq_length, cfg.hidden_size)
+        self.token_type_embeddings = torch.nn.Embedding(2, cfg.hidden_size)
+        self.LayerNorm = torch.nn.LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
+
+
+class _SelfAttention(torch.nn.Module):
+    def __init__(self, h: int):
+        super().__init__()
+        self.query, self.key, self.value = (torch.nn.Linear(h, h) for _ in range(3))
+
+
+class _DenseLN(torch.nn.Module):
+    def __init__(self, n_in: int, h: int, eps: float):
+        super().__init__()
+        self.dense = torch.nn.Linear(n_in, h)
+        self.LayerNorm = torch.nn.LayerNorm(h, eps=eps)
+
+
+class _AttentionBlock(torch.nn.Module):
+    def __init__(self, cfg: EncoderConfig):
+        super().__init__()
+        setattr(self, "self", _SelfAttention(cfg.hidden_size))
+        self.output = _DenseLN(cfg.hidden_size, cfg.hidden_size, cfg.layer_norm_eps)
+
+
+class _Intermediate(torch.nn.Module):
+    def __init__(self, cfg: EncoderConfig):
+        super().__init__()
+        self.dense = torch.nn.Linear(cfg.hidden_size, cfg.intermediate_size)
+
+
+class _Layer(torch.nn.Module):
+    def __init__(self, cfg: EncoderConfig):
+        super().__init__()
+        self.attention = _AttentionBlock(cfg)
+        self.intermediate = _Intermediate(cfg)
+        self.output = _DenseLN(cfg.intermediate_size, cfg.hidden_size, cfg.layer_norm_eps)
+
+
+class _Encoder(torch.nn.Module):
+    def __init__(self, cfg: EncoderConfig):
+        super().__init__()
+        self.layer = torch.nn.ModuleList([_Layer(cfg) for _ in range(cfg.num_hidden_layers)])
+
+
+class _Pooler(torch.nn.Module):
+    def __init__(self, h: int):
+        super().__init__()
+        self.dense = torch.nn.Linear(h, h)       # BertPooler: present in the checkpoint, unused by the path
+
+
+class SeqEncoder(torch.nn.Module):
+    """``BertModel(is_decoder=True)`` on item embeddings.  ``forward(item_idx, table)``: ``item_idx`` (B, L)
+    int64 history indices (0 = padding, right-padded as ``pad_sequence`` does, data.py:801), ``table`` the
+    frozen fp32 item table (N+1, H) with a zero row 0 (models.py:247-253)."""
+
+    def __init__(self, config: EncoderConfig | None = None, *, compute_dtype: torch.dtype = torch.float32):
+        super().__init__()
+        self.config = cfg = config or EncoderConfig()
+        assert cfg.hidden_size == 384 and cfg.hidden_size // cfg.num_attention_heads == 32, (
+            "the encoder kernels are specialised for hidden size 384 / head_dim 32")
+        assert compute_dtype in (torch.float32, torch.bfloat16)
+        self.compute_dtype = compute_dtype
+        self.embeddings = _Embeddings(cfg)
+        self.encoder = _Encoder(cfg)
+        self.pooler = _Pooler(cfg.hidden_size)
+        self.apply(self._init_weights)
+
+    @staticmethod
+    def _init_weights(m):       # BertPreTrainedModel._init_weights: normal(0, 0.02), zero biases, unit LayerNorm
+        if isinstance(m, (torch.nn.Linear, torch.nn.Embedding)):
+            m.weight.data.normal_(mean=0.0, std=0.02)
+            if isinstance(m, torch.nn.Linear):
+                m.bias.data.zero_()
+        elif isinstance(m, torch.nn.LayerNorm):
+            m.weight.data.fill_(1.0)
+            m.bias.data.zero_()
+
+    @property
+    def max_seq_length(self) -> int:
+        return self.config.max_seq_length
+
+    def _linear(self, x, lin):
+        cd = self.compute_dtype
+        if cd == torch.float32:
+            return F.linear(x, lin.weight, lin.bias)
+        return F.linear(x.to(cd), lin.weight.to(cd), lin.bias.to(cd))
+
+    def encode_tokens(self, item_idx: torch.Tensor, table: torch.Tensor):
+        """(token_embeddings (B, L, H) fp32, attention_mask (B, L) uint8) for the last ``max_seq_length``
+        positions of ``item_idx`` (models.py:334-337)."""
+        cfg, cd = self.config, self.compute_dtype
+        if not item_idx.is_cuda:
+            raise N.NativeError("SeqEncoder needs CUDA tensors; there is no CPU fallback")
+        idx = item_idx[:, -cfg.max_seq_length:]
+        emb = self.embeddings
+        x, mask = _EmbedLN.apply(table, idx, emb.position_embeddings.weight, emb.token_type_embeddings.weight,
+                                 emb.LayerNorm.weight, emb.LayerNorm.bias, cfg.layer_norm_eps)
+        for layer in self.encoder.layer:
+            att = getattr(layer.attention, "self")
+            w = torch.cat([att.query.weight, att.key.weight, att.value.weight], 0)
+            b = torch.cat([att.query.bias, att.key.bias, att.value.bias], 0)
+            xin = x if cd == torch.float32 else x.to(cd)
+            qkv = F.linear(xin, w.to(cd), b.to(cd))                              # (B, L, 3H)
+            ctx = _Attention.apply(qkv, mask, cfg.num_attention_heads)
+            x = _AddLN.apply(self._linear(ctx, layer.attention.output.dense), x,
+                             layer.attention.output.LayerNorm.weight, layer.attention.output.LayerNorm.bias,
+                             cfg.layer_norm_eps)
+            inter = _Gelu.apply(self._linear(x, layer.intermediate.dense))
+            x = _AddLN.apply(self._linear(inter, layer.output.dense), x, layer.output.LayerNorm.weight,
+                             layer.output.LayerNorm.bias, cfg.layer_norm_eps)
+        return x, mask
+
+    def pool(self, tokens: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+        """sentence_transformers ``Pooling`` (models.py:141-145) + optional ``Normalize``."""
+        m = mask.to(tokens.dtype)[..., None]
+        mode = self.config.pooling_mode
+        if mode == "mean":
+            out = (tokens * m).sum(1) / m.sum(1).clamp(min=1e-9)
+        elif mode == "max":
+            out = tokens.masked_fill(m == 0, -1e9).max(1).values
+        elif mode == "cls":
+            out = tokens[:, 0]
+        else:   # lasttoken: the last position with attention (right padding)
+            last = (mask.long().sum(1) - 1).clamp(min=0)
+            out = tokens[torch.arange(tokens.size(0), device=tokens.device), last]
+        return F.normalize(out, p=2, dim=1) if self.config.is_normalized else out
+
+    def forward(self, item_idx: torch.Tensor, table: torch.Tensor) -> dict[str, torch.Tensor]:
+        tokens, mask = self.encode_tokens(item_idx, table)
+        return {"token_embeddings": tokens, "sentence_embedding": self.pool(tokens, mask),
+                "attention_mask": mask.long()}
+
+
+def encoder_train_step(encoder: SeqEncoder, step, table: torch.Tensor, history_item_idx, pos_item_idx,
+                       neg_item_idx):
+    """One training step of the whole model path (trainer.py:288-300): encoder forward -> the sync-free
+    scoring-and-loss step (:class:`~xfmr_rec_b200.step.PoolLossStep`: gathers, fused contraction + loss,
+    dL/d token_embeddings) -> encoder backward, with the loss step's gradient consumed IN PLACE as the
+    upstream gradient of ``token_embeddings`` (no autograd node for the loss, no extra copy).  Returns the
+    loss (0-dim tensor); parameter gradients are accumulated in ``.grad``."""
+    tokens, _ = encoder.encode_tokens(history_item_idx, table)
+    loss, dtok = step(tokens.detach(), history_item_idx[:, -encoder.max_seq_length:], pos_item_idx, neg_item_idx)
+    tokens.backward(dtok.view_as(tokens).to(tokens.dtype))
+    return loss
