@@ -92,7 +92,9 @@ def test_encoder_fp32_matches_the_reference_bert(golden_dir, tag):
         else:
             continue
         scale = max(np.abs(ref).max(), 1e-6)
-        assert np.abs(got - ref).max() <= 2e-4 * scale, (key, np.abs(got - ref).max(), scale)
+        # (+ 5e-6 absolute: the key-bias gradient is exactly zero in exact arithmetic -- a shift of every key
+        #  leaves the softmax unchanged -- so both sides hold fp32 rounding noise there)
+        assert np.abs(got - ref).max() <= 2e-4 * scale + 5e-6, (key, np.abs(got - ref).max(), scale)
         checked += 1
     assert checked >= 20
     assert enc.pooler.dense.weight.grad is None and enc.embeddings.word_embeddings.weight.grad is None
