@@ -116,7 +116,8 @@ def test_encoder_bf16_mixed_is_close_to_fp32(golden_dir):
     assert np.linalg.norm(got - want) <= 2e-2 * np.linalg.norm(want)
     (tok * torch.from_numpy(z["upstream"]).cuda()).sum().backward()
     for key in z.files:
-        if key.startswith("grad/") and "position" not in key:
+        # (the key-bias gradient is exactly zero in exact arithmetic: nothing to compare but rounding noise)
+        if key.startswith("grad/") and "position" not in key and not key.endswith("self.key.bias"):
             got, ref = dict(enc16.named_parameters())[key[5:]].grad.cpu().numpy(), z[key]
             assert np.linalg.norm(got - ref) <= 5e-2 * np.linalg.norm(ref) + 1e-4, key
 
@@ -161,7 +162,8 @@ def test_encoder_train_step_feeds_the_loss_step_gradient_in_place(golden_dir):
     neg = torch.randint(1, n + 1, (b, l), device="cuda") * valid
     enc = SeqEncoder(EncoderConfig(num_hidden_layers=2, intermediate_size=96, max_seq_length=l)).cuda()
     loss_fn = xr.InfoNCELoss(xr.LossConfig())
-    step = xr.PoolLossStep(emb, loss_fn, b, l, token_dtype=torch.float32)
+    # (fp32 encoder output; logits rounded to bf16 as under bf16-mixed autocast, like the bf16 module path below)
+    step = xr.PoolLossStep(emb, loss_fn, b, l, token_dtype=torch.float32, logits_bf16=True)
     loss = encoder_train_step(enc, step, table, hist, pos, neg)
     got = {k: p.grad.clone() for k, p in enc.named_parameters() if p.grad is not None}
     enc.zero_grad()
@@ -170,6 +172,8 @@ def test_encoder_train_step_feeds_the_loss_step_gradient_in_place(golden_dir):
     l2 = loss_fn(out["query_embed"].bfloat16(), out["candidate_embed"])
     l2.backward()
     assert float(loss) == pytest.approx(float(l2), rel=1e-5)
+    # the module path hands the encoder a bf16-rounded dL/dquery (the loss module returns the query's dtype),
+    # the step an fp32 one: parameter gradients agree to bf16 resolution, norm-wise
     for k, p in enc.named_parameters():
-        if p.grad is not None:
-            assert torch.allclose(got[k], p.grad, rtol=2e-2, atol=1e-4 * float(p.grad.abs().max())), k
+        if p.grad is not None and not k.endswith("self.key.bias"):
+            assert float((got[k] - p.grad).norm()) <= 1e-2 * float(p.grad.norm()) + 1e-6, k
