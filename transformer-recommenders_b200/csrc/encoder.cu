@@ -429,6 +429,311 @@ enc_attn_bwd_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ keyma
   }
 }
 
+// ---- bf16 attention on the tensor cores ----------------------------------------------------------------------
+// Same arithmetic as the kernels above for bf16 activations, with the four contractions of a head
+// (Q K^T, P V; dO V^T, dS K, P^T dO, dS^T Q) issued as warp-level m16n8k16 bf16 MMAs with fp32 accumulators.
+// A head is 32 wide: Q K^T is two k-steps, so a head never fills a 128-row tcgen05 tile worth its TMEM
+// round trip for the softmax; the whole layer is 7.8 GFLOP forward and the kernel is bound by issuing
+// exp / max / pack around the MMAs.  One block per (sequence, head); a warp owns 16 queries (forward, dQ pass)
+// or 16 keys (dK / dV pass).  The probabilities feed the second MMA straight from the accumulator registers
+// (the C fragment of two adjacent n8 tiles IS the A fragment of the next k16 step).  Deterministic: no atomics.
+namespace enc {
+constexpr int RS = 40;   // row stride (bf16) of the row-major [L][32] tiles: 20 words -> the 8 rows x 4 words
+                         // one fragment load touches fall in 32 different banks
+__host__ __device__ constexpr int pad16(int l) { return (l + 15) & ~15; }
+__host__ __device__ constexpr int ts_of(int lp) { return lp + 8; }   // row stride of the transposed [32][L] tiles
+}  // namespace enc
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t lds32(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+
+// A fragment (16 rows x 32 dims = two k-steps) of a row-major tile whose first row is `rows`
+__device__ __forceinline__ void load_a_rows(const __nv_bfloat16* rows, int g, int t, uint32_t (&a)[2][4]) {
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    a[ks][0] = lds32(rows + g * enc::RS + 16 * ks + 2 * t);
+    a[ks][1] = lds32(rows + (g + 8) * enc::RS + 16 * ks + 2 * t);
+    a[ks][2] = lds32(rows + g * enc::RS + 16 * ks + 2 * t + 8);
+    a[ks][3] = lds32(rows + (g + 8) * enc::RS + 16 * ks + 2 * t + 8);
+  }
+}
+// c[nt] (16 x 8) += A (16 x 32) . X[n0 + 8 nt + ..][0..32]^T for nt = 0, 1: X row-major, its rows are the n index
+__device__ __forceinline__ void mma_rows(float (&c)[2][4], const uint32_t (&a)[2][4], const __nv_bfloat16* x, int n0,
+                                         int g, int t) {
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    const __nv_bfloat16* r = x + (n0 + 8 * nt + g) * enc::RS + 2 * t;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) mma16816(c[nt], a[ks], lds32(r + 16 * ks), lds32(r + 16 * ks + 8));
+  }
+}
+// acc[dt] (16 x 8 dims) += A (16 x 16, k = positions k0 .. k0+15) . Xt[8 dt + ..][k0 ..]: Xt is [32][ts] transposed
+__device__ __forceinline__ void mma_cols(float (&acc)[4][4], const uint32_t (&a)[4], const __nv_bfloat16* xt, int ts,
+                                         int k0, int g, int t) {
+#pragma unroll
+  for (int dt = 0; dt < 4; ++dt) {
+    const __nv_bfloat16* r = xt + (8 * dt + g) * ts + k0 + 2 * t;
+    mma16816(acc[dt], a, lds32(r), lds32(r + 8));
+  }
+}
+// tile order of a block's warps: heaviest tiles first, alternating direction so every warp gets a similar sum
+__device__ __forceinline__ int tile_of(int round, int warp, int nw, int n_tiles, bool heavy_last) {
+  const int k = (round & 1) ? round * nw + (nw - 1 - warp) : round * nw + warp;
+  if (k >= n_tiles) return -1;
+  return heavy_last ? n_tiles - 1 - k : k;
+}
+
+// one head's [L][32] slice of a (rows, ld) bf16 matrix -> row-major tile (and, optionally, its transpose); rows
+// L .. lp-1 are zero so that masked probabilities never meet a NaN inside an MMA
+__device__ __forceinline__ void fill_tile(const __nv_bfloat16* __restrict__ src, int64_t ld, int seq_len, int lp,
+                                          __nv_bfloat16* rowmajor, __nv_bfloat16* transposed) {
+  const int ts = enc::ts_of(lp);
+  for (int e = threadIdx.x; e < lp * 4; e += blockDim.x) {
+    const int j = e >> 2, c = e & 3;
+    int4 v = make_int4(0, 0, 0, 0);
+    if (j < seq_len) v = *reinterpret_cast<const int4*>(src + (int64_t)j * ld + 8 * c);
+    if (rowmajor) *reinterpret_cast<int4*>(rowmajor + j * enc::RS + 8 * c) = v;
+    if (transposed) {
+      const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+      for (int d = 0; d < 8; ++d) transposed[(8 * c + d) * ts + j] = h[d];
+    }
+  }
+  if (transposed)
+    for (int e = threadIdx.x; e < 32 * 8; e += blockDim.x) transposed[(e >> 3) * ts + lp + (e & 7)] = __float2bfloat16_rn(0.f);
+}
+
+__global__ void __launch_bounds__(256)
+enc_attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __restrict__ keymask, int seq_len,
+                        int n_heads, __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lp = enc::pad16(seq_len), ts = enc::ts_of(lp);
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);   // [lp][RS]
+  __nv_bfloat16* sK = sQ + lp * enc::RS;                            // [lp][RS]
+  __nv_bfloat16* sVt = sK + lp * enc::RS;                           // [32][ts]
+  uint8_t* s_mask = reinterpret_cast<uint8_t*>(sVt + 32 * ts);      // [lp]
+  const int b = blockIdx.x / n_heads, h = blockIdx.x % n_heads;
+  const int hid = n_heads * enc::HD;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const __nv_bfloat16* base = qkv + (int64_t)b * seq_len * 3 * hid + h * enc::HD;
+  fill_tile(base, 3 * hid, seq_len, lp, sQ, nullptr);
+  fill_tile(base + hid, 3 * hid, seq_len, lp, sK, nullptr);
+  fill_tile(base + 2 * hid, 3 * hid, seq_len, lp, nullptr, sVt);
+  for (int j = threadIdx.x; j < lp; j += blockDim.x) s_mask[j] = j < seq_len ? keymask[(int64_t)b * seq_len + j] : 0;
+  __syncthreads();
+  const float scale = 0.17677669529663687f;   // 1 / sqrt(32)
+  const int n_tiles = lp >> 4;
+  for (int round = 0;; ++round) {
+    const int tile = tile_of(round, warp, nw, n_tiles, true);
+    if (tile < 0) break;
+    const int i0 = tile << 4;
+    uint32_t qa[2][4];
+    load_a_rows(sQ + i0 * enc::RS, g, t, qa);
+    float m[2] = {-CUDART_INF_F, -CUDART_INF_F}, l[2] = {0.f, 0.f};
+    float o[4][4] = {};
+    for (int kb = 0; kb <= i0; kb += 16) {
+      float s[2][4] = {};
+      mma_rows(s, qa, sK, kb, g, t);
+      float mx[2] = {-CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = kb + 8 * nt + 2 * t + (e & 1), qi = i0 + g + 8 * (e >> 1);
+          const bool ok = key <= qi && s_mask[key];
+          s[nt][e] = ok ? s[nt][e] * scale : -CUDART_INF_F;
+          mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
+        }
+      float corr[2], mnew[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        mnew[r] = fmaxf(m[r], mx[r]);
+        corr[r] = mnew[r] == -CUDART_INF_F ? 1.f : __expf(m[r] - mnew[r]);
+        m[r] = mnew[r];
+      }
+      float p[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = e >> 1;
+          p[nt][e] = mnew[r] == -CUDART_INF_F ? 0.f : __expf(s[nt][e] - mnew[r]);
+        }
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+        l[r] = l[r] * corr[r] + p[0][2 * r] + p[0][2 * r + 1] + p[1][2 * r] + p[1][2 * r + 1];
+#pragma unroll
+      for (int dt = 0; dt < 4; ++dt) {
+        o[dt][0] *= corr[0]; o[dt][1] *= corr[0];
+        o[dt][2] *= corr[1]; o[dt][3] *= corr[1];
+      }
+      const uint32_t pa[4] = {pack_bf16x2(p[0][0], p[0][1]), pack_bf16x2(p[0][2], p[0][3]),
+                              pack_bf16x2(p[1][0], p[1][1]), pack_bf16x2(p[1][2], p[1][3])};
+      mma_cols(o, pa, sVt, ts, kb, g, t);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+      const int qi = i0 + g + 8 * r;
+      if (qi >= seq_len) continue;
+      const float inv = l[r] > 0.f ? 1.f / l[r] : 0.f;
+      const int64_t tok = (int64_t)b * seq_len + qi;
+#pragma unroll
+      for (int dt = 0; dt < 4; ++dt)
+        *reinterpret_cast<uint32_t*>(ctx + tok * hid + h * enc::HD + 8 * dt + 2 * t) =
+            pack_bf16x2(o[dt][2 * r] * inv, o[dt][2 * r + 1] * inv);
+      if (t == 0) lse[((int64_t)b * n_heads + h) * seq_len + qi] = l[r] > 0.f ? m[r] + __logf(l[r]) : CUDART_INF_F;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+enc_attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __restrict__ keymask,
+                        const __nv_bfloat16* __restrict__ ctx, const __nv_bfloat16* __restrict__ dctx,
+                        const float* __restrict__ lse, int seq_len, int n_heads, __nv_bfloat16* __restrict__ dqkv) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lp = enc::pad16(seq_len), ts = enc::ts_of(lp);
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+  __nv_bfloat16* sK = sQ + lp * enc::RS;
+  __nv_bfloat16* sV = sK + lp * enc::RS;
+  __nv_bfloat16* sdO = sV + lp * enc::RS;
+  __nv_bfloat16* sQt = sdO + lp * enc::RS;     // [32][ts]
+  __nv_bfloat16* sKt = sQt + 32 * ts;
+  __nv_bfloat16* sdOt = sKt + 32 * ts;
+  float* s_lse = reinterpret_cast<float*>(sdOt + 32 * ts);   // [lp]
+  float* s_delta = s_lse + lp;                               // [lp]
+  uint8_t* s_mask = reinterpret_cast<uint8_t*>(s_delta + lp);
+  const int b = blockIdx.x / n_heads, h = blockIdx.x % n_heads;
+  const int hid = n_heads * enc::HD;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const float scale = 0.17677669529663687f;
+  const __nv_bfloat16* base = qkv + (int64_t)b * seq_len * 3 * hid + h * enc::HD;
+  __nv_bfloat16* dbase = dqkv + (int64_t)b * seq_len * 3 * hid + h * enc::HD;
+  const __nv_bfloat16* dO = dctx + (int64_t)b * seq_len * hid + h * enc::HD;
+  const __nv_bfloat16* O = ctx + (int64_t)b * seq_len * hid + h * enc::HD;
+  fill_tile(base, 3 * hid, seq_len, lp, sQ, sQt);
+  fill_tile(base + hid, 3 * hid, seq_len, lp, sK, sKt);
+  fill_tile(base + 2 * hid, 3 * hid, seq_len, lp, sV, nullptr);
+  fill_tile(dO, hid, seq_len, lp, sdO, sdOt);
+  for (int j = threadIdx.x; j < lp; j += blockDim.x) {
+    s_mask[j] = j < seq_len ? keymask[(int64_t)b * seq_len + j] : 0;
+    s_lse[j] = j < seq_len ? lse[((int64_t)b * n_heads + h) * seq_len + j] : CUDART_INF_F;
+  }
+  // delta_i = dO_i . O_i (warp per query, lane = dim)
+  for (int i = warp; i < lp; i += nw) {
+    float v = 0.f;
+    if (i < seq_len) v = __bfloat162float(dO[(int64_t)i * hid + lane]) * __bfloat162float(O[(int64_t)i * hid + lane]);
+    v = warp_sum(v);
+    if (lane == 0) s_delta[i] = v;
+  }
+  __syncthreads();
+  const int n_tiles = lp >> 4;
+  // pass A: dQ of 16 queries per warp
+  for (int round = 0;; ++round) {
+    const int tile = tile_of(round, warp, nw, n_tiles, true);
+    if (tile < 0) break;
+    const int i0 = tile << 4;
+    uint32_t qa[2][4], doa[2][4];
+    load_a_rows(sQ + i0 * enc::RS, g, t, qa);
+    load_a_rows(sdO + i0 * enc::RS, g, t, doa);
+    const float lse_r[2] = {s_lse[i0 + g], s_lse[i0 + g + 8]}, delta_r[2] = {s_delta[i0 + g], s_delta[i0 + g + 8]};
+    float dq[4][4] = {};
+    for (int kb = 0; kb <= i0; kb += 16) {
+      float s[2][4] = {}, dp[2][4] = {};
+      mma_rows(s, qa, sK, kb, g, t);
+      mma_rows(dp, doa, sV, kb, g, t);
+      float ds[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = e >> 1;
+          const int key = kb + 8 * nt + 2 * t + (e & 1), qi = i0 + g + 8 * r;
+          const bool ok = key <= qi && s_mask[key] && lse_r[r] != CUDART_INF_F;
+          ds[nt][e] = ok ? __expf(s[nt][e] * scale - lse_r[r]) * (dp[nt][e] - delta_r[r]) : 0.f;
+        }
+      const uint32_t dsa[4] = {pack_bf16x2(ds[0][0], ds[0][1]), pack_bf16x2(ds[0][2], ds[0][3]),
+                               pack_bf16x2(ds[1][0], ds[1][1]), pack_bf16x2(ds[1][2], ds[1][3])};
+      mma_cols(dq, dsa, sKt, ts, kb, g, t);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int qi = i0 + g + 8 * r;
+      if (qi >= seq_len) continue;
+#pragma unroll
+      for (int dt = 0; dt < 4; ++dt)
+        *reinterpret_cast<uint32_t*>(dbase + (int64_t)qi * 3 * hid + 8 * dt + 2 * t) =
+            pack_bf16x2(dq[dt][2 * r] * scale, dq[dt][2 * r + 1] * scale);
+    }
+  }
+  // pass B: dK, dV of 16 keys per warp (transposed problem: rows = keys, columns = queries)
+  for (int round = 0;; ++round) {
+    const int tile = tile_of(round, warp, nw, n_tiles, false);
+    if (tile < 0) break;
+    const int j0 = tile << 4;
+    uint32_t ka[2][4], va[2][4];
+    load_a_rows(sK + j0 * enc::RS, g, t, ka);
+    load_a_rows(sV + j0 * enc::RS, g, t, va);
+    const bool key_ok[2] = {s_mask[j0 + g] != 0, s_mask[j0 + g + 8] != 0};
+    float dk[4][4] = {}, dv[4][4] = {};
+    for (int qb = j0; qb < lp; qb += 16) {
+      float st[2][4] = {}, dpt[2][4] = {};
+      mma_rows(st, ka, sQ, qb, g, t);
+      mma_rows(dpt, va, sdO, qb, g, t);
+      float p[2][4], ds[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = e >> 1;
+          const int qi = qb + 8 * nt + 2 * t + (e & 1), key = j0 + g + 8 * r;
+          const float lq = s_lse[qi];
+          const bool ok = key <= qi && key_ok[r] && lq != CUDART_INF_F;
+          p[nt][e] = ok ? __expf(st[nt][e] * scale - lq) : 0.f;
+          ds[nt][e] = p[nt][e] * (dpt[nt][e] - s_delta[qi]);
+        }
+      const uint32_t pa[4] = {pack_bf16x2(p[0][0], p[0][1]), pack_bf16x2(p[0][2], p[0][3]),
+                              pack_bf16x2(p[1][0], p[1][1]), pack_bf16x2(p[1][2], p[1][3])};
+      const uint32_t dsa[4] = {pack_bf16x2(ds[0][0], ds[0][1]), pack_bf16x2(ds[0][2], ds[0][3]),
+                               pack_bf16x2(ds[1][0], ds[1][1]), pack_bf16x2(ds[1][2], ds[1][3])};
+      mma_cols(dv, pa, sdOt, ts, qb, g, t);
+      mma_cols(dk, dsa, sQt, ts, qb, g, t);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int key = j0 + g + 8 * r;
+      if (key >= seq_len) continue;
+#pragma unroll
+      for (int dt = 0; dt < 4; ++dt) {
+        *reinterpret_cast<uint32_t*>(dbase + (int64_t)key * 3 * hid + hid + 8 * dt + 2 * t) =
+            pack_bf16x2(dk[dt][2 * r] * scale, dk[dt][2 * r + 1] * scale);
+        *reinterpret_cast<uint32_t*>(dbase + (int64_t)key * 3 * hid + 2 * hid + 8 * dt + 2 * t) =
+            pack_bf16x2(dv[dt][2 * r], dv[dt][2 * r + 1]);
+      }
+    }
+  }
+}
+
+static size_t attn_mma_smem(int seq_len, bool bwd) {
+  const size_t lp = enc::pad16(seq_len), ts = enc::ts_of((int)lp);
+  if (!bwd) return (2 * lp * enc::RS + 32 * ts) * 2 + lp;
+  return (4 * lp * enc::RS + 3 * 32 * ts) * 2 + 2 * lp * 4 + lp;
+}
+
 static inline int enc_grid(int64_t warps_needed) {
   int64_t blocks = (warps_needed + 7) / 8;
   const int64_t cap = (int64_t)sm_count() * 8;
@@ -547,6 +852,30 @@ extern "C" int xr_enc_gelu(const void* x, const void* dy, int64_t n, int dtype, 
   return XR_OK;
 }
 
+static int enc_attention_launch_mma(const void* qkv, const uint8_t* keymask, const void* ctx, const void* dctx,
+                                    float* lse, int64_t batch, int seq_len, int n_heads, void* out, cudaStream_t s) {
+  using bf = __nv_bfloat16;
+  const unsigned grid = (unsigned)(batch * n_heads);
+  static bool configured = false;
+  if (!configured) {
+    XR_CUDA(cudaFuncSetAttribute(enc_attn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)attn_mma_smem(enc::MAX_L, false)));
+    XR_CUDA(cudaFuncSetAttribute(enc_attn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)attn_mma_smem(enc::MAX_L, true)));
+    configured = true;
+  }
+  if (!dctx) {
+    enc_attn_fwd_mma_kernel<<<grid, 256, attn_mma_smem(seq_len, false), s>>>((const bf*)qkv, keymask, seq_len, n_heads,
+                                                                            (bf*)out, lse);
+    XR_LAUNCH_CHECK("enc_attn_fwd_mma");
+  } else {
+    enc_attn_bwd_mma_kernel<<<grid, 256, attn_mma_smem(seq_len, true), s>>>(
+        (const bf*)qkv, keymask, (const bf*)ctx, (const bf*)dctx, lse, seq_len, n_heads, (bf*)out);
+    XR_LAUNCH_CHECK("enc_attn_bwd_mma");
+  }
+  return XR_OK;
+}
+
 template <typename T>
 static int enc_attention_launch(const void* qkv, const uint8_t* keymask, const void* ctx, const void* dctx,
                                 float* lse, int64_t batch, int seq_len, int n_heads, void* out, cudaStream_t s) {
@@ -587,8 +916,12 @@ extern "C" int xr_enc_attention(const void* qkv, const uint8_t* keymask, const v
   cudaStream_t s = as_stream(stream);
   if (dtype == XR_F32)
     return enc_attention_launch<float>(qkv, keymask, ctx, dctx, lse, batch, (int)seq_len, (int)n_heads, out, s);
-  if (dtype == XR_BF16)
-    return enc_attention_launch<__nv_bfloat16>(qkv, keymask, ctx, dctx, lse, batch, (int)seq_len, (int)n_heads, out, s);
+  if (dtype == XR_BF16) {
+    // the tensor-core kernels read 16-byte row segments: every head slice starts 64 B into a 16 B-aligned row
+    XR_CHECK_ARG(((uintptr_t)qkv | (uintptr_t)out | (uintptr_t)ctx | (uintptr_t)dctx) % 16 == 0,
+                 "xr_enc_attention: bf16 buffers must be 16-byte aligned");
+    return enc_attention_launch_mma(qkv, keymask, ctx, dctx, lse, batch, (int)seq_len, (int)n_heads, out, s);
+  }
   XR_CHECK_ARG(false, "xr_enc_attention: bad dtype");
   return XR_E_INVALID;
 }
