@@ -450,21 +450,31 @@ int xr_retrieval_metrics(const int64_t* rec, int64_t u, int64_t k, const int64_t
 size_t xr_enc_ln_workspace_bytes(int64_t n_tok);
 int xr_enc_embed_ln_fwd(const float* table, int64_t n_table_rows, const int64_t* idx, const float* pos_emb,
                         const float* type_emb, const float* gamma, const float* beta, int64_t batch,
-                        int64_t seq_len, int64_t dim, float eps, float* out, float* stats, uint8_t* mask,
-                        int32_t* err_flag, void* stream);
+                        int64_t seq_len, int64_t dim, float eps, float* out, void* out_bf16 /* nullable */,
+                        float* stats, uint8_t* mask, int32_t* err_flag, void* stream);
 /* gradients of the position embeddings (seq_len, H), token-type row 0 (H), LayerNorm weight / bias; the item
- * table is frozen (models.py:251-253).  workspace: xr_enc_ln_workspace_bytes(batch * seq_len).            */
+ * table is frozen (models.py:251-253).  The upstream gradient is dout (fp32) + dout_bf16 (the gradient of the
+ * bf16 copy), either may be NULL.  workspace: xr_enc_ln_workspace_bytes(batch * seq_len).                  */
 int xr_enc_embed_ln_bwd(const float* table, int64_t n_table_rows, const int64_t* idx, const float* pos_emb,
                         const float* type_emb, const float* gamma, const float* stats, const float* dout,
-                        int64_t batch, int64_t seq_len, int64_t dim, float* dpos, float* dtype0, float* dgamma,
-                        float* dbeta, void* workspace, void* stream);
-/* out = LayerNorm(y + residual) (BertSelfOutput / BertOutput; y = the dense layer's output incl. bias).
- * Backward: dresidual (fp32) and dy (y's dtype) both receive the LayerNorm input gradient.                */
-int xr_enc_add_ln_fwd(const void* y, int y_dtype, const float* residual, const float* gamma, const float* beta,
-                      int64_t n_tok, int64_t dim, float eps, float* out, float* stats, void* stream);
-int xr_enc_add_ln_bwd(const void* y, int y_dtype, const float* residual, const float* gamma, const float* stats,
-                      const float* dout, int64_t n_tok, int64_t dim, float* dresidual, void* dy, float* dgamma,
-                      float* dbeta, void* workspace, void* stream);
+                        const void* dout_bf16, int64_t batch, int64_t seq_len, int64_t dim, float* dpos,
+                        float* dtype0, float* dgamma, float* dbeta, void* workspace, void* stream);
+/* out = LayerNorm(y + bias + residual) (BertSelfOutput / BertOutput; y = the dense layer's product, its bias
+ * added here; bias may be NULL when y already holds it).  out_bf16 (nullable): the same rows rounded to bf16,
+ * the next GEMM's input.  Backward: dresidual (fp32) and dy (y's dtype) both receive the LayerNorm input
+ * gradient, dbias (nullable) its column sums; upstream = dout (fp32) + dout_bf16, either may be NULL.
+ * workspace: xr_enc_ln_workspace_bytes(1).                                                                  */
+int xr_enc_add_ln_fwd(const void* y, int y_dtype, const float* bias, const float* residual, const float* gamma,
+                      const float* beta, int64_t n_tok, int64_t dim, float eps, float* out, void* out_bf16,
+                      float* stats, void* stream);
+int xr_enc_add_ln_bwd(const void* y, int y_dtype, const float* bias, const float* residual, const float* gamma,
+                      const float* stats, const float* dout, const void* dout_bf16, int64_t n_tok, int64_t dim,
+                      float* dresidual, void* dy, float* dbias, float* dgamma, float* dbeta, void* workspace,
+                      void* stream);
+/* out[c] = sum over rows of x[r][c] (a linear layer's bias gradient: torch.nn.Linear inside BertSelfAttention /
+ * BertIntermediate); fp32 accumulation in a fixed order.  width must be a multiple of 16 bytes of elements. */
+size_t xr_enc_colsum_workspace_bytes(int64_t width);
+int xr_enc_colsum(const void* x, int dtype, int64_t rows, int64_t width, float* out, void* workspace, void* stream);
 /* exact (erf) GELU: dy == NULL -> out = gelu(x); else out = dy * gelu'(x).                               */
 int xr_enc_gelu(const void* x, const void* dy, int64_t n, int dtype, void* out, void* stream);
 /* causal + key-padding multi-head self-attention on qkv (B, L, 3 * n_heads * 32) = [Q | K | V]; keymask

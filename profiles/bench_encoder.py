@@ -14,7 +14,7 @@ import torch
 
 import xfmr_rec_b200 as xr
 from xfmr_rec_b200.data import synthetic_batch
-from xfmr_rec_b200.encoder import EncoderConfig, SeqEncoder, encoder_train_step
+from xfmr_rec_b200.encoder import EncoderConfig, GraphedEncoderStep, SeqEncoder, encoder_train_step
 
 dev = torch.device("cuda", 0)
 B, L, N_ITEMS = 128, 200, 27278
@@ -64,6 +64,11 @@ for name, cd in (("bf16", torch.bfloat16), ("fp32", torch.float32)):
         out["train_step_with_encoder"] = {"ms_per_step": ms, "seq_per_s": B / ms * 1e3,
                                           "note": "encoder forward (bf16-mixed) -> sync-free scoring-and-loss step -> "
                                                   "encoder backward; parameter gradients left in .grad (no optimizer)"}
+        gstep = GraphedEncoderStep(enc, xr.PoolLossStep(emb, xr.InfoNCELoss(xr.LossConfig()), B, L, token_dtype=torch.float32,
+                                                        logits_bf16=True, use_graph=False), table, L)
+        ms = timeit(lambda: gstep(hist, pos, neg), reps=50)
+        out["train_step_with_encoder_one_graph"] = {"ms_per_step": ms, "seq_per_s": B / ms * 1e3}
+        del gstep
     del enc
 
 try:

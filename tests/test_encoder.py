@@ -177,3 +177,69 @@ def test_encoder_train_step_feeds_the_loss_step_gradient_in_place(golden_dir):
     for k, p in enc.named_parameters():
         if p.grad is not None and not k.endswith("self.key.bias"):
             assert float((got[k] - p.grad).norm()) <= 1e-2 * float(p.grad.norm()) + 1e-6, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seq_len", [1, 37, 200, 384])
+def test_attention_tensor_core_path_matches_the_fp32_kernels(seq_len):
+    """bf16 activations run the warp-MMA attention kernels, fp32 activations the scalar ones: same masks
+    (causal AND key padding, a fully padded sequence included), same bf16-representable inputs, outputs and
+    all three gradients within bf16 rounding of the fp32 kernels' (norm-wise 1e-2; the tensor-core path rounds
+    P and dS to bf16 before their second contraction).  Ragged lengths exercise the 16-row padding."""
+    from xfmr_rec_b200.encoder import _Attention
+
+    g = torch.Generator(device="cuda").manual_seed(seq_len)
+    b, heads = 5, 12
+    qkv = torch.randn((b, seq_len, 3 * 384), generator=g, device="cuda").bfloat16()
+    mask = torch.ones((b, seq_len), dtype=torch.uint8, device="cuda")
+    for i in range(b - 1):                      # left padding of different lengths
+        mask[i, : (i * seq_len) // 7] = 0
+    mask[b - 1] = 0                             # nothing to attend to: zero output, zero gradient
+    up = torch.randn((b, seq_len, 384), generator=g, device="cuda").bfloat16()
+    res = {}
+    for dt in (torch.float32, torch.bfloat16):
+        x = qkv.detach().to(dt).clone().requires_grad_(True)
+        out = _Attention.apply(x, mask, heads)
+        out.backward(up.to(dt))
+        res[dt] = (out.detach().float(), x.grad.float())
+    for got, want in zip(res[torch.bfloat16], res[torch.float32]):
+        assert torch.isfinite(got).all()
+        assert float((got - want).norm()) <= 1e-2 * float(want.norm()) + 1e-6
+    assert float(res[torch.bfloat16][0][b - 1].abs().max()) == 0.0
+    assert float(res[torch.bfloat16][1][b - 1].abs().max()) == 0.0
+    x = qkv.detach().clone().requires_grad_(True)
+    out2 = _Attention.apply(x, mask, heads)
+    out2.backward(up)
+    assert torch.equal(out2.float(), res[torch.bfloat16][0]) and torch.equal(x.grad.float(), res[torch.bfloat16][1])
+
+
+@pytest.mark.gpu
+def test_graphed_encoder_step_equals_the_eager_step(golden_dir):
+    """One CUDA graph for encoder forward + scoring-and-loss step + encoder backward: same loss and the same
+    parameter gradients (bit for bit: every kernel on the path is deterministic) as the eager
+    encoder_train_step on two different batches."""
+    import xfmr_rec_b200 as xr
+    from xfmr_rec_b200.data import synthetic_batch
+    from xfmr_rec_b200.encoder import EncoderConfig, GraphedEncoderStep, SeqEncoder, encoder_train_step
+
+    B, L, n_items = 16, 48, 3000
+    torch.manual_seed(0)
+    enc = SeqEncoder(EncoderConfig(num_hidden_layers=2, intermediate_size=128, max_seq_length=L),
+                     compute_dtype=torch.bfloat16).cuda()
+    batches = [synthetic_batch(n_items, B, L, dim=384, seed=s) for s in (1, 2)]
+    table = torch.from_numpy(batches[0]["table"]).cuda()
+    emb = xr.models.ItemEmbeddings(table, add_padding_row=False).cuda()
+    mk = lambda **kw: xr.PoolLossStep(emb, xr.InfoNCELoss(xr.LossConfig()), B, L, token_dtype=torch.float32,
+                                      logits_bf16=True, **kw)
+    eager_step, graphed = mk(), GraphedEncoderStep(enc, mk(use_graph=False), table, L)
+    for b in batches:
+        hist, pos, neg = (torch.from_numpy(b[k]).cuda() for k in ("history_item_idx", "pos_item_idx", "neg_item_idx"))
+        loss_g = graphed(hist, pos, neg).clone()
+        grads_g = {n: p.grad.clone() for n, p in enc.named_parameters() if p.grad is not None}
+        enc.zero_grad(set_to_none=False)     # the .grad tensors belong to the graph: zero them in place
+        loss_e = encoder_train_step(enc, eager_step, table, hist, pos, neg).clone()
+        grads_e = {n: p.grad.clone() for n, p in enc.named_parameters() if p.grad is not None}
+        assert float(loss_g) == float(loss_e)
+        assert grads_g.keys() == grads_e.keys() and len(grads_g) > 30
+        for n in grads_g:
+            assert torch.equal(grads_g[n], grads_e[n]), n

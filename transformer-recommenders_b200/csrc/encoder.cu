@@ -61,8 +61,8 @@ __global__ void __launch_bounds__(256)
 enc_embed_ln_fwd_kernel(const float* __restrict__ table, int64_t n_table_rows, const int64_t* __restrict__ idx,
                         const float* __restrict__ pos_emb, const float* __restrict__ type_emb,
                         const float* __restrict__ gamma, const float* __restrict__ beta, int64_t n_tok, int seq_len,
-                        float eps, float* __restrict__ out, float* __restrict__ stats, uint8_t* __restrict__ mask,
-                        int32_t* __restrict__ err_flag) {
+                        float eps, float* __restrict__ out, __nv_bfloat16* __restrict__ out_lp,
+                        float* __restrict__ stats, uint8_t* __restrict__ mask, int32_t* __restrict__ err_flag) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -87,6 +87,9 @@ enc_embed_ln_fwd_kernel(const float* __restrict__ table, int64_t n_table_rows, c
     ln_row(x, gamma, beta, eps, lane, y, mean, rstd);
 #pragma unroll
     for (int k = 0; k < enc::PER; ++k) out[t * enc::H + lane + 32 * k] = y[k];
+    if (out_lp)
+#pragma unroll
+      for (int k = 0; k < enc::PER; ++k) out_lp[t * enc::H + lane + 32 * k] = __float2bfloat16_rn(y[k]);
     if (lane == 0) {
       stats[2 * t] = mean;
       stats[2 * t + 1] = rstd;
@@ -119,39 +122,51 @@ __device__ __forceinline__ void ln_row_bwd(const float (&x)[enc::PER], const flo
 
 constexpr int LNB_BLOCKS = 296;   // partial rows of the parameter-gradient reductions (two per SM)
 
-// fold per-warp dgamma / dbeta (registers) into the block's partial row: fixed order inside the block
-__device__ __forceinline__ void ln_param_partials(const float (&dg)[enc::PER], const float (&db)[enc::PER],
-                                                  float* __restrict__ part /* [gridDim.x][2][H] */) {
-  __shared__ float s_g[8][enc::H], s_b[8][enc::H];
+// fold the warps' column sums (registers; vector v of NV) into the block's partial rows part[block][v][H]:
+// fixed order inside the block
+template <int NV>
+__device__ __forceinline__ void ln_param_partials(const float (&acc)[NV][enc::PER],
+                                                  float* __restrict__ part /* [gridDim.x][NV][H] */) {
+  __shared__ float s_acc[8][NV][enc::H];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k < enc::PER; ++k) {
-    s_g[warp][lane + 32 * k] = dg[k];
-    s_b[warp][lane + 32 * k] = db[k];
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < enc::H; c += blockDim.x) {
-    float g = 0.f, b = 0.f;
+  for (int v = 0; v < NV; ++v)
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      g += s_g[w][c];
-      b += s_b[w][c];
-    }
-    part[((size_t)blockIdx.x * 2) * enc::H + c] = g;
-    part[((size_t)blockIdx.x * 2 + 1) * enc::H + c] = b;
+    for (int k = 0; k < enc::PER; ++k) s_acc[warp][v][lane + 32 * k] = acc[v][k];
+  __syncthreads();
+  for (int e = threadIdx.x; e < NV * enc::H; e += blockDim.x) {
+    const int v = e / enc::H, c = e % enc::H;
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += s_acc[w][v][c];
+    part[((size_t)blockIdx.x * NV + v) * enc::H + c] = a;
   }
 }
 
-// out[j][c] = sum over the n_part partial rows, fixed order (deterministic)
-__global__ void enc_fold_partials_kernel(const float* __restrict__ part, int n_part, int n_vec, int width,
-                                         float* __restrict__ out0, float* __restrict__ out1) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= width) return;
-  for (int j = 0; j < n_vec; ++j) {
-    float s = 0.f;
-    for (int p = 0; p < n_part; ++p) s += part[((size_t)p * n_vec + j) * width + c];
-    (j == 0 ? out0 : out1)[c] = s;
+// out_v[c] = sum over the n_part partial rows part[p][v][c]; a block owns 32 columns of one vector, its 8 warps
+// take every 8th partial row, then one fixed-order sum over the warps: deterministic, ~40 loads per thread
+__global__ void __launch_bounds__(256)
+enc_fold_partials_kernel(const float* __restrict__ part, int n_part, int n_vec, int width, float* __restrict__ out0,
+                         float* __restrict__ out1, float* __restrict__ out2) {
+  __shared__ float s[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int v = blockIdx.y, c = blockIdx.x * 32 + lane;
+  float a = 0.f;
+  if (c < width)
+    for (int p = warp; p < n_part; p += 8) a += part[((size_t)p * n_vec + v) * width + c];
+  s[warp][lane] = a;
+  __syncthreads();
+  if (warp == 0 && c < width) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s[w][lane];
+    float* out = v == 0 ? out0 : (v == 1 ? out1 : out2);
+    if (out) out[c] = t;
   }
+}
+static inline void launch_fold(const float* part, int n_part, int n_vec, int width, float* o0, float* o1, float* o2,
+                               cudaStream_t s) {
+  enc_fold_partials_kernel<<<dim3((width + 31) / 32, n_vec), 256, 0, s>>>(part, n_part, n_vec, width, o0, o1, o2);
 }
 
 // backward of embed_ln: dgamma, dbeta (partials), d position_emb[l] (sum over the batch), d token_type_emb[0]
@@ -161,14 +176,12 @@ __global__ void __launch_bounds__(256)
 enc_embed_ln_bwd_kernel(const float* __restrict__ table, int64_t n_table_rows, const int64_t* __restrict__ idx,
                         const float* __restrict__ pos_emb, const float* __restrict__ type_emb,
                         const float* __restrict__ gamma, const float* __restrict__ stats,
-                        const float* __restrict__ dout, int64_t n_tok, int seq_len, float* __restrict__ dx_out,
-                        float* __restrict__ part) {
+                        const float* __restrict__ dout, const __nv_bfloat16* __restrict__ dout_lp, int64_t n_tok,
+                        int seq_len, float* __restrict__ dx_out, float* __restrict__ part) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  float dg[enc::PER], db[enc::PER];
-#pragma unroll
-  for (int k = 0; k < enc::PER; ++k) dg[k] = db[k] = 0.f;
+  float acc[2][enc::PER] = {};
   for (int64_t t = warp; t < n_tok; t += nwarps) {
     int64_t row = idx[t];
     if (row < 0 || row >= n_table_rows) row = 0;
@@ -178,13 +191,13 @@ enc_embed_ln_bwd_kernel(const float* __restrict__ table, int64_t n_table_rows, c
     for (int k = 0; k < enc::PER; ++k) {
       const int c = lane + 32 * k;
       x[k] = __ldg(table + row * enc::H + c) + pos_emb[(int64_t)l * enc::H + c] + type_emb[c];
-      dy[k] = dout[t * enc::H + c];
+      dy[k] = (dout ? dout[t * enc::H + c] : 0.f) + (dout_lp ? __bfloat162float(dout_lp[t * enc::H + c]) : 0.f);
     }
-    ln_row_bwd(x, dy, gamma, stats[2 * t], stats[2 * t + 1], lane, dx, dg, db);
+    ln_row_bwd(x, dy, gamma, stats[2 * t], stats[2 * t + 1], lane, dx, acc[0], acc[1]);
 #pragma unroll
     for (int k = 0; k < enc::PER; ++k) dx_out[t * enc::H + lane + 32 * k] = dx[k];
   }
-  ln_param_partials(dg, db, part);
+  ln_param_partials<2>(acc, part);
 }
 
 // dpos[l][c] = sum_b dx[b][l][c]  (fixed order over b); one thread per (l, c)
@@ -208,9 +221,9 @@ __global__ void enc_sum_rows_kernel(const float* __restrict__ x, int rows, float
 // ---- LayerNorm(y + residual): BertSelfOutput / BertOutput ------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
-enc_add_ln_fwd_kernel(const T* __restrict__ y, const float* __restrict__ res, const float* __restrict__ gamma,
-                      const float* __restrict__ beta, int64_t n_tok, float eps, float* __restrict__ out,
-                      float* __restrict__ stats) {
+enc_add_ln_fwd_kernel(const T* __restrict__ y, const float* __restrict__ bias, const float* __restrict__ res,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, int64_t n_tok, float eps,
+                      float* __restrict__ out, __nv_bfloat16* __restrict__ out_lp, float* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -219,12 +232,15 @@ enc_add_ln_fwd_kernel(const T* __restrict__ y, const float* __restrict__ res, co
 #pragma unroll
     for (int k = 0; k < enc::PER; ++k) {
       const int c = lane + 32 * k;
-      x[k] = to_f32(y[t * enc::H + c]) + res[t * enc::H + c];
+      x[k] = to_f32(y[t * enc::H + c]) + (bias ? bias[c] : 0.f) + res[t * enc::H + c];
     }
     float mean, rstd;
     ln_row(x, gamma, beta, eps, lane, o, mean, rstd);
 #pragma unroll
     for (int k = 0; k < enc::PER; ++k) out[t * enc::H + lane + 32 * k] = o[k];
+    if (out_lp)
+#pragma unroll
+      for (int k = 0; k < enc::PER; ++k) out_lp[t * enc::H + lane + 32 * k] = __float2bfloat16_rn(o[k]);
     if (lane == 0) {
       stats[2 * t] = mean;
       stats[2 * t + 1] = rstd;
@@ -232,53 +248,108 @@ enc_add_ln_fwd_kernel(const T* __restrict__ y, const float* __restrict__ res, co
   }
 }
 
-// dx = dLN (the gradient of BOTH y and the residual); dgamma / dbeta partials
+// dx = dLN (the gradient of BOTH y and the residual); partials of dgamma, dbeta and of the dense layer's bias
+// gradient (the column sums of dx).  The upstream gradient is dout (fp32) + dout_lp (bf16), either may be null.
 template <typename T>
 __global__ void __launch_bounds__(256)
-enc_add_ln_bwd_kernel(const T* __restrict__ y, const float* __restrict__ res, const float* __restrict__ gamma,
-                      const float* __restrict__ stats, const float* __restrict__ dout, int64_t n_tok,
+enc_add_ln_bwd_kernel(const T* __restrict__ y, const float* __restrict__ bias, const float* __restrict__ res,
+                      const float* __restrict__ gamma, const float* __restrict__ stats,
+                      const float* __restrict__ dout, const __nv_bfloat16* __restrict__ dout_lp, int64_t n_tok,
                       float* __restrict__ dx_out, T* __restrict__ dy_out, float* __restrict__ part) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  float dg[enc::PER], db[enc::PER];
-#pragma unroll
-  for (int k = 0; k < enc::PER; ++k) dg[k] = db[k] = 0.f;
+  float acc[3][enc::PER] = {};
   for (int64_t t = warp; t < n_tok; t += nwarps) {
     float x[enc::PER], dy[enc::PER], dx[enc::PER];
 #pragma unroll
     for (int k = 0; k < enc::PER; ++k) {
       const int c = lane + 32 * k;
-      x[k] = to_f32(y[t * enc::H + c]) + res[t * enc::H + c];
-      dy[k] = dout[t * enc::H + c];
+      x[k] = to_f32(y[t * enc::H + c]) + (bias ? bias[c] : 0.f) + res[t * enc::H + c];
+      dy[k] = (dout ? dout[t * enc::H + c] : 0.f) + (dout_lp ? __bfloat162float(dout_lp[t * enc::H + c]) : 0.f);
     }
-    ln_row_bwd(x, dy, gamma, stats[2 * t], stats[2 * t + 1], lane, dx, dg, db);
+    ln_row_bwd(x, dy, gamma, stats[2 * t], stats[2 * t + 1], lane, dx, acc[0], acc[1]);
 #pragma unroll
     for (int k = 0; k < enc::PER; ++k) {
       const int c = lane + 32 * k;
       dx_out[t * enc::H + c] = dx[k];                 // gradient of the residual stream (fp32)
       dy_out[t * enc::H + c] = from_f32<T>(dx[k]);    // gradient of the linear layer's output (its dtype)
+      acc[2][k] += dx[k];
     }
   }
-  ln_param_partials(dg, db, part);
+  ln_param_partials<3>(acc, part);
 }
 
 // ---- exact GELU (BertIntermediate, hidden_act = "gelu") ----------------------------------------------------
+__device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float v) {
+  const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * v * v);
+  return cdf + v * pdf;
+}
+// 16 bytes per thread and access (VEC = 16 / sizeof(T) elements); the scalar tail covers n % VEC and
+// unaligned buffers (vec_ok = 0)
 template <typename T>
-__global__ void enc_gelu_fwd_kernel(const T* __restrict__ x, int64_t n, T* __restrict__ y) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float v = to_f32(x[i]);
-    y[i] = from_f32<T>(0.5f * v * (1.0f + erff(v * 0.70710678118654752f)));
+__global__ void __launch_bounds__(256)
+enc_gelu_fwd_kernel(const T* __restrict__ x, int64_t n, T* __restrict__ y, int vec_ok) {
+  constexpr int VEC = 16 / sizeof(T);
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nv = vec_ok ? n / VEC : 0;
+  for (int64_t i = tid; i < nv; i += nth) {
+    int4 raw = ld_stream16(x + i * VEC);
+    T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) e[k] = from_f32<T>(gelu_f(to_f32(e[k])));
+    *reinterpret_cast<int4*>(y + i * VEC) = raw;
   }
+  for (int64_t i = nv * VEC + tid; i < n; i += nth) y[i] = from_f32<T>(gelu_f(to_f32(x[i])));
 }
 template <typename T>
-__global__ void enc_gelu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, int64_t n,
-                                    T* __restrict__ dx) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float v = to_f32(x[i]);
-    const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752f));
-    const float pdf = 0.3989422804014327f * __expf(-0.5f * v * v);
-    dx[i] = from_f32<T>(to_f32(dy[i]) * (cdf + v * pdf));
+__global__ void __launch_bounds__(256)
+enc_gelu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, int64_t n, T* __restrict__ dx, int vec_ok) {
+  constexpr int VEC = 16 / sizeof(T);
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nv = vec_ok ? n / VEC : 0;
+  for (int64_t i = tid; i < nv; i += nth) {
+    int4 rx = ld_stream16(x + i * VEC), rd = ld_stream16(dy + i * VEC);
+    const T* ex = reinterpret_cast<const T*>(&rx);
+    T* ed = reinterpret_cast<T*>(&rd);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) ed[k] = from_f32<T>(to_f32(ed[k]) * gelu_grad_f(to_f32(ex[k])));
+    st_stream16(dx + i * VEC, rd);
+  }
+  for (int64_t i = nv * VEC + tid; i < n; i += nth) dx[i] = from_f32<T>(to_f32(dy[i]) * gelu_grad_f(to_f32(x[i])));
+}
+
+// column sums of a (rows, width) matrix (a linear layer's bias gradient): block = 8 warps x 32 lanes, a lane owns
+// VEC consecutive columns, warp w of row slice blockIdx.y takes rows y * 8 + w, + 8 * gridDim.y, ...; partial rows
+// part[y][width] folded by enc_fold_partials_kernel.  Fixed order everywhere: deterministic.
+constexpr int COLSUM_SLICES = 64;
+template <typename T>
+__global__ void __launch_bounds__(256)
+enc_colsum_kernel(const T* __restrict__ x, int64_t rows, int width, float* __restrict__ part) {
+  constexpr int VEC = 16 / sizeof(T);
+  __shared__ float s[8][32 * VEC];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = (blockIdx.x * 32 + lane) * VEC;
+  float a[VEC] = {};
+  if (c0 < width)
+    for (int64_t r = (int64_t)blockIdx.y * 8 + warp; r < rows; r += 8 * (int64_t)gridDim.y) {
+      int4 raw = ld_stream16(x + r * width + c0);
+      const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) a[k] += to_f32(e[k]);
+    }
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) s[warp][lane * VEC + k] = a[k];
+  __syncthreads();
+  for (int e = threadIdx.x; e < 32 * VEC; e += blockDim.x) {
+    const int c = blockIdx.x * 32 * VEC + e;
+    if (c >= width) continue;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s[w][e];
+    part[(size_t)blockIdx.y * width + c] = t;
   }
 }
 
@@ -438,10 +509,9 @@ enc_attn_bwd_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ keyma
 // or 16 keys (dK / dV pass).  The probabilities feed the second MMA straight from the accumulator registers
 // (the C fragment of two adjacent n8 tiles IS the A fragment of the next k16 step).  Deterministic: no atomics.
 namespace enc {
-constexpr int RS = 40;   // row stride (bf16) of the row-major [L][32] tiles: 20 words -> the 8 rows x 4 words
-                         // one fragment load touches fall in 32 different banks
+constexpr int RS = 40;   // row stride (bf16) of the [L][32] tiles: 80 bytes -> the eight 16-byte rows of an 8x8
+                         // ldmatrix block fall in eight different 16-byte bank groups
 __host__ __device__ constexpr int pad16(int l) { return (l + 15) & ~15; }
-__host__ __device__ constexpr int ts_of(int lp) { return lp + 8; }   // row stride of the transposed [32][L] tiles
 }  // namespace enc
 
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -466,23 +536,41 @@ __device__ __forceinline__ void load_a_rows(const __nv_bfloat16* rows, int g, in
     a[ks][3] = lds32(rows + (g + 8) * enc::RS + 16 * ks + 2 * t + 8);
   }
 }
-// c[nt] (16 x 8) += A (16 x 32) . X[n0 + 8 nt + ..][0..32]^T for nt = 0, 1: X row-major, its rows are the n index
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const __nv_bfloat16* row) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const __nv_bfloat16* row) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// c[nt] (16 x 8) += A (16 x 32) . X[n0 + 8 nt + ..][0..32]^T for nt = 0, 1: X row-major, its rows are the n index.
+// One ldmatrix.x4 per n tile: the four 8x8 blocks (rows n0 + 8 nt .., columns 0-7 / 8-15 / 16-23 / 24-31) are
+// the B fragments {b0, b1} of the two k-steps.
 __device__ __forceinline__ void mma_rows(float (&c)[2][4], const uint32_t (&a)[2][4], const __nv_bfloat16* x, int n0,
-                                         int g, int t) {
+                                         int lane) {
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt) {
-    const __nv_bfloat16* r = x + (n0 + 8 * nt + g) * enc::RS + 2 * t;
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) mma16816(c[nt], a[ks], lds32(r + 16 * ks), lds32(r + 16 * ks + 8));
+    uint32_t b[4];
+    ldmatrix_x4(b, x + (n0 + 8 * nt + (lane & 7)) * enc::RS + 8 * (lane >> 3));
+    mma16816(c[nt], a[0], b[0], b[1]);
+    mma16816(c[nt], a[1], b[2], b[3]);
   }
 }
-// acc[dt] (16 x 8 dims) += A (16 x 16, k = positions k0 .. k0+15) . Xt[8 dt + ..][k0 ..]: Xt is [32][ts] transposed
-__device__ __forceinline__ void mma_cols(float (&acc)[4][4], const uint32_t (&a)[4], const __nv_bfloat16* xt, int ts,
-                                         int k0, int g, int t) {
+// acc[dt] (16 x 8 columns 8 dt ..) += A (16 x 16, k = rows k0 .. k0+15 of X) . X[k0 ..][8 dt ..]: X row-major with
+// the k index as its rows -- the transposing ldmatrix hands out the {k, k+1} pairs the B fragment wants, so no
+// transposed copy of X is kept.  One ldmatrix.x4.trans serves two column tiles.
+__device__ __forceinline__ void mma_cols(float (&acc)[4][4], const uint32_t (&a)[4], const __nv_bfloat16* x, int k0,
+                                         int lane) {
+  const int m = lane >> 3;
 #pragma unroll
-  for (int dt = 0; dt < 4; ++dt) {
-    const __nv_bfloat16* r = xt + (8 * dt + g) * ts + k0 + 2 * t;
-    mma16816(acc[dt], a, lds32(r), lds32(r + 8));
+  for (int pr = 0; pr < 2; ++pr) {
+    uint32_t b[4];
+    ldmatrix_x4_trans(b, x + (k0 + (lane & 7) + 8 * (m & 1)) * enc::RS + 16 * pr + 8 * (m >> 1));
+    mma16816(acc[2 * pr], a, b[0], b[1]);
+    mma16816(acc[2 * pr + 1], a, b[2], b[3]);
   }
 }
 // tile order of a block's warps: heaviest tiles first, alternating direction so every warp gets a similar sum
@@ -492,43 +580,35 @@ __device__ __forceinline__ int tile_of(int round, int warp, int nw, int n_tiles,
   return heavy_last ? n_tiles - 1 - k : k;
 }
 
-// one head's [L][32] slice of a (rows, ld) bf16 matrix -> row-major tile (and, optionally, its transpose); rows
-// L .. lp-1 are zero so that masked probabilities never meet a NaN inside an MMA
+// one head's [L][32] slice of a (rows, ld) bf16 matrix -> row-major tile; rows L .. lp-1 are zero so that masked
+// probabilities never meet a NaN inside an MMA
 __device__ __forceinline__ void fill_tile(const __nv_bfloat16* __restrict__ src, int64_t ld, int seq_len, int lp,
-                                          __nv_bfloat16* rowmajor, __nv_bfloat16* transposed) {
-  const int ts = enc::ts_of(lp);
+                                          __nv_bfloat16* rowmajor) {
   for (int e = threadIdx.x; e < lp * 4; e += blockDim.x) {
     const int j = e >> 2, c = e & 3;
     int4 v = make_int4(0, 0, 0, 0);
-    if (j < seq_len) v = *reinterpret_cast<const int4*>(src + (int64_t)j * ld + 8 * c);
-    if (rowmajor) *reinterpret_cast<int4*>(rowmajor + j * enc::RS + 8 * c) = v;
-    if (transposed) {
-      const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&v);
-#pragma unroll
-      for (int d = 0; d < 8; ++d) transposed[(8 * c + d) * ts + j] = h[d];
-    }
+    if (j < seq_len) v = ld_stream16(src + (int64_t)j * ld + 8 * c);
+    *reinterpret_cast<int4*>(rowmajor + j * enc::RS + 8 * c) = v;
   }
-  if (transposed)
-    for (int e = threadIdx.x; e < 32 * 8; e += blockDim.x) transposed[(e >> 3) * ts + lp + (e & 7)] = __float2bfloat16_rn(0.f);
 }
 
 __global__ void __launch_bounds__(256)
 enc_attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __restrict__ keymask, int seq_len,
                         int n_heads, __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lp = enc::pad16(seq_len), ts = enc::ts_of(lp);
+  const int lp = enc::pad16(seq_len);
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);   // [lp][RS]
   __nv_bfloat16* sK = sQ + lp * enc::RS;                            // [lp][RS]
-  __nv_bfloat16* sVt = sK + lp * enc::RS;                           // [32][ts]
-  uint8_t* s_mask = reinterpret_cast<uint8_t*>(sVt + 32 * ts);      // [lp]
+  __nv_bfloat16* sV = sK + lp * enc::RS;                            // [lp][RS]
+  uint8_t* s_mask = reinterpret_cast<uint8_t*>(sV + lp * enc::RS);  // [lp]
   const int b = blockIdx.x / n_heads, h = blockIdx.x % n_heads;
   const int hid = n_heads * enc::HD;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const __nv_bfloat16* base = qkv + (int64_t)b * seq_len * 3 * hid + h * enc::HD;
-  fill_tile(base, 3 * hid, seq_len, lp, sQ, nullptr);
-  fill_tile(base + hid, 3 * hid, seq_len, lp, sK, nullptr);
-  fill_tile(base + 2 * hid, 3 * hid, seq_len, lp, nullptr, sVt);
+  fill_tile(base, 3 * hid, seq_len, lp, sQ);
+  fill_tile(base + hid, 3 * hid, seq_len, lp, sK);
+  fill_tile(base + 2 * hid, 3 * hid, seq_len, lp, sV);
   for (int j = threadIdx.x; j < lp; j += blockDim.x) s_mask[j] = j < seq_len ? keymask[(int64_t)b * seq_len + j] : 0;
   __syncthreads();
   const float scale = 0.17677669529663687f;   // 1 / sqrt(32)
@@ -543,7 +623,7 @@ enc_attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __
     float o[4][4] = {};
     for (int kb = 0; kb <= i0; kb += 16) {
       float s[2][4] = {};
-      mma_rows(s, qa, sK, kb, g, t);
+      mma_rows(s, qa, sK, kb, lane);
       float mx[2] = {-CUDART_INF_F, -CUDART_INF_F};
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt)
@@ -581,7 +661,7 @@ enc_attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __
       }
       const uint32_t pa[4] = {pack_bf16x2(p[0][0], p[0][1]), pack_bf16x2(p[0][2], p[0][3]),
                               pack_bf16x2(p[1][0], p[1][1]), pack_bf16x2(p[1][2], p[1][3])};
-      mma_cols(o, pa, sVt, ts, kb, g, t);
+      mma_cols(o, pa, sV, kb, lane);
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -605,15 +685,12 @@ enc_attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __
                         const __nv_bfloat16* __restrict__ ctx, const __nv_bfloat16* __restrict__ dctx,
                         const float* __restrict__ lse, int seq_len, int n_heads, __nv_bfloat16* __restrict__ dqkv) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lp = enc::pad16(seq_len), ts = enc::ts_of(lp);
-  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+  const int lp = enc::pad16(seq_len);
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);   // four [lp][RS] tiles
   __nv_bfloat16* sK = sQ + lp * enc::RS;
   __nv_bfloat16* sV = sK + lp * enc::RS;
   __nv_bfloat16* sdO = sV + lp * enc::RS;
-  __nv_bfloat16* sQt = sdO + lp * enc::RS;     // [32][ts]
-  __nv_bfloat16* sKt = sQt + 32 * ts;
-  __nv_bfloat16* sdOt = sKt + 32 * ts;
-  float* s_lse = reinterpret_cast<float*>(sdOt + 32 * ts);   // [lp]
+  float* s_lse = reinterpret_cast<float*>(sdO + lp * enc::RS);      // [lp]
   float* s_delta = s_lse + lp;                               // [lp]
   uint8_t* s_mask = reinterpret_cast<uint8_t*>(s_delta + lp);
   const int b = blockIdx.x / n_heads, h = blockIdx.x % n_heads;
@@ -625,10 +702,10 @@ enc_attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __
   __nv_bfloat16* dbase = dqkv + (int64_t)b * seq_len * 3 * hid + h * enc::HD;
   const __nv_bfloat16* dO = dctx + (int64_t)b * seq_len * hid + h * enc::HD;
   const __nv_bfloat16* O = ctx + (int64_t)b * seq_len * hid + h * enc::HD;
-  fill_tile(base, 3 * hid, seq_len, lp, sQ, sQt);
-  fill_tile(base + hid, 3 * hid, seq_len, lp, sK, sKt);
-  fill_tile(base + 2 * hid, 3 * hid, seq_len, lp, sV, nullptr);
-  fill_tile(dO, hid, seq_len, lp, sdO, sdOt);
+  fill_tile(base, 3 * hid, seq_len, lp, sQ);
+  fill_tile(base + hid, 3 * hid, seq_len, lp, sK);
+  fill_tile(base + 2 * hid, 3 * hid, seq_len, lp, sV);
+  fill_tile(dO, hid, seq_len, lp, sdO);
   for (int j = threadIdx.x; j < lp; j += blockDim.x) {
     s_mask[j] = j < seq_len ? keymask[(int64_t)b * seq_len + j] : 0;
     s_lse[j] = j < seq_len ? lse[((int64_t)b * n_heads + h) * seq_len + j] : CUDART_INF_F;
@@ -654,8 +731,8 @@ enc_attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __
     float dq[4][4] = {};
     for (int kb = 0; kb <= i0; kb += 16) {
       float s[2][4] = {}, dp[2][4] = {};
-      mma_rows(s, qa, sK, kb, g, t);
-      mma_rows(dp, doa, sV, kb, g, t);
+      mma_rows(s, qa, sK, kb, lane);
+      mma_rows(dp, doa, sV, kb, lane);
       float ds[2][4];
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt)
@@ -668,7 +745,7 @@ enc_attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __
         }
       const uint32_t dsa[4] = {pack_bf16x2(ds[0][0], ds[0][1]), pack_bf16x2(ds[0][2], ds[0][3]),
                                pack_bf16x2(ds[1][0], ds[1][1]), pack_bf16x2(ds[1][2], ds[1][3])};
-      mma_cols(dq, dsa, sKt, ts, kb, g, t);
+      mma_cols(dq, dsa, sK, kb, lane);
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -692,8 +769,8 @@ enc_attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __
     float dk[4][4] = {}, dv[4][4] = {};
     for (int qb = j0; qb < lp; qb += 16) {
       float st[2][4] = {}, dpt[2][4] = {};
-      mma_rows(st, ka, sQ, qb, g, t);
-      mma_rows(dpt, va, sdO, qb, g, t);
+      mma_rows(st, ka, sQ, qb, lane);
+      mma_rows(dpt, va, sdO, qb, lane);
       float p[2][4], ds[2][4];
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt)
@@ -710,8 +787,8 @@ enc_attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __
                               pack_bf16x2(p[1][0], p[1][1]), pack_bf16x2(p[1][2], p[1][3])};
       const uint32_t dsa[4] = {pack_bf16x2(ds[0][0], ds[0][1]), pack_bf16x2(ds[0][2], ds[0][3]),
                                pack_bf16x2(ds[1][0], ds[1][1]), pack_bf16x2(ds[1][2], ds[1][3])};
-      mma_cols(dv, pa, sdOt, ts, qb, g, t);
-      mma_cols(dk, dsa, sQt, ts, qb, g, t);
+      mma_cols(dv, pa, sdO, qb, lane);
+      mma_cols(dk, dsa, sQ, qb, lane);
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -729,9 +806,9 @@ enc_attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __
 }
 
 static size_t attn_mma_smem(int seq_len, bool bwd) {
-  const size_t lp = enc::pad16(seq_len), ts = enc::ts_of((int)lp);
-  if (!bwd) return (2 * lp * enc::RS + 32 * ts) * 2 + lp;
-  return (4 * lp * enc::RS + 3 * 32 * ts) * 2 + 2 * lp * 4 + lp;
+  const size_t lp = enc::pad16(seq_len);
+  if (!bwd) return 3 * lp * enc::RS * 2 + lp;
+  return 4 * lp * enc::RS * 2 + 2 * lp * 4 + lp;
 }
 
 static inline int enc_grid(int64_t warps_needed) {
@@ -747,13 +824,14 @@ using namespace xr;
 
 extern "C" size_t xr_enc_ln_workspace_bytes(int64_t n_tok) {
   // partial rows of the parameter-gradient reductions + one (n_tok, H) fp32 scratch for the embedding backward
-  return (size_t)LNB_BLOCKS * 2 * enc::H * 4 + (size_t)(n_tok > 0 ? n_tok : 1) * enc::H * 4 + 512;
+  return (size_t)LNB_BLOCKS * 3 * enc::H * 4 + (size_t)(n_tok > 0 ? n_tok : 1) * enc::H * 4 + 512;
 }
 
 extern "C" int xr_enc_embed_ln_fwd(const float* table, int64_t n_table_rows, const int64_t* idx,
                                    const float* pos_emb, const float* type_emb, const float* gamma,
                                    const float* beta, int64_t batch, int64_t seq_len, int64_t dim, float eps,
-                                   float* out, float* stats, uint8_t* mask, int32_t* err_flag, void* stream) {
+                                   float* out, void* out_bf16, float* stats, uint8_t* mask, int32_t* err_flag,
+                                   void* stream) {
   XR_CHECK_ARG(table && idx && pos_emb && type_emb && gamma && beta && out && stats && mask,
                "xr_enc_embed_ln_fwd: null pointer");
   XR_CHECK_ARG(dim == enc::H, "xr_enc_embed_ln_fwd: this build is specialised for hidden size %d", enc::H);
@@ -761,28 +839,29 @@ extern "C" int xr_enc_embed_ln_fwd(const float* table, int64_t n_table_rows, con
   const int64_t n_tok = batch * seq_len;
   if (n_tok == 0) return XR_OK;
   enc_embed_ln_fwd_kernel<<<enc_grid(n_tok), 256, 0, as_stream(stream)>>>(
-      table, n_table_rows, idx, pos_emb, type_emb, gamma, beta, n_tok, (int)seq_len, eps, out, stats, mask, err_flag);
+      table, n_table_rows, idx, pos_emb, type_emb, gamma, beta, n_tok, (int)seq_len, eps, out, (__nv_bfloat16*)out_bf16,
+      stats, mask, err_flag);
   XR_LAUNCH_CHECK("enc_embed_ln_fwd");
   return XR_OK;
 }
 
 extern "C" int xr_enc_embed_ln_bwd(const float* table, int64_t n_table_rows, const int64_t* idx,
                                    const float* pos_emb, const float* type_emb, const float* gamma,
-                                   const float* stats, const float* dout, int64_t batch, int64_t seq_len,
-                                   int64_t dim, float* dpos, float* dtype0, float* dgamma, float* dbeta,
-                                   void* workspace, void* stream) {
-  XR_CHECK_ARG(table && idx && pos_emb && type_emb && gamma && stats && dout && dpos && dtype0 && dgamma && dbeta &&
-                   workspace,
+                                   const float* stats, const float* dout, const void* dout_bf16, int64_t batch,
+                                   int64_t seq_len, int64_t dim, float* dpos, float* dtype0, float* dgamma,
+                                   float* dbeta, void* workspace, void* stream) {
+  XR_CHECK_ARG(table && idx && pos_emb && type_emb && gamma && stats && (dout || dout_bf16) && dpos && dtype0 &&
+                   dgamma && dbeta && workspace,
                "xr_enc_embed_ln_bwd: null pointer");
   XR_CHECK_ARG(dim == enc::H && batch >= 1 && seq_len >= 1, "xr_enc_embed_ln_bwd: bad sizes");
   cudaStream_t s = as_stream(stream);
   const int64_t n_tok = batch * seq_len;
   float* part = (float*)workspace;
-  float* dx = part + (size_t)LNB_BLOCKS * 2 * enc::H;
+  float* dx = part + (size_t)LNB_BLOCKS * 3 * enc::H;
   enc_embed_ln_bwd_kernel<<<LNB_BLOCKS, 256, 0, s>>>(table, n_table_rows, idx, pos_emb, type_emb, gamma, stats, dout,
-                                                     n_tok, (int)seq_len, dx, part);
+                                                     (const __nv_bfloat16*)dout_bf16, n_tok, (int)seq_len, dx, part);
   XR_LAUNCH_CHECK("enc_embed_ln_bwd");
-  enc_fold_partials_kernel<<<(enc::H + 127) / 128, 128, 0, s>>>(part, LNB_BLOCKS, 2, enc::H, dgamma, dbeta);
+  launch_fold(part, LNB_BLOCKS, 2, enc::H, dgamma, dbeta, nullptr, s);
   XR_LAUNCH_CHECK("enc_fold_partials");
   const int64_t n = seq_len * enc::H;
   enc_sum_over_batch_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dx, (int)batch, (int)seq_len, dpos);
@@ -792,42 +871,46 @@ extern "C" int xr_enc_embed_ln_bwd(const float* table, int64_t n_table_rows, con
   return XR_OK;
 }
 
-extern "C" int xr_enc_add_ln_fwd(const void* y, int y_dtype, const float* residual, const float* gamma,
-                                 const float* beta, int64_t n_tok, int64_t dim, float eps, float* out,
-                                 float* stats, void* stream) {
+extern "C" int xr_enc_add_ln_fwd(const void* y, int y_dtype, const float* bias, const float* residual,
+                                 const float* gamma, const float* beta, int64_t n_tok, int64_t dim, float eps,
+                                 float* out, void* out_bf16, float* stats, void* stream) {
   XR_CHECK_ARG(y && residual && gamma && beta && out && stats, "xr_enc_add_ln_fwd: null pointer");
   XR_CHECK_ARG(dim == enc::H && n_tok >= 0, "xr_enc_add_ln_fwd: bad sizes");
   if (n_tok == 0) return XR_OK;
   cudaStream_t s = as_stream(stream);
   if (y_dtype == XR_F32)
-    enc_add_ln_fwd_kernel<float><<<enc_grid(n_tok), 256, 0, s>>>((const float*)y, residual, gamma, beta, n_tok, eps, out, stats);
+    enc_add_ln_fwd_kernel<float><<<enc_grid(n_tok), 256, 0, s>>>((const float*)y, bias, residual, gamma, beta, n_tok, eps,
+                                                                 out, (__nv_bfloat16*)out_bf16, stats);
   else if (y_dtype == XR_BF16)
-    enc_add_ln_fwd_kernel<__nv_bfloat16><<<enc_grid(n_tok), 256, 0, s>>>((const __nv_bfloat16*)y, residual, gamma, beta, n_tok, eps, out, stats);
+    enc_add_ln_fwd_kernel<__nv_bfloat16><<<enc_grid(n_tok), 256, 0, s>>>(
+        (const __nv_bfloat16*)y, bias, residual, gamma, beta, n_tok, eps, out, (__nv_bfloat16*)out_bf16, stats);
   else
     XR_CHECK_ARG(false, "xr_enc_add_ln_fwd: bad dtype");
   XR_LAUNCH_CHECK("enc_add_ln_fwd");
   return XR_OK;
 }
 
-extern "C" int xr_enc_add_ln_bwd(const void* y, int y_dtype, const float* residual, const float* gamma,
-                                 const float* stats, const float* dout, int64_t n_tok, int64_t dim,
-                                 float* dresidual, void* dy, float* dgamma, float* dbeta, void* workspace,
-                                 void* stream) {
-  XR_CHECK_ARG(y && residual && gamma && stats && dout && dresidual && dy && dgamma && dbeta && workspace,
+extern "C" int xr_enc_add_ln_bwd(const void* y, int y_dtype, const float* bias, const float* residual,
+                                 const float* gamma, const float* stats, const float* dout, const void* dout_bf16,
+                                 int64_t n_tok, int64_t dim, float* dresidual, void* dy, float* dbias, float* dgamma,
+                                 float* dbeta, void* workspace, void* stream) {
+  XR_CHECK_ARG(y && residual && gamma && stats && (dout || dout_bf16) && dresidual && dy && dgamma && dbeta && workspace,
                "xr_enc_add_ln_bwd: null pointer");
   XR_CHECK_ARG(dim == enc::H && n_tok >= 1, "xr_enc_add_ln_bwd: bad sizes");
   cudaStream_t s = as_stream(stream);
   float* part = (float*)workspace;
   if (y_dtype == XR_F32)
-    enc_add_ln_bwd_kernel<float><<<LNB_BLOCKS, 256, 0, s>>>((const float*)y, residual, gamma, stats, dout, n_tok,
-                                                            dresidual, (float*)dy, part);
+    enc_add_ln_bwd_kernel<float><<<LNB_BLOCKS, 256, 0, s>>>((const float*)y, bias, residual, gamma, stats, dout,
+                                                            (const __nv_bfloat16*)dout_bf16, n_tok, dresidual,
+                                                            (float*)dy, part);
   else if (y_dtype == XR_BF16)
-    enc_add_ln_bwd_kernel<__nv_bfloat16><<<LNB_BLOCKS, 256, 0, s>>>((const __nv_bfloat16*)y, residual, gamma, stats, dout,
-                                                                    n_tok, dresidual, (__nv_bfloat16*)dy, part);
+    enc_add_ln_bwd_kernel<__nv_bfloat16><<<LNB_BLOCKS, 256, 0, s>>>(
+        (const __nv_bfloat16*)y, bias, residual, gamma, stats, dout, (const __nv_bfloat16*)dout_bf16, n_tok, dresidual,
+        (__nv_bfloat16*)dy, part);
   else
     XR_CHECK_ARG(false, "xr_enc_add_ln_bwd: bad dtype");
   XR_LAUNCH_CHECK("enc_add_ln_bwd");
-  enc_fold_partials_kernel<<<(enc::H + 127) / 128, 128, 0, s>>>(part, LNB_BLOCKS, 2, enc::H, dgamma, dbeta);
+  launch_fold(part, LNB_BLOCKS, 3, enc::H, dgamma, dbeta, dbias, s);
   XR_LAUNCH_CHECK("enc_fold_partials");
   return XR_OK;
 }
@@ -836,19 +919,43 @@ extern "C" int xr_enc_gelu(const void* x, const void* dy, int64_t n, int dtype, 
   XR_CHECK_ARG(x && out && n >= 0, "xr_enc_gelu: bad arguments");
   if (n == 0) return XR_OK;
   cudaStream_t s = as_stream(stream);
-  int64_t blocks = (n + 255) / 256;
-  const int64_t cap = (int64_t)sm_count() * 16;
+  int64_t blocks = (n / 4 + 255) / 256 + 1;
+  const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
+  const int vec_ok = (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)out) % 16) == 0;
   if (dtype == XR_F32) {
-    if (dy) enc_gelu_bwd_kernel<float><<<(unsigned)blocks, 256, 0, s>>>((const float*)x, (const float*)dy, n, (float*)out);
-    else enc_gelu_fwd_kernel<float><<<(unsigned)blocks, 256, 0, s>>>((const float*)x, n, (float*)out);
+    if (dy) enc_gelu_bwd_kernel<float><<<(unsigned)blocks, 256, 0, s>>>((const float*)x, (const float*)dy, n, (float*)out, vec_ok);
+    else enc_gelu_fwd_kernel<float><<<(unsigned)blocks, 256, 0, s>>>((const float*)x, n, (float*)out, vec_ok);
   } else if (dtype == XR_BF16) {
-    if (dy) enc_gelu_bwd_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, n, (__nv_bfloat16*)out);
-    else enc_gelu_fwd_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>((const __nv_bfloat16*)x, n, (__nv_bfloat16*)out);
+    using bf = __nv_bfloat16;
+    if (dy) enc_gelu_bwd_kernel<bf><<<(unsigned)blocks, 256, 0, s>>>((const bf*)x, (const bf*)dy, n, (bf*)out, vec_ok);
+    else enc_gelu_fwd_kernel<bf><<<(unsigned)blocks, 256, 0, s>>>((const bf*)x, n, (bf*)out, vec_ok);
   } else {
     XR_CHECK_ARG(false, "xr_enc_gelu: bad dtype");
   }
   XR_LAUNCH_CHECK("enc_gelu");
+  return XR_OK;
+}
+
+extern "C" size_t xr_enc_colsum_workspace_bytes(int64_t width) {
+  return (size_t)COLSUM_SLICES * (size_t)(width > 0 ? width : 1) * 4 + 256;
+}
+
+extern "C" int xr_enc_colsum(const void* x, int dtype, int64_t rows, int64_t width, float* out, void* workspace,
+                             void* stream) {
+  XR_CHECK_ARG(x && out && workspace, "xr_enc_colsum: null pointer");
+  XR_CHECK_ARG(rows >= 0 && width >= 1 && width <= (1 << 20), "xr_enc_colsum: bad sizes");
+  const int vec = dtype == XR_BF16 ? 8 : 4;
+  XR_CHECK_ARG(dtype == XR_BF16 || dtype == XR_F32, "xr_enc_colsum: bad dtype");
+  XR_CHECK_ARG(width % vec == 0 && (uintptr_t)x % 16 == 0, "xr_enc_colsum: rows must be whole 16-byte vectors");
+  cudaStream_t s = as_stream(stream);
+  float* part = (float*)workspace;
+  const dim3 grid((unsigned)((width / vec + 31) / 32), COLSUM_SLICES);
+  if (dtype == XR_BF16) enc_colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, rows, (int)width, part);
+  else enc_colsum_kernel<float><<<grid, 256, 0, s>>>((const float*)x, rows, (int)width, part);
+  XR_LAUNCH_CHECK("enc_colsum");
+  launch_fold(part, COLSUM_SLICES, 1, (int)width, out, nullptr, nullptr, s);
+  XR_LAUNCH_CHECK("enc_fold_partials");
   return XR_OK;
 }
 

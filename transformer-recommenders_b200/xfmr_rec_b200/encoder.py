@@ -10,8 +10,9 @@ returns: ``token_embeddings`` (B, L, H), ``sentence_embedding`` (pooled) and the
 What runs where: everything around the linear layers is a hand-written CUDA kernel in
 ``csrc/encoder.cu`` — the history gather fused with the position / token-type embeddings and the first
 LayerNorm, causal multi-head attention (forward and a deterministic backward), exact GELU, and
-``LayerNorm(dense_out + residual)`` forward / backward.  The linear layers are plain GEMMs and go through
-cuBLAS (``torch.nn.functional.linear``).  ``compute_dtype=torch.bfloat16`` reproduces Lightning's
+``LayerNorm(dense_out + bias + residual)`` forward / backward (which also yields the dense bias gradient and
+the bf16 copy the next GEMM reads), and the deterministic column sum behind the other bias gradients.  The
+linear layers are plain GEMMs and go through cuBLAS (``torch.nn.functional.linear`` / ``@``).  ``compute_dtype=torch.bfloat16`` reproduces Lightning's
 ``bf16-mixed`` policy: bf16 GEMMs / attention / GELU, fp32 residual stream, LayerNorm and softmax.
 
 Not implemented: dropout (HF default 0.1 in training mode) — the module behaves as ``BertModel.eval()``
@@ -50,34 +51,49 @@ def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
+def _pn(t):
+    return None if t is None else ops._p(t)
+
+
+def _grad_pair(dout, dout_lp):
+    """The two upstream gradients of a LayerNorm with an fp32 output and a bf16 copy: either may be absent."""
+    dout = None if dout is None else dout.contiguous().float()
+    dout_lp = None if dout_lp is None else dout_lp.contiguous().to(torch.bfloat16)
+    return dout, dout_lp
+
+
 class _EmbedLN(torch.autograd.Function):
-    """x0 = LayerNorm(table[idx] + position_emb[l] + token_type_emb[0]); mask = any(table[idx] != 0)."""
+    """x0 = LayerNorm(table[idx] + position_emb[l] + token_type_emb[0]); mask = any(table[idx] != 0).
+    Returns (x0 fp32, x0 rounded to bf16 when ``want_lowp`` else None, mask)."""
 
     @staticmethod
-    def forward(ctx, table, idx, pos_w, type_w, ln_w, ln_b, eps):
+    def forward(ctx, table, idx, pos_w, type_w, ln_w, ln_b, eps, want_lowp):
         dev = ops._require_cuda(table, idx, pos_w, type_w, ln_w, ln_b)
         b, l = idx.shape
         h = table.size(1)
         assert table.dtype == torch.float32 and l <= pos_w.size(0)
         table, idx = table.contiguous(), idx.contiguous()
         out = torch.empty((b, l, h), dtype=torch.float32, device=dev)
+        out_lp = torch.empty((b, l, h), dtype=torch.bfloat16, device=dev) if want_lowp else None
         stats = torch.empty((b * l, 2), dtype=torch.float32, device=dev)
         mask = torch.empty((b, l), dtype=torch.uint8, device=dev)
         with ops._on(dev):
             N.call("xr_enc_embed_ln_fwd", ops._p(table), table.size(0), ops._p(idx), ops._p(pos_w), ops._p(type_w),
-                   ops._p(ln_w), ops._p(ln_b), b, l, h, float(eps), ops._p(out), ops._p(stats), ops._p(mask), None,
-                   ops._stream())
+                   ops._p(ln_w), ops._p(ln_b), b, l, h, float(eps), ops._p(out), _pn(out_lp), ops._p(stats),
+                   ops._p(mask), None, ops._stream())
         ctx.save_for_backward(table, idx, pos_w, type_w, ln_w, stats)
         ctx.mark_non_differentiable(mask)
-        return out, mask
+        return out, out_lp, mask
 
     @staticmethod
-    def backward(ctx, dout, _dmask):
+    def backward(ctx, dout, dout_lp, _dmask):
         table, idx, pos_w, type_w, ln_w, stats = ctx.saved_tensors
-        dev = dout.device
+        dev = idx.device
         b, l = idx.shape
         h = table.size(1)
-        dout = dout.contiguous().float()
+        dout, dout_lp = _grad_pair(dout, dout_lp)
+        if dout is None and dout_lp is None:
+            return (None,) * 8
         dpos = torch.zeros_like(pos_w)
         dtype = torch.zeros_like(type_w)
         dg, db = torch.empty_like(ln_w), torch.empty_like(ln_w)
@@ -86,44 +102,81 @@ class _EmbedLN(torch.autograd.Function):
         dt0 = torch.empty(h, dtype=torch.float32, device=dev)
         with ops._on(dev):
             N.call("xr_enc_embed_ln_bwd", ops._p(table), table.size(0), ops._p(idx), ops._p(pos_w), ops._p(type_w),
-                   ops._p(ln_w), ops._p(stats), ops._p(dout), b, l, h, ops._p(dpos_l), ops._p(dt0), ops._p(dg),
-                   ops._p(db), ops._p(ws), ops._stream())
+                   ops._p(ln_w), ops._p(stats), _pn(dout), _pn(dout_lp), b, l, h, ops._p(dpos_l), ops._p(dt0),
+                   ops._p(dg), ops._p(db), ops._p(ws), ops._stream())
         dpos[:l] = dpos_l
         dtype[0] = dt0
-        return None, None, dpos, dtype, dg, db, None
+        return None, None, dpos, dtype, dg, db, None, None
 
 
 class _AddLN(torch.autograd.Function):
-    """LayerNorm(y + residual): BertSelfOutput / BertOutput (dropout p = 0)."""
+    """LayerNorm(y + bias + residual): BertSelfOutput / BertOutput (dropout p = 0) with the dense layer's bias
+    add folded in, so that its gradient (the column sums of the LayerNorm input gradient) comes out of the
+    same backward pass.  Returns (out fp32, out rounded to bf16 when ``want_lowp`` else None)."""
 
     @staticmethod
-    def forward(ctx, y, residual, ln_w, ln_b, eps):
-        dev = ops._require_cuda(y, residual, ln_w, ln_b)
+    def forward(ctx, y, bias, residual, ln_w, ln_b, eps, want_lowp):
+        dev = ops._require_cuda(y, bias, residual, ln_w, ln_b)
         y, residual = y.contiguous(), residual.contiguous()
-        assert residual.dtype == torch.float32
+        assert residual.dtype == torch.float32 and bias.dtype == torch.float32
         n_tok, h = y.numel() // y.size(-1), y.size(-1)
         out = torch.empty(residual.shape, dtype=torch.float32, device=dev)
+        out_lp = torch.empty(residual.shape, dtype=torch.bfloat16, device=dev) if want_lowp else None
         stats = torch.empty((n_tok, 2), dtype=torch.float32, device=dev)
         with ops._on(dev):
-            N.call("xr_enc_add_ln_fwd", ops._p(y), ops._dt(y), ops._p(residual), ops._p(ln_w), ops._p(ln_b), n_tok, h,
-                   float(eps), ops._p(out), ops._p(stats), ops._stream())
-        ctx.save_for_backward(y, residual, ln_w, stats)
-        return out
+            N.call("xr_enc_add_ln_fwd", ops._p(y), ops._dt(y), ops._p(bias), ops._p(residual), ops._p(ln_w),
+                   ops._p(ln_b), n_tok, h, float(eps), ops._p(out), _pn(out_lp), ops._p(stats), ops._stream())
+        ctx.save_for_backward(y, bias, residual, ln_w, stats)
+        return out, out_lp
 
     @staticmethod
-    def backward(ctx, dout):
-        y, residual, ln_w, stats = ctx.saved_tensors
-        dev = dout.device
+    def backward(ctx, dout, dout_lp):
+        y, bias, residual, ln_w, stats = ctx.saved_tensors
+        dev = y.device
         n_tok, h = y.numel() // y.size(-1), y.size(-1)
-        dout = dout.contiguous().float()
+        dout, dout_lp = _grad_pair(dout, dout_lp)
+        if dout is None and dout_lp is None:
+            return (None,) * 7
         dres = torch.empty_like(residual)
         dy = torch.empty_like(y)
-        dg, db = torch.empty_like(ln_w), torch.empty_like(ln_w)
+        dbias, dg, db = torch.empty_like(bias), torch.empty_like(ln_w), torch.empty_like(ln_w)
         ws = _ws(N.lib().xr_enc_ln_workspace_bytes(1), dev)
         with ops._on(dev):
-            N.call("xr_enc_add_ln_bwd", ops._p(y), ops._dt(y), ops._p(residual), ops._p(ln_w), ops._p(stats),
-                   ops._p(dout), n_tok, h, ops._p(dres), ops._p(dy), ops._p(dg), ops._p(db), ops._p(ws), ops._stream())
-        return dy, dres, dg, db, None
+            N.call("xr_enc_add_ln_bwd", ops._p(y), ops._dt(y), ops._p(bias), ops._p(residual), ops._p(ln_w),
+                   ops._p(stats), _pn(dout), _pn(dout_lp), n_tok, h, ops._p(dres), ops._p(dy), ops._p(dbias),
+                   ops._p(dg), ops._p(db), ops._p(ws), ops._stream())
+        return dy, dbias, dres, dg, db, None, None
+
+
+class _Linear(torch.autograd.Function):
+    """y = x W^T (+ bias) in ``x``'s dtype; the weight (fp32 master) is rounded to that dtype per call, as
+    autocast does.  The GEMMs (forward, dX, dW) are cuBLAS; the bias gradient is this library's deterministic
+    column sum.  ``bias=None``: the consumer (:class:`_AddLN`) adds the bias and produces its gradient."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        wc = weight.to(x.dtype)
+        ctx.save_for_backward(x, wc)
+        ctx.has_bias = bias is not None
+        ctx.master_dtype = weight.dtype
+        return F.linear(x, wc, None if bias is None else bias.to(x.dtype))
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wc = ctx.saved_tensors
+        dy = dy.contiguous().to(x.dtype)
+        dy2, x2 = dy.view(-1, dy.size(-1)), x.reshape(-1, x.size(-1))
+        dx = (dy2 @ wc).view(x.shape) if ctx.needs_input_grad[0] else None
+        dw = (dy2.t() @ x2).to(ctx.master_dtype)
+        db = None
+        if ctx.has_bias:
+            db = torch.empty(dy2.size(1), dtype=torch.float32, device=dy.device)
+            ws = _ws(N.lib().xr_enc_colsum_workspace_bytes(dy2.size(1)), dy.device)
+            with ops._on(dy.device):
+                N.call("xr_enc_colsum", ops._p(dy2), ops._dt(dy2), dy2.size(0), dy2.size(1), ops._p(db), ops._p(ws),
+                       ops._stream())
+            db = db.to(ctx.master_dtype)
+        return dx, dw, db
 
 
 class _Gelu(torch.autograd.Function):
@@ -267,35 +320,33 @@ class SeqEncoder(torch.nn.Module):
     def max_seq_length(self) -> int:
         return self.config.max_seq_length
 
-    def _linear(self, x, lin):
-        cd = self.compute_dtype
-        if cd == torch.float32:
-            return F.linear(x, lin.weight, lin.bias)
-        return F.linear(x.to(cd), lin.weight.to(cd), lin.bias.to(cd))
-
     def encode_tokens(self, item_idx: torch.Tensor, table: torch.Tensor):
         """(token_embeddings (B, L, H) fp32, attention_mask (B, L) uint8) for the last ``max_seq_length``
-        positions of ``item_idx`` (models.py:334-337)."""
+        positions of ``item_idx`` (models.py:334-337).  With ``compute_dtype=bfloat16`` every LayerNorm also
+        emits its output rounded to bf16 (the next GEMM's input) and sums the two upstream gradients in its
+        backward: no stand-alone cast or add kernels on the residual stream."""
         cfg, cd = self.config, self.compute_dtype
         if not item_idx.is_cuda:
             raise N.NativeError("SeqEncoder needs CUDA tensors; there is no CPU fallback")
+        lowp = cd != torch.float32
         idx = item_idx[:, -cfg.max_seq_length:]
         emb = self.embeddings
-        x, mask = _EmbedLN.apply(table, idx, emb.position_embeddings.weight, emb.token_type_embeddings.weight,
-                                 emb.LayerNorm.weight, emb.LayerNorm.bias, cfg.layer_norm_eps)
-        for layer in self.encoder.layer:
-            att = getattr(layer.attention, "self")
+        x, x_lp, mask = _EmbedLN.apply(table, idx, emb.position_embeddings.weight, emb.token_type_embeddings.weight,
+                                       emb.LayerNorm.weight, emb.LayerNorm.bias, cfg.layer_norm_eps, lowp)
+        n_layers = len(self.encoder.layer)
+        for li, layer in enumerate(self.encoder.layer):
+            att, att_out, ffn_out = getattr(layer.attention, "self"), layer.attention.output, layer.output
             w = torch.cat([att.query.weight, att.key.weight, att.value.weight], 0)
             b = torch.cat([att.query.bias, att.key.bias, att.value.bias], 0)
-            xin = x if cd == torch.float32 else x.to(cd)
-            qkv = F.linear(xin, w.to(cd), b.to(cd))                              # (B, L, 3H)
+            qkv = _Linear.apply(x_lp if lowp else x, w, b)                       # (B, L, 3H)
             ctx = _Attention.apply(qkv, mask, cfg.num_attention_heads)
-            x = _AddLN.apply(self._linear(ctx, layer.attention.output.dense), x,
-                             layer.attention.output.LayerNorm.weight, layer.attention.output.LayerNorm.bias,
-                             cfg.layer_norm_eps)
-            inter = _Gelu.apply(self._linear(x, layer.intermediate.dense))
-            x = _AddLN.apply(self._linear(inter, layer.output.dense), x, layer.output.LayerNorm.weight,
-                             layer.output.LayerNorm.bias, cfg.layer_norm_eps)
+            x, x_lp = _AddLN.apply(_Linear.apply(ctx, att_out.dense.weight, None), att_out.dense.bias, x,
+                                   att_out.LayerNorm.weight, att_out.LayerNorm.bias, cfg.layer_norm_eps, lowp)
+            inter = _Gelu.apply(_Linear.apply(x_lp if lowp else x, layer.intermediate.dense.weight,
+                                              layer.intermediate.dense.bias))
+            x, x_lp = _AddLN.apply(_Linear.apply(inter, ffn_out.dense.weight, None), ffn_out.dense.bias, x,
+                                   ffn_out.LayerNorm.weight, ffn_out.LayerNorm.bias, cfg.layer_norm_eps,
+                                   lowp and li + 1 < n_layers)
         return x, mask
 
     def pool(self, tokens: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
@@ -330,3 +381,58 @@ def encoder_train_step(encoder: SeqEncoder, step, table: torch.Tensor, history_i
     loss, dtok = step(tokens.detach(), history_item_idx[:, -encoder.max_seq_length:], pos_item_idx, neg_item_idx)
     tokens.backward(dtok.view_as(tokens).to(tokens.dtype))
     return loss
+
+
+class GraphedEncoderStep:
+    """:func:`encoder_train_step` on static shapes as ONE CUDA graph: encoder forward, the scoring-and-loss
+    step and the encoder backward (about 110 kernel launches for two layers) are captured once and replayed
+    per batch, so the step costs its GPU time instead of its Python / launch time.
+
+    ``step`` must be built with ``use_graph=False`` (its launches are recorded into this graph).  After a call
+    every parameter's ``.grad`` holds THIS batch's gradient (overwritten, not accumulated: the tensors live
+    in the graph's memory pool).  ``optimizer`` (optional, built with ``capturable=True``) is stepped inside
+    the graph."""
+
+    def __init__(self, encoder: SeqEncoder, step, table: torch.Tensor, history_len: int, *, optimizer=None,
+                 warmup: int = 3) -> None:
+        if step.graph is not None:
+            raise ValueError("GraphedEncoderStep: build the PoolLossStep with use_graph=False")
+        dev = table.device
+        self.encoder, self.step, self.table, self.optimizer = encoder, step, table, optimizer
+        lmax = encoder.max_seq_length
+        if min(history_len, lmax) != step.l:
+            raise ValueError(f"the loss step is sized for {step.l} positions, the encoder emits {min(history_len, lmax)}")
+        self.hist = torch.zeros((step.b, history_len), dtype=torch.int64, device=dev)
+        self.pos = torch.zeros((step.b, step.l), dtype=torch.int64, device=dev)
+        self.neg = torch.zeros((step.b, step.l), dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):          # warm-up: one-time kernel attributes, cuBLAS workspaces
+                for _ in range(max(1, warmup)):
+                    encoder.zero_grad(set_to_none=True)
+                    self._body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(dev)
+            encoder.zero_grad(set_to_none=True)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss = self._body()
+                if optimizer is not None:
+                    optimizer.step()
+
+    def _body(self):
+        enc = self.encoder
+        tokens, _ = enc.encode_tokens(self.hist, self.table)
+        loss, dtok = self.step.enqueue(tokens.detach(), self.hist[:, -enc.max_seq_length:], self.pos, self.neg)
+        tokens.backward(dtok.view_as(tokens).to(tokens.dtype))
+        return loss
+
+    def __call__(self, history_item_idx, pos_item_idx, neg_item_idx) -> torch.Tensor:
+        """Copy one batch (device or pinned host tensors) into the static buffers and replay.  Returns the
+        loss (0-dim tensor, a view of a static buffer valid until the next call)."""
+        self.hist.copy_(history_item_idx, non_blocking=True)
+        self.pos.copy_(pos_item_idx, non_blocking=True)
+        self.neg.copy_(neg_item_idx, non_blocking=True)
+        self.graph.replay()
+        return self.loss

@@ -227,6 +227,25 @@ class PoolLossStep:
         self.load(token_embeddings, history_item_idx, pos_item_idx, neg_item_idx)
         return self.run()
 
+    def enqueue(self, token_embeddings, history_item_idx, pos_item_idx, neg_item_idx):
+        """``load()`` + ``run()`` for DEVICE inputs entirely on the current stream: no copy stream, no events,
+        not the step's own graph.  This is the form an enclosing CUDA-graph capture can record (see
+        :class:`~xfmr_rec_b200.encoder.GraphedEncoderStep`); eager use is equivalent to ``__call__``."""
+        n = self.n_pos
+        for t in (token_embeddings, history_item_idx, pos_item_idx, neg_item_idx):
+            if not t.is_cuda:
+                raise N.NativeError("PoolLossStep.enqueue takes device tensors (use __call__ for host batches)")
+        with torch.cuda.device(self.device):
+            self.hist.copy_(history_item_idx.reshape(n))
+            self.pos.copy_(pos_item_idx.reshape(n))
+            self.neg.copy_(neg_item_idx.reshape(n))
+            self.tok.copy_(token_embeddings.reshape(n, self.d))
+            self._tok_src = None
+            self._launch()
+        loss = self.loss_buf.view(torch.float32)[2]
+        dtok = self.dtok.view(self.b, self.l, self.d) if self.dtok is not None else None
+        return loss, dtok
+
     def loss_dict(self) -> tuple[dict[str, torch.Tensor], dict[str, float]]:
         """What ``compute_losses`` logs (trainer.py:250-263) for the last ``run()`` of a
         ``monitor=True`` step: ({"loss/<Name>": 0-dim fp32 tensor} for all seven losses, the
