@@ -544,6 +544,7 @@ def main():
         line["configs"]["cfg3_ccl_sampled"] = bench_cfg3(xr, dev, world, peaks, max_over_ranks, flush)
         line["configs"]["cfg5_points"] = bench_cfg5(xr, dev, peaks, flush) if rank == 0 or world == 1 else None
         line["configs"]["hbm_kernels"] = bench_hbm_kernels(xr, dev, peaks, flush) if rank == 0 or world == 1 else None
+        line["configs"]["encoder_train_step"] = bench_encoder_step(xr, dev, flush) if rank == 0 or world == 1 else None
         torch.cuda.empty_cache()
     if not args.no_retrieval:
         line["retrieval"] = bench_retrieval(args, xr, dev, rank, world, peaks)
@@ -704,6 +705,41 @@ def bench_cfg5(xr, dev, peaks, flush):
         torch.cuda.empty_cache()
     return {"workload": "BPR / SSM sweep points, fused epilogue vs materialised (B, N) logits on the same GPU "
                         "(BASELINE configs[4])", "points": out}
+
+
+def bench_encoder_step(xr, dev, flush):
+    """the train step WITH the sequence encoder (models.py:51-102, 306-345) at the configs[1]
+    shape -- encoder forward (2 layers, d = 384, 12 heads, intermediate 1536 = all-MiniLM-L6-v2's, bf16-mixed)
+    -> the scoring-and-loss step of the headline line -> encoder backward, all in one CUDA graph."""
+    import torch
+
+    from xfmr_rec_b200.data import synthetic_batch
+    from xfmr_rec_b200.encoder import EncoderConfig, GraphedEncoderStep, SeqEncoder
+
+    b = synthetic_batch(N_ITEMS, BATCH, SEQ_LEN, dim=DIM, seed=5)
+    table = torch.from_numpy(b["table"]).to(dev)
+    hist, pos, neg = (torch.from_numpy(b[k]).to(dev) for k in ("history_item_idx", "pos_item_idx", "neg_item_idx"))
+    torch.manual_seed(0)
+    cfg = EncoderConfig(num_hidden_layers=2, intermediate_size=1536, max_seq_length=SEQ_LEN)
+    enc = SeqEncoder(cfg, compute_dtype=torch.bfloat16).to(dev)
+    emb = xr.models.ItemEmbeddings(table, add_padding_row=False).to(dev)
+    step = xr.PoolLossStep(emb, xr.InfoNCELoss(xr.LossConfig()), BATCH, SEQ_LEN, token_dtype=torch.float32,
+                           logits_bf16=True, use_graph=False)
+    graphed = GraphedEncoderStep(enc, step, table, SEQ_LEN)
+    ms = _timeit(torch, lambda: graphed(hist, pos, neg), flush, reps=20)
+    with torch.no_grad():
+        fwd_ms = _timeit(torch, lambda: enc.encode_tokens(hist, table), flush, reps=10)
+    loss = float(graphed(hist, pos, neg))
+    n_par = sum(p.numel() for n, p in enc.named_parameters() if p.grad is not None)
+    return {"value": BATCH / (ms / 1e3), "unit": "seq/s", "ms_per_step": ms, "encoder_forward_eager_ms": fwd_ms,
+            "loss": loss, "trained_parameters": n_par,
+            "encoder": {"layers": 2, "hidden": DIM, "heads": 12, "intermediate": 1536, "compute": "bf16-mixed "
+                        "(bf16 GEMMs / attention / GELU, fp32 residual stream, LayerNorm and softmax)", "dropout": 0.0},
+            "note": "GraphedEncoderStep: encoder forward + PoolLossStep + encoder backward (parameter gradients "
+                    "in .grad, no optimizer) replayed as one CUDA graph; L2 flushed between steps; the linear "
+                    "layers are cuBLAS GEMMs, everything else this repository's kernels (csrc/encoder.cu). "
+                    "Reference encoder class (transformers BertModel, eager, autocast bf16) on the same GPU: "
+                    "profiles/encoder_r02.json"}
 
 
 def bench_hbm_kernels(xr, dev, peaks, flush):

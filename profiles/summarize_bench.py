@@ -25,6 +25,8 @@ for name, leg in (d.get("configs") or {}).items():
             print(name, p["loss"], p["queries"], "x", p["candidates"], "fused", round(p["fused_ms"], 3), "ms (kernel", round(p["fused_kernel_ms"], 3),
                   ") materialised", round(p["materialised_logits_ms"], 2), "ms speedup", round(p["speedup"], 1), "frac burst",
                   round(p["roofline"]["frac"], 3), "sustained", round(p["roofline"]["frac_of_sustained_peak"], 3))
+    elif name == "encoder_train_step":
+        print(name, round(leg["value"]), leg["unit"], round(leg["ms_per_step"], 4), "ms; encoder forward (eager)", round(leg["encoder_forward_eager_ms"], 4), "ms")
     else:
         for kname, kk in leg.items():
             print(name, kname, {a: (round(b, 4) if isinstance(b, float) else b) for a, b in kk["roofline"].items() if a not in ("note",)})
