@@ -852,7 +852,8 @@ def bench_retrieval(args, xr, dev, rank, world, peaks):
                          "kernel_share_of_search": k_ms / ms, "traffic": None,
                          "note": "2*U*N*D FLOP against the sustained bf16 peak (the kernel runs for milliseconds "
                                  "under the power cap)" if tensor_bound else
-                                 "catalog bytes N*D*2 read once against the measured HBM copy bandwidth"}})
+                                 "catalog bytes N*D*2 read once against the measured HBM COPY bandwidth (a copy reads and "
+                                 "writes; a read-only stream can exceed it, so frac may pass 1)"}})
     head = points[0]
     out = {"metric": "full-catalog top-100 queries/sec", "value": head["queries_per_s"], "unit": "queries/s",
            "catalog_rows": n, "queries": head["queries"], "k": k, "ms_per_batch": head["ms_per_batch"],
