@@ -988,6 +988,7 @@ extern "C" int xr_kth_largest(const float* x, int64_t u, int64_t n, int64_t ld, 
 namespace xr {
 constexpr int64_t kFilterOvfCap = 8192;   // overflow slots per query (sub-buckets that run full spill here)
 constexpr int64_t kFilterTarget = 4096;   // survivors per query the sample stride aims at
+constexpr int64_t kFilterSampleRows = 163840;   // rows the threshold sample may score on a small shard
 constexpr int kFilterMargin = 28;         // rank positions of slack between the two score arithmetics
 struct ScoreTopkPlan {
   int64_t kk, k_sel, stride, ld_s, n_sub, cap_b;
@@ -1005,6 +1006,10 @@ static ScoreTopkPlan plan_score_topk(int64_t u, int64_t n, int64_t k, int64_t ma
   // at least 4 kk groups so that its kk-th maximum exists
   int64_t s = kFilterTarget / pl.kk;
   if (s > 32) s = 32;
+  // small shards: a denser sample (>= ~160k rows stay cheap next to the launch latency) gives a tighter
+  // threshold, so the filter epilogue and the finalize see proportionally fewer survivors
+  if (s > n / kFilterSampleRows) s = n / kFilterSampleRows;
+  if (s < 1) s = 1;
   const int64_t groups = (n + 15) / 16;
   while (s > 1 && groups / s < 4 * pl.kk) --s;
   if (s < 1) s = 1;
