@@ -196,6 +196,12 @@ int xr_dq_pool(const float* dlogits, int64_t ld, const void* q, const void* pos,
 int xr_dq_dense(const float* dlogits, int64_t ld, const void* q, const void* cand, int64_t m,
                 int64_t c, int64_t dim, int dtype, int cosine, const float* q_inv_norm,
                 const float* cand_inv_norm, float* dq, void* stream);
+/* dL/d candidate_embed for a dense (M, C, D) candidate tensor (losses.py:128-155 is differentiable in both
+ * arguments; the trainer never needs it: models.py:251-253 freezes the table).  dot: w * q_i; cosine (pass the
+ * forward's logits and both inverse norms): w * (q^ - cos * c^) / |c|.  dcand: (M, C, D) fp32.             */
+int xr_dcand_dense(const float* dlogits, const float* logits, int64_t ld, const void* q, const void* cand,
+                   int64_t m, int64_t c, int64_t dim, int dtype, int cosine, const float* q_inv_norm,
+                   const float* cand_inv_norm, float* dcand, void* stream);
 int xr_dq_sampled(const float* dlogits, int64_t ld, const void* q, const void* table,
                   int64_t n_rows, const int64_t* cand_idx, int64_t m, int64_t c, int64_t dim,
                   int dtype, const float* table_inv_norm, const float* q_inv_norm, float* dq,

@@ -174,6 +174,35 @@ def test_losses_match_reference_fp32(xr, golden_dir, case, form):
         assert_close_grad(q.grad.cpu().numpy(), z[f"dq/{name}"], FP32_REL)
 
 
+@pytest.mark.parametrize("case", ["dcand_default", "dcand_explicit_scaled"])
+def test_candidate_gradient_matches_reference(xr, golden_dir, case):
+    """The reference's losses are differentiable in BOTH arguments (losses.py:128-155): for the dense
+    (M, C, D) candidate tensor of its own API, dL/dcandidate_embed (xr_dcand_dense) and dL/dquery equal the
+    reference's autograd (fixtures from the reference itself, make_golden_dcand.py), incl. a negative tied
+    with the positive, a zero-norm candidate and explicit targets; a candidate-only gradient works too."""
+    z, cfg_kw = load(golden_dir, case)
+    cfg = xr.LossConfig(**cfg_kw)
+    target = dev(z["target"]) if "target" in z else None
+    for cls in xr.LOSS_CLASSES:
+        name = cls.__name__
+        q = dev(z["query"]).requires_grad_(True)
+        cand = dev(z["cand"]).requires_grad_(True)
+        loss = cls(cfg)(query_embed=q, candidate_embed=cand, target=target)
+        assert float(loss) == pytest.approx(float(z[f"loss/{name}"]), rel=FP32_REL, abs=1e-5), (case, name)
+        loss.backward()
+        assert_close_grad(q.grad.cpu().numpy(), z[f"dq/{name}"], FP32_REL)
+        got, want = cand.grad.cpu().numpy(), z[f"dcand/{name}"]
+        assert got.shape == want.shape
+        assert_close_grad(got.reshape(-1, got.shape[-1]), want.reshape(-1, want.shape[-1]), FP32_REL)
+        cand2 = dev(z["cand"]).requires_grad_(True)
+        (2.0 * cls(cfg)(query_embed=dev(z["query"]), candidate_embed=cand2, target=target)).backward()
+        assert torch.allclose(cand2.grad, 2.0 * cand.grad, rtol=1e-6, atol=1e-9)
+    with pytest.raises(NotImplementedError):    # handles stand for the frozen table: no gradient
+        h = xr.PoolCandidates(dev(z["cand"])[:, 0], dev(z["cand"])[0])
+        h.requires_grad = True
+        xr.InfoNCELoss(xr.LossConfig())(query_embed=dev(z["query"]).requires_grad_(True), candidate_embed=h)
+
+
 @pytest.mark.parametrize("case", GOLDEN_FP32)
 def test_logits_statistics_match_reference(xr, golden_dir, case):
     z, cfg_kw = load(golden_dir, case)

@@ -442,6 +442,57 @@ extern "C" int xr_dq_dense(const float* dlogits, int64_t ld, const void* q, cons
                                             cosine ? cand_inv_norm : nullptr, cosine, dq, s);
 }
 
+// dL/d candidate_embed of a DENSE (M, C, D) candidate tensor (the reference's own API form; its trainer never
+// asks for it: the table is frozen, models.py:251-253).  Dot logits (losses.py:195): dcand[i][c] = w q_i.
+// Cosine logits (losses.py:206-208): dcand[i][c] = w (q^_i - cos c^_ic) / max(|c_ic|, eps), cos = the logit.
+// One warp per candidate row, 16-byte stores when D % 4 == 0; HBM-bound (writes M C D fp32).
+template <typename T>
+__global__ void __launch_bounds__(256)
+dcand_dense_kernel(const float* __restrict__ dlogits, const float* __restrict__ logits, int64_t ld,
+                   const T* __restrict__ q, const T* __restrict__ cand, int64_t rows, int64_t c, int dim, int cosine,
+                   const float* __restrict__ q_inv, const float* __restrict__ cand_inv, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const int64_t i = r / c, j = r % c;
+    const float w = dlogits[i * ld + j];
+    const T* qr = q + i * dim;
+    const T* cr = cand + r * dim;
+    float* o = out + r * dim;
+    if (!cosine) {
+      for (int d = lane; d < dim; d += 32) o[d] = w * to_f32(qr[d]);
+    } else {
+      const float cosv = logits[i * ld + j], qi = q_inv[i], ci = cand_inv[r];
+      for (int d = lane; d < dim; d += 32) o[d] = w * (to_f32(qr[d]) * qi - cosv * to_f32(cr[d]) * ci) * ci;
+    }
+  }
+}
+
+extern "C" int xr_dcand_dense(const float* dlogits, const float* logits, int64_t ld, const void* q, const void* cand,
+                              int64_t m, int64_t c, int64_t dim, int dtype, int cosine, const float* q_inv_norm,
+                              const float* cand_inv_norm, float* dcand, void* stream) {
+  XR_CHECK_ARG(dlogits && q && cand && dcand && ld >= c, "xr_dcand_dense: bad arguments");
+  XR_CHECK_ARG(!cosine || (logits && q_inv_norm && cand_inv_norm), "xr_dcand_dense: cosine needs the logits and norms");
+  int rc = check_row_args("xr_dcand_dense", m, c, dim, dtype, q, cand);
+  if (rc) return rc;
+  if (m == 0 || c == 0) return XR_OK;
+  cudaStream_t s = as_stream(stream);
+  const int64_t rows = m * c;
+  int64_t blocks = (rows + 7) / 8;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (dtype == XR_F32)
+    dcand_dense_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(dlogits, logits, ld, (const float*)q, (const float*)cand,
+                                                               rows, c, (int)dim, cosine, q_inv_norm, cand_inv_norm, dcand);
+  else
+    dcand_dense_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>(
+        dlogits, logits, ld, (const __nv_bfloat16*)q, (const __nv_bfloat16*)cand, rows, c, (int)dim, cosine,
+        q_inv_norm, cand_inv_norm, dcand);
+  XR_LAUNCH_CHECK("dcand_dense");
+  return XR_OK;
+}
+
 extern "C" int xr_dq_sampled(const float* dlogits, int64_t ld, const void* q, const void* table,
                              int64_t n_rows, const int64_t* cand_idx, int64_t m, int64_t c,
                              int64_t dim, int dtype, const float* table_inv_norm,

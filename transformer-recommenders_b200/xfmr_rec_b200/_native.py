@@ -63,6 +63,7 @@ PROTOTYPES = {
     "xr_rowloss": (_int, [_p, _i64, _i64, _i64, _int, _p, _cfgp, _u32, _int, _f, _p, _p, _p, _p, _p, _p]),
     "xr_dq_pool": (_int, [_p, _i64, _p, _p, _p, _i64, _i64, _i64, _int, _int, _p, _p, _p]),
     "xr_dq_dense": (_int, [_p, _i64, _p, _p, _i64, _i64, _i64, _int, _int, _p, _p, _p, _p]),
+    "xr_dcand_dense": (_int, [_p, _p, _i64, _p, _p, _i64, _i64, _i64, _int, _int, _p, _p, _p, _p]),
     "xr_dq_sampled": (_int, [_p, _i64, _p, _p, _i64, _p, _i64, _i64, _i64, _int, _p, _p, _p, _p]),
     "xr_seq_sample_batch": (_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _int, _int, C.c_uint64,
                                    C.c_uint64, _p, _p, _p, _p, _p]),

@@ -137,6 +137,24 @@ class _AttachGrad(torch.autograd.Function):
         return (dq * grad_out).to(ctx.q_dtype), None, None
 
 
+class _AttachGradBoth(torch.autograd.Function):
+    """Dense (M, C, D) candidate tensor that requires grad (the reference's losses are differentiable in
+    both arguments, losses.py:128-155): the precomputed dL/dquery and dL/dcandidate_embed."""
+
+    @staticmethod
+    def forward(ctx, query, cand, loss, dq, dcand):
+        ctx.save_for_backward(dq, dcand)
+        ctx.q_dtype, ctx.c_dtype = query.dtype, cand.dtype
+        ctx.q_grad = dq is not None
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        dq, dcand = ctx.saved_tensors
+        gq = (dq * grad_out).to(ctx.q_dtype) if ctx.needs_input_grad[0] and dq is not None else None
+        return gq, (dcand * grad_out).to(ctx.c_dtype), None, None, None
+
+
 class _AttachGradScatter(torch.autograd.Function):
     """Same, but connected to the encoder output the query rows were compacted from
     (models.compute_embeds): backward is ONE kernel — grad_output scale, cast and scatter into the
@@ -252,10 +270,12 @@ class EmbedLoss(torch.nn.Module, abc.ABC):
         m, c = candidate_embed.size(0), candidate_embed.size(1)
         mode, tgt = self.check_target(m, c, target)
         need_grad = torch.is_grad_enabled() and query_embed.requires_grad
-        if getattr(candidate_embed, "requires_grad", False):
+        self._dcand = None
+        cand_grad = torch.is_grad_enabled() and bool(getattr(candidate_embed, "requires_grad", False))
+        if cand_grad and not isinstance(candidate_embed, torch.Tensor):
             raise NotImplementedError(
-                "gradients w.r.t. candidate_embed are not produced: the item table is frozen in the "
-                "reference (models.py:251-253); detach the candidates"
+                "gradients w.r.t. a candidate HANDLE are not produced: the item table is frozen in the "
+                "reference (models.py:251-253); pass the dense (M, C, D) tensor to differentiate it"
             )
         if m == 0:  # empty batch: every sum is 0 (and the stats block reports zero rows)
             z = torch.zeros(N.XR_NUM_LOSSES, dtype=torch.float64, device=query_embed.device)
@@ -265,7 +285,7 @@ class EmbedLoss(torch.nn.Module, abc.ABC):
         cdt, logits_bf16 = self._compute_dtype(query_embed)
         cfg = ops.make_cfg(self.config, logits_bf16=logits_bf16)
         kind = N.LOSS_KIND.get(type(self).__name__, -1)
-        grad_kind = kind if need_grad else -1
+        grad_kind = kind if (need_grad or cand_grad) else -1
         q = query_embed.detach()
 
         if isinstance(candidate_embed, _CandidateHandle) and mode != N.TARGET_FIRST:
@@ -275,7 +295,7 @@ class EmbedLoss(torch.nn.Module, abc.ABC):
             return self._pool(q, candidate_embed, cfg, cdt, kind, grad_kind, want_stats)
         if isinstance(candidate_embed, SampledCandidates):
             return self._sampled(q, candidate_embed, cfg, cdt, grad_kind, want_stats)
-        return self._dense(q, candidate_embed.detach(), cfg, cdt, mode, tgt, grad_kind, want_stats)
+        return self._dense(q, candidate_embed.detach(), cfg, cdt, mode, tgt, grad_kind, want_stats, cand_grad)
 
     def _pool(self, q, cand, cfg, cdt, kind, grad_kind, want_stats):
         pos, neg = cand.pos.detach(), cand.neg.detach()
@@ -339,7 +359,7 @@ class EmbedLoss(torch.nn.Module, abc.ABC):
         dq = ops.dq_sampled(dl, q, table, idx, table_inv, q_inv) if dl is not None else None
         return losses, stats, dq
 
-    def _dense(self, q, cand, cfg, cdt, mode, tgt, grad_kind, want_stats):
+    def _dense(self, q, cand, cfg, cdt, mode, tgt, grad_kind, want_stats, cand_grad=False):
         q, cand = q.to(cdt).contiguous(), cand.to(cdt).contiguous()
         q_inv = None
         if self.COSINE:
@@ -350,6 +370,8 @@ class EmbedLoss(torch.nn.Module, abc.ABC):
         dq = None
         if dl is not None:
             dq = ops.dq_dense(dl, q, cand, cosine=self.COSINE, q_inv=q_inv, cand_inv=cand_inv)
+            if cand_grad:
+                self._dcand = ops.dcand_dense(dl, logits, q, cand, cosine=self.COSINE, q_inv=q_inv, cand_inv=cand_inv)
         return losses, stats, dq
 
     def forward(self, query_embed, candidate_embed, target=None):
@@ -358,6 +380,9 @@ class EmbedLoss(torch.nn.Module, abc.ABC):
         loss = losses[N.LOSS_KIND[type(self).__name__]]
         if loss.dtype != torch.float32:
             loss = loss.to(torch.float32)
+        dcand, self._dcand = getattr(self, "_dcand", None), None
+        if dcand is not None:
+            return _AttachGradBoth.apply(query_embed, candidate_embed, loss, dq, dcand)
         if dq is not None:
             src = getattr(query_embed, "_xr_src", None)
             if src is not None and src[0].requires_grad and dq.size(1) % 8 == 0:

@@ -261,6 +261,17 @@ def dq_dense(dlogits, q, cand, cosine=False, q_inv=None, cand_inv=None):
     return dq
 
 
+def dcand_dense(dlogits, logits, q, cand, cosine=False, q_inv=None, cand_inv=None):
+    """dL/d candidate_embed of a dense (M, C, D) candidate tensor (xr_dcand_dense), fp32."""
+    dev = _require_cuda(dlogits, q, cand)
+    m, c, d = cand.shape
+    out = torch.empty((m, c, d), dtype=torch.float32, device=dev)
+    with _on(dev):
+        N.call("xr_dcand_dense", _p(dlogits), _p(logits), dlogits.size(1), _p(q), _p(cand), m, c, d, _dt(q),
+               int(cosine), _p(q_inv), _p(cand_inv), _p(out), _stream())
+    return out
+
+
 def dq_sampled(dlogits, q, table, cand_idx, table_inv=None, q_inv=None):
     dev = _require_cuda(dlogits, q, table, cand_idx)
     m, c = cand_idx.shape
