@@ -220,6 +220,15 @@ size_t xr_pool_step_monitor_workspace_bytes(int64_t n_pos, int64_t dim);
 int xr_pool_step_monitor(int64_t n_pos, int64_t dim, const xr_loss_config* cfg, double* losses_dot,
                          double* losses_cos, double* stats_out, void* workspace,
                          size_t workspace_bytes, void* stream);
+/* The compute phase of the step WITH the monitoring folded into the train kernel (trainer.py:250-263 +
+ * 288-300 from ONE tensor-core pass): train loss, dL/dtok, losses_dot[7], losses_cos[7], stats[16].  InfoNCE
+ * train loss, scale > 0, no hard-negative mining; call after xr_pool_step_ingest on the same stream with a
+ * workspace of xr_pool_step_monitor_workspace_bytes.  The dot family equals xr_pool_step_monitor bit for bit;
+ * the cosine family is evaluated as (score / |q|) / |n| with fp32 inverse norms.                          */
+int xr_pool_step_compute_mon(int64_t n_pos, int64_t dim, int loss_kind, const xr_loss_config* cfg,
+                             float grad_scale, void* dtok, int dtok_dtype, double* loss_out, double* losses_dot,
+                             double* losses_cos, double* stats_out, void* workspace, size_t workspace_bytes,
+                             void* stream);
 
 /* ---- SeqBatch construction (the step right before the path) ---------------
  * SeqDataset.__getitem__ + collate (data.py:669-805) for a whole batch in one launch:

@@ -137,17 +137,23 @@ def test_step_rejects_what_it_does_not_serve(xr):
                         xr.InfoNCELoss(xr.LossConfig()), 2, 8)
 
 
+@pytest.mark.parametrize("one_pass", [True, False])
 @pytest.mark.parametrize("graph", [True, False])
 @pytest.mark.parametrize("cfg_kw", [{}, dict(mask_false_negatives=False, scale=4.0, margin=0.2)])
-def test_step_with_monitor_equals_evaluate_all(xr, graph, cfg_kw):
+def test_step_with_monitor_equals_evaluate_all(xr, graph, cfg_kw, one_pass):
     """PoolLossStep(monitor=True): the train loss + gradient AND everything compute_losses logs
     (trainer.py:250-263: LogitsStatistics + all seven losses) from one sync-free sequence; same
-    numbers as evaluate_all on the module path (identical kernels on identical operands)."""
+    numbers as evaluate_all on the module path.  one_pass (default): ONE tensor-core pass -- the train
+    kernel accumulates the monitoring sums too; train loss and gradient stay bit-identical, the dot family
+    and the statistics equal the separate all-losses pass (same arithmetic on the same scores), the cosine
+    family is evaluated as (score / |q|) / |n| with fp32 inverse norms and agrees to bf16 tolerance with
+    the pass over bf16-normalised operands.  one_pass=False: the three-pass sequence, identical kernels."""
     b = orc.synth_batch(3000, 16, 60, dim=384, seed=4)
     emb = xr.models.ItemEmbeddings(torch.from_numpy(b["table"]), add_padding_row=False).cuda()
     cfg = xr.LossConfig(**cfg_kw)
     loss_fn = xr.InfoNCELoss(cfg)
-    step = xr.PoolLossStep(emb, loss_fn, 16, 60, use_graph=graph, monitor=True)
+    step = xr.PoolLossStep(emb, loss_fn, 16, 60, use_graph=graph, monitor=True, monitor_one_pass=one_pass)
+    assert step.monitor_one_pass == one_pass
     for rep in range(2):     # replay twice: no state may leak between steps
         loss, dtok = run_step(step, b, torch.bfloat16)
         got, got_stats = step.loss_dict()
@@ -160,7 +166,9 @@ def test_step_with_monitor_equals_evaluate_all(xr, graph, cfg_kw):
         assert torch.equal(loss, want["loss/InfoNCELoss"].detach())
         assert torch.equal(dtok.reshape(tok.grad.shape), tok.grad)
         for k, v in want.items():
-            assert float(got[k]) == pytest.approx(float(v), rel=1e-6, abs=1e-6), k
+            cos_key = k.split("/")[1] in orc.COSINE_LOSSES
+            tol = 4e-3 if (one_pass and cos_key) else 1e-6
+            assert float(got[k]) == pytest.approx(float(v), rel=tol, abs=tol), k
         assert got_stats.keys() == want_stats.keys()
         for k, v in want_stats.items():
             assert got_stats[k] == pytest.approx(v, rel=1e-6, abs=1e-9), k

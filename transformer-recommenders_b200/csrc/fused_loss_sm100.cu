@@ -84,7 +84,12 @@ struct FusedParams {
   float* t_out;        // [m]                                      (KIND_DIAG)
   float* part_o;       // [slots][96 four-column groups][128 rows][4]  partial dQ of every segment
   float* part_s;       // [slots][CG][128][NSCAL]
-  float* part_all;     // [slots][CG][128][NSCAL_ALL]              (KIND_ALL_*)
+  float* part_all;     // [slots][CG][128][NSCAL_ALL]              (KIND_ALL_*; dot family of a MON train launch)
+  // MON train launches (the train kernel also accumulates what compute_losses logs, trainer.py:250-263):
+  float* part_all_cos;      // [slots][CG][128][NSCAL_ALL] cosine-family sums
+  const float* mon_inv_q;   // [m]  1 / max(|q_i|, eps)
+  const float* mon_inv_n;   // [cn rounded up to a tile] 1 / max(|n_j|, eps)
+  const float* mon_t_cos;   // [m]  cosine target logits (t_i / |q_i|) / |pos_i|
   float* gmax;         // [m][gmax_ld] group maxima                (KIND_GMAX)
   long long gmax_ld;
   int tile_stride;     // KIND_GMAX: only every tile_stride-th 64-row catalog tile is scored (0 = 1)
@@ -238,7 +243,7 @@ __device__ __forceinline__ void group_all(const uint32_t (&v)[16], int ncols, fl
   }
 }
 
-template <int KIND, bool RBF, int DBG>
+template <int KIND, bool RBF, int DBG, bool MON = false>
 __global__ void __launch_bounds__(fk::THREADS, 1)
 fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
                   const __grid_constant__ CUtensorMap tmap_b, const FusedParams p) {
@@ -569,6 +574,16 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
       float cnt = 0.f, sum_a = 0.f, sum_w = 0.f, diag_val = 0.f;
       AllAcc acc;
       acc.reset();
+      // MON: the cosine family is evaluated on the SAME scores, l_cos = (s / |q|) / |n| (losses.py:206-208 with
+      // fp32 inverse norms), against the cosine target built with the same association, so a pool entry equal
+      // to the row's positive still ties exactly
+      AllAcc acc_c;
+      acc_c.reset();
+      float mon_iq = 0.f, mon_tc_eff = CUDART_INF_F;
+      if (MON && row_ok) {
+        mon_iq = p.mon_inv_q[row];
+        if (p.mask_fn) mon_tc_eff = p.mon_t_cos[row];
+      }
       // KIND_FILTER: this lane's sub-bucket for the item = (row, catalog split, column group); its fill
       // count lives in a register (see score_gmax2_sm100.cu)
       const int sub = KIND == KIND_FILTER ? (slot / sh.rb_count) * CG + cg : 0;
@@ -672,6 +687,26 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
             tc_fence_before();
             mbar_arrive(bar_p_full(wb));
           }
+          if (MON) {   // after W is on its way to the gradient MMA: the monitoring sums are off the S -> W -> dQ chain
+            const int c0 = rot_tile(t0, T, rb, tl) * BN + cg * 16;
+            uint32_t vc[16];
+            const float4* ninv = reinterpret_cast<const float4*>(p.mon_inv_n + c0);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const float4 w4 = __ldg(ninv + jj);
+              vc[4 * jj + 0] = __float_as_uint(__fmul_rn(__fmul_rn(__uint_as_float(v[4 * jj + 0]), mon_iq), w4.x));
+              vc[4 * jj + 1] = __float_as_uint(__fmul_rn(__fmul_rn(__uint_as_float(v[4 * jj + 1]), mon_iq), w4.y));
+              vc[4 * jj + 2] = __float_as_uint(__fmul_rn(__fmul_rn(__uint_as_float(v[4 * jj + 2]), mon_iq), w4.z));
+              vc[4 * jj + 3] = __float_as_uint(__fmul_rn(__fmul_rn(__uint_as_float(v[4 * jj + 3]), mon_iq), w4.w));
+            }
+            if (ncols >= 16) {
+              group_all<false, RBF, true>(v, ncols, t_eff, tm, zref2, scale2, p.scale, p.margin, round_scaled, acc);
+              group_all<true, false, true>(vc, ncols, mon_tc_eff, 0.f, 0.f, 0.f, 1.f, p.margin, false, acc_c);
+            } else {
+              group_all<false, RBF, false>(v, ncols, t_eff, tm, zref2, scale2, p.scale, p.margin, round_scaled, acc);
+              group_all<true, false, false>(vc, ncols, mon_tc_eff, 0.f, 0.f, 0.f, 1.f, p.margin, false, acc_c);
+            }
+          }
         }
         if (late_read) {
           tc_fence_before();
@@ -722,6 +757,17 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (row_ok) {
           float* ds = p.part_s + (((size_t)slot * CG + cg) * BM + r_local) * NSCAL;
           *reinterpret_cast<float4*>(ds) = make_float4(cnt, sum_a, sum_w, 0.f);
+        }
+        if (MON && row_ok) {
+          const size_t off = (((size_t)slot * CG + cg) * BM + r_local) * NSCAL_ALL;
+          float4* dd = reinterpret_cast<float4*>(p.part_all + off);
+          dd[0] = make_float4(acc.cnt, acc.s_exp, acc.s_sp, acc.s_hinge);
+          dd[1] = make_float4(acc.s_logi, acc.s_contr, acc.s_v, acc.s_sq);
+          dd[2] = make_float4(acc.vmin, acc.vmax, 0.f, 0.f);
+          float4* dc = reinterpret_cast<float4*>(p.part_all_cos + off);
+          dc[0] = make_float4(acc_c.cnt, 0.f, 0.f, 0.f);
+          dc[1] = make_float4(0.f, acc_c.s_contr, 0.f, 0.f);
+          dc[2] = make_float4(CUDART_INF_F, -CUDART_INF_F, 0.f, 0.f);
         }
       }
       tt += T;
@@ -1176,6 +1222,27 @@ static int launch_fused1(const CUtensorMap& tq, const CUtensorMap& tb, const Fus
   XR_LAUNCH_CHECK("fused_pool_kernel");
   return XR_OK;
 }
+// train kernel that also accumulates the monitoring sums of both logit families (InfoNCE train loss)
+template <bool RBF>
+static int launch_fused_mon1(const CUtensorMap& tq, const CUtensorMap& tb, const FusedParams& p, int grid,
+                             cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    XR_CUDA(cudaFuncSetAttribute(fused_pool_kernel<XR_LOSS_INFONCE, RBF, 0, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, fk::SMEM_BYTES));
+    configured = true;
+  }
+  FusedParams pp = p;
+  pp.ctrl_low = g_ctrl_low;
+  fused_pool_kernel<XR_LOSS_INFONCE, RBF, 0, true><<<grid, fk::THREADS, fk::SMEM_BYTES, s>>>(tq, tb, pp);
+  XR_LAUNCH_CHECK("fused_pool_kernel<MON>");
+  return XR_OK;
+}
+static int launch_fused_mon(const CUtensorMap& tq, const CUtensorMap& tb, const FusedParams& p, int grid,
+                            cudaStream_t s) {
+  return p.logits_bf16 ? launch_fused_mon1<true>(tq, tb, p, grid, s) : launch_fused_mon1<false>(tq, tb, p, grid, s);
+}
+
 template <int KIND>
 static int launch_fused(const CUtensorMap& tq, const CUtensorMap& tb, const FusedParams& p,
                         int grid, cudaStream_t s) {
@@ -1228,6 +1295,48 @@ extern "C" size_t xr_fused_pool_workspace_bytes(int64_t m, int64_t cn, int64_t d
 // shape (m, cn) is exact; otherwise (m, cn) are upper bounds that size tensor maps and grids and
 // the kernels read the real shape and plan from ws.dyn (written by fused_plan_kernel earlier on
 // the same stream).
+// one-pass monitoring (xr_pool_step_compute_mon): the train kernel also accumulates the sums behind every
+// loss of both logit families and LogitsStatistics; these are the extra buffers and outputs
+struct MonArgs {
+  float *part_dot, *part_cos;     // [slots][CG][128][NSCAL_ALL] each
+  float *inv_q, *inv_n, *t_cos;   // [n_pos], [n_pos + 64], [n_pos]
+  double* row_out;                // [n_pos][ROW_SLOTS] + the reduction's scratch
+  double *losses_dot, *losses_cos, *stats;
+  long long n_pos;
+};
+
+// inverse row norms for the cosine family of a MON launch (losses.py:206-208: norms clamped at eps), the same
+// summation order as xr_normalize_rows.  job 0: row r of q and pos -> inv_q[r], t_cos[r] = (t[r] inv_q) inv_pos;
+// job 1: row r of neg -> inv_n[r].  Warp per row, rows up to the device-side counts.
+__global__ void __launch_bounds__(256)
+mon_inv_norms_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ pos,
+                     const __nv_bfloat16* __restrict__ neg, const float* __restrict__ t, long long m, long long cn,
+                     const FusedDyn* __restrict__ dyn, float eps, float* __restrict__ inv_q,
+                     float* __restrict__ inv_n, float* __restrict__ t_cos) {
+  if (dyn) {
+    m = dyn->m;
+    cn = dyn->cn;
+  }
+  const int job = blockIdx.y;
+  const long long rows = job == 0 ? m : cn;
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    if (job == 0) {
+      const float iq = normalize_row384_bf16(q + r * fk::D, nullptr, eps, lane);
+      const float ip = normalize_row384_bf16(pos + r * fk::D, nullptr, eps, lane);
+      if (lane == 0) {
+        inv_q[r] = iq;
+        t_cos[r] = __fmul_rn(__fmul_rn(t[r], iq), ip);
+      }
+    } else {
+      const float in = normalize_row384_bf16(neg + r * fk::D, nullptr, eps, lane);
+      if (lane == 0) inv_n[r] = in;
+    }
+  }
+}
+
 struct StepScatter {   // xr_pool_step: write dL/dtok straight into the (n_pos, D) layout
   const int64_t* inv_pos;
   const int64_t* sel_pos;
@@ -1239,7 +1348,7 @@ static int fused_launch_all(const void* q, const void* pos, const void* neg, lon
                             long long cn, int loss_kind, const xr_loss_config* cfg,
                             const float* q_inv_norm, float grad_scale, float* dq, double* loss_out,
                             float* row_loss, const FusedWs& ws, bool dynamic, cudaStream_t s,
-                            const StepScatter* sc = nullptr) {
+                            const StepScatter* sc = nullptr, const MonArgs* mon = nullptr) {
   const int n_sm = sm_count();
   const FusedPlan pl = make_plan(m, cn, n_sm);
   const FusedDyn* dyn_main = dynamic ? ws.dyn : nullptr;
@@ -1271,6 +1380,14 @@ static int fused_launch_all(const void* q, const void* pos, const void* neg, lon
     XR_LAUNCH_CHECK("zref_bound");
     zref = ws.zref;
   }
+  if (mon) {   // inverse norms + cosine targets (needs the diagonal pass above)
+    long long gx = (m * 32 + 255) / 256;
+    if (gx > (long long)n_sm * 4) gx = (long long)n_sm * 4;
+    mon_inv_norms_kernel<<<dim3((unsigned)gx, 2), 256, 0, s>>>(
+        (const __nv_bfloat16*)q, (const __nv_bfloat16*)pos, (const __nv_bfloat16*)neg, ws.t, m, cn, dyn_main, 1e-8f,
+        mon->inv_q, mon->inv_n, mon->t_cos);
+    XR_LAUNCH_CHECK("mon_inv_norms");
+  }
 
   FusedParams p{};
   p.dyn = dyn_main;
@@ -1278,6 +1395,10 @@ static int fused_launch_all(const void* q, const void* pos, const void* neg, lon
   p.mask_fn = cfg->mask_false_negatives; p.logits_bf16 = cfg->logits_bf16;
   p.with_grad = dq != nullptr || (sc && sc->dtok); p.scale = cfg->scale; p.margin = cfg->margin;
   p.t = ws.t; p.zref = zref; p.part_o = ws.part_o; p.part_s = ws.part_s; p.hang_flag = ws.flags;
+  if (mon) {
+    p.part_all = mon->part_dot; p.part_all_cos = mon->part_cos;
+    p.mon_inv_q = mon->inv_q; p.mon_inv_n = mon->inv_n; p.mon_t_cos = mon->t_cos;
+  }
   // dynamic: the tile count is only known on the device; surplus CTAs get an empty range and exit.
   // The finalize kernels derive the segments of a row block from (m, cn, grid) exactly as the kernel does.
   const int grid = dynamic ? n_sm : pl.grid;
@@ -1285,6 +1406,10 @@ static int fused_launch_all(const void* q, const void* pos, const void* neg, lon
   if (prof) cudaEventRecord(g_prof_ev[g_prof_n][0], s);
   switch (loss_kind) {
     case XR_LOSS_INFONCE:
+      if (mon) {
+        rc = launch_fused_mon(tq, tn, p, grid, s);
+        break;
+      }
       if (g_wait_stats || g_ablate || g_timeline) {   // profiling aid
         if (!g_dbg_dev) XR_CUDA(cudaMalloc(&g_dbg_dev, sizeof(g_dbg_host)));
         p.dbg = g_dbg_dev;
@@ -1314,6 +1439,25 @@ static int fused_launch_all(const void* q, const void* pos, const void* neg, lon
   // loss_out[1] (if the caller left room) receives the fp32 copy the loss module returns
   sum_rows_kernel<<<1, 1024, 0, s>>>(rl, m, loss_out, reinterpret_cast<float*>(loss_out + 1), dyn_main);
   XR_LAUNCH_CHECK("sum_rows");
+  if (mon) {
+    // the monitoring sums -> the row slots rowloss_kernel produces -> losses[7] / stats[16], one family after
+    // the other through the same row buffer (stream order)
+    double* scratch = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(mon->row_out) +
+                                                align256((size_t)mon->n_pos * ROW_SLOTS * 8));
+    const int fblocks = (int)((m + 255) / 256);
+    fused_finalize_all_kernel<<<fblocks, 256, 0, s>>>(mon->part_dot, ws.t, zref, (int)m, (int)cn, grid, 0,
+                                                      cfg->logits_bf16, cfg->scale, cfg->margin, mon->row_out, dyn_main);
+    XR_LAUNCH_CHECK("fused_finalize_all");
+    if ((rc = launch_rowloss_reduce(mon->row_out, m, cn + 1, 0, mon->losses_dot, mon->stats, s,
+                                    reinterpret_cast<const int*>(dyn_main), scratch)))
+      return rc;
+    fused_finalize_all_kernel<<<fblocks, 256, 0, s>>>(mon->part_cos, mon->t_cos, nullptr, (int)m, (int)cn, grid, 1,
+                                                      0, cfg->scale, cfg->margin, mon->row_out, dyn_main);
+    XR_LAUNCH_CHECK("fused_finalize_all");
+    if ((rc = launch_rowloss_reduce(mon->row_out, m, cn + 1, 0, mon->losses_cos, nullptr, s,
+                                    reinterpret_cast<const int*>(dyn_main), scratch)))
+      return rc;
+  }
   if (g_wait_stats || g_timeline) {
     XR_CUDA(cudaMemcpyAsync(g_wait_host, ws.flags + 16, sizeof(g_wait_host), cudaMemcpyDeviceToHost, s));
     if (g_dbg_dev) XR_CUDA(cudaMemcpyAsync(g_dbg_host, g_dbg_dev, sizeof(g_dbg_host), cudaMemcpyDeviceToHost, s));
@@ -1588,6 +1732,7 @@ struct MonitorWs {
   __nv_bfloat16 *qn, *pn, *nn;
   float *inv, *inv_q;   // inv: scratch for pos / neg norms; inv_q: 1/||q|| kept for the cosine chain rule
   double* row_out;
+  float *part_dot, *part_cos, *inv_n, *t_cos;   // one-pass monitoring (xr_pool_step_compute_mon)
   size_t bytes;
 };
 static MonitorWs carve_monitor_ws(void* base, long long n_pos) {
@@ -1600,6 +1745,11 @@ static MonitorWs carve_monitor_ws(void* base, long long n_pos) {
   w.inv = (float*)p;          p += align256(n * 4);
   w.inv_q = (float*)p;        p += align256(n * 4);
   w.row_out = (double*)p;     p += align256(n * ROW_SLOTS * 8) + kRowlossPartialBytes;
+  const size_t part = align256((size_t)max_plan_slots(n_pos, sm_count_max()) * fk::CG * fk::BM * fk::NSCAL_ALL * 4);
+  w.part_dot = (float*)p;     p += part;
+  w.part_cos = (float*)p;     p += part;
+  w.inv_n = (float*)p;        p += align256((n + 64) * 4);
+  w.t_cos = (float*)p;        p += align256(n * 4);
   w.bytes = (size_t)(p - (uint8_t*)base);
   return w;
 }
@@ -1746,6 +1896,35 @@ extern "C" int xr_pool_step_monitor(int64_t n_pos, int64_t dim, const xr_loss_co
   ccfg.logits_bf16 = 0;   // cosine logits stay fp32 under autocast
   return fused_all_launch(mw.qn, mw.pn, mw.nn, n_pos, n_pos, 1, &ccfg, w.fused, true, mw.row_out,
                           losses_cos, nullptr, s);
+}
+
+// The compute phase WITH the monitoring folded into the train kernel: one tensor-core pass produces the train
+// loss, dL/dtok and the sums behind all seven losses + LogitsStatistics (the dot family from the scores, the
+// cosine family from the same scores times fp32 inverse norms) -- instead of the train pass plus the two
+// all-losses passes of xr_pool_step_monitor.  InfoNCE train loss only (the trainer's default); the dot-family
+// numbers are bit-identical to xr_pool_step_monitor's, the cosine family agrees to bf16 tolerance (it no
+// longer rounds the normalised operands to bf16).
+extern "C" int xr_pool_step_compute_mon(int64_t n_pos, int64_t dim, int loss_kind, const xr_loss_config* cfg,
+                                        float grad_scale, void* dtok, int dtok_dtype, double* loss_out,
+                                        double* losses_dot, double* losses_cos, double* stats_out,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  XR_CHECK_ARG(cfg && loss_out && losses_dot && losses_cos && stats_out && workspace,
+               "xr_pool_step_compute_mon: null pointer");
+  XR_CHECK_ARG(dim == fk::D && n_pos > 0 && n_pos < (1ll << 30), "xr_pool_step_compute_mon: bad sizes");
+  XR_CHECK_ARG(loss_kind == XR_LOSS_INFONCE && cfg->num_hard_negatives == 0 && cfg->scale > 0.f,
+               "xr_pool_step_compute_mon: serves the InfoNCE train loss with scale > 0 and no hard-negative mining");
+  XR_CHECK_ARG(!dtok || dtok_dtype == XR_F32 || dtok_dtype == XR_BF16, "xr_pool_step_compute_mon: dtok must be fp32 or bf16");
+  XR_CHECK_ARG(workspace_bytes >= xr_pool_step_monitor_workspace_bytes(n_pos, dim) && (uintptr_t)workspace % 256 == 0,
+               "xr_pool_step_compute_mon: workspace too small or misaligned");
+  int rc;
+  if ((rc = check_fused_device("xr_pool_step_compute_mon"))) return rc;
+  const StepWs w = carve_step_ws(workspace, n_pos);
+  const MonitorWs mw = carve_monitor_ws((uint8_t*)workspace + w.bytes, n_pos);
+  const StepScatter sc{w.inv_pos, w.sel_pos, n_pos, dtok, dtok_dtype == XR_BF16};
+  const MonArgs mon{mw.part_dot, mw.part_cos, mw.inv_q, mw.inv_n, mw.t_cos, mw.row_out,
+                    losses_dot, losses_cos, stats_out, n_pos};
+  return fused_launch_all(w.q, w.pos, w.neg, n_pos, n_pos, loss_kind, cfg, nullptr, grad_scale, nullptr, loss_out,
+                          nullptr, w.fused, true, as_stream(stream), dtok ? &sc : nullptr, &mon);
 }
 
 // ---- retrieval: group maxima of Q . Cat^T on the tensor cores -----------------------------------

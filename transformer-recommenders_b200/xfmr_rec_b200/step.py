@@ -40,7 +40,7 @@ class PoolLossStep:
                  token_dtype: torch.dtype = torch.bfloat16, grad_dtype: torch.dtype | None = None,
                  want_grad: bool = True, logits_bf16: bool | None = None, use_graph: bool = True,
                  check_indices: bool = False, monitor: bool = False, pipelined: bool = False,
-                 host_tokens_in_place: bool = False) -> None:
+                 host_tokens_in_place: bool = False, monitor_one_pass: bool = True) -> None:
         name = type(loss).__name__
         if name not in _STEP_KINDS:
             raise NotImplementedError(
@@ -89,6 +89,9 @@ class PoolLossStep:
                       else N.lib().xr_pool_step_workspace_bytes(n, self.d))
             # monitor: LogitsStatistics + all seven losses (trainer.py:250-263) in the same sequence
             self.monitor = bool(monitor)
+            # one tensor-core pass for the train loss, its gradient AND the monitoring sums of both logit
+            # families (xr_pool_step_compute_mon) instead of three; the InfoNCE train loss only
+            self.monitor_one_pass = bool(monitor and monitor_one_pass and name == "InfoNCELoss" and cfg.scale > 0)
             self.mon_dot = torch.zeros(N.XR_NUM_LOSSES, dtype=torch.float64, device=dev)
             self.mon_cos = torch.zeros(N.XR_NUM_LOSSES, dtype=torch.float64, device=dev)
             self.mon_stats = torch.zeros(N.XR_STATS_SLOTS, dtype=torch.float64, device=dev)
@@ -118,7 +121,17 @@ class PoolLossStep:
             self._capture()
 
     # ------------------------------------------------------------------------------------------
+    def _launch_compute_mon(self) -> None:
+        N.call("xr_pool_step_compute_mon", self.n_pos, self.d, self.kind, C.byref(self.cfg), 1.0,
+               ops._p(self.dtok), ops._DT[self.dtok.dtype] if self.dtok is not None else N.XR_F32,
+               ops._p(self.loss_buf), ops._p(self.mon_dot), ops._p(self.mon_cos), ops._p(self.mon_stats),
+               C.c_void_p(self._ws_ptr), self._ws_bytes, ops._stream())
+
     def _launch(self) -> None:
+        if self.monitor_one_pass:
+            self._launch_ingest()
+            self._launch_compute_mon()
+            return
         N.call("xr_pool_step", ops._p(self.hist), ops._p(self.pos), ops._p(self.neg), self.n_pos,
                ops._p(self.tok), ops._DT[self.tok.dtype], ops._p(self.table), ops._p(self.rownz),
                self.n_table_rows, self.d, self.kind, C.byref(self.cfg), 1.0, ops._p(self.dtok),
@@ -138,6 +151,9 @@ class PoolLossStep:
                C.c_void_p(self._ws_ptr), self._ws_bytes, ops._stream())
 
     def _launch_compute(self) -> None:
+        if self.monitor_one_pass:
+            self._launch_compute_mon()
+            return
         N.call("xr_pool_step_compute", self.n_pos, self.d, self.kind, C.byref(self.cfg), 1.0,
                ops._p(self.dtok), ops._DT[self.dtok.dtype] if self.dtok is not None else N.XR_F32,
                ops._p(self.loss_buf), C.c_void_p(self._ws_ptr), self._ws_bytes, ops._stream())
