@@ -205,42 +205,75 @@ template <bool COS, bool RBF, bool FULL>
 __device__ __forceinline__ void group_all(const uint32_t (&v)[16], int ncols, float t_eff, float tm,
                                           float zref2, float scale2, float scale, float margin,
                                           bool round_scaled, AllAcc& a) {
-  float prod_nce = 1.f, prod_logi = 1.f, relu_nce = 0.f;
+  // masked-out logits are replaced by a huge negative value ONCE, after which every term below
+  // vanishes by itself (2^-huge = 0, relu(-huge) = 0, 1 + 0 = 1): this epilogue is bound by issue
+  // slots (ncu: 79 % issue-active), so the per-term selects this saves are what matters.  The sums run on
+  // PAIRS of logits with the packed fp32x2 instructions of sm_100 (add / mul / fma on two floats per issue
+  // slot; each half rounds exactly as the scalar instruction does); selects, min / max and MUFU stay scalar.
+  constexpr float kDead = -1.0e30f;
+  if (COS) {   // LogitsStatistics is defined on the dot logits (losses.py:383-386): no neg stats here
+    float2 contr = make_float2(0.f, 0.f);
+    const float2 shift = make_float2(margin - 1.0f, margin - 1.0f);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    float l = __uint_as_float(v[j]);
-    if (RBF) l = bf16_round(l);
-    bool ok = l < t_eff;
-    if (!FULL) ok = ok && (j < ncols);
-    // masked-out logits are replaced by a huge negative value ONCE, after which every term below
-    // vanishes by itself (2^-huge = 0, relu(-huge) = 0, 1 + 0 = 1): this epilogue is bound by issue
-    // slots (ncu: 79 % issue-active), so the eight per-term selects this saves are what matters
-    constexpr float kDead = -1.0e30f;
-    const float le = ok ? l : kDead;
-    a.cnt += ok ? 1.f : 0.f;
-    if (COS) {   // LogitsStatistics is defined on the dot logits (losses.py:383-386): no neg stats here
-      a.s_contr += fmaxf(le - 1.0f + margin, 0.f);
-    } else {
-      const float lm = ok ? l : 0.f;
-      a.s_v += lm;
-      a.s_sq = fmaf(lm, lm, a.s_sq);
-      a.vmin = fminf(a.vmin, ok ? l : CUDART_INF_F);
-      a.vmax = fmaxf(a.vmax, le);
-      float z2;
-      if (round_scaled) z2 = bf16_round(le * scale) * kLog2e;
-      else z2 = le * scale2;
-      a.s_exp += ex2f(z2 - zref2);
-      prod_nce *= 1.0f + ex2f(-fabsf(le) * kLog2e);
-      relu_nce += fmaxf(le, 0.f);
-      const float x = le - tm;
-      prod_logi *= 1.0f + ex2f(-fabsf(x) * kLog2e);
-      a.s_hinge += fmaxf(x, 0.f);
+    for (int j = 0; j < 16; j += 2) {
+      const float l0 = __uint_as_float(v[j]), l1 = __uint_as_float(v[j + 1]);
+      bool ok0 = l0 < t_eff, ok1 = l1 < t_eff;
+      if (!FULL) {
+        ok0 = ok0 && (j < ncols);
+        ok1 = ok1 && (j + 1 < ncols);
+      }
+      a.cnt += ok0 ? 1.f : 0.f;
+      a.cnt += ok1 ? 1.f : 0.f;
+      const float2 x = __fadd2_rn(make_float2(ok0 ? l0 : kDead, ok1 ? l1 : kDead), shift);
+      contr = __fadd2_rn(contr, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
     }
+    a.s_contr += contr.x + contr.y;
+    return;
   }
-  if (!COS) {
-    a.s_sp += relu_nce + lg2f(prod_nce) * kLn2;
-    a.s_logi += lg2f(prod_logi) * kLn2;   // + s_hinge (the relu part) in the finalize
+  float2 prod_nce = make_float2(1.f, 1.f), prod_logi = make_float2(1.f, 1.f), relu_nce = make_float2(0.f, 0.f);
+  float2 sv = make_float2(0.f, 0.f), ssq = make_float2(0.f, 0.f), sexp = make_float2(0.f, 0.f);
+  float2 shinge = make_float2(0.f, 0.f);
+  const float2 one2 = make_float2(1.f, 1.f), sc2 = make_float2(scale2, scale2), nz2 = make_float2(-zref2, -zref2);
+  const float2 ntm2 = make_float2(-tm, -tm);
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) {
+    float l0 = __uint_as_float(v[j]), l1 = __uint_as_float(v[j + 1]);
+    if (RBF) {   // autocast: the bmm output is bf16 (losses.py:195 under trainer.py:450)
+      const __nv_bfloat162 h = __floats2bfloat162_rn(l0, l1);
+      const uint32_t u = *reinterpret_cast<const uint32_t*>(&h);
+      l0 = __uint_as_float(u << 16);
+      l1 = __uint_as_float(u & 0xFFFF0000u);
+    }
+    bool ok0 = l0 < t_eff, ok1 = l1 < t_eff;
+    if (!FULL) {
+      ok0 = ok0 && (j < ncols);
+      ok1 = ok1 && (j + 1 < ncols);
+    }
+    const float2 le = make_float2(ok0 ? l0 : kDead, ok1 ? l1 : kDead);
+    a.cnt += ok0 ? 1.f : 0.f;
+    a.cnt += ok1 ? 1.f : 0.f;
+    const float2 lm = make_float2(ok0 ? l0 : 0.f, ok1 ? l1 : 0.f);
+    sv = __fadd2_rn(sv, lm);
+    ssq = __ffma2_rn(lm, lm, ssq);
+    a.vmin = fminf(a.vmin, fminf(ok0 ? l0 : CUDART_INF_F, ok1 ? l1 : CUDART_INF_F));
+    a.vmax = fmaxf(a.vmax, fmaxf(le.x, le.y));
+    float2 z;
+    if (round_scaled) z = __fadd2_rn(make_float2(bf16_round(le.x * scale) * kLog2e, bf16_round(le.y * scale) * kLog2e), nz2);
+    else z = __ffma2_rn(le, sc2, nz2);
+    sexp = __fadd2_rn(sexp, make_float2(ex2f(z.x), ex2f(z.y)));
+    prod_nce = __fmul2_rn(prod_nce, __fadd2_rn(one2, make_float2(ex2f(-fabsf(le.x) * kLog2e), ex2f(-fabsf(le.y) * kLog2e))));
+    relu_nce = __fadd2_rn(relu_nce, make_float2(fmaxf(le.x, 0.f), fmaxf(le.y, 0.f)));
+    const float2 x = __fadd2_rn(le, ntm2);
+    prod_logi = __fmul2_rn(prod_logi, __fadd2_rn(one2, make_float2(ex2f(-fabsf(x.x) * kLog2e), ex2f(-fabsf(x.y) * kLog2e))));
+    shinge = __fadd2_rn(shinge, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
   }
+  a.s_v += sv.x + sv.y;
+  a.s_sq += ssq.x + ssq.y;
+  a.s_exp += sexp.x + sexp.y;
+  a.s_hinge += shinge.x + shinge.y;
+  // the two half-products are <= 2^8 each: their product stays far inside fp32 range
+  a.s_sp += (relu_nce.x + relu_nce.y) + lg2f(prod_nce.x * prod_nce.y) * kLn2;
+  a.s_logi += lg2f(prod_logi.x * prod_logi.y) * kLn2;   // + s_hinge (the relu part) in the finalize
 }
 
 template <int KIND, bool RBF, int DBG, bool MON = false>
