@@ -201,7 +201,7 @@ struct AllAcc {
 // one column group (16 logits of one row) for the ALL kinds.  softplus(x) = relu(x) + ln(1 + e^-|x|);
 // the 16 factors (1 + e^-|x|) lie in (1, 2], so their PRODUCT (<= 65536) is taken first and one
 // lg2 per group replaces sixteen (the MUFU unit bounds this epilogue).
-template <bool COS, bool RBF, bool FULL>
+template <bool COS, bool RBF, bool FULL, bool WITH_EXP = true>
 __device__ __forceinline__ void group_all(const uint32_t (&v)[16], int ncols, float t_eff, float tm,
                                           float zref2, float scale2, float scale, float margin,
                                           bool round_scaled, AllAcc& a) {
@@ -257,10 +257,12 @@ __device__ __forceinline__ void group_all(const uint32_t (&v)[16], int ncols, fl
     ssq = __ffma2_rn(lm, lm, ssq);
     a.vmin = fminf(a.vmin, fminf(ok0 ? l0 : CUDART_INF_F, ok1 ? l1 : CUDART_INF_F));
     a.vmax = fmaxf(a.vmax, fmaxf(le.x, le.y));
-    float2 z;
-    if (round_scaled) z = __fadd2_rn(make_float2(bf16_round(le.x * scale) * kLog2e, bf16_round(le.y * scale) * kLog2e), nz2);
-    else z = __ffma2_rn(le, sc2, nz2);
-    sexp = __fadd2_rn(sexp, make_float2(ex2f(z.x), ex2f(z.y)));
+    if (WITH_EXP) {   // (a MON train launch takes the softmax sum from the train epilogue's own weights)
+      float2 z;
+      if (round_scaled) z = __fadd2_rn(make_float2(bf16_round(le.x * scale) * kLog2e, bf16_round(le.y * scale) * kLog2e), nz2);
+      else z = __ffma2_rn(le, sc2, nz2);
+      sexp = __fadd2_rn(sexp, make_float2(ex2f(z.x), ex2f(z.y)));
+    }
     prod_nce = __fmul2_rn(prod_nce, __fadd2_rn(one2, make_float2(ex2f(-fabsf(le.x) * kLog2e), ex2f(-fabsf(le.y) * kLog2e))));
     relu_nce = __fadd2_rn(relu_nce, make_float2(fmaxf(le.x, 0.f), fmaxf(le.y, 0.f)));
     const float2 x = __fadd2_rn(le, ntm2);
@@ -733,10 +735,10 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
               vc[4 * jj + 3] = __float_as_uint(__fmul_rn(__fmul_rn(__uint_as_float(v[4 * jj + 3]), mon_iq), w4.w));
             }
             if (ncols >= 16) {
-              group_all<false, RBF, true>(v, ncols, t_eff, tm, zref2, scale2, p.scale, p.margin, round_scaled, acc);
+              group_all<false, RBF, true, false>(v, ncols, t_eff, tm, zref2, scale2, p.scale, p.margin, round_scaled, acc);
               group_all<true, false, true>(vc, ncols, mon_tc_eff, 0.f, 0.f, 0.f, 1.f, p.margin, false, acc_c);
             } else {
-              group_all<false, RBF, false>(v, ncols, t_eff, tm, zref2, scale2, p.scale, p.margin, round_scaled, acc);
+              group_all<false, RBF, false, false>(v, ncols, t_eff, tm, zref2, scale2, p.scale, p.margin, round_scaled, acc);
               group_all<true, false, false>(vc, ncols, mon_tc_eff, 0.f, 0.f, 0.f, 1.f, p.margin, false, acc_c);
             }
           }
@@ -794,7 +796,8 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (MON && row_ok) {
           const size_t off = (((size_t)slot * CG + cg) * BM + r_local) * NSCAL_ALL;
           float4* dd = reinterpret_cast<float4*>(p.part_all + off);
-          dd[0] = make_float4(acc.cnt, acc.s_exp, acc.s_sp, acc.s_hinge);
+          // InfoNCE's softmax sum IS the train epilogue's sum of weights (same exponentials, same mask)
+          dd[0] = make_float4(acc.cnt, sum_w, acc.s_sp, acc.s_hinge);
           dd[1] = make_float4(acc.s_logi, acc.s_contr, acc.s_v, acc.s_sq);
           dd[2] = make_float4(acc.vmin, acc.vmax, 0.f, 0.f);
           float4* dc = reinterpret_cast<float4*>(p.part_all_cos + off);
