@@ -53,6 +53,9 @@ enum RowSlot {
 constexpr size_t kRowlossPartialBytes = 16384;   // scratch of the two-launch row-slot reduction
 int launch_rowloss_reduce(const double* row_out, int64_t m, int64_t c, int n_hard, double* losses_out,
                           double* stats_out, cudaStream_t s, const int* dyn_m_cn, double* partial);
+int launch_rowloss_reduce2(const double* row_out, const double* row_out2, int64_t m, int64_t c, double* losses_out,
+                           double* stats_out, double* losses_out2, cudaStream_t s, const int* dyn_m_cn,
+                           double* partial);
 
 // ---- small device helpers --------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

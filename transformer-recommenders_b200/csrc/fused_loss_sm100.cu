@@ -1015,11 +1015,20 @@ __global__ void __launch_bounds__(256)
 fused_finalize_all_kernel(const float* __restrict__ part_all, const float* __restrict__ t_raw,
                           const float* __restrict__ zref, int m, int cn, int grid, int cosine, int logits_bf16,
                           float scale, float margin, double* __restrict__ row_out,
-                          const FusedDyn* __restrict__ dyn) {
+                          const FusedDyn* __restrict__ dyn, const float* __restrict__ part_all2 = nullptr,
+                          const float* __restrict__ t_raw2 = nullptr, double* __restrict__ row_out2 = nullptr) {
   using namespace fk;
   if (dyn) {
     m = dyn->m;
     cn = dyn->cn;
+  }
+  if (blockIdx.y == 1) {   // one-pass monitoring: the cosine family's sums, targets and rows
+    part_all = part_all2;
+    t_raw = t_raw2;
+    zref = nullptr;
+    cosine = 1;
+    logits_bf16 = 0;
+    row_out = row_out2;
   }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
@@ -1336,7 +1345,8 @@ extern "C" size_t xr_fused_pool_workspace_bytes(int64_t m, int64_t cn, int64_t d
 struct MonArgs {
   float *part_dot, *part_cos;     // [slots][CG][128][NSCAL_ALL] each
   float *inv_q, *inv_n, *t_cos;   // [n_pos], [n_pos + 64], [n_pos]
-  double* row_out;                // [n_pos][ROW_SLOTS] + the reduction's scratch
+  double *row_out, *row_out2;     // [n_pos][ROW_SLOTS] per logit family
+  double* scratch;                // 2 x kRowlossPartialBytes: the reductions' partials
   double *losses_dot, *losses_cos, *stats;
   long long n_pos;
 };
@@ -1476,22 +1486,14 @@ static int fused_launch_all(const void* q, const void* pos, const void* neg, lon
   sum_rows_kernel<<<1, 1024, 0, s>>>(rl, m, loss_out, reinterpret_cast<float*>(loss_out + 1), dyn_main);
   XR_LAUNCH_CHECK("sum_rows");
   if (mon) {
-    // the monitoring sums -> the row slots rowloss_kernel produces -> losses[7] / stats[16], one family after
-    // the other through the same row buffer (stream order)
-    double* scratch = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(mon->row_out) +
-                                                align256((size_t)mon->n_pos * ROW_SLOTS * 8));
+    // the monitoring sums of both families -> the row slots rowloss_kernel produces -> losses[7] / stats[16]
     const int fblocks = (int)((m + 255) / 256);
-    fused_finalize_all_kernel<<<fblocks, 256, 0, s>>>(mon->part_dot, ws.t, zref, (int)m, (int)cn, grid, 0,
-                                                      cfg->logits_bf16, cfg->scale, cfg->margin, mon->row_out, dyn_main);
+    fused_finalize_all_kernel<<<dim3(fblocks, 2), 256, 0, s>>>(mon->part_dot, ws.t, zref, (int)m, (int)cn, grid, 0,
+                                                               cfg->logits_bf16, cfg->scale, cfg->margin, mon->row_out,
+                                                               dyn_main, mon->part_cos, mon->t_cos, mon->row_out2);
     XR_LAUNCH_CHECK("fused_finalize_all");
-    if ((rc = launch_rowloss_reduce(mon->row_out, m, cn + 1, 0, mon->losses_dot, mon->stats, s,
-                                    reinterpret_cast<const int*>(dyn_main), scratch)))
-      return rc;
-    fused_finalize_all_kernel<<<fblocks, 256, 0, s>>>(mon->part_cos, mon->t_cos, nullptr, (int)m, (int)cn, grid, 1,
-                                                      0, cfg->scale, cfg->margin, mon->row_out, dyn_main);
-    XR_LAUNCH_CHECK("fused_finalize_all");
-    if ((rc = launch_rowloss_reduce(mon->row_out, m, cn + 1, 0, mon->losses_cos, nullptr, s,
-                                    reinterpret_cast<const int*>(dyn_main), scratch)))
+    if ((rc = launch_rowloss_reduce2(mon->row_out, mon->row_out2, m, cn + 1, mon->losses_dot, mon->stats,
+                                     mon->losses_cos, s, reinterpret_cast<const int*>(dyn_main), mon->scratch)))
       return rc;
   }
   if (g_wait_stats || g_timeline) {
@@ -1769,6 +1771,7 @@ struct MonitorWs {
   float *inv, *inv_q;   // inv: scratch for pos / neg norms; inv_q: 1/||q|| kept for the cosine chain rule
   double* row_out;
   float *part_dot, *part_cos, *inv_n, *t_cos;   // one-pass monitoring (xr_pool_step_compute_mon)
+  double *row_out2, *scratch2;
   size_t bytes;
 };
 static MonitorWs carve_monitor_ws(void* base, long long n_pos) {
@@ -1786,6 +1789,8 @@ static MonitorWs carve_monitor_ws(void* base, long long n_pos) {
   w.part_cos = (float*)p;     p += part;
   w.inv_n = (float*)p;        p += align256((n + 64) * 4);
   w.t_cos = (float*)p;        p += align256(n * 4);
+  w.row_out2 = (double*)p;    p += align256(n * ROW_SLOTS * 8);
+  w.scratch2 = (double*)p;    p += 2 * kRowlossPartialBytes;
   w.bytes = (size_t)(p - (uint8_t*)base);
   return w;
 }
@@ -1957,7 +1962,7 @@ extern "C" int xr_pool_step_compute_mon(int64_t n_pos, int64_t dim, int loss_kin
   const StepWs w = carve_step_ws(workspace, n_pos);
   const MonitorWs mw = carve_monitor_ws((uint8_t*)workspace + w.bytes, n_pos);
   const StepScatter sc{w.inv_pos, w.sel_pos, n_pos, dtok, dtok_dtype == XR_BF16};
-  const MonArgs mon{mw.part_dot, mw.part_cos, mw.inv_q, mw.inv_n, mw.t_cos, mw.row_out,
+  const MonArgs mon{mw.part_dot, mw.part_cos, mw.inv_q, mw.inv_n, mw.t_cos, mw.row_out, mw.row_out2, mw.scratch2,
                     losses_dot, losses_cos, stats_out, n_pos};
   return fused_launch_all(w.q, w.pos, w.neg, n_pos, n_pos, loss_kind, cfg, nullptr, grad_scale, nullptr, loss_out,
                           nullptr, w.fused, true, as_stream(stream), dtok ? &sc : nullptr, &mon);

@@ -50,7 +50,12 @@ constexpr int RR_BLOCKS = 64, RR_THREADS = 256, RR_NS = 13;   // 6 losses + dens
 constexpr int RR_STRIDE = RR_NS + 4;                          // + pos min/max, neg min/max
 __global__ void __launch_bounds__(RR_THREADS)
 rowloss_partial_kernel(const double* __restrict__ row_out, int64_t m, int64_t c, int n_hard,
-                       double* __restrict__ partial, const int* __restrict__ dyn_m_cn) {
+                       double* __restrict__ partial, const int* __restrict__ dyn_m_cn,
+                       const double* __restrict__ row_out2) {
+  if (blockIdx.y == 1) {   // second logit family of a one-pass monitoring launch: its own rows and partials
+    row_out = row_out2;
+    partial += (size_t)RR_BLOCKS * RR_STRIDE;
+  }
   if (dyn_m_cn) {   // shape known only on the device (sync-free step): {rows, pool size}
     m = dyn_m_cn[0];
     c = (int64_t)dyn_m_cn[1] + 1;
@@ -107,7 +112,12 @@ rowloss_partial_kernel(const double* __restrict__ row_out, int64_t m, int64_t c,
 
 __global__ void rowloss_reduce_kernel(const double* __restrict__ partial, int64_t m, int64_t c, int n_hard,
                                       double* __restrict__ losses_out, double* __restrict__ stats_out,
-                                      const int* __restrict__ dyn_m_cn) {
+                                      const int* __restrict__ dyn_m_cn, double* __restrict__ losses_out2) {
+  if (blockIdx.x == 1) {   // second family: losses only
+    partial += (size_t)RR_BLOCKS * RR_STRIDE;
+    losses_out = losses_out2;
+    stats_out = nullptr;
+  }
   if (dyn_m_cn) {
     m = dyn_m_cn[0];
     c = (int64_t)dyn_m_cn[1] + 1;
@@ -156,9 +166,22 @@ __global__ void rowloss_reduce_kernel(const double* __restrict__ partial, int64_
 // `partial`: kRowlossPartialBytes of scratch.
 int launch_rowloss_reduce(const double* row_out, int64_t m, int64_t c, int n_hard, double* losses_out,
                           double* stats_out, cudaStream_t s, const int* dyn_m_cn, double* partial) {
-  rowloss_partial_kernel<<<RR_BLOCKS, RR_THREADS, 0, s>>>(row_out, m, c, n_hard, partial, dyn_m_cn);
+  rowloss_partial_kernel<<<RR_BLOCKS, RR_THREADS, 0, s>>>(row_out, m, c, n_hard, partial, dyn_m_cn, nullptr);
   XR_LAUNCH_CHECK("rowloss_partial");
-  rowloss_reduce_kernel<<<1, 32, 0, s>>>(partial, m, c, n_hard, losses_out, stats_out, dyn_m_cn);
+  rowloss_reduce_kernel<<<1, 32, 0, s>>>(partial, m, c, n_hard, losses_out, stats_out, dyn_m_cn, nullptr);
+  XR_LAUNCH_CHECK("rowloss_reduce");
+  return XR_OK;
+}
+
+// two logit families at once (one-pass monitoring): row_out / losses_out + stats of the first, row_out2 /
+// losses_out2 of the second; `partial` holds both families' partials (2 * RR_BLOCKS * RR_STRIDE doubles)
+int launch_rowloss_reduce2(const double* row_out, const double* row_out2, int64_t m, int64_t c, double* losses_out,
+                           double* stats_out, double* losses_out2, cudaStream_t s, const int* dyn_m_cn,
+                           double* partial) {
+  static_assert(2 * RR_BLOCKS * RR_STRIDE * sizeof(double) <= kRowlossPartialBytes * 2, "scratch");
+  rowloss_partial_kernel<<<dim3(RR_BLOCKS, 2), RR_THREADS, 0, s>>>(row_out, m, c, 0, partial, dyn_m_cn, row_out2);
+  XR_LAUNCH_CHECK("rowloss_partial");
+  rowloss_reduce_kernel<<<2, 32, 0, s>>>(partial, m, c, 0, losses_out, stats_out, dyn_m_cn, losses_out2);
   XR_LAUNCH_CHECK("rowloss_reduce");
   return XR_OK;
 }
