@@ -519,10 +519,12 @@ def main():
         "loss": loss_val,
         "per_rank_region_ms": per_rank or None,
         "compute_losses": {"value": world * BATCH / (mon_ms / 1e3), "unit": "seq/s", "ms_per_step": mon_ms,
-                           "gpu_launches_per_step": 20,
+                           "gpu_launches_per_step": 11,
                            "note": "PoolLossStep(monitor=True): the step above PLUS LogitsStatistics and all "
-                                   "seven losses (what trainer.py:250-263 logs every step) in the same graph "
-                                   "replay; L2 flushed between steps",
+                                   "seven losses (what trainer.py:250-263 logs every step) from the SAME "
+                                   "tensor-core pass (xr_pool_step_compute_mon: the train kernel accumulates "
+                                   "the monitoring sums of both logit families), one graph replay; L2 flushed "
+                                   "between steps",
                            "losses": {k: float(v) for k, v in mon_losses.items()}},
         "module_api": {"value": world * BATCH / (mod_ms / mod_steps / 1e3), "unit": "seq/s",
                        "ms_per_step": mod_ms / mod_steps,

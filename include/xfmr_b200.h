@@ -229,6 +229,14 @@ int xr_pool_step_compute_mon(int64_t n_pos, int64_t dim, int loss_kind, const xr
                              float grad_scale, void* dtok, int dtok_dtype, double* loss_out, double* losses_dot,
                              double* losses_cos, double* stats_out, void* workspace, size_t workspace_bytes,
                              void* stream);
+/* The same one-pass evaluation for exact shapes (the module path of trainer.py:213-264, compute_losses):
+ * InfoNCE loss (loss_out[0], fp32 copy in the low half of loss_out[1]) and dq (m, dim) fp32 (nullable),
+ * losses_dot[7], losses_cos[7], stats[16] from ONE tensor-core pass.  bf16 operands, dim 384.            */
+size_t xr_fused_pool_loss_mon_workspace_bytes(int64_t m, int64_t cn, int64_t dim);
+int xr_fused_pool_loss_mon(const void* q, const void* pos, const void* neg, int64_t m, int64_t cn, int64_t dim,
+                           const xr_loss_config* cfg, float grad_scale, float* dq, double* loss_out,
+                           double* losses_dot, double* losses_cos, double* stats_out, void* workspace,
+                           size_t workspace_bytes, void* stream);
 
 /* ---- SeqBatch construction (the step right before the path) ---------------
  * SeqDataset.__getitem__ + collate (data.py:669-805) for a whole batch in one launch:

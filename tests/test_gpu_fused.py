@@ -388,9 +388,12 @@ def test_fused_all_losses_and_stats_one_pass(xr, m, cn):
                 np.testing.assert_allclose(stats[[9, 10]], s2[[9, 10]], rtol=1e-3, atol=2e-3)
 
 
-def test_evaluate_all_uses_two_passes_and_matches_modules(xr):
+def test_evaluate_all_matches_modules(xr):
     """evaluate_all (= compute_losses, trainer.py:213-264): same numbers as the seven loss modules
-    and LogitsStatistics called one by one."""
+    and LogitsStatistics called one by one.  With a gradient wanted it is ONE tensor-core pass
+    (xr_fused_pool_loss_mon: train loss + dq + both families + statistics); without, one forward pass per
+    family -- the dot family and the statistics agree between the two to fp32 summation order, the cosine
+    family to bf16 tolerance; loss value and gradient are those of the InfoNCE module bit for bit."""
     q, pos, neg = make_inputs(300, 1000, seed=11)
     cfg = xr.LossConfig()
     qt = bf(q).requires_grad_(True)
@@ -398,6 +401,17 @@ def test_evaluate_all_uses_two_passes_and_matches_modules(xr):
     out, stats = xr.losses.evaluate_all(cfg, qt, cand)
     out["loss/InfoNCELoss"].backward()
     assert qt.grad is not None and bool(torch.isfinite(qt.grad).all())
+    q2 = bf(q).requires_grad_(True)
+    l2 = xr.InfoNCELoss(cfg)(q2, cand)
+    l2.backward()
+    assert torch.equal(out["loss/InfoNCELoss"].detach(), l2.detach()) and torch.equal(qt.grad, q2.grad)
+    with torch.no_grad():
+        out_ng, stats_ng = xr.losses.evaluate_all(cfg, bf(q), cand)
+    for k, v in out_ng.items():
+        tol = 4e-3 if k.split("/")[1] in orc.COSINE_LOSSES else 1e-6
+        assert float(out[k]) == pytest.approx(float(v), rel=tol, abs=tol), k
+    for k, v in stats_ng.items():
+        assert stats[k] == pytest.approx(v, rel=1e-6, abs=1e-9), k
     for name in orc.LOSS_NAMES:
         want = float(getattr(xr, name)(cfg)(bf(q), cand))
         assert float(out[f"loss/{name}"]) == pytest.approx(want, rel=2e-3, abs=2e-3), name

@@ -1550,6 +1550,63 @@ extern "C" int xr_fused_pool_loss(const void* q, const void* pos, const void* ne
                           row_loss, ws, false, as_stream(stream));
 }
 
+// ---- train loss + gradient + the monitoring of BOTH logit families from one pass (exact shapes) ------------
+// The module-path form of xr_pool_step_compute_mon: what trainer.py:213-264 (compute_losses) needs for one
+// batch -- InfoNCE loss and dL/dq, losses_dot[7], losses_cos[7], stats[16] -- from ONE tensor-core pass over
+// the pool.  Workspace: xr_fused_pool_loss_mon_workspace_bytes(m, cn, dim).
+struct MonWs {
+  float *part_dot, *part_cos, *inv_q, *inv_n, *t_cos;
+  double *row_out, *row_out2, *scratch;
+  size_t bytes;
+};
+static MonWs carve_mon_ws(void* base, long long m, long long cn, long long slots) {
+  MonWs w;
+  uint8_t* p = (uint8_t*)base;
+  const size_t part = align256((size_t)slots * fk::CG * fk::BM * fk::NSCAL_ALL * 4);
+  w.part_dot = (float*)p;   p += part;
+  w.part_cos = (float*)p;   p += part;
+  w.inv_q = (float*)p;      p += align256((size_t)m * 4);
+  w.inv_n = (float*)p;      p += align256((size_t)(cn + 64) * 4);
+  w.t_cos = (float*)p;      p += align256((size_t)m * 4);
+  w.row_out = (double*)p;   p += align256((size_t)m * ROW_SLOTS * 8);
+  w.row_out2 = (double*)p;  p += align256((size_t)m * ROW_SLOTS * 8);
+  w.scratch = (double*)p;   p += 2 * kRowlossPartialBytes;
+  w.bytes = (size_t)(p - (uint8_t*)base);
+  return w;
+}
+
+extern "C" size_t xr_fused_pool_loss_mon_workspace_bytes(int64_t m, int64_t cn, int64_t dim) {
+  if (dim != fk::D || m <= 0 || cn <= 0) return 512;
+  const FusedPlan pl = make_plan(m, cn, sm_count_max());
+  return carve_fused_ws(nullptr, m, pl.slots).bytes + carve_mon_ws(nullptr, m, cn, pl.slots).bytes;
+}
+
+extern "C" int xr_fused_pool_loss_mon(const void* q, const void* pos, const void* neg, int64_t m, int64_t cn,
+                                      int64_t dim, const xr_loss_config* cfg, float grad_scale, float* dq,
+                                      double* loss_out, double* losses_dot, double* losses_cos,
+                                      double* stats_out, void* workspace, size_t workspace_bytes, void* stream) {
+  XR_CHECK_ARG(q && pos && neg && cfg && loss_out && losses_dot && losses_cos && stats_out && workspace,
+               "xr_fused_pool_loss_mon: null pointer");
+  XR_CHECK_ARG(dim == fk::D, "xr_fused_pool_loss_mon: this build is specialised for dim = %d", fk::D);
+  XR_CHECK_ARG(m > 0 && cn > 0 && m < (1ll << 30) && cn < (1ll << 30), "xr_fused_pool_loss_mon: bad sizes");
+  XR_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)pos % 16 == 0) && ((uintptr_t)neg % 16 == 0) &&
+                   (uintptr_t)workspace % 256 == 0,
+               "xr_fused_pool_loss_mon: operands must be 16-byte aligned, the workspace 256-byte aligned");
+  XR_CHECK_ARG(cfg->num_hard_negatives == 0 && cfg->scale > 0.f,
+               "xr_fused_pool_loss_mon: needs scale > 0 and no hard-negative mining");
+  XR_CHECK_ARG(workspace_bytes >= xr_fused_pool_loss_mon_workspace_bytes(m, cn, dim),
+               "xr_fused_pool_loss_mon: workspace too small");
+  int rc;
+  if ((rc = check_fused_device("xr_fused_pool_loss_mon"))) return rc;
+  const FusedPlan pl = make_plan(m, cn, sm_count_max());
+  const FusedWs ws = carve_fused_ws(workspace, m, pl.slots);
+  const MonWs mw = carve_mon_ws((uint8_t*)workspace + ws.bytes, m, cn, pl.slots);
+  const MonArgs mon{mw.part_dot, mw.part_cos, mw.inv_q, mw.inv_n, mw.t_cos, mw.row_out, mw.row_out2, mw.scratch,
+                    losses_dot, losses_cos, stats_out, m};
+  return fused_launch_all(q, pos, neg, m, cn, XR_LOSS_INFONCE, cfg, nullptr, grad_scale, dq, loss_out, nullptr, ws,
+                          false, as_stream(stream), nullptr, &mon);
+}
+
 // ---- every loss of one logit family + LogitsStatistics in ONE pass over the pool ----------------
 // trainer.py:250-263 evaluates LogitsStatistics and all seven losses on every training step (eight
 // logit computations in the reference).  Forward only: diagonal pass -> [softmax reference bound]

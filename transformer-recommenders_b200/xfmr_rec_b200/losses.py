@@ -493,15 +493,51 @@ LossType = Literal[
 ]
 
 
+def _one_pass(config, query_embed, candidate_embed, target, train_loss):
+    """Train loss (InfoNCE) with its autograd edge AND both families' losses + statistics from ONE tensor-core
+    pass (xr_fused_pool_loss_mon) when the batch qualifies: pool candidates on the bf16 tensor-core path for
+    both logit families, gradient wanted, no hard-negative mining, scale > 0.  None otherwise."""
+    if not (train_loss == "InfoNCELoss" and target is None and isinstance(candidate_embed, PoolCandidates)
+            and torch.is_grad_enabled() and query_embed.requires_grad and query_embed.is_cuda):
+        return None
+    if config.num_hard_negatives or config.scale <= 0 or config.target_position != "first":
+        return None
+    dot, cos = InfoNCELoss(config), AlignmentContrastiveLoss(config)
+    cdt, logits_bf16 = dot._compute_dtype(query_embed)
+    if cdt != torch.bfloat16 or cos._compute_dtype(query_embed)[0] != torch.bfloat16:
+        return None
+    q, pos, neg = (t.detach().to(cdt).contiguous() for t in (query_embed, candidate_embed.pos, candidate_embed.neg))
+    if q.size(0) == 0 or neg.size(0) == 0 or not ops.fused_pool_supported(q, neg):
+        return None
+    dot.check_embeds(query_embed, candidate_embed)
+    cfg = ops.make_cfg(config, logits_bf16=logits_bf16)
+    loss, dq, l_dot, l_cos, stats = ops.fused_pool_loss_mon(q, pos, neg, cfg)
+    loss32 = loss.view(torch.float32)[2]
+    src = getattr(query_embed, "_xr_src", None)
+    if src is not None and src[0].requires_grad and dq.size(1) % 8 == 0:
+        attached = _AttachGradScatter.apply(src[0], loss32, dq, src[1])
+    else:
+        attached = _AttachGrad.apply(query_embed, loss32, dq)
+    return attached, l_dot, l_cos, stats
+
+
 def evaluate_all(config, query_embed, candidate_embed, target=None, *, train_loss="InfoNCELoss"):
     """What ``RecommenderLightningModule.compute_losses`` asks for each step
     (trainer.py:250-263): LogitsStatistics + every loss in LOSS_CLASSES, with the autograd edge
     on ``train_loss`` only.  The two logit families (dot, cosine) are each evaluated ONCE
     instead of the reference's eight separate logit computations.
     Returns (dict loss/<Name> -> 0-dim tensor, stats dict)."""
+    out: dict[str, torch.Tensor] = {}
+    one = _one_pass(config, query_embed, candidate_embed, target, train_loss)
+    if one is not None:
+        attached, l_dot, l_cos, stats = one
+        for cls in LOSS_CLASSES:
+            src = l_cos if cls.COSINE else l_dot
+            out[f"loss/{cls.__name__}"] = src[N.LOSS_KIND[cls.__name__]].to(torch.float32)
+        out[f"loss/{train_loss}"] = attached
+        return out, stats_dict(stats.tolist())
     dot = InfoNCELoss(config)
     cos = AlignmentContrastiveLoss(config)
-    out: dict[str, torch.Tensor] = {}
     with torch.no_grad():
         l_dot, stats, _ = dot._evaluate(query_embed, candidate_embed, target, want_stats=True)
         l_cos, _, _ = cos._evaluate(query_embed, candidate_embed, target, want_stats=True)
@@ -526,17 +562,24 @@ def compute_losses(config, embeds: dict, *, train_loss: str = "InfoNCELoss") -> 
     numel = attention_mask.numel()
     counts = torch.stack([attention_mask.count_nonzero(), embeds["positive_mask"].count_nonzero()])
     q, cand = embeds["query_embed"], embeds["candidate_embed"]
-    dot, cos = InfoNCELoss(config), AlignmentContrastiveLoss(config)
-    with torch.no_grad():
-        l_dot, stats, _ = dot._evaluate(q, cand, None, want_stats=True)
-        l_cos, _, _ = cos._evaluate(q, cand, None, want_stats=True)
+    one = _one_pass(config, q, cand, None, train_loss)
+    attached = None
+    if one is not None:      # ONE tensor-core pass: train loss + gradient + both families + statistics
+        attached, l_dot, l_cos, stats = one
+    else:
+        dot, cos = InfoNCELoss(config), AlignmentContrastiveLoss(config)
+        with torch.no_grad():
+            l_dot, stats, _ = dot._evaluate(q, cand, None, want_stats=True)
+            l_cos, _, _ = cos._evaluate(q, cand, None, want_stats=True)
     host = torch.cat([counts.to(torch.float64), stats]).tolist()     # the single host sync
     attn_non_zero, pos_non_zero = int(host[0]), int(host[1])
     losses: dict = {}
     train_cls = {c.__name__: c for c in LOSS_CLASSES}[train_loss]
     for cls in LOSS_CLASSES:
         key = f"loss/{cls.__name__}"
-        if cls is train_cls and torch.is_grad_enabled() and q.requires_grad:
+        if cls is train_cls and attached is not None:
+            loss = attached
+        elif cls is train_cls and torch.is_grad_enabled() and q.requires_grad:
             loss = cls(config)(q, cand)
         else:
             src = l_cos if cls.COSINE else l_dot
