@@ -723,7 +723,7 @@ def bench_encoder_step(xr, dev, flush):
     hist, pos, neg = (torch.from_numpy(b[k]).to(dev) for k in ("history_item_idx", "pos_item_idx", "neg_item_idx"))
     torch.manual_seed(0)
     cfg = EncoderConfig(num_hidden_layers=2, intermediate_size=1536, max_seq_length=SEQ_LEN)
-    enc = SeqEncoder(cfg, compute_dtype=torch.bfloat16).to(dev)
+    enc = SeqEncoder(cfg, compute_dtype=torch.bfloat16).to(dev).train()    # dropout 0.1 / 0.1 (HF defaults)
     emb = xr.models.ItemEmbeddings(table, add_padding_row=False).to(dev)
     step = xr.PoolLossStep(emb, xr.InfoNCELoss(xr.LossConfig()), BATCH, SEQ_LEN, token_dtype=torch.float32,
                            logits_bf16=True, use_graph=False)
@@ -736,7 +736,9 @@ def bench_encoder_step(xr, dev, flush):
     return {"value": BATCH / (ms / 1e3), "unit": "seq/s", "ms_per_step": ms, "encoder_forward_eager_ms": fwd_ms,
             "loss": loss, "trained_parameters": n_par,
             "encoder": {"layers": 2, "hidden": DIM, "heads": 12, "intermediate": 1536, "compute": "bf16-mixed "
-                        "(bf16 GEMMs / attention / GELU, fp32 residual stream, LayerNorm and softmax)", "dropout": 0.0},
+                        "(bf16 GEMMs / attention / GELU, fp32 residual stream, LayerNorm and softmax)",
+                        "dropout": "0.1 hidden / 0.1 attention (training mode, HF defaults): counter-based masks "
+                                   "recomputed in the backward"},
             "note": "GraphedEncoderStep: encoder forward + PoolLossStep + encoder backward (parameter gradients "
                     "in .grad, no optimizer) replayed as one CUDA graph; L2 flushed between steps; the linear "
                     "layers are cuBLAS GEMMs, everything else this repository's kernels (csrc/encoder.cu). "

@@ -470,18 +470,27 @@ int xr_retrieval_metrics(const int64_t* rec, int64_t u, int64_t k, const int64_t
  * embed_ln: out[b,l,:] = LayerNorm(table[idx[b,l]] + pos_emb[l] + type_emb[0:H]) (BertEmbeddings with
  * inputs_embeds; the history gather of models.py:336-338 fused in), stats (B*L, 2) = {mean, rstd},
  * mask[b,l] = any(table[idx[b,l]] != 0) (the attention mask of models.py:343).                           */
+/* Dropout (HF BertConfig: hidden_dropout_prob / attention_probs_dropout_prob, 0.1 by default, training mode):
+ * every entry point below that has a dropout site takes `rng` = device pointer to {int64 seed, int64 step
+ * counter} (NULL = no dropout), the probability and a site id.  The keep mask is a pure function of (seed,
+ * counter, site, element) through Philox4x32-10: the backward entry recomputes it from the SAME rng values,
+ * nothing is stored, and a CUDA-graph replay draws a fresh mask when the caller bumps the counter on the
+ * device.  Hidden-state sites use 16-bit draws (p_eff = round(65536 p) / 65536), the attention-probability
+ * site 8-bit draws (p_eff = round(256 p) / 256); kept values are scaled by 1 / (1 - p_eff).              */
 size_t xr_enc_ln_workspace_bytes(int64_t n_tok);
 int xr_enc_embed_ln_fwd(const float* table, int64_t n_table_rows, const int64_t* idx, const float* pos_emb,
                         const float* type_emb, const float* gamma, const float* beta, int64_t batch,
                         int64_t seq_len, int64_t dim, float eps, float* out, void* out_bf16 /* nullable */,
-                        float* stats, uint8_t* mask, int32_t* err_flag, void* stream);
+                        float* stats, uint8_t* mask, int32_t* err_flag, const int64_t* rng, float drop_p, int site,
+                        void* stream);
 /* gradients of the position embeddings (seq_len, H), token-type row 0 (H), LayerNorm weight / bias; the item
  * table is frozen (models.py:251-253).  The upstream gradient is dout (fp32) + dout_bf16 (the gradient of the
  * bf16 copy), either may be NULL.  workspace: xr_enc_ln_workspace_bytes(batch * seq_len).                  */
 int xr_enc_embed_ln_bwd(const float* table, int64_t n_table_rows, const int64_t* idx, const float* pos_emb,
                         const float* type_emb, const float* gamma, const float* stats, const float* dout,
                         const void* dout_bf16, int64_t batch, int64_t seq_len, int64_t dim, float* dpos,
-                        float* dtype0, float* dgamma, float* dbeta, void* workspace, void* stream);
+                        float* dtype0, float* dgamma, float* dbeta, void* workspace, const int64_t* rng, float drop_p,
+                        int site, void* stream);
 /* out = LayerNorm(y + bias + residual) (BertSelfOutput / BertOutput; y = the dense layer's product, its bias
  * added here; bias may be NULL when y already holds it).  out_bf16 (nullable): the same rows rounded to bf16,
  * the next GEMM's input.  Backward: dresidual (fp32) and dy (y's dtype) both receive the LayerNorm input
@@ -489,11 +498,11 @@ int xr_enc_embed_ln_bwd(const float* table, int64_t n_table_rows, const int64_t*
  * workspace: xr_enc_ln_workspace_bytes(1).                                                                  */
 int xr_enc_add_ln_fwd(const void* y, int y_dtype, const float* bias, const float* residual, const float* gamma,
                       const float* beta, int64_t n_tok, int64_t dim, float eps, float* out, void* out_bf16,
-                      float* stats, void* stream);
+                      float* stats, const int64_t* rng, float drop_p, int site, void* stream);
 int xr_enc_add_ln_bwd(const void* y, int y_dtype, const float* bias, const float* residual, const float* gamma,
                       const float* stats, const float* dout, const void* dout_bf16, int64_t n_tok, int64_t dim,
                       float* dresidual, void* dy, float* dbias, float* dgamma, float* dbeta, void* workspace,
-                      void* stream);
+                      const int64_t* rng, float drop_p, int site, void* stream);
 /* out[c] = sum over rows of x[r][c] (a linear layer's bias gradient: torch.nn.Linear inside BertSelfAttention /
  * BertIntermediate); fp32 accumulation in a fixed order.  width must be a multiple of 16 bytes of elements. */
 size_t xr_enc_colsum_workspace_bytes(int64_t width);
@@ -505,7 +514,7 @@ int xr_enc_gelu(const void* x, const void* dy, int64_t n, int dtype, void* out, 
  * dctx != NULL: backward, out = dqkv, lse and ctx from the forward.  Deterministic (no atomics).          */
 int xr_enc_attention(const void* qkv, const uint8_t* keymask, const void* ctx, const void* dctx, float* lse,
                      int64_t batch, int64_t seq_len, int64_t n_heads, int64_t head_dim, int dtype, void* out,
-                     void* stream);
+                     const int64_t* rng, float drop_p, int site, void* stream);
 
 #ifdef __cplusplus
 }

@@ -39,7 +39,7 @@ def timeit(fn, reps=20, warm=3):
 
 
 for name, cd in (("bf16", torch.bfloat16), ("fp32", torch.float32)):
-    enc = SeqEncoder(cfg, compute_dtype=cd).to(dev)
+    enc = SeqEncoder(cfg, compute_dtype=cd).to(dev).train()      # dropout 0.1 / 0.1 (HF defaults), as the reference trains
     up = torch.randn(B, L, 384, device=dev)
 
     def fwd():
@@ -77,7 +77,7 @@ try:
 
     hf = BertModel(BertConfig(vocab_size=1, hidden_size=384, num_hidden_layers=2, num_attention_heads=12,
                               intermediate_size=1536, max_position_embeddings=L, is_decoder=True,
-                              hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)).to(dev)
+                              hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1)).to(dev).train()
     inputs = table[hist]
     mask = (inputs != 0).any(-1).long()
     up = torch.randn(B, L, 384, device=dev)
@@ -94,8 +94,8 @@ try:
 
     out["reference_bert_bf16_autocast_same_gpu"] = {"forward_ms": timeit(hf_fwd), "forward_backward_ms": timeit(hf_fwd_bwd),
                                                     "import_s": round(time.time() - t0, 1),
-                                                    "note": "transformers BertModel (the class models.py:92-101 builds), eager, "
-                                                            "dropout 0, torch.autocast(bfloat16), gather done by torch"}
+                                                    "note": "transformers BertModel (the class models.py:92-101 builds), eager, training mode "
+                                                            "(dropout 0.1 / 0.1 as the reference trains), torch.autocast(bfloat16), gather done by torch"}
 except Exception as e:   # transformers missing on the box
     out["reference_bert_bf16_autocast_same_gpu"] = {"unavailable": repr(e)}
 print(json.dumps(out, indent=1))

@@ -59,7 +59,7 @@ def _load(golden_dir, tag):
     layers, inter, max_pos, seed = (int(v) for v in z["config"])
     enc = SeqEncoder(EncoderConfig(num_hidden_layers=layers, intermediate_size=inter, max_seq_length=max_pos))
     enc.load_state_dict(seeded_state_dict(enc.state_dict(), seed))
-    return z, enc.cuda()
+    return z, enc.cuda().eval()      # the fixtures come from BertModel.eval(): no dropout
 
 
 @pytest.mark.gpu
@@ -107,7 +107,7 @@ def test_encoder_bf16_mixed_is_close_to_fp32(golden_dir):
     from xfmr_rec_b200.encoder import SeqEncoder
 
     z, enc = _load(golden_dir, "2layer_i128")
-    enc16 = SeqEncoder(enc.config, compute_dtype=torch.bfloat16).cuda()
+    enc16 = SeqEncoder(enc.config, compute_dtype=torch.bfloat16).cuda().eval()
     enc16.load_state_dict(enc.state_dict())
     idx, table = torch.from_numpy(z["idx"]).cuda(), torch.from_numpy(z["table"]).cuda()
     tok = enc16(idx, table)["token_embeddings"]
@@ -160,7 +160,7 @@ def test_encoder_train_step_feeds_the_loss_step_gradient_in_place(golden_dir):
     hist = torch.randint(1, n + 1, (b, l), device="cuda") * valid
     pos = torch.randint(1, n + 1, (b, l), device="cuda") * valid
     neg = torch.randint(1, n + 1, (b, l), device="cuda") * valid
-    enc = SeqEncoder(EncoderConfig(num_hidden_layers=2, intermediate_size=96, max_seq_length=l)).cuda()
+    enc = SeqEncoder(EncoderConfig(num_hidden_layers=2, intermediate_size=96, max_seq_length=l)).cuda().eval()
     loss_fn = xr.InfoNCELoss(xr.LossConfig())
     # (fp32 encoder output; logits rounded to bf16 as under bf16-mixed autocast, like the bf16 module path below)
     step = xr.PoolLossStep(emb, loss_fn, b, l, token_dtype=torch.float32, logits_bf16=True)
@@ -225,7 +225,7 @@ def test_graphed_encoder_step_equals_the_eager_step(golden_dir):
     B, L, n_items = 16, 48, 3000
     torch.manual_seed(0)
     enc = SeqEncoder(EncoderConfig(num_hidden_layers=2, intermediate_size=128, max_seq_length=L),
-                     compute_dtype=torch.bfloat16).cuda()
+                     compute_dtype=torch.bfloat16).cuda().eval()
     batches = [synthetic_batch(n_items, B, L, dim=384, seed=s) for s in (1, 2)]
     table = torch.from_numpy(batches[0]["table"]).cuda()
     emb = xr.models.ItemEmbeddings(table, add_padding_row=False).cuda()
@@ -243,3 +243,135 @@ def test_graphed_encoder_step_equals_the_eager_step(golden_dir):
         assert grads_g.keys() == grads_e.keys() and len(grads_g) > 30
         for n in grads_g:
             assert torch.equal(grads_g[n], grads_e[n]), n
+
+
+@pytest.mark.gpu
+def test_hidden_dropout_masks_are_seeded_scaled_and_fresh_per_forward(golden_dir):
+    """Training mode: dropout(LayerNorm(...)) on the embeddings (BertEmbeddings) keeps a value with
+    probability 1 - p_eff and scales it by 1 / (1 - p_eff) (p_eff = round(65536 p) / 65536); the mask is a
+    function of (seed, forward counter): two modules with the same seed agree bit for bit, consecutive
+    forwards of one module differ; eval mode is the deterministic encoder."""
+    from xfmr_rec_b200.encoder import EncoderConfig, SeqEncoder
+
+    z, ref = _load(golden_dir, "default_1layer")
+    idx, table = torch.from_numpy(z["idx"]).cuda(), torch.from_numpy(z["table"]).cuda()
+    cfg = ref.config.model_copy(update={"hidden_dropout_prob": 0.25, "attention_probs_dropout_prob": 0.0,
+                                        "num_hidden_layers": 0})
+    mk = lambda seed: SeqEncoder(cfg, seed=seed).cuda()
+    a, b, c = mk(7), mk(7), mk(8)
+    for m in (a, b, c):
+        m.load_state_dict(ref.state_dict(), strict=False)
+    base = a.eval()(idx, table)["token_embeddings"]
+    a.train()
+    out_a1, out_b1, out_c1 = (m(idx, table)["token_embeddings"] for m in (a, b, c))
+    out_a2 = a(idx, table)["token_embeddings"]
+    assert torch.equal(out_a1, out_b1) and not torch.equal(out_a1, out_c1) and not torch.equal(out_a1, out_a2)
+    thr = round(0.25 * 65536)
+    scale = 65536.0 / (65536 - thr)
+    kept = out_a1 != 0
+    assert torch.allclose(out_a1[kept], (base * scale)[kept], rtol=1e-6, atol=0)
+    n = base.numel()
+    frac = float((~kept & (base != 0)).sum()) / n
+    assert abs(frac - thr / 65536) < 4 * (0.25 * 0.75 / n) ** 0.5
+    # backward uses the forward's mask: the gradient w.r.t. the LayerNorm weight of a dropped-out network equals
+    # autograd through (base-graph output) * mask * scale
+    a.zero_grad()
+    out = a(idx, table)["token_embeddings"]
+    up = torch.randn_like(out)
+    (out * up).sum().backward()
+    g_drop = a.embeddings.LayerNorm.bias.grad.clone()
+    want = (up * (out != 0) * scale).sum((0, 1))        # d out / d beta = mask * scale
+    assert torch.allclose(g_drop, want, rtol=1e-4, atol=1e-4)
+
+
+def _attention_reference(qkv, keymask, keep, scale_drop, up):
+    """torch fp32 autograd of causal + key-padding attention with a FIXED dropout mask on the probabilities."""
+    b, l, h3 = qkv.shape
+    hid = h3 // 3
+    x = qkv.detach().float().clone().requires_grad_(True)
+    q, k, v = (t.view(b, l, 12, 32).transpose(1, 2) for t in x.split(hid, dim=-1))
+    s = q @ k.transpose(-1, -2) / 32 ** 0.5
+    allow = torch.tril(torch.ones(l, l, dtype=torch.bool, device=x.device))[None, None] & keymask.bool()[:, None, None, :]
+    p = torch.softmax(s.masked_fill(~allow, float("-inf")), dim=-1)
+    p = torch.nan_to_num(p, nan=0.0)
+    out = ((p * keep * scale_drop) @ v).transpose(1, 2).reshape(b, l, hid)
+    out.backward(up.float())
+    return out.detach(), x.grad
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_attention_dropout_forward_and_backward_share_one_mask(dtype):
+    """Dropout on the attention probabilities (BertSelfAttention): with V = one-hot rows the output IS the
+    dropped probability matrix, which gives the mask the kernel drew; the kernel's gradients (dQ pass and
+    dK / dV pass recompute the mask in two different fragment layouts) must equal torch autograd with that
+    mask held fixed.  Also: kept fraction ~ 1 - p_eff (8-bit draws), scale 1 / (1 - p_eff), fresh mask when the
+    counter advances, same mask for the same {seed, counter}."""
+    from xfmr_rec_b200.encoder import _Attention
+
+    b, l, heads, p_drop = 3, 32, 12, 0.3
+    g = torch.Generator(device="cuda").manual_seed(5)
+    qkv = torch.randn((b, l, 3 * 384), generator=g, device="cuda")
+    eye = torch.eye(32, device="cuda")[:l]                       # V_j = e_j for every head
+    qkv[:, :, 768:] = eye.repeat(1, heads)[None]
+    qkv = qkv.to(dtype)
+    mask = torch.ones((b, l), dtype=torch.uint8, device="cuda")
+    mask[1, :5] = 0
+    rng = torch.tensor([11, 3], dtype=torch.int64, device="cuda")
+    thr = round(p_drop * 256)
+    scale = 256.0 / (256 - thr)
+    with torch.no_grad():
+        p_eval = _Attention.apply(qkv, mask, heads).float().view(b, l, heads, 32).transpose(1, 2)
+        p_drop1 = _Attention.apply(qkv, mask, heads, rng, p_drop, 1).float().view(b, l, heads, 32).transpose(1, 2)
+        again = _Attention.apply(qkv, mask, heads, rng.clone(), p_drop, 1).float().view(b, l, heads, 32).transpose(1, 2)
+        other = _Attention.apply(qkv, mask, heads, rng + torch.tensor([0, 1], device="cuda"), p_drop, 1).float()
+    assert torch.equal(p_drop1, again) and not torch.equal(p_drop1.transpose(1, 2).reshape(b, l, -1), other)
+    live = p_eval > 1e-3                                          # entries whose fate is visible
+    keep = (p_drop1 != 0)
+    tol = 2e-2 if dtype == torch.bfloat16 else 1e-5
+    assert torch.allclose(p_drop1[live & keep], (p_eval * scale)[live & keep], rtol=tol, atol=tol)
+    n_live = int(live.sum())
+    frac = float((live & ~keep).sum()) / n_live
+    assert abs(frac - thr / 256) < 4 * (0.3 * 0.7 / n_live) ** 0.5, (frac, thr / 256)
+    # gradients with the drawn mask held fixed (entries the probe cannot see are ~0 and do not matter)
+    x = qkv.clone().requires_grad_(True)
+    up = torch.randn((b, l, 384), generator=g, device="cuda").to(dtype)
+    out = _Attention.apply(x, mask, heads, rng, p_drop, 1)
+    out.backward(up)
+    keep_full = keep | ~live
+    want_out, want_grad = _attention_reference(qkv, mask, keep_full.float(), scale, up)
+    assert float((out.float() - want_out).norm()) <= (2e-2 if dtype == torch.bfloat16 else 2e-3) * float(want_out.norm())
+    err = float((x.grad.float() - want_grad).norm()) / float(want_grad.norm())
+    assert err <= (3e-2 if dtype == torch.bfloat16 else 5e-3), err
+
+
+@pytest.mark.gpu
+def test_encoder_trains_with_dropout_and_graph_replays_draw_fresh_masks():
+    """Default config (HF's 0.1 / 0.1) in training mode: finite loss and gradients, and two replays of the
+    one-graph train step on the SAME batch give different losses (the forward counter lives on the device)."""
+    import xfmr_rec_b200 as xr
+    from xfmr_rec_b200.data import synthetic_batch
+    from xfmr_rec_b200.encoder import EncoderConfig, GraphedEncoderStep, SeqEncoder
+
+    B, L = 8, 40
+    b = synthetic_batch(2000, B, L, dim=384, seed=3)
+    table = torch.from_numpy(b["table"]).cuda()
+    torch.manual_seed(0)
+    enc = SeqEncoder(EncoderConfig(num_hidden_layers=2, intermediate_size=128, max_seq_length=L),
+                     compute_dtype=torch.bfloat16).cuda().train()
+    emb = xr.models.ItemEmbeddings(table, add_padding_row=False).cuda()
+    step = xr.PoolLossStep(emb, xr.InfoNCELoss(xr.LossConfig()), B, L, token_dtype=torch.float32, logits_bf16=True,
+                           use_graph=False)
+    graphed = GraphedEncoderStep(enc, step, table, L)
+    hist, pos, neg = (torch.from_numpy(b[k]).cuda() for k in ("history_item_idx", "pos_item_idx", "neg_item_idx"))
+    l1 = float(graphed(hist, pos, neg))
+    g1 = enc.encoder.layer[0].output.dense.weight.grad.clone()
+    l2 = float(graphed(hist, pos, neg))
+    g2 = enc.encoder.layer[0].output.dense.weight.grad.clone()
+    assert np.isfinite([l1, l2]).all() and l1 != l2
+    assert bool(torch.isfinite(g1).all()) and not torch.equal(g1, g2)
+    enc.eval()
+    with torch.no_grad():
+        e1 = enc(hist, table)["token_embeddings"]
+        e2 = enc(hist, table)["token_embeddings"]
+    assert torch.equal(e1, e2)

@@ -13,6 +13,7 @@
 // are plain GEMMs and go through cuBLAS (torch.nn.functional.linear) in xfmr_rec_b200/encoder.py.
 // Activations are fp32 or bf16 (template parameter); all reductions are fp32.
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace xr {
 
@@ -32,6 +33,94 @@ __device__ __forceinline__ float from_f32<float>(float v) {
 template <>
 __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
   return __float2bfloat16_rn(v);
+}
+
+// ---- dropout (HF BertConfig defaults: hidden_dropout_prob = attention_probs_dropout_prob = 0.1, active in
+// training mode; models.py:92-101 builds the BertModel with them).  Masks are a pure function of
+// (seed, step counter, site, element coordinates) through Philox4x32-10, so the backward pass recomputes them
+// instead of storing them, and CUDA-graph replays draw fresh masks because {seed, counter} live in device
+// memory (`rng`; a null pointer or p == 0 switches the site off).
+struct DropCtx {
+  uint32_t k0, k1, site, ctr, thr;
+  float scale;
+  bool on;
+};
+// bits: 16 (hidden sites: keep iff r16 >= thr, p_eff = thr / 65536) or 8 (attention: p_eff = thr / 256)
+__device__ __forceinline__ DropCtx make_drop(const int64_t* __restrict__ rng, float p, int site, int bits) {
+  DropCtx d;
+  d.on = rng != nullptr && p > 0.f;
+  d.k0 = d.k1 = d.ctr = d.thr = 0;
+  d.site = (uint32_t)site;
+  d.scale = 1.f;
+  if (d.on) {
+    const uint64_t seed = (uint64_t)rng[0], ctr = (uint64_t)rng[1];
+    d.k0 = (uint32_t)seed;
+    d.k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(ctr >> 32);
+    d.ctr = (uint32_t)ctr;
+    const float full = bits == 16 ? 65536.f : 256.f;
+    d.thr = (uint32_t)(p * full + 0.5f);
+    if (d.thr >= (uint32_t)full) d.thr = (uint32_t)full - 1;
+    d.scale = full / (full - (float)d.thr);
+  }
+  return d;
+}
+// hidden-state sites (warp per token, lane-strided columns c = lane + 32 k): bit k of the result = keep
+// element k of this lane.  Two Philox calls per lane and token give its twelve 16-bit draws.
+__device__ __forceinline__ uint32_t drop_bits(int64_t tok, int lane, const DropCtx& d) {
+  if (!d.on) return 0xFFFFFFFFu;
+  uint32_t bits = 0;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const U4 r = philox((uint32_t)tok, (uint32_t)((uint64_t)tok >> 32) ^ (uint32_t)(lane | (q << 8)), d.site, d.ctr,
+                        d.k0, d.k1);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      const int k = 8 * q + h;
+      if (k < enc::PER && ((w[h >> 1] >> (16 * (h & 1))) & 0xFFFFu) >= d.thr) bits |= 1u << k;
+    }
+  }
+  return bits;
+}
+__device__ __forceinline__ void drop_apply(float (&x)[enc::PER], uint32_t bits, const DropCtx& d) {
+  if (!d.on) return;
+#pragma unroll
+  for (int k = 0; k < enc::PER; ++k) x[k] = (bits >> k) & 1u ? x[k] * d.scale : 0.f;
+}
+__device__ __forceinline__ void drop_row(float (&x)[enc::PER], int64_t tok, int lane, const DropCtx& d) {
+  drop_apply(x, drop_bits(tok, lane, d), d);
+}
+// attention-probability site: the 16 x 16 block (query tile, key block) of one (sequence, head) draws 256
+// bytes from 16 Philox calls laid out so that BOTH fragment layouts of the tensor-core kernels (queries along
+// rows in the forward / dQ pass, keys along rows in the dK / dV pass) find the eight elements a lane holds in
+// ONE call: call = ((r % 8) / 2) * 4 + (c % 8) / 2, byte = (r % 2) * 8 + (r / 8) * 4 + (c % 2) * 2 + c / 8 for
+// the element at (query r, key c) of the block.
+struct DropBlock {
+  uint32_t w[4];
+};
+__device__ __forceinline__ DropBlock attn_drop_call(const DropCtx& d, uint32_t bh, uint32_t q_tile, uint32_t k_tile,
+                                                    int call) {
+  const U4 r = philox(bh, (q_tile << 16) | k_tile, d.site | ((uint32_t)call << 8), d.ctr, d.k0, d.k1);
+  return DropBlock{{r.x, r.y, r.z, r.w}};
+}
+__device__ __forceinline__ bool attn_keep(const DropBlock& b, int slot, const DropCtx& d) {
+  return ((b.w[slot >> 2] >> (8 * (slot & 3))) & 0xFFu) >= d.thr;
+}
+// forward / dQ-pass fragment: a lane's eight elements are bytes (g % 2) * 8 + [0, 8) of its call: pick that
+// half once (static register indexing afterwards); local slot = (e >> 1) * 4 + (e & 1) * 2 + nt
+__device__ __forceinline__ uint64_t attn_row_half(const DropBlock& b, int g) {
+  const uint32_t lo = (g & 1) ? b.w[2] : b.w[0], hi = (g & 1) ? b.w[3] : b.w[1];
+  return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ bool attn_keep8(uint64_t half, int local_slot, const DropCtx& d) {
+  return ((uint32_t)(half >> (8 * local_slot)) & 0xFFu) >= d.thr;
+}
+// one element at a time (the fp32 kernels): query i, key j of (sequence, head) bh
+__device__ __forceinline__ float attn_drop_elem(const DropCtx& d, uint32_t bh, int i, int j) {
+  if (!d.on) return 1.f;
+  const int r = i & 15, c = j & 15;
+  const DropBlock b = attn_drop_call(d, bh, (uint32_t)(i >> 4), (uint32_t)(j >> 4), ((r & 7) >> 1) * 4 + ((c & 7) >> 1));
+  return attn_keep(b, (r & 1) * 8 + (r >> 3) * 4 + (c & 1) * 2 + (c >> 3), d) ? d.scale : 0.f;
 }
 
 // warp-per-token LayerNorm over x[PER] (lane-strided columns c = lane + 32 k), HF semantics: biased variance
@@ -62,7 +151,9 @@ enc_embed_ln_fwd_kernel(const float* __restrict__ table, int64_t n_table_rows, c
                         const float* __restrict__ pos_emb, const float* __restrict__ type_emb,
                         const float* __restrict__ gamma, const float* __restrict__ beta, int64_t n_tok, int seq_len,
                         float eps, float* __restrict__ out, __nv_bfloat16* __restrict__ out_lp,
-                        float* __restrict__ stats, uint8_t* __restrict__ mask, int32_t* __restrict__ err_flag) {
+                        float* __restrict__ stats, uint8_t* __restrict__ mask, int32_t* __restrict__ err_flag,
+                        const int64_t* __restrict__ rng, float drop_p, int site) {
+  const DropCtx dc = make_drop(rng, drop_p, site, 16);
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -85,6 +176,7 @@ enc_embed_ln_fwd_kernel(const float* __restrict__ table, int64_t n_table_rows, c
     nz = __any_sync(0xffffffffu, nz);     // models.py:343: (inputs_embeds != 0).any(-1)
     float mean, rstd;
     ln_row(x, gamma, beta, eps, lane, y, mean, rstd);
+    drop_row(y, t, lane, dc);        // BertEmbeddings: dropout(LayerNorm(...))
 #pragma unroll
     for (int k = 0; k < enc::PER; ++k) out[t * enc::H + lane + 32 * k] = y[k];
     if (out_lp)
@@ -177,7 +269,9 @@ enc_embed_ln_bwd_kernel(const float* __restrict__ table, int64_t n_table_rows, c
                         const float* __restrict__ pos_emb, const float* __restrict__ type_emb,
                         const float* __restrict__ gamma, const float* __restrict__ stats,
                         const float* __restrict__ dout, const __nv_bfloat16* __restrict__ dout_lp, int64_t n_tok,
-                        int seq_len, float* __restrict__ dx_out, float* __restrict__ part) {
+                        int seq_len, float* __restrict__ dx_out, float* __restrict__ part,
+                        const int64_t* __restrict__ rng, float drop_p, int site) {
+  const DropCtx dc = make_drop(rng, drop_p, site, 16);
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -193,6 +287,7 @@ enc_embed_ln_bwd_kernel(const float* __restrict__ table, int64_t n_table_rows, c
       x[k] = __ldg(table + row * enc::H + c) + pos_emb[(int64_t)l * enc::H + c] + type_emb[c];
       dy[k] = (dout ? dout[t * enc::H + c] : 0.f) + (dout_lp ? __bfloat162float(dout_lp[t * enc::H + c]) : 0.f);
     }
+    drop_row(dy, t, lane, dc);       // the same mask as the forward
     ln_row_bwd(x, dy, gamma, stats[2 * t], stats[2 * t + 1], lane, dx, acc[0], acc[1]);
 #pragma unroll
     for (int k = 0; k < enc::PER; ++k) dx_out[t * enc::H + lane + 32 * k] = dx[k];
@@ -223,7 +318,9 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 enc_add_ln_fwd_kernel(const T* __restrict__ y, const float* __restrict__ bias, const float* __restrict__ res,
                       const float* __restrict__ gamma, const float* __restrict__ beta, int64_t n_tok, float eps,
-                      float* __restrict__ out, __nv_bfloat16* __restrict__ out_lp, float* __restrict__ stats) {
+                      float* __restrict__ out, __nv_bfloat16* __restrict__ out_lp, float* __restrict__ stats,
+                      const int64_t* __restrict__ rng, float drop_p, int site) {
+  const DropCtx dc = make_drop(rng, drop_p, site, 16);
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -232,8 +329,11 @@ enc_add_ln_fwd_kernel(const T* __restrict__ y, const float* __restrict__ bias, c
 #pragma unroll
     for (int k = 0; k < enc::PER; ++k) {
       const int c = lane + 32 * k;
-      x[k] = to_f32(y[t * enc::H + c]) + (bias ? bias[c] : 0.f) + res[t * enc::H + c];
+      x[k] = to_f32(y[t * enc::H + c]) + (bias ? bias[c] : 0.f);
     }
+    drop_row(x, t, lane, dc);        // BertSelfOutput / BertOutput: LayerNorm(dropout(dense(h)) + residual)
+#pragma unroll
+    for (int k = 0; k < enc::PER; ++k) x[k] += res[t * enc::H + lane + 32 * k];
     float mean, rstd;
     ln_row(x, gamma, beta, eps, lane, o, mean, rstd);
 #pragma unroll
@@ -255,7 +355,9 @@ __global__ void __launch_bounds__(256)
 enc_add_ln_bwd_kernel(const T* __restrict__ y, const float* __restrict__ bias, const float* __restrict__ res,
                       const float* __restrict__ gamma, const float* __restrict__ stats,
                       const float* __restrict__ dout, const __nv_bfloat16* __restrict__ dout_lp, int64_t n_tok,
-                      float* __restrict__ dx_out, T* __restrict__ dy_out, float* __restrict__ part) {
+                      float* __restrict__ dx_out, T* __restrict__ dy_out, float* __restrict__ part,
+                      const int64_t* __restrict__ rng, float drop_p, int site) {
+  const DropCtx dc = make_drop(rng, drop_p, site, 16);
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -265,16 +367,24 @@ enc_add_ln_bwd_kernel(const T* __restrict__ y, const float* __restrict__ bias, c
 #pragma unroll
     for (int k = 0; k < enc::PER; ++k) {
       const int c = lane + 32 * k;
-      x[k] = to_f32(y[t * enc::H + c]) + (bias ? bias[c] : 0.f) + res[t * enc::H + c];
+      x[k] = to_f32(y[t * enc::H + c]) + (bias ? bias[c] : 0.f);
       dy[k] = (dout ? dout[t * enc::H + c] : 0.f) + (dout_lp ? __bfloat162float(dout_lp[t * enc::H + c]) : 0.f);
     }
+    const uint32_t keep = drop_bits(t, lane, dc);
+    drop_apply(x, keep, dc);         // rebuild the forward's LayerNorm input with the same mask
+#pragma unroll
+    for (int k = 0; k < enc::PER; ++k) x[k] += res[t * enc::H + lane + 32 * k];
     ln_row_bwd(x, dy, gamma, stats[2 * t], stats[2 * t + 1], lane, dx, acc[0], acc[1]);
+    float dyd[enc::PER];             // through the dropout: gradient of dense(h) + bias
+#pragma unroll
+    for (int k = 0; k < enc::PER; ++k) dyd[k] = dx[k];
+    drop_apply(dyd, keep, dc);
 #pragma unroll
     for (int k = 0; k < enc::PER; ++k) {
       const int c = lane + 32 * k;
       dx_out[t * enc::H + c] = dx[k];                 // gradient of the residual stream (fp32)
-      dy_out[t * enc::H + c] = from_f32<T>(dx[k]);    // gradient of the linear layer's output (its dtype)
-      acc[2][k] += dx[k];
+      dy_out[t * enc::H + c] = from_f32<T>(dyd[k]);   // gradient of the linear layer's output (its dtype)
+      acc[2][k] += dyd[k];
     }
   }
   ln_param_partials<3>(acc, part);
@@ -362,7 +472,9 @@ enc_colsum_kernel(const T* __restrict__ x, int64_t rows, int width, float* __res
 template <typename T>
 __global__ void __launch_bounds__(256)
 enc_attn_fwd_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ keymask, int seq_len, int n_heads,
-                    T* __restrict__ ctx, float* __restrict__ lse) {
+                    T* __restrict__ ctx, float* __restrict__ lse, const int64_t* __restrict__ rng, float drop_p,
+                    int site) {
+  const DropCtx dc = make_drop(rng, drop_p, site, 8);
   extern __shared__ float sm[];
   float* sK = sm;                                   // [L][33]
   float* sV = sm + (size_t)seq_len * 33;            // [L][33]
@@ -396,8 +508,9 @@ enc_attn_fwd_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ keyma
       const float corr = __expf(m - mnew);          // exp(-inf) = 0 on the first valid chunk
       l = l * corr + warp_sum(p);
       o *= corr;
+      const float pd = p * attn_drop_elem(dc, blockIdx.x, i, j);   // dropout on the probabilities, not on their sum
       const int jn = min(32, i + 1 - j0);
-      for (int jj = 0; jj < jn; ++jj) o = fmaf(__shfl_sync(0xffffffffu, p, jj), sV[(size_t)(j0 + jj) * 33 + lane], o);
+      for (int jj = 0; jj < jn; ++jj) o = fmaf(__shfl_sync(0xffffffffu, pd, jj), sV[(size_t)(j0 + jj) * 33 + lane], o);
       m = mnew;
     }
     const int64_t t = (int64_t)b * seq_len + i;
@@ -413,7 +526,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 enc_attn_bwd_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ keymask, const T* __restrict__ ctx,
                     const T* __restrict__ dctx, const float* __restrict__ lse, int seq_len, int n_heads,
-                    T* __restrict__ dqkv) {
+                    T* __restrict__ dqkv, const int64_t* __restrict__ rng, float drop_p, int site) {
+  const DropCtx dc = make_drop(rng, drop_p, site, 8);
   extern __shared__ float sm[];
   float* sQ = sm;                                   // [L][33] scaled queries
   float* sK = sQ + (size_t)seq_len * 33;
@@ -464,7 +578,7 @@ enc_attn_bwd_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ keyma
           s = fmaf(sQ[i * 33 + d], sK[jc * 33 + d], s);
           dp = fmaf(sdO[i * 33 + d], sV[jc * 33 + d], dp);
         }
-        const float ds = ok ? __expf(s - lse_i) * (dp - delta_i) : 0.f;   // lane = key
+        const float ds = ok ? __expf(s - lse_i) * (dp * attn_drop_elem(dc, blockIdx.x, i, j) - delta_i) : 0.f;   // lane = key
         const int jn = min(32, i + 1 - j0);
         for (int jj = 0; jj < jn; ++jj) dq = fmaf(__shfl_sync(0xffffffffu, ds, jj), sK[(size_t)(j0 + jj) * 33 + lane], dq);
       }
@@ -486,10 +600,12 @@ enc_attn_bwd_kernel(const T* __restrict__ qkv, const uint8_t* __restrict__ keyma
           dp = fmaf(sdO[ic * 33 + d], sV[j * 33 + d], dp);
         }
         const float p = ok ? __expf(s - s_lse[ic]) : 0.f;             // lane = query
-        const float ds = p * (dp - s_delta[ic]);
+        const float f = attn_drop_elem(dc, blockIdx.x, ic, j);
+        const float ds = p * (dp * f - s_delta[ic]);
+        const float pdrop = p * f;
         const int in = min(32, seq_len - i0);
         for (int ii = 0; ii < in; ++ii) {
-          const float pb = __shfl_sync(0xffffffffu, p, ii), dsb = __shfl_sync(0xffffffffu, ds, ii);
+          const float pb = __shfl_sync(0xffffffffu, pdrop, ii), dsb = __shfl_sync(0xffffffffu, ds, ii);
           dv = fmaf(pb, sdO[(size_t)(i0 + ii) * 33 + lane], dv);
           dk = fmaf(dsb, sQ[(size_t)(i0 + ii) * 33 + lane], dk);      // sQ already carries the 1/sqrt(d) scale
         }
@@ -594,7 +710,9 @@ __device__ __forceinline__ void fill_tile(const __nv_bfloat16* __restrict__ src,
 
 __global__ void __launch_bounds__(256)
 enc_attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __restrict__ keymask, int seq_len,
-                        int n_heads, __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse) {
+                        int n_heads, __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse,
+                        const int64_t* __restrict__ rng, float drop_p, int site) {
+  const DropCtx dc = make_drop(rng, drop_p, site, 8);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lp = enc::pad16(seq_len);
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);   // [lp][RS]
@@ -659,6 +777,15 @@ enc_attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __
         o[dt][0] *= corr[0]; o[dt][1] *= corr[0];
         o[dt][2] *= corr[1]; o[dt][3] *= corr[1];
       }
+      if (dc.on) {   // dropout on the probabilities that reach P V; the softmax sum l keeps all of them
+        const uint64_t half =
+            attn_row_half(attn_drop_call(dc, blockIdx.x, (uint32_t)tile, (uint32_t)(kb >> 4), (g >> 1) * 4 + t), g);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            p[nt][e] = attn_keep8(half, (e >> 1) * 4 + (e & 1) * 2 + nt, dc) ? p[nt][e] * dc.scale : 0.f;
+      }
       const uint32_t pa[4] = {pack_bf16x2(p[0][0], p[0][1]), pack_bf16x2(p[0][2], p[0][3]),
                               pack_bf16x2(p[1][0], p[1][1]), pack_bf16x2(p[1][2], p[1][3])};
       mma_cols(o, pa, sV, kb, lane);
@@ -683,7 +810,9 @@ enc_attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __
 __global__ void __launch_bounds__(256)
 enc_attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __restrict__ keymask,
                         const __nv_bfloat16* __restrict__ ctx, const __nv_bfloat16* __restrict__ dctx,
-                        const float* __restrict__ lse, int seq_len, int n_heads, __nv_bfloat16* __restrict__ dqkv) {
+                        const float* __restrict__ lse, int seq_len, int n_heads, __nv_bfloat16* __restrict__ dqkv,
+                        const int64_t* __restrict__ rng, float drop_p, int site) {
+  const DropCtx dc = make_drop(rng, drop_p, site, 8);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lp = enc::pad16(seq_len);
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);   // four [lp][RS] tiles
@@ -733,6 +862,9 @@ enc_attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __
       float s[2][4] = {}, dp[2][4] = {};
       mma_rows(s, qa, sK, kb, lane);
       mma_rows(dp, doa, sV, kb, lane);
+      uint64_t half = 0;
+      if (dc.on)
+        half = attn_row_half(attn_drop_call(dc, blockIdx.x, (uint32_t)tile, (uint32_t)(kb >> 4), (g >> 1) * 4 + t), g);
       float ds[2][4];
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt)
@@ -741,7 +873,9 @@ enc_attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __
           const int r = e >> 1;
           const int key = kb + 8 * nt + 2 * t + (e & 1), qi = i0 + g + 8 * r;
           const bool ok = key <= qi && s_mask[key] && lse_r[r] != CUDART_INF_F;
-          ds[nt][e] = ok ? __expf(s[nt][e] * scale - lse_r[r]) * (dp[nt][e] - delta_r[r]) : 0.f;
+          float dpe = dp[nt][e];       // dL/dP through the dropout: the forward's mask, recomputed
+          if (dc.on) dpe = attn_keep8(half, (e >> 1) * 4 + (e & 1) * 2 + nt, dc) ? dpe * dc.scale : 0.f;
+          ds[nt][e] = ok ? __expf(s[nt][e] * scale - lse_r[r]) * (dpe - delta_r[r]) : 0.f;
         }
       const uint32_t dsa[4] = {pack_bf16x2(ds[0][0], ds[0][1]), pack_bf16x2(ds[0][2], ds[0][3]),
                                pack_bf16x2(ds[1][0], ds[1][1]), pack_bf16x2(ds[1][2], ds[1][3])};
@@ -771,6 +905,10 @@ enc_attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __
       float st[2][4] = {}, dpt[2][4] = {};
       mma_rows(st, ka, sQ, qb, lane);
       mma_rows(dpt, va, sdO, qb, lane);
+      // transposed fragment: this lane holds (query 8 nt + 2 t + (e & 1), key g + 8 (e >> 1)) of the block, all in
+      // Philox call t * 4 + g / 2 (see attn_drop_call)
+      DropBlock db{};
+      if (dc.on) db = attn_drop_call(dc, blockIdx.x, (uint32_t)(qb >> 4), (uint32_t)tile, t * 4 + (g >> 1));
       float p[2][4], ds[2][4];
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt)
@@ -780,8 +918,12 @@ enc_attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __
           const int qi = qb + 8 * nt + 2 * t + (e & 1), key = j0 + g + 8 * r;
           const float lq = s_lse[qi];
           const bool ok = key <= qi && key_ok[r] && lq != CUDART_INF_F;
-          p[nt][e] = ok ? __expf(st[nt][e] * scale - lq) : 0.f;
-          ds[nt][e] = p[nt][e] * (dpt[nt][e] - s_delta[qi]);
+          const float pn = ok ? __expf(st[nt][e] * scale - lq) : 0.f;
+          float f = 1.f;
+          if (dc.on)   // byte (e & 1) * 8 + nt * 4 + (g & 1) * 2 + (e >> 1): word index static, shift per lane
+            f = ((db.w[(e & 1) * 2 + nt] >> (8 * ((g & 1) * 2 + (e >> 1)))) & 0xFFu) >= dc.thr ? dc.scale : 0.f;
+          ds[nt][e] = pn * (dpt[nt][e] * f - s_delta[qi]);
+          p[nt][e] = pn * f;          // the dropped probabilities: what multiplied V in the forward
         }
       const uint32_t pa[4] = {pack_bf16x2(p[0][0], p[0][1]), pack_bf16x2(p[0][2], p[0][3]),
                               pack_bf16x2(p[1][0], p[1][1]), pack_bf16x2(p[1][2], p[1][3])};
@@ -831,7 +973,7 @@ extern "C" int xr_enc_embed_ln_fwd(const float* table, int64_t n_table_rows, con
                                    const float* pos_emb, const float* type_emb, const float* gamma,
                                    const float* beta, int64_t batch, int64_t seq_len, int64_t dim, float eps,
                                    float* out, void* out_bf16, float* stats, uint8_t* mask, int32_t* err_flag,
-                                   void* stream) {
+                                   const int64_t* rng, float drop_p, int site, void* stream) {
   XR_CHECK_ARG(table && idx && pos_emb && type_emb && gamma && beta && out && stats && mask,
                "xr_enc_embed_ln_fwd: null pointer");
   XR_CHECK_ARG(dim == enc::H, "xr_enc_embed_ln_fwd: this build is specialised for hidden size %d", enc::H);
@@ -840,7 +982,7 @@ extern "C" int xr_enc_embed_ln_fwd(const float* table, int64_t n_table_rows, con
   if (n_tok == 0) return XR_OK;
   enc_embed_ln_fwd_kernel<<<enc_grid(n_tok), 256, 0, as_stream(stream)>>>(
       table, n_table_rows, idx, pos_emb, type_emb, gamma, beta, n_tok, (int)seq_len, eps, out, (__nv_bfloat16*)out_bf16,
-      stats, mask, err_flag);
+      stats, mask, err_flag, rng, drop_p, site);
   XR_LAUNCH_CHECK("enc_embed_ln_fwd");
   return XR_OK;
 }
@@ -849,7 +991,8 @@ extern "C" int xr_enc_embed_ln_bwd(const float* table, int64_t n_table_rows, con
                                    const float* pos_emb, const float* type_emb, const float* gamma,
                                    const float* stats, const float* dout, const void* dout_bf16, int64_t batch,
                                    int64_t seq_len, int64_t dim, float* dpos, float* dtype0, float* dgamma,
-                                   float* dbeta, void* workspace, void* stream) {
+                                   float* dbeta, void* workspace, const int64_t* rng, float drop_p, int site,
+                                   void* stream) {
   XR_CHECK_ARG(table && idx && pos_emb && type_emb && gamma && stats && (dout || dout_bf16) && dpos && dtype0 &&
                    dgamma && dbeta && workspace,
                "xr_enc_embed_ln_bwd: null pointer");
@@ -859,7 +1002,8 @@ extern "C" int xr_enc_embed_ln_bwd(const float* table, int64_t n_table_rows, con
   float* part = (float*)workspace;
   float* dx = part + (size_t)LNB_BLOCKS * 3 * enc::H;
   enc_embed_ln_bwd_kernel<<<LNB_BLOCKS, 256, 0, s>>>(table, n_table_rows, idx, pos_emb, type_emb, gamma, stats, dout,
-                                                     (const __nv_bfloat16*)dout_bf16, n_tok, (int)seq_len, dx, part);
+                                                     (const __nv_bfloat16*)dout_bf16, n_tok, (int)seq_len, dx, part,
+                                                     rng, drop_p, site);
   XR_LAUNCH_CHECK("enc_embed_ln_bwd");
   launch_fold(part, LNB_BLOCKS, 2, enc::H, dgamma, dbeta, nullptr, s);
   XR_LAUNCH_CHECK("enc_fold_partials");
@@ -873,17 +1017,19 @@ extern "C" int xr_enc_embed_ln_bwd(const float* table, int64_t n_table_rows, con
 
 extern "C" int xr_enc_add_ln_fwd(const void* y, int y_dtype, const float* bias, const float* residual,
                                  const float* gamma, const float* beta, int64_t n_tok, int64_t dim, float eps,
-                                 float* out, void* out_bf16, float* stats, void* stream) {
+                                 float* out, void* out_bf16, float* stats, const int64_t* rng, float drop_p,
+                                 int site, void* stream) {
   XR_CHECK_ARG(y && residual && gamma && beta && out && stats, "xr_enc_add_ln_fwd: null pointer");
   XR_CHECK_ARG(dim == enc::H && n_tok >= 0, "xr_enc_add_ln_fwd: bad sizes");
   if (n_tok == 0) return XR_OK;
   cudaStream_t s = as_stream(stream);
   if (y_dtype == XR_F32)
     enc_add_ln_fwd_kernel<float><<<enc_grid(n_tok), 256, 0, s>>>((const float*)y, bias, residual, gamma, beta, n_tok, eps,
-                                                                 out, (__nv_bfloat16*)out_bf16, stats);
+                                                                 out, (__nv_bfloat16*)out_bf16, stats, rng, drop_p, site);
   else if (y_dtype == XR_BF16)
     enc_add_ln_fwd_kernel<__nv_bfloat16><<<enc_grid(n_tok), 256, 0, s>>>(
-        (const __nv_bfloat16*)y, bias, residual, gamma, beta, n_tok, eps, out, (__nv_bfloat16*)out_bf16, stats);
+        (const __nv_bfloat16*)y, bias, residual, gamma, beta, n_tok, eps, out, (__nv_bfloat16*)out_bf16, stats, rng,
+        drop_p, site);
   else
     XR_CHECK_ARG(false, "xr_enc_add_ln_fwd: bad dtype");
   XR_LAUNCH_CHECK("enc_add_ln_fwd");
@@ -893,7 +1039,8 @@ extern "C" int xr_enc_add_ln_fwd(const void* y, int y_dtype, const float* bias, 
 extern "C" int xr_enc_add_ln_bwd(const void* y, int y_dtype, const float* bias, const float* residual,
                                  const float* gamma, const float* stats, const float* dout, const void* dout_bf16,
                                  int64_t n_tok, int64_t dim, float* dresidual, void* dy, float* dbias, float* dgamma,
-                                 float* dbeta, void* workspace, void* stream) {
+                                 float* dbeta, void* workspace, const int64_t* rng, float drop_p, int site,
+                                 void* stream) {
   XR_CHECK_ARG(y && residual && gamma && stats && (dout || dout_bf16) && dresidual && dy && dgamma && dbeta && workspace,
                "xr_enc_add_ln_bwd: null pointer");
   XR_CHECK_ARG(dim == enc::H && n_tok >= 1, "xr_enc_add_ln_bwd: bad sizes");
@@ -902,11 +1049,11 @@ extern "C" int xr_enc_add_ln_bwd(const void* y, int y_dtype, const float* bias, 
   if (y_dtype == XR_F32)
     enc_add_ln_bwd_kernel<float><<<LNB_BLOCKS, 256, 0, s>>>((const float*)y, bias, residual, gamma, stats, dout,
                                                             (const __nv_bfloat16*)dout_bf16, n_tok, dresidual,
-                                                            (float*)dy, part);
+                                                            (float*)dy, part, rng, drop_p, site);
   else if (y_dtype == XR_BF16)
     enc_add_ln_bwd_kernel<__nv_bfloat16><<<LNB_BLOCKS, 256, 0, s>>>(
         (const __nv_bfloat16*)y, bias, residual, gamma, stats, dout, (const __nv_bfloat16*)dout_bf16, n_tok, dresidual,
-        (__nv_bfloat16*)dy, part);
+        (__nv_bfloat16*)dy, part, rng, drop_p, site);
   else
     XR_CHECK_ARG(false, "xr_enc_add_ln_bwd: bad dtype");
   XR_LAUNCH_CHECK("enc_add_ln_bwd");
@@ -960,7 +1107,8 @@ extern "C" int xr_enc_colsum(const void* x, int dtype, int64_t rows, int64_t wid
 }
 
 static int enc_attention_launch_mma(const void* qkv, const uint8_t* keymask, const void* ctx, const void* dctx,
-                                    float* lse, int64_t batch, int seq_len, int n_heads, void* out, cudaStream_t s) {
+                                    float* lse, int64_t batch, int seq_len, int n_heads, void* out, cudaStream_t s,
+                                    const int64_t* rng, float drop_p, int site) {
   using bf = __nv_bfloat16;
   const unsigned grid = (unsigned)(batch * n_heads);
   static bool configured = false;
@@ -973,11 +1121,11 @@ static int enc_attention_launch_mma(const void* qkv, const uint8_t* keymask, con
   }
   if (!dctx) {
     enc_attn_fwd_mma_kernel<<<grid, 256, attn_mma_smem(seq_len, false), s>>>((const bf*)qkv, keymask, seq_len, n_heads,
-                                                                            (bf*)out, lse);
+                                                                            (bf*)out, lse, rng, drop_p, site);
     XR_LAUNCH_CHECK("enc_attn_fwd_mma");
   } else {
     enc_attn_bwd_mma_kernel<<<grid, 256, attn_mma_smem(seq_len, true), s>>>(
-        (const bf*)qkv, keymask, (const bf*)ctx, (const bf*)dctx, lse, seq_len, n_heads, (bf*)out);
+        (const bf*)qkv, keymask, (const bf*)ctx, (const bf*)dctx, lse, seq_len, n_heads, (bf*)out, rng, drop_p, site);
     XR_LAUNCH_CHECK("enc_attn_bwd_mma");
   }
   return XR_OK;
@@ -985,7 +1133,8 @@ static int enc_attention_launch_mma(const void* qkv, const uint8_t* keymask, con
 
 template <typename T>
 static int enc_attention_launch(const void* qkv, const uint8_t* keymask, const void* ctx, const void* dctx,
-                                float* lse, int64_t batch, int seq_len, int n_heads, void* out, cudaStream_t s) {
+                                float* lse, int64_t batch, int seq_len, int n_heads, void* out, cudaStream_t s,
+                                const int64_t* rng, float drop_p, int site) {
   const unsigned grid = (unsigned)(batch * n_heads);
   if (!dctx) {
     const size_t smem = (size_t)seq_len * 33 * 2 * 4;
@@ -994,7 +1143,8 @@ static int enc_attention_launch(const void* qkv, const uint8_t* keymask, const v
       XR_CUDA(cudaFuncSetAttribute(enc_attn_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(enc::MAX_L * 33 * 2 * 4)));
       conf = enc::MAX_L * 33 * 2 * 4;
     }
-    enc_attn_fwd_kernel<T><<<grid, 256, smem, s>>>((const T*)qkv, keymask, seq_len, n_heads, (T*)out, lse);
+    enc_attn_fwd_kernel<T><<<grid, 256, smem, s>>>((const T*)qkv, keymask, seq_len, n_heads, (T*)out, lse, rng, drop_p,
+                                                   site);
     XR_LAUNCH_CHECK("enc_attn_fwd");
   } else {
     const size_t smem = ((size_t)seq_len * 33 * 4 + 2 * (size_t)seq_len) * 4;
@@ -1005,7 +1155,7 @@ static int enc_attention_launch(const void* qkv, const uint8_t* keymask, const v
       conf = (enc::MAX_L * 33 * 4 + 2 * enc::MAX_L) * 4;
     }
     enc_attn_bwd_kernel<T><<<grid, 256, smem, s>>>((const T*)qkv, keymask, (const T*)ctx, (const T*)dctx, lse, seq_len,
-                                                   n_heads, (T*)out);
+                                                   n_heads, (T*)out, rng, drop_p, site);
     XR_LAUNCH_CHECK("enc_attn_bwd");
   }
   return XR_OK;
@@ -1013,7 +1163,7 @@ static int enc_attention_launch(const void* qkv, const uint8_t* keymask, const v
 
 extern "C" int xr_enc_attention(const void* qkv, const uint8_t* keymask, const void* ctx, const void* dctx,
                                 float* lse, int64_t batch, int64_t seq_len, int64_t n_heads, int64_t head_dim,
-                                int dtype, void* out, void* stream) {
+                                int dtype, void* out, const int64_t* rng, float drop_p, int site, void* stream) {
   XR_CHECK_ARG(qkv && keymask && lse && out, "xr_enc_attention: null pointer");
   XR_CHECK_ARG(head_dim == enc::HD, "xr_enc_attention: this build is specialised for head_dim = %d", enc::HD);
   XR_CHECK_ARG(batch >= 0 && seq_len >= 1 && seq_len <= enc::MAX_L && n_heads >= 1,
@@ -1022,12 +1172,14 @@ extern "C" int xr_enc_attention(const void* qkv, const uint8_t* keymask, const v
   if (batch == 0) return XR_OK;
   cudaStream_t s = as_stream(stream);
   if (dtype == XR_F32)
-    return enc_attention_launch<float>(qkv, keymask, ctx, dctx, lse, batch, (int)seq_len, (int)n_heads, out, s);
+    return enc_attention_launch<float>(qkv, keymask, ctx, dctx, lse, batch, (int)seq_len, (int)n_heads, out, s, rng,
+                                       drop_p, site);
   if (dtype == XR_BF16) {
     // the tensor-core kernels read 16-byte row segments: every head slice starts 64 B into a 16 B-aligned row
     XR_CHECK_ARG(((uintptr_t)qkv | (uintptr_t)out | (uintptr_t)ctx | (uintptr_t)dctx) % 16 == 0,
                  "xr_enc_attention: bf16 buffers must be 16-byte aligned");
-    return enc_attention_launch_mma(qkv, keymask, ctx, dctx, lse, batch, (int)seq_len, (int)n_heads, out, s);
+    return enc_attention_launch_mma(qkv, keymask, ctx, dctx, lse, batch, (int)seq_len, (int)n_heads, out, s, rng,
+                                    drop_p, site);
   }
   XR_CHECK_ARG(false, "xr_enc_attention: bad dtype");
   return XR_E_INVALID;

@@ -28,6 +28,7 @@
 //     is the sequential rule "redraw while the value was already taken", evaluated in parallel
 //     rounds where, among equal draws of one round, the lowest sequence position keeps the value.
 #include "common.cuh"
+#include "philox.cuh"
 
 #include <climits>
 
@@ -45,23 +46,9 @@ __host__ __device__ inline uint64_t splitmix64(uint64_t x) {
   return x ^ (x >> 31);
 }
 
-// Philox4x32-10 (Salmon et al. 2011): counter (c0..c3), key (k0, k1) -> 4 random words
-struct U4 {
-  uint32_t x, y, z, w;
-};
-__device__ __forceinline__ U4 philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                     uint32_t k1) {
-  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
-    const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-    k0 += W0; k1 += W1;
-  }
-  return U4{c0, c1, c2, c3};
-}
+// Philox4x32-10: philox.cuh (shared with the encoder's dropout)
+using xr::U4;
+using xr::philox;
 // uniform integer in [0, n): high 64 bits of (64 random bits) x n -- bias < n / 2^64
 __device__ __forceinline__ uint64_t uniform_below(const U4& r, uint64_t n) {
   const uint64_t u = ((uint64_t)r.x << 32) | (uint64_t)r.y;

@@ -109,14 +109,14 @@ PROTOTYPES = {
     "xr_score_topk": (_int, [_p, _i64, _p, _i64, _i64, _i64, _i64, _p, _p, _i64, _p, _p, _p, _p, _sz, _p]),
     "xr_retrieval_metrics": (_int, [_p, _i64, _i64, _p, _p, _i64, _p, _p, _p]),
     "xr_enc_ln_workspace_bytes": (_sz, [_i64]),
-    "xr_enc_embed_ln_fwd": (_int, [_p, _i64, _p, _p, _p, _p, _p, _i64, _i64, _i64, _f, _p, _p, _p, _p, _p, _p]),
-    "xr_enc_embed_ln_bwd": (_int, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p]),
-    "xr_enc_add_ln_fwd": (_int, [_p, _int, _p, _p, _p, _p, _i64, _i64, _f, _p, _p, _p, _p]),
-    "xr_enc_add_ln_bwd": (_int, [_p, _int, _p, _p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p]),
+    "xr_enc_embed_ln_fwd": (_int, [_p, _i64, _p, _p, _p, _p, _p, _i64, _i64, _i64, _f, _p, _p, _p, _p, _p, _p, _f, _int, _p]),
+    "xr_enc_embed_ln_bwd": (_int, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _f, _int, _p]),
+    "xr_enc_add_ln_fwd": (_int, [_p, _int, _p, _p, _p, _p, _i64, _i64, _f, _p, _p, _p, _p, _f, _int, _p]),
+    "xr_enc_add_ln_bwd": (_int, [_p, _int, _p, _p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _f, _int, _p]),
     "xr_enc_colsum_workspace_bytes": (_sz, [_i64]),
     "xr_enc_colsum": (_int, [_p, _int, _i64, _i64, _p, _p, _p]),
     "xr_enc_gelu": (_int, [_p, _p, _i64, _int, _p, _p]),
-    "xr_enc_attention": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _int, _p, _p]),
+    "xr_enc_attention": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _int, _p, _p, _f, _int, _p]),
 }
 
 _lib = None

@@ -15,8 +15,11 @@ the bf16 copy the next GEMM reads), and the deterministic column sum behind the 
 linear layers are plain GEMMs and go through cuBLAS (``torch.nn.functional.linear`` / ``@``).  ``compute_dtype=torch.bfloat16`` reproduces Lightning's
 ``bf16-mixed`` policy: bf16 GEMMs / attention / GELU, fp32 residual stream, LayerNorm and softmax.
 
-Not implemented: dropout (HF default 0.1 in training mode) — the module behaves as ``BertModel.eval()``
-does and as training with ``hidden_dropout_prob = attention_probs_dropout_prob = 0``.
+Dropout: ``hidden_dropout_prob`` / ``attention_probs_dropout_prob`` (HF defaults 0.1) are active in training
+mode, as in HuggingFace: on the embedding LayerNorm output, on the attention probabilities and on the two dense
+outputs of every layer.  The keep masks are counter-based (Philox4x32-10 keyed by a seed and a forward counter
+that live in device memory): the backward recomputes them, nothing is stored, CUDA-graph replays draw fresh
+masks.  ``.eval()`` (or both probabilities 0) gives the deterministic encoder the parity tests pin.
 """
 
 from __future__ import annotations
@@ -43,6 +46,9 @@ class EncoderConfig(pydantic.BaseModel):
     intermediate_size: int = 48
     max_seq_length: int = 32
     layer_norm_eps: float = 1e-12
+    # BertConfig defaults (models.py:92-100 passes neither): active in training mode only, as in HuggingFace
+    hidden_dropout_prob: float = 0.1
+    attention_probs_dropout_prob: float = 0.1
     pooling_mode: Literal["mean", "max", "cls", "lasttoken"] = "mean"
     is_normalized: bool = False
 
@@ -67,7 +73,7 @@ class _EmbedLN(torch.autograd.Function):
     Returns (x0 fp32, x0 rounded to bf16 when ``want_lowp`` else None, mask)."""
 
     @staticmethod
-    def forward(ctx, table, idx, pos_w, type_w, ln_w, ln_b, eps, want_lowp):
+    def forward(ctx, table, idx, pos_w, type_w, ln_w, ln_b, eps, want_lowp, rng=None, drop_p=0.0, site=0):
         dev = ops._require_cuda(table, idx, pos_w, type_w, ln_w, ln_b)
         b, l = idx.shape
         h = table.size(1)
@@ -80,20 +86,21 @@ class _EmbedLN(torch.autograd.Function):
         with ops._on(dev):
             N.call("xr_enc_embed_ln_fwd", ops._p(table), table.size(0), ops._p(idx), ops._p(pos_w), ops._p(type_w),
                    ops._p(ln_w), ops._p(ln_b), b, l, h, float(eps), ops._p(out), _pn(out_lp), ops._p(stats),
-                   ops._p(mask), None, ops._stream())
-        ctx.save_for_backward(table, idx, pos_w, type_w, ln_w, stats)
+                   ops._p(mask), None, _pn(rng), float(drop_p), int(site), ops._stream())
+        ctx.save_for_backward(table, idx, pos_w, type_w, ln_w, stats, rng)
+        ctx.drop = (float(drop_p), int(site))
         ctx.mark_non_differentiable(mask)
         return out, out_lp, mask
 
     @staticmethod
     def backward(ctx, dout, dout_lp, _dmask):
-        table, idx, pos_w, type_w, ln_w, stats = ctx.saved_tensors
+        table, idx, pos_w, type_w, ln_w, stats, rng = ctx.saved_tensors
         dev = idx.device
         b, l = idx.shape
         h = table.size(1)
         dout, dout_lp = _grad_pair(dout, dout_lp)
         if dout is None and dout_lp is None:
-            return (None,) * 8
+            return (None,) * 11
         dpos = torch.zeros_like(pos_w)
         dtype = torch.zeros_like(type_w)
         dg, db = torch.empty_like(ln_w), torch.empty_like(ln_w)
@@ -103,10 +110,10 @@ class _EmbedLN(torch.autograd.Function):
         with ops._on(dev):
             N.call("xr_enc_embed_ln_bwd", ops._p(table), table.size(0), ops._p(idx), ops._p(pos_w), ops._p(type_w),
                    ops._p(ln_w), ops._p(stats), _pn(dout), _pn(dout_lp), b, l, h, ops._p(dpos_l), ops._p(dt0),
-                   ops._p(dg), ops._p(db), ops._p(ws), ops._stream())
+                   ops._p(dg), ops._p(db), ops._p(ws), _pn(rng), ctx.drop[0], ctx.drop[1], ops._stream())
         dpos[:l] = dpos_l
         dtype[0] = dt0
-        return None, None, dpos, dtype, dg, db, None, None
+        return None, None, dpos, dtype, dg, db, None, None, None, None, None
 
 
 class _AddLN(torch.autograd.Function):
@@ -115,7 +122,7 @@ class _AddLN(torch.autograd.Function):
     same backward pass.  Returns (out fp32, out rounded to bf16 when ``want_lowp`` else None)."""
 
     @staticmethod
-    def forward(ctx, y, bias, residual, ln_w, ln_b, eps, want_lowp):
+    def forward(ctx, y, bias, residual, ln_w, ln_b, eps, want_lowp, rng=None, drop_p=0.0, site=0):
         dev = ops._require_cuda(y, bias, residual, ln_w, ln_b)
         y, residual = y.contiguous(), residual.contiguous()
         assert residual.dtype == torch.float32 and bias.dtype == torch.float32
@@ -125,18 +132,20 @@ class _AddLN(torch.autograd.Function):
         stats = torch.empty((n_tok, 2), dtype=torch.float32, device=dev)
         with ops._on(dev):
             N.call("xr_enc_add_ln_fwd", ops._p(y), ops._dt(y), ops._p(bias), ops._p(residual), ops._p(ln_w),
-                   ops._p(ln_b), n_tok, h, float(eps), ops._p(out), _pn(out_lp), ops._p(stats), ops._stream())
-        ctx.save_for_backward(y, bias, residual, ln_w, stats)
+                   ops._p(ln_b), n_tok, h, float(eps), ops._p(out), _pn(out_lp), ops._p(stats), _pn(rng),
+                   float(drop_p), int(site), ops._stream())
+        ctx.save_for_backward(y, bias, residual, ln_w, stats, rng)
+        ctx.drop = (float(drop_p), int(site))
         return out, out_lp
 
     @staticmethod
     def backward(ctx, dout, dout_lp):
-        y, bias, residual, ln_w, stats = ctx.saved_tensors
+        y, bias, residual, ln_w, stats, rng = ctx.saved_tensors
         dev = y.device
         n_tok, h = y.numel() // y.size(-1), y.size(-1)
         dout, dout_lp = _grad_pair(dout, dout_lp)
         if dout is None and dout_lp is None:
-            return (None,) * 7
+            return (None,) * 10
         dres = torch.empty_like(residual)
         dy = torch.empty_like(y)
         dbias, dg, db = torch.empty_like(bias), torch.empty_like(ln_w), torch.empty_like(ln_w)
@@ -144,8 +153,8 @@ class _AddLN(torch.autograd.Function):
         with ops._on(dev):
             N.call("xr_enc_add_ln_bwd", ops._p(y), ops._dt(y), ops._p(bias), ops._p(residual), ops._p(ln_w),
                    ops._p(stats), _pn(dout), _pn(dout_lp), n_tok, h, ops._p(dres), ops._p(dy), ops._p(dbias),
-                   ops._p(dg), ops._p(db), ops._p(ws), ops._stream())
-        return dy, dbias, dres, dg, db, None, None
+                   ops._p(dg), ops._p(db), ops._p(ws), _pn(rng), ctx.drop[0], ctx.drop[1], ops._stream())
+        return dy, dbias, dres, dg, db, None, None, None, None, None
 
 
 class _Linear(torch.autograd.Function):
@@ -206,7 +215,7 @@ class _Attention(torch.autograd.Function):
     """Causal + key-padding multi-head self-attention on packed qkv (B, L, 3H), head_dim 32."""
 
     @staticmethod
-    def forward(ctx, qkv, mask, n_heads):
+    def forward(ctx, qkv, mask, n_heads, rng=None, drop_p=0.0, site=0):
         dev = ops._require_cuda(qkv, mask)
         qkv, mask = qkv.contiguous(), mask.contiguous()
         b, l, h3 = qkv.shape
@@ -215,22 +224,24 @@ class _Attention(torch.autograd.Function):
         lse = torch.empty((b, n_heads, l), dtype=torch.float32, device=dev)
         with ops._on(dev):
             N.call("xr_enc_attention", ops._p(qkv), ops._p(mask), None, None, ops._p(lse), b, l, n_heads,
-                   hid // n_heads, ops._dt(qkv), ops._p(out), ops._stream())
-        ctx.save_for_backward(qkv, mask, out, lse)
+                   hid // n_heads, ops._dt(qkv), ops._p(out), _pn(rng), float(drop_p), int(site), ops._stream())
+        ctx.save_for_backward(qkv, mask, out, lse, rng)
         ctx.n_heads = n_heads
+        ctx.drop = (float(drop_p), int(site))
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        qkv, mask, out, lse = ctx.saved_tensors
+        qkv, mask, out, lse, rng = ctx.saved_tensors
         b, l, h3 = qkv.shape
         hid = h3 // 3
         dout = dout.contiguous().to(qkv.dtype)
         dqkv = torch.empty_like(qkv)
         with ops._on(qkv.device):
             N.call("xr_enc_attention", ops._p(qkv), ops._p(mask), ops._p(out), ops._p(dout), ops._p(lse), b, l,
-                   ctx.n_heads, hid // ctx.n_heads, ops._dt(qkv), ops._p(dqkv), ops._stream())
-        return dqkv, None, None
+                   ctx.n_heads, hid // ctx.n_heads, ops._dt(qkv), ops._p(dqkv), _pn(rng), ctx.drop[0], ctx.drop[1],
+                   ops._stream())
+        return dqkv, None, None, None, None, None
 
 
 # ---- module tree with HuggingFace BertModel's parameter names -------------------------------------------
@@ -294,7 +305,8 @@ class SeqEncoder(torch.nn.Module):
     int64 history indices (0 = padding, right-padded as ``pad_sequence`` does, data.py:801), ``table`` the
     frozen fp32 item table (N+1, H) with a zero row 0 (models.py:247-253)."""
 
-    def __init__(self, config: EncoderConfig | None = None, *, compute_dtype: torch.dtype = torch.float32):
+    def __init__(self, config: EncoderConfig | None = None, *, compute_dtype: torch.dtype = torch.float32,
+                 seed: int = 0):
         super().__init__()
         self.config = cfg = config or EncoderConfig()
         assert cfg.hidden_size == 384 and cfg.hidden_size // cfg.num_attention_heads == 32, (
@@ -304,6 +316,8 @@ class SeqEncoder(torch.nn.Module):
         self.embeddings = _Embeddings(cfg)
         self.encoder = _Encoder(cfg)
         self.pooler = _Pooler(cfg.hidden_size)
+        # dropout state {seed, forward counter}: device memory, so CUDA-graph replays draw fresh masks
+        self.register_buffer("_rng", torch.tensor([int(seed), 0], dtype=torch.int64), persistent=False)
         self.apply(self._init_weights)
 
     @staticmethod
@@ -331,22 +345,32 @@ class SeqEncoder(torch.nn.Module):
         lowp = cd != torch.float32
         idx = item_idx[:, -cfg.max_seq_length:]
         emb = self.embeddings
+        # dropout (training mode only): this forward's {seed, counter} snapshot travels to the backward through
+        # the autograd contexts; the module's counter advances on the device
+        ph = cfg.hidden_dropout_prob if self.training else 0.0
+        pa = cfg.attention_probs_dropout_prob if self.training else 0.0
+        rng = None
+        if ph > 0 or pa > 0:
+            rng = self._rng.clone()
+            self._rng[1] += 1
         x, x_lp, mask = _EmbedLN.apply(table, idx, emb.position_embeddings.weight, emb.token_type_embeddings.weight,
-                                       emb.LayerNorm.weight, emb.LayerNorm.bias, cfg.layer_norm_eps, lowp)
+                                       emb.LayerNorm.weight, emb.LayerNorm.bias, cfg.layer_norm_eps, lowp,
+                                       rng, ph, 0)
         n_layers = len(self.encoder.layer)
         for li, layer in enumerate(self.encoder.layer):
             att, att_out, ffn_out = getattr(layer.attention, "self"), layer.attention.output, layer.output
             w = torch.cat([att.query.weight, att.key.weight, att.value.weight], 0)
             b = torch.cat([att.query.bias, att.key.bias, att.value.bias], 0)
             qkv = _Linear.apply(x_lp if lowp else x, w, b)                       # (B, L, 3H)
-            ctx = _Attention.apply(qkv, mask, cfg.num_attention_heads)
+            ctx = _Attention.apply(qkv, mask, cfg.num_attention_heads, rng, pa, 4 * li + 1)
             x, x_lp = _AddLN.apply(_Linear.apply(ctx, att_out.dense.weight, None), att_out.dense.bias, x,
-                                   att_out.LayerNorm.weight, att_out.LayerNorm.bias, cfg.layer_norm_eps, lowp)
+                                   att_out.LayerNorm.weight, att_out.LayerNorm.bias, cfg.layer_norm_eps, lowp,
+                                   rng, ph, 4 * li + 2)
             inter = _Gelu.apply(_Linear.apply(x_lp if lowp else x, layer.intermediate.dense.weight,
                                               layer.intermediate.dense.bias))
             x, x_lp = _AddLN.apply(_Linear.apply(inter, ffn_out.dense.weight, None), ffn_out.dense.bias, x,
                                    ffn_out.LayerNorm.weight, ffn_out.LayerNorm.bias, cfg.layer_norm_eps,
-                                   lowp and li + 1 < n_layers)
+                                   lowp and li + 1 < n_layers, rng, ph, 4 * li + 3)
         return x, mask
 
     def pool(self, tokens: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
