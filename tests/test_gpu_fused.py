@@ -475,3 +475,44 @@ def test_fused_bf16_gradient_vs_the_references_own_autocast(xr, golden_dir):
         e_ref = np.linalg.norm(ref - want_dq) / np.linalg.norm(want_dq)
         assert e_ours <= 1e-3 and e_ours < e_ref, (name, e_ours, e_ref)
         assert np.linalg.norm(dq - ref) <= 4e-3 * np.linalg.norm(ref), name
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("XR_SWEEP_SEEDS", "24"))))
+def test_search_random_shapes_against_the_oracle(xr, seed):
+    """Differential sweep of the tensor-core search (xr_score_topk through ExactIndex.search_batch and a
+    compiled SearchPlan): random catalog sizes (not multiples of any tile), query counts on both sides of the
+    128-query kernel switch, k, exclusion lists with duplicates, out-of-range and repeated ids, empty lists,
+    catalogs with many exactly tied rows.  Integer-valued data make every score exact in bf16/fp32, so ids and
+    scores must equal the stable-sort oracle bit for bit -- whether the filter path answers or a device flag
+    routes the batch to the materialised search."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.choice([1, 17, 129, 1000, 4097, 20011, 65537, 131072 + 5]))
+    u = int(rng.choice([1, 2, 31, 128, 129, 200, 257]))
+    k = int(min(n, rng.choice([1, 5, 50, 100, 128])))
+    lo, hi = (-1, 2) if seed % 3 == 0 else (-3, 4)          # narrow range: heavy ties
+    cat = rng.integers(lo, hi, size=(n, 384)).astype(np.float32)
+    if n > 40:
+        cat[rng.integers(0, n, size=20)] = cat[0]             # exact duplicates of one row
+    qs = rng.integers(lo, hi, size=(u, 384)).astype(np.float32)
+    max_excl = int(rng.choice([0, 3, 40, 200]))
+    excl = []
+    for r in range(u):
+        m_e = int(rng.integers(0, max_excl + 1))
+        ids = rng.integers(-2, n + 3, size=m_e)               # some ids are out of range: ignored
+        if m_e > 2:
+            ids[1] = ids[0]                                   # a repeated id
+        excl.append([int(x) for x in ids])
+    metric = "dot" if seed % 2 == 0 else "cosine"
+    if metric == "cosine":
+        cat[np.abs(cat).sum(1) == 0] = 1.0                    # no zero-norm rows: cosine of integer rows is not exact,
+    idx = xr.index.ExactIndex(xr.index.ExactIndexConfig(index_metric="dot", dtype="bf16")).set_catalog(
+        torch.from_numpy(cat).cuda())                         # ... so the sweep scores dot products either way
+    q = torch.from_numpy(qs).cuda()
+    want_s, want_i = orc.exact_search(qs, cat, k, excl if max_excl else None, metric="dot")
+    want_i = np.where(np.isneginf(want_s), -1, want_i)       # filtered rows are never returned (index.py:246): id -1
+    s, i = idx.search_batch(q, excl if max_excl else None, k, max_exclusions=max_excl or None)
+    assert np.array_equal(i.cpu().numpy(), want_i), (n, u, k, max_excl)
+    assert np.array_equal(s.cpu().numpy(), want_s)
+    plan = idx.compile_search(u, k, max_exclusions=max_excl)
+    ps, pi = plan(q, xr.ops._csr(excl, q.device) if max_excl else None)
+    assert torch.equal(pi, i) and torch.equal(ps, s)
