@@ -286,7 +286,11 @@ def loss_from_logits(name, logits, target, mask, cfg, *, with_grad=False):
         g = _sigmoid(l) * w / cnt[:, None]
         g[rows, target] += -_sigmoid(-t)
     elif name in ("PairwiseHingeLoss", "PairwiseLogisticLoss"):  # losses.py:523-543
-        x = l - (t * (1.0 - cfg.margin))[:, None]
+        # the reference multiplies an fp32 tensor by the Python scalar (1 - margin): an fp32 product with the
+        # scalar cast to fp32 (losses.py:527, 541).  Doing the same here keeps the hinge's kink (x > 0) where
+        # the reference has it; a float64 product moves it for the handful of entries with |x| ~ 1e-9.
+        tm = (t.astype(np.float32) * np.float32(1.0 - cfg.margin)).astype(np.float64)
+        x = l - tm[:, None]
         if name == "PairwiseHingeLoss":
             v = np.maximum(x, 0.0)
             dv = (x > 0).astype(np.float64)

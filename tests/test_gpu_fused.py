@@ -516,3 +516,28 @@ def test_search_random_shapes_against_the_oracle(xr, seed):
     plan = idx.compile_search(u, k, max_exclusions=max_excl)
     ps, pi = plan(q, xr.ops._csr(excl, q.device) if max_excl else None)
     assert torch.equal(pi, i) and torch.equal(ps, s)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_fused_random_shapes_against_the_oracle(xr, seed):
+    """Stream-K edge cases of the fused loss kernel: random (rows, pool) shapes with extreme aspect ratios --
+    one candidate tile and thousands of rows (every CTA crosses many row blocks: many segments), one row block
+    and a long pool (one row block split over all CTAs), fewer tiles than CTAs, sizes one off every tile
+    boundary -- for a random fused kind and config; loss and dL/dq against the float64 oracle on the operands
+    the kernel saw, and forward-only == forward+backward."""
+    rng = np.random.default_rng(500 + seed)
+    shapes = [(4000, 64), (5000, 1), (1, 9000), (128, 20000), (129, 12801), (17, 17), (2500, 130), (640, 641),
+              (3000, 700), (127, 63)]
+    m, cn = shapes[seed % len(shapes)]
+    if seed >= len(shapes):
+        m, cn = int(rng.integers(1, 3000)), int(rng.integers(1, 3000))
+    name = FUSED[int(rng.integers(0, len(FUSED)))]
+    cfg_kw, lbf = [({}, True), ({"scale": 5.0, "margin": 0.3}, True), ({"mask_false_negatives": False}, False),
+                   ({"scale": 0.5}, False)][int(rng.integers(0, 4))]
+    q, pos, neg = make_inputs(m, cn, seed=seed)
+    loss, dq, (qh, ph, nh, q_inv) = run_fused(xr, name, q, pos, neg, cfg_kw, lbf)
+    want, want_dq = oracle_on_bf16(name, qh, ph, nh, q_inv, cfg_kw, lbf)
+    assert loss == pytest.approx(want, rel=2e-3, abs=2e-3), (name, m, cn, cfg_kw, loss, want)
+    assert np.linalg.norm(dq - want_dq) <= 2e-3 * np.linalg.norm(want_dq) + 1e-6, (name, m, cn, cfg_kw)
+    loss_f, _, _ = run_fused(xr, name, q, pos, neg, cfg_kw, lbf, want_grad=False)
+    assert loss_f == loss
