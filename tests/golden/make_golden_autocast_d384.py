@@ -45,6 +45,18 @@ def main():
             rec[f"{tag}/loss/{loss_name}"] = np.array(loss.item(), dtype=np.float64)
             rec[f"{tag}/dq/{loss_name}"] = qq.grad.numpy()
     np.savez_compressed(OUT / "losses_pool_autocast_bf16_d384.npz", **rec)
+    # the same under a non-default margin and scale: under autocast the reference rounds target * (1 - margin)
+    # and logits - that to bf16 (bf16 tensor arithmetic, losses.py:527, 541), and logits * scale (losses.py:486)
+    rec2 = {"query": q.numpy(), "pos": pos.numpy(), "neg": neg.numpy(), "cfg": np.array([5.0, 0.3])}
+    cfg2 = ref.LossConfig(scale=5.0, margin=0.3)
+    for loss_name, cls in zip(LOSS_NAMES, ref.LOSS_CLASSES):
+        qq = q.clone().requires_grad_(True)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            loss = cls(cfg2)(query_embed=qq, candidate_embed=cand)
+        loss.backward()
+        rec2[f"autocast/loss/{loss_name}"] = np.array(loss.item(), dtype=np.float64)
+        rec2[f"autocast/dq/{loss_name}"] = qq.grad.numpy()
+    np.savez_compressed(OUT / "losses_pool_autocast_bf16_d384_margin.npz", **rec2)
     for name in LOSS_NAMES:
         a, b = rec[f"autocast/dq/{name}"].astype(np.float64), rec[f"fp32/dq/{name}"].astype(np.float64)
         print(f"{name:28s} loss autocast {float(rec[f'autocast/loss/{name}']):.5f} fp32 {float(rec[f'fp32/loss/{name}']):.5f}"
