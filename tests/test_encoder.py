@@ -375,3 +375,32 @@ def test_encoder_trains_with_dropout_and_graph_replays_draw_fresh_masks():
         e1 = enc(hist, table)["token_embeddings"]
         e2 = enc(hist, table)["token_embeddings"]
     assert torch.equal(e1, e2)
+
+
+@pytest.mark.gpu
+def test_training_loop_reduces_the_loss():
+    """End to end as INTEGRATION.md 6 / 9 wire it: SeqEncoder (bf16-mixed, dropout on) -> PoolLossStep ->
+    encoder backward from the step's dtok -> AdamW.  Forty steps on one small batch must cut the InfoNCE loss
+    substantially (the encoder memorises the batch), with finite parameters throughout."""
+    import xfmr_rec_b200 as xr
+    from xfmr_rec_b200.data import synthetic_batch
+    from xfmr_rec_b200.encoder import EncoderConfig, SeqEncoder, encoder_train_step
+
+    B, L = 16, 32
+    b = synthetic_batch(400, B, L, dim=384, seed=9)
+    table = torch.from_numpy(b["table"]).cuda()
+    hist, pos, neg = (torch.from_numpy(b[k]).cuda() for k in ("history_item_idx", "pos_item_idx", "neg_item_idx"))
+    torch.manual_seed(1)
+    enc = SeqEncoder(EncoderConfig(num_hidden_layers=2, intermediate_size=256, max_seq_length=L),
+                     compute_dtype=torch.bfloat16, seed=5).cuda().train()
+    emb = xr.models.ItemEmbeddings(table, add_padding_row=False).cuda()
+    step = xr.PoolLossStep(emb, xr.InfoNCELoss(xr.LossConfig()), B, L, token_dtype=torch.float32, logits_bf16=True)
+    opt = torch.optim.AdamW([p for p in enc.parameters() if p.requires_grad], lr=2e-3, weight_decay=0.0)
+    losses = []
+    for _ in range(40):
+        opt.zero_grad(set_to_none=True)
+        losses.append(float(encoder_train_step(enc, step, table, hist, pos, neg)))
+        opt.step()
+    assert all(np.isfinite(losses)), losses
+    assert np.mean(losses[-5:]) < 0.6 * np.mean(losses[:3]), (losses[:3], losses[-5:])
+    assert all(bool(torch.isfinite(p).all()) for p in enc.parameters())
