@@ -221,8 +221,8 @@ int xr_pool_step_monitor(int64_t n_pos, int64_t dim, const xr_loss_config* cfg, 
                          double* losses_cos, double* stats_out, void* workspace,
                          size_t workspace_bytes, void* stream);
 /* The compute phase of the step WITH the monitoring folded into the train kernel (trainer.py:250-263 +
- * 288-300 from ONE tensor-core pass): train loss, dL/dtok, losses_dot[7], losses_cos[7], stats[16].  InfoNCE
- * train loss, scale > 0, no hard-negative mining; call after xr_pool_step_ingest on the same stream with a
+ * 288-300 from ONE tensor-core pass): train loss, dL/dtok, losses_dot[7], losses_cos[7], stats[16].  Dot-family
+ * train losses (InfoNCE, NCE, pairwise hinge / logistic), scale > 0, no hard-negative mining; call after xr_pool_step_ingest on the same stream with a
  * workspace of xr_pool_step_monitor_workspace_bytes.  The dot family equals xr_pool_step_monitor bit for bit;
  * the cosine family is evaluated as (score / |q|) / |n| with fp32 inverse norms.                          */
 int xr_pool_step_compute_mon(int64_t n_pos, int64_t dim, int loss_kind, const xr_loss_config* cfg,
@@ -230,11 +230,11 @@ int xr_pool_step_compute_mon(int64_t n_pos, int64_t dim, int loss_kind, const xr
                              double* losses_cos, double* stats_out, void* workspace, size_t workspace_bytes,
                              void* stream);
 /* The same one-pass evaluation for exact shapes (the module path of trainer.py:213-264, compute_losses):
- * InfoNCE loss (loss_out[0], fp32 copy in the low half of loss_out[1]) and dq (m, dim) fp32 (nullable),
+ * train loss of a dot-family kind (loss_out[0], fp32 copy in the low half of loss_out[1]) and dq (m, dim) fp32 (nullable),
  * losses_dot[7], losses_cos[7], stats[16] from ONE tensor-core pass.  bf16 operands, dim 384.            */
 size_t xr_fused_pool_loss_mon_workspace_bytes(int64_t m, int64_t cn, int64_t dim);
 int xr_fused_pool_loss_mon(const void* q, const void* pos, const void* neg, int64_t m, int64_t cn, int64_t dim,
-                           const xr_loss_config* cfg, float grad_scale, float* dq, double* loss_out,
+                           int loss_kind, const xr_loss_config* cfg, float grad_scale, float* dq, double* loss_out,
                            double* losses_dot, double* losses_cos, double* stats_out, void* workspace,
                            size_t workspace_bytes, void* stream);
 

@@ -249,3 +249,32 @@ def test_step_orders_after_the_producer_stream(xr):
         torch.cuda.synchronize()
         assert torch.equal(loss, want_loss), (float(loss), float(want_loss))
         assert torch.equal(dtok.reshape(want_grad.shape), want_grad)
+
+
+@pytest.mark.parametrize("name", ["NCELoss", "PairwiseHingeLoss", "PairwiseLogisticLoss"])
+@pytest.mark.parametrize("cfg_kw", [{}, dict(mask_false_negatives=False, scale=3.0, margin=0.25)])
+def test_one_pass_monitoring_serves_every_dot_family_train_loss(xr, name, cfg_kw):
+    """The one-pass monitoring kernel with NCE / pairwise hinge / pairwise logistic (BPR) as the TRAIN loss:
+    train loss and gradient bit-identical to the unmonitored step, every logged loss and statistic equal to the
+    three-pass monitoring sequence (dot family and statistics to fp32 summation order, cosine family to bf16
+    tolerance) and to the float64 oracle."""
+    b = orc.synth_batch(3000, 16, 60, dim=384, seed=8)
+    emb = xr.models.ItemEmbeddings(torch.from_numpy(b["table"]), add_padding_row=False).cuda()
+    cfg = xr.LossConfig(**cfg_kw)
+    loss_fn = getattr(xr, name)(cfg)
+    plain = xr.PoolLossStep(emb, loss_fn, 16, 60)
+    one = xr.PoolLossStep(emb, loss_fn, 16, 60, monitor=True)
+    three = xr.PoolLossStep(emb, loss_fn, 16, 60, monitor=True, monitor_one_pass=False)
+    assert one.monitor_one_pass and not three.monitor_one_pass
+    l0, g0 = run_step(plain, b, torch.bfloat16)
+    l1, g1 = run_step(one, b, torch.bfloat16)
+    l3, g3 = run_step(three, b, torch.bfloat16)
+    assert torch.equal(l0, l1) and torch.equal(g0, g1) and torch.equal(l0, l3) and torch.equal(g0, g3)
+    got1, st1 = one.loss_dict()
+    got3, st3 = three.loss_dict()
+    for k, v in got3.items():
+        tol = 4e-3 if k.split("/")[1] in orc.COSINE_LOSSES else 1e-6
+        assert float(got1[k]) == pytest.approx(float(v), rel=tol, abs=tol), k
+    for k, v in st3.items():
+        assert st1[k] == pytest.approx(v, rel=1e-6, abs=1e-9), k
+    assert float(got1[f"loss/{name}"]) == pytest.approx(float(l1), rel=1e-6)

@@ -735,10 +735,12 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
               vc[4 * jj + 3] = __float_as_uint(__fmul_rn(__fmul_rn(__uint_as_float(v[4 * jj + 3]), mon_iq), w4.w));
             }
             if (ncols >= 16) {
-              group_all<false, RBF, true, false>(v, ncols, t_eff, tm, zref2, scale2, p.scale, p.margin, round_scaled, acc);
+              group_all<false, RBF, true, KIND != XR_LOSS_INFONCE>(v, ncols, t_eff, tm, zref2, scale2, p.scale, p.margin,
+                                                                  round_scaled, acc);
               group_all<true, false, true>(vc, ncols, mon_tc_eff, 0.f, 0.f, 0.f, 1.f, p.margin, false, acc_c);
             } else {
-              group_all<false, RBF, false, false>(v, ncols, t_eff, tm, zref2, scale2, p.scale, p.margin, round_scaled, acc);
+              group_all<false, RBF, false, KIND != XR_LOSS_INFONCE>(v, ncols, t_eff, tm, zref2, scale2, p.scale, p.margin,
+                                                                   round_scaled, acc);
               group_all<true, false, false>(vc, ncols, mon_tc_eff, 0.f, 0.f, 0.f, 1.f, p.margin, false, acc_c);
             }
           }
@@ -796,8 +798,9 @@ fused_pool_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (MON && row_ok) {
           const size_t off = (((size_t)slot * CG + cg) * BM + r_local) * NSCAL_ALL;
           float4* dd = reinterpret_cast<float4*>(p.part_all + off);
-          // InfoNCE's softmax sum IS the train epilogue's sum of weights (same exponentials, same mask)
-          dd[0] = make_float4(acc.cnt, sum_w, acc.s_sp, acc.s_hinge);
+          // an InfoNCE train launch does not recompute the softmax sum: it IS the train epilogue's sum of
+          // weights (same exponentials, same mask); the other train kinds accumulate it with the rest
+          dd[0] = make_float4(acc.cnt, KIND == XR_LOSS_INFONCE ? sum_w : acc.s_exp, acc.s_sp, acc.s_hinge);
           dd[1] = make_float4(acc.s_logi, acc.s_contr, acc.s_v, acc.s_sq);
           dd[2] = make_float4(acc.vmin, acc.vmax, 0.f, 0.f);
           float4* dc = reinterpret_cast<float4*>(p.part_all_cos + off);
@@ -1267,25 +1270,27 @@ static int launch_fused1(const CUtensorMap& tq, const CUtensorMap& tb, const Fus
   XR_LAUNCH_CHECK("fused_pool_kernel");
   return XR_OK;
 }
-// train kernel that also accumulates the monitoring sums of both logit families (InfoNCE train loss)
-template <bool RBF>
+// train kernel that also accumulates the monitoring sums of both logit families (dot-family train losses)
+template <int KIND, bool RBF>
 static int launch_fused_mon1(const CUtensorMap& tq, const CUtensorMap& tb, const FusedParams& p, int grid,
                              cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    XR_CUDA(cudaFuncSetAttribute(fused_pool_kernel<XR_LOSS_INFONCE, RBF, 0, true>,
+    XR_CUDA(cudaFuncSetAttribute(fused_pool_kernel<KIND, RBF, 0, true>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, fk::SMEM_BYTES));
     configured = true;
   }
   FusedParams pp = p;
   pp.ctrl_low = g_ctrl_low;
-  fused_pool_kernel<XR_LOSS_INFONCE, RBF, 0, true><<<grid, fk::THREADS, fk::SMEM_BYTES, s>>>(tq, tb, pp);
+  fused_pool_kernel<KIND, RBF, 0, true><<<grid, fk::THREADS, fk::SMEM_BYTES, s>>>(tq, tb, pp);
   XR_LAUNCH_CHECK("fused_pool_kernel<MON>");
   return XR_OK;
 }
+template <int KIND>
 static int launch_fused_mon(const CUtensorMap& tq, const CUtensorMap& tb, const FusedParams& p, int grid,
                             cudaStream_t s) {
-  return p.logits_bf16 ? launch_fused_mon1<true>(tq, tb, p, grid, s) : launch_fused_mon1<false>(tq, tb, p, grid, s);
+  return p.logits_bf16 ? launch_fused_mon1<KIND, true>(tq, tb, p, grid, s)
+                       : launch_fused_mon1<KIND, false>(tq, tb, p, grid, s);
 }
 
 template <int KIND>
@@ -1417,7 +1422,7 @@ static int fused_launch_all(const void* q, const void* pos, const void* neg, lon
   if ((rc = launch_fused<fk::KIND_DIAG>(tq, tp, pd, pl.rb < n_sm ? pl.rb : n_sm, s))) return rc;
 
   const float* zref = nullptr;
-  if (loss_kind == XR_LOSS_INFONCE && !cfg->mask_false_negatives) {
+  if ((loss_kind == XR_LOSS_INFONCE || mon) && !cfg->mask_false_negatives) {   // (the monitored InfoNCE needs it too)
     unsigned* nmax = (unsigned*)(ws.flags + 8);
     negnorm_max_kernel<<<n_sm * 4, 256, 0, s>>>((const __nv_bfloat16*)neg, cn, nmax, dyn_main);
     XR_LAUNCH_CHECK("negnorm_max");
@@ -1453,7 +1458,7 @@ static int fused_launch_all(const void* q, const void* pos, const void* neg, lon
   switch (loss_kind) {
     case XR_LOSS_INFONCE:
       if (mon) {
-        rc = launch_fused_mon(tq, tn, p, grid, s);
+        rc = launch_fused_mon<XR_LOSS_INFONCE>(tq, tn, p, grid, s);
         break;
       }
       if (g_wait_stats || g_ablate || g_timeline) {   // profiling aid
@@ -1466,9 +1471,17 @@ static int fused_launch_all(const void* q, const void* pos, const void* neg, lon
       }
       else rc = launch_fused<XR_LOSS_INFONCE>(tq, tn, p, grid, s);
       break;
-    case XR_LOSS_NCE: rc = launch_fused<XR_LOSS_NCE>(tq, tn, p, grid, s); break;
-    case XR_LOSS_PAIRWISE_HINGE: rc = launch_fused<XR_LOSS_PAIRWISE_HINGE>(tq, tn, p, grid, s); break;
-    case XR_LOSS_PAIRWISE_LOGISTIC: rc = launch_fused<XR_LOSS_PAIRWISE_LOGISTIC>(tq, tn, p, grid, s); break;
+    case XR_LOSS_NCE:
+      rc = mon ? launch_fused_mon<XR_LOSS_NCE>(tq, tn, p, grid, s) : launch_fused<XR_LOSS_NCE>(tq, tn, p, grid, s);
+      break;
+    case XR_LOSS_PAIRWISE_HINGE:
+      rc = mon ? launch_fused_mon<XR_LOSS_PAIRWISE_HINGE>(tq, tn, p, grid, s)
+               : launch_fused<XR_LOSS_PAIRWISE_HINGE>(tq, tn, p, grid, s);
+      break;
+    case XR_LOSS_PAIRWISE_LOGISTIC:
+      rc = mon ? launch_fused_mon<XR_LOSS_PAIRWISE_LOGISTIC>(tq, tn, p, grid, s)
+               : launch_fused<XR_LOSS_PAIRWISE_LOGISTIC>(tq, tn, p, grid, s);
+      break;
     case XR_LOSS_CONTRASTIVE: rc = launch_fused<XR_LOSS_CONTRASTIVE>(tq, tn, p, grid, s); break;
     default: rc = launch_fused<XR_LOSS_ALIGNMENT_CONTRASTIVE>(tq, tn, p, grid, s); break;
   }
@@ -1582,8 +1595,8 @@ extern "C" size_t xr_fused_pool_loss_mon_workspace_bytes(int64_t m, int64_t cn, 
 }
 
 extern "C" int xr_fused_pool_loss_mon(const void* q, const void* pos, const void* neg, int64_t m, int64_t cn,
-                                      int64_t dim, const xr_loss_config* cfg, float grad_scale, float* dq,
-                                      double* loss_out, double* losses_dot, double* losses_cos,
+                                      int64_t dim, int loss_kind, const xr_loss_config* cfg, float grad_scale,
+                                      float* dq, double* loss_out, double* losses_dot, double* losses_cos,
                                       double* stats_out, void* workspace, size_t workspace_bytes, void* stream) {
   XR_CHECK_ARG(q && pos && neg && cfg && loss_out && losses_dot && losses_cos && stats_out && workspace,
                "xr_fused_pool_loss_mon: null pointer");
@@ -1592,6 +1605,9 @@ extern "C" int xr_fused_pool_loss_mon(const void* q, const void* pos, const void
   XR_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)pos % 16 == 0) && ((uintptr_t)neg % 16 == 0) &&
                    (uintptr_t)workspace % 256 == 0,
                "xr_fused_pool_loss_mon: operands must be 16-byte aligned, the workspace 256-byte aligned");
+  XR_CHECK_ARG(loss_kind == XR_LOSS_INFONCE || loss_kind == XR_LOSS_NCE || loss_kind == XR_LOSS_PAIRWISE_HINGE ||
+                   loss_kind == XR_LOSS_PAIRWISE_LOGISTIC,
+               "xr_fused_pool_loss_mon: the train loss must be of the dot family");
   XR_CHECK_ARG(cfg->num_hard_negatives == 0 && cfg->scale > 0.f,
                "xr_fused_pool_loss_mon: needs scale > 0 and no hard-negative mining");
   XR_CHECK_ARG(workspace_bytes >= xr_fused_pool_loss_mon_workspace_bytes(m, cn, dim),
@@ -1603,7 +1619,7 @@ extern "C" int xr_fused_pool_loss_mon(const void* q, const void* pos, const void
   const MonWs mw = carve_mon_ws((uint8_t*)workspace + ws.bytes, m, cn, pl.slots);
   const MonArgs mon{mw.part_dot, mw.part_cos, mw.inv_q, mw.inv_n, mw.t_cos, mw.row_out, mw.row_out2, mw.scratch,
                     losses_dot, losses_cos, stats_out, m};
-  return fused_launch_all(q, pos, neg, m, cn, XR_LOSS_INFONCE, cfg, nullptr, grad_scale, dq, loss_out, nullptr, ws,
+  return fused_launch_all(q, pos, neg, m, cn, loss_kind, cfg, nullptr, grad_scale, dq, loss_out, nullptr, ws,
                           false, as_stream(stream), nullptr, &mon);
 }
 
@@ -2009,8 +2025,11 @@ extern "C" int xr_pool_step_compute_mon(int64_t n_pos, int64_t dim, int loss_kin
   XR_CHECK_ARG(cfg && loss_out && losses_dot && losses_cos && stats_out && workspace,
                "xr_pool_step_compute_mon: null pointer");
   XR_CHECK_ARG(dim == fk::D && n_pos > 0 && n_pos < (1ll << 30), "xr_pool_step_compute_mon: bad sizes");
-  XR_CHECK_ARG(loss_kind == XR_LOSS_INFONCE && cfg->num_hard_negatives == 0 && cfg->scale > 0.f,
-               "xr_pool_step_compute_mon: serves the InfoNCE train loss with scale > 0 and no hard-negative mining");
+  XR_CHECK_ARG((loss_kind == XR_LOSS_INFONCE || loss_kind == XR_LOSS_NCE || loss_kind == XR_LOSS_PAIRWISE_HINGE ||
+                loss_kind == XR_LOSS_PAIRWISE_LOGISTIC) &&
+                   cfg->num_hard_negatives == 0 && cfg->scale > 0.f,
+               "xr_pool_step_compute_mon: serves the dot-family train losses (InfoNCE, NCE, pairwise hinge / "
+               "logistic) with scale > 0 and no hard-negative mining");
   XR_CHECK_ARG(!dtok || dtok_dtype == XR_F32 || dtok_dtype == XR_BF16, "xr_pool_step_compute_mon: dtok must be fp32 or bf16");
   XR_CHECK_ARG(workspace_bytes >= xr_pool_step_monitor_workspace_bytes(n_pos, dim) && (uintptr_t)workspace % 256 == 0,
                "xr_pool_step_compute_mon: workspace too small or misaligned");

@@ -84,7 +84,7 @@ PROTOTYPES = {
     "xr_pool_step_monitor_workspace_bytes": (_sz, [_i64, _i64]),
     "xr_pool_step_monitor": (_int, [_i64, _i64, _cfgp, _p, _p, _p, _p, _sz, _p]),
     "xr_fused_pool_loss_mon_workspace_bytes": (_sz, [_i64, _i64, _i64]),
-    "xr_fused_pool_loss_mon": (_int, [_p, _p, _p, _i64, _i64, _i64, _cfgp, C.c_float, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "xr_fused_pool_loss_mon": (_int, [_p, _p, _p, _i64, _i64, _i64, _int, _cfgp, C.c_float, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "xr_pool_step_compute_mon": (_int, [_i64, _i64, _int, _cfgp, C.c_float, _p, _int, _p, _p, _p, _p, _p, _sz, _p]),
     "xr_fused_pool_loss": (_int, [_p, _p, _p, _i64, _i64, _i64, _int, _cfgp, _p, _f, _p, _p, _p, _p, _sz, _p]),
     "xr_fused_pool_all_workspace_bytes": (_sz, [_i64, _i64, _i64]),

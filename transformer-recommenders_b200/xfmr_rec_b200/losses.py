@@ -493,11 +493,14 @@ LossType = Literal[
 ]
 
 
+_MON_TRAIN_KINDS = ("InfoNCELoss", "NCELoss", "PairwiseHingeLoss", "PairwiseLogisticLoss")
+
+
 def _one_pass(config, query_embed, candidate_embed, target, train_loss):
-    """Train loss (InfoNCE) with its autograd edge AND both families' losses + statistics from ONE tensor-core
+    """Train loss (a dot-family kind) with its autograd edge AND both families' losses + statistics from ONE tensor-core
     pass (xr_fused_pool_loss_mon) when the batch qualifies: pool candidates on the bf16 tensor-core path for
     both logit families, gradient wanted, no hard-negative mining, scale > 0.  None otherwise."""
-    if not (train_loss == "InfoNCELoss" and target is None and isinstance(candidate_embed, PoolCandidates)
+    if not (train_loss in _MON_TRAIN_KINDS and target is None and isinstance(candidate_embed, PoolCandidates)
             and torch.is_grad_enabled() and query_embed.requires_grad and query_embed.is_cuda):
         return None
     if config.num_hard_negatives or config.scale <= 0 or config.target_position != "first":
@@ -511,7 +514,7 @@ def _one_pass(config, query_embed, candidate_embed, target, train_loss):
         return None
     dot.check_embeds(query_embed, candidate_embed)
     cfg = ops.make_cfg(config, logits_bf16=logits_bf16)
-    loss, dq, l_dot, l_cos, stats = ops.fused_pool_loss_mon(q, pos, neg, cfg)
+    loss, dq, l_dot, l_cos, stats = ops.fused_pool_loss_mon(q, pos, neg, N.LOSS_KIND[train_loss], cfg)
     loss32 = loss.view(torch.float32)[2]
     src = getattr(query_embed, "_xr_src", None)
     if src is not None and src[0].requires_grad and dq.size(1) % 8 == 0:

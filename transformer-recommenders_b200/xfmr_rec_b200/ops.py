@@ -345,8 +345,8 @@ def fused_pool_all(q, pos, neg, cfg, cosine):
     return losses, stats
 
 
-def fused_pool_loss_mon(q, pos, neg, cfg, want_grad=True, grad_scale=1.0):
-    """InfoNCE loss + dL/dq AND every loss of both logit families + the LogitsStatistics block from ONE
+def fused_pool_loss_mon(q, pos, neg, loss_kind, cfg, want_grad=True, grad_scale=1.0):
+    """Train loss (a dot-family kind) + dL/dq AND every loss of both logit families + the LogitsStatistics block from ONE
     tcgen05 pass (xr_fused_pool_loss_mon): what compute_losses (trainer.py:213-264) needs for a batch.
     Returns (loss f64[2] (fp32 copy in the low half of [1]), dq | None, losses_dot f64[7], losses_cos f64[7],
     stats f64[16])."""
@@ -362,7 +362,7 @@ def fused_pool_loss_mon(q, pos, neg, cfg, want_grad=True, grad_scale=1.0):
     stats = torch.empty(N.XR_STATS_SLOTS, dtype=torch.float64, device=dev)
     ws = _ws(N.lib().xr_fused_pool_loss_mon_workspace_bytes(m, cn, d), dev)
     with _on(dev):
-        N.call("xr_fused_pool_loss_mon", _p(q), _p(pos), _p(neg), m, cn, d, C.byref(cfg), float(grad_scale),
+        N.call("xr_fused_pool_loss_mon", _p(q), _p(pos), _p(neg), m, cn, d, int(loss_kind), C.byref(cfg), float(grad_scale),
                _p(dq), _p(loss), _p(l_dot), _p(l_cos), _p(stats), _p(ws), ws.numel(), _stream())
     return loss, dq, l_dot, l_cos, stats
 

@@ -90,8 +90,9 @@ class PoolLossStep:
             # monitor: LogitsStatistics + all seven losses (trainer.py:250-263) in the same sequence
             self.monitor = bool(monitor)
             # one tensor-core pass for the train loss, its gradient AND the monitoring sums of both logit
-            # families (xr_pool_step_compute_mon) instead of three; the InfoNCE train loss only
-            self.monitor_one_pass = bool(monitor and monitor_one_pass and name == "InfoNCELoss" and cfg.scale > 0)
+            # families (xr_pool_step_compute_mon) instead of three; the dot-family train losses
+            self.monitor_one_pass = bool(monitor and monitor_one_pass and cfg.scale > 0 and name in (
+                "InfoNCELoss", "NCELoss", "PairwiseHingeLoss", "PairwiseLogisticLoss"))
             self.mon_dot = torch.zeros(N.XR_NUM_LOSSES, dtype=torch.float64, device=dev)
             self.mon_cos = torch.zeros(N.XR_NUM_LOSSES, dtype=torch.float64, device=dev)
             self.mon_stats = torch.zeros(N.XR_STATS_SLOTS, dtype=torch.float64, device=dev)
