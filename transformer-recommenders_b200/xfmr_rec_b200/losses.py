@@ -262,8 +262,9 @@ class EmbedLoss(torch.nn.Module, abc.ABC):
         return (torch.bfloat16 if bf16 else torch.float32), (bf16 and not self.COSINE)
 
     # -- execution ----------------------------------------------------------------------------
-    def _evaluate(self, query_embed, candidate_embed, target, *, want_stats=False):
-        """Returns (losses f64[7], stats f64[16] | None, dq fp32 | None)."""
+    def _evaluate(self, query_embed, candidate_embed, target, *, want_stats=False, want_dcand=False):
+        """Returns (losses f64[7], stats f64[16] | None, dq fp32 | None).  ``want_dcand`` (forward() only): a
+        dense candidate tensor that requires grad also gets its gradient, left in ``self._dcand`` for forward()."""
         self.check_embeds(query_embed, candidate_embed)
         if not query_embed.is_cuda:
             raise N.NativeError("xfmr_rec_b200 losses need CUDA tensors; there is no CPU fallback")
@@ -271,7 +272,8 @@ class EmbedLoss(torch.nn.Module, abc.ABC):
         mode, tgt = self.check_target(m, c, target)
         need_grad = torch.is_grad_enabled() and query_embed.requires_grad
         self._dcand = None
-        cand_grad = torch.is_grad_enabled() and bool(getattr(candidate_embed, "requires_grad", False))
+        cand_grad = (want_dcand and torch.is_grad_enabled()
+                     and bool(getattr(candidate_embed, "requires_grad", False)))
         if cand_grad and not isinstance(candidate_embed, torch.Tensor):
             raise NotImplementedError(
                 "gradients w.r.t. a candidate HANDLE are not produced: the item table is frozen in the "
@@ -376,7 +378,7 @@ class EmbedLoss(torch.nn.Module, abc.ABC):
 
     def forward(self, query_embed, candidate_embed, target=None):
         """Summed loss over the batch (xfmr_rec/losses.py:128-155)."""
-        losses, _, dq = self._evaluate(query_embed, candidate_embed, target)
+        losses, _, dq = self._evaluate(query_embed, candidate_embed, target, want_dcand=True)
         loss = losses[N.LOSS_KIND[type(self).__name__]]
         if loss.dtype != torch.float32:
             loss = loss.to(torch.float32)
