@@ -6,6 +6,8 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import xfmr_oracle as orc
+
 HF_KEYS_LAYER = [
     "attention.self.query.weight", "attention.self.query.bias", "attention.self.key.weight",
     "attention.self.key.bias", "attention.self.value.weight", "attention.self.value.bias",
@@ -404,3 +406,29 @@ def test_training_loop_reduces_the_loss():
     assert all(np.isfinite(losses)), losses
     assert np.mean(losses[-5:]) < 0.6 * np.mean(losses[:3]), (losses[:3], losses[-5:])
     assert all(bool(torch.isfinite(p).all()) for p in enc.parameters())
+
+
+@pytest.mark.gpu
+def test_evaluate_users_is_encode_then_search_then_metrics(golden_dir):
+    """SURVEY 8f ranks 1 + 3 together: evaluate_users = model.encode (sequence encoder, pooled, eval mode) ->
+    exact search with the user's whole history excluded -> the seven metrics; equal to the same steps done by
+    hand, and the recommended rows equal the oracle's exact search on the encoder's embeddings."""
+    import xfmr_rec_b200 as xr
+
+    z, enc = _load(golden_dir, "2layer_i128")
+    enc.train()                                              # evaluate_users must switch dropout off itself
+    idx_t, table = torch.from_numpy(z["idx"]).cuda(), torch.from_numpy(z["table"]).cuda()
+    n_items = table.size(0) - 1
+    index = xr.index.ExactIndex(xr.index.ExactIndexConfig(index_metric="cosine", dtype="fp32")).set_catalog(table[1:])
+    rng = np.random.default_rng(2)
+    targets = [list(map(int, rng.integers(0, n_items, size=int(rng.integers(0, 5))))) for _ in range(idx_t.size(0))]
+    means, per_user, valid, rec = xr.evaluate.evaluate_users(enc, table, index, idx_t, targets, 10)
+    assert enc.training
+    q = enc.eval()(idx_t, table)["sentence_embedding"].detach()
+    hist = [[int(x) - 1 for x in row if x != 0] for row in z["idx"]]
+    means2, per_user2, valid2, rec2 = xr.evaluate.evaluate_batch(index, q, hist, targets, 10)
+    assert torch.equal(rec, rec2) and torch.equal(per_user, per_user2) and torch.equal(valid, valid2)
+    _, want = orc.exact_search(q.cpu().numpy(), z["table"][1:], 10, hist, metric="cosine")
+    assert np.array_equal(rec.cpu().numpy(), want)
+    for r in range(idx_t.size(0)):
+        assert not set(rec[r].tolist()) & set(hist[r])

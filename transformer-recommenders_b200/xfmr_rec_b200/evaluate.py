@@ -40,3 +40,29 @@ def evaluate_batch(index, query_embeds: torch.Tensor, history_rows, target_rows,
     means_t = (per_user * w[:, None]).sum(0) / torch.clamp(n, min=1.0)
     means = {f"{stage}/{name}": means_t[i] for i, name in enumerate(METRIC_NAMES)}
     return means, per_user, valid, rec_rows
+
+
+@torch.no_grad()
+def evaluate_users(encoder, table: torch.Tensor, index, history_item_idx: torch.Tensor, target_rows, top_k: int,
+                   *, item_row_offset: int = -1, stage: str = "val"):
+    """The whole per-user validation of the reference for U users at once, on the device: ``model.encode``
+    (models.py:347-364: the user's history through the sequence encoder, pooled) -> ``items_index.search``
+    with the history excluded (trainer.py:311-315) -> the seven metrics (trainer.py:266-285).
+
+    ``history_item_idx`` (U, L) int64: rows of the item table, 0 = padding (right-padded); ``table`` the
+    frozen item table with its zero row 0.  ``item_row_offset`` maps a table row to its catalog row of
+    ``index`` (-1 when the catalog holds the table's rows 1.. in order).  The encoder runs in eval mode (no
+    dropout) and is put back into its previous mode.  Returns what :func:`evaluate_batch` returns."""
+    was_training = encoder.training
+    encoder.eval()
+    try:
+        queries = encoder(history_item_idx, table)["sentence_embedding"]
+    finally:
+        encoder.train(was_training)
+    hist = history_item_idx      # the WHOLE history is excluded (trainer.py:311-315), also what the encoder truncated
+    mask = hist != 0
+    counts = mask.sum(1)
+    offs = torch.zeros(hist.size(0) + 1, dtype=torch.int64, device=hist.device)
+    offs[1:] = torch.cumsum(counts, 0)
+    rows = hist[mask] + item_row_offset                         # GLOBAL catalog rows (search_batch contract)
+    return evaluate_batch(index, queries, (offs, rows.contiguous()), target_rows, top_k, stage)
