@@ -714,3 +714,42 @@ def test_item_index_service_wire_format(xr):
         svc.get_id("nope")
     wire = S.Query.model_validate_json(qs[1].model_dump_json())       # JSON round trip of a request
     assert [c.item_id for c in svc.search(wire)] == [c.item_id for c in many[1]]
+
+
+def test_recommend_service_request_path(xr):
+    """service.py:96-134 + 202-262 without BentoML: item ids -> stored embeddings -> Model.embed (the B200-native
+    sequence encoder, eval mode) -> search with the query's own items excluded.  The batched entry point equals the
+    per-query calls; the embedding equals the encoder's pooled output for the same item rows; unknown ids are
+    dropped, an empty query returns no candidates."""
+    from xfmr_rec_b200 import service as S
+    from xfmr_rec_b200.encoder import EncoderConfig, SeqEncoder
+
+    rng = np.random.default_rng(4)
+    n = 2000
+    emb = (rng.standard_normal((n, 384)) / 384 ** 0.5).astype(np.float32)
+    data = {"item_id": [f"i{j}" for j in range(n)], "item_text": [f"text {j}" for j in range(n)],
+            "embedding": torch.from_numpy(emb)}
+    idx = xr.index.ExactIndex(xr.index.ExactIndexConfig(store_embeddings=True)).index_data(data)
+    torch.manual_seed(0)
+    enc = SeqEncoder(EncoderConfig(num_hidden_layers=2, intermediate_size=96, max_seq_length=8)).cuda()
+    svc = S.RecommendService(S.ModelService(enc), S.ItemIndexService(idx))
+    assert not enc.training
+    hists = [[f"i{j}" for j in rng.integers(0, n, size=k)] for k in (3, 12, 1)]
+    hists[1][2] = "unknown-item"
+    qs = [S.Query(item_ids=list(h), top_k=7, exclude_item_ids=["i5"]) for h in hists] + [S.Query(top_k=3)]
+    many = svc.recommend_with_queries([q.model_copy(deep=True) for q in qs])
+    for q, got, h in zip(qs, many, hists + [[]]):
+        one = svc.recommend_with_query(q.model_copy(deep=True))
+        assert [c.item_id for c in one] == [c.item_id for c in got]
+        if not h:
+            assert got == []
+            continue
+        assert len(got) == 7 and not {c.item_id for c in got} & ({"i5"} | set(h))
+    # the embedding of query 1: the encoder on the last 8 KNOWN items of its history (table = the item embeddings)
+    known = [int(x[1:]) for x in hists[1] if x != "unknown-item"][-8:]
+    table = torch.cat([torch.zeros(1, 384), torch.from_numpy(emb)]).cuda()
+    want = enc(torch.tensor([[r + 1 for r in known]], device="cuda"), table)["sentence_embedding"][0]
+    q1 = svc.embed_query(svc.process_query(qs[1].model_copy(deep=True)))
+    np.testing.assert_allclose(q1.embedding, want.detach().cpu().numpy(), rtol=1e-5, atol=1e-6)
+    first = svc.recommend_with_item_id("i3", top_k=4)
+    assert len(first) == 4 and "i3" not in {c.item_id for c in first}

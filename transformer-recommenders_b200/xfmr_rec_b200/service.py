@@ -9,6 +9,9 @@ the same field names, defaults and JSON shape (embeddings as float lists), so a 
 reference's ``/search``, ``/get_id`` and ``/get_ids`` routes can talk to an ``ItemIndexService``
 unchanged.  ``search_many`` is the batched entry point the reference lacks: U queries become ONE
 ``search_batch`` call (one tensor-core pass over the catalog) instead of U ANN round trips.
+:class:`ModelService` (``Model.embed``, service.py:96-134, on the B200-native sequence encoder) and
+:class:`RecommendService` (``Service.recommend_with_query`` / ``recommend_with_item_id``, service.py:202-262)
+complete the request path: item ids -> stored embeddings -> sequence embedding -> exact search.
 """
 
 from __future__ import annotations
@@ -145,3 +148,90 @@ class ItemIndexService:
         results = self.index.get_ids(item_ids).to_list()
         items = pydantic.TypeAdapter(list[ItemQuery]).validate_python(results)
         return {item.item_id: item for item in items}
+
+
+class ModelService:
+    """``Model`` of service.py:96-134 over a :class:`~xfmr_rec_b200.encoder.SeqEncoder`: ``embed`` turns the
+    ``input_embeds`` of a BATCH of queries (their items' embeddings, last ``max_seq_length`` of them) into the
+    pooled sentence embedding, in one encoder forward (eval mode: no dropout)."""
+
+    def __init__(self, encoder) -> None:
+        self.encoder = encoder.eval()
+        self.embed_dim: int = encoder.config.hidden_size
+
+    def max_seq_length(self) -> int:
+        """service.py:108-110."""
+        return self.encoder.max_seq_length
+
+    @torch.inference_mode()
+    def embed(self, queries: list[Query]) -> list[Query]:
+        """service.py:112-134: pad the per-query item embeddings to one (B, L, D) batch (a query without
+        ``input_embeds`` contributes one zero row, i.e. an empty sequence), mask = any(row != 0), encode, pool."""
+        if not queries:
+            return queries
+        dev = next(self.encoder.parameters()).device
+        lmax = self.max_seq_length()
+        seqs = [torch.as_tensor(np.asarray(q.input_embeds, dtype=np.float32)[-lmax:]) if q.input_embeds is not None
+                else torch.zeros(1, self.embed_dim) for q in queries]
+        batch = torch.nn.utils.rnn.pad_sequence(seqs, batch_first=True).to(dev)          # (B, L, D), zero padded
+        b, l, d = batch.shape
+        # the encoder gathers rows of a table: here the "table" is the padded batch itself
+        rows = torch.arange(b * l, device=dev, dtype=torch.int64).view(b, l)
+        emb = self.encoder(rows, batch.reshape(b * l, d).contiguous())["sentence_embedding"].float().cpu().numpy()
+        for q, e in zip(queries, emb):
+            q.embedding = e
+        return queries
+
+
+class RecommendService:
+    """The composition of service.py:202-262 (``Service``) without the BentoML plumbing: look the query's items
+    up, embed the sequence, exclude what the user already has, search."""
+
+    def __init__(self, model: ModelService, item_index: ItemIndexService) -> None:
+        self.model, self.item_index = model, item_index
+
+    def process_query(self, query: Query) -> Query:
+        """service.py:222-235: item ids -> their stored embeddings (unknown ids are dropped, the last
+        ``max_seq_length`` kept)."""
+        if query.item_ids is None or query.input_embeds is not None:
+            return query
+        items = self.item_index.get_ids(query.item_ids)
+        item_ids = [i for i in query.item_ids if i in items]
+        query.item_ids = item_ids[-self.model.max_seq_length():]
+        embs = [items[i].embedding for i in query.item_ids]
+        query.input_embeds = np.stack(embs) if embs else None
+        return query
+
+    def embed_query(self, query: Query) -> Query:
+        """service.py:237-245."""
+        if query.input_embeds is None or query.embedding is not None:
+            return query
+        return self.model.embed([query])[0]
+
+    def recommend_with_query(self, query: Query) -> list[ItemCandidate]:
+        """service.py:208-220."""
+        query = self.embed_query(self.process_query(query))
+        query.exclude_item_ids = [*(query.exclude_item_ids or []), *(query.item_ids or [])]
+        if query.embedding is None:
+            return []
+        return self.item_index.search(query)
+
+    def recommend_with_queries(self, queries: list[Query]) -> list[list[ItemCandidate]]:
+        """The batched form the reference lacks: ONE encoder forward and ONE catalog pass for all queries."""
+        queries = [self.process_query(q) for q in queries]
+        todo = [q for q in queries if q.input_embeds is not None and q.embedding is None]
+        self.model.embed(todo)
+        for q in queries:
+            q.exclude_item_ids = [*(q.exclude_item_ids or []), *(q.item_ids or [])]
+        have = [q for q in queries if q.embedding is not None]
+        found = iter(self.item_index.search_many(have))
+        return [next(found) if q.embedding is not None else [] for q in queries]
+
+    def recommend_with_item_id(self, item_id: str, exclude_item_ids: list[str] | None = None,
+                               top_k: int = TOP_K) -> list[ItemCandidate]:
+        """service.py:247-262."""
+        item = self.item_index.get_id(item_id)
+        query = Query(item_ids=[item.item_id], item_texts=[item.item_text],
+                      input_embeds=item.embedding[None, :] if item.embedding is not None else None,
+                      exclude_item_ids=exclude_item_ids, top_k=top_k)
+        return self.recommend_with_query(query)
