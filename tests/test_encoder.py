@@ -432,3 +432,30 @@ def test_evaluate_users_is_encode_then_search_then_metrics(golden_dir):
     assert np.array_equal(rec.cpu().numpy(), want)
     for r in range(idx_t.size(0)):
         assert not set(rec[r].tolist()) & set(hist[r])
+
+
+@pytest.mark.gpu
+def test_whole_train_step_with_optimizer_as_one_cuda_graph():
+    """GraphedEncoderStep(optimizer=AdamW(capturable=True)): encoder forward, scoring-and-loss step, encoder
+    backward AND the optimizer update are ONE CUDA graph; replaying it on a batch trains the encoder (the loss
+    falls), with fresh dropout masks per replay."""
+    import xfmr_rec_b200 as xr
+    from xfmr_rec_b200.data import synthetic_batch
+    from xfmr_rec_b200.encoder import EncoderConfig, GraphedEncoderStep, SeqEncoder
+
+    B, L = 16, 32
+    b = synthetic_batch(400, B, L, dim=384, seed=9)
+    table = torch.from_numpy(b["table"]).cuda()
+    hist, pos, neg = (torch.from_numpy(b[k]).cuda() for k in ("history_item_idx", "pos_item_idx", "neg_item_idx"))
+    torch.manual_seed(1)
+    enc = SeqEncoder(EncoderConfig(num_hidden_layers=2, intermediate_size=256, max_seq_length=L),
+                     compute_dtype=torch.bfloat16, seed=5).cuda().train()
+    trained = [p for n, p in enc.named_parameters() if not n.startswith(("pooler", "embeddings.word"))]
+    opt = torch.optim.AdamW(trained, lr=2e-3, weight_decay=0.0, capturable=True)
+    emb = xr.models.ItemEmbeddings(table, add_padding_row=False).cuda()
+    step = xr.PoolLossStep(emb, xr.InfoNCELoss(xr.LossConfig()), B, L, token_dtype=torch.float32, logits_bf16=True,
+                           use_graph=False)
+    graphed = GraphedEncoderStep(enc, step, table, L, optimizer=opt)
+    losses = [float(graphed(hist, pos, neg)) for _ in range(40)]
+    assert all(np.isfinite(losses)), losses
+    assert np.mean(losses[-5:]) < 0.6 * np.mean(losses[:3]), (losses[:3], losses[-5:])
