@@ -729,18 +729,29 @@ def bench_encoder_step(xr, dev, flush):
                            logits_bf16=True, use_graph=False)
     graphed = GraphedEncoderStep(enc, step, table, SEQ_LEN)
     ms = _timeit(torch, lambda: graphed(hist, pos, neg), flush, reps=20)
+    # the same with the optimizer update inside the graph (what a Lightning training_step + optimizer_step does)
+    del graphed
+    enc.zero_grad(set_to_none=True)
+    trained = [p for n, p in enc.named_parameters() if not n.startswith(("pooler", "embeddings.word"))]
+    opt = torch.optim.AdamW(trained, lr=1e-3, weight_decay=0.01, capturable=True, fused=True)   # config.yaml: lr, wd
+    step2 = xr.PoolLossStep(emb, xr.InfoNCELoss(xr.LossConfig()), BATCH, SEQ_LEN, token_dtype=torch.float32,
+                            logits_bf16=True, use_graph=False)
+    graphed = GraphedEncoderStep(enc, step2, table, SEQ_LEN, optimizer=opt)
+    ms_opt = _timeit(torch, lambda: graphed(hist, pos, neg), flush, reps=20)
     with torch.no_grad():
         fwd_ms = _timeit(torch, lambda: enc.encode_tokens(hist, table), flush, reps=10)
     loss = float(graphed(hist, pos, neg))
     n_par = sum(p.numel() for n, p in enc.named_parameters() if p.grad is not None)
-    return {"value": BATCH / (ms / 1e3), "unit": "seq/s", "ms_per_step": ms, "encoder_forward_eager_ms": fwd_ms,
+    return {"value": BATCH / (ms / 1e3), "unit": "seq/s", "ms_per_step": ms, "ms_per_step_with_adamw": ms_opt,
+            "encoder_forward_eager_ms": fwd_ms,
             "loss": loss, "trained_parameters": n_par,
             "encoder": {"layers": 2, "hidden": DIM, "heads": 12, "intermediate": 1536, "compute": "bf16-mixed "
                         "(bf16 GEMMs / attention / GELU, fp32 residual stream, LayerNorm and softmax)",
                         "dropout": "0.1 hidden / 0.1 attention (training mode, HF defaults): counter-based masks "
                                    "recomputed in the backward"},
             "note": "GraphedEncoderStep: encoder forward + PoolLossStep + encoder backward (parameter gradients "
-                    "in .grad, no optimizer) replayed as one CUDA graph; L2 flushed between steps; the linear "
+                    "in .grad) replayed as one CUDA graph, and the same graph with the AdamW update inside "
+                    "(ms_per_step_with_adamw); L2 flushed between steps; the linear "
                     "layers are cuBLAS GEMMs, everything else this repository's kernels (csrc/encoder.cu). "
                     "Reference encoder class (transformers BertModel, eager, autocast bf16) on the same GPU: "
                     "profiles/encoder_r02.json"}

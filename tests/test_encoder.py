@@ -455,7 +455,12 @@ def test_whole_train_step_with_optimizer_as_one_cuda_graph():
     emb = xr.models.ItemEmbeddings(table, add_padding_row=False).cuda()
     step = xr.PoolLossStep(emb, xr.InfoNCELoss(xr.LossConfig()), B, L, token_dtype=torch.float32, logits_bf16=True,
                            use_graph=False)
+    before = [p.detach().clone() for p in trained]
     graphed = GraphedEncoderStep(enc, step, table, L, optimizer=opt)
+    assert all(torch.equal(a, b) for a, b in zip(before, trained))      # building the graph trains nothing
     losses = [float(graphed(hist, pos, neg)) for _ in range(40)]
     assert all(np.isfinite(losses)), losses
     assert np.mean(losses[-5:]) < 0.6 * np.mean(losses[:3]), (losses[:3], losses[-5:])
+    # the moments persist across replays (a state created inside the capture would be reset by every replay)
+    st = opt.state[trained[0]]
+    assert float(st["step"]) == 40 and float(st["exp_avg_sq"].abs().sum()) > 0

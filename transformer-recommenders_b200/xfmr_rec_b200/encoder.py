@@ -438,12 +438,32 @@ class GraphedEncoderStep:
                     self._body()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize(dev)
+            if optimizer is not None:
+                self._init_optimizer_state(optimizer)
             encoder.zero_grad(set_to_none=True)
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.loss = self._body()
                 if optimizer is not None:
                     optimizer.step()
+
+    @staticmethod
+    def _init_optimizer_state(optimizer) -> None:
+        """Create the optimizer's state tensors BEFORE the capture (a first ``step()`` inside it would record
+        their allocation and zero-fill into the graph: every replay would then reset the moments).  One step
+        with lr = weight_decay = 0 on the warm-up gradients leaves the parameters untouched; the state it
+        created is then zeroed in place, step counters included."""
+        saved = [(g["lr"], g["weight_decay"]) for g in optimizer.param_groups]
+        for g in optimizer.param_groups:
+            g["lr"] = g["lr"] * 0 if torch.is_tensor(g["lr"]) else 0.0
+            g["weight_decay"] = 0.0
+        optimizer.step()
+        for g, (lr, wd) in zip(optimizer.param_groups, saved):
+            g["lr"], g["weight_decay"] = lr, wd
+        for st in optimizer.state.values():
+            for v in st.values():
+                if torch.is_tensor(v):
+                    v.zero_()
 
     def _body(self):
         enc = self.encoder
