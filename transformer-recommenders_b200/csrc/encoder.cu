@@ -212,7 +212,8 @@ __device__ __forceinline__ void ln_row_bwd(const float (&x)[enc::PER], const flo
   for (int k = 0; k < enc::PER; ++k) dx[k] = rstd * (dxh[k] - s1 - xh[k] * s2);
 }
 
-constexpr int LNB_BLOCKS = 296;   // partial rows of the parameter-gradient reductions (two per SM)
+constexpr int LNB_BLOCKS = 888;   // partial rows of the parameter-gradient reductions (six blocks per SM: the
+                                  // backward kernels recompute dropout masks, two blocks per SM left them latency-bound)
 
 // fold the warps' column sums (registers; vector v of NV) into the block's partial rows part[block][v][H]:
 // fixed order inside the block
@@ -235,30 +236,32 @@ __device__ __forceinline__ void ln_param_partials(const float (&acc)[NV][enc::PE
   }
 }
 
-// out_v[c] = sum over the n_part partial rows part[p][v][c]; a block owns 32 columns of one vector, its 8 warps
-// take every 8th partial row, then one fixed-order sum over the warps: deterministic, ~40 loads per thread
-__global__ void __launch_bounds__(256)
+// out_v[c] = sum over the n_part partial rows part[p][v][c]; a block owns 32 columns of one vector, its 32 warps
+// take every 32nd partial row, then one fixed-order sum over the warps: deterministic, ~30 loads per thread
+constexpr int FOLD_WARPS = 32;
+__global__ void __launch_bounds__(FOLD_WARPS * 32)
 enc_fold_partials_kernel(const float* __restrict__ part, int n_part, int n_vec, int width, float* __restrict__ out0,
                          float* __restrict__ out1, float* __restrict__ out2) {
-  __shared__ float s[8][32];
+  __shared__ float s[FOLD_WARPS][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int v = blockIdx.y, c = blockIdx.x * 32 + lane;
   float a = 0.f;
   if (c < width)
-    for (int p = warp; p < n_part; p += 8) a += part[((size_t)p * n_vec + v) * width + c];
+    for (int p = warp; p < n_part; p += FOLD_WARPS) a += part[((size_t)p * n_vec + v) * width + c];
   s[warp][lane] = a;
   __syncthreads();
   if (warp == 0 && c < width) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += s[w][lane];
+    for (int w = 0; w < FOLD_WARPS; ++w) t += s[w][lane];
     float* out = v == 0 ? out0 : (v == 1 ? out1 : out2);
     if (out) out[c] = t;
   }
 }
 static inline void launch_fold(const float* part, int n_part, int n_vec, int width, float* o0, float* o1, float* o2,
                                cudaStream_t s) {
-  enc_fold_partials_kernel<<<dim3((width + 31) / 32, n_vec), 256, 0, s>>>(part, n_part, n_vec, width, o0, o1, o2);
+  enc_fold_partials_kernel<<<dim3((width + 31) / 32, n_vec), FOLD_WARPS * 32, 0, s>>>(part, n_part, n_vec, width, o0, o1,
+                                                                                     o2);
 }
 
 // backward of embed_ln: dgamma, dbeta (partials), d position_emb[l] (sum over the batch), d token_type_emb[0]
@@ -351,7 +354,7 @@ enc_add_ln_fwd_kernel(const T* __restrict__ y, const float* __restrict__ bias, c
 // dx = dLN (the gradient of BOTH y and the residual); partials of dgamma, dbeta and of the dense layer's bias
 // gradient (the column sums of dx).  The upstream gradient is dout (fp32) + dout_lp (bf16), either may be null.
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)   // <= 128 registers: with the dropout recompute ptxas took 141 -> one block per SM
 enc_add_ln_bwd_kernel(const T* __restrict__ y, const float* __restrict__ bias, const float* __restrict__ res,
                       const float* __restrict__ gamma, const float* __restrict__ stats,
                       const float* __restrict__ dout, const __nv_bfloat16* __restrict__ dout_lp, int64_t n_tok,
