@@ -464,3 +464,26 @@ def test_whole_train_step_with_optimizer_as_one_cuda_graph():
     # the moments persist across replays (a state created inside the capture would be reset by every replay)
     st = opt.state[trained[0]]
     assert float(st["step"]) == 40 and float(st["exp_avg_sq"].abs().sum()) > 0
+
+
+@pytest.mark.gpu
+def test_gelu_kernels_match_torch_exact_gelu():
+    """hidden_act = "gelu" (erf form).  fp32: erff, 1e-6; bf16 activations: the 1.5e-7-accurate polynomial erf,
+    outputs and gradients equal torch's exact GELU evaluated in fp32 and rounded to bf16, up to one bf16 ulp
+    on a handful of rounding ties."""
+    from xfmr_rec_b200.encoder import _Gelu
+
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x32 = torch.cat([torch.randn(100_003, generator=g, device="cuda") * 2.5,
+                     torch.tensor([0.0, -0.0, 1e-8, -1e-8, 8.0, -8.0, 30.0, -30.0], device="cuda")])
+    up32 = torch.randn_like(x32)
+    for dt, tol in ((torch.float32, 2e-6), (torch.bfloat16, 8e-3)):
+        x = x32.detach().to(dt).clone().requires_grad_(True)
+        y = _Gelu.apply(x)
+        y.backward(up32.to(dt))
+        xr_ = x.detach().float().requires_grad_(True)
+        want = torch.nn.functional.gelu(xr_)
+        want.backward(up32.to(dt).float())
+        assert torch.allclose(y.float(), want.detach().to(dt).float(), rtol=tol, atol=tol * 1e-2 + 1e-7)
+        assert torch.allclose(x.grad.float(), xr_.grad.to(dt).float(), rtol=tol, atol=tol)
+        assert bool(torch.isfinite(y.float()).all()) and bool(torch.isfinite(x.grad.float()).all())
