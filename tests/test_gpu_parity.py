@@ -753,3 +753,10 @@ def test_recommend_service_request_path(xr):
     np.testing.assert_allclose(q1.embedding, want.detach().cpu().numpy(), rtol=1e-5, atol=1e-6)
     first = svc.recommend_with_item_id("i3", top_k=4)
     assert len(first) == 4 and "i3" not in {c.item_id for c in first}
+    users = S.UserIndexService([{"user_id": "u1", "user_text": "{}", "history": {"item_id": ["i1", "i2"], "item_text": ["a", "b"]},
+                                 "target": {"item_id": ["i9"], "item_text": ["c"]}}])
+    recs = svc.recommend_with_user_id(users, "u1", top_k=6)
+    want = svc.recommend_with_query(S.Query(item_ids=["i1", "i2", "i9"], top_k=6))
+    assert [c.item_id for c in recs] == [c.item_id for c in want] and not {"i1", "i2", "i9"} & {c.item_id for c in recs}
+    with pytest.raises(S.NotFound):
+        users.get_id("nobody")

@@ -227,6 +227,19 @@ class RecommendService:
         found = iter(self.item_index.search_many(have))
         return [next(found) if q.embedding is not None else [] for q in queries]
 
+    def recommend_with_user_id(self, user_index: "UserIndexService", user_id: str,
+                                exclude_item_ids: list[str] | None = None, top_k: int = TOP_K) -> list[ItemCandidate]:
+        """service.py:264-289: the user's history and target items form the query sequence (and are excluded)."""
+        user = user_index.get_id(user_id)
+        item_ids: list[str] = []
+        item_texts: list[str] = []
+        for act in (user.history, user.target):
+            if act:
+                item_ids += act.item_id
+                item_texts += act.item_text
+        return self.recommend_with_query(Query(item_ids=item_ids, item_texts=item_texts,
+                                               exclude_item_ids=exclude_item_ids, top_k=top_k))
+
     def recommend_with_item_id(self, item_id: str, exclude_item_ids: list[str] | None = None,
                                top_k: int = TOP_K) -> list[ItemCandidate]:
         """service.py:247-262."""
@@ -235,3 +248,20 @@ class RecommendService:
                       input_embeds=item.embedding[None, :] if item.embedding is not None else None,
                       exclude_item_ids=exclude_item_ids, top_k=top_k)
         return self.recommend_with_query(query)
+
+
+class UserIndexService:
+    """``UserIndex`` of service.py:183-199: a key lookup over the users table (``user_id``, ``user_text``,
+    ``history`` / ``target`` activities).  The reference keeps the table in LanceDB; any mapping or iterable of
+    rows in that column layout serves (e.g. ``datasets.Dataset.to_list()`` of its users parquet)."""
+
+    def __init__(self, rows) -> None:
+        if isinstance(rows, dict):
+            rows = rows.values()
+        self._rows = {str(r["user_id"]): r for r in rows}
+
+    def get_id(self, user_id: str) -> UserQuery:
+        row = self._rows.get(str(user_id))
+        if row is None:
+            raise NotFound(f"user not found: {user_id = }")
+        return UserQuery.model_validate(row)
