@@ -258,7 +258,10 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: ONE JSON line
         # the per-step collectives run UNDER the next step's kernels: the persistent tensor-core kernel
         # leaves `reserve` SMs free for NCCL's CTAs (dist.reserve_sms) and NCCL is told to use that many
-        reserve = int(os.environ.get("XR_BENCH_RESERVE_SMS", "8"))
+        # Measured on 2 / 4 / 8 B200 (profiles/README.md): 8 SMs suffice where NCCL reduces in the switch (8 GPUs:
+        # NVLS) or with one peer (2 GPUs); the 4-GPU ring needs 16 CTAs to move 16 MB inside one step (0.388 ms
+        # per step with 8, 0.295 with 16, 0.336 with no reservation)
+        reserve = int(os.environ.get("XR_BENCH_RESERVE_SMS", "16" if world == 4 else "8"))
         if reserve > 0:
             os.environ.setdefault("NCCL_MAX_CTAS", str(reserve))
         dist.init_process_group("nccl", device_id=dev)
