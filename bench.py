@@ -260,7 +260,7 @@ def main():
         # leaves `reserve` SMs free for NCCL's CTAs (dist.reserve_sms) and NCCL is told to use that many
         # Measured on 2 / 4 / 8 B200 (profiles/README.md): 8 SMs suffice where NCCL reduces in the switch (8 GPUs:
         # NVLS) or with one peer (2 GPUs); the 4-GPU ring needs 16 CTAs to move 16 MB inside one step (0.388 ms
-        # per step with 8, 0.295 with 16, 0.336 with no reservation)
+        # per step with 8, 0.295 with 16, 0.336 with no reservation); at 8 GPUs 4 are too few (0.333 against 0.296)
         reserve = int(os.environ.get("XR_BENCH_RESERVE_SMS", "16" if world == 4 else "8"))
         if reserve > 0:
             os.environ.setdefault("NCCL_MAX_CTAS", str(reserve))
