@@ -757,9 +757,22 @@ enc_attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const __nv_bfloat16* base = qkv + (int64_t)b * seq_len * 3 * hid + h * enc::HD;
-  fill_tile(base, 3 * hid, seq_len, lp, sQ);
-  fill_tile(base + hid, 3 * hid, seq_len, lp, sK);
-  fill_tile(base + 2 * hid, 3 * hid, seq_len, lp, sV);
+  // one pass over the head's rows with all three loads of a row segment in flight (three separate fill loops
+  // left the prologue latency-bound: ncu showed the kernel stalled on global loads, not on its MMAs)
+#pragma unroll 2
+  for (int e = threadIdx.x; e < lp * 4; e += blockDim.x) {
+    const int j = e >> 2, c = e & 3;
+    int4 vq = make_int4(0, 0, 0, 0), vk = vq, vv = vq;
+    if (j < seq_len) {
+      const __nv_bfloat16* src = base + (int64_t)j * 3 * hid + 8 * c;
+      vq = ld_stream16(src);
+      vk = ld_stream16(src + hid);
+      vv = ld_stream16(src + 2 * hid);
+    }
+    *reinterpret_cast<int4*>(sQ + j * enc::RS + 8 * c) = vq;
+    *reinterpret_cast<int4*>(sK + j * enc::RS + 8 * c) = vk;
+    *reinterpret_cast<int4*>(sV + j * enc::RS + 8 * c) = vv;
+  }
   for (int j = threadIdx.x; j < lp; j += blockDim.x) s_mask[j] = j < seq_len ? keymask[(int64_t)b * seq_len + j] : 0;
   __syncthreads();
   const float scale = 0.17677669529663687f;   // 1 / sqrt(32)
@@ -864,20 +877,42 @@ enc_attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __
   __nv_bfloat16* dbase = dqkv + (int64_t)b * seq_len * 3 * hid + h * enc::HD;
   const __nv_bfloat16* dO = dctx + (int64_t)b * seq_len * hid + h * enc::HD;
   const __nv_bfloat16* O = ctx + (int64_t)b * seq_len * hid + h * enc::HD;
-  fill_tile(base, 3 * hid, seq_len, lp, sQ);
-  fill_tile(base + hid, 3 * hid, seq_len, lp, sK);
-  fill_tile(base + 2 * hid, 3 * hid, seq_len, lp, sV);
-  fill_tile(dO, hid, seq_len, lp, sdO);
+  // one pass over the head's rows with all five loads of a row segment in flight; delta_i = dO_i . O_i falls
+  // out of the same pass (four lanes hold a row: two shuffles).  Separate fill loops and a warp-per-row delta
+  // loop left the prologue latency-bound: ncu showed 4.1 long-scoreboard stalls per issued instruction.
+  // (lp * 4 is a multiple of 64: whole warps enter or skip an iteration, the shuffles are safe)
+#pragma unroll 2
+  for (int e = threadIdx.x; e < lp * 4; e += blockDim.x) {
+    const int j = e >> 2, c = e & 3;
+    int4 vq = make_int4(0, 0, 0, 0), vk = vq, vv = vq, vd = vq, vo = vq;
+    if (j < seq_len) {
+      const __nv_bfloat16* src = base + (int64_t)j * 3 * hid + 8 * c;
+      vq = ld_stream16(src);
+      vk = ld_stream16(src + hid);
+      vv = ld_stream16(src + 2 * hid);
+      vd = ld_stream16(dO + (int64_t)j * hid + 8 * c);
+      vo = ld_stream16(O + (int64_t)j * hid + 8 * c);
+    }
+    *reinterpret_cast<int4*>(sQ + j * enc::RS + 8 * c) = vq;
+    *reinterpret_cast<int4*>(sK + j * enc::RS + 8 * c) = vk;
+    *reinterpret_cast<int4*>(sV + j * enc::RS + 8 * c) = vv;
+    *reinterpret_cast<int4*>(sdO + j * enc::RS + 8 * c) = vd;
+    const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&vd);
+    const __nv_bfloat162* ho = reinterpret_cast<const __nv_bfloat162*>(&vo);
+    float part = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 a = __bfloat1622float2(hd[k]), o2 = __bfloat1622float2(ho[k]);
+      part = fmaf(a.x, o2.x, part);
+      part = fmaf(a.y, o2.y, part);
+    }
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    if (c == 0) s_delta[j] = part;
+  }
   for (int j = threadIdx.x; j < lp; j += blockDim.x) {
     s_mask[j] = j < seq_len ? keymask[(int64_t)b * seq_len + j] : 0;
     s_lse[j] = j < seq_len ? lse[((int64_t)b * n_heads + h) * seq_len + j] : CUDART_INF_F;
-  }
-  // delta_i = dO_i . O_i (warp per query, lane = dim)
-  for (int i = warp; i < lp; i += nw) {
-    float v = 0.f;
-    if (i < seq_len) v = __bfloat162float(dO[(int64_t)i * hid + lane]) * __bfloat162float(O[(int64_t)i * hid + lane]);
-    v = warp_sum(v);
-    if (lane == 0) s_delta[i] = v;
   }
   __syncthreads();
   const int n_tiles = lp >> 4;
