@@ -247,6 +247,7 @@ enc_fold_partials_kernel(const float* __restrict__ part, int n_part, int n_vec, 
   const int v = blockIdx.y, c = blockIdx.x * 32 + lane;
   float a = 0.f;
   if (c < width)
+#pragma unroll 8
     for (int p = warp; p < n_part; p += FOLD_WARPS) a += part[((size_t)p * n_vec + v) * width + c];
   s[warp][lane] = a;
   __syncthreads();
@@ -405,7 +406,8 @@ __device__ __forceinline__ float gelu_grad_f(float v) {
 // instruction-bound otherwise (39 M elements per launch) -- and the backward's exp(-x^2 / 2) IS that exponential.
 __device__ __forceinline__ void gelu_fast_parts(float v, float& cdf, float& e) {
   const float z = fabsf(v) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t;   // MUFU reciprocal (2^-22 relative error: far below the polynomial's 1.5e-7 and a bf16 ulp)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   e = __expf(-z * z);                                    // = exp(-v^2 / 2)
   const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f),
                               0.254829592f);
@@ -440,9 +442,19 @@ enc_gelu_fwd_kernel(const T* __restrict__ x, int64_t n, T* __restrict__ y, int v
   const int64_t nv = vec_ok ? n / VEC : 0;
   for (int64_t i = tid; i < nv; i += nth) {
     int4 raw = ld_stream16(x + i * VEC);
-    T* e = reinterpret_cast<T*>(&raw);
+    if (sizeof(T) == 2) {   // bf16: unpack / pack two elements per instruction
+      uint32_t* w = reinterpret_cast<uint32_t*>(&raw);
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) e[k] = from_f32<T>(gelu_of<T>(to_f32(e[k])));
+      for (int k = 0; k < 4; ++k) {
+        const float lo = __uint_as_float(w[k] << 16), hi = __uint_as_float(w[k] & 0xFFFF0000u);
+        const __nv_bfloat162 r = __floats2bfloat162_rn(gelu_of<T>(lo), gelu_of<T>(hi));
+        w[k] = *reinterpret_cast<const uint32_t*>(&r);
+      }
+    } else {
+      T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) e[k] = from_f32<T>(gelu_of<T>(to_f32(e[k])));
+    }
     *reinterpret_cast<int4*>(y + i * VEC) = raw;
   }
   for (int64_t i = nv * VEC + tid; i < n; i += nth) y[i] = from_f32<T>(gelu_of<T>(to_f32(x[i])));
@@ -455,10 +467,22 @@ enc_gelu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, int64_t n
   const int64_t nv = vec_ok ? n / VEC : 0;
   for (int64_t i = tid; i < nv; i += nth) {
     int4 rx = ld_stream16(x + i * VEC), rd = ld_stream16(dy + i * VEC);
-    const T* ex = reinterpret_cast<const T*>(&rx);
-    T* ed = reinterpret_cast<T*>(&rd);
+    if (sizeof(T) == 2) {   // bf16: unpack / pack two elements per instruction
+      const uint32_t* wx = reinterpret_cast<const uint32_t*>(&rx);
+      uint32_t* wd = reinterpret_cast<uint32_t*>(&rd);
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) ed[k] = from_f32<T>(to_f32(ed[k]) * gelu_grad_of<T>(to_f32(ex[k])));
+      for (int k = 0; k < 4; ++k) {
+        const float x0 = __uint_as_float(wx[k] << 16), x1 = __uint_as_float(wx[k] & 0xFFFF0000u);
+        const float d0 = __uint_as_float(wd[k] << 16), d1 = __uint_as_float(wd[k] & 0xFFFF0000u);
+        const __nv_bfloat162 r = __floats2bfloat162_rn(d0 * gelu_grad_of<T>(x0), d1 * gelu_grad_of<T>(x1));
+        wd[k] = *reinterpret_cast<const uint32_t*>(&r);
+      }
+    } else {
+      const T* ex = reinterpret_cast<const T*>(&rx);
+      T* ed = reinterpret_cast<T*>(&rd);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) ed[k] = from_f32<T>(to_f32(ed[k]) * gelu_grad_of<T>(to_f32(ex[k])));
+    }
     st_stream16(dx + i * VEC, rd);
   }
   for (int64_t i = nv * VEC + tid; i < n; i += nth) dx[i] = from_f32<T>(to_f32(dy[i]) * gelu_grad_of<T>(to_f32(x[i])));
@@ -467,7 +491,7 @@ enc_gelu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, int64_t n
 // column sums of a (rows, width) matrix (a linear layer's bias gradient): block = 8 warps x 32 lanes, a lane owns
 // VEC consecutive columns, warp w of row slice blockIdx.y takes rows y * 8 + w, + 8 * gridDim.y, ...; partial rows
 // part[y][width] folded by enc_fold_partials_kernel.  Fixed order everywhere: deterministic.
-constexpr int COLSUM_SLICES = 64;
+constexpr int COLSUM_SLICES = 192;   // row slices = grid.y (64 left the kernel latency-bound: 384 blocks, 33 % warps active)
 template <typename T>
 __global__ void __launch_bounds__(256)
 enc_colsum_kernel(const T* __restrict__ x, int64_t rows, int width, float* __restrict__ part) {
