@@ -873,16 +873,27 @@ fused_finalize_kernel(const float* __restrict__ part_o, const float* __restrict_
     const SkRange sr = sk_segments(rb, nt, rb_count, grid);
     // ---- phase A ----
     if (want_o) {
+      // a thread owns 6 of the 96 column quads of one row: all six loads of a segment are in flight together
+      // (one load at a time left this phase waiting on L2 latency: ncu, 15.7 long-scoreboard stalls per issue)
       const int r = threadIdx.x & (FR - 1);
-      for (int c4 = threadIdx.x / FR; c4 < D / 4; c4 += 256 / FR) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int c = sr.c_first; c <= sr.c_last; ++c) {   // fixed order: deterministic
-          const float4 v = *reinterpret_cast<const float4*>(
-              part_o + (size_t)(c + rb) * BM * D + ((size_t)c4 * BM + rl0 + r) * 4);
-          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      constexpr int NQ = (D / 4) / (256 / FR);   // 6
+      float4 acc[NQ];
+#pragma unroll
+      for (int k = 0; k < NQ; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = sr.c_first; c <= sr.c_last; ++c) {   // fixed order: deterministic
+        const float* seg = part_o + (size_t)(c + rb) * BM * D + (size_t)(rl0 + r) * 4;
+        float4 v[NQ];
+#pragma unroll
+        for (int k = 0; k < NQ; ++k)
+          v[k] = *reinterpret_cast<const float4*>(seg + (size_t)(threadIdx.x / FR + k * (256 / FR)) * BM * 4);
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) {
+          acc[k].x += v[k].x; acc[k].y += v[k].y; acc[k].z += v[k].z; acc[k].w += v[k].w;
         }
-        *reinterpret_cast<float4*>(&s_o[r][c4 * 4]) = acc;
       }
+#pragma unroll
+      for (int k = 0; k < NQ; ++k)
+        *reinterpret_cast<float4*>(&s_o[r][(threadIdx.x / FR + k * (256 / FR)) * 4]) = acc[k];
     }
     if (threadIdx.x < FR) {
       float cnt = 0.f, sum_a = 0.f, sum_w = 0.f;
