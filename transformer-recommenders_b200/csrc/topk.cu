@@ -653,7 +653,9 @@ filter_finalize_kernel(const FilterOut fo, const float* __restrict__ thresh, int
 
 // ---- k-th largest of every row (the thresholds of the scoring filter): block per row, 4-pass radix
 //      select on the order-preserving 32-bit keys; the row (tens of KB) is re-read from L2 per pass ------
-__global__ void __launch_bounds__(TK_THREADS)
+constexpr int KTH_THREADS = 1024;   // one block per row: with 256 threads the few hundred blocks of a search left
+                                    // the GPU at 21 % warps active and every pass walked 76 dependent loads
+__global__ void __launch_bounds__(KTH_THREADS)
 kth_largest_kernel(const float* __restrict__ x, int64_t n, int64_t ld, int kth, float* __restrict__ out) {
   __shared__ unsigned s_hist[256];
   __shared__ unsigned s_pick[2];
@@ -666,9 +668,9 @@ kth_largest_kernel(const float* __restrict__ x, int64_t n, int64_t ld, int kth, 
   uint32_t prefix = 0u, mask = 0u;
   unsigned want = (unsigned)kth;
   for (int shift = 24; shift >= 0; shift -= 8) {
-    s_hist[threadIdx.x] = 0u;
+    if (threadIdx.x < 256) s_hist[threadIdx.x] = 0u;
     __syncthreads();
-    for (int64_t i = threadIdx.x; i < n; i += TK_THREADS) {
+    for (int64_t i = threadIdx.x; i < n; i += KTH_THREADS) {
       const uint32_t key = float_key(__ldg(row + i));
       if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
     }
@@ -979,7 +981,7 @@ extern "C" int xr_kth_largest(const float* x, int64_t u, int64_t n, int64_t ld, 
                               void* stream) {
   XR_CHECK_ARG(x && out && u >= 0 && n >= 0 && ld >= n && kth >= 1, "xr_kth_largest: bad arguments");
   if (u == 0) return XR_OK;
-  kth_largest_kernel<<<(unsigned)u, TK_THREADS, 0, as_stream(stream)>>>(x, n, ld, (int)kth, out);
+  kth_largest_kernel<<<(unsigned)u, KTH_THREADS, 0, as_stream(stream)>>>(x, n, ld, (int)kth, out);
   XR_LAUNCH_CHECK("kth_largest");
   return XR_OK;
 }
